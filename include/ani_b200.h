@@ -1,0 +1,199 @@
+/*
+ * ani_b200.h -- C-ABI of the B200-native ANI energy+force hot path.
+ *
+ * Drop-in boundary.  Every entry point takes plain device
+ * pointers, sizes and an explicit cudaStream_t (passed as void*), never allocates,
+ * never synchronises the host, and returns 0 on success or a negative ANI_ERR_* code
+ * (ani_b200_error_string() explains it).  Device-side conditions that the reference
+ * reports as exceptions (neighbour overflow, periodic cell smaller than the cutoff)
+ * are raised through a device status word that the caller reads when convenient.
+ *
+ * What each entry point replaces in the reference (paths under /root/reference/torchani):
+ *   ani_b200_build_cells        neighbors.py:418-507,554-615 (_cell_list bucketing), utils.py:237-255
+ *                               (map_to_central), csrc/cell_list.cpp:266-350
+ *   ani_b200_species_layout     nn/_containers.py:412-415 (per-species nonzero/index_select)
+ *   ani_b200_aev_forward        neighbors.py:64-113,968-1002 + aev/_computer.py:274-350;
+ *                               csrc/cuaev.cpp:189-246 (cuaev::run / run_with_half_nbrlist),
+ *                               csrc/aev.cu:323-472,768-834 (K8/K9), :975-1039 (K4)
+ *   ani_b200_aev_backward       csrc/cuaev.cpp:134-163, csrc/aev.cu:474-766,837-967 (K10/K11)
+ *   ani_b200_half_neighbor_*    neighbors.py:366-415 (cell_list), :187-212 (all_pairs) -> Neighbors
+ *   ani_b200_mlp_forward_backward  nn/_containers.py:377-421,608-651, nn/_core.py:146-167,
+ *                               nn/_infer.py:61-216 (BmmEnsemble), csrc/mnp.cpp:63-236 (mnp::run)
+ *   ani_b200_reduce_energies    nn/_containers.py:418-421,633-636, sae.py:54-64
+ */
+#ifndef ANI_B200_H
+#define ANI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANI_B200_ABI_VERSION 1
+
+#define ANI_MAX_SPECIES 8
+#define ANI_MAX_SHFR 32
+#define ANI_MAX_SHFA 8
+#define ANI_MAX_SHFZ 8
+#define ANI_MAX_MEMBERS 16
+#define ANI_TILE_ROWS 128 /* rows of the species-grouped AEV matrix per MLP tile */
+
+/* error codes (return values) */
+#define ANI_OK 0
+#define ANI_ERR_BAD_ARG (-1)
+#define ANI_ERR_UNSUPPORTED (-2)
+#define ANI_ERR_CUDA (-3)
+
+/* bits of the device status word (int32, written by kernels, never cleared by them) */
+#define ANI_STATUS_NBR_OVERFLOW 1   /* an atom has more radial neighbours than nbr_cap   */
+#define ANI_STATUS_ANG_OVERFLOW 2   /* an atom has more angular neighbours than ANI_MAX_ANG */
+#define ANI_STATUS_CELL_TOO_SMALL 4 /* periodic cell thinner than the cutoff (neighbors.py:402-403) */
+#define ANI_STATUS_PAIR_OVERFLOW 8  /* half neighbour list exceeds the caller's capacity */
+
+#define ANI_MAX_ANG 96 /* angular neighbours (<= Rca) one central atom may have */
+
+/* AEV constants; mirrors the CuaevComputer constructor (csrc/cuaev.cpp:247-278).       */
+typedef struct ani_aev_params {
+  float rcr, rca;            /* radial / angular cutoffs                                  */
+  float eta_r, eta_a, zeta;  /* float32-rounded, as the reference's buffers hold them      */
+  int32_t n_shf_r, n_shf_a, n_shf_z;
+  int32_t num_species;
+  int32_t cutoff_kind;       /* 0 = cosine (cutoffs.py:70-81), 1 = smooth (cutoffs.py:84-101) */
+  float shf_r[ANI_MAX_SHFR];
+  float shf_a[ANI_MAX_SHFA];
+  float cos_z[ANI_MAX_SHFZ]; /* cos / sin of the angular sections ShfZ                     */
+  float sin_z[ANI_MAX_SHFZ];
+} ani_aev_params;
+
+/* Device-resident description of the bucket grid, written by ani_b200_build_cells.     */
+typedef struct ani_grid {
+  float cell[9];   /* rows are lattice vectors (identity-like bounding box without PBC)  */
+  float inv[9];    /* inverse: frac = (r - origin) @ inv                                  */
+  float origin[3];
+  int32_t dims[3]; /* buckets per lattice direction                                       */
+  int32_t pbc;     /* 1 = periodic in all three directions                                */
+  int32_t nbins;   /* real buckets; padding atoms live in bucket index nbins              */
+  int32_t mode;    /* 0 = one conformer on a grid, 1 = batch, bucket == conformer         */
+  int32_t n_per_conf;
+  int32_t n_real;  /* number of non-padding atoms (== bin_start[nbins])                  */
+} ani_grid;
+
+int ani_b200_abi_version(void);
+const char* ani_b200_error_string(int code);
+/* Last CUDA error string seen by this library on the calling thread (for ANI_ERR_CUDA). */
+const char* ani_b200_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------ */
+/* 1. Bucket the atoms: wrap into the cell (PBC), assign buckets, stable counting sort.   */
+/*    coords  [n_conf*n_per_conf*3] f32, species [n_conf*n_per_conf] i32 (-1 = padding)    */
+/*    cell    device f32[9] (rows = lattice vectors) or NULL; pbc 0/1 (all directions)      */
+/*    mode 0 requires n_conf == 1; mode 1 requires pbc == 0.                                */
+/*    Outputs (all device):                                                                 */
+/*      grid            ani_grid                                                            */
+/*      bin_start       i32[max_bins+2]  exclusive scan of bucket populations               */
+/*      sorted_orig     i32[n]           bucket-sorted position -> flat input index         */
+/*      spos            f32[n*4]         wrapped x,y,z + species (int bits) in sorted order  */
+/*      sbin            i32[n]           bucket of each sorted atom                         */
+/*      orig_to_sorted  i32[n]           inverse of sorted_orig                             */
+/*    Scratch: scratch_i32[3*n + max_bins + 2].                                             */
+int ani_b200_build_cells(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
+                         const float* cell, int pbc, int mode, float cutoff, int max_bins,
+                         ani_grid* grid, int32_t* bin_start, int32_t* sorted_orig,
+                         int32_t* orig_to_sorted, float* spos, int32_t* sbin, int32_t* scratch_i32,
+                         int32_t* status, void* stream);
+
+/* 2. Species-grouped row layout for the MLP: atoms lo..hi-1 (bucket-sorted positions,     */
+/*    clipped to the real atoms) get rows grouped by species, every species block padded    */
+/*    to a multiple of ANI_TILE_ROWS.                                                       */
+/*      row_of      i32[n]        row of sorted atom i (undefined outside lo..hi-1)         */
+/*      row_atom    i32[rows_cap] sorted atom of a row, -1 for padding rows                 */
+/*      tile_species i32[rows_cap/ANI_TILE_ROWS]  species of each row tile, -1 = unused      */
+/*      layout_info i32[4]: {n_tiles, n_rows, n_owned_atoms, 0}                             */
+/*    Scratch: scratch_i32[(ceil(n/256)+2) * ANI_MAX_SPECIES + 64].                         */
+int ani_b200_species_layout(const float* spos, const ani_grid* grid, int n, int lo, int hi,
+                            int num_species, int rows_cap, int32_t* row_of, int32_t* row_atom,
+                            int32_t* tile_species, int32_t* layout_info, int32_t* scratch_i32,
+                            void* stream);
+
+/* 3. Fused neighbour search + AEV forward for sorted atoms lo..hi-1.                      */
+/*      row_of     row of the output matrix for each sorted atom (species-grouped rows for   */
+/*                 the fused engine, flat input index for the AEVComputer API)               */
+/*      aev        f32[rows][ldx]; columns 0..out_dim-1 of the atom's row are overwritten    */
+/*      nbr_cnt    i32[n]; nbr_list i32[n*nbr_cap]: neighbours within Rcr of every processed  */
+/*                 atom as (sorted index | image code << 26); kept for the backward pass      */
+int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
+                         const int32_t* bin_start, const float* spos, const int32_t* sbin, int n,
+                         int lo, int hi, const int32_t* row_of, float* aev, int ldx,
+                         int32_t* nbr_cnt, int32_t* nbr_list, int nbr_cap, int32_t* status,
+                         void* stream);
+
+/* 4. AEV backward: grad_aev (same row layout as the forward output) -> dE/dcoords,         */
+/*    accumulated (+=, float atomics) into grad_coords f32[n*3] in flat INPUT order.         */
+int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                          const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
+                          const float* grad_aev, int ldx, const int32_t* nbr_cnt,
+                          const int32_t* nbr_list, int nbr_cap, float* grad_coords,
+                          int32_t* status, void* stream);
+
+/* 5. Reference-format half neighbour list (neighbors.py:13-18) from the bucket grid.       */
+/*    Two calls: count (fills pair_start i32[n+1], exclusive scan, total in pair_start[n]),  */
+/*    then fill with capacity `cap` pairs.  indices are flat INPUT indices, idx0 < idx1       */
+/*    except for self-image pairs; diff = x[idx0] - x[idx1] + shift (neighbors.py:107-111).   */
+int ani_b200_half_neighbor_count(const ani_grid* grid, const int32_t* bin_start, const float* spos,
+                                 const int32_t* sbin, const int32_t* sorted_orig, int n,
+                                 float cutoff, int32_t* pair_start, void* stream);
+int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, const float* spos,
+                                const int32_t* sbin, const int32_t* sorted_orig, int n, float cutoff,
+                                const int32_t* pair_start, int64_t cap, int64_t* idx0, int64_t* idx1,
+                                float* distances, float* diff_vectors, int32_t* status, void* stream);
+
+/* 6. Ensemble MLP forward + backward-to-input on the species-grouped AEV matrix.           */
+/*    Layer widths: in -> h1 -> h2 -> h3 -> 1, CELU(alpha) after the three hidden layers.    */
+typedef struct ani_mlp_species {
+  int32_t h1, h2, h3, pad_;
+  const float* w1;  /* [ldx][M*h1]   w1[k][m*h1+o] = W1_m[o][k], rows >= in_dim are zero     */
+  const float* b1;  /* [M*h1]                                                                  */
+  const float* w2;  /* [M][h1][h2]   transposed Linear weights (K-major)                       */
+  const float* b2;  /* [M*h2]                                                                  */
+  const float* w3;  /* [M][h2][h3]                                                             */
+  const float* b3;  /* [M*h3]                                                                  */
+  const float* w4;  /* [M][h3]                                                                 */
+  const float* b4;  /* [M]                                                                     */
+  const float* w3n; /* [M][h3][h2]   natural Linear layout (out-major) for the backward pass   */
+  const float* w2n; /* [M][h2][h1]                                                             */
+  const float* w1n; /* [M*h1][ldx]                                                             */
+} ani_mlp_species;
+
+typedef struct ani_mlp_model {
+  int32_t num_species, num_members, in_dim, ldx;
+  int32_t h1_max, h2_max, h3_max, pad_;
+  float celu_alpha;
+  float member_scale[ANI_MAX_MEMBERS]; /* d(output)/d(member energy): 1/M_active or 0       */
+  ani_mlp_species sp[ANI_MAX_SPECIES];
+} ani_mlp_model;
+
+/*    x            f32[rows_cap][ldx]   in: AEVs; out: dE/dAEV (in place)                     */
+/*    act1/2/3     f32[rows_cap][M*h{1,2,3}_max]  workspaces (activations, then gradients)    */
+/*    e_member     f32[M][rows_cap]     per-member atomic energies                            */
+int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
+                                  const int32_t* tile_species, const int32_t* row_atom,
+                                  float* act1, float* act2, float* act3, float* e_member,
+                                  int want_backward, void* stream);
+
+/* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
+/*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */
+/*      member_atomic_out f32[M][n] or NULL                                                    */
+/*      energies_out f64[n_conf]  NN energy + self energies (sae f64[num_species] or NULL)     */
+/*    Only atoms whose sorted position is in lo..hi-1 contribute (others give 0), so the     */
+/*    per-rank results of a sharded run add up to the full answer.                            */
+int ani_b200_reduce_energies(const ani_mlp_model* model, const float* e_member, int rows_cap,
+                             const int32_t* row_of, const int32_t* orig_to_sorted,
+                             const int32_t* species, int n, int lo, int hi, int n_conf,
+                             int n_per_conf, const double* sae, float* atomic_out,
+                             float* member_atomic_out, double* energies_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANI_B200_H */

@@ -1,0 +1,124 @@
+"""ctypes binding of ``libani_b200.so`` (the C-ABI declared in ``include/ani_b200.h``).
+
+There is exactly one compute path: the CUDA library.  If it is missing or does not load the
+import fails loudly -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libani_b200.so")
+
+ANI_MAX_SPECIES = 8
+ANI_MAX_SHFR = 32
+ANI_MAX_SHFA = 8
+ANI_MAX_SHFZ = 8
+ANI_MAX_MEMBERS = 16
+ANI_TILE_ROWS = 128
+ANI_MAX_ANG = 96
+
+STATUS_NBR_OVERFLOW = 1
+STATUS_ANG_OVERFLOW = 2
+STATUS_CELL_TOO_SMALL = 4
+STATUS_PAIR_OVERFLOW = 8
+
+
+class AEVParams(C.Structure):
+    _fields_ = [
+        ("rcr", C.c_float), ("rca", C.c_float),
+        ("eta_r", C.c_float), ("eta_a", C.c_float), ("zeta", C.c_float),
+        ("n_shf_r", C.c_int32), ("n_shf_a", C.c_int32), ("n_shf_z", C.c_int32),
+        ("num_species", C.c_int32), ("cutoff_kind", C.c_int32),
+        ("shf_r", C.c_float * ANI_MAX_SHFR), ("shf_a", C.c_float * ANI_MAX_SHFA),
+        ("cos_z", C.c_float * ANI_MAX_SHFZ), ("sin_z", C.c_float * ANI_MAX_SHFZ),
+    ]
+
+
+class Grid(C.Structure):
+    _fields_ = [
+        ("cell", C.c_float * 9), ("inv", C.c_float * 9), ("origin", C.c_float * 3),
+        ("dims", C.c_int32 * 3), ("pbc", C.c_int32), ("nbins", C.c_int32), ("mode", C.c_int32),
+        ("n_per_conf", C.c_int32), ("n_real", C.c_int32),
+    ]
+
+
+class MLPSpecies(C.Structure):
+    _fields_ = [("h1", C.c_int32), ("h2", C.c_int32), ("h3", C.c_int32), ("pad_", C.c_int32)] + [
+        (k, C.c_void_p) for k in ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "w3n", "w2n", "w1n")
+    ]
+
+
+class MLPModel(C.Structure):
+    _fields_ = [
+        ("num_species", C.c_int32), ("num_members", C.c_int32), ("in_dim", C.c_int32), ("ldx", C.c_int32),
+        ("h1_max", C.c_int32), ("h2_max", C.c_int32), ("h3_max", C.c_int32), ("pad_", C.c_int32),
+        ("celu_alpha", C.c_float), ("member_scale", C.c_float * ANI_MAX_MEMBERS),
+        ("sp", MLPSpecies * ANI_MAX_SPECIES),
+    ]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_F = C.c_float
+
+_PROTOTYPES = {
+    "ani_b200_abi_version": (C.c_int, []),
+    "ani_b200_error_string": (C.c_char_p, [_I]),
+    "ani_b200_last_cuda_error": (C.c_char_p, []),
+    "ani_b200_build_cells": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ani_b200_species_layout": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
+    "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
+    "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
+    "ani_b200_half_neighbor_fill": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "ani_b200_reduce_energies": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+
+class ANIB200Error(RuntimeError):
+    pass
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m torchani_b200.build` "
+            "(nvcc, sm_100a).  torchani_b200 has no CPU / PyTorch fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ani_b200_abi_version() != 1:
+        raise ImportError("libani_b200.so ABI version mismatch")
+    return lib
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = _load()
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        l = lib()
+        msg = l.ani_b200_error_string(rc).decode()
+        if rc == -3:
+            msg += " -- " + l.ani_b200_last_cuda_error().decode()
+        raise ANIB200Error(f"{what}: {msg}" if what else msg)
+
+
+def ptr(t) -> int:
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

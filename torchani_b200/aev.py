@@ -1,0 +1,253 @@
+"""``AEVComputer`` with the interface of ``torchani.AEVComputer`` (aev/_computer.py:42-272).
+
+``forward(elem_idxs, coords, cell, pbc) -> (C, A, out_dim)`` runs the fused B200 kernel
+(neighbour search + radial + angular in one pass, ``ani_b200_aev_forward``) and carries an
+autograd edge to ``coords`` whose backward is ``ani_b200_aev_backward``.  The only compute
+strategy is ``"b200"``: the reference's ``pyaev`` / ``cuaev`` strings are rejected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import typing as tp
+import warnings
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, ptr
+from .engine import AEVConstants, _linspace
+from .neighbors import BucketGrid, Neighbors, NeighborlistArg, _parse_neighborlist, _validate_inputs
+
+
+class SpeciesAEV(tp.NamedTuple):
+    species: Tensor
+    aevs: Tensor
+
+
+class _Term(torch.nn.Module):
+    def __init__(self, cutoff: float, cutoff_fn: str = "cosine") -> None:
+        super().__init__()
+        if cutoff_fn not in ("cosine", "smooth"):
+            raise ValueError(f"Unsupported cutoff fn for the B200 kernels: {cutoff_fn}")
+        self.cutoff = float(cutoff)
+        self.cutoff_fn = cutoff_fn
+        self.num_feats = 0
+
+
+class ANIRadial(_Term):
+    """Constants of the radial sub-AEV (aev/_terms.py:118-241).  Holds parameters only; the
+    terms are evaluated inside the fused CUDA kernel."""
+
+    def __init__(self, eta: float, shifts: tp.Sequence[float], cutoff: float, cutoff_fn: str = "cosine"):
+        super().__init__(cutoff, cutoff_fn)
+        self.register_buffer("eta", torch.tensor([eta], dtype=torch.float))
+        self.register_buffer("shifts", torch.tensor(shifts, dtype=torch.float))
+        self.num_feats = len(shifts)
+
+    @classmethod
+    def cover_linearly(cls, start: float = 0.9, cutoff: float = 5.2, eta: float = 19.7,
+                       num_shifts: int = 16, cutoff_fn: str = "cosine"):
+        return cls(eta, _linspace(start, cutoff, num_shifts), cutoff, cutoff_fn)
+
+    @classmethod
+    def like_1x(cls, cutoff_fn: str = "cosine"):
+        return cls.cover_linearly(0.9, 5.2, 16.0, 16, cutoff_fn)
+
+    @classmethod
+    def like_2x(cls, cutoff_fn: str = "cosine"):
+        return cls.cover_linearly(0.8, 5.1, 19.7, 16, cutoff_fn)
+
+
+class ANIAngular(_Term):
+    """Constants of the angular sub-AEV (aev/_terms.py:244-408)."""
+
+    def __init__(self, eta: float, zeta: float, shifts: tp.Sequence[float], sections: tp.Sequence[float],
+                 cutoff: float, cutoff_fn: str = "cosine"):
+        super().__init__(cutoff, cutoff_fn)
+        self.register_buffer("eta", torch.tensor([eta], dtype=torch.float))
+        self.register_buffer("zeta", torch.tensor([zeta], dtype=torch.float))
+        self.register_buffer("shifts", torch.tensor(shifts, dtype=torch.float))
+        self.register_buffer("sections", torch.tensor(sections, dtype=torch.float))
+        self.num_feats = len(shifts) * len(sections)
+
+    @classmethod
+    def cover_linearly(cls, start: float = 0.9, cutoff: float = 3.5, eta: float = 12.5, zeta: float = 14.1,
+                       num_shifts: int = 8, num_sections: int = 4, cutoff_fn: str = "cosine"):
+        angle_start = math.pi / num_sections / 2
+        return cls(eta, zeta, _linspace(start, cutoff, num_shifts),
+                   _linspace(angle_start, math.pi + angle_start, num_sections), cutoff, cutoff_fn)
+
+    @classmethod
+    def like_1x(cls, cutoff_fn: str = "cosine"):
+        return cls.cover_linearly(0.9, 3.5, 8.0, 32.0, 4, 8, cutoff_fn)
+
+    @classmethod
+    def like_2x(cls, cutoff_fn: str = "cosine"):
+        return cls.cover_linearly(0.8, 3.5, 12.5, 14.1, 8, 4, cutoff_fn)
+
+
+class _AEVFunction(torch.autograd.Function):
+    """coords -> AEVs through the fused kernel; backward = the force kernel."""
+
+    @staticmethod
+    def forward(ctx, coords: Tensor, species: Tensor, cell: tp.Optional[Tensor], pbc: bool,
+                computer: "AEVComputer") -> Tensor:
+        consts = computer.constants
+        g = BucketGrid(species, coords, cell, pbc, consts.rcr)
+        n = g.n
+        dev = coords.device
+        out = torch.zeros(n, consts.out_dim, dtype=torch.float32, device=dev)
+        cap = computer.nbr_cap
+        nbr_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        nbr_list = torch.zeros(n * cap, dtype=torch.int32, device=dev)
+        params = computer._params()
+        # rows of the output are the flat input indices: row_of == sorted_orig
+        check(_lib.lib().ani_b200_aev_forward(C.byref(params), ptr(g.grid), ptr(g.bin_start), ptr(g.spos),
+                                              ptr(g.sbin), n, 0, n, ptr(g.sorted_orig), ptr(out),
+                                              consts.out_dim, ptr(nbr_cnt), ptr(nbr_list), cap, ptr(g.status),
+                                              g.stream), "aev_forward")
+        ctx.g, ctx.nbr_cnt, ctx.nbr_list, ctx.computer = g, nbr_cnt, nbr_list, computer
+        computer._last_grid = g
+        return out.view(species.shape[0], species.shape[1], consts.out_dim)
+
+    @staticmethod
+    def backward(ctx, grad_aev: Tensor):
+        g, computer = ctx.g, ctx.computer
+        consts = computer.constants
+        grad_aev = grad_aev.reshape(g.n, consts.out_dim).to(torch.float32).contiguous()
+        grad = torch.zeros(g.n, 3, dtype=torch.float32, device=grad_aev.device)
+        params = computer._params()
+        st = torch.cuda.current_stream(grad_aev.device).cuda_stream
+        check(_lib.lib().ani_b200_aev_backward(C.byref(params), ptr(g.grid), ptr(g.spos), ptr(g.sorted_orig),
+                                               g.n, 0, g.n, ptr(g.sorted_orig), ptr(grad_aev), consts.out_dim,
+                                               ptr(ctx.nbr_cnt), ptr(ctx.nbr_list), computer.nbr_cap, ptr(grad),
+                                               ptr(g.status), st), "aev_backward")
+        return grad.view(g.n_conf, g.n_per_conf, 3), None, None, None, None
+
+
+class AEVComputer(torch.nn.Module):
+    r"""Computes atomic environment vectors on a B200 (interface of aev/_computer.py:42-272).
+
+    Args:
+        radial, angular: ``ANIRadial`` / ``ANIAngular`` (or ``"ani1x"`` / ``"ani2x"``)
+        num_species: number of supported elements
+        strategy: only ``"b200"`` (``"auto"`` is accepted as an alias)
+        neighborlist: kept for interface compatibility; the fused kernel searches the bucket
+            grid itself, the module is what ``model.neighborlist`` exposes to callers.
+    """
+
+    def __init__(self, radial: tp.Union[str, ANIRadial], angular: tp.Union[str, ANIAngular], num_species: int,
+                 strategy: str = "b200", cutoff_fn: tp.Optional[str] = None,
+                 neighborlist: NeighborlistArg = "cell_list", nbr_cap: int = 128):
+        super().__init__()
+        if isinstance(radial, str):
+            radial = {"ani1x": ANIRadial.like_1x, "ani1ccx": ANIRadial.like_1x, "ani2x": ANIRadial.like_2x}[radial]()
+        if isinstance(angular, str):
+            angular = {"ani1x": ANIAngular.like_1x, "ani1ccx": ANIAngular.like_1x,
+                       "ani2x": ANIAngular.like_2x}[angular]()
+        if type(radial) is not ANIRadial or type(angular) is not ANIAngular:
+            raise ValueError("the B200 kernels implement ANIRadial / ANIAngular terms only")
+        if radial.cutoff_fn != angular.cutoff_fn:
+            raise ValueError("Cutoff fn must be the same for angular and radial terms")
+        if angular.cutoff > radial.cutoff:
+            raise ValueError(f"Angular cutoff {angular.cutoff} should be smaller than radial cutoff {radial.cutoff}")
+        self.radial, self.angular = radial, angular
+        self.num_species = num_species
+        self.num_species_pairs = num_species * (num_species + 1) // 2
+        self.radial_len = radial.num_feats * num_species
+        self.angular_len = angular.num_feats * self.num_species_pairs
+        self.out_dim = self.radial_len + self.angular_len
+        self.register_buffer("triu_index", self._calculate_triu_index(num_species))
+        self.neighborlist = _parse_neighborlist(neighborlist)
+        self.nbr_cap = nbr_cap
+        self._strategy = ""
+        self.set_strategy(strategy)
+        self._struct = None
+        self._last_grid: tp.Optional[BucketGrid] = None
+        self.constants.to_struct()  # validates the configuration early
+
+    # -- strategy strings (aev/_computer.py:120-149) ---------------------------------------
+    @property
+    def strategy(self) -> str:
+        return self._strategy
+
+    def set_strategy(self, strat: str) -> None:
+        if strat in ("b200", "auto"):
+            self._strategy = "b200"
+        elif strat in ("pyaev", "cuaev", "cuaev-fused", "cuaev-interface"):
+            raise ValueError(f"{strat} strategy is not available in torchani_b200 (only 'b200')")
+        else:
+            raise ValueError("Unknown compute strategy")
+
+    @staticmethod
+    def _calculate_triu_index(num_species: int) -> Tensor:
+        # aev/_computer.py:184-191
+        s1, s2 = torch.triu_indices(num_species, num_species).unbind(0)
+        ret = torch.zeros(num_species, num_species, dtype=torch.long)
+        ret[s1, s2] = torch.arange(s1.shape[0])
+        ret[s2, s1] = torch.arange(s1.shape[0])
+        return ret
+
+    @property
+    def constants(self) -> AEVConstants:
+        r, a = self.radial, self.angular
+        return AEVConstants(self.num_species, r.cutoff, a.cutoff, float(r.eta.item()),
+                            tuple(float(v) for v in r.shifts.tolist()), float(a.eta.item()),
+                            float(a.zeta.item()), tuple(float(v) for v in a.shifts.tolist()),
+                            tuple(float(v) for v in a.sections.tolist()), r.cutoff_fn)
+
+    def _params(self):
+        if self._struct is None:
+            self._struct = self.constants.to_struct()
+        return self._struct
+
+    def forward(self, elem_idxs: Tensor, coords: tp.Optional[Tensor] = None, cell: tp.Optional[Tensor] = None,
+                pbc: tp.Optional[Tensor] = None) -> Tensor:
+        if isinstance(elem_idxs, tuple):  # legacy call form, aev/_computer.py:211-222
+            warnings.warn("`aev_computer((species, coords), cell, pbc)` is the TorchANI 1 signature; "
+                          "use `aev_computer(species, coords, cell, pbc)`")
+            _idx, _coords = elem_idxs
+            return SpeciesAEV(_idx, self(_idx, _coords, coords, cell))
+        assert coords is not None
+        assert elem_idxs.dim() == 2
+        assert coords.shape == (elem_idxs.shape[0], elem_idxs.shape[1], 3)
+        _validate_inputs(self.radial.cutoff, elem_idxs, coords, cell, pbc)
+        aev = _AEVFunction.apply(coords, elem_idxs, cell, pbc is not None, self)
+        if self._last_grid is not None:
+            self._last_grid.raise_on_status()
+        return aev
+
+    def compute_from_neighbors(self, elem_idxs: Tensor, coords: Tensor, neighbors: Neighbors) -> Tensor:
+        raise NotImplementedError(
+            "AEVs from an externally filtered pair list are not implemented on the B200 path yet; "
+            "call forward(elem_idxs, coords, cell, pbc) (fused neighbour search) instead"
+        )
+
+    # -- constructors (aev/_computer.py:498-666) -------------------------------------------
+    @classmethod
+    def like_1x(cls, num_species: int = 4, strategy: str = "b200", cutoff_fn: str = "cosine",
+                neighborlist: NeighborlistArg = "cell_list", **kw):
+        return cls(ANIRadial.like_1x(cutoff_fn), ANIAngular.like_1x(cutoff_fn), num_species, strategy,
+                   neighborlist=neighborlist, **kw)
+
+    @classmethod
+    def like_2x(cls, num_species: int = 7, strategy: str = "b200", cutoff_fn: str = "cosine",
+                neighborlist: NeighborlistArg = "cell_list", **kw):
+        return cls(ANIRadial.like_2x(cutoff_fn), ANIAngular.like_2x(cutoff_fn), num_species, strategy,
+                   neighborlist=neighborlist, **kw)
+
+    @classmethod
+    def from_constants(cls, radial_cutoff: float, angular_cutoff: float, radial_eta: float,
+                       radial_shifts: tp.Sequence[float], angular_eta: float, angular_zeta: float,
+                       angular_shifts: tp.Sequence[float], sections: tp.Sequence[float], num_species: int,
+                       strategy: str = "b200", cutoff_fn: str = "cosine",
+                       neighborlist: NeighborlistArg = "cell_list"):
+        return cls(ANIRadial(radial_eta, radial_shifts, radial_cutoff, cutoff_fn),
+                   ANIAngular(angular_eta, angular_zeta, angular_shifts, sections, angular_cutoff, cutoff_fn),
+                   num_species, strategy, neighborlist=neighborlist)
+
+    def extra_repr(self) -> str:
+        return (f"out_dim={self.out_dim}, radial_len={self.radial_len}, angular_len={self.angular_len}, "
+                f"num_species={self.num_species}, strategy={self._strategy}")

@@ -1,0 +1,762 @@
+// Fused neighbour search + AEV forward, and AEV backward (forces), one warp per central atom.
+//
+// Forward (replaces neighbors.py:64-113,968-1002 + aev/_computer.py:274-350; the reference's
+// GPU path is csrc/aev.cu K1-K9): the warp walks the 27 buckets around its atom, compacts the
+// neighbours within Rcr into shared memory with ballots, accumulates the radial block with a
+// (shift x neighbour-parity) lane layout, counting-sorts the neighbours within Rca by species
+// and then, for each species pair, every lane evaluates whole triples (32 angular features in
+// registers) followed by one warp transpose-reduce.  No atomics anywhere in the forward pass.
+//
+// Backward (csrc/aev.cu K10/K11): recomputes the geometry from the stored neighbour words and
+// evaluates dE/dr_j for every ORDERED pair (j, k) so that each neighbour's gradient is owned by
+// a group of lanes (register accumulation, shuffle reduce, plain shared-memory add); only the
+// final per-neighbour vectors go to global memory (fire-and-forget float reductions).
+#include "common.cuh"
+
+namespace ani {
+
+constexpr int AEV_WARPS = 4;  // warps (= central atoms) per CTA
+
+struct NeighbourRange {
+  int lo, hi, code;
+};
+
+// bucket range + image code for offset (ox, oy, oz) around bucket (ix, iy, iz); false if it
+// does not exist (non-periodic boundary)
+__device__ __forceinline__ bool neighbour_bucket(const ani_grid& g, const int32_t* __restrict__ bin_start,
+                                                 int ix, int iy, int iz, int ox, int oy, int oz,
+                                                 NeighbourRange& r) {
+  int j[3] = {ix + ox, iy + oy, iz + oz};
+  int w[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    w[d] = 0;
+    if (j[d] < 0) {
+      w[d] = -1;
+      j[d] += g.dims[d];
+    } else if (j[d] >= g.dims[d]) {
+      w[d] = 1;
+      j[d] -= g.dims[d];
+    }
+  }
+  if (!g.pbc && (w[0] | w[1] | w[2])) return false;
+  int b = (j[0] * g.dims[1] + j[1]) * g.dims[2] + j[2];
+  r.lo = bin_start[b];
+  r.hi = bin_start[b + 1];
+  r.code = (w[0] + 1) * 9 + (w[1] + 1) * 3 + (w[2] + 1);
+  return true;
+}
+
+// per-warp shared memory carve-up (byte offsets), shared by forward and backward
+struct WarpSmem {
+  float4* nd;            // [cap] dx, dy, dz, R   (neighbour - centre)
+  float* nfc;            // [cap] forward: fc(R; Rcr).  backward: unused
+  int32_t* nj;           // [cap] neighbour word
+  float* fgrad;          // [cap*3] backward only
+  unsigned char* nsp;    // [cap] species
+  unsigned char* aidx;   // [ANI_MAX_ANG] angular neighbours (index into nd), species-sorted
+  float* afc;            // [ANI_MAX_ANG] fc(R; Rca)
+  float* afcd;           // [ANI_MAX_ANG] d fc / dR (backward)
+  int32_t* seg;          // [ANI_MAX_SPECIES + 1] species segments of aidx
+  float* rad;            // forward: [2*RL] accumulators; backward: g_rad [RL] + g_ang [32*gstride]
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(int cap, int rad_floats, bool backward) {
+  size_t b = (size_t)cap * 16 + (size_t)cap * 4 + (size_t)cap * 4;
+  if (backward) b += (size_t)cap * 12;
+  b += (size_t)cap;                          // nsp
+  b += ANI_MAX_ANG;                          // aidx
+  b = (b + 15) / 16 * 16;
+  b += (size_t)ANI_MAX_ANG * 4 * 2;          // afc, afcd
+  b += 16 * 4;                               // seg (padded)
+  b += (size_t)rad_floats * 4;
+  return (b + 15) / 16 * 16;
+}
+
+__device__ __forceinline__ WarpSmem carve(unsigned char* base, int cap, bool backward) {
+  WarpSmem s;
+  unsigned char* p = base;
+  s.nd = reinterpret_cast<float4*>(p);
+  p += (size_t)cap * 16;
+  s.nfc = reinterpret_cast<float*>(p);
+  p += (size_t)cap * 4;
+  s.nj = reinterpret_cast<int32_t*>(p);
+  p += (size_t)cap * 4;
+  s.fgrad = reinterpret_cast<float*>(p);
+  if (backward) p += (size_t)cap * 12;
+  s.nsp = p;
+  p += cap;
+  s.aidx = p;
+  p += ANI_MAX_ANG;
+  p = base + ((size_t)(p - base) + 15) / 16 * 16;
+  s.afc = reinterpret_cast<float*>(p);
+  p += ANI_MAX_ANG * 4;
+  s.afcd = reinterpret_cast<float*>(p);
+  p += ANI_MAX_ANG * 4;
+  s.seg = reinterpret_cast<int32_t*>(p);
+  p += 16 * 4;
+  s.rad = reinterpret_cast<float*>(p);
+  return s;
+}
+
+// Counting sort (by species) of the neighbours within Rca.  Fills aidx/afc(/afcd)/seg, returns
+// the number of angular neighbours (clamped to ANI_MAX_ANG).
+template <bool WITH_GRAD>
+__device__ __forceinline__ int build_angular_list(const ani_aev_params& P, const WarpSmem& s, int cnt, int lane,
+                                                  int32_t* status) {
+  const int S = P.num_species;
+  int seg_cnt[ANI_MAX_SPECIES];
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) seg_cnt[k] = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    int n = base + lane;
+    int sp = -1;
+    if (n < cnt && s.nd[n].w <= P.rca) sp = s.nsp[n];
+#pragma unroll
+    for (int k = 0; k < ANI_MAX_SPECIES; ++k) {
+      unsigned m = __ballot_sync(ANI_FULL_MASK, sp == k);
+      seg_cnt[k] += __popc(m);
+    }
+  }
+  int seg_start[ANI_MAX_SPECIES + 1];
+  seg_start[0] = 0;
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) seg_start[k + 1] = seg_start[k] + seg_cnt[k];
+  int total = seg_start[ANI_MAX_SPECIES];
+  if (total > ANI_MAX_ANG) {
+    if (lane == 0) atomicOr(status, ANI_STATUS_ANG_OVERFLOW);
+    total = ANI_MAX_ANG;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k <= ANI_MAX_SPECIES; ++k)
+      if (k <= S) s.seg[k] = min(seg_start[k], ANI_MAX_ANG);
+  }
+  int run[ANI_MAX_SPECIES];
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) run[k] = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < cnt; base += 32) {
+    int n = base + lane;
+    int sp = -1;
+    float R = 0.f;
+    if (n < cnt) {
+      R = s.nd[n].w;
+      if (R <= P.rca) sp = s.nsp[n];
+    }
+    int pos = -1;
+#pragma unroll
+    for (int k = 0; k < ANI_MAX_SPECIES; ++k) {
+      unsigned m = __ballot_sync(ANI_FULL_MASK, sp == k);
+      if (sp == k) pos = seg_start[k] + run[k] + __popc(m & lt);
+      run[k] += __popc(m);
+    }
+    if (pos >= 0 && pos < ANI_MAX_ANG) {
+      s.aidx[pos] = (unsigned char)n;
+      if (WITH_GRAD) {
+        float f, df;
+        cutoff_value_grad(R, P.rca, P.cutoff_kind, f, df);
+        s.afc[pos] = f;
+        s.afcd[pos] = df;
+      } else {
+        s.afc[pos] = cutoff_value(R, P.rca, P.cutoff_kind);
+      }
+    }
+  }
+  __syncwarp();
+  return total;
+}
+
+// q-th unordered pair (a < b) of a triangle
+__device__ __forceinline__ void triangle_decode(int q, int& a, int& b) {
+  b = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)q)) * 0.5f);
+  while (b * (b - 1) / 2 > q) --b;
+  while ((b + 1) * b / 2 <= q) ++b;
+  a = q - b * (b - 1) / 2;
+}
+
+// sum acc[f] over the 32 lanes; lane l returns the total of feature l (31 shuffles)
+__device__ __forceinline__ float transpose_reduce32(float (&acc)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float send = up ? acc[i] : acc[i + half];
+      float keep = up ? acc[i + half] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(ANI_FULL_MASK, send, half);
+    }
+  }
+  return acc[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+template <int NA, int NZ>
+__global__ void __launch_bounds__(AEV_WARPS * 32)
+    k_aev_forward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
+                  const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
+                  const int32_t* __restrict__ sbin, int lo, int hi, const int32_t* __restrict__ row_of,
+                  float* __restrict__ aev, int ldx, int32_t* __restrict__ nbr_cnt,
+                  int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes) {
+  static_assert(NA * NZ == 32, "one lane per angular feature");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ani_grid g = *grid;
+  hi = min(hi, g.n_real);
+  const int i = lo + blockIdx.x * AEV_WARPS + warp;
+  if (i >= hi) return;
+  const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, false);
+  const int S = P.num_species;
+  const int nR = P.n_shf_r;
+  const int RL = S * nR;
+
+  // ---- 1. neighbours within Rcr -> shared memory
+  const float4 pi = spos[i];
+  const float rcr2 = P.rcr * P.rcr;
+  const unsigned lt = (1u << lane) - 1u;
+  int cnt = 0;
+  {
+    const int b = sbin[i];
+    int ix = 0, iy = 0, iz = 0, span = 0;
+    if (g.mode == 0) {
+      iz = b % g.dims[2];
+      iy = (b / g.dims[2]) % g.dims[1];
+      ix = b / (g.dims[2] * g.dims[1]);
+      span = 1;
+    }
+    for (int ox = -span; ox <= span; ++ox)
+      for (int oy = -span; oy <= span; ++oy)
+        for (int oz = -span; oz <= span; ++oz) {
+          NeighbourRange r;
+          if (g.mode == 0) {
+            if (!neighbour_bucket(g, bin_start, ix, iy, iz, ox, oy, oz, r)) continue;
+          } else {
+            r.lo = bin_start[b];
+            r.hi = bin_start[b + 1];
+            r.code = 13;
+          }
+          const float3 sh = (r.code == 13) ? make_float3(0.f, 0.f, 0.f) : image_shift(g, r.code);
+          for (int base = r.lo; base < r.hi; base += 32) {
+            const int c = base + lane;
+            const bool valid = c < r.hi;
+            const float4 p = valid ? spos[c] : pi;
+            const float dx = (p.x + sh.x) - pi.x, dy = (p.y + sh.y) - pi.y, dz = (p.z + sh.z) - pi.z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const bool keep = valid && r2 <= rcr2 && !(c == i && r.code == 13);
+            const unsigned m = __ballot_sync(ANI_FULL_MASK, keep);
+            if (keep) {
+              const int pos = cnt + __popc(m & lt);
+              if (pos < cap) {
+                s.nd[pos] = make_float4(dx, dy, dz, sqrtf(r2));
+                s.nj[pos] = c | (r.code << ANI_IMG_SHIFT);
+                s.nsp[pos] = (unsigned char)__float_as_int(p.w);
+              }
+            }
+            cnt += __popc(m);
+          }
+        }
+  }
+  if (cnt > cap) {
+    if (lane == 0) atomicOr(status, ANI_STATUS_NBR_OVERFLOW);
+    cnt = cap;
+  }
+  __syncwarp();
+  if (lane == 0) nbr_cnt[i] = cnt;
+  for (int n = lane; n < cnt; n += 32) {
+    nbr_list[(size_t)i * cap + n] = s.nj[n];
+    s.nfc[n] = cutoff_value(s.nd[n].w, P.rcr, P.cutoff_kind);
+  }
+  for (int t = lane; t < 2 * RL; t += 32) s.rad[t] = 0.f;
+  __syncwarp();
+
+  const size_t row = (size_t)row_of[i] * ldx;
+
+  // ---- 2. radial block: lane = (shift m, neighbour parity h); the two parities own separate
+  //         accumulator arrays, lanes of one parity hit distinct addresses -> no atomics
+  {
+    const int lpn = (nR <= 16) ? 16 : 32;
+    const int halves = 32 / lpn;
+    const int m = lane % lpn, h = lane / lpn;
+    const float shf = P.shf_r[m < nR ? m : 0];
+    for (int n = h; n < cnt; n += halves) {
+      const float R = s.nd[n].w;
+      const float d = R - shf;
+      const float v = 0.25f * expf(-P.eta_r * d * d) * s.nfc[n];
+      if (m < nR) s.rad[h * RL + s.nsp[n] * nR + m] += v;
+    }
+    __syncwarp();
+    for (int t = lane; t < RL; t += 32) aev[row + t] = s.rad[t] + (halves == 2 ? s.rad[RL + t] : 0.f);
+  }
+
+  // ---- 3. angular block
+  const int n_ang = build_angular_list<false>(P, s, cnt, lane, status);
+  (void)n_ang;
+  float shfA[NA], cz[NZ], sz[NZ];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) shfA[a] = P.shf_a[a];
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) {
+    cz[z] = P.cos_z[z];
+    sz[z] = P.sin_z[z];
+  }
+  int p = 0;
+  for (int s1 = 0; s1 < S; ++s1) {
+    const int a0 = s.seg[s1], na = s.seg[s1 + 1] - a0;
+    for (int s2 = s1; s2 < S; ++s2, ++p) {
+      const int b0 = s.seg[s2], nb = s.seg[s2 + 1] - b0;
+      const int count = (s1 == s2) ? na * (na - 1) / 2 : na * nb;
+      float out = 0.f;
+      if (count > 0) {
+        float acc[32];
+#pragma unroll
+        for (int f = 0; f < 32; ++f) acc[f] = 0.f;
+        for (int q = lane; q < count; q += 32) {
+          int ja, jb;
+          if (s1 == s2) {
+            triangle_decode(q, ja, jb);
+            ja += a0;
+            jb += a0;
+          } else {
+            ja = a0 + q / nb;
+            jb = b0 + q % nb;
+          }
+          const float4 dj = s.nd[s.aidx[ja]], dk = s.nd[s.aidx[jb]];
+          const float w2 = 2.0f * s.afc[ja] * s.afc[jb];
+          const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
+          const float c = 0.95f * dot / fmaxf(dj.w * dk.w, 1e-10f);
+          const float sn = sqrtf(fmaxf(1.0f - c * c, 0.f));
+          const float rbar = 0.5f * (dj.w + dk.w);
+          float f1[NZ];
+#pragma unroll
+          for (int z = 0; z < NZ; ++z) {
+            const float base = fmaxf(0.5f * (1.0f + c * cz[z] + sn * sz[z]), 0.f);
+            f1[z] = exp2f(P.zeta * log2f(base));
+          }
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const float d = rbar - shfA[a];
+            const float f2 = expf(-P.eta_a * d * d) * w2;
+#pragma unroll
+            for (int z = 0; z < NZ; ++z) acc[a * NZ + z] += f1[z] * f2;
+          }
+        }
+        out = transpose_reduce32(acc, lane);
+      }
+      aev[row + RL + p * 32 + lane] = out;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------
+template <int NA, int NZ>
+__global__ void __launch_bounds__(AEV_WARPS * 32)
+    k_aev_backward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
+                   const float4* __restrict__ spos, const int32_t* __restrict__ sorted_orig, int lo, int hi,
+                   const int32_t* __restrict__ row_of, const float* __restrict__ gaev, int ldx,
+                   const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ nbr_list, int cap,
+                   float* __restrict__ grad_coords, int32_t* __restrict__ status, size_t warp_bytes) {
+  static_assert(NA * NZ == 32, "one lane per angular feature");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ani_grid g = *grid;
+  hi = min(hi, g.n_real);
+  const int i = lo + blockIdx.x * AEV_WARPS + warp;
+  if (i >= hi) return;
+  const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, true);
+  const int S = P.num_species;
+  const int nR = P.n_shf_r;
+  const int RL = S * nR;
+  const int NP = S * (S + 1) / 2;
+  const int gstride = NP | 1;  // odd stride -> conflict-free lane-varying species-pair lookups
+  float* g_rad = s.rad;
+  float* g_ang = s.rad + RL;
+
+  // ---- 1. upstream gradient row -> shared memory (angular part transposed: [feature][pair])
+  const size_t row = (size_t)row_of[i] * ldx;
+  for (int t = lane; t < RL; t += 32) g_rad[t] = gaev[row + t];
+  for (int pp = 0; pp < NP; ++pp) g_ang[lane * gstride + pp] = gaev[row + RL + pp * 32 + lane];
+
+  // ---- 2. geometry of the stored neighbours
+  const float4 pi = spos[i];
+  const int cnt = nbr_cnt[i];
+  for (int n = lane; n < cnt; n += 32) {
+    const int word = nbr_list[(size_t)i * cap + n];
+    const int j = word & ANI_IDX_MASK, code = (unsigned)word >> ANI_IMG_SHIFT;
+    const float4 p = spos[j];
+    float3 sh = make_float3(0.f, 0.f, 0.f);
+    if (code != 13) sh = image_shift(g, code);
+    const float dx = (p.x + sh.x) - pi.x, dy = (p.y + sh.y) - pi.y, dz = (p.z + sh.z) - pi.z;
+    s.nd[n] = make_float4(dx, dy, dz, sqrtf(dx * dx + dy * dy + dz * dz));
+    s.nj[n] = j;
+    s.nsp[n] = (unsigned char)__float_as_int(p.w);
+  }
+  __syncwarp();
+
+  // ---- 3. radial: dE/dR_n = sum_m g[s_n, m] * (G' fc + G fc'), then along the unit vector
+  {
+    const int lpn = (nR <= 16) ? 16 : 32;
+    const int halves = 32 / lpn;
+    const int m = lane % lpn, h = lane / lpn;
+    const float shf = P.shf_r[m < nR ? m : 0];
+    for (int base = 0; base < cnt; base += halves) {
+      const int n = base + h;
+      const bool valid = n < cnt;
+      float contrib = 0.f;
+      float4 d = make_float4(0.f, 0.f, 0.f, 1.f);
+      if (valid) {
+        d = s.nd[n];
+        float fc, dfc;
+        cutoff_value_grad(d.w, P.rcr, P.cutoff_kind, fc, dfc);
+        const float x = d.w - shf;
+        const float G = 0.25f * expf(-P.eta_r * x * x);
+        if (m < nR) contrib = g_rad[s.nsp[n] * nR + m] * G * (-2.0f * P.eta_r * x * fc + dfc);
+      }
+      for (int o = lpn / 2; o > 0; o >>= 1) contrib += __shfl_xor_sync(ANI_FULL_MASK, contrib, o);
+      if (valid && m == 0) {
+        const float sc = d.w > 1e-10f ? contrib / d.w : 0.f;
+        s.fgrad[3 * n + 0] = sc * d.x;
+        s.fgrad[3 * n + 1] = sc * d.y;
+        s.fgrad[3 * n + 2] = sc * d.z;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- 4. angular, ordered pairs (j, k): lanes own rows j
+  const int n_ang = build_angular_list<true>(P, s, cnt, lane, status);
+  if (n_ang >= 2) {
+    float shfA[NA], cz[NZ], sz[NZ];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) shfA[a] = P.shf_a[a];
+#pragma unroll
+    for (int z = 0; z < NZ; ++z) {
+      cz[z] = P.cos_z[z];
+      sz[z] = P.sin_z[z];
+    }
+    int lpr = 1;
+    while (lpr * 2 * n_ang <= 32) lpr *= 2;
+    const int rows_per_pass = 32 / lpr;
+    const int sub = lane % lpr;
+    for (int row0 = 0; row0 < n_ang; row0 += rows_per_pass) {
+      const int j = row0 + lane / lpr;
+      const bool jvalid = j < n_ang;
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      if (jvalid) {
+        const int nj_ = s.aidx[j];
+        const float4 dj = s.nd[nj_];
+        const float fcj = s.afc[j], dfcj = s.afcd[j];
+        const int sj = s.nsp[nj_];
+        const float inv_rj = dj.w > 1e-10f ? 1.0f / dj.w : 0.f;
+        for (int k = sub; k < n_ang; k += lpr) {
+          if (k == j) continue;
+          const int nk_ = s.aidx[k];
+          const float4 dk = s.nd[nk_];
+          const float fck = s.afc[k];
+          const int pidx = pair_index(sj, (int)s.nsp[nk_], S);
+          const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
+          const float inv_rr = 1.0f / fmaxf(dj.w * dk.w, 1e-10f);
+          const float cosT = dot * inv_rr;
+          const float c = 0.95f * cosT;
+          const float sn = sqrtf(fmaxf(1.0f - c * c, 0.f));
+          const float c_over_s = c / sn;
+          const float rbar = 0.5f * (dj.w + dk.w);
+          float f2[NA], f2p[NA];
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const float d = rbar - shfA[a];
+            f2[a] = expf(-P.eta_a * d * d);
+            f2p[a] = -2.0f * P.eta_a * d * f2[a];
+          }
+          float S0 = 0.f, S1 = 0.f, S2 = 0.f;
+#pragma unroll
+          for (int z = 0; z < NZ; ++z) {
+            float tz = 0.f, uz = 0.f;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+              const float gv = g_ang[(a * NZ + z) * gstride + pidx];
+              tz += gv * f2[a];
+              uz += gv * f2p[a];
+            }
+            const float base = fmaxf(0.5f * (1.0f + c * cz[z] + sn * sz[z]), 0.f);
+            const float lg = log2f(base);
+            const float f1 = exp2f(P.zeta * lg);
+            const float pw1 = exp2f((P.zeta - 1.0f) * lg);
+            const float f1p = P.zeta * pw1 * (0.475f * (cz[z] - c_over_s * sz[z]));
+            S0 += f1 * tz;
+            S1 += f1p * tz;
+            S2 += f1 * uz;
+          }
+          const float W = fcj * fck;
+          const float dEdRj = S2 * W + 2.0f * S0 * dfcj * fck;  // 2*(0.5*S2*W + S0*fcj'*fck)
+          const float dEdcos = 2.0f * W * S1;
+          const float coefj = (dEdRj - dEdcos * cosT * inv_rj) * inv_rj;
+          const float coefk = dEdcos * inv_rr;
+          gx += coefj * dj.x + coefk * dk.x;
+          gy += coefj * dj.y + coefk * dk.y;
+          gz += coefj * dj.z + coefk * dk.z;
+        }
+      }
+      for (int o = lpr / 2; o > 0; o >>= 1) {
+        gx += __shfl_xor_sync(ANI_FULL_MASK, gx, o);
+        gy += __shfl_xor_sync(ANI_FULL_MASK, gy, o);
+        gz += __shfl_xor_sync(ANI_FULL_MASK, gz, o);
+      }
+      if (jvalid && sub == 0) {
+        const int nj_ = s.aidx[j];
+        s.fgrad[3 * nj_ + 0] += gx;
+        s.fgrad[3 * nj_ + 1] += gy;
+        s.fgrad[3 * nj_ + 2] += gz;
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+
+  // ---- 5. scatter: neighbour j gets +dE_i/dr_j, the centre gets minus the sum
+  float sx = 0.f, sy = 0.f, sz_ = 0.f;
+  for (int n = lane; n < cnt; n += 32) {
+    const float fx = s.fgrad[3 * n], fy = s.fgrad[3 * n + 1], fz = s.fgrad[3 * n + 2];
+    const int oj = sorted_orig[s.nj[n]];
+    atomicAdd(&grad_coords[3 * (size_t)oj + 0], fx);
+    atomicAdd(&grad_coords[3 * (size_t)oj + 1], fy);
+    atomicAdd(&grad_coords[3 * (size_t)oj + 2], fz);
+    sx += fx;
+    sy += fy;
+    sz_ += fz;
+  }
+  sx = warp_sum(sx);
+  sy = warp_sum(sy);
+  sz_ = warp_sum(sz_);
+  if (lane == 0) {
+    const int oi = sorted_orig[i];
+    atomicAdd(&grad_coords[3 * (size_t)oi + 0], -sx);
+    atomicAdd(&grad_coords[3 * (size_t)oi + 1], -sy);
+    atomicAdd(&grad_coords[3 * (size_t)oi + 2], -sz_);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// reference-format half neighbour list (API parity path; one thread per atom)
+// ---------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void k_half_list(const ani_grid* __restrict__ grid, const int32_t* __restrict__ bin_start,
+                            const float4* __restrict__ spos, const int32_t* __restrict__ sbin,
+                            const int32_t* __restrict__ sorted_orig, int n, float cutoff,
+                            int32_t* __restrict__ pair_count, const int32_t* __restrict__ pair_start,
+                            long long cap, int64_t* __restrict__ idx0, int64_t* __restrict__ idx1,
+                            float* __restrict__ distances, float* __restrict__ diffs,
+                            int32_t* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ani_grid g = *grid;
+  int count = 0;
+  if (i < g.n_real) {
+    const float4 pi = spos[i];
+    const int oi = sorted_orig[i];
+    const float c2 = cutoff * cutoff;
+    long long out = FILL ? (long long)pair_start[i] : 0;
+    const int b = sbin[i];
+    int ix = 0, iy = 0, iz = 0, span = 0;
+    if (g.mode == 0) {
+      iz = b % g.dims[2];
+      iy = (b / g.dims[2]) % g.dims[1];
+      ix = b / (g.dims[2] * g.dims[1]);
+      span = 1;
+    }
+    for (int ox = -span; ox <= span; ++ox)
+      for (int oy = -span; oy <= span; ++oy)
+        for (int oz = -span; oz <= span; ++oz) {
+          NeighbourRange r;
+          if (g.mode == 0) {
+            if (!neighbour_bucket(g, bin_start, ix, iy, iz, ox, oy, oz, r)) continue;
+          } else {
+            r.lo = bin_start[b];
+            r.hi = bin_start[b + 1];
+            r.code = 13;
+          }
+          const float3 sh = (r.code == 13) ? make_float3(0.f, 0.f, 0.f) : image_shift(g, r.code);
+          for (int c = r.lo; c < r.hi; ++c) {
+            const int oj = sorted_orig[c];
+            // every unordered pair is seen from both ends; keep it at the lower input index
+            // (self-image pairs: keep the upper half of the image codes)
+            if (!(oi < oj || (oi == oj && r.code > 13))) continue;
+            const float4 p = spos[c];
+            const float dx = pi.x - (p.x + sh.x), dy = pi.y - (p.y + sh.y), dz = pi.z - (p.z + sh.z);
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            if (r2 > c2) continue;
+            if (FILL) {
+              if (out < cap) {
+                idx0[out] = oi;
+                idx1[out] = oj;
+                distances[out] = sqrtf(r2);
+                diffs[3 * out + 0] = dx;
+                diffs[3 * out + 1] = dy;
+                diffs[3 * out + 2] = dz;
+              } else {
+                atomicOr(status, ANI_STATUS_PAIR_OVERFLOW);
+              }
+              ++out;
+            }
+            ++count;
+          }
+        }
+  }
+  if (!FILL) pair_count[i] = count;
+}
+
+// exclusive scan of an int array by one block: out[0..m], out[m] = total
+__global__ void k_scan_i32(const int32_t* __restrict__ in, int m, int32_t* __restrict__ out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += blockDim.x) {
+    const int i = base + tid;
+    const int v = (i < m) ? in[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(ANI_FULL_MASK, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = (lane < (blockDim.x >> 5)) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(ANI_FULL_MASK, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;
+    }
+    __syncthreads();
+    const int incl = x + ((w == 0) ? 0 : s_warp[w - 1]) + s_carry;
+    if (i < m) out[i] = incl - v;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (tid == 0) out[m] = s_carry;
+}
+
+static int check_params(const ani_aev_params* p) {
+  if (!p) return ANI_ERR_BAD_ARG;
+  if (p->num_species < 1 || p->num_species > ANI_MAX_SPECIES) return ANI_ERR_UNSUPPORTED;
+  if (p->n_shf_r < 1 || p->n_shf_r > ANI_MAX_SHFR) return ANI_ERR_UNSUPPORTED;
+  if (!((p->n_shf_a == 8 && p->n_shf_z == 4) || (p->n_shf_a == 4 && p->n_shf_z == 8)))
+    return ANI_ERR_UNSUPPORTED;  // one lane per angular feature: ShfA x ShfZ must be 8x4 or 4x8
+  if (!(p->rca < p->rcr) || p->rca <= 0.f) return ANI_ERR_BAD_ARG;  // aev/_computer.py:233
+  if (!(p->zeta > 1.0f)) return ANI_ERR_UNSUPPORTED;
+  if (p->cutoff_kind != 0 && p->cutoff_kind != 1) return ANI_ERR_UNSUPPORTED;
+  return ANI_OK;
+}
+
+}  // namespace ani
+
+using namespace ani;
+
+extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
+                                    const float* spos, const int32_t* sbin, int n, int lo, int hi,
+                                    const int32_t* row_of, float* aev, int ldx, int32_t* nbr_cnt,
+                                    int32_t* nbr_list, int nbr_cap, int32_t* status, void* stream) {
+  int rc = check_params(params);
+  if (rc != ANI_OK) return rc;
+  if (!grid || !bin_start || !spos || !sbin || !row_of || !aev || !nbr_cnt || !nbr_list || !status)
+    return ANI_ERR_BAD_ARG;
+  if (lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
+  if (nbr_cap < 32 || nbr_cap > 256 || nbr_cap % 32) return ANI_ERR_BAD_ARG;
+  const int out_dim = params->num_species * params->n_shf_r +
+                      params->num_species * (params->num_species + 1) / 2 * 32;
+  if (ldx < out_dim) return ANI_ERR_BAD_ARG;
+  if (hi == lo) return ANI_OK;
+  const int RL = params->num_species * params->n_shf_r;
+  const size_t wb = warp_smem_bytes(nbr_cap, 2 * RL, false);
+  const size_t smem = wb * AEV_WARPS;
+  const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* sp4 = reinterpret_cast<const float4*>(spos);
+  if (params->n_shf_a == 8) {
+    auto k = k_aev_forward<8, 4>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx,
+                                            nbr_cnt, nbr_list, nbr_cap, status, wb);
+  } else {
+    auto k = k_aev_forward<4, 8>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx,
+                                            nbr_cnt, nbr_list, nbr_cap, status, wb);
+  }
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                                     const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
+                                     const float* grad_aev, int ldx, const int32_t* nbr_cnt,
+                                     const int32_t* nbr_list, int nbr_cap, float* grad_coords, int32_t* status,
+                                     void* stream) {
+  int rc = check_params(params);
+  if (rc != ANI_OK) return rc;
+  if (!grid || !spos || !sorted_orig || !row_of || !grad_aev || !nbr_cnt || !nbr_list || !grad_coords || !status)
+    return ANI_ERR_BAD_ARG;
+  if (lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
+  if (nbr_cap < 32 || nbr_cap > 256 || nbr_cap % 32) return ANI_ERR_BAD_ARG;
+  if (hi == lo) return ANI_OK;
+  const int S = params->num_species;
+  const int RL = S * params->n_shf_r;
+  const int NP = S * (S + 1) / 2;
+  const size_t wb = warp_smem_bytes(nbr_cap, RL + 32 * (NP | 1), true);
+  const size_t smem = wb * AEV_WARPS;
+  const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float4* sp4 = reinterpret_cast<const float4*>(spos);
+  if (params->n_shf_a == 8) {
+    auto k = k_aev_backward<8, 4>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
+                                            nbr_cnt, nbr_list, nbr_cap, grad_coords, status, wb);
+  } else {
+    auto k = k_aev_backward<4, 8>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
+                                            nbr_cnt, nbr_list, nbr_cap, grad_coords, status, wb);
+  }
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_half_neighbor_count(const ani_grid* grid, const int32_t* bin_start, const float* spos,
+                                            const int32_t* sbin, const int32_t* sorted_orig, int n, float cutoff,
+                                            int32_t* pair_start, void* stream) {
+  if (!grid || !bin_start || !spos || !sbin || !sorted_orig || !pair_start || n < 1) return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  // counts go to pair_start[n+1 .. 2n], the scan to pair_start[0 .. n]
+  int32_t* counts = pair_start + (n + 1);
+  k_half_list<false><<<(n + 127) / 128, 128, 0, st>>>(grid, bin_start, reinterpret_cast<const float4*>(spos), sbin,
+                                                      sorted_orig, n, cutoff, counts, nullptr, 0, nullptr, nullptr,
+                                                      nullptr, nullptr, nullptr);
+  k_scan_i32<<<1, 1024, 0, st>>>(counts, n, pair_start);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, const float* spos,
+                                           const int32_t* sbin, const int32_t* sorted_orig, int n, float cutoff,
+                                           const int32_t* pair_start, int64_t cap, int64_t* idx0, int64_t* idx1,
+                                           float* distances, float* diff_vectors, int32_t* status, void* stream) {
+  if (!grid || !bin_start || !spos || !sbin || !sorted_orig || !pair_start || !idx0 || !idx1 || !distances ||
+      !diff_vectors || !status || n < 1)
+    return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_half_list<true><<<(n + 127) / 128, 128, 0, st>>>(grid, bin_start, reinterpret_cast<const float4*>(spos), sbin,
+                                                     sorted_orig, n, cutoff, nullptr, pair_start, (long long)cap,
+                                                     idx0, idx1, distances, diff_vectors, status);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}

@@ -1,0 +1,401 @@
+// Bucket grid construction: wrap atoms into the cell, assign buckets, stable counting sort,
+// species-grouped row layout for the MLP.  Replaces the ATen op chain of
+// neighbors.py:418-507,554-615 / csrc/cell_list.cpp:266-350 with five small sync-free kernels.
+#include "common.cuh"
+
+namespace ani {
+
+// ---------------------------------------------------------------------------------------
+// grid setup: one block.  mode 0 + pbc: buckets from the perpendicular widths of the cell
+// (>= 1 bucket per cutoff, neighbors.py:618-662 uses edge lengths; widths are the safe
+// choice for triclinic cells).  mode 0 without pbc: bounding box of the real atoms.
+// ---------------------------------------------------------------------------------------
+__global__ void k_grid_setup(const float* __restrict__ coords, const int32_t* __restrict__ species,
+                             int n, int n_conf, int n_per_conf, const float* __restrict__ cell, int pbc,
+                             int mode, float cutoff, int max_bins, ani_grid* __restrict__ grid,
+                             int32_t* __restrict__ status) {
+  __shared__ float s_min[3][32], s_max[3][32];
+  const int tid = threadIdx.x;
+  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+  if (mode == 0 && !pbc) {
+    for (int a = tid; a < n; a += blockDim.x) {
+      if (species[a] < 0) continue;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float v = coords[3 * a + d];
+        lo[d] = fminf(lo[d], v);
+        hi[d] = fmaxf(hi[d], v);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(ANI_FULL_MASK, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(ANI_FULL_MASK, hi[d], o));
+      }
+      if ((tid & 31) == 0) {
+        s_min[d][tid >> 5] = lo[d];
+        s_max[d][tid >> 5] = hi[d];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  ani_grid g;
+  for (int k = 0; k < 9; ++k) g.cell[k] = g.inv[k] = 0.f;
+  g.origin[0] = g.origin[1] = g.origin[2] = 0.f;
+  g.dims[0] = g.dims[1] = g.dims[2] = 1;
+  g.pbc = pbc;
+  g.mode = mode;
+  g.n_per_conf = n_per_conf;
+  g.n_real = 0;
+  const float bucket = cutoff + 1e-5f;
+  if (mode == 1) {
+    g.nbins = n_conf;
+    g.cell[0] = g.cell[4] = g.cell[8] = 1.f;
+    g.inv[0] = g.inv[4] = g.inv[8] = 1.f;
+  } else {
+    if (pbc) {
+      // inverse of the 3x3 cell in double (host-quality), rows of `cell` are lattice vectors
+      double c[9];
+      for (int k = 0; k < 9; ++k) c[k] = (double)cell[k];
+      double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) +
+                   c[2] * (c[3] * c[7] - c[4] * c[6]);
+      double id = 1.0 / det;
+      double iv[9];
+      iv[0] = (c[4] * c[8] - c[5] * c[7]) * id;
+      iv[1] = (c[2] * c[7] - c[1] * c[8]) * id;
+      iv[2] = (c[1] * c[5] - c[2] * c[4]) * id;
+      iv[3] = (c[5] * c[6] - c[3] * c[8]) * id;
+      iv[4] = (c[0] * c[8] - c[2] * c[6]) * id;
+      iv[5] = (c[2] * c[3] - c[0] * c[5]) * id;
+      iv[6] = (c[3] * c[7] - c[4] * c[6]) * id;
+      iv[7] = (c[1] * c[6] - c[0] * c[7]) * id;
+      iv[8] = (c[0] * c[4] - c[1] * c[3]) * id;
+      for (int k = 0; k < 9; ++k) {
+        g.cell[k] = cell[k];
+        g.inv[k] = (float)iv[k];
+      }
+      for (int d = 0; d < 3; ++d) {
+        // frac_d = r . inv[:, d]; planes frac_d = const are 1/|inv[:, d]| apart
+        double w = 1.0 / sqrt(iv[d] * iv[d] + iv[3 + d] * iv[3 + d] + iv[6 + d] * iv[6 + d]);
+        int nd = (int)floor(w / (double)bucket);
+        if (nd < 1) {
+          atomicOr(status, ANI_STATUS_CELL_TOO_SMALL);
+          nd = 1;
+        }
+        g.dims[d] = nd;
+      }
+    } else {
+      float mn[3], mx[3];
+      for (int d = 0; d < 3; ++d) {
+        mn[d] = 1e30f;
+        mx[d] = -1e30f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) {
+          mn[d] = fminf(mn[d], s_min[d][w]);
+          mx[d] = fmaxf(mx[d], s_max[d][w]);
+        }
+        if (mn[d] > mx[d]) mn[d] = mx[d] = 0.f;  // no real atoms
+        float ext = (mx[d] - mn[d]) + 2e-3f;
+        g.origin[d] = mn[d] - 1e-3f;
+        g.cell[4 * d] = ext;
+        g.inv[4 * d] = 1.0f / ext;
+        int nd = (int)floorf(ext / bucket);
+        g.dims[d] = nd < 1 ? 1 : nd;
+      }
+    }
+    // respect the caller's bucket capacity (buckets may only get larger than the cutoff)
+    int cap = max_bins - 1;
+    while ((long long)g.dims[0] * g.dims[1] * g.dims[2] > (long long)cap) {
+      int big = 0;
+      if (g.dims[1] > g.dims[big]) big = 1;
+      if (g.dims[2] > g.dims[big]) big = 2;
+      g.dims[big] = max(1, g.dims[big] - max(1, g.dims[big] / 8));
+    }
+    g.nbins = g.dims[0] * g.dims[1] * g.dims[2];
+  }
+  *grid = g;
+}
+
+__device__ __forceinline__ void wrapped_position(const ani_grid& g, const float* __restrict__ coords, int a,
+                                                 float3& pos, int& bin) {
+  float x = coords[3 * a], y = coords[3 * a + 1], z = coords[3 * a + 2];
+  if (g.mode == 1) {
+    pos = make_float3(x, y, z);
+    bin = a / g.n_per_conf;
+    return;
+  }
+  float rx = x - g.origin[0], ry = y - g.origin[1], rz = z - g.origin[2];
+  float f[3];
+  f[0] = rx * g.inv[0] + ry * g.inv[3] + rz * g.inv[6];
+  f[1] = rx * g.inv[1] + ry * g.inv[4] + rz * g.inv[7];
+  f[2] = rx * g.inv[2] + ry * g.inv[5] + rz * g.inv[8];
+  int idx[3];
+  float k[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (g.pbc) {
+      k[d] = floorf(f[d]);  // utils.py:249-250 (map_to_central): frac -= floor(frac)
+      f[d] -= k[d];
+    }
+    int i = (int)floorf(f[d] * (float)g.dims[d]);
+    idx[d] = min(max(i, 0), g.dims[d] - 1);
+  }
+  // Subtract whole lattice vectors from the input position instead of rebuilding it from the
+  // fractional coordinates: atoms already inside the cell keep their exact float32 position
+  // (the reference's frac @ cell round trip costs ~1e-7 * |cell| of absolute accuracy).
+  pos.x = x - (k[0] * g.cell[0] + k[1] * g.cell[3] + k[2] * g.cell[6]);
+  pos.y = y - (k[0] * g.cell[1] + k[1] * g.cell[4] + k[2] * g.cell[7]);
+  pos.z = z - (k[0] * g.cell[2] + k[1] * g.cell[5] + k[2] * g.cell[8]);
+  bin = (idx[0] * g.dims[1] + idx[1]) * g.dims[2] + idx[2];
+}
+
+__global__ void k_bin_assign(const float* __restrict__ coords, const int32_t* __restrict__ species, int n,
+                             const ani_grid* __restrict__ grid, int32_t* __restrict__ bin_of,
+                             int32_t* __restrict__ slot, int32_t* __restrict__ bin_count) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const ani_grid g = *grid;
+  int bin;
+  if (species[a] < 0) {
+    bin = g.nbins;  // padding atoms: trash bucket, never a neighbour, never a centre
+  } else {
+    float3 p;
+    wrapped_position(g, coords, a, p, bin);
+  }
+  bin_of[a] = bin;
+  slot[a] = atomicAdd(&bin_count[bin], 1);
+}
+
+// exclusive scan of cnt[0..m-1] -> start[0..m] by one block (m = nbins + 1, read from grid)
+__global__ void k_bin_scan(const int32_t* __restrict__ cnt, ani_grid* grid, int32_t* __restrict__ start) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int m = grid->nbins + 1;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += blockDim.x) {
+    int i = base + tid;
+    int v = (i < m) ? cnt[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(ANI_FULL_MASK, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = (lane < (blockDim.x >> 5)) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(ANI_FULL_MASK, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    int warp_off = (w == 0) ? 0 : s_warp[w - 1];
+    int incl = x + warp_off + s_carry;
+    if (i < m) start[i] = incl - v;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    start[m] = s_carry;
+    grid->n_real = start[m - 1];  // everything before the trash bucket
+  }
+}
+
+__global__ void k_bin_scatter(int n, const int32_t* __restrict__ bin_of, const int32_t* __restrict__ slot,
+                              const int32_t* __restrict__ bin_start, int32_t* __restrict__ tmp_list) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  tmp_list[bin_start[bin_of[a]] + slot[a]] = a;
+}
+
+// the atomics above give an arbitrary order inside a bucket; rank by input index to make the
+// sorted order (and with it every later summation order) deterministic
+__global__ void k_bin_finalize(const float* __restrict__ coords, const int32_t* __restrict__ species, int n,
+                               const ani_grid* __restrict__ grid, const int32_t* __restrict__ bin_of,
+                               const int32_t* __restrict__ bin_start, const int32_t* __restrict__ tmp_list,
+                               int32_t* __restrict__ sorted_orig, int32_t* __restrict__ orig_to_sorted,
+                               float4* __restrict__ spos, int32_t* __restrict__ sbin) {
+  int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const ani_grid g = *grid;
+  int b = bin_of[a];
+  int lo = bin_start[b], hi = bin_start[b + 1];
+  int rank = 0;
+  for (int e = lo; e < hi; ++e) rank += (tmp_list[e] < a);
+  int i = lo + rank;
+  sorted_orig[i] = a;
+  orig_to_sorted[a] = i;
+  sbin[i] = b;
+  float3 p = make_float3(0.f, 0.f, 0.f);
+  int sp = species[a];
+  if (sp >= 0) {
+    int bb;
+    wrapped_position(g, coords, a, p, bb);
+  }
+  spos[i] = make_float4(p.x, p.y, p.z, __int_as_float(sp));
+}
+
+// ---------------------------------------------------------------------------------------
+// species-grouped row layout (three kernels, deterministic):
+//   1. per-chunk species histogram of the owned sorted atoms
+//   2. one block: scan chunks per species, pad each species block to ANI_TILE_ROWS rows,
+//      emit the tile table
+//   3. per-chunk: assign rows (ballot ranks inside the chunk)
+// ---------------------------------------------------------------------------------------
+constexpr int LAYOUT_CHUNK = 256;
+
+__global__ void k_layout_count(const float4* __restrict__ spos, const ani_grid* __restrict__ grid, int lo,
+                               int hi, int S, int32_t* __restrict__ chunk_hist) {
+  __shared__ int s_h[ANI_MAX_SPECIES];
+  const int n_real = grid->n_real;
+  hi = min(hi, n_real);
+  if (threadIdx.x < ANI_MAX_SPECIES) s_h[threadIdx.x] = 0;
+  __syncthreads();
+  int i = lo + blockIdx.x * LAYOUT_CHUNK + threadIdx.x;
+  int sp = (i < hi) ? __float_as_int(spos[i].w) : -1;
+  for (int s = 0; s < S; ++s) {
+    unsigned m = __ballot_sync(ANI_FULL_MASK, sp == s);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&s_h[s], __popc(m));
+  }
+  __syncthreads();
+  if (threadIdx.x < ANI_MAX_SPECIES) chunk_hist[blockIdx.x * ANI_MAX_SPECIES + threadIdx.x] = s_h[threadIdx.x];
+}
+
+__global__ void k_layout_scan(int n_chunks, int S, int rows_cap, int32_t* __restrict__ chunk_hist,
+                              int32_t* __restrict__ species_base, int32_t* __restrict__ tile_species,
+                              int32_t* __restrict__ row_atom, int32_t* __restrict__ layout_info) {
+  // chunk_hist[c][s] -> exclusive prefix over chunks (in place); species_base[s] = first row
+  __shared__ int s_tot[ANI_MAX_SPECIES];
+  __shared__ int s_base[ANI_MAX_SPECIES + 1];
+  const int tid = threadIdx.x;
+  if (tid < S) {
+    int run = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+      int v = chunk_hist[c * ANI_MAX_SPECIES + tid];
+      chunk_hist[c * ANI_MAX_SPECIES + tid] = run;
+      run += v;
+    }
+    s_tot[tid] = run;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int row = 0, owned = 0;
+    for (int s = 0; s < S; ++s) {
+      s_base[s] = row;
+      species_base[s] = row;
+      owned += s_tot[s];
+      row += (s_tot[s] + ANI_TILE_ROWS - 1) / ANI_TILE_ROWS * ANI_TILE_ROWS;
+    }
+    s_base[S] = row;
+    layout_info[0] = row / ANI_TILE_ROWS;
+    layout_info[1] = row;
+    layout_info[2] = owned;
+    layout_info[3] = 0;
+  }
+  __syncthreads();
+  const int n_tiles_cap = rows_cap / ANI_TILE_ROWS;
+  for (int t = tid; t < n_tiles_cap; t += blockDim.x) {
+    int r = t * ANI_TILE_ROWS, sp = -1;
+    for (int s = 0; s < S; ++s)
+      if (r >= s_base[s] && r < s_base[s + 1] && r < s_base[s] + s_tot[s]) sp = s;
+    tile_species[t] = sp;
+  }
+  for (int r = tid; r < rows_cap; r += blockDim.x) row_atom[r] = -1;
+}
+
+__global__ void k_layout_assign(const float4* __restrict__ spos, const ani_grid* __restrict__ grid, int lo,
+                                int hi, int S, const int32_t* __restrict__ chunk_hist,
+                                const int32_t* __restrict__ species_base, int32_t* __restrict__ row_of,
+                                int32_t* __restrict__ row_atom) {
+  __shared__ int s_wcnt[LAYOUT_CHUNK / 32][ANI_MAX_SPECIES];
+  const int n_real = grid->n_real;
+  hi = min(hi, n_real);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int i = lo + blockIdx.x * LAYOUT_CHUNK + threadIdx.x;
+  int sp = (i < hi) ? __float_as_int(spos[i].w) : -1;
+  int my_rank = 0;
+  for (int s = 0; s < S; ++s) {
+    unsigned m = __ballot_sync(ANI_FULL_MASK, sp == s);
+    if (sp == s) my_rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_wcnt[w][s] = __popc(m);
+  }
+  __syncthreads();
+  if (sp >= 0) {
+    int off = 0;
+    for (int ww = 0; ww < w; ++ww) off += s_wcnt[ww][sp];
+    int row = species_base[sp] + chunk_hist[blockIdx.x * ANI_MAX_SPECIES + sp] + off + my_rank;
+    row_of[i] = row;
+    row_atom[row] = i;
+  }
+}
+
+}  // namespace ani
+
+using namespace ani;
+
+extern "C" int ani_b200_build_cells(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
+                                    const float* cell, int pbc, int mode, float cutoff, int max_bins,
+                                    ani_grid* grid, int32_t* bin_start, int32_t* sorted_orig,
+                                    int32_t* orig_to_sorted, float* spos, int32_t* sbin, int32_t* scratch_i32,
+                                    int32_t* status, void* stream) {
+  if (!coords || !species || !grid || !bin_start || !sorted_orig || !orig_to_sorted || !spos || !sbin ||
+      !scratch_i32 || !status)
+    return ANI_ERR_BAD_ARG;
+  if (n_conf < 1 || n_per_conf < 1 || cutoff <= 0.f || max_bins < 2) return ANI_ERR_BAD_ARG;
+  if (mode == 0 && n_conf != 1) return ANI_ERR_UNSUPPORTED;
+  if (mode == 1 && (pbc || n_conf + 1 > max_bins)) return ANI_ERR_UNSUPPORTED;
+  if (mode != 0 && mode != 1) return ANI_ERR_BAD_ARG;
+  if (pbc && !cell) return ANI_ERR_BAD_ARG;
+  const long long n_ll = (long long)n_conf * n_per_conf;
+  if (n_ll >= (1ll << ANI_IMG_SHIFT)) return ANI_ERR_UNSUPPORTED;
+  const int n = (int)n_ll;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* bin_of = scratch_i32;
+  int32_t* slot = scratch_i32 + n;
+  int32_t* tmp_list = scratch_i32 + 2 * (size_t)n;
+  int32_t* bin_count = scratch_i32 + 3 * (size_t)n;
+  cudaMemsetAsync(bin_count, 0, sizeof(int32_t) * (size_t)(max_bins + 1), st);
+  k_grid_setup<<<1, 1024, 0, st>>>(coords, species, n, n_conf, n_per_conf, cell, pbc, mode, cutoff, max_bins,
+                                   grid, status);
+  const int nb = (n + 255) / 256;
+  k_bin_assign<<<nb, 256, 0, st>>>(coords, species, n, grid, bin_of, slot, bin_count);
+  k_bin_scan<<<1, 1024, 0, st>>>(bin_count, grid, bin_start);
+  k_bin_scatter<<<nb, 256, 0, st>>>(n, bin_of, slot, bin_start, tmp_list);
+  k_bin_finalize<<<nb, 256, 0, st>>>(coords, species, n, grid, bin_of, bin_start, tmp_list, sorted_orig,
+                                     orig_to_sorted, reinterpret_cast<float4*>(spos), sbin);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_species_layout(const float* spos, const ani_grid* grid, int n, int lo, int hi,
+                                       int num_species, int rows_cap, int32_t* row_of, int32_t* row_atom,
+                                       int32_t* tile_species, int32_t* layout_info, int32_t* scratch_i32,
+                                       void* stream) {
+  if (!spos || !grid || !row_of || !row_atom || !tile_species || !layout_info || !scratch_i32)
+    return ANI_ERR_BAD_ARG;
+  if (num_species < 1 || num_species > ANI_MAX_SPECIES || lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
+  if (rows_cap % ANI_TILE_ROWS != 0) return ANI_ERR_BAD_ARG;
+  // worst case rows: every species block rounds up by (almost) one tile
+  if ((long long)rows_cap < (long long)(hi - lo) + (long long)num_species * (ANI_TILE_ROWS - 1))
+    return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_chunks = max(1, (hi - lo + LAYOUT_CHUNK - 1) / LAYOUT_CHUNK);
+  int32_t* chunk_hist = scratch_i32;
+  int32_t* species_base = scratch_i32 + (size_t)(n_chunks + 1) * ANI_MAX_SPECIES;
+  const float4* sp4 = reinterpret_cast<const float4*>(spos);
+  k_layout_count<<<n_chunks, LAYOUT_CHUNK, 0, st>>>(sp4, grid, lo, hi, num_species, chunk_hist);
+  k_layout_scan<<<1, 1024, 0, st>>>(n_chunks, num_species, rows_cap, chunk_hist, species_base, tile_species,
+                                    row_atom, layout_info);
+  k_layout_assign<<<n_chunks, LAYOUT_CHUNK, 0, st>>>(sp4, grid, lo, hi, num_species, chunk_hist, species_base,
+                                                     row_of, row_atom);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}

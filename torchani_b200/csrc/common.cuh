@@ -1,0 +1,79 @@
+// Shared device helpers for the B200-native ANI hot path (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ani_b200.h"
+
+#define ANI_WARP 32
+#define ANI_FULL_MASK 0xffffffffu
+#define ANI_IMG_SHIFT 26                       // neighbour word: sorted index | image code << 26
+#define ANI_IDX_MASK ((1u << ANI_IMG_SHIFT) - 1u)
+
+namespace ani {
+
+// thread-local record of the last CUDA error (returned through the C-ABI)
+void set_cuda_error(cudaError_t e);
+#define ANI_CUDA_CHECK_LAUNCH()                         \
+  do {                                                  \
+    cudaError_t e__ = cudaGetLastError();               \
+    if (e__ != cudaSuccess) {                           \
+      ani::set_cuda_error(e__);                         \
+      return ANI_ERR_CUDA;                              \
+    }                                                   \
+  } while (0)
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ANI_FULL_MASK, v, o);
+  return v;
+}
+
+// index of the unordered species pair (a, b) in the row-major upper triangle of an SxS
+// matrix (aev/_computer.py:184-191 == csrc/aev.cu:23-29)
+__device__ __forceinline__ int pair_index(int a, int b, int S) {
+  int lo = min(a, b), hi = max(a, b);
+  return lo * (2 * S - lo + 1) / 2 + (hi - lo);
+}
+
+// cutoff function and derivative (cutoffs.py:70-101; derivative forms as aev.cu:141-178)
+__device__ __forceinline__ float cutoff_value(float r, float rc, int kind) {
+  if (kind == 0) return 0.5f * cosf(r * (3.14159265358979323846f / rc)) + 0.5f;
+  float x = r / rc;
+  float den = fmaxf(1e-10f, 1.0f - x * x);
+  return expf(1.0f - 1.0f / den);
+}
+
+__device__ __forceinline__ void cutoff_value_grad(float r, float rc, int kind, float& f, float& df) {
+  if (kind == 0) {
+    float s, c;
+    float a = 3.14159265358979323846f / rc;
+    sincosf(r * a, &s, &c);
+    f = 0.5f * c + 0.5f;
+    df = -0.5f * a * s;
+  } else {
+    float x = r / rc;
+    float one_m = 1.0f - x * x;
+    if (one_m > 1e-10f) {
+      f = expf(1.0f - 1.0f / one_m);
+      df = f * (-2.0f * x / (rc * one_m * one_m));
+    } else {
+      f = expf(1.0f - 1e10f);
+      df = 0.0f;
+    }
+  }
+}
+
+// image code (0..26) -> lattice shift vector.  code = (wx+1)*9 + (wy+1)*3 + (wz+1)
+__device__ __forceinline__ float3 image_shift(const ani_grid& g, int code) {
+  float wx = (float)(code / 9 - 1), wy = (float)((code / 3) % 3 - 1), wz = (float)(code % 3 - 1);
+  float3 s;
+  s.x = wx * g.cell[0] + wy * g.cell[3] + wz * g.cell[6];
+  s.y = wx * g.cell[1] + wy * g.cell[4] + wz * g.cell[7];
+  s.z = wx * g.cell[2] + wy * g.cell[5] + wz * g.cell[8];
+  return s;
+}
+
+}  // namespace ani

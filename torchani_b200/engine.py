@@ -1,0 +1,349 @@
+"""Host side of the fused hot path: owns the device workspaces (the C-ABI never allocates) and
+sequences the kernels of ``libani_b200.so`` on the current CUDA stream.
+
+One step  =  bucket grid -> species layout -> fused neighbour search + AEV -> ensemble MLP
+forward + backward-to-AEV -> AEV backward (dE/dcoords) -> energy reduction.  No host
+synchronisation happens inside a step; device-side error conditions accumulate in a status
+word that is checked when results are read (``Engine.check_status``).
+
+PyTorch is used only for device memory, streams and (in ``parallel.py``) torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import typing as tp
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import AEVParams, Grid, MLPModel, check, ptr
+
+TILE = _lib.ANI_TILE_ROWS
+
+
+def _f32(v: float) -> float:
+    return float(np.float32(v))
+
+
+class AEVConstants(tp.NamedTuple):
+    """The numbers that define an ANI AEV (see aev/_computer.py:499-600 in the reference)."""
+
+    num_species: int
+    rcr: float
+    rca: float
+    eta_r: float
+    shf_r: tp.Tuple[float, ...]
+    eta_a: float
+    zeta: float
+    shf_a: tp.Tuple[float, ...]
+    shf_z: tp.Tuple[float, ...]
+    cutoff_fn: str = "cosine"
+
+    @property
+    def radial_len(self) -> int:
+        return self.num_species * len(self.shf_r)
+
+    @property
+    def angular_len(self) -> int:
+        return self.num_species * (self.num_species + 1) // 2 * len(self.shf_a) * len(self.shf_z)
+
+    @property
+    def out_dim(self) -> int:
+        return self.radial_len + self.angular_len
+
+    def to_struct(self) -> AEVParams:
+        if self.cutoff_fn not in ("cosine", "smooth"):
+            raise ValueError(f"cutoff function {self.cutoff_fn!r} is not supported by the B200 kernels")
+        if (len(self.shf_a), len(self.shf_z)) not in ((8, 4), (4, 8)):
+            raise ValueError("the B200 AEV kernels need ShfA x ShfZ = 8x4 (ANI-2x) or 4x8 (ANI-1x)")
+        if len(self.shf_r) > _lib.ANI_MAX_SHFR or self.num_species > _lib.ANI_MAX_SPECIES:
+            raise ValueError("too many radial shifts / species for the B200 kernels")
+        p = AEVParams()
+        p.rcr, p.rca = self.rcr, self.rca
+        # the reference keeps eta/zeta/shifts as float32 buffers (aev/_terms.py:153-156,288-292)
+        p.eta_r, p.eta_a, p.zeta = _f32(self.eta_r), _f32(self.eta_a), _f32(self.zeta)
+        p.n_shf_r, p.n_shf_a, p.n_shf_z = len(self.shf_r), len(self.shf_a), len(self.shf_z)
+        p.num_species = self.num_species
+        p.cutoff_kind = 0 if self.cutoff_fn == "cosine" else 1
+        for k, v in enumerate(self.shf_r):
+            p.shf_r[k] = _f32(v)
+        for k, v in enumerate(self.shf_a):
+            p.shf_a[k] = _f32(v)
+        for k, v in enumerate(self.shf_z):
+            p.cos_z[k] = math.cos(_f32(v))
+            p.sin_z[k] = math.sin(_f32(v))
+        return p
+
+
+def _linspace(start: float, stop: float, steps: int) -> tp.Tuple[float, ...]:
+    return tuple(start + ((stop - start) / steps) * j for j in range(steps))  # utils.py:101-107
+
+
+def constants_2x(num_species: int = 7, cutoff_fn: str = "cosine") -> AEVConstants:
+    a0 = math.pi / 4 / 2
+    return AEVConstants(num_species, 5.1, 3.5, 19.7, _linspace(0.8, 5.1, 16), 12.5, 14.1,
+                        _linspace(0.8, 3.5, 8), _linspace(a0, math.pi + a0, 4), cutoff_fn)
+
+
+def constants_1x(num_species: int = 4, cutoff_fn: str = "cosine") -> AEVConstants:
+    a0 = math.pi / 8 / 2
+    return AEVConstants(num_species, 5.2, 3.5, 16.0, _linspace(0.9, 5.2, 16), 8.0, 32.0,
+                        _linspace(0.9, 3.5, 4), _linspace(a0, math.pi + a0, 8), cutoff_fn)
+
+
+class PackedNetworks:
+    """Device-resident, kernel-layout copy of an ensemble of per-element MLPs.
+
+    ``weights[member][species_index] = [(W [out,in], b [out]) x 4]`` in ``torch.nn.Linear``
+    layout (nn/_core.py:117-149).  All members must share the layer widths of a species.
+    """
+
+    def __init__(self, weights: tp.Sequence[tp.Sequence[tp.Sequence[tp.Tuple[Tensor, Tensor]]]],
+                 in_dim: int, device: torch.device, celu_alpha: float = 0.1):
+        self.device = torch.device(device)
+        M = len(weights)
+        S = len(weights[0])
+        if not (1 <= M <= _lib.ANI_MAX_MEMBERS) or not (1 <= S <= _lib.ANI_MAX_SPECIES):
+            raise ValueError("unsupported number of ensemble members / species")
+        self.num_members, self.num_species, self.in_dim = M, S, in_dim
+        self.ldx = (in_dim + 31) // 32 * 32
+        self.celu_alpha = celu_alpha
+        self.dims: tp.List[tp.Tuple[int, int, int]] = []
+        self._keep: tp.List[Tensor] = []
+        self.model = MLPModel()
+        mdl = self.model
+        mdl.num_species, mdl.num_members, mdl.in_dim, mdl.ldx = S, M, in_dim, self.ldx
+        mdl.celu_alpha = celu_alpha
+        f32 = dict(dtype=torch.float32, device=self.device)
+        for s in range(S):
+            layers0 = weights[0][s]
+            if len(layers0) != 4:
+                raise ValueError("the B200 MLP kernels support exactly 3 hidden layers + 1 output")
+            h1, h2, h3 = (int(layers0[k][0].shape[0]) for k in range(3))
+            if int(layers0[3][0].shape[0]) != 1:
+                raise ValueError("out_dim != 1 is not supported")
+            if layers0[0][0].shape[1] != in_dim:
+                raise ValueError("first layer width does not match the AEV length")
+            if any(h % 16 for h in (h1, h2, h3)):
+                raise ValueError("hidden widths must be multiples of 16")
+            self.dims.append((h1, h2, h3))
+            W = [[weights[m][s][k][0].detach().to(**f32) for m in range(M)] for k in range(4)]
+            Bv = [[weights[m][s][k][1].detach().to(**f32) for m in range(M)] for k in range(4)]
+            for m in range(M):
+                if tuple(W[0][m].shape) != (h1, in_dim) or tuple(W[1][m].shape) != (h2, h1) \
+                        or tuple(W[2][m].shape) != (h3, h2) or tuple(W[3][m].shape) != (1, h3):
+                    raise ValueError("all ensemble members must share the layer widths of an element")
+            w1n = torch.zeros(M * h1, self.ldx, **f32)
+            w1n[:, :in_dim] = torch.cat(W[0], 0)
+            t = {
+                "w1": w1n.t().contiguous(),                                   # [ldx][M*h1]
+                "b1": torch.cat(Bv[0]).contiguous(),
+                "w2": torch.stack([w.t().contiguous() for w in W[1]]).contiguous(),   # [M][h1][h2]
+                "b2": torch.cat(Bv[1]).contiguous(),
+                "w3": torch.stack([w.t().contiguous() for w in W[2]]).contiguous(),   # [M][h2][h3]
+                "b3": torch.cat(Bv[2]).contiguous(),
+                "w4": torch.cat(W[3], 0).contiguous(),                        # [M][h3]
+                "b4": torch.cat(Bv[3]).contiguous(),                          # [M]
+                "w3n": torch.stack(W[2]).contiguous(),                        # [M][h3][h2]
+                "w2n": torch.stack(W[1]).contiguous(),                        # [M][h2][h1]
+                "w1n": w1n.contiguous(),                                      # [M*h1][ldx]
+            }
+            sp = mdl.sp[s]
+            sp.h1, sp.h2, sp.h3 = h1, h2, h3
+            for k, v in t.items():
+                self._keep.append(v)
+                setattr(sp, k, v.data_ptr())
+        mdl.h1_max = max(d[0] for d in self.dims)
+        mdl.h2_max = max(d[1] for d in self.dims)
+        mdl.h3_max = max(d[2] for d in self.dims)
+        self.set_active_members(list(range(M)))
+
+    def set_active_members(self, idxs: tp.Sequence[int]) -> None:
+        """nn/_core.py:99-110: the ensemble output is the mean over the active members."""
+        for i in idxs:
+            if not 0 <= i < self.num_members:
+                raise IndexError(f"Idx {i} should be 0 <= idx < {self.num_members}")
+        self.active = list(idxs)
+        for m in range(_lib.ANI_MAX_MEMBERS):
+            self.model.member_scale[m] = (1.0 / len(self.active)) if m in self.active else 0.0
+
+    @property
+    def ld(self) -> tp.Tuple[int, int, int]:
+        M = self.num_members
+        return M * self.model.h1_max, M * self.model.h2_max, M * self.model.h3_max
+
+    def flops_per_atom(self, species_index: int, backward: bool = True) -> float:
+        h1, h2, h3 = self.dims[species_index]
+        macs = self.in_dim * h1 + h1 * h2 + h2 * h3 + h3
+        return 2.0 * macs * self.num_members * (2 if backward else 1)
+
+
+class Workspace:
+    """All device buffers for one (n_conf, n_per_conf) problem shape."""
+
+    def __init__(self, n_conf: int, n_per_conf: int, num_species: int, ldx: int, ld: tp.Tuple[int, int, int],
+                 num_members: int, nbr_cap: int, device: torch.device, owned_cap: tp.Optional[int] = None):
+        n = n_conf * n_per_conf
+        self.n, self.n_conf, self.n_per_conf = n, n_conf, n_per_conf
+        owned = n if owned_cap is None else min(n, owned_cap)
+        self.rows_cap = (owned + num_species * (TILE - 1) + TILE - 1) // TILE * TILE
+        self.max_bins = max(64, n + 2) if n_conf == 1 else n_conf + 2
+        i32 = dict(dtype=torch.int32, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        self.grid = torch.zeros(C.sizeof(Grid) // 4, **i32)
+        self.status = torch.zeros(1, **i32)
+        self.bin_start = torch.zeros(self.max_bins + 2, **i32)
+        self.sorted_orig = torch.zeros(n, **i32)
+        self.orig_to_sorted = torch.zeros(n, **i32)
+        self.spos = torch.zeros(n, 4, **f32)
+        self.sbin = torch.zeros(n, **i32)
+        self.scratch = torch.zeros(3 * n + self.max_bins + 2 + (n // 256 + 3) * 8 + 64, **i32)
+        self.row_of = torch.zeros(n, **i32)
+        self.row_atom = torch.zeros(self.rows_cap, **i32)
+        self.tile_species = torch.zeros(self.rows_cap // TILE, **i32)
+        self.layout_info = torch.zeros(4, **i32)
+        self.nbr_cap = nbr_cap
+        self.nbr_cnt = torch.zeros(n, **i32)
+        self.nbr_list = torch.zeros(n * nbr_cap, **i32)
+        self.x = torch.zeros(self.rows_cap, ldx, **f32)
+        self.act1 = torch.zeros(self.rows_cap, ld[0], **f32)
+        self.act2 = torch.zeros(self.rows_cap, ld[1], **f32)
+        self.act3 = torch.zeros(self.rows_cap, ld[2], **f32)
+        self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
+        self.species_i32 = torch.zeros(n, **i32)
+        self.coords = torch.zeros(n, 3, **f32)
+        self.cell = torch.zeros(9, **f32)
+        self.grad = torch.zeros(n, 3, **f32)
+        self.atomic = torch.zeros(n, **f32)
+        self.member_atomic = torch.zeros(num_members, n, **f32)
+        self.energies = torch.zeros(n_conf, dtype=torch.float64, device=device)
+
+
+class StepResult(tp.NamedTuple):
+    energies: Tensor          # (C,) float64: NN energy + self energies of the owned atoms
+    atomic_energies: Tensor   # (C, A) float32: NN atomic energies (ensemble mean), 0 for padding
+    member_atomic: Tensor     # (M, C, A) float32 per-member NN atomic energies
+    grad: tp.Optional[Tensor]  # (C, A, 3) float32 dE/dcoords (forces = -grad) or None
+
+
+class Engine:
+    """Fused ANI energy(+force) step on one GPU.  ``lo_frac/hi_frac`` select the slice of
+    bucket-sorted atoms this engine owns (multi-GPU sharding, see parallel.py)."""
+
+    def __init__(self, consts: AEVConstants, nets: PackedNetworks, sae: tp.Optional[tp.Sequence[float]] = None,
+                 nbr_cap: int = 128):
+        if nets.in_dim != consts.out_dim:
+            raise ValueError("network input width != AEV length")
+        if nets.num_species != consts.num_species:
+            raise ValueError("network / AEV species mismatch")
+        self.consts, self.nets = consts, nets
+        self.device = nets.device
+        self.params = consts.to_struct()
+        self.nbr_cap = nbr_cap
+        self.sae = None
+        if sae is not None:
+            self.sae = torch.tensor(list(sae), dtype=torch.float64, device=self.device)
+        self._ws: tp.Dict[tp.Tuple[int, int], Workspace] = {}
+        self.lib = _lib.lib()
+        self.launches_per_step = 0
+
+    # -- workspaces ------------------------------------------------------------------------
+    def workspace(self, n_conf: int, n_per_conf: int) -> Workspace:
+        key = (n_conf, n_per_conf)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = Workspace(n_conf, n_per_conf, self.consts.num_species, self.nets.ldx, self.nets.ld,
+                           self.nets.num_members, self.nbr_cap, self.device)
+            self._ws[key] = ws
+        return ws
+
+    # -- one step --------------------------------------------------------------------------
+    def step(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None, pbc: bool = False,
+             want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1)) -> StepResult:
+        """species (C, A) int (element indices, -1 padding), coords (C, A, 3) on this device.
+        ``shard = (rank, world)``: only atoms whose bucket-sorted position falls into this
+        rank's slice are evaluated; gradients/energies are partial sums to be all-reduced."""
+        dev = self.device
+        n_conf, n_per_conf = species.shape
+        if coords.shape != (n_conf, n_per_conf, 3):
+            raise ValueError("coords must have shape (C, A, 3)")
+        if species.device != dev or coords.device != dev:
+            raise ValueError(f"inputs must live on {dev} (the B200 engine has no CPU path)")
+        if pbc and cell is None:
+            raise ValueError("If pbc is not None, cell should be present")
+        if pbc and n_conf != 1:
+            raise NotImplementedError("periodic batches (C > 1 with one shared cell) are not supported yet")
+        ws = self.workspace(n_conf, n_per_conf)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        L = self.lib
+        n = ws.n
+        ws.species_i32.copy_(species.reshape(-1))
+        ws.coords.copy_(coords.reshape(-1, 3))
+        cell_ptr = None
+        if pbc:
+            ws.cell.copy_(cell.reshape(-1))
+            cell_ptr = ptr(ws.cell)
+        mode = 0 if n_conf == 1 else 1
+        check(L.ani_b200_build_cells(ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr,
+                                     int(bool(pbc)), mode, self.consts.rcr, ws.max_bins, ptr(ws.grid),
+                                     ptr(ws.bin_start), ptr(ws.sorted_orig), ptr(ws.orig_to_sorted),
+                                     ptr(ws.spos), ptr(ws.sbin), ptr(ws.scratch), ptr(ws.status), st),
+              "build_cells")
+        rank, world = shard
+        lo = (n * rank) // world
+        hi = (n * (rank + 1)) // world
+        check(L.ani_b200_species_layout(ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species,
+                                        ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
+                                        ptr(ws.layout_info), ptr(ws.scratch), st), "species_layout")
+        check(L.ani_b200_aev_forward(C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos),
+                                     ptr(ws.sbin), n, lo, hi, ptr(ws.row_of), ptr(ws.x), self.nets.ldx,
+                                     ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st),
+              "aev_forward")
+        check(L.ani_b200_mlp_forward_backward(C.byref(self.nets.model), ptr(ws.x), ws.rows_cap,
+                                              ptr(ws.tile_species), ptr(ws.row_atom), ptr(ws.act1),
+                                              ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad), st),
+              "mlp_forward_backward")
+        grad = None
+        if want_grad:
+            ws.grad.zero_()
+            check(L.ani_b200_aev_backward(C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
+                                          n, lo, hi, ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt),
+                                          ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.grad), ptr(ws.status), st),
+                  "aev_backward")
+            grad = ws.grad.view(n_conf, n_per_conf, 3)
+        check(L.ani_b200_reduce_energies(C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of),
+                                         ptr(ws.orig_to_sorted), ptr(ws.species_i32), n, lo, hi, n_conf,
+                                         n_per_conf, ptr(self.sae), ptr(ws.atomic), ptr(ws.member_atomic),
+                                         ptr(ws.energies), st), "reduce_energies")
+        # kernels launched by this library in one step (memsets excluded):
+        #   build_cells 5, layout 3, aev fwd 1, mlp 4 (+3 bwd), aev bwd 1, reduce 1
+        self.launches_per_step = 5 + 3 + 1 + 4 + (4 if want_grad else 0) + 1
+        return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
+                          ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
+
+    # -- status ----------------------------------------------------------------------------
+    def check_status(self, ws: tp.Optional[Workspace] = None) -> None:
+        """Raise for device-side conditions (one D2H read; call when results are consumed)."""
+        for w in ([ws] if ws is not None else list(self._ws.values())):
+            code = int(w.status.item())
+            if code == 0:
+                continue
+            w.status.zero_()
+            if code & _lib.STATUS_CELL_TOO_SMALL:
+                raise RuntimeError("Cell is too small to perform pbc calculations")  # neighbors.py:402-403
+            if code & _lib.STATUS_NBR_OVERFLOW:
+                raise RuntimeError(f"an atom has more than nbr_cap={w.nbr_cap} neighbours within Rcr; "
+                                   "construct the engine with a larger nbr_cap (<= 256)")
+            if code & _lib.STATUS_ANG_OVERFLOW:
+                raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within Rca")
+            if code & _lib.STATUS_PAIR_OVERFLOW:
+                raise RuntimeError("half neighbour list capacity exceeded")
+
+    def grid_info(self, ws: Workspace) -> Grid:
+        g = Grid()
+        raw = ws.grid.cpu().numpy().tobytes()
+        C.memmove(C.byref(g), raw, C.sizeof(Grid))
+        return g

@@ -1,0 +1,282 @@
+"""ANI model assembly with the interface of ``torchani.arch.ANI`` / ``torchani.models``.
+
+``ANI.forward((species, coords), cell, pbc, charge, atomic, ensemble_values)`` mirrors
+arch.py:302-349 and returns ``SpeciesEnergies``; energies carry an autograd edge to ``coords``,
+so ``torch.autograd.grad(energy, coords)`` (ase.py:159-162, grad.py:57-62) works unchanged.  For
+the plain energy(+force) call the whole step runs through the fused ``Engine`` (one launch
+sequence, forces produced in the forward pass and stashed for backward); ``atomic=True`` /
+``ensemble_values=True`` use the same engine outputs.
+
+Pretrained ANI parameters are not shipped (the reference downloads them, arch.py:1185-1220):
+``ANI2x()`` / ``ANI1x()`` build the published architectures with seeded random weights, and
+``load_state_dict`` accepts the reference's state-dict keys.  ``from_torchani(model)`` converts
+an existing ``torchani.arch.ANI`` instance (weights, AEV constants, self energies).
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+from torch import Tensor
+
+from .aev import AEVComputer
+from .engine import Engine, StepResult
+from .neighbors import NeighborlistArg, _validate_inputs
+from .nn import (ANINetworks, ATOMIC_NUMBER, AtomicContainer, AtomicNetwork, Ensemble, SpeciesConverter,
+                 SpeciesEnergies)
+
+SYMBOLS_1X = ("H", "C", "N", "O")
+SYMBOLS_2X = ("H", "C", "N", "O", "S", "F", "Cl")
+# constants.py:88-96 (wb97x-631gd ground-state atomic energies, Hartree)
+GSAES_WB97X_631GD = {"H": -0.4993212, "C": -37.8338334, "N": -54.5732825, "O": -75.0424519,
+                     "S": -398.0814169, "F": -99.6949007, "Cl": -460.1167008}
+
+
+class SelfEnergy(torch.nn.Module):
+    """Constant per-element energies (sae.py:16-64).  The fused engine adds them in float64."""
+
+    def __init__(self, symbols: tp.Sequence[str], self_energies: tp.Sequence[float]):
+        super().__init__()
+        if len(symbols) != len(self_energies):
+            raise ValueError("one self energy per symbol is required")
+        self.symbols = tuple(symbols)
+        self.register_buffer("self_energies", torch.tensor(list(self_energies), dtype=torch.float64))
+        self._enabled = True
+
+    @classmethod
+    def with_gsaes(cls, symbols: tp.Sequence[str], functional: str = "wb97x", basis_set: str = "631gd"):
+        if (functional.lower(), basis_set.lower()) != ("wb97x", "631gd"):
+            raise ValueError("only the wb97x-631gd GSAEs are bundled")
+        return cls(symbols, [GSAES_WB97X_631GD[s] for s in symbols])
+
+    def forward(self, elem_idxs: Tensor, atomic: bool = False) -> Tensor:
+        e = self.self_energies.to(elem_idxs.device)[elem_idxs.clamp(min=0)].masked_fill(elem_idxs == -1, 0.0)
+        return e if atomic else e.sum(dim=-1)
+
+
+class _FusedEnergy(torch.autograd.Function):
+    """coords -> (energies (C,), atomic NN energies (C, A), member atomic (M, C, A)); the
+    gradient of the ensemble-mean energy is produced by the forward launch sequence."""
+
+    @staticmethod
+    def forward(ctx, coords: Tensor, species: Tensor, cell: tp.Optional[Tensor], pbc: bool, engine: Engine,
+                want_grad: bool):
+        res: StepResult = engine.step(species, coords.detach(), cell, pbc, want_grad=want_grad)
+        ctx.want_grad = want_grad
+        if want_grad:
+            ctx.save_for_backward(res.grad.clone())
+        ctx.mark_non_differentiable(res.member_atomic)
+        return res.energies.clone(), res.atomic_energies.clone(), res.member_atomic.clone()
+
+    @staticmethod
+    def backward(ctx, g_energy, g_atomic, g_member):
+        if not ctx.want_grad:
+            raise RuntimeError("energies were computed without forces (coords.requires_grad was False)")
+        (grad,) = ctx.saved_tensors
+        out = None
+        if g_energy is not None:
+            out = grad * g_energy.to(grad.dtype).view(-1, 1, 1)
+        if g_atomic is not None and bool((g_atomic != 0).any()):
+            raise NotImplementedError("per-atom upstream gradients are not supported by the fused engine; "
+                                      "use AEVComputer + Ensemble modules directly")
+        return out, None, None, None, None, None
+
+
+class ANI(torch.nn.Module):
+    r"""ANI-style neural network interatomic potential (interface of arch.py:90-381)."""
+
+    def __init__(self, symbols: tp.Sequence[str], aev_computer: AEVComputer, neural_networks: AtomicContainer,
+                 energy_shifter: SelfEnergy, periodic_table_index: bool = True):
+        super().__init__()
+        self.register_buffer("atomic_numbers", torch.tensor([ATOMIC_NUMBER[e] for e in symbols], dtype=torch.long))
+        assert len(energy_shifter.self_energies) == len(symbols)
+        assert aev_computer.num_species == len(symbols)
+        assert neural_networks.num_species == len(symbols)
+        self.symbols = tuple(symbols)
+        self.aev_computer = aev_computer
+        self.neural_networks = neural_networks
+        self.neighborlist = aev_computer.neighborlist
+        self.energy_shifter = energy_shifter
+        self.species_converter = SpeciesConverter(symbols)
+        self.cutoff = aev_computer.radial.cutoff
+        self.periodic_table_index = periodic_table_index
+        self._engine: tp.Optional[Engine] = None
+        self._engine_key: tp.Any = None
+
+    # -- reference conveniences (arch.py:132-146,253-275) ----------------------------------
+    def set_active_members(self, idxs: tp.List[int]) -> None:
+        self.neural_networks.set_active_members(idxs)
+
+    def set_strategy(self, strategy: str) -> None:
+        self.aev_computer.set_strategy(strategy)
+
+    def __len__(self) -> int:
+        return self.neural_networks.get_active_members_num()
+
+    def __getitem__(self, idx: int) -> "ANI":
+        import copy
+        nets = self.neural_networks
+        if not isinstance(nets, Ensemble):
+            raise ValueError("Only ensembles can be indexed")
+        return ANI(self.symbols, copy.deepcopy(self.aev_computer), copy.deepcopy(nets[idx]),
+                   copy.deepcopy(self.energy_shifter), self.periodic_table_index)
+
+    def to_infer_model(self, use_mnp: bool = False) -> "ANI":
+        return self
+
+    # -- fused engine ----------------------------------------------------------------------
+    def engine(self, device: torch.device) -> Engine:
+        nets = self.neural_networks.packed(device)
+        key = (str(device), id(nets))
+        if self._engine is None or self._engine_key != key:
+            sae = self.energy_shifter.self_energies.tolist() if self.energy_shifter._enabled else None
+            self._engine = Engine(self.aev_computer.constants, nets, sae, nbr_cap=self.aev_computer.nbr_cap)
+            self._engine_key = key
+        return self._engine
+
+    @staticmethod
+    def _check_inputs(elem_idxs: Tensor, coords: Tensor, charge: int = 0) -> None:
+        assert elem_idxs.dim() == 2
+        assert coords.shape == (elem_idxs.shape[0], elem_idxs.shape[1], 3)
+        assert charge == 0, "Model only supports neutral molecules"
+
+    def forward(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                pbc: tp.Optional[Tensor] = None, charge: int = 0, atomic: bool = False,
+                ensemble_values: bool = False) -> SpeciesEnergies:
+        species, coords = species_coordinates
+        self._check_inputs(species, coords, charge)
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        _validate_inputs(self.cutoff, elem_idxs, coords, cell, pbc)
+        eng = self.engine(coords.device)
+        e, e_atomic, e_member = _FusedEnergy.apply(coords, elem_idxs, cell, pbc is not None, eng,
+                                                   bool(coords.requires_grad))
+        energies: Tensor
+        if ensemble_values:
+            active = self.neural_networks.active_members_idxs
+            energies = e_member[active].to(coords.dtype)
+            if self.energy_shifter._enabled:
+                energies = energies + self.energy_shifter(elem_idxs, atomic=True).to(coords.dtype)
+            if not atomic:
+                energies = energies.sum(-1)
+        elif atomic:
+            energies = e_atomic.to(coords.dtype)
+            if self.energy_shifter._enabled:
+                energies = energies + self.energy_shifter(elem_idxs, atomic=True).to(coords.dtype)
+        else:
+            energies = e.to(coords.dtype)
+        return SpeciesEnergies(elem_idxs, energies)
+
+    def energies_f64(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                     pbc: tp.Optional[Tensor] = None) -> Tensor:
+        """Total energies in float64 as accumulated on the device (the float32 tensor returned by
+        ``forward`` loses ~3e-3 Ha at |E| ~ 2.5e4 Ha)."""
+        species, coords = species_coordinates
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        eng = self.engine(coords.device)
+        return eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=False).energies.clone()
+
+    def energies_and_forces(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None,
+                            pbc: tp.Optional[Tensor] = None) -> tp.Tuple[Tensor, Tensor]:
+        """grad.py:263-290 without the autograd round trip: (energies f64 (C,), forces f32 (C,A,3))."""
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        eng = self.engine(coords.device)
+        res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True)
+        return res.energies.clone(), -res.grad
+
+    # -- state dicts of the reference (arch.py:278-290) ------------------------------------
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs) -> None:
+        for old in list(state_dict.keys()):
+            new = old.replace("potentials.nnp.aev_computer.", "aev_computer.")
+            new = new.replace("potentials.nnp.neural_networks.", "neural_networks.")
+            new = new.replace("radial_terms", "radial").replace("angular_terms", "angular")
+            new = new.replace(".EtaR", ".eta").replace(".ShfR", ".shifts").replace(".EtaA", ".eta")
+            new = new.replace(".Zeta", ".zeta").replace(".ShfA", ".shifts").replace(".ShfZ", ".sections")
+            if new != old:
+                state_dict[new] = state_dict.pop(old).reshape(-1) if any(
+                    new.endswith(k) for k in (".eta", ".zeta", ".shifts", ".sections")) else state_dict.pop(old)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+def _assemble(symbols, aev_ctor, net_ctor, ensemble_size: int, neighborlist: NeighborlistArg,
+              periodic_table_index: bool, seed: tp.Optional[int], device) -> ANI:
+    if seed is not None:
+        torch.manual_seed(seed)
+    aevc = aev_ctor(num_species=len(symbols), neighborlist=neighborlist)
+    members = [net_ctor(symbols, aevc.out_dim) for _ in range(ensemble_size)]
+    nets: AtomicContainer = Ensemble(members) if ensemble_size > 1 else members[0]
+    model = ANI(symbols, aevc, nets, SelfEnergy.with_gsaes(symbols), periodic_table_index)
+    model.requires_grad_(False)
+    return model.to(device) if device is not None else model
+
+
+def ANI2x(model_index: tp.Optional[int] = None, neighborlist: NeighborlistArg = "cell_list",
+          periodic_table_index: bool = True, device=None, seed: tp.Optional[int] = 0) -> ANI:
+    """ANI-2x architecture (models.py:165-198): 7 elements, 1008-dim AEV, 8-member ensemble.
+    Weights are seeded random (no download in this environment)."""
+    model = _assemble(SYMBOLS_2X, AEVComputer.like_2x, ANINetworks.like_2x, 8, neighborlist,
+                      periodic_table_index, seed, device)
+    return model if model_index is None else model[model_index]
+
+
+def ANI1x(model_index: tp.Optional[int] = None, neighborlist: NeighborlistArg = "cell_list",
+          periodic_table_index: bool = True, device=None, seed: tp.Optional[int] = 0) -> ANI:
+    """ANI-1x architecture (models.py:105-131): 4 elements, 384-dim AEV, 8-member ensemble."""
+    model = _assemble(SYMBOLS_1X, AEVComputer.like_1x, ANINetworks.like_1x, 8, neighborlist,
+                      periodic_table_index, seed, device)
+    return model if model_index is None else model[model_index]
+
+
+def from_weight_lists(kind: str, weights, device=None, neighborlist: NeighborlistArg = "cell_list",
+                      periodic_table_index: bool = False) -> ANI:
+    """Build an ANI-1x / ANI-2x shaped model from ``weights[member][symbol] = [(W, b) x 4]``."""
+    symbols = SYMBOLS_2X if kind == "2x" else SYMBOLS_1X
+    aev_ctor = AEVComputer.like_2x if kind == "2x" else AEVComputer.like_1x
+    net_ctor = ANINetworks.like_2x if kind == "2x" else ANINetworks.like_1x
+    model = _assemble(symbols, aev_ctor, net_ctor, len(weights), neighborlist, periodic_table_index, None, None)
+    members = model.neural_networks.member_networks()
+    with torch.no_grad():
+        for net, w_m in zip(members, weights):
+            for s in symbols:
+                for (w_dst, b_dst), (w, b) in zip(net.atomics[s].linear_pairs(), w_m[s]):
+                    w_dst.copy_(w)
+                    b_dst.copy_(b)
+    return model.to(device) if device is not None else model
+
+
+def from_torchani(ref_model, device=None) -> ANI:
+    """Convert a ``torchani.arch.ANI`` instance (reference, e.g. ``torchani.models.ANI2x()``) into
+    the B200 model: same symbols, AEV constants, network weights and self energies."""
+    aevr = ref_model.potentials["nnp"].aev_computer
+    netr = ref_model.potentials["nnp"].neural_networks
+    symbols = tuple(netr.symbols)
+    cutoff_fn = getattr(aevr.radial.cutoff_fn, "_cuaev_name", "") or ""
+    if cutoff_fn not in ("cosine", "smooth"):
+        raise ValueError("only the cosine and smooth(order=2, eps=1e-10) cutoffs are supported")
+    aevc = AEVComputer.from_constants(
+        aevr.radial.cutoff, aevr.angular.cutoff, float(aevr.radial.eta), aevr.radial.shifts.tolist(),
+        float(aevr.angular.eta), float(aevr.angular.zeta), aevr.angular.shifts.tolist(),
+        aevr.angular.sections.tolist(), aevr.num_species, cutoff_fn=cutoff_fn)
+    ref_members = list(netr.members) if hasattr(netr, "members") else [netr]
+    members = []
+    for rm in ref_members:
+        mods = {}
+        for s in symbols:
+            ra = rm.atomics[s]
+            lins = list(ra.layers) + [ra.final_layer]
+            dims = [lins[0].in_features] + [l.out_features for l in lins]
+            an = AtomicNetwork(dims)
+            with torch.no_grad():
+                for (w_dst, b_dst), l in zip(an.linear_pairs(), lins):
+                    if l.bias is None:
+                        raise ValueError("bias-free networks are not supported")
+                    w_dst.copy_(l.weight)
+                    b_dst.copy_(l.bias)
+            mods[s] = an
+        members.append(ANINetworks(mods))
+    nets: AtomicContainer = Ensemble(members) if len(members) > 1 else members[0]
+    nets.set_active_members(list(netr.active_members_idxs))
+    sae = SelfEnergy(symbols, ref_model.energy_shifter.self_energies.double().tolist())
+    sae._enabled = bool(ref_model.energy_shifter._enabled)
+    model = ANI(symbols, aevc, nets, sae, ref_model.periodic_table_index)
+    model.requires_grad_(False)
+    return model.to(device) if device is not None else model

@@ -1,0 +1,192 @@
+"""Neighbour lists with the interface of ``torchani.neighbors`` (neighbors.py:13-18,140-166).
+
+``CellList`` / ``AllPairs`` / ``AdaptiveList`` all run the same B200 bucket-grid kernels
+(``ani_b200_build_cells`` + ``ani_b200_half_neighbor_*``): one conformer is bucketed on a grid
+(periodic or bounding box), a batch uses one bucket per conformer.  The result has the
+reference's format -- ``Neighbors(indices (2,P) int64 into the flattened atoms, distances (P,),
+diff_vectors (P,3) = x[idx0] - x[idx1] + shift)`` -- and carries autograd to ``coords`` the same
+way (neighbors.py:107-112).  Pair ORDER differs from the reference (it is not specified there
+either: the reference's argsort is unstable); compare as sets.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import typing as tp
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import Grid, check, ptr
+
+
+class Neighbors(tp.NamedTuple):
+    r"""Holds pairs of atoms that are neighbors (neighbors.py:13-18)."""
+
+    indices: Tensor  #: Long tensor with idxs of neighbor pairs. Shape ``(2, pairs)``
+    distances: Tensor  #: The associated pair distances. Shape is ``(pairs,)``
+    diff_vectors: Tensor  #: The associated difference vectors. Shape is ``(pairs, 3)``
+
+
+def discard_outside_cutoff(neighbors: Neighbors, cutoff: float) -> Neighbors:
+    r"""Discard neighbors with distances that lie outside of the given cutoff (neighbors.py:46-55)"""
+    keep = (neighbors.distances <= cutoff).nonzero().flatten()
+    return Neighbors(neighbors.indices.index_select(1, keep), neighbors.distances.index_select(0, keep),
+                     neighbors.diff_vectors.index_select(0, keep))
+
+
+def _validate_inputs(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor],
+                     pbc: tp.Optional[Tensor], supports_batches: bool = True) -> None:
+    # neighbors.py:918-949
+    if cutoff <= 0.0:
+        raise ValueError("Cutoff must be a strictly positive float")
+    if species.dim() != 2 or coords.shape != (species.shape[0], species.shape[1], 3):
+        raise ValueError("species must be (C, A) and coords (C, A, 3)")
+    if not supports_batches and coords.shape[0] != 1:
+        raise ValueError("This neighborlist doesn't support batches")
+    if pbc is not None:
+        if not bool(pbc.any()):
+            raise ValueError(
+                "pbc = torch.tensor([False, False, False]) is not supported anymore please use pbc = None"
+            )
+        if cell is None:
+            raise ValueError("If pbc is not None, cell should be present")
+        if not bool(pbc.all()):
+            raise ValueError("The B200 neighborlists don't support PBC only in some directions")
+    elif cell is not None:
+        raise ValueError("Cell is not supported if not using pbc")
+    if coords.device.type != "cuda":
+        raise ValueError("torchani_b200 runs on CUDA tensors only (there is no CPU path)")
+    if coords.dtype != torch.float32:
+        raise ValueError("torchani_b200 kernels are float32; got " + str(coords.dtype))
+
+
+class BucketGrid:
+    """Device buffers of one bucket-grid build (shared by the neighbour list and the AEV API)."""
+
+    def __init__(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor], pbc: bool, cutoff: float):
+        dev = coords.device
+        n_conf, n_per_conf = species.shape
+        if pbc and n_conf != 1:
+            raise NotImplementedError("periodic batches (C > 1 with one shared cell) are not supported yet")
+        n = n_conf * n_per_conf
+        self.n, self.n_conf, self.n_per_conf = n, n_conf, n_per_conf
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.max_bins = max(64, n + 2) if n_conf == 1 else n_conf + 2
+        self.grid = torch.zeros(C.sizeof(Grid) // 4, **i32)
+        self.status = torch.zeros(1, **i32)
+        self.bin_start = torch.zeros(self.max_bins + 2, **i32)
+        self.sorted_orig = torch.zeros(n, **i32)
+        self.orig_to_sorted = torch.zeros(n, **i32)
+        self.spos = torch.zeros(n, 4, dtype=torch.float32, device=dev)
+        self.sbin = torch.zeros(n, **i32)
+        scratch = torch.zeros(3 * n + self.max_bins + 2, **i32)
+        self.species_i32 = species.reshape(-1).to(torch.int32).contiguous()
+        coords_f = coords.detach().reshape(-1, 3).contiguous()
+        cell_f = None if cell is None else cell.detach().to(torch.float32).reshape(-1).contiguous()
+        self.stream = torch.cuda.current_stream(dev).cuda_stream
+        check(_lib.lib().ani_b200_build_cells(
+            ptr(coords_f), ptr(self.species_i32), n_conf, n_per_conf, ptr(cell_f), int(pbc),
+            0 if n_conf == 1 else 1, float(cutoff), self.max_bins, ptr(self.grid), ptr(self.bin_start),
+            ptr(self.sorted_orig), ptr(self.orig_to_sorted), ptr(self.spos), ptr(self.sbin), ptr(scratch),
+            ptr(self.status), self.stream), "build_cells")
+
+    def raise_on_status(self) -> None:
+        code = int(self.status.item())
+        if code & _lib.STATUS_CELL_TOO_SMALL:
+            raise RuntimeError("Cell is too small to perform pbc calculations")  # neighbors.py:402-403
+        if code & _lib.STATUS_NBR_OVERFLOW:
+            raise RuntimeError("neighbour capacity exceeded (raise nbr_cap, <= 256)")
+        if code & _lib.STATUS_ANG_OVERFLOW:
+            raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within the angular cutoff")
+        if code & _lib.STATUS_PAIR_OVERFLOW:
+            raise RuntimeError("half neighbour list capacity exceeded")
+
+
+def _half_list(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor],
+               pbc: tp.Optional[Tensor]) -> Neighbors:
+    g = BucketGrid(species, coords, cell, pbc is not None, cutoff)
+    L = _lib.lib()
+    n = g.n
+    dev = coords.device
+    pair_start = torch.zeros(2 * n + 2, dtype=torch.int32, device=dev)
+    check(L.ani_b200_half_neighbor_count(ptr(g.grid), ptr(g.bin_start), ptr(g.spos), ptr(g.sbin),
+                                         ptr(g.sorted_orig), n, float(cutoff), ptr(pair_start), g.stream),
+          "half_neighbor_count")
+    num_pairs = int(pair_start[n].item())  # the one host sync of this API (the reference has several)
+    g.raise_on_status()
+    idx = torch.empty(2, num_pairs, dtype=torch.int64, device=dev)
+    dist = torch.empty(num_pairs, dtype=torch.float32, device=dev)
+    diff = torch.empty(num_pairs, 3, dtype=torch.float32, device=dev)
+    if num_pairs:
+        check(L.ani_b200_half_neighbor_fill(ptr(g.grid), ptr(g.bin_start), ptr(g.spos), ptr(g.sbin),
+                                            ptr(g.sorted_orig), n, float(cutoff), ptr(pair_start), num_pairs,
+                                            idx[0].data_ptr(), idx[1].data_ptr(), ptr(dist), ptr(diff),
+                                            ptr(g.status), g.stream), "half_neighbor_fill")
+    if coords.requires_grad:
+        # same autograd edge as neighbors.py:107-112: diff = x[i0] - x[i1] + (constant shift)
+        flat = coords.reshape(-1, 3)
+        raw = flat.index_select(0, idx[0]) - flat.index_select(0, idx[1])
+        diff = raw + (diff - raw.detach())
+        dist = diff.norm(2, -1)
+    return Neighbors(idx, dist, diff)
+
+
+def cell_list(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None,
+              pbc: tp.Optional[Tensor] = None) -> Neighbors:
+    """neighbors.py:366-415 (single conformer)."""
+    _validate_inputs(cutoff, species, coords, cell, pbc, supports_batches=False)
+    return _half_list(cutoff, species, coords, cell, pbc)
+
+
+def all_pairs(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None,
+              pbc: tp.Optional[Tensor] = None) -> Neighbors:
+    """neighbors.py:187-212 (batches without PBC, one conformer with PBC).  Same pair set as the
+    reference's O(N^2) enumeration as long as the periodic cell is at least one cutoff wide."""
+    _validate_inputs(cutoff, species, coords, cell, pbc, supports_batches=True)
+    return _half_list(cutoff, species, coords, cell, pbc)
+
+
+class Neighborlist(torch.nn.Module):
+    r"""Base class for modules that compute pairs of neighbors (neighbors.py:140-166)."""
+
+    def forward(self, cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None,
+                pbc: tp.Optional[Tensor] = None) -> Neighbors:
+        raise NotImplementedError("Must be implemented by subclasses")
+
+
+class AllPairs(Neighborlist):
+    def forward(self, cutoff, species, coords, cell=None, pbc=None) -> Neighbors:
+        return all_pairs(cutoff, species, coords, cell, pbc)
+
+
+class CellList(Neighborlist):
+    def forward(self, cutoff, species, coords, cell=None, pbc=None) -> Neighbors:
+        return cell_list(cutoff, species, coords, cell, pbc)
+
+
+class AdaptiveList(Neighborlist):
+    """neighbors.py:317-363: the reference switches algorithm by size; the bucket grid adapts by
+    itself (one bucket for small systems), so this is the same kernel."""
+
+    def __init__(self, threshold: int = 190, threshold_nopbc: int = 1770) -> None:
+        super().__init__()
+        self._thresh, self._thresh_nopbc = threshold, threshold_nopbc
+
+    def forward(self, cutoff, species, coords, cell=None, pbc=None) -> Neighbors:
+        _validate_inputs(cutoff, species, coords, cell, pbc, supports_batches=False)
+        return _half_list(cutoff, species, coords, cell, pbc)
+
+
+NeighborlistArg = tp.Union[str, Neighborlist]
+
+
+def _parse_neighborlist(neighborlist: NeighborlistArg = "cell_list") -> Neighborlist:
+    # neighbors.py:899-914
+    if isinstance(neighborlist, Neighborlist):
+        return neighborlist
+    table = {"all_pairs": AllPairs, "cell_list": CellList, "adaptive": AdaptiveList,
+             "fast_cell_list": CellList, "base": Neighborlist}
+    if neighborlist not in table:
+        raise ValueError(f"Unsupported neighborlist: {neighborlist}")
+    return table[neighborlist]()
