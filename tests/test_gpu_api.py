@@ -1,0 +1,147 @@
+"""GPU tests of the drop-in modules (interfaces of torchani.neighbors / AEVComputer / nn / ANI)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle.ani_oracle as orc
+from helpers import (AEV_ATOL, AEV_RTOL, E_ATOL, E_RTOL, F_ATOL, assert_close, golden_inputs, load_golden,
+                     oracle_model)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pairs_sorted(indices, distances):
+    lo = np.minimum(indices[0], indices[1])
+    hi = np.maximum(indices[0], indices[1])
+    order = np.lexsort((distances, hi, lo))
+    return lo[order], hi[order], distances[order]
+
+
+@pytest.mark.parametrize("name", ["water30_pbc_ani2x", "benzene_pbc_ani2x", "randbatch_ani2x", "kat2x5_ani2x"])
+def test_neighborlists_match_reference_pairs(name):
+    from torchani_b200.neighbors import AllPairs, CellList
+    rec = load_golden(name)
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    nl = CellList() if species.shape[0] == 1 else AllPairs()
+    args = [species.to(DEV), coords.to(DEV), None if cell is None else cell.to(DEV),
+            None if pbc is None else pbc.to(DEV)]
+    nb = nl(5.1, *args)
+    assert nb.indices.shape == (2, int(rec["num_pairs"])) and nb.indices.dtype == torch.int64
+    lo, hi, d = _pairs_sorted(nb.indices.cpu().numpy(), nb.distances.cpu().numpy())
+    glo, ghi, gd = _pairs_sorted(rec["pairs"], rec["distances"])
+    assert (lo == glo).all() and (hi == ghi).all()
+    assert np.abs(d - gd).max() < 5e-6
+    assert torch.allclose(nb.diff_vectors.norm(dim=-1), nb.distances, atol=1e-6)
+    # autograd edge to coords like neighbors.py:107-112
+    c = args[1].clone().requires_grad_(True)
+    nb = nl(5.1, args[0], c, args[2], args[3])
+    (g,) = torch.autograd.grad(nb.distances.sum(), c)
+    assert bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+
+
+def test_neighborlist_validation():
+    from torchani_b200.neighbors import CellList
+    nl = CellList()
+    sp = torch.zeros(1, 4, dtype=torch.long, device=DEV)
+    co = torch.rand(1, 4, 3, device=DEV)
+    with pytest.raises(ValueError):
+        nl(5.1, sp, co, None, torch.tensor([False, False, False], device=DEV))
+    with pytest.raises(ValueError):
+        nl(5.1, sp, co, torch.eye(3, device=DEV), None)
+    with pytest.raises(ValueError):
+        nl(-1.0, sp, co)
+    with pytest.raises(RuntimeError, match="too small"):
+        nl(5.1, sp, co, torch.eye(3, device=DEV) * 3.0, torch.tensor([True, True, True], device=DEV))
+    with pytest.raises(ValueError):
+        nl(5.1, sp.cpu(), co.cpu())
+
+
+@pytest.mark.parametrize("name", ["water30_pbc_ani2x", "randbatch_ani2x", "ch4_ani1x"])
+def test_aev_computer_forward_backward(name):
+    from torchani_b200.aev import AEVComputer
+    rec = load_golden(name)
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    aevc = (AEVComputer.like_2x() if rec["kind"] == "2x" else AEVComputer.like_1x()).to(DEV)
+    c = coords.to(DEV).requires_grad_(True)
+    aev = aevc(species.to(DEV), c, None if cell is None else cell.to(DEV), None if pbc is None else pbc.to(DEV))
+    assert aev.shape == (*species.shape, aevc.out_dim)
+    # oracle AEV + a random linear functional of it for the backward check
+    spec = orc.aev_spec_2x() if rec["kind"] == "2x" else orc.aev_spec_1x()
+    c64 = coords.double().requires_grad_(True)
+    nb = orc.neighborlist(rec["neighborlist"], spec.rcr, species, c64, None if cell is None else cell.double(), pbc)
+    ref = orc.aev_from_neighbors(spec, species, nb)
+    assert_close("aev", aev.detach().cpu().numpy(), ref.detach().numpy(), AEV_RTOL, AEV_ATOL)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64) * 1e-2
+    (g_ref,) = torch.autograd.grad((ref * w).sum(), c64)
+    (g,) = torch.autograd.grad((aev * w.float().to(DEV)).sum(), c)
+    assert_close("dL/dcoords", g.cpu().numpy(), g_ref.numpy(), 1e-4, 2e-5)
+    # padding rows are exactly zero
+    pad = (species == -1)
+    if bool(pad.any()):
+        assert float(aev.detach().cpu()[pad].abs().max()) == 0.0
+
+
+def test_ensemble_forward_on_given_aevs():
+    from torchani_b200 import models
+    rec = load_golden("randbatch_ani2x")
+    species, coords, _, _ = golden_inputs(rec, torch.float32)
+    om = oracle_model("2x", torch.float32)
+    model = models.from_weight_lists("2x", om.weights, device=DEV)
+    ens = model.neural_networks
+    aev_ref = torch.tensor(rec["aev"], dtype=torch.float32)
+    a = aev_ref.to(DEV).requires_grad_(True)
+    e = ens(species.to(DEV), a)
+    assert e.shape == (species.shape[0],)
+    assert_close("molecular NN energies", e.detach().cpu().numpy(), rec["energy_nn"], 1e-5, 2e-6)
+    e_at = ens(species.to(DEV), a, atomic=True)
+    assert_close("atomic", e_at.detach().cpu().numpy(), rec["member_atomic"].mean(0), E_RTOL, E_ATOL)
+    e_mem = ens(species.to(DEV), a, atomic=True, ensemble_values=True)
+    assert_close("member atomic", e_mem.detach().cpu().numpy(), rec["member_atomic"], E_RTOL, E_ATOL)
+    # backward-to-input vs oracle autograd
+    a64 = torch.tensor(rec["aev"]).requires_grad_(True)
+    m64 = oracle_model("2x", torch.float64)
+    e64 = orc.ensemble_atomic_energies(m64.symbols, m64.weights, species, a64).mean(0).sum()
+    (g_ref,) = torch.autograd.grad(e64, a64)
+    (g,) = torch.autograd.grad(e.sum(), a)
+    assert_close("dE/dAEV", g.cpu().numpy(), g_ref.numpy(), 1e-4, 1e-7)
+    # set_active_members
+    ens.set_active_members([0, 5])
+    e2 = ens(species.to(DEV), a.detach(), atomic=True)
+    assert_close("active members", e2.cpu().numpy(), rec["member_atomic"][[0, 5]].mean(0), E_RTOL, E_ATOL)
+    ens.set_active_members(list(range(8)))
+    # a single ANINetworks member == that member of the ensemble (tests/test_ensemble.py:22-37)
+    e_m3 = ens[3](species.to(DEV), a.detach(), atomic=True)
+    assert_close("member 3", e_m3.cpu().numpy(), rec["member_atomic"][3], E_RTOL, E_ATOL)
+
+
+@pytest.mark.parametrize("name", ["water30_pbc_ani2x", "kat2x5_ani2x", "small264_nopbc_ani2x"])
+def test_ani_model_energy_and_autograd_forces(name):
+    """models.ANI2x-style call: energies = model((Z, coords), cell, pbc).energies; F = -dE/dx."""
+    from torchani_b200 import models
+    rec = load_golden(name)
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    om = oracle_model("2x", torch.float32)
+    model = models.from_weight_lists("2x", om.weights, device=DEV, periodic_table_index=True)
+    znum = torch.tensor([orc.ATOMIC_NUMBERS[s] for s in orc.SYMBOLS_2X])
+    z = torch.where(species >= 0, znum[species.clamp(min=0)], torch.full_like(species, -1))
+    c = coords.to(DEV).requires_grad_(True)
+    cell_d = None if cell is None else cell.to(DEV)
+    pbc_d = None if pbc is None else pbc.to(DEV)
+    out = model((z.to(DEV), c), cell_d, pbc_d)
+    assert out.species.cpu().tolist() == species.tolist()
+    (g,) = torch.autograd.grad(out.energies.sum(), c)
+    assert_close("forces", -g.cpu().numpy(), rec["forces"], 0.0, F_ATOL)
+    sae = orc.self_energies(orc.SYMBOLS_2X, orc.GSAES_WB97X_631GD, species, torch.float64).sum(-1).numpy()
+    assert_close("energies", out.energies.detach().cpu().numpy(), rec["energy_nn"] + sae, 2e-7, 1e-5)
+    e64 = model.energies_f64((z.to(DEV), coords.to(DEV)), cell_d, pbc_d)
+    assert_close("energies f64", e64.cpu().numpy(), rec["energy_nn"] + sae, 0.0, 1e-5)
+    at = model((z.to(DEV), coords.to(DEV)), cell_d, pbc_d, atomic=True).energies
+    assert at.shape == species.shape
+    ev = model((z.to(DEV), coords.to(DEV)), cell_d, pbc_d, ensemble_values=True).energies
+    assert ev.shape == (8, species.shape[0])
+    assert_close("ensemble mean", ev.mean(0).cpu().numpy(), rec["energy_nn"] + sae, 2e-7, 1e-5)
+    e2, f2 = model.energies_and_forces(z.to(DEV), coords.to(DEV), cell_d, pbc_d)
+    assert_close("forces (direct)", f2.cpu().numpy(), rec["forces"], 0.0, F_ATOL)
+    with pytest.raises(ValueError):
+        model((torch.full_like(z, 15).to(DEV), c), cell_d, pbc_d)  # phosphorus is not an ANI-2x element

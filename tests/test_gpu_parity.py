@@ -1,0 +1,226 @@
+"""GPU parity of the fused engine (through the C-ABI) against the CPU oracle / golden vectors.
+
+Bars (north_star): AEV and atomic energies 1e-5 relative, forces 1e-4 Ha/A, vs the float64
+oracle evaluated on the same float32-rounded inputs (helpers.py spells out the tolerances)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.ani_oracle as orc
+from helpers import (AEV_ATOL, AEV_RTOL, E_ATOL, E_RTOL, F_ATOL, GOLDEN_CASES, assert_close, golden_inputs,
+                     load_golden, oracle_model)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engines():
+    from torchani_b200.engine import Engine, PackedNetworks, constants_1x, constants_2x
+    dev = torch.device("cuda:0")
+    out = {}
+    for kind, consts in (("2x", constants_2x()), ("1x", constants_1x())):
+        m = oracle_model(kind)
+        nets = PackedNetworks([[wm[s] for s in m.symbols] for wm in m.weights], consts.out_dim, dev)
+        out[kind] = Engine(consts, nets, [m.sae[s] for s in m.symbols])
+    return out
+
+
+def gpu_aev(eng, species, coords, cell, pbc):
+    """AEV forward only, returned in input order (C, A, D)."""
+    from torchani_b200._lib import check, lib, ptr
+    dev = eng.device
+    res = eng.step(species.to(dev), coords.to(dev), None if cell is None else cell.to(dev), pbc is not None,
+                   want_grad=False)
+    ws = eng.workspace(*species.shape)
+    n = species.numel()
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib().ani_b200_aev_forward(C.byref(eng.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos),
+                                     ptr(ws.sbin), n, 0, n, ptr(ws.row_of), ptr(ws.x), eng.nets.ldx,
+                                     ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st))
+    torch.cuda.synchronize()
+    eng.check_status(ws)
+    D = eng.consts.out_dim
+    n_real = int((species >= 0).sum())
+    so = ws.sorted_orig[:n_real].long()
+    rows = ws.row_of[:n_real].long()
+    aev = torch.zeros(n, D, device=dev)
+    aev[so] = ws.x[rows, :D]
+    return aev.view(*species.shape, D).cpu(), res
+
+
+def run_and_compare(eng, model, species, coords32, cell32, pbc):
+    ref = orc.compute(model, species, coords32.double(), None if cell32 is None else cell32.double(), pbc)
+    aev, _ = gpu_aev(eng, species, coords32, cell32, pbc)
+    dev = eng.device
+    res = eng.step(species.to(dev), coords32.to(dev), None if cell32 is None else cell32.to(dev),
+                   pbc is not None, want_grad=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    assert_close("aev", aev.numpy(), ref["aev"].numpy(), AEV_RTOL, AEV_ATOL)
+    assert_close("member atomic energies", res.member_atomic.cpu().numpy(), ref["member_atomic"].numpy(),
+                 E_RTOL, E_ATOL)
+    assert_close("atomic energies", res.atomic_energies.cpu().numpy(), ref["atomic_nn"].numpy(), E_RTOL, E_ATOL)
+    n_real = int((species >= 0).sum())
+    assert_close("total energies", res.energies.cpu().numpy(), ref["energy"].numpy(), 0.0, 2e-7 * max(n_real, 10))
+    assert_close("forces", -res.grad.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+    return ref, res
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_cases(engines, name):
+    rec = load_golden(name)
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    eng = engines[rec["kind"]]
+    model = oracle_model(rec["kind"], torch.float64, rec["neighborlist"])
+    ref, res = run_and_compare(eng, model, species, coords, cell, pbc)
+    # and against the reference-generated fixture itself (float64 inputs there, float32 here)
+    assert np.abs(-res.grad.cpu().numpy() - rec["forces"]).max() < F_ATOL
+    assert np.abs(res.member_atomic.cpu().numpy() - rec["member_atomic"]).max() < 2e-5
+    ws = eng.workspace(*species.shape)
+    n_real = int((species >= 0).sum())
+    assert int(ws.nbr_cnt[:n_real].sum().item()) == 2 * int(rec["num_pairs"])
+
+
+def test_conformer_batch_256(engines):
+    """BASELINE config 3: 256 GDB-like conformers, -1 padding, no PBC."""
+    species, coords = orc.conformer_batch(256, seed=1234)
+    model = oracle_model("2x", torch.float64, "all_pairs")
+    run_and_compare(engines["2x"], model, species, coords, None, None)
+
+
+def test_water_1k_box(engines):
+    """BASELINE config 2: 999-atom periodic water box."""
+    _, idx, coords, cell, pbc = orc.water_box(333, seed=5)
+    run_and_compare(engines["2x"], oracle_model("2x", torch.float64, "cell_list"), idx, coords, cell, pbc)
+
+
+def test_uniform_random_box_close_contacts(engines):
+    """_testing.make_molecs-style uniform random HCNO box (worst-case close contacts)."""
+    g = torch.Generator().manual_seed(11)
+    n, L = 600, (600 / 0.1) ** (1 / 3)
+    coords = (torch.rand(1, n, 3, generator=g) * L + 1e-3)
+    idx = torch.randint(0, 4, (1, n), generator=g)
+    cell = torch.eye(3) * (L + 2e-3)
+    pbc = torch.tensor([True, True, True])
+    model = oracle_model("2x", torch.float64, "cell_list")
+    ref = orc.compute(model, idx, coords.double(), cell.double(), pbc)
+    eng = engines["2x"]
+    aev, res = gpu_aev(eng, idx, coords, cell, pbc)
+    assert_close("aev", aev.numpy(), ref["aev"].numpy(), 2e-5, 2e-5)
+    res = eng.step(idx.cuda(), coords.cuda(), cell.cuda(), True)
+    # random overlaps give forces of O(10) Ha/A: judge them relative to that scale
+    f_ref = ref["forces"].numpy()
+    assert np.abs(-res.grad.cpu().numpy() - f_ref).max() <= 1e-5 * np.abs(f_ref).max() + F_ATOL
+
+
+def test_water_10k_box_properties(engines):
+    """BASELINE config 4 size: checked through size-independent properties + the oracle."""
+    eng = engines["2x"]
+    _, idx, coords, cell, pbc = orc.water_box(3333, seed=0)
+    d = eng.device
+    sp, co, ce = idx.to(d), coords.to(d), cell.to(d)
+    r0 = eng.step(sp, co, ce, True)
+    e0, g0, at0 = r0.energies.clone(), r0.grad.clone(), r0.atomic_energies.clone()
+    eng.check_status()
+    # Newton's third law: the net force vanishes
+    assert float(g0.sum(1).abs().max()) < 5e-5
+    # energy is the sum of atomic energies + self energies
+    sae = torch.tensor([orc.GSAES_WB97X_631GD[s] for s in orc.SYMBOLS_2X], dtype=torch.float64, device=d)
+    assert abs(float(at0.double().sum() + sae[sp].sum() - e0[0])) < 1e-6 * 9999
+    # translation by an arbitrary vector (atoms leave the cell and are wrapped back)
+    shift = torch.tensor([3.21, -47.5, 101.3], device=d)
+    r1 = eng.step(sp, co + shift, ce, True)
+    assert abs(float(r1.energies[0] - e0[0])) < 2e-4
+    assert float((r1.grad - g0).abs().max()) < 2e-5
+    # permutation of the atom order
+    perm = torch.randperm(9999, generator=torch.Generator().manual_seed(1)).to(d)
+    r2 = eng.step(sp[:, perm], co[:, perm], ce, True)
+    assert abs(float(r2.energies[0] - e0[0])) < 1e-5
+    assert float((r2.grad - g0[:, perm]).abs().max()) < 2e-5
+    # sharded evaluation (what every rank of a multi-GPU run computes) adds up to the whole
+    parts_e, parts_g = 0.0, torch.zeros_like(g0)
+    for r in range(4):
+        rr = eng.step(sp, co, ce, True, shard=(r, 4))
+        parts_e += float(rr.energies[0])
+        parts_g += rr.grad
+    assert abs(parts_e - float(e0[0])) < 1e-5
+    assert float((parts_g - g0).abs().max()) < 2e-5
+    # finally the oracle itself at full size (float64, a few seconds)
+    ref = orc.compute(oracle_model("2x", torch.float64, "cell_list"), idx, coords.double(), cell.double(), pbc)
+    assert_close("forces", -g0.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+    assert_close("atomic energies", at0.cpu().numpy(), ref["atomic_nn"].numpy(), E_RTOL, E_ATOL)
+    assert abs(float(e0[0]) - float(ref["energy"][0])) < 5e-3
+
+
+def test_forces_are_the_gradient_of_the_energy(engines):
+    """Central finite differences of the float64-accumulated energy vs the analytic forces."""
+    eng = engines["2x"]
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    d = eng.device
+    sp, ce = species.to(d), cell.to(d)
+    res = eng.step(sp, coords.to(d), ce, True)
+    grad = res.grad.clone().cpu()
+    h = 2e-3
+    for (a, k) in [(0, 0), (7, 2), (13, 1), (29, 0)]:
+        cp, cm = coords.clone(), coords.clone()
+        cp[0, a, k] += h
+        cm[0, a, k] -= h
+        ep = float(eng.step(sp, cp.to(d), ce, True, want_grad=False).energies[0])
+        em = float(eng.step(sp, cm.to(d), ce, True, want_grad=False).energies[0])
+        assert abs((ep - em) / (2 * h) - float(grad[0, a, k])) < 2e-4
+
+
+def test_edge_cases(engines):
+    eng = engines["1x"]
+    d = eng.device
+    rca, rcr = 3.5, 5.2
+    # tests/test_aev.py:61-131: atoms exactly at / just beyond the cutoffs, lone atom
+    for dist in [1.0, rca, rca + 1e-4, rcr, rcr + 1e-4, 2 * rcr]:
+        coords = torch.tensor([[[-dist, 0.0, 0.0], [0.0, 0.0, 0.0], [0.0, 0.0, dist]]])
+        species = torch.tensor([[3, 1, 3]])
+        ref = orc.compute(oracle_model("1x", torch.float64, "all_pairs"), species, coords.double())
+        aev, res = gpu_aev(eng, species, coords, None, None)
+        assert_close(f"aev d={dist}", aev.numpy(), ref["aev"].numpy(), AEV_RTOL, AEV_ATOL)
+    aev, res = gpu_aev(eng, torch.tensor([[0]]), torch.zeros(1, 1, 3), None, None)
+    assert float(aev.abs().max()) == 0.0
+    # coincident atoms: no NaN (tests/test_aev.py:184-189)
+    coords = torch.tensor([[[0.0, 0.0, 0.0], [0.0, 0.0, 0.0], [1.0, 0.0, 0.0]]])
+    res = eng.step(torch.tensor([[0, 0, 1]], device=d), coords.to(d), None, False)
+    assert bool(torch.isfinite(res.grad).all()) and bool(torch.isfinite(res.energies).all())
+    # a fully padded conformer in a batch gives zero energy and zero AEV
+    species = torch.tensor([[1, 0, 0, 0, 0], [-1, -1, -1, -1, -1]])
+    coords = torch.randn(2, 5, 3, generator=torch.Generator().manual_seed(0))
+    res = eng.step(species.to(d), coords.to(d), None, False)
+    assert float(res.energies[1]) == 0.0 and float(res.grad[1].abs().max()) == 0.0
+    # periodic cell thinner than the cutoff is an error (neighbors.py:402-403)
+    eng2 = engines["2x"]
+    res = eng2.step(torch.zeros(1, 4, dtype=torch.long, device=d), torch.rand(1, 4, 3, device=d),
+                    torch.eye(3, device=d) * 4.0, True)
+    with pytest.raises(RuntimeError, match="too small"):
+        eng2.check_status()
+
+
+def test_smooth_cutoff_and_active_members(engines):
+    from torchani_b200.engine import Engine, constants_2x
+    eng = engines["2x"]
+    rec = load_golden("benzene_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    # smooth cutoff (cutoffs.py:84-101)
+    eng_s = Engine(constants_2x(cutoff_fn="smooth"), eng.nets, None)
+    m = oracle_model("2x", torch.float64, "cell_list")
+    m = m._replace(spec=m.spec._replace(cutoff_fn="smooth"))
+    run_and_compare(eng_s, m._replace(sae={s: 0.0 for s in m.symbols}), species, coords, cell, pbc)
+    # subset of active ensemble members (nn/_core.py:99-110)
+    eng.nets.set_active_members([1, 4, 6])
+    try:
+        d = eng.device
+        res = eng.step(species.to(d), coords.to(d), cell.to(d), True)
+        ref = orc.compute(oracle_model("2x", torch.float64, "cell_list"), species, coords.double(), cell.double(),
+                          pbc, members=[1, 4, 6])
+        assert_close("atomic", res.atomic_energies.cpu().numpy(), ref["atomic_nn"].numpy(), E_RTOL, E_ATOL)
+        assert_close("forces", -res.grad.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+    finally:
+        eng.nets.set_active_members(list(range(8)))

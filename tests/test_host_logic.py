@@ -1,0 +1,153 @@
+"""Host-side logic that needs no GPU: weight packing, constants, module trees / state dicts,
+species conversion, sharding arithmetic and the 2-rank (gloo) reduction of partial results."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle.ani_oracle as orc
+from helpers import ROOT, oracle_model
+
+
+def test_constants_match_oracle_spec():
+    from torchani_b200.engine import constants_1x, constants_2x
+    for mine, ref in ((constants_2x(), orc.aev_spec_2x()), (constants_1x(), orc.aev_spec_1x())):
+        assert mine.out_dim == ref.out_dim and mine.radial_len == ref.radial_len
+        assert mine.shf_r == ref.shf_r and mine.shf_a == ref.shf_a and mine.shf_z == ref.shf_z
+        st = mine.to_struct()
+        assert st.eta_r == np.float32(ref.eta_r) and st.zeta == np.float32(ref.zeta)
+        assert abs(st.cos_z[0] - math.cos(np.float32(ref.shf_z[0]))) < 1e-7
+    assert constants_2x().out_dim == 1008 and constants_1x().out_dim == 384
+
+
+def test_unsupported_configurations_are_rejected_loudly():
+    from torchani_b200.engine import constants_2x
+    with pytest.raises(ValueError):
+        constants_2x()._replace(shf_a=(0.9, 1.0, 1.1)).to_struct()
+    with pytest.raises(ValueError):
+        constants_2x()._replace(cutoff_fn="triweight").to_struct()
+    from torchani_b200.aev import AEVComputer
+    with pytest.raises(ValueError):
+        AEVComputer.like_2x(strategy="pyaev")
+    with pytest.raises(ValueError):
+        AEVComputer.like_2x().set_strategy("cuaev")
+    from torchani_b200.nn import AtomicNetwork
+    with pytest.raises(ValueError):
+        AtomicNetwork((1008, 256, 192, 160, 1), activation="gelu")
+
+
+def test_weight_packing_layout():
+    from torchani_b200.engine import PackedNetworks
+    m = oracle_model("2x", members=3)
+    w = [[wm[s] for s in m.symbols] for wm in m.weights]
+    nets = PackedNetworks(w, 1008, torch.device("cpu"))
+    assert nets.ldx == 1024 and nets.num_members == 3 and nets.dims[0] == (256, 192, 160)
+    sp0 = {k: t for k, t in zip(("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "w3n", "w2n", "w1n"),
+                                 nets._keep[:11])}
+    # layer 1: members concatenated along N, K padded to ldx with zeros
+    assert sp0["w1"].shape == (1024, 3 * 256)
+    assert torch.equal(sp0["w1"][:1008, 256:512], m.weights[1]["H"][0][0].t())
+    assert float(sp0["w1"][1008:].abs().max()) == 0.0
+    assert torch.equal(sp0["w2"][2], m.weights[2]["H"][1][0].t())
+    assert torch.equal(sp0["w3n"][1], m.weights[1]["H"][2][0])
+    assert torch.equal(sp0["w4"][2], m.weights[2]["H"][3][0][0])
+    assert torch.equal(sp0["w1n"][256:512, :1008], m.weights[1]["H"][0][0])
+    nets.set_active_members([0, 2])
+    assert list(nets.model.member_scale)[:3] == [0.5, 0.0, 0.5]
+    with pytest.raises(IndexError):
+        nets.set_active_members([5])
+
+
+def test_model_tree_and_reference_state_dict_keys():
+    from torchani_b200 import models
+    m = models.ANI2x(seed=1)
+    keys = set(m.state_dict().keys())
+    assert "neural_networks.members.7.atomics.Cl.final_layer.bias" in keys
+    assert "neural_networks.members.0.atomics.H.layers.0.weight" in keys
+    assert m.aev_computer.out_dim == 1008 and len(m) == 8
+    assert sum(p.numel() for p in m.neural_networks.members[0].parameters()) == 1713223
+    # the reference's key names (arch.py:278-290) load
+    sd = {}
+    for k, v in m.state_dict().items():
+        k = k.replace("aev_computer.", "potentials.nnp.aev_computer.") if k.startswith("aev_computer.") else k
+        k = k.replace("neural_networks.", "potentials.nnp.neural_networks.") if k.startswith("neural_networks.") else k
+        sd[k] = v.clone()
+    m2 = models.ANI2x(seed=2)
+    m2.load_state_dict(sd)
+    a = m.neural_networks.members[3].atomics["O"].layers[1].weight
+    b = m2.neural_networks.members[3].atomics["O"].layers[1].weight
+    assert torch.equal(a, b)
+    sub = m[2]
+    assert len(sub) == 1 and sub.neural_networks.num_species == 7
+
+
+def test_species_converter_and_self_energy():
+    from torchani_b200.models import SelfEnergy
+    from torchani_b200.nn import SpeciesConverter
+    conv = SpeciesConverter(["H", "C", "N", "O"])
+    z = torch.tensor([[6, 1, 1, 1, 1], [7, 1, 1, 1, -1]])
+    assert conv(z).tolist() == [[1, 0, 0, 0, 0], [2, 0, 0, 0, -1]]
+    with pytest.raises(ValueError):
+        conv(torch.tensor([[16, 1]]))
+    sae = SelfEnergy.with_gsaes(["H", "C", "N", "O"])
+    e = sae(conv(z))
+    assert abs(float(e[1]) - (-54.5732825 - 3 * 0.4993212)) < 1e-9
+
+
+def test_shard_bounds_cover_everything():
+    from torchani_b200.parallel import shard_bounds
+    for n in (1, 7, 999, 9999):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+_GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from torchani_b200.parallel import allreduce_partials, shard_bounds
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+r, w = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+full_grad = torch.randn(3, 10, 3)
+full_e = torch.randn(3, dtype=torch.float64)
+lo, hi = shard_bounds(30, r, w)
+mask = torch.zeros(30); mask[lo:hi] = 1
+part_grad = (full_grad.view(30, 3) * mask.view(-1, 1)).view(3, 10, 3)
+part_e = full_e * (1.0 / w)
+grad, e = allreduce_partials(part_grad, part_e)
+assert torch.allclose(grad.float(), full_grad, atol=1e-6), "gradient all-reduce wrong"
+assert torch.allclose(e, full_e, atol=1e-12)
+dist.destroy_process_group()
+print("ok", r)
+'''
+
+
+def test_two_rank_gloo_allreduce_of_partials(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0, err
+        assert "ok" in out
+
+
+def test_synthetic_generators_agree_with_the_oracle_copies():
+    from torchani_b200 import synthetic
+    a = synthetic.water_box(20, seed=3)
+    b = orc.water_box(20, seed=3)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    sa, ca = synthetic.conformer_batch(5, seed=2)
+    sb, cb = orc.conformer_batch(5, seed=2)
+    assert torch.equal(sa, sb) and torch.equal(ca, cb)
+    wa = synthetic.make_weights(("H", "O"), synthetic.DIMS_2X, 1008, 2, seed=9)
+    wb = orc.make_weights(("H", "O"), orc.DIMS_2X, 1008, 2, seed=9)
+    assert torch.equal(wa[1]["O"][2][0], wb[1]["O"][2][0])

@@ -165,6 +165,7 @@ class AEVComputer(torch.nn.Module):
         self._strategy = ""
         self.set_strategy(strategy)
         self._struct = None
+        self._consts: tp.Optional[AEVConstants] = None
         self._last_grid: tp.Optional[BucketGrid] = None
         self.constants.to_struct()  # validates the configuration early
 
@@ -192,6 +193,11 @@ class AEVComputer(torch.nn.Module):
 
     @property
     def constants(self) -> AEVConstants:
+        if self._consts is None:  # reading the buffers costs a device sync: do it once
+            self._consts = self._read_constants()
+        return self._consts
+
+    def _read_constants(self) -> AEVConstants:
         r, a = self.radial, self.angular
         return AEVConstants(self.num_species, r.cutoff, a.cutoff, float(r.eta.item()),
                             tuple(float(v) for v in r.shifts.tolist()), float(a.eta.item()),
@@ -247,6 +253,11 @@ class AEVComputer(torch.nn.Module):
         return cls(ANIRadial(radial_eta, radial_shifts, radial_cutoff, cutoff_fn),
                    ANIAngular(angular_eta, angular_zeta, angular_shifts, sections, angular_cutoff, cutoff_fn),
                    num_species, strategy, neighborlist=neighborlist)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs) -> None:
+        self._consts = None
+        self._struct = None
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def extra_repr(self) -> str:
         return (f"out_dim={self.out_dim}, radial_len={self.radial_len}, angular_len={self.angular_len}, "

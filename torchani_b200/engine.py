@@ -249,6 +249,25 @@ class Engine:
         self._ws: tp.Dict[tp.Tuple[int, int], Workspace] = {}
         self.lib = _lib.lib()
         self.launches_per_step = 0
+        # per-stage CUDA-event timing (bench.py's roofline leg); off by default
+        self.profile = False
+        self.stage_events: tp.Dict[str, tp.List[tp.Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
+
+    def _timed(self, name: str, fn: tp.Callable[[], int]) -> None:
+        """Run one C-ABI stage; with ``profile`` on, bracket it with events on the launch stream."""
+        if not self.profile:
+            check(fn(), name)
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(fn(), name)
+        b.record()
+        self.stage_events.setdefault(name, []).append((a, b))
+
+    def stage_times_ms(self) -> tp.Dict[str, float]:
+        """Mean device time per call of every stage (synchronises)."""
+        torch.cuda.synchronize(self.device)
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.stage_events.items() if v}
 
     # -- workspaces ------------------------------------------------------------------------
     def workspace(self, n_conf: int, n_per_conf: int) -> Workspace:
@@ -287,37 +306,35 @@ class Engine:
             ws.cell.copy_(cell.reshape(-1))
             cell_ptr = ptr(ws.cell)
         mode = 0 if n_conf == 1 else 1
-        check(L.ani_b200_build_cells(ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr,
-                                     int(bool(pbc)), mode, self.consts.rcr, ws.max_bins, ptr(ws.grid),
-                                     ptr(ws.bin_start), ptr(ws.sorted_orig), ptr(ws.orig_to_sorted),
-                                     ptr(ws.spos), ptr(ws.sbin), ptr(ws.scratch), ptr(ws.status), st),
-              "build_cells")
+        self._timed("build_cells", lambda: L.ani_b200_build_cells(
+            ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
+            self.consts.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
+            ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.scratch), ptr(ws.status), st))
         rank, world = shard
         lo = (n * rank) // world
         hi = (n * (rank + 1)) // world
-        check(L.ani_b200_species_layout(ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species,
-                                        ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
-                                        ptr(ws.layout_info), ptr(ws.scratch), st), "species_layout")
-        check(L.ani_b200_aev_forward(C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos),
-                                     ptr(ws.sbin), n, lo, hi, ptr(ws.row_of), ptr(ws.x), self.nets.ldx,
-                                     ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st),
-              "aev_forward")
-        check(L.ani_b200_mlp_forward_backward(C.byref(self.nets.model), ptr(ws.x), ws.rows_cap,
-                                              ptr(ws.tile_species), ptr(ws.row_atom), ptr(ws.act1),
-                                              ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad), st),
-              "mlp_forward_backward")
+        self._timed("species_layout", lambda: L.ani_b200_species_layout(
+            ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species, ws.rows_cap, ptr(ws.row_of),
+            ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info), ptr(ws.scratch), st))
+        self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
+            C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin), n, lo, hi,
+            ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
+            ptr(ws.status), st))
+        self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
+            C.byref(self.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species), ptr(ws.row_atom),
+            ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad), st))
         grad = None
         if want_grad:
             ws.grad.zero_()
-            check(L.ani_b200_aev_backward(C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
-                                          n, lo, hi, ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt),
-                                          ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.grad), ptr(ws.status), st),
-                  "aev_backward")
+            self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
+                C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig), n, lo, hi,
+                ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
+                ptr(ws.grad), ptr(ws.status), st))
             grad = ws.grad.view(n_conf, n_per_conf, 3)
-        check(L.ani_b200_reduce_energies(C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of),
-                                         ptr(ws.orig_to_sorted), ptr(ws.species_i32), n, lo, hi, n_conf,
-                                         n_per_conf, ptr(self.sae), ptr(ws.atomic), ptr(ws.member_atomic),
-                                         ptr(ws.energies), st), "reduce_energies")
+        self._timed("reduce_energies", lambda: L.ani_b200_reduce_energies(
+            C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),
+            ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
+            ptr(ws.member_atomic), ptr(ws.energies), st))
         # kernels launched by this library in one step (memsets excluded):
         #   build_cells 5, layout 3, aev fwd 1, mlp 4 (+3 bwd), aev bwd 1, reduce 1
         self.launches_per_step = 5 + 3 + 1 + 4 + (4 if want_grad else 0) + 1
