@@ -73,7 +73,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
@@ -180,12 +180,12 @@ def main():
     def one_step():
         return sharded.step(sp_d, co_d, ce_d, True)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # sampled from the warm-up to the end of the end-to-end region (GPU under load throughout)
     for _ in range(warmup):
         one_step()
     eng.check_status()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     evs = []
     for _ in range(args.steps):
         flush.fill_(1)
@@ -195,7 +195,6 @@ def main():
         b.record()
         evs.append((a, b))
     barrier()
-    clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     t_all = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -235,6 +234,7 @@ def main():
         b.record()
         e2e_evs.append((a, b))
     barrier()
+    clocks = sampler.stop()
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
     t_e2e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -211,13 +211,15 @@ struct ReduceArgs {
   float member_scale[ANI_MAX_MEMBERS];
 };
 
-__global__ void __launch_bounds__(1024) k_reduce_energies(const __grid_constant__ ReduceArgs args) {
-  __shared__ double s_part[32];
-  const int c = blockIdx.x;
-  const int A = args.n_per_conf;
-  double acc = 0.0;
-  for (int t = threadIdx.x; t < A; t += blockDim.x) {
-    const int a = c * A + t;
+__global__ void __launch_bounds__(256) k_reduce_energies(const __grid_constant__ ReduceArgs args) {
+  // one thread per atom; conformer sums by warp-aggregated float64 atomics (energies_out is
+  // zeroed by the launcher)
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = a < args.n;
+  double contrib = 0.0;
+  int conf = -1;
+  if (in_range) {
+    conf = a / args.n_per_conf;
     const int sp = args.species[a];
     float e = 0.f;
     bool owned = false;
@@ -235,15 +237,15 @@ __global__ void __launch_bounds__(1024) k_reduce_energies(const __grid_constant_
       e += args.member_scale[m] * em;
     }
     if (args.atomic_out) args.atomic_out[a] = e;
-    if (owned) acc += (double)e + (args.sae ? args.sae[sp] : 0.0);
+    if (owned) contrib = (double)e + (args.sae ? args.sae[sp] : 0.0);
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(ANI_FULL_MASK, acc, o);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double v = (threadIdx.x < (blockDim.x >> 5)) ? s_part[threadIdx.x] : 0.0;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(ANI_FULL_MASK, v, o);
-    if (threadIdx.x == 0) args.energies_out[c] = v;
+  const int conf0 = __shfl_sync(ANI_FULL_MASK, conf, 0);
+  const bool uniform = __all_sync(ANI_FULL_MASK, conf == conf0 || !in_range);
+  if (uniform) {
+    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(ANI_FULL_MASK, contrib, o);
+    if ((threadIdx.x & 31) == 0 && conf0 >= 0 && contrib != 0.0) atomicAdd(&args.energies_out[conf0], contrib);
+  } else if (in_range && contrib != 0.0) {
+    atomicAdd(&args.energies_out[conf], contrib);
   }
 }
 
@@ -357,8 +359,8 @@ extern "C" int ani_b200_reduce_energies(const ani_mlp_model* model, const float*
   ra.num_members = model->num_members;
   for (int m = 0; m < ANI_MAX_MEMBERS; ++m)
     ra.member_scale[m] = m < model->num_members ? model->member_scale[m] : 0.f;
-  const int threads = n_per_conf >= 1024 ? 1024 : (n_per_conf >= 256 ? 256 : 64);
-  k_reduce_energies<<<n_conf, threads, 0, (cudaStream_t)stream>>>(ra);
+  cudaMemsetAsync(energies_out, 0, sizeof(double) * (size_t)n_conf, (cudaStream_t)stream);
+  k_reduce_energies<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(ra);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }
