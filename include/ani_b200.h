@@ -109,7 +109,8 @@ int ani_b200_build_cells(const float* coords, const int32_t* species, int n_conf
 /*      row_of      i32[n]        row of sorted atom i (undefined outside lo..hi-1)         */
 /*      row_atom    i32[rows_cap] sorted atom of a row, -1 for padding rows                 */
 /*      tile_species i32[rows_cap/ANI_TILE_ROWS]  species of each row tile, -1 = unused      */
-/*      layout_info i32[4]: {n_tiles, n_rows, n_owned_atoms, 0}                             */
+/*      layout_info i32[16]: {n_tiles, n_rows, n_owned_atoms, 0, first row tile of species   */
+/*                  0..S-1, total row tiles, ...}  (device-side tile lists of the GEMMs)      */
 /*    Scratch: scratch_i32[(ceil(n/256)+2) * ANI_MAX_SPECIES + 64].                         */
 int ani_b200_species_layout(const float* spos, const ani_grid* grid, int n, int lo, int hi,
                             int num_species, int rows_cap, int32_t* row_of, int32_t* row_atom,
@@ -150,19 +151,27 @@ int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, 
 
 /* 6. Ensemble MLP forward + backward-to-input on the species-grouped AEV matrix.           */
 /*    Layer widths: in -> h1 -> h2 -> h3 -> 1, CELU(alpha) after the three hidden layers.    */
+/*    "tiled B operand" of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K]):     */
+/*    K is zero-padded to a multiple of 32, every value is split into hi = x & 0xffffe000 and    */
+/*    lo = x - hi, and the result is stored as                                                    */
+/*        [member][n tile (256 rows, the last one shorter)][k block (32 floats)]                   */
+/*        [hi: bn rows x 128 B][lo: bn rows x 128 B]                                              */
+/*    where every 8-row x 128-byte group is written in the tcgen05 SWIZZLE_128B order (16-byte     */
+/*    chunk c of row r sits at chunk position c ^ (r & 7)).  One K-block of one tile is therefore  */
+/*    two contiguous byte ranges that a single cp.async.bulk moves into shared memory.            */
 typedef struct ani_mlp_species {
   int32_t h1, h2, h3, pad_;
-  const float* w1;  /* [ldx][M*h1]   w1[k][m*h1+o] = W1_m[o][k], rows >= in_dim are zero     */
-  const float* b1;  /* [M*h1]                                                                  */
-  const float* w2;  /* [M][h1][h2]   transposed Linear weights (K-major)                       */
-  const float* b2;  /* [M*h2]                                                                  */
-  const float* w3;  /* [M][h2][h3]                                                             */
-  const float* b3;  /* [M*h3]                                                                  */
-  const float* w4;  /* [M][h3]                                                                 */
-  const float* b4;  /* [M]                                                                     */
-  const float* w3n; /* [M][h3][h2]   natural Linear layout (out-major) for the backward pass   */
-  const float* w2n; /* [M][h2][h1]                                                             */
-  const float* w1n; /* [M*h1][ldx]                                                             */
+  const float* b1;   /* [M*h1]                                                                  */
+  const float* b2;   /* [M*h2]                                                                  */
+  const float* b3;   /* [M*h3]                                                                  */
+  const float* w4;   /* [M][h3]                                                                 */
+  const float* b4;   /* [M]                                                                     */
+  const float* t_f1; /* forward  layer 1: B = W1 stacked over members [M*h1][in_dim -> ldx]    */
+  const float* t_f2; /* forward  layer 2: per member B = W2_m [h2][h1]                          */
+  const float* t_f3; /* forward  layer 3: per member B = W3_m [h3][h2]                          */
+  const float* t_b3; /* backward layer 3: per member B = W3_m^T [h2][h3]                        */
+  const float* t_b2; /* backward layer 2: per member B = W2_m^T [h1][h2]                        */
+  const float* t_b1; /* backward layer 1: B = W1^T [ldx][M*h1]                                  */
 } ani_mlp_species;
 
 typedef struct ani_mlp_model {
@@ -174,12 +183,13 @@ typedef struct ani_mlp_model {
 } ani_mlp_model;
 
 /*    x            f32[rows_cap][ldx]   in: AEVs; out: dE/dAEV (in place)                     */
+/*    tile_species / row_atom / layout_info: outputs of ani_b200_species_layout              */
 /*    act1/2/3     f32[rows_cap][M*h{1,2,3}_max]  workspaces (activations, then gradients)    */
 /*    e_member     f32[M][rows_cap]     per-member atomic energies                            */
 int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
                                   const int32_t* tile_species, const int32_t* row_atom,
-                                  float* act1, float* act2, float* act3, float* e_member,
-                                  int want_backward, void* stream);
+                                  const int32_t* layout_info, float* act1, float* act2, float* act3,
+                                  float* e_member, int want_backward, void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
 /*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */

@@ -147,7 +147,7 @@ def run_case(name, engines):
           f"max-abs {np.abs(e_tot - ref['energy'].numpy()).max():.3e}")
     # dE/dAEV: rerun fwd+mlp (x currently holds fresh AEVs)
     check(L.ani_b200_mlp_forward_backward(C.byref(eng.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species),
-                                          ptr(ws.row_atom), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3),
+                                          ptr(ws.row_atom), ptr(ws.layout_info), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3),
                                           ptr(ws.e_member), 1, st))
     torch.cuda.synchronize()
     gx = ws.x.cpu().numpy()

@@ -40,22 +40,52 @@ def test_unsupported_configurations_are_rejected_loudly():
         AtomicNetwork((1008, 256, 192, 160, 1), activation="gelu")
 
 
+def _untile(t, n, k):
+    """Inverse of engine.tile_b_operand (numpy, element-wise from the documented layout)."""
+    kp = (k + 31) // 32 * 32
+    nkb = kp // 32
+    t = t.numpy()
+    hi = np.zeros((n, kp), np.float32)
+    lo = np.zeros((n, kp), np.float32)
+    for r in range(n):
+        n0 = r // 256 * 256
+        bn = min(256, n - n0)
+        rr = r - n0
+        for kb in range(nkb):
+            for ch in range(8):
+                base = n0 * nkb * 64 + kb * bn * 64 + (rr // 8) * 256 + (rr % 8) * 32 + ((ch ^ (rr % 8)) * 4)
+                hi[r, kb * 32 + ch * 4: kb * 32 + ch * 4 + 4] = t[base: base + 4]
+                lo[r, kb * 32 + ch * 4: kb * 32 + ch * 4 + 4] = t[base + bn * 32: base + bn * 32 + 4]
+    return hi, lo
+
+
 def test_weight_packing_layout():
-    from torchani_b200.engine import PackedNetworks
+    from torchani_b200.engine import PackedNetworks, tile_b_operand
+    # the tiled / split / swizzled B operand round-trips and hi + lo == x exactly
+    b = torch.randn(272, 48, generator=torch.Generator().manual_seed(0))
+    hi, lo = _untile(tile_b_operand(b), 272, 48)
+    assert np.array_equal((hi + lo)[:, :48], b.numpy()) and float(np.abs(hi[:, 48:]).max()) == 0.0
+    assert np.array_equal(hi.view(np.int32) & 0x1fff, np.zeros_like(hi, dtype=np.int32))  # exact TF32
+    assert np.abs(lo[:, :48]).max() <= np.abs(b.numpy()).max() * 2.0 ** -10
     m = oracle_model("2x", members=3)
     w = [[wm[s] for s in m.symbols] for wm in m.weights]
     nets = PackedNetworks(w, 1008, torch.device("cpu"))
     assert nets.ldx == 1024 and nets.num_members == 3 and nets.dims[0] == (256, 192, 160)
-    sp0 = {k: t for k, t in zip(("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "w3n", "w2n", "w1n"),
-                                 nets._keep[:11])}
-    # layer 1: members concatenated along N, K padded to ldx with zeros
-    assert sp0["w1"].shape == (1024, 3 * 256)
-    assert torch.equal(sp0["w1"][:1008, 256:512], m.weights[1]["H"][0][0].t())
-    assert float(sp0["w1"][1008:].abs().max()) == 0.0
-    assert torch.equal(sp0["w2"][2], m.weights[2]["H"][1][0].t())
-    assert torch.equal(sp0["w3n"][1], m.weights[1]["H"][2][0])
+    names = ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
+    sp0 = dict(zip(names, nets._keep[:11]))
+    # layer 1: members stacked along N, K padded to ldx with zeros
+    hi, lo = _untile(sp0["t_f1"][: 256 * 32 * 64], 256, 1024)       # first n tile = member 0
+    assert np.array_equal((hi + lo)[:, :1008], m.weights[0]["H"][0][0].numpy())
+    assert float(np.abs(hi[:, 1008:]).max()) == 0.0
+    # per-member layer 2 (forward: W2 [h2][h1]; backward: W2^T [h1][h2])
+    per = 192 * 8 * 64
+    hi, lo = _untile(sp0["t_f2"][2 * per: 3 * per], 192, 256)
+    assert np.array_equal(hi + lo, m.weights[2]["H"][1][0].numpy())
+    per = 256 * 6 * 64
+    hi, lo = _untile(sp0["t_b2"][per: 2 * per], 256, 192)
+    assert np.array_equal(hi + lo, m.weights[1]["H"][1][0].t().numpy())
     assert torch.equal(sp0["w4"][2], m.weights[2]["H"][3][0][0])
-    assert torch.equal(sp0["w1n"][256:512, :1008], m.weights[1]["H"][0][0])
+    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 32) * 64
     nets.set_active_members([0, 2])
     assert list(nets.model.member_scale)[:3] == [0.5, 0.0, 0.5]
     with pytest.raises(IndexError):

@@ -46,7 +46,7 @@ class Grid(C.Structure):
 
 class MLPSpecies(C.Structure):
     _fields_ = [("h1", C.c_int32), ("h2", C.c_int32), ("h3", C.c_int32), ("pad_", C.c_int32)] + [
-        (k, C.c_void_p) for k in ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "w3n", "w2n", "w1n")
+        (k, C.c_void_p) for k in ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
     ]
 
 
@@ -73,7 +73,7 @@ _PROTOTYPES = {
     "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
     "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "ani_b200_half_neighbor_fill": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
-    "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
     "ani_b200_reduce_energies": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 

@@ -299,6 +299,9 @@ __global__ void k_layout_scan(int n_chunks, int S, int rows_cap, int32_t* __rest
     layout_info[1] = row;
     layout_info[2] = owned;
     layout_info[3] = 0;
+    // [4 + s] = first row tile of species s, [4 + S] = total row tiles (tile lists of the GEMMs)
+    for (int s = 0; s <= S; ++s) layout_info[4 + s] = s_base[s] / ANI_TILE_ROWS;
+    for (int s = S + 1; s <= ANI_MAX_SPECIES; ++s) layout_info[4 + s] = row / ANI_TILE_ROWS;
   }
   __syncthreads();
   const int n_tiles_cap = rows_cap / ANI_TILE_ROWS;

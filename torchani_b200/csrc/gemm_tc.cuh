@@ -1,0 +1,471 @@
+// Persistent, warp-specialised tcgen05 grouped GEMM for the ensemble MLP (sm_100a).
+//
+//   C[128-row tile, bn] = epilogue( A[128, K] x B[bn, K]^T )        both operands K-major fp32
+//
+// fp32 accuracy on the tensor cores ("3xTF32"): every fp32 operand is split into
+// hi = x & 0xffffe000 (exact TF32) and lo = x - hi (exact in fp32); the MMA thread issues three
+// kind::tf32 products per K-step (lo*hi, hi*lo, hi*hi) into one fp32 accumulator in tensor
+// memory.  The dropped lo*lo term is ~2^-22 relative.
+//   * B (weights) is split, tiled and swizzled ONCE at model-pack time (ani_b200.h, "tiled B
+//     operand"); a K-block of a tile is two contiguous byte ranges that one thread moves with
+//     cp.async.bulk (TMA) straight into the SWIZZLE_128B shared-memory layout.
+//   * A (activations) is split on the fly by the producer warps: coalesced 16-byte loads, the
+//     loads of K-block k+1 are in flight while K-block k is split and stored.
+//
+// Roles (13 warps, one CTA per SM, persistent over the device-side tile list):
+//   warps 0-3  epilogue : tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..32w+31);
+//                         global traffic is staged through a 32x32 shared-memory transpose so
+//                         that loads (old activation for CELU') and stores are 128-byte rows
+//   warp  4    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
+//   warps 5-12 producer : A split + swizzled st.shared + fence.proxy.async; thread 0 also
+//                         issues the bulk copies of B (mbarrier expect_tx / complete_tx)
+// Pipelines: smem full/empty (2 stages x 96 KB) and TMEM full/empty (2 x 256 columns), so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#pragma once
+#include "common.cuh"
+
+namespace ani {
+namespace tc {
+
+constexpr int TM = ANI_TILE_ROWS;        // 128 rows per tile == UMMA M
+constexpr int TN_MAX = 256;              // UMMA N (columns of one accumulator)
+constexpr int TK = 32;                   // fp32 per K-block = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = TM * 128;           // 16 KB
+constexpr int B_TILE_BYTES = TN_MAX * 128;       // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi+lo of A and B = 96 KB
+constexpr int EPI_LD = 36;                                  // padded row of the 32x32 transpose buffer (floats)
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;               // one buffer per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, FIRST_PROD_WARP = 5, NUM_PROD_WARPS = 8;
+constexpr int NPT = NUM_PROD_WARPS * 32;  // producer threads
+constexpr int THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 288
+constexpr int TMEM_COLS = 512;
+
+enum { EPI_BIAS_CELU = 0, EPI_MUL_DCELU = 1, EPI_PLAIN = 2 };
+
+struct Species {
+  const float* Bt;    // tiled B operand (hi/lo split, swizzled), see ani_b200.h
+  const float* bias;  // [N] (+ member * bias_mstride) or nullptr
+  int K, N;
+  int a_moff, c_moff, bias_mstride;
+};
+
+struct Args {
+  const float* A;
+  float* C;
+  int lda, ldc;
+  int members;                  // GEMMs per row tile (grid z of the SIMT version)
+  const int32_t* layout_info;   // [4 + S + 1]: ..., first row tile of species s, total row tiles
+  int num_species;
+  float alpha;
+  Species sp[ANI_MAX_SPECIES];
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion signalled on the mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, single CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// 16 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=bn
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ float celu(float x, float alpha) {
+  return x > 0.f ? x : alpha * (expf(x / alpha) - 1.0f);
+}
+__device__ __forceinline__ float dcelu_from_out(float y, float alpha) {
+  return y > 0.f ? 1.0f : (y + alpha) / alpha;
+}
+
+// ---- tile enumeration -----------------------------------------------------------------------
+// Row tiles of one species are contiguous; tile t -> (species, row tile, member, n0, bn).
+struct TileMap {
+  int first_rt[ANI_MAX_SPECIES + 1];   // first row tile of each species (+ total)
+  int ntn[ANI_MAX_SPECIES];            // N tiles per (row tile, member)
+  int prefix[ANI_MAX_SPECIES + 1];     // exclusive prefix of tile counts
+};
+
+struct Tile {
+  int s, rt, mem, n0, bn;
+};
+
+__device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm) {
+  const int S = a.num_species;
+  int run = 0;
+  for (int s = 0; s < S; ++s) {
+    tm.first_rt[s] = a.layout_info[4 + s];
+    tm.ntn[s] = (a.sp[s].N + TN_MAX - 1) / TN_MAX;
+  }
+  tm.first_rt[S] = a.layout_info[4 + S];
+  for (int s = 0; s < S; ++s) {
+    tm.prefix[s] = run;
+    run += (tm.first_rt[s + 1] - tm.first_rt[s]) * a.members * tm.ntn[s];
+  }
+  tm.prefix[S] = run;
+}
+
+__device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, int t) {
+  Tile x;
+  int s = 0;
+  while (t >= tm.prefix[s + 1]) ++s;
+  const int local = t - tm.prefix[s];
+  const int ntn = tm.ntn[s];
+  const int nt = local % ntn;
+  const int rm = local / ntn;
+  x.s = s;
+  x.mem = rm % a.members;
+  x.rt = tm.first_rt[s] + rm / a.members;
+  x.n0 = nt * TN_MAX;
+  x.bn = min(TN_MAX, a.sp[s].N - x.n0);
+  return x;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+__device__ __forceinline__ void split_store(unsigned char* st_hi, unsigned char* st_lo, int c, float4 v) {
+  const int row = c >> 3, ch = c & 7;
+  float4 hi, lo;
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+  lo.x = v.x - hi.x;
+  lo.y = v.y - hi.y;
+  lo.z = v.z - hi.z;
+  lo.w = v.w - hi.w;
+  const uint32_t off =
+      (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+  *reinterpret_cast<float4*>(st_hi + off) = hi;
+  *reinterpret_cast<float4*>(st_lo + off) = lo;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Args args) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte aligned operand tiles (SWIZZLE_128B atoms are 8 x 128 B)
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* epi_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
+  uint64_t* full = bars;                     // [STAGES]  producers (+ TMA bytes) -> MMA
+  uint64_t* empty = bars + STAGES;           // [STAGES]  MMA (commit) -> producers
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]       MMA (commit) -> epilogue
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  __shared__ TileMap tm;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    build_tile_map(args, tm);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], NPT + 1);  // every producer thread + the expect_tx arrival of the TMA thread
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], NUM_EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = tm.prefix[args.num_species];
+
+  if (warp >= FIRST_PROD_WARP) {
+    // ================================ producers ================================
+    const int pt = threadIdx.x - FIRST_PROD_WARP * 32;  // 0..NPT-1
+    constexpr int A_IT = (TM * 8) / NPT;                // 16-byte chunks of A per thread (4)
+    uint32_t stage = 0, phase = 0;
+    float4 cur[A_IT], nxt[A_IT];
+
+    auto load_a = [&](float4 (&dst)[A_IT], const float* __restrict__ A, int K, int k0) {
+#pragma unroll
+      for (int i = 0; i < A_IT; ++i) {
+        const int c = pt + i * NPT;
+        const int row = c >> 3, ch = c & 7;
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + ch * 4 < K) dst[i] = *reinterpret_cast<const float4*>(A + (size_t)row * args.lda + k0 + ch * 4);
+      }
+    };
+
+    int t = blockIdx.x;
+    Tile tl = {};
+    const float* A = nullptr;
+    int K = 0, nkb = 0;
+    if (t < total_tiles) {
+      tl = decode_tile(args, tm, t);
+      A = args.A + (size_t)tl.rt * TM * args.lda + (size_t)tl.mem * args.sp[tl.s].a_moff;
+      K = args.sp[tl.s].K;
+      nkb = (K + TK - 1) / TK;
+      load_a(cur, A, K, 0);
+    }
+    while (t < total_tiles) {
+      const Species& sp = args.sp[tl.s];
+      // tiled B: [member][n tile][k block][hi bn x 128 B | lo bn x 128 B]
+      const unsigned char* Bt = reinterpret_cast<const unsigned char*>(sp.Bt) +
+                                ((size_t)tl.mem * sp.N + (size_t)tl.n0) * nkb * 256;
+      const uint32_t b_bytes = (uint32_t)tl.bn * 128u;
+      // next tile (for the cross-tile prefetch of A)
+      const int t_next = t + gridDim.x;
+      Tile tl_next = {};
+      const float* A_next = nullptr;
+      int K_next = 0;
+      if (t_next < total_tiles) {
+        tl_next = decode_tile(args, tm, t_next);
+        A_next = args.A + (size_t)tl_next.rt * TM * args.lda + (size_t)tl_next.mem * args.sp[tl_next.s].a_moff;
+        K_next = args.sp[tl_next.s].K;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        // prefetch the A chunks of the next K-block (or of the next tile's first one)
+        if (kb + 1 < nkb) {
+          load_a(nxt, A, K, (kb + 1) * TK);
+        } else if (A_next) {
+          load_a(nxt, A_next, K_next, 0);
+        }
+        mbar_wait(&empty[stage], phase ^ 1);
+        unsigned char* st = smem + stage * STAGE_BYTES;
+        if (pt == 0) {
+          mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
+          const unsigned char* src = Bt + (size_t)kb * tl.bn * 256;
+          bulk_g2s(st + 2 * A_TILE_BYTES, src, b_bytes, &full[stage]);
+          bulk_g2s(st + 2 * A_TILE_BYTES + B_TILE_BYTES, src + b_bytes, b_bytes, &full[stage]);
+        }
+#pragma unroll
+        for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, cur[i]);
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&full[stage]);
+#pragma unroll
+        for (int i = 0; i < A_IT; ++i) cur[i] = nxt[i];
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      t = t_next;
+      tl = tl_next;
+      A = A_next;
+      K = K_next;
+      nkb = (K + TK - 1) / TK;
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================ MMA issuer ================================
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(args, tm, t);
+      const int nkb = (args.sp[tl.s].K + TK - 1) / TK;
+      const uint32_t idesc = make_idesc(tl.bn);
+      mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TN_MAX;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
+          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < TK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 B = 2 x 16 B along the swizzle row
+            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty[stage]);                   // smem slot free once these MMAs retire
+          if (kb == nkb - 1) umma_commit(&tfull[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    // Per 32-column chunk: (CELU' only) coalesced load of the stored activation into the warp's
+    // 32x32 buffer; tcgen05.ld (thread = row); elementwise op; result back into the buffer;
+    // coalesced 128-byte-row stores.
+    uint32_t acc = 0, acc_phase = 0;
+    const float alpha = args.alpha;
+    float* buf = epi_buf + warp * 32 * EPI_LD;
+    const int cr = lane >> 3, cq = (lane & 7) * 4;  // coalesced phase: row cr + 4*i, columns cq..cq+3
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(args, tm, t);
+      const Species& sp = args.sp[tl.s];
+      float* __restrict__ cbase =
+          args.C + (size_t)(tl.rt * TM + warp * 32) * args.ldc + (size_t)tl.mem * sp.c_moff + tl.n0;
+      const float* __restrict__ bias =
+          (EPI == EPI_BIAS_CELU) ? sp.bias + (size_t)tl.mem * sp.bias_mstride + tl.n0 : nullptr;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TN_MAX;
+      for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+        const int ncol = min(32, tl.bn - c0);  // 32 or 16 (bn is a multiple of 16)
+        if (EPI == EPI_MUL_DCELU) {
+          if (cq < ncol) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = cr + 4 * i;
+              *reinterpret_cast<float4*>(&buf[r * EPI_LD + cq]) =
+                  *reinterpret_cast<const float4*>(cbase + (size_t)r * args.ldc + c0 + cq);
+            }
+          }
+          __syncwarp();
+        }
+        float v[32];
+        {
+          float lo16[16];
+          tmem_ld16(taddr + c0, lo16);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = lo16[j];
+          if (ncol > 16) {
+            float hi16[16];
+            tmem_ld16(taddr + c0 + 16, hi16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[16 + j] = hi16[j];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (4 * q < ncol) {
+            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            float4* slot = reinterpret_cast<float4*>(&buf[lane * EPI_LD + 4 * q]);
+            if (EPI == EPI_BIAS_CELU) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
+              o.x = celu(o.x + b.x, alpha);
+              o.y = celu(o.y + b.y, alpha);
+              o.z = celu(o.z + b.z, alpha);
+              o.w = celu(o.w + b.w, alpha);
+            } else if (EPI == EPI_MUL_DCELU) {
+              const float4 y = *slot;
+              o.x *= dcelu_from_out(y.x, alpha);
+              o.y *= dcelu_from_out(y.y, alpha);
+              o.z *= dcelu_from_out(y.z, alpha);
+              o.w *= dcelu_from_out(y.w, alpha);
+            }
+            *slot = o;
+          }
+        }
+        __syncwarp();
+        if (cq < ncol) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = cr + 4 * i;
+            *reinterpret_cast<float4*>(cbase + (size_t)r * args.ldc + c0 + cq) =
+                *reinterpret_cast<const float4*>(&buf[r * EPI_LD + cq]);
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace ani

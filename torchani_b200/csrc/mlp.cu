@@ -7,153 +7,20 @@
 //     C[tile rows, N] = epilogue(A[tile rows, K] x B[K, N])
 // The 8 ensemble members share the layer-1 input, so layer 1 is one GEMM with the members
 // concatenated along N (the AEV is read once, not 8x as in BmmLinear's expand()).
-// Backward-to-input runs the same kernel on the natural-layout weights; CELU'(x) is recovered
+// Backward-to-input runs the same kernel on the transposed weights; CELU'(x) is recovered
 // from the stored activation y as (y > 0 ? 1 : (y + alpha) / alpha)  (csrc/mnp.cpp:206-209).
 //
-// v1 arithmetic: fp32 FFMA register-tiled GEMM (128x128x16 CTA tile, 8x8 per thread).
+// Arithmetic: tcgen05 tensor cores with an fp32-accurate 3xTF32 split (gemm_tc.cuh).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace ani {
 
-constexpr int BM = ANI_TILE_ROWS, BN = 128, BK = 16;
-constexpr int GEMM_THREADS = 256;
-
-enum { EPI_BIAS_CELU = 0, EPI_MUL_DCELU = 1, EPI_PLAIN = 2 };
-
-struct GemmSpecies {
-  const float* B;     // [K][ldb] (+ member * b_mstride)
-  const float* bias;  // (+ member * bias_mstride) or nullptr
-  int K, N, ldb;
-  int a_moff, c_moff, bias_mstride;  // per-member column offsets into A / C, bias stride
-  long long b_mstride;
-};
-
-struct GemmArgs {
-  const float* A;
-  float* C;
-  int lda, ldc;
-  const int32_t* tile_species;
-  float alpha;
-  GemmSpecies sp[ANI_MAX_SPECIES];
-};
-
-__device__ __forceinline__ float celu(float x, float alpha) {
-  return x > 0.f ? x : alpha * (expf(x / alpha) - 1.0f);
-}
 __device__ __forceinline__ float dcelu_from_out(float y, float alpha) {
   return y > 0.f ? 1.0f : (y + alpha) / alpha;
-}
-
-template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) k_gemm(const __grid_constant__ GemmArgs args) {
-  const int s = args.tile_species[blockIdx.y];
-  if (s < 0) return;
-  const GemmSpecies& sp = args.sp[s];
-  const int n0 = blockIdx.x * BN;
-  if (n0 >= sp.N) return;
-  const int mem = blockIdx.z;
-  const int row0 = blockIdx.y * BM;
-  const float* __restrict__ A = args.A + (size_t)row0 * args.lda + (size_t)mem * sp.a_moff;
-  const float* __restrict__ B = sp.B + (size_t)mem * sp.b_mstride;
-  float* __restrict__ C = args.C + (size_t)row0 * args.ldc + (size_t)mem * sp.c_moff;
-  const int K = sp.K, N = sp.N, lda = args.lda, ldb = sp.ldb;
-
-  __shared__ __align__(16) float As[BK][BM + 4];
-  __shared__ __align__(16) float Bs[BK][BN];
-
-  const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;
-  // global -> register staging
-  const int a_r0 = tid >> 2, a_kq = (tid & 3) * 4;            // rows a_r0 and a_r0 + 64
-  const int b_kr0 = tid >> 5, b_c = (tid & 31) * 4;            // k rows b_kr0 and b_kr0 + 8
-  const bool b_ok = (n0 + b_c) < N;
-  float4 ra[2], rb[2];
-
-  auto load_tiles = [&](int k0) {
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      ra[it] = *reinterpret_cast<const float4*>(A + (size_t)(a_r0 + it * 64) * lda + k0 + a_kq);
-      rb[it] = b_ok ? *reinterpret_cast<const float4*>(B + (size_t)(k0 + b_kr0 + it * 8) * ldb + n0 + b_c)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_tiles = [&]() {
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int r = a_r0 + it * 64;
-      As[a_kq + 0][r] = ra[it].x;
-      As[a_kq + 1][r] = ra[it].y;
-      As[a_kq + 2][r] = ra[it].z;
-      As[a_kq + 3][r] = ra[it].w;
-      *reinterpret_cast<float4*>(&Bs[b_kr0 + it * 8][b_c]) = rb[it];
-    }
-  };
-
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-  load_tiles(0);
-  store_tiles();
-  __syncthreads();
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    const bool more = (k0 + BK) < K;
-    if (more) load_tiles(k0 + BK);
-#pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-    if (more) {
-      store_tiles();
-      __syncthreads();
-    }
-  }
-
-  // ---- epilogue
-  const float* bias = (EPI == EPI_BIAS_CELU) ? sp.bias + (size_t)mem * sp.bias_mstride : nullptr;
-  const float alpha = args.alpha;
-#pragma unroll
-  for (int jh = 0; jh < 2; ++jh) {
-    const int c = n0 + jh * 64 + tx * 4;
-    if (c >= N) continue;
-    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (EPI == EPI_BIAS_CELU) bv = *reinterpret_cast<const float4*>(bias + c);
-#pragma unroll
-    for (int ih = 0; ih < 2; ++ih) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = ih * 64 + ty * 4 + i;
-        float* cp = C + (size_t)r * args.ldc + c;
-        float4 v = make_float4(acc[ih * 4 + i][jh * 4 + 0], acc[ih * 4 + i][jh * 4 + 1],
-                               acc[ih * 4 + i][jh * 4 + 2], acc[ih * 4 + i][jh * 4 + 3]);
-        if (EPI == EPI_BIAS_CELU) {
-          v.x = celu(v.x + bv.x, alpha);
-          v.y = celu(v.y + bv.y, alpha);
-          v.z = celu(v.z + bv.z, alpha);
-          v.w = celu(v.w + bv.w, alpha);
-        } else if (EPI == EPI_MUL_DCELU) {
-          const float4 y = *reinterpret_cast<const float4*>(cp);
-          v.x *= dcelu_from_out(y.x, alpha);
-          v.y *= dcelu_from_out(y.y, alpha);
-          v.z *= dcelu_from_out(y.z, alpha);
-          v.w *= dcelu_from_out(y.w, alpha);
-        }
-        *reinterpret_cast<float4*>(cp) = v;
-      }
-    }
-  }
 }
 
 // final layer (h3 -> 1) + seed of the backward pass; one warp per (row, member)
@@ -249,61 +116,73 @@ __global__ void __launch_bounds__(256) k_reduce_energies(const __grid_constant__
   }
 }
 
-template <int EPI>
-static void launch_gemm(const GemmArgs& ga, int n_tiles_cap, int n_max, int members, cudaStream_t st) {
-  dim3 grid((n_max + BN - 1) / BN, n_tiles_cap, members);
-  k_gemm<EPI><<<grid, GEMM_THREADS, 0, st>>>(ga);
-}
-
 }  // namespace ani
 
 using namespace ani;
 
+// tensor-core launch: one persistent CTA per SM walks the device-side tile list
+template <int EPI>
+static void launch_gemm_tc(const tc::Args& a, cudaStream_t st) {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  auto k = tc::k_gemm_tc<EPI>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    attr_set = true;
+  }
+  k<<<num_sms, tc::THREADS, tc::SMEM_BYTES, st>>>(a);
+}
+
 extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
-                                             const int32_t* tile_species, const int32_t* row_atom, float* act1,
-                                             float* act2, float* act3, float* e_member, int want_backward,
-                                             void* stream) {
-  if (!model || !x || !tile_species || !row_atom || !act1 || !act2 || !act3 || !e_member) return ANI_ERR_BAD_ARG;
+                                             const int32_t* tile_species, const int32_t* row_atom,
+                                             const int32_t* layout_info, float* act1, float* act2, float* act3,
+                                             float* e_member, int want_backward, void* stream) {
+  if (!model || !x || !tile_species || !row_atom || !layout_info || !act1 || !act2 || !act3 || !e_member)
+    return ANI_ERR_BAD_ARG;
   const int S = model->num_species, M = model->num_members;
   if (S < 1 || S > ANI_MAX_SPECIES || M < 1 || M > ANI_MAX_MEMBERS) return ANI_ERR_BAD_ARG;
   if (rows_cap < ANI_TILE_ROWS || rows_cap % ANI_TILE_ROWS) return ANI_ERR_BAD_ARG;
   const int ldx = model->ldx;
-  if (ldx % BK || ldx < model->in_dim) return ANI_ERR_BAD_ARG;
+  if (ldx % 32 || ldx < model->in_dim) return ANI_ERR_BAD_ARG;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    if (p.h1 % BK || p.h2 % BK || p.h3 % BK || p.h1 < BK || p.h2 < BK || p.h3 < BK) return ANI_ERR_UNSUPPORTED;
+    if (p.h1 % 16 || p.h2 % 16 || p.h3 % 16 || p.h1 < 16 || p.h2 < 16 || p.h3 < 16) return ANI_ERR_UNSUPPORTED;
     if (p.h1 > model->h1_max || p.h2 > model->h2_max || p.h3 > model->h3_max) return ANI_ERR_BAD_ARG;
-    if (!p.w1 || !p.b1 || !p.w2 || !p.b2 || !p.w3 || !p.b3 || !p.w4 || !p.b4 || !p.w3n || !p.w2n || !p.w1n)
+    if (!p.b1 || !p.b2 || !p.b3 || !p.w4 || !p.b4 || !p.t_f1 || !p.t_f2 || !p.t_f3 || !p.t_b3 || !p.t_b2 || !p.t_b1)
       return ANI_ERR_BAD_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int n_tiles_cap = rows_cap / ANI_TILE_ROWS;
   const int ld1 = M * model->h1_max, ld2 = M * model->h2_max, ld3 = M * model->h3_max;
-  GemmArgs ga;
-  ga.tile_species = tile_species;
-  ga.alpha = model->celu_alpha;
-  for (int s = S; s < ANI_MAX_SPECIES; ++s) ga.sp[s] = GemmSpecies{nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0};
+  tc::Args ta;
+  ta.layout_info = layout_info;
+  ta.num_species = S;
+  ta.alpha = model->celu_alpha;
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0};
 
-  // ---- forward layer 1: all members at once (N = M*h1)
-  ga.A = x; ga.lda = ldx; ga.C = act1; ga.ldc = ld1;
+  // ---- forward.  Layer 1: the members share the input -> one GEMM with N = M*h1.
+  ta.A = x; ta.lda = ldx; ta.C = act1; ta.ldc = ld1; ta.members = 1;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ga.sp[s] = GemmSpecies{p.w1, p.b1, ldx, M * p.h1, M * p.h1, 0, 0, 0, 0};
+    ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0};
   }
-  launch_gemm<EPI_BIAS_CELU>(ga, n_tiles_cap, M * model->h1_max, 1, st);
-  // ---- forward layer 2, 3: one GEMM per member (grid z)
-  ga.A = act1; ga.lda = ld1; ga.C = act2; ga.ldc = ld2;
+  launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
+  ta.A = act1; ta.lda = ld1; ta.C = act2; ta.ldc = ld2; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ga.sp[s] = GemmSpecies{p.w2, p.b2, p.h1, p.h2, p.h2, p.h1, p.h2, p.h2, (long long)p.h1 * p.h2};
+    ta.sp[s] = tc::Species{p.t_f2, p.b2, p.h1, p.h2, p.h1, p.h2, p.h2};
   }
-  launch_gemm<EPI_BIAS_CELU>(ga, n_tiles_cap, model->h2_max, M, st);
-  ga.A = act2; ga.lda = ld2; ga.C = act3; ga.ldc = ld3;
+  launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
+  ta.A = act2; ta.lda = ld2; ta.C = act3; ta.ldc = ld3; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ga.sp[s] = GemmSpecies{p.w3, p.b3, p.h2, p.h3, p.h3, p.h2, p.h3, p.h3, (long long)p.h2 * p.h3};
+    ta.sp[s] = tc::Species{p.t_f3, p.b3, p.h2, p.h3, p.h2, p.h3, p.h3};
   }
-  launch_gemm<EPI_BIAS_CELU>(ga, n_tiles_cap, model->h3_max, M, st);
+  launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
   // ---- head: energies + gradient seed
   {
     HeadArgs ha;
@@ -322,24 +201,24 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   }
   if (want_backward) {
     // ---- backward: G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
-    ga.A = act3; ga.lda = ld3; ga.C = act2; ga.ldc = ld2;
+    ta.A = act3; ta.lda = ld3; ta.C = act2; ta.ldc = ld2; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ga.sp[s] = GemmSpecies{p.w3n, nullptr, p.h3, p.h2, p.h2, p.h3, p.h2, 0, (long long)p.h3 * p.h2};
+      ta.sp[s] = tc::Species{p.t_b3, nullptr, p.h3, p.h2, p.h3, p.h2, 0};
     }
-    launch_gemm<EPI_MUL_DCELU>(ga, n_tiles_cap, model->h2_max, M, st);
-    ga.A = act2; ga.lda = ld2; ga.C = act1; ga.ldc = ld1;
+    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
+    ta.A = act2; ta.lda = ld2; ta.C = act1; ta.ldc = ld1; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ga.sp[s] = GemmSpecies{p.w2n, nullptr, p.h2, p.h1, p.h1, p.h2, p.h1, 0, (long long)p.h2 * p.h1};
+      ta.sp[s] = tc::Species{p.t_b2, nullptr, p.h2, p.h1, p.h2, p.h1, 0};
     }
-    launch_gemm<EPI_MUL_DCELU>(ga, n_tiles_cap, model->h1_max, M, st);
-    ga.A = act1; ga.lda = ld1; ga.C = x; ga.ldc = ldx;
+    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
+    ta.A = act1; ta.lda = ld1; ta.C = x; ta.ldc = ldx; ta.members = 1;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ga.sp[s] = GemmSpecies{p.w1n, nullptr, M * p.h1, ldx, ldx, 0, 0, 0, 0};
+      ta.sp[s] = tc::Species{p.t_b1, nullptr, M * p.h1, ldx, 0, 0, 0};
     }
-    launch_gemm<EPI_PLAIN>(ga, n_tiles_cap, ldx, 1, st);
+    launch_gemm_tc<tc::EPI_PLAIN>(ta, st);
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;

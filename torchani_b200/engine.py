@@ -94,6 +94,34 @@ def constants_1x(num_species: int = 4, cutoff_fn: str = "cosine") -> AEVConstant
                         _linspace(0.9, 3.5, 4), _linspace(a0, math.pi + a0, 8), cutoff_fn)
 
 
+def tile_b_operand(b: Tensor) -> Tensor:
+    """``B[N][K]`` (float32, K-major) -> the "tiled B operand" byte layout of include/ani_b200.h:
+    K zero-padded to 32, hi/lo TF32 split, [n tile of 256 rows][k block][hi bn x 128 B | lo bn x 128 B]
+    with every 8-row group in tcgen05 SWIZZLE_128B order.  Returned as a flat float32 tensor."""
+    n, k = b.shape
+    assert n % 8 == 0, "rows of a B operand must come in groups of 8"
+    kp = (k + 31) // 32 * 32
+    nkb = kp // 32
+    bp = torch.zeros(n, kp, dtype=torch.float32, device=b.device)
+    bp[:, :k] = b
+    hi = (bp.view(torch.int32) & -8192).view(torch.float32)   # 0xffffe000
+    lo = bp - hi
+    rows = torch.arange(8, device=b.device).view(8, 1)
+    pos = torch.arange(8, device=b.device).view(1, 8)
+    src_chunk = (pos ^ rows)                                    # chunk stored at position p of row r is p ^ r
+    out = []
+    for n0 in range(0, n, 256):
+        bn = min(256, n - n0)
+        parts = []
+        for part in (hi, lo):
+            x = part[n0:n0 + bn].view(bn // 8, 8, nkb, 8, 4)           # [group][row][kb][chunk][4]
+            x = x.permute(2, 0, 1, 3, 4)                                # [kb][group][row][chunk][4]
+            idx = src_chunk.view(1, 1, 8, 8, 1).expand(nkb, bn // 8, 8, 8, 4)
+            parts.append(torch.gather(x, 3, idx).reshape(nkb, bn * 32))
+        out.append(torch.stack(parts, 1).reshape(-1))                  # [kb][hi|lo][bn*32]
+    return torch.cat(out).contiguous()
+
+
 class PackedNetworks:
     """Device-resident, kernel-layout copy of an ensemble of per-element MLPs.
 
@@ -139,17 +167,18 @@ class PackedNetworks:
             w1n = torch.zeros(M * h1, self.ldx, **f32)
             w1n[:, :in_dim] = torch.cat(W[0], 0)
             t = {
-                "w1": w1n.t().contiguous(),                                   # [ldx][M*h1]
                 "b1": torch.cat(Bv[0]).contiguous(),
-                "w2": torch.stack([w.t().contiguous() for w in W[1]]).contiguous(),   # [M][h1][h2]
                 "b2": torch.cat(Bv[1]).contiguous(),
-                "w3": torch.stack([w.t().contiguous() for w in W[2]]).contiguous(),   # [M][h2][h3]
                 "b3": torch.cat(Bv[2]).contiguous(),
                 "w4": torch.cat(W[3], 0).contiguous(),                        # [M][h3]
                 "b4": torch.cat(Bv[3]).contiguous(),                          # [M]
-                "w3n": torch.stack(W[2]).contiguous(),                        # [M][h3][h2]
-                "w2n": torch.stack(W[1]).contiguous(),                        # [M][h2][h1]
-                "w1n": w1n.contiguous(),                                      # [M*h1][ldx]
+                # B operands [N][K] (K-major) of the six GEMMs, tiled for the tensor-core kernel
+                "t_f1": tile_b_operand(w1n),                                          # N = M*h1, K = ldx
+                "t_f2": torch.cat([tile_b_operand(w) for w in W[1]]),                 # per member [h2][h1]
+                "t_f3": torch.cat([tile_b_operand(w) for w in W[2]]),                 # per member [h3][h2]
+                "t_b3": torch.cat([tile_b_operand(w.t().contiguous()) for w in W[2]]),  # [h2][h3]
+                "t_b2": torch.cat([tile_b_operand(w.t().contiguous()) for w in W[1]]),  # [h1][h2]
+                "t_b1": tile_b_operand(w1n.t().contiguous()),                         # N = ldx, K = M*h1
             }
             sp = mdl.sp[s]
             sp.h1, sp.h2, sp.h3 = h1, h2, h3
@@ -204,7 +233,7 @@ class Workspace:
         self.row_of = torch.zeros(n, **i32)
         self.row_atom = torch.zeros(self.rows_cap, **i32)
         self.tile_species = torch.zeros(self.rows_cap // TILE, **i32)
-        self.layout_info = torch.zeros(4, **i32)
+        self.layout_info = torch.zeros(16, **i32)
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
@@ -322,7 +351,7 @@ class Engine:
             ptr(ws.status), st))
         self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
             C.byref(self.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species), ptr(ws.row_atom),
-            ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad), st))
+            ptr(ws.layout_info), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad), st))
         grad = None
         if want_grad:
             ws.grad.zero_()

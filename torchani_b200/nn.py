@@ -89,7 +89,7 @@ class _MLPFunction(torch.autograd.Function):
         row_of = torch.zeros(n, **i32)
         row_atom = torch.zeros(rows_cap, **i32)
         tile_species = torch.zeros(rows_cap // TILE, **i32)
-        layout_info = torch.zeros(4, **i32)
+        layout_info = torch.zeros(16, **i32)
         scratch = torch.zeros((n // 256 + 3) * 8 + 64, **i32)
         st = torch.cuda.current_stream(dev).cuda_stream
         L = _lib.lib()
@@ -108,8 +108,8 @@ class _MLPFunction(torch.autograd.Function):
         act3 = torch.empty(rows_cap, ld[2], dtype=torch.float32, device=dev)
         e_member = torch.zeros(M, rows_cap, dtype=torch.float32, device=dev)
         check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x), rows_cap, ptr(tile_species),
-                                              ptr(row_atom), ptr(act1), ptr(act2), ptr(act3), ptr(e_member),
-                                              int(want_grad), st), "mlp_forward_backward")
+                                              ptr(row_atom), ptr(layout_info), ptr(act1), ptr(act2), ptr(act3),
+                                              ptr(e_member), int(want_grad), st), "mlp_forward_backward")
         em_sorted = e_member[:, rows] * real.view(1, -1)          # (M, n) in `order` order
         out = torch.zeros(M, n, dtype=torch.float32, device=dev)
         out[:, order] = em_sorted
