@@ -12,6 +12,7 @@
  *   ani_b200_build_cells        neighbors.py:418-507,554-615 (_cell_list bucketing), utils.py:237-255
  *                               (map_to_central), csrc/cell_list.cpp:266-350
  *   ani_b200_species_layout     nn/_containers.py:412-415 (per-species nonzero/index_select)
+ *   ani_b200_active_aev_blocks  (no counterpart: exact block-sparsity of the AEV the reference ignores)
  *   ani_b200_aev_forward        neighbors.py:64-113,968-1002 + aev/_computer.py:274-350;
  *                               csrc/cuaev.cpp:189-246 (cuaev::run / run_with_half_nbrlist),
  *                               csrc/aev.cu:323-472,768-834 (K8/K9), :975-1039 (K4)
@@ -117,6 +118,14 @@ int ani_b200_species_layout(const float* spos, const ani_grid* grid, int n, int 
                             int32_t* tile_species, int32_t* layout_info, int32_t* scratch_i32,
                             void* stream);
 
+/* 2b. Active 32-column blocks of the AEV matrix: blocks[0] = count, blocks[1..] = ascending */
+/*    block ids whose columns belong to an element / element pair present among the real      */
+/*    atoms.  All other AEV columns are identically zero for every atom (and their gradient   */
+/*    is never consumed), so the MLP may skip them.  blocks i32[ldx/32 + 1]; scratch i32[1].   */
+int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, int num_species,
+                               int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* blocks,
+                               int32_t* scratch_i32, void* stream);
+
 /* 3. Fused neighbour search + AEV forward for sorted atoms lo..hi-1.                      */
 /*      row_of     row of the output matrix for each sorted atom (species-grouped rows for   */
 /*                 the fused engine, flat input index for the AEVComputer API)               */
@@ -186,10 +195,14 @@ typedef struct ani_mlp_model {
 /*    tile_species / row_atom / layout_info: outputs of ani_b200_species_layout              */
 /*    act1/2/3     f32[rows_cap][M*h{1,2,3}_max]  workspaces (activations, then gradients)    */
 /*    e_member     f32[M][rows_cap]     per-member atomic energies                            */
+/*    aev_blocks   output of ani_b200_active_aev_blocks or NULL (= every column is live).   */
+/*                 With a block list, layer 1 skips the dead K-blocks and dE/dAEV is written   */
+/*                 only for the live column blocks (the others keep their previous content).   */
 int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
                                   const int32_t* tile_species, const int32_t* row_atom,
-                                  const int32_t* layout_info, float* act1, float* act2, float* act3,
-                                  float* e_member, int want_backward, void* stream);
+                                  const int32_t* layout_info, const int32_t* aev_blocks, float* act1,
+                                  float* act2, float* act3, float* e_member, int want_backward,
+                                  void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
 /*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */

@@ -340,9 +340,66 @@ __global__ void k_layout_assign(const float4* __restrict__ spos, const ani_grid*
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Active 32-column blocks of the AEV: a column belongs to one neighbour species (radial) or one
+// species pair (angular); if that species / pair does not occur among the real atoms, the column
+// is identically zero for every atom and its gradient is never consumed.
+// ---------------------------------------------------------------------------------------
+__global__ void k_species_present(const float4* __restrict__ spos, const ani_grid* __restrict__ grid, int n,
+                                  int32_t* __restrict__ present) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int sp = (i < n && i < grid->n_real) ? __float_as_int(spos[i].w) : -1;
+  unsigned mask = 0;
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s)
+    if (__any_sync(ANI_FULL_MASK, sp == s)) mask |= 1u << s;
+  if ((threadIdx.x & 31) == 0 && mask) atomicOr(present, (int)mask);
+}
+
+__global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int n_shf_r, int angular_sub,
+                                int out_dim, int ldx, int32_t* __restrict__ blocks) {
+  if (threadIdx.x != 0) return;
+  const unsigned mask = (unsigned)*present;
+  const int RL = S * n_shf_r;
+  int count = 0;
+  for (int b = 0; b < ldx / 32; ++b) {
+    bool active = false;
+    for (int c = b * 32; c < b * 32 + 32 && c < out_dim && !active; ++c) {
+      if (c < RL) {
+        active = (mask >> (c / n_shf_r)) & 1u;
+      } else {
+        const int p = (c - RL) / angular_sub;
+        // invert the row-major upper-triangle pair index
+        int s1 = 0, rem = p;
+        while (rem >= S - s1) {
+          rem -= S - s1;
+          ++s1;
+        }
+        const int s2 = s1 + rem;
+        active = ((mask >> s1) & 1u) && ((mask >> s2) & 1u);
+      }
+    }
+    if (active) blocks[1 + count++] = b;
+  }
+  blocks[0] = count;
+}
+
 }  // namespace ani
 
 using namespace ani;
+
+extern "C" int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, int num_species,
+                                          int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* blocks,
+                                          int32_t* scratch_i32, void* stream) {
+  if (!spos || !grid || !blocks || !scratch_i32) return ANI_ERR_BAD_ARG;
+  if (num_species < 1 || num_species > ANI_MAX_SPECIES || n_shf_r < 1 || angular_sub < 1 || ldx % 32 || out_dim > ldx)
+    return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch_i32, 0, sizeof(int32_t), st);
+  k_species_present<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(spos), grid, n, scratch_i32);
+  k_active_blocks<<<1, 32, 0, st>>>(scratch_i32, num_species, n_shf_r, angular_sub, out_dim, ldx, blocks);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
 
 extern "C" int ani_b200_build_cells(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
                                     const float* cell, int pbc, int mode, float cutoff, int max_bins,

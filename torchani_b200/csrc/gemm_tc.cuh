@@ -57,6 +57,8 @@ struct Args {
   int lda, ldc;
   int members;                  // GEMMs per row tile (grid z of the SIMT version)
   const int32_t* layout_info;   // [4 + S + 1]: ..., first row tile of species s, total row tiles
+  const int32_t* kblocks;       // optional list of live 32-wide K-blocks: [count, ids...]  (layer-1 forward)
+  const int32_t* nblocks;       // optional list of live 32-wide column blocks of C          (layer-1 backward)
   int num_species;
   float alpha;
   Species sp[ANI_MAX_SPECIES];
@@ -164,10 +166,14 @@ __device__ __forceinline__ float dcelu_from_out(float y, float alpha) {
 
 // ---- tile enumeration -----------------------------------------------------------------------
 // Row tiles of one species are contiguous; tile t -> (species, row tile, member, n0, bn).
+constexpr int MAX_BLOCKS = 64;         // ldx / 32 <= 64
 struct TileMap {
   int first_rt[ANI_MAX_SPECIES + 1];   // first row tile of each species (+ total)
   int ntn[ANI_MAX_SPECIES];            // N tiles per (row tile, member)
   int prefix[ANI_MAX_SPECIES + 1];     // exclusive prefix of tile counts
+  int n_eff[ANI_MAX_SPECIES];          // columns actually computed (compacted when nblocks is given)
+  int kb_count, nb_count;              // live K-blocks (-1: dense) / live column blocks (-1: dense)
+  int kb[MAX_BLOCKS], nb[MAX_BLOCKS];
 };
 
 struct Tile {
@@ -177,9 +183,19 @@ struct Tile {
 __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm) {
   const int S = a.num_species;
   int run = 0;
+  tm.kb_count = tm.nb_count = -1;
+  if (a.kblocks) {
+    tm.kb_count = min(a.kblocks[0], MAX_BLOCKS);
+    for (int i = 0; i < tm.kb_count; ++i) tm.kb[i] = a.kblocks[1 + i];
+  }
+  if (a.nblocks) {
+    tm.nb_count = min(a.nblocks[0], MAX_BLOCKS);
+    for (int i = 0; i < tm.nb_count; ++i) tm.nb[i] = a.nblocks[1 + i];
+  }
   for (int s = 0; s < S; ++s) {
     tm.first_rt[s] = a.layout_info[4 + s];
-    tm.ntn[s] = (a.sp[s].N + TN_MAX - 1) / TN_MAX;
+    tm.n_eff[s] = tm.nb_count >= 0 ? tm.nb_count * 32 : a.sp[s].N;
+    tm.ntn[s] = (tm.n_eff[s] + TN_MAX - 1) / TN_MAX;
   }
   tm.first_rt[S] = a.layout_info[4 + S];
   for (int s = 0; s < S; ++s) {
@@ -201,7 +217,7 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
   x.mem = rm % a.members;
   x.rt = tm.first_rt[s] + rm / a.members;
   x.n0 = nt * TN_MAX;
-  x.bn = min(TN_MAX, a.sp[s].N - x.n0);
+  x.bn = min(TN_MAX, tm.n_eff[s] - x.n0);
   return x;
 }
 
@@ -275,6 +291,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       }
     };
 
+    // K-blocks may be a compacted list of live blocks (layer-1 forward)
+    auto num_kb = [&](int K) { return tm.kb_count >= 0 ? tm.kb_count : (K + TK - 1) / TK; };
+    auto kb_id = [&](int i) { return tm.kb_count >= 0 ? tm.kb[i] : i; };
     int t = blockIdx.x;
     Tile tl = {};
     const float* A = nullptr;
@@ -283,14 +302,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       tl = decode_tile(args, tm, t);
       A = args.A + (size_t)tl.rt * TM * args.lda + (size_t)tl.mem * args.sp[tl.s].a_moff;
       K = args.sp[tl.s].K;
-      nkb = (K + TK - 1) / TK;
-      load_a(cur, A, K, 0);
+      nkb = num_kb(K);
+      if (nkb > 0) load_a(cur, A, K, kb_id(0) * TK);
     }
     while (t < total_tiles) {
       const Species& sp = args.sp[tl.s];
       // tiled B: [member][n tile][k block][hi bn x 128 B | lo bn x 128 B]
-      const unsigned char* Bt = reinterpret_cast<const unsigned char*>(sp.Bt) +
-                                ((size_t)tl.mem * sp.N + (size_t)tl.n0) * nkb * 256;
+      const int nkb_all = (K + TK - 1) / TK;  // K-blocks of the stored operand
+      const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) + (size_t)tl.mem * sp.N * nkb_all * 256;
+      const unsigned char* Bt = Bm + (size_t)tl.n0 * nkb_all * 256;
       const uint32_t b_bytes = (uint32_t)tl.bn * 128u;
       // next tile (for the cross-tile prefetch of A)
       const int t_next = t + gridDim.x;
@@ -305,17 +325,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       for (int kb = 0; kb < nkb; ++kb) {
         // prefetch the A chunks of the next K-block (or of the next tile's first one)
         if (kb + 1 < nkb) {
-          load_a(nxt, A, K, (kb + 1) * TK);
+          load_a(nxt, A, K, kb_id(kb + 1) * TK);
         } else if (A_next) {
-          load_a(nxt, A_next, K_next, 0);
+          load_a(nxt, A_next, K_next, kb_id(0) * TK);
         }
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char* st = smem + stage * STAGE_BYTES;
         if (pt == 0) {
           mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
-          const unsigned char* src = Bt + (size_t)kb * tl.bn * 256;
-          bulk_g2s(st + 2 * A_TILE_BYTES, src, b_bytes, &full[stage]);
-          bulk_g2s(st + 2 * A_TILE_BYTES + B_TILE_BYTES, src + b_bytes, b_bytes, &full[stage]);
+          const int kbi = kb_id(kb);
+          if (tm.nb_count < 0) {
+            const unsigned char* src = Bt + (size_t)kbi * tl.bn * 256;
+            bulk_g2s(st + 2 * A_TILE_BYTES, src, b_bytes, &full[stage]);
+            bulk_g2s(st + 2 * A_TILE_BYTES + B_TILE_BYTES, src + b_bytes, b_bytes, &full[stage]);
+          } else {
+            // gathered column blocks: 32 rows (4 KB) of the stored operand per live block
+            for (int q = 0; q < tl.bn / 32; ++q) {
+              const int row0 = tm.nb[tl.n0 / 32 + q] * 32;
+              const int n0s = row0 / TN_MAX * TN_MAX;
+              const int bns = min(TN_MAX, sp.N - n0s);
+              const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * 256 + (size_t)(row0 - n0s) * 128;
+              bulk_g2s(st + 2 * A_TILE_BYTES + q * 4096, src, 4096, &full[stage]);
+              bulk_g2s(st + 2 * A_TILE_BYTES + B_TILE_BYTES + q * 4096, src + (size_t)bns * 128, 4096, &full[stage]);
+            }
+          }
         }
 #pragma unroll
         for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, cur[i]);
@@ -332,14 +365,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       tl = tl_next;
       A = A_next;
       K = K_next;
-      nkb = (K + TK - 1) / TK;
+      nkb = num_kb(K);
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ================================
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode_tile(args, tm, t);
-      const int nkb = (args.sp[tl.s].K + TK - 1) / TK;
+      const int nkb = tm.kb_count >= 0 ? tm.kb_count : (args.sp[tl.s].K + TK - 1) / TK;
       const uint32_t idesc = make_idesc(tl.bn);
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
@@ -384,8 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
-      float* __restrict__ cbase =
-          args.C + (size_t)(tl.rt * TM + warp * 32) * args.ldc + (size_t)tl.mem * sp.c_moff + tl.n0;
+      float* __restrict__ crow0 = args.C + (size_t)(tl.rt * TM + warp * 32) * args.ldc + (size_t)tl.mem * sp.c_moff;
       const float* __restrict__ bias =
           (EPI == EPI_BIAS_CELU) ? sp.bias + (size_t)tl.mem * sp.bias_mstride + tl.n0 : nullptr;
       mbar_wait(&tfull[acc], acc_phase);
@@ -393,13 +425,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TN_MAX;
       for (int c0 = 0; c0 < tl.bn; c0 += 32) {
         const int ncol = min(32, tl.bn - c0);  // 32 or 16 (bn is a multiple of 16)
+        // first column of this chunk in C (compacted column blocks map back to their place)
+        float* __restrict__ cbase = crow0 + (tm.nb_count >= 0 ? tm.nb[(tl.n0 + c0) / 32] * 32 : tl.n0 + c0);
         if (EPI == EPI_MUL_DCELU) {
           if (cq < ncol) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = cr + 4 * i;
               *reinterpret_cast<float4*>(&buf[r * EPI_LD + cq]) =
-                  *reinterpret_cast<const float4*>(cbase + (size_t)r * args.ldc + c0 + cq);
+                  *reinterpret_cast<const float4*>(cbase + (size_t)r * args.ldc + cq);
             }
           }
           __syncwarp();
@@ -443,7 +477,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = cr + 4 * i;
-            *reinterpret_cast<float4*>(cbase + (size_t)r * args.ldc + c0 + cq) =
+            *reinterpret_cast<float4*>(cbase + (size_t)r * args.ldc + cq) =
                 *reinterpret_cast<const float4*>(&buf[r * EPI_LD + cq]);
           }
         }

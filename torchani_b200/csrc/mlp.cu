@@ -140,8 +140,9 @@ static void launch_gemm_tc(const tc::Args& a, cudaStream_t st) {
 
 extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
                                              const int32_t* tile_species, const int32_t* row_atom,
-                                             const int32_t* layout_info, float* act1, float* act2, float* act3,
-                                             float* e_member, int want_backward, void* stream) {
+                                             const int32_t* layout_info, const int32_t* aev_blocks, float* act1,
+                                             float* act2, float* act3, float* e_member, int want_backward,
+                                             void* stream) {
   if (!model || !x || !tile_species || !row_atom || !layout_info || !act1 || !act2 || !act3 || !e_member)
     return ANI_ERR_BAD_ARG;
   const int S = model->num_species, M = model->num_members;
@@ -160,6 +161,8 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   const int ld1 = M * model->h1_max, ld2 = M * model->h2_max, ld3 = M * model->h3_max;
   tc::Args ta;
   ta.layout_info = layout_info;
+  ta.kblocks = nullptr;
+  ta.nblocks = nullptr;
   ta.num_species = S;
   ta.alpha = model->celu_alpha;
   for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0};
@@ -170,7 +173,9 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
     const ani_mlp_species& p = model->sp[s];
     ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0};
   }
+  ta.kblocks = aev_blocks;  // dead AEV column blocks contribute exact zeros: skip them
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
+  ta.kblocks = nullptr;
   ta.A = act1; ta.lda = ld1; ta.C = act2; ta.ldc = ld2; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
@@ -218,7 +223,9 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
       const ani_mlp_species& p = model->sp[s];
       ta.sp[s] = tc::Species{p.t_b1, nullptr, M * p.h1, ldx, 0, 0, 0};
     }
+    ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
     launch_gemm_tc<tc::EPI_PLAIN>(ta, st);
+    ta.nblocks = nullptr;
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;

@@ -234,6 +234,7 @@ class Workspace:
         self.row_atom = torch.zeros(self.rows_cap, **i32)
         self.tile_species = torch.zeros(self.rows_cap // TILE, **i32)
         self.layout_info = torch.zeros(16, **i32)
+        self.aev_blocks = torch.zeros(ldx // 32 + 1, **i32)
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
@@ -345,13 +346,18 @@ class Engine:
         self._timed("species_layout", lambda: L.ani_b200_species_layout(
             ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species, ws.rows_cap, ptr(ws.row_of),
             ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info), ptr(ws.scratch), st))
+        c = self.consts
+        self._timed("species_layout", lambda: L.ani_b200_active_aev_blocks(
+            ptr(ws.spos), ptr(ws.grid), n, c.num_species, len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim,
+            self.nets.ldx, ptr(ws.aev_blocks), ptr(ws.scratch), st))
         self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
             C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin), n, lo, hi,
             ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
             ptr(ws.status), st))
         self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
             C.byref(self.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species), ptr(ws.row_atom),
-            ptr(ws.layout_info), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad), st))
+            ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
+            int(want_grad), st))
         grad = None
         if want_grad:
             ws.grad.zero_()
@@ -365,8 +371,8 @@ class Engine:
             ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
             ptr(ws.member_atomic), ptr(ws.energies), st))
         # kernels launched by this library in one step (memsets excluded):
-        #   build_cells 5, layout 3, aev fwd 1, mlp 4 (+3 bwd), aev bwd 1, reduce 1
-        self.launches_per_step = 5 + 3 + 1 + 4 + (4 if want_grad else 0) + 1
+        #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 4 (+3 bwd), aev bwd 1, reduce 1
+        self.launches_per_step = 5 + 5 + 1 + 4 + (4 if want_grad else 0) + 1
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
                           ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
 

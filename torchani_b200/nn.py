@@ -108,7 +108,7 @@ class _MLPFunction(torch.autograd.Function):
         act3 = torch.empty(rows_cap, ld[2], dtype=torch.float32, device=dev)
         e_member = torch.zeros(M, rows_cap, dtype=torch.float32, device=dev)
         check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x), rows_cap, ptr(tile_species),
-                                              ptr(row_atom), ptr(layout_info), ptr(act1), ptr(act2), ptr(act3),
+                                              ptr(row_atom), ptr(layout_info), None, ptr(act1), ptr(act2), ptr(act3),
                                               ptr(e_member), int(want_grad), st), "mlp_forward_backward")
         em_sorted = e_member[:, rows] * real.view(1, -1)          # (M, n) in `order` order
         out = torch.zeros(M, n, dtype=torch.float32, device=dev)
