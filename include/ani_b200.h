@@ -161,13 +161,13 @@ int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, 
 /* 6. Ensemble MLP forward + backward-to-input on the species-grouped AEV matrix.           */
 /*    Layer widths: in -> h1 -> h2 -> h3 -> 1, CELU(alpha) after the three hidden layers.    */
 /*    "tiled B operand" of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K]):     */
-/*    K is zero-padded to a multiple of 32, every value is split into hi = x & 0xffffe000 and    */
+/*    K is zero-padded to a multiple of 16, every value is split into hi = x & 0xffffe000 and    */
 /*    lo = x - hi, and the result is stored as                                                    */
-/*        [member][n tile (256 rows, the last one shorter)][k block (32 floats)]                   */
-/*        [hi: bn rows x 128 B][lo: bn rows x 128 B]                                              */
-/*    where every 8-row x 128-byte group is written in the tcgen05 SWIZZLE_128B order (16-byte     */
-/*    chunk c of row r sits at chunk position c ^ (r & 7)).  One K-block of one tile is therefore  */
-/*    two contiguous byte ranges that a single cp.async.bulk moves into shared memory.            */
+/*        [member][n tile (256 rows, the last one shorter)][k block (16 floats)]                   */
+/*        [hi: bn rows x 64 B][lo: bn rows x 64 B]                                                */
+/*    where every 8-row x 64-byte group is written in the tcgen05 SWIZZLE_64B order (16-byte       */
+/*    chunk c of row r sits at chunk position c ^ ((r >> 1) & 3)).  One K-block of one tile is     */
+/*    therefore two contiguous byte ranges that a single cp.async.bulk moves into shared memory.  */
 typedef struct ani_mlp_species {
   int32_t h1, h2, h3, pad_;
   const float* b1;   /* [M*h1]                                                                  */

@@ -42,8 +42,8 @@ def test_unsupported_configurations_are_rejected_loudly():
 
 def _untile(t, n, k):
     """Inverse of engine.tile_b_operand (numpy, element-wise from the documented layout)."""
-    kp = (k + 31) // 32 * 32
-    nkb = kp // 32
+    kp = (k + 15) // 16 * 16
+    nkb = kp // 16
     t = t.numpy()
     hi = np.zeros((n, kp), np.float32)
     lo = np.zeros((n, kp), np.float32)
@@ -52,21 +52,22 @@ def _untile(t, n, k):
         bn = min(256, n - n0)
         rr = r - n0
         for kb in range(nkb):
-            for ch in range(8):
-                base = n0 * nkb * 64 + kb * bn * 64 + (rr // 8) * 256 + (rr % 8) * 32 + ((ch ^ (rr % 8)) * 4)
-                hi[r, kb * 32 + ch * 4: kb * 32 + ch * 4 + 4] = t[base: base + 4]
-                lo[r, kb * 32 + ch * 4: kb * 32 + ch * 4 + 4] = t[base + bn * 32: base + bn * 32 + 4]
+            for ch in range(4):
+                base = n0 * nkb * 32 + kb * bn * 32 + (rr // 8) * 128 + (rr % 8) * 16 + ((ch ^ ((rr >> 1) & 3)) * 4)
+                hi[r, kb * 16 + ch * 4: kb * 16 + ch * 4 + 4] = t[base: base + 4]
+                lo[r, kb * 16 + ch * 4: kb * 16 + ch * 4 + 4] = t[base + bn * 16: base + bn * 16 + 4]
     return hi, lo
 
 
 def test_weight_packing_layout():
     from torchani_b200.engine import PackedNetworks, tile_b_operand
     # the tiled / split / swizzled B operand round-trips and hi + lo == x exactly
-    b = torch.randn(272, 48, generator=torch.Generator().manual_seed(0))
-    hi, lo = _untile(tile_b_operand(b), 272, 48)
-    assert np.array_equal((hi + lo)[:, :48], b.numpy()) and float(np.abs(hi[:, 48:]).max()) == 0.0
+    b = torch.randn(272, 40, generator=torch.Generator().manual_seed(0))
+    hi, lo = _untile(tile_b_operand(b), 272, 40)
+    assert hi.shape == (272, 48)                                      # K padded to a multiple of 16
+    assert np.array_equal((hi + lo)[:, :40], b.numpy()) and float(np.abs(hi[:, 40:]).max()) == 0.0
     assert np.array_equal(hi.view(np.int32) & 0x1fff, np.zeros_like(hi, dtype=np.int32))  # exact TF32
-    assert np.abs(lo[:, :48]).max() <= np.abs(b.numpy()).max() * 2.0 ** -10
+    assert np.abs(lo[:, :40]).max() <= np.abs(b.numpy()).max() * 2.0 ** -10
     m = oracle_model("2x", members=3)
     w = [[wm[s] for s in m.symbols] for wm in m.weights]
     nets = PackedNetworks(w, 1008, torch.device("cpu"))
@@ -74,18 +75,18 @@ def test_weight_packing_layout():
     names = ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
     sp0 = dict(zip(names, nets._keep[:11]))
     # layer 1: members stacked along N, K padded to ldx with zeros
-    hi, lo = _untile(sp0["t_f1"][: 256 * 32 * 64], 256, 1024)       # first n tile = member 0
+    hi, lo = _untile(sp0["t_f1"][: 256 * 64 * 32], 256, 1024)       # first n tile = member 0
     assert np.array_equal((hi + lo)[:, :1008], m.weights[0]["H"][0][0].numpy())
     assert float(np.abs(hi[:, 1008:]).max()) == 0.0
     # per-member layer 2 (forward: W2 [h2][h1]; backward: W2^T [h1][h2])
-    per = 192 * 8 * 64
+    per = 192 * 16 * 32
     hi, lo = _untile(sp0["t_f2"][2 * per: 3 * per], 192, 256)
     assert np.array_equal(hi + lo, m.weights[2]["H"][1][0].numpy())
-    per = 256 * 6 * 64
+    per = 256 * 12 * 32
     hi, lo = _untile(sp0["t_b2"][per: 2 * per], 256, 192)
     assert np.array_equal(hi + lo, m.weights[1]["H"][1][0].t().numpy())
     assert torch.equal(sp0["w4"][2], m.weights[2]["H"][3][0][0])
-    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 32) * 64
+    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 16) * 32
     nets.set_active_members([0, 2])
     assert list(nets.model.member_scale)[:3] == [0.5, 0.0, 0.5]
     with pytest.raises(IndexError):

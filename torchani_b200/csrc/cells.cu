@@ -357,30 +357,33 @@ __global__ void k_species_present(const float4* __restrict__ spos, const ani_gri
 
 __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int n_shf_r, int angular_sub,
                                 int out_dim, int ldx, int32_t* __restrict__ blocks) {
-  if (threadIdx.x != 0) return;
+  // one warp; lane c tests column b*32 + c of block b, the ballot decides, lane 0 appends
   const unsigned mask = (unsigned)*present;
   const int RL = S * n_shf_r;
+  const int lane = threadIdx.x;
   int count = 0;
   for (int b = 0; b < ldx / 32; ++b) {
+    const int c = b * 32 + lane;
     bool active = false;
-    for (int c = b * 32; c < b * 32 + 32 && c < out_dim && !active; ++c) {
+    if (c < out_dim) {
       if (c < RL) {
         active = (mask >> (c / n_shf_r)) & 1u;
       } else {
-        const int p = (c - RL) / angular_sub;
         // invert the row-major upper-triangle pair index
-        int s1 = 0, rem = p;
+        int s1 = 0, rem = (c - RL) / angular_sub;
         while (rem >= S - s1) {
           rem -= S - s1;
           ++s1;
         }
-        const int s2 = s1 + rem;
-        active = ((mask >> s1) & 1u) && ((mask >> s2) & 1u);
+        active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
       }
     }
-    if (active) blocks[1 + count++] = b;
+    if (__any_sync(ANI_FULL_MASK, active)) {
+      if (lane == 0) blocks[1 + count] = b;
+      ++count;
+    }
   }
-  blocks[0] = count;
+  if (lane == 0) blocks[0] = count;
 }
 
 }  // namespace ani

@@ -19,7 +19,8 @@
 //   warp  4    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
 //   warps 5-12 producer : A split + swizzled st.shared + fence.proxy.async; thread 0 also
 //                         issues the bulk copies of B (mbarrier expect_tx / complete_tx)
-// Pipelines: smem full/empty (2 stages x 96 KB) and TMEM full/empty (2 x 256 columns), so the
+// Pipelines: smem full/empty (4 stages x 48 KB: three K-blocks in flight cover the L2/HBM latency
+// of the one being multiplied) and TMEM full/empty (2 x 256 columns), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include "common.cuh"
@@ -29,11 +30,13 @@ namespace tc {
 
 constexpr int TM = ANI_TILE_ROWS;        // 128 rows per tile == UMMA M
 constexpr int TN_MAX = 256;              // UMMA N (columns of one accumulator)
-constexpr int TK = 32;                   // fp32 per K-block = one 128-byte swizzle row
-constexpr int STAGES = 2;
-constexpr int A_TILE_BYTES = TM * 128;           // 16 KB
-constexpr int B_TILE_BYTES = TN_MAX * 128;       // 32 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi+lo of A and B = 96 KB
+constexpr int TK = 16;                   // fp32 per K-block = one 64-byte swizzle row (SWIZZLE_64B)
+constexpr int ROW_BYTES = TK * 4;        // 64
+constexpr int GROUP_BYTES = 8 * ROW_BYTES;       // 8-row swizzle group = 512 B (descriptor SBO)
+constexpr int STAGES = 4;
+constexpr int A_TILE_BYTES = TM * ROW_BYTES;     // 8 KB
+constexpr int B_TILE_BYTES = TN_MAX * ROW_BYTES; // 16 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi+lo of A and B = 48 KB
 constexpr int EPI_LD = 36;                                  // padded row of the 32x32 transpose buffer (floats)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;               // one buffer per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -42,13 +45,15 @@ constexpr int NPT = NUM_PROD_WARPS * 32;  // producer threads
 constexpr int THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 288
 constexpr int TMEM_COLS = 512;
 
-enum { EPI_BIAS_CELU = 0, EPI_MUL_DCELU = 1, EPI_PLAIN = 2 };
+enum { EPI_BIAS_CELU = 0, EPI_MUL_DCELU = 1, EPI_PLAIN = 2, EPI_HEAD = 3 };
 
 struct Species {
   const float* Bt;    // tiled B operand (hi/lo split, swizzled), see ani_b200.h
   const float* bias;  // [N] (+ member * bias_mstride) or nullptr
   int K, N;
   int a_moff, c_moff, bias_mstride;
+  const float* w4;    // EPI_HEAD: final layer weights [M][N] and biases [M]
+  const float* b4;
 };
 
 struct Args {
@@ -61,6 +66,12 @@ struct Args {
   const int32_t* nblocks;       // optional list of live 32-wide column blocks of C          (layer-1 backward)
   int num_species;
   float alpha;
+  // EPI_HEAD (layer 3 + final layer + gradient seed fused in the epilogue)
+  float* e_member;              // [M][rows_cap]
+  const int32_t* row_atom;      // [rows_cap], -1 for padding rows
+  int rows_cap;
+  int want_backward;
+  float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
 };
 
@@ -142,26 +153,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+// shared-memory matrix descriptor: K-major, SWIZZLE_64B, 8-row groups 512 B apart
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
   d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row groups
+  d |= (uint64_t)(GROUP_BYTES >> 4) << 32;       // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
   return d;
+}
+// byte offset of 16-byte chunk `ch` (0..3) of row `row` inside a K-major SWIZZLE_64B tile
+__device__ __forceinline__ uint32_t swz_off(int row, int ch) {
+  return (uint32_t)(row >> 3) * GROUP_BYTES + (uint32_t)(row & 7) * ROW_BYTES + (uint32_t)((ch ^ ((row >> 1) & 3)) << 4);
 }
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
-__device__ __forceinline__ float celu(float x, float alpha) {
-  return x > 0.f ? x : alpha * (expf(x / alpha) - 1.0f);
+// CELU(x) = max(0,x) + min(0, alpha*(exp(x/alpha)-1)) with exp via ex2.approx (rel. error ~2^-22:
+// the negative branch is bounded by alpha, so the absolute error is < 1e-8 for alpha = 0.1)
+struct CeluConst {
+  float alpha, inv_alpha, inv_alpha_log2e;
+};
+__device__ __forceinline__ float celu(float x, const CeluConst& c) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * c.inv_alpha_log2e));
+  return x > 0.f ? x : fmaf(c.alpha, e, -c.alpha);
 }
-__device__ __forceinline__ float dcelu_from_out(float y, float alpha) {
-  return y > 0.f ? 1.0f : (y + alpha) / alpha;
+__device__ __forceinline__ float dcelu_from_out(float y, const CeluConst& c) {
+  return y > 0.f ? 1.0f : fmaf(y, c.inv_alpha, 1.0f);
 }
 
 // ---- tile enumeration -----------------------------------------------------------------------
@@ -223,7 +245,7 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
 
 // ---- the kernel -----------------------------------------------------------------------------
 __device__ __forceinline__ void split_store(unsigned char* st_hi, unsigned char* st_lo, int c, float4 v) {
-  const int row = c >> 3, ch = c & 7;
+  const int row = c >> 2, ch = c & 3;
   float4 hi, lo;
   hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
   hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
@@ -233,16 +255,23 @@ __device__ __forceinline__ void split_store(unsigned char* st_hi, unsigned char*
   lo.y = v.y - hi.y;
   lo.z = v.z - hi.z;
   lo.w = v.w - hi.w;
-  const uint32_t off =
-      (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+  const uint32_t off = swz_off(row, ch);
   *reinterpret_cast<float4*>(st_hi + off) = hi;
   *reinterpret_cast<float4*>(st_lo + off) = lo;
 }
 
+// position of a producer in the flattened (tile, K-block) sequence of its CTA
+struct KItem {
+  int t, kb, nkb, K;
+  Tile tl;
+  const float* A;
+  bool valid;
+};
+
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Args args) {
   extern __shared__ unsigned char smem_raw[];
-  // 1024-byte aligned operand tiles (SWIZZLE_128B atoms are 8 x 128 B)
+  // 1024-byte aligned operand tiles (swizzle groups are 8 rows x 64 B)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* epi_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
@@ -258,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   if (threadIdx.x == 0) {
     build_tile_map(args, tm);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], NPT + 1);  // every producer thread + the expect_tx arrival of the TMA thread
+      mbar_init(&full[i], NUM_PROD_WARPS + 1);  // one arrival per producer warp + the expect_tx arrival
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -273,106 +302,112 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = tm.prefix[args.num_species];
+  // K-blocks are 16 floats; the optional live-block lists are in 32-column AEV blocks
+  auto num_kb = [&](int K) { return tm.kb_count >= 0 ? 2 * tm.kb_count : (K + TK - 1) / TK; };
+  auto kb_id = [&](int i) { return tm.kb_count >= 0 ? tm.kb[i >> 1] * 2 + (i & 1) : i; };
 
   if (warp >= FIRST_PROD_WARP) {
     // ================================ producers ================================
     const int pt = threadIdx.x - FIRST_PROD_WARP * 32;  // 0..NPT-1
-    constexpr int A_IT = (TM * 8) / NPT;                // 16-byte chunks of A per thread (4)
-    uint32_t stage = 0, phase = 0;
-    float4 cur[A_IT], nxt[A_IT];
+    constexpr int A_IT = (TM * 4) / NPT;                // 16-byte chunks of A per thread per K-block (2)
 
-    auto load_a = [&](float4 (&dst)[A_IT], const float* __restrict__ A, int K, int k0) {
+    auto set_tile = [&](KItem& it) {
+      it.valid = it.t < total_tiles;
+      if (it.valid) {
+        it.tl = decode_tile(args, tm, it.t);
+        it.K = args.sp[it.tl.s].K;
+        it.nkb = num_kb(it.K);
+        it.A = args.A + (size_t)it.tl.rt * TM * args.lda + (size_t)it.tl.mem * args.sp[it.tl.s].a_moff;
+        it.kb = 0;
+      }
+    };
+    auto advance = [&](KItem& it) {
+      if (!it.valid) return;
+      if (++it.kb >= it.nkb) {
+        it.t += gridDim.x;
+        set_tile(it);
+      }
+    };
+    auto load_a = [&](float4 (&dst)[A_IT], const KItem& it) {
+      if (!it.valid) return;
+      const int k0 = kb_id(it.kb) * TK;
 #pragma unroll
       for (int i = 0; i < A_IT; ++i) {
         const int c = pt + i * NPT;
-        const int row = c >> 3, ch = c & 7;
+        const int row = c >> 2, ch = c & 3;
         dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + ch * 4 < K) dst[i] = *reinterpret_cast<const float4*>(A + (size_t)row * args.lda + k0 + ch * 4);
+        if (k0 + ch * 4 < it.K)
+          dst[i] = *reinterpret_cast<const float4*>(it.A + (size_t)row * args.lda + k0 + ch * 4);
       }
     };
 
-    // K-blocks may be a compacted list of live blocks (layer-1 forward)
-    auto num_kb = [&](int K) { return tm.kb_count >= 0 ? tm.kb_count : (K + TK - 1) / TK; };
-    auto kb_id = [&](int i) { return tm.kb_count >= 0 ? tm.kb[i] : i; };
-    int t = blockIdx.x;
-    Tile tl = {};
-    const float* A = nullptr;
-    int K = 0, nkb = 0;
-    if (t < total_tiles) {
-      tl = decode_tile(args, tm, t);
-      A = args.A + (size_t)tl.rt * TM * args.lda + (size_t)tl.mem * args.sp[tl.s].a_moff;
-      K = args.sp[tl.s].K;
-      nkb = num_kb(K);
-      if (nkb > 0) load_a(cur, A, K, kb_id(0) * TK);
+    KItem cur, pf;
+    cur.t = blockIdx.x;
+    set_tile(cur);
+    pf = cur;
+    // register ring: the A chunks of the next RING-1 K-blocks are in flight (HBM latency ~1.5 us
+    // vs ~0.3 us of tensor work per K-block) while the oldest one is split and stored
+    constexpr int RING = 6;
+    float4 ring[RING][A_IT];
+#pragma unroll
+    for (int d = 0; d < RING - 1; ++d) {
+      load_a(ring[d], pf);
+      advance(pf);
     }
-    while (t < total_tiles) {
-      const Species& sp = args.sp[tl.s];
-      // tiled B: [member][n tile][k block][hi bn x 128 B | lo bn x 128 B]
-      const int nkb_all = (K + TK - 1) / TK;  // K-blocks of the stored operand
-      const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) + (size_t)tl.mem * sp.N * nkb_all * 256;
-      const unsigned char* Bt = Bm + (size_t)tl.n0 * nkb_all * 256;
-      const uint32_t b_bytes = (uint32_t)tl.bn * 128u;
-      // next tile (for the cross-tile prefetch of A)
-      const int t_next = t + gridDim.x;
-      Tile tl_next = {};
-      const float* A_next = nullptr;
-      int K_next = 0;
-      if (t_next < total_tiles) {
-        tl_next = decode_tile(args, tm, t_next);
-        A_next = args.A + (size_t)tl_next.rt * TM * args.lda + (size_t)tl_next.mem * args.sp[tl_next.s].a_moff;
-        K_next = args.sp[tl_next.s].K;
-      }
-      for (int kb = 0; kb < nkb; ++kb) {
-        // prefetch the A chunks of the next K-block (or of the next tile's first one)
-        if (kb + 1 < nkb) {
-          load_a(nxt, A, K, kb_id(kb + 1) * TK);
-        } else if (A_next) {
-          load_a(nxt, A_next, K_next, kb_id(0) * TK);
-        }
-        mbar_wait(&empty[stage], phase ^ 1);
-        unsigned char* st = smem + stage * STAGE_BYTES;
-        if (pt == 0) {
-          mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
-          const int kbi = kb_id(kb);
-          if (tm.nb_count < 0) {
-            const unsigned char* src = Bt + (size_t)kbi * tl.bn * 256;
-            bulk_g2s(st + 2 * A_TILE_BYTES, src, b_bytes, &full[stage]);
-            bulk_g2s(st + 2 * A_TILE_BYTES + B_TILE_BYTES, src + b_bytes, b_bytes, &full[stage]);
-          } else {
-            // gathered column blocks: 32 rows (4 KB) of the stored operand per live block
-            for (int q = 0; q < tl.bn / 32; ++q) {
-              const int row0 = tm.nb[tl.n0 / 32 + q] * 32;
-              const int n0s = row0 / TN_MAX * TN_MAX;
-              const int bns = min(TN_MAX, sp.N - n0s);
-              const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * 256 + (size_t)(row0 - n0s) * 128;
-              bulk_g2s(st + 2 * A_TILE_BYTES + q * 4096, src, 4096, &full[stage]);
-              bulk_g2s(st + 2 * A_TILE_BYTES + B_TILE_BYTES + q * 4096, src + (size_t)bns * 128, 4096, &full[stage]);
-            }
+    uint32_t stage = 0, phase = 0;
+    while (cur.valid) {
+      load_a(ring[RING - 1], pf);
+      advance(pf);
+      mbar_wait(&empty[stage], phase ^ 1);
+      unsigned char* st = smem + stage * STAGE_BYTES;
+      {
+        // B: TMA bulk copies, one per thread (dense: hi, lo; gathered column blocks: 2 per block)
+        const Species& sp = args.sp[cur.tl.s];
+        const int nkb_all = (cur.K + TK - 1) / TK;  // K-blocks of the stored operand
+        const unsigned char* Bm =
+            reinterpret_cast<const unsigned char*>(sp.Bt) + (size_t)cur.tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
+        const int kbi = kb_id(cur.kb);
+        const uint32_t b_bytes = (uint32_t)cur.tl.bn * ROW_BYTES;
+        if (pt == 0) mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
+        if (tm.nb_count < 0) {
+          // [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
+          if (pt < 2) {
+            const unsigned char* src =
+                Bm + ((size_t)cur.tl.n0 * nkb_all + (size_t)kbi * cur.tl.bn) * (2 * ROW_BYTES) + (size_t)pt * b_bytes;
+            bulk_g2s(st + 2 * A_TILE_BYTES + pt * B_TILE_BYTES, src, b_bytes, &full[stage]);
           }
-        }
-#pragma unroll
-        for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, cur[i]);
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-        mbar_arrive(&full[stage]);
-#pragma unroll
-        for (int i = 0; i < A_IT; ++i) cur[i] = nxt[i];
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        } else if (pt < 2 * (cur.tl.bn / 32)) {
+          // gathered column blocks: 32 rows (2 KB) of the stored operand per live block and part
+          const int q = pt >> 1, part = pt & 1;
+          const int row0 = tm.nb[cur.tl.n0 / 32 + q] * 32;
+          const int n0s = row0 / TN_MAX * TN_MAX;
+          const int bns = min(TN_MAX, sp.N - n0s);
+          const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * (2 * ROW_BYTES) +
+                                     (size_t)(row0 - n0s) * ROW_BYTES + (size_t)part * bns * ROW_BYTES;
+          bulk_g2s(st + 2 * A_TILE_BYTES + part * B_TILE_BYTES + q * 32 * ROW_BYTES, src, 32 * ROW_BYTES, &full[stage]);
         }
       }
-      t = t_next;
-      tl = tl_next;
-      A = A_next;
-      K = K_next;
-      nkb = num_kb(K);
+#pragma unroll
+      for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, ring[0][i]);
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+#pragma unroll
+      for (int d = 0; d < RING - 1; ++d)
+#pragma unroll
+        for (int i = 0; i < A_IT; ++i) ring[d][i] = ring[d + 1][i];
+      advance(cur);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ================================
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode_tile(args, tm, t);
-      const int nkb = tm.kb_count >= 0 ? tm.kb_count : (args.sp[tl.s].K + TK - 1) / TK;
+      const int nkb = num_kb(args.sp[tl.s].K);
       const uint32_t idesc = make_idesc(tl.bn);
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
@@ -407,36 +442,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
   } else {
     // ================================ epilogue ================================
-    // Per 32-column chunk: (CELU' only) coalesced load of the stored activation into the warp's
-    // 32x32 buffer; tcgen05.ld (thread = row); elementwise op; result back into the buffer;
-    // coalesced 128-byte-row stores.
+    // Per 32-column chunk: (CELU' only) the stored activation arrives through a coalesced,
+    // one-chunk-ahead prefetch into the warp's 32x32 buffer; tcgen05.ld (thread = row);
+    // elementwise op; result back into the buffer; coalesced 128-byte-row stores.
     uint32_t acc = 0, acc_phase = 0;
-    const float alpha = args.alpha;
+    const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
     float* buf = epi_buf + warp * 32 * EPI_LD;
-    const int cr = lane >> 3, cq = (lane & 7) * 4;  // coalesced phase: row cr + 4*i, columns cq..cq+3
+    const int cr = lane >> 3, cq = (lane & 7) * 4;  // coalesced phase: rows cr + 4*i, columns cq..cq+3
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
       float* __restrict__ crow0 = args.C + (size_t)(tl.rt * TM + warp * 32) * args.ldc + (size_t)tl.mem * sp.c_moff;
-      const float* __restrict__ bias =
-          (EPI == EPI_BIAS_CELU) ? sp.bias + (size_t)tl.mem * sp.bias_mstride + tl.n0 : nullptr;
+      const float* __restrict__ bias = (EPI == EPI_BIAS_CELU || EPI == EPI_HEAD)
+                                           ? sp.bias + (size_t)tl.mem * sp.bias_mstride + tl.n0
+                                           : nullptr;
+      // EPI_HEAD: this thread's row produces one atomic energy e = w4 . celu(z3) + b4
+      const float* __restrict__ w4 = (EPI == EPI_HEAD) ? sp.w4 + (size_t)tl.mem * sp.N : nullptr;
+      const int my_row = tl.rt * TM + warp * 32 + lane;
+      float e_acc = 0.f, seed = 0.f;
+      bool row_valid = false;
+      if (EPI == EPI_HEAD) {
+        row_valid = args.row_atom[my_row] >= 0;
+        seed = row_valid ? args.member_scale[tl.mem] : 0.f;
+      }
+      // first column of chunk c0 in C (compacted column blocks map back to their place)
+      auto chunk_ptr = [&](int c0) {
+        return crow0 + (tm.nb_count >= 0 ? tm.nb[(tl.n0 + c0) / 32] * 32 : tl.n0 + c0);
+      };
+      float4 yreg[8];
+      auto load_y = [&](int c0) {
+        const int ncol = min(32, tl.bn - c0);
+        if (cq < ncol) {
+          const float* p = chunk_ptr(c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) yreg[i] = *reinterpret_cast<const float4*>(p + (size_t)(cr + 4 * i) * args.ldc + cq);
+        }
+      };
+      if (EPI == EPI_MUL_DCELU) load_y(0);  // independent of the accumulator: overlaps the MMA wait
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TN_MAX;
       for (int c0 = 0; c0 < tl.bn; c0 += 32) {
         const int ncol = min(32, tl.bn - c0);  // 32 or 16 (bn is a multiple of 16)
-        // first column of this chunk in C (compacted column blocks map back to their place)
-        float* __restrict__ cbase = crow0 + (tm.nb_count >= 0 ? tm.nb[(tl.n0 + c0) / 32] * 32 : tl.n0 + c0);
+        float* __restrict__ cbase = chunk_ptr(c0);
         if (EPI == EPI_MUL_DCELU) {
           if (cq < ncol) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = cr + 4 * i;
-              *reinterpret_cast<float4*>(&buf[r * EPI_LD + cq]) =
-                  *reinterpret_cast<const float4*>(cbase + (size_t)r * args.ldc + cq);
-            }
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&buf[(cr + 4 * i) * EPI_LD + cq]) = yreg[i];
           }
           __syncwarp();
+          if (c0 + 32 < tl.bn) load_y(c0 + 32);
         }
         float v[32];
         {
@@ -458,22 +513,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             float4* slot = reinterpret_cast<float4*>(&buf[lane * EPI_LD + 4 * q]);
             if (EPI == EPI_BIAS_CELU) {
               const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-              o.x = celu(o.x + b.x, alpha);
-              o.y = celu(o.y + b.y, alpha);
-              o.z = celu(o.z + b.z, alpha);
-              o.w = celu(o.w + b.w, alpha);
+              o.x = celu(o.x + b.x, cc);
+              o.y = celu(o.y + b.y, cc);
+              o.z = celu(o.z + b.z, cc);
+              o.w = celu(o.w + b.w, cc);
             } else if (EPI == EPI_MUL_DCELU) {
               const float4 y = *slot;
-              o.x *= dcelu_from_out(y.x, alpha);
-              o.y *= dcelu_from_out(y.y, alpha);
-              o.z *= dcelu_from_out(y.z, alpha);
-              o.w *= dcelu_from_out(y.w, alpha);
+              o.x *= dcelu_from_out(y.x, cc);
+              o.y *= dcelu_from_out(y.y, cc);
+              o.z *= dcelu_from_out(y.z, cc);
+              o.w *= dcelu_from_out(y.w, cc);
+            } else if (EPI == EPI_HEAD) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
+              const float4 w = *reinterpret_cast<const float4*>(w4 + c0 + 4 * q);
+              float a;
+              a = celu(o.x + b.x, cc); e_acc = fmaf(a, w.x, e_acc); o.x = seed * w.x * dcelu_from_out(a, cc);
+              a = celu(o.y + b.y, cc); e_acc = fmaf(a, w.y, e_acc); o.y = seed * w.y * dcelu_from_out(a, cc);
+              a = celu(o.z + b.z, cc); e_acc = fmaf(a, w.z, e_acc); o.z = seed * w.z * dcelu_from_out(a, cc);
+              a = celu(o.w + b.w, cc); e_acc = fmaf(a, w.w, e_acc); o.w = seed * w.w * dcelu_from_out(a, cc);
             }
             *slot = o;
           }
         }
         __syncwarp();
-        if (cq < ncol) {
+        if (cq < ncol && (EPI != EPI_HEAD || args.want_backward)) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = cr + 4 * i;
@@ -483,6 +546,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         }
         __syncwarp();
       }
+      if (EPI == EPI_HEAD)
+        args.e_member[(size_t)tl.mem * args.rows_cap + my_row] = row_valid ? e_acc + sp.b4[tl.mem] : 0.f;
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) {

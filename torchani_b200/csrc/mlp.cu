@@ -19,49 +19,6 @@
 
 namespace ani {
 
-__device__ __forceinline__ float dcelu_from_out(float y, float alpha) {
-  return y > 0.f ? 1.0f : (y + alpha) / alpha;
-}
-
-// final layer (h3 -> 1) + seed of the backward pass; one warp per (row, member)
-struct HeadArgs {
-  float* act3;
-  int ld3;
-  float* e_member;
-  int rows_cap;
-  const int32_t* tile_species;
-  const int32_t* row_atom;
-  float alpha;
-  int num_members;
-  int want_backward;
-  float member_scale[ANI_MAX_MEMBERS];
-  const float* w4[ANI_MAX_SPECIES];
-  const float* b4[ANI_MAX_SPECIES];
-  int h3[ANI_MAX_SPECIES];
-};
-
-__global__ void __launch_bounds__(256) k_mlp_head(const __grid_constant__ HeadArgs args) {
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int M = args.num_members;
-  const int row = warp_global / M, m = warp_global % M;
-  if (row >= args.rows_cap) return;
-  const int s = args.tile_species[row / ANI_TILE_ROWS];
-  if (s < 0) return;
-  const bool valid = args.row_atom[row] >= 0;
-  const int h3 = args.h3[s];
-  float* a3 = args.act3 + (size_t)row * args.ld3 + (size_t)m * h3;
-  const float* w4 = args.w4[s] + (size_t)m * h3;
-  float e = 0.f;
-  for (int c = lane; c < h3; c += 32) e += a3[c] * w4[c];
-  e = warp_sum(e);
-  if (lane == 0) args.e_member[(size_t)m * args.rows_cap + row] = valid ? e + args.b4[s][m] : 0.f;
-  if (args.want_backward) {
-    const float seed = valid ? args.member_scale[m] : 0.f;
-    for (int c = lane; c < h3; c += 32) a3[c] = seed * w4[c] * dcelu_from_out(a3[c], args.alpha);
-  }
-}
-
 // per-conformer reduction of atomic energies (fp64 accumulation) + self energies (sae.py:54-64)
 struct ReduceArgs {
   const float* e_member;
@@ -154,6 +111,7 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
     const ani_mlp_species& p = model->sp[s];
     if (p.h1 % 16 || p.h2 % 16 || p.h3 % 16 || p.h1 < 16 || p.h2 < 16 || p.h3 < 16) return ANI_ERR_UNSUPPORTED;
     if (p.h1 > model->h1_max || p.h2 > model->h2_max || p.h3 > model->h3_max) return ANI_ERR_BAD_ARG;
+    if (p.h3 > tc::TN_MAX) return ANI_ERR_UNSUPPORTED;  // the fused final layer needs h3 in one accumulator
     if (!p.b1 || !p.b2 || !p.b3 || !p.w4 || !p.b4 || !p.t_f1 || !p.t_f2 || !p.t_f3 || !p.t_b3 || !p.t_b2 || !p.t_b1)
       return ANI_ERR_BAD_ARG;
   }
@@ -165,13 +123,18 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   ta.nblocks = nullptr;
   ta.num_species = S;
   ta.alpha = model->celu_alpha;
-  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0};
+  ta.e_member = e_member;
+  ta.row_atom = row_atom;
+  ta.rows_cap = rows_cap;
+  ta.want_backward = want_backward;
+  for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ta.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
 
   // ---- forward.  Layer 1: the members share the input -> one GEMM with N = M*h1.
   ta.A = x; ta.lda = ldx; ta.C = act1; ta.ldc = ld1; ta.members = 1;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0};
+    ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr};
   }
   ta.kblocks = aev_blocks;  // dead AEV column blocks contribute exact zeros: skip them
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
@@ -179,49 +142,35 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   ta.A = act1; ta.lda = ld1; ta.C = act2; ta.ldc = ld2; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{p.t_f2, p.b2, p.h1, p.h2, p.h1, p.h2, p.h2};
+    ta.sp[s] = tc::Species{p.t_f2, p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr};
   }
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
   ta.A = act2; ta.lda = ld2; ta.C = act3; ta.ldc = ld3; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{p.t_f3, p.b3, p.h2, p.h3, p.h2, p.h3, p.h3};
+    ta.sp[s] = tc::Species{p.t_f3, p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4};
   }
-  launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
-  // ---- head: energies + gradient seed
-  {
-    HeadArgs ha;
-    ha.act3 = act3; ha.ld3 = ld3; ha.e_member = e_member; ha.rows_cap = rows_cap;
-    ha.tile_species = tile_species; ha.row_atom = row_atom; ha.alpha = model->celu_alpha;
-    ha.num_members = M; ha.want_backward = want_backward;
-    for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ha.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
-    for (int s = 0; s < ANI_MAX_SPECIES; ++s) {
-      ha.w4[s] = s < S ? model->sp[s].w4 : nullptr;
-      ha.b4[s] = s < S ? model->sp[s].b4 : nullptr;
-      ha.h3[s] = s < S ? model->sp[s].h3 : 0;
-    }
-    const long long warps = (long long)rows_cap * M;
-    const int blocks = (int)((warps + 7) / 8);
-    k_mlp_head<<<blocks, 256, 0, st>>>(ha);
-  }
+  // layer 3 + final layer (h3 -> 1) + gradient seed, fused in the epilogue: act3 receives
+  // G3 = scale_m * w4 * celu'(a3) directly, e_member the per-member atomic energies
+  launch_gemm_tc<tc::EPI_HEAD>(ta, st);
   if (want_backward) {
     // ---- backward: G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
     ta.A = act3; ta.lda = ld3; ta.C = act2; ta.ldc = ld2; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{p.t_b3, nullptr, p.h3, p.h2, p.h3, p.h2, 0};
+      ta.sp[s] = tc::Species{p.t_b3, nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
     ta.A = act2; ta.lda = ld2; ta.C = act1; ta.ldc = ld1; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{p.t_b2, nullptr, p.h2, p.h1, p.h2, p.h1, 0};
+      ta.sp[s] = tc::Species{p.t_b2, nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
     ta.A = act1; ta.lda = ld1; ta.C = x; ta.ldc = ldx; ta.members = 1;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{p.t_b1, nullptr, M * p.h1, ldx, 0, 0, 0};
+      ta.sp[s] = tc::Species{p.t_b1, nullptr, M * p.h1, ldx, 0, 0, 0, nullptr, nullptr};
     }
     ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
     launch_gemm_tc<tc::EPI_PLAIN>(ta, st);

@@ -96,29 +96,29 @@ def constants_1x(num_species: int = 4, cutoff_fn: str = "cosine") -> AEVConstant
 
 def tile_b_operand(b: Tensor) -> Tensor:
     """``B[N][K]`` (float32, K-major) -> the "tiled B operand" byte layout of include/ani_b200.h:
-    K zero-padded to 32, hi/lo TF32 split, [n tile of 256 rows][k block][hi bn x 128 B | lo bn x 128 B]
-    with every 8-row group in tcgen05 SWIZZLE_128B order.  Returned as a flat float32 tensor."""
+    K zero-padded to 16, hi/lo TF32 split, [n tile of 256 rows][k block of 16][hi bn x 64 B | lo bn x 64 B]
+    with every 8-row group in tcgen05 SWIZZLE_64B order.  Returned as a flat float32 tensor."""
     n, k = b.shape
     assert n % 8 == 0, "rows of a B operand must come in groups of 8"
-    kp = (k + 31) // 32 * 32
-    nkb = kp // 32
+    kp = (k + 15) // 16 * 16
+    nkb = kp // 16
     bp = torch.zeros(n, kp, dtype=torch.float32, device=b.device)
     bp[:, :k] = b
     hi = (bp.view(torch.int32) & -8192).view(torch.float32)   # 0xffffe000
     lo = bp - hi
     rows = torch.arange(8, device=b.device).view(8, 1)
-    pos = torch.arange(8, device=b.device).view(1, 8)
-    src_chunk = (pos ^ rows)                                    # chunk stored at position p of row r is p ^ r
+    pos = torch.arange(4, device=b.device).view(1, 4)
+    src_chunk = pos ^ ((rows >> 1) & 3)                         # chunk stored at position p of row r
     out = []
     for n0 in range(0, n, 256):
         bn = min(256, n - n0)
         parts = []
         for part in (hi, lo):
-            x = part[n0:n0 + bn].view(bn // 8, 8, nkb, 8, 4)           # [group][row][kb][chunk][4]
+            x = part[n0:n0 + bn].view(bn // 8, 8, nkb, 4, 4)           # [group][row][kb][chunk][4]
             x = x.permute(2, 0, 1, 3, 4)                                # [kb][group][row][chunk][4]
-            idx = src_chunk.view(1, 1, 8, 8, 1).expand(nkb, bn // 8, 8, 8, 4)
-            parts.append(torch.gather(x, 3, idx).reshape(nkb, bn * 32))
-        out.append(torch.stack(parts, 1).reshape(-1))                  # [kb][hi|lo][bn*32]
+            idx = src_chunk.view(1, 1, 8, 4, 1).expand(nkb, bn // 8, 8, 4, 4)
+            parts.append(torch.gather(x, 3, idx).reshape(nkb, bn * 16))
+        out.append(torch.stack(parts, 1).reshape(-1))                  # [kb][hi|lo][bn*16]
     return torch.cat(out).contiguous()
 
 
@@ -371,8 +371,8 @@ class Engine:
             ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
             ptr(ws.member_atomic), ptr(ws.energies), st))
         # kernels launched by this library in one step (memsets excluded):
-        #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 4 (+3 bwd), aev bwd 1, reduce 1
-        self.launches_per_step = 5 + 5 + 1 + 4 + (4 if want_grad else 0) + 1
+        #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 3 (+3 bwd), aev bwd 1, reduce 1
+        self.launches_per_step = 5 + 5 + 1 + 3 + (4 if want_grad else 0) + 1
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
                           ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
 
