@@ -345,61 +345,65 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     cur.t = blockIdx.x;
     set_tile(cur);
     pf = cur;
-    // register ring: the A chunks of the next RING-1 K-blocks are in flight (HBM latency ~1.5 us
-    // vs ~0.3 us of tensor work per K-block) while the oldest one is split and stored
+    // register ring with STATIC slots: slot k holds the A chunks of the K-block that is RING
+    // iterations ahead; it is consumed (split + stored) and immediately refilled.  No register of an
+    // in-flight load is ever moved, so RING K-blocks of HBM/L2 latency really overlap.
     constexpr int RING = 6;
     float4 ring[RING][A_IT];
 #pragma unroll
-    for (int d = 0; d < RING - 1; ++d) {
+    for (int d = 0; d < RING; ++d) {
       load_a(ring[d], pf);
       advance(pf);
     }
     uint32_t stage = 0, phase = 0;
     while (cur.valid) {
-      load_a(ring[RING - 1], pf);
-      advance(pf);
-      mbar_wait(&empty[stage], phase ^ 1);
-      unsigned char* st = smem + stage * STAGE_BYTES;
-      {
-        // B: TMA bulk copies, one per thread (dense: hi, lo; gathered column blocks: 2 per block)
-        const Species& sp = args.sp[cur.tl.s];
-        const int nkb_all = (cur.K + TK - 1) / TK;  // K-blocks of the stored operand
-        const unsigned char* Bm =
-            reinterpret_cast<const unsigned char*>(sp.Bt) + (size_t)cur.tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
-        const int kbi = kb_id(cur.kb);
-        const uint32_t b_bytes = (uint32_t)cur.tl.bn * ROW_BYTES;
-        if (pt == 0) mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
-        if (tm.nb_count < 0) {
-          // [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
-          if (pt < 2) {
-            const unsigned char* src =
-                Bm + ((size_t)cur.tl.n0 * nkb_all + (size_t)kbi * cur.tl.bn) * (2 * ROW_BYTES) + (size_t)pt * b_bytes;
-            bulk_g2s(st + 2 * A_TILE_BYTES + pt * B_TILE_BYTES, src, b_bytes, &full[stage]);
+#pragma unroll
+      for (int k = 0; k < RING; ++k) {
+        if (cur.valid) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = smem + stage * STAGE_BYTES;
+          {
+            // B: TMA bulk copies, one per thread (dense: hi, lo; gathered column blocks: 2 per block)
+            const Species& sp = args.sp[cur.tl.s];
+            const int nkb_all = (cur.K + TK - 1) / TK;  // K-blocks of the stored operand
+            const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) +
+                                      (size_t)cur.tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
+            const int kbi = kb_id(cur.kb);
+            const uint32_t b_bytes = (uint32_t)cur.tl.bn * ROW_BYTES;
+            if (pt == 0) mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
+            if (tm.nb_count < 0) {
+              // [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
+              if (pt < 2) {
+                const unsigned char* src = Bm +
+                                           ((size_t)cur.tl.n0 * nkb_all + (size_t)kbi * cur.tl.bn) * (2 * ROW_BYTES) +
+                                           (size_t)pt * b_bytes;
+                bulk_g2s(st + 2 * A_TILE_BYTES + pt * B_TILE_BYTES, src, b_bytes, &full[stage]);
+              }
+            } else if (pt < 2 * (cur.tl.bn / 32)) {
+              // gathered column blocks: 32 rows (2 KB) of the stored operand per live block and part
+              const int q = pt >> 1, part = pt & 1;
+              const int row0 = tm.nb[cur.tl.n0 / 32 + q] * 32;
+              const int n0s = row0 / TN_MAX * TN_MAX;
+              const int bns = min(TN_MAX, sp.N - n0s);
+              const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * (2 * ROW_BYTES) +
+                                         (size_t)(row0 - n0s) * ROW_BYTES + (size_t)part * bns * ROW_BYTES;
+              bulk_g2s(st + 2 * A_TILE_BYTES + part * B_TILE_BYTES + q * 32 * ROW_BYTES, src, 32 * ROW_BYTES,
+                       &full[stage]);
+            }
           }
-        } else if (pt < 2 * (cur.tl.bn / 32)) {
-          // gathered column blocks: 32 rows (2 KB) of the stored operand per live block and part
-          const int q = pt >> 1, part = pt & 1;
-          const int row0 = tm.nb[cur.tl.n0 / 32 + q] * 32;
-          const int n0s = row0 / TN_MAX * TN_MAX;
-          const int bns = min(TN_MAX, sp.N - n0s);
-          const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * (2 * ROW_BYTES) +
-                                     (size_t)(row0 - n0s) * ROW_BYTES + (size_t)part * bns * ROW_BYTES;
-          bulk_g2s(st + 2 * A_TILE_BYTES + part * B_TILE_BYTES + q * 32 * ROW_BYTES, src, 32 * ROW_BYTES, &full[stage]);
+#pragma unroll
+          for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, ring[k][i]);
+          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[stage]);
+          load_a(ring[k], pf);  // refill this slot for the K-block RING iterations ahead
+          advance(pf);
+          advance(cur);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-      }
-#pragma unroll
-      for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, ring[0][i]);
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
-#pragma unroll
-      for (int d = 0; d < RING - 1; ++d)
-#pragma unroll
-        for (int i = 0; i < A_IT; ++i) ring[d][i] = ring[d + 1][i];
-      advance(cur);
-      if (++stage == STAGES) {
-        stage = 0;
-        phase ^= 1;
       }
     }
   } else if (warp == MMA_WARP) {

@@ -196,6 +196,7 @@ class PackedNetworks:
             if not 0 <= i < self.num_members:
                 raise IndexError(f"Idx {i} should be 0 <= idx < {self.num_members}")
         self.active = list(idxs)
+        self.version = getattr(self, "version", 0) + 1   # captured CUDA graphs bake the scales in
         for m in range(_lib.ANI_MAX_MEMBERS):
             self.model.member_scale[m] = (1.0 / len(self.active)) if m in self.active else 0.0
 
@@ -264,7 +265,7 @@ class Engine:
     bucket-sorted atoms this engine owns (multi-GPU sharding, see parallel.py)."""
 
     def __init__(self, consts: AEVConstants, nets: PackedNetworks, sae: tp.Optional[tp.Sequence[float]] = None,
-                 nbr_cap: int = 128):
+                 nbr_cap: int = 128, cuda_graph: bool = True):
         if nets.in_dim != consts.out_dim:
             raise ValueError("network input width != AEV length")
         if nets.num_species != consts.num_species:
@@ -277,6 +278,9 @@ class Engine:
         if sae is not None:
             self.sae = torch.tensor(list(sae), dtype=torch.float64, device=self.device)
         self._ws: tp.Dict[tp.Tuple[int, int], Workspace] = {}
+        self.cuda_graph = cuda_graph
+        self._graphs: tp.Dict[tp.Any, torch.cuda.CUDAGraph] = {}
+        self._graph_seen: tp.Dict[tp.Any, int] = {}
         self.lib = _lib.lib()
         self.launches_per_step = 0
         # per-stage CUDA-event timing (bench.py's roofline leg); off by default
@@ -314,7 +318,10 @@ class Engine:
              want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1)) -> StepResult:
         """species (C, A) int (element indices, -1 padding), coords (C, A, 3) on this device.
         ``shard = (rank, world)``: only atoms whose bucket-sorted position falls into this
-        rank's slice are evaluated; gradients/energies are partial sums to be all-reduced."""
+        rank's slice are evaluated; gradients/energies are partial sums to be all-reduced.
+
+        The launch sequence of a given problem shape is captured into a CUDA graph on its second
+        use and replayed afterwards (``cuda_graph=False`` at construction disables this)."""
         dev = self.device
         n_conf, n_per_conf = species.shape
         if coords.shape != (n_conf, n_per_conf, 3):
@@ -326,23 +333,50 @@ class Engine:
         if pbc and n_conf != 1:
             raise NotImplementedError("periodic batches (C > 1 with one shared cell) are not supported yet")
         ws = self.workspace(n_conf, n_per_conf)
-        st = torch.cuda.current_stream(dev).cuda_stream
-        L = self.lib
         n = ws.n
+        # inputs -> persistent buffers (what the graph reads)
         ws.species_i32.copy_(species.reshape(-1))
         ws.coords.copy_(coords.reshape(-1, 3))
-        cell_ptr = None
         if pbc:
             ws.cell.copy_(cell.reshape(-1))
-            cell_ptr = ptr(ws.cell)
+        rank, world = shard
+        lo = (n * rank) // world
+        hi = (n * (rank + 1)) // world
+        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.version)
+        if not self.cuda_graph or self.profile:
+            self._launch(ws, bool(pbc), want_grad, lo, hi)
+        else:
+            graph = self._graphs.get(key)
+            if graph is not None:
+                graph.replay()
+            elif self._graph_seen.get(key, 0) < 1:
+                self._graph_seen[key] = 1          # first use: eager (also sets kernel attributes)
+                self._launch(ws, bool(pbc), want_grad, lo, hi)
+            else:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._launch(ws, bool(pbc), want_grad, lo, hi)
+                self._graphs[key] = graph
+                graph.replay()
+        # kernels launched by this library in one step (memsets excluded):
+        #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 3 (+3 bwd), aev bwd 1, reduce 1
+        self.launches_per_step = 5 + 5 + 1 + 3 + (4 if want_grad else 0) + 1
+        grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
+        return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
+                          ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
+
+    def _launch(self, ws: Workspace, pbc: bool, want_grad: bool, lo: int, hi: int) -> None:
+        """Enqueue the kernels of one step on the current stream (graph-capturable: no allocation,
+        no synchronisation, only this library's launches and two memsets)."""
+        L = self.lib
+        n, n_conf, n_per_conf = ws.n, ws.n_conf, ws.n_per_conf
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        cell_ptr = ptr(ws.cell) if pbc else None
         mode = 0 if n_conf == 1 else 1
         self._timed("build_cells", lambda: L.ani_b200_build_cells(
             ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
             self.consts.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
             ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.scratch), ptr(ws.status), st))
-        rank, world = shard
-        lo = (n * rank) // world
-        hi = (n * (rank + 1)) // world
         self._timed("species_layout", lambda: L.ani_b200_species_layout(
             ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species, ws.rows_cap, ptr(ws.row_of),
             ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info), ptr(ws.scratch), st))
@@ -358,23 +392,16 @@ class Engine:
             C.byref(self.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species), ptr(ws.row_atom),
             ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
             int(want_grad), st))
-        grad = None
         if want_grad:
             ws.grad.zero_()
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
                 ptr(ws.grad), ptr(ws.status), st))
-            grad = ws.grad.view(n_conf, n_per_conf, 3)
         self._timed("reduce_energies", lambda: L.ani_b200_reduce_energies(
             C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),
             ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
             ptr(ws.member_atomic), ptr(ws.energies), st))
-        # kernels launched by this library in one step (memsets excluded):
-        #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 3 (+3 bwd), aev bwd 1, reduce 1
-        self.launches_per_step = 5 + 5 + 1 + 3 + (4 if want_grad else 0) + 1
-        return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
-                          ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
 
     # -- status ----------------------------------------------------------------------------
     def check_status(self, ws: tp.Optional[Workspace] = None) -> None:
