@@ -203,24 +203,19 @@ def main():
     value = n_atoms / (ms_per_step * 1e-3)
     eng.check_status()
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the region
-    h_coords = coords.clone().pin_memory()
-    h_cell = cell.clone().pin_memory()
-    h_forces = torch.empty(1, n_atoms, 3, dtype=torch.float32).pin_memory()
-    h_energy = torch.empty(1, dtype=torch.float64).pin_memory()
-    pbc_d = pbc.to(dev)
+    # ---- end to end through the public API with HOST buffers: calculator.HostCalculator.calculate
+    #      (host positions in, host energy + forces out; H2D, graph replay, D2H and the sync inside)
+    from torchani_b200.calculator import HostCalculator
+    calc = HostCalculator(model, z[0].numpy(), cell.numpy(), pbc=True, shard=(rank, world))
+    h_pos = coords[0].numpy().copy()
 
     def e2e_step():
-        c = h_coords.to(dev, non_blocking=True)
-        ce = h_cell.to(dev, non_blocking=True)
-        if world == 1:
-            e, f = model.energies_and_forces(z_d, c, ce, pbc_d)
-        else:
-            e, g = sharded.step(sp_d, c, ce, True)
-            f = (-g).to(torch.float32)
-        h_forces.copy_(f, non_blocking=True)
-        h_energy.copy_(e, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads E and F on the host
+        e, f = calc.calculate(h_pos)
+        if world > 1:  # partial results of this rank's atom slice -> one all-reduce (as in ShardedEngine)
+            buf = torch.cat([torch.from_numpy(f).reshape(-1).double(), torch.tensor([e], dtype=torch.float64)]).to(dev)
+            dist.all_reduce(buf)
+            buf.cpu()
+        return e, f
 
     for _ in range(3):
         e2e_step()
@@ -240,8 +235,8 @@ def main():
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = n_atoms / (float(t_e2e.item()) / args.steps * 1e-3)
-    h2d = h_coords.numel() * 4 + h_cell.numel() * 4
-    d2h = h_forces.numel() * 4 + 8
+    h2d = calc.h2d_bytes
+    d2h = calc.d2h_bytes
 
     # ---- per-stage device times for the roofline (separate short run, events per C-ABI call)
     eng.profile = True
@@ -287,8 +282,8 @@ def main():
                 "ns_per_day": 0.0864 / (ms_per_step * 1e-3), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": float(t_e2e.item()) / args.steps,
-                        "api": "torchani_b200.models.ANI.energies_and_forces (pinned host coords/cell in, "
-                               "host energy+forces out)"},
+                        "api": "torchani_b200.calculator.HostCalculator.calculate (host positions in, host "
+                               "energy+forces out; counterpart of torchani.ase.Calculator.calculate)"},
                 "gpu_launches": eng.launches_per_step * args.steps,
                 "stage_ms": stage, "roofline": roofline, "roofline_aev": roofline_aev, "cpu_baseline": cpu}
         print(json.dumps(line))

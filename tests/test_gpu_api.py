@@ -145,3 +145,30 @@ def test_ani_model_energy_and_autograd_forces(name):
     assert_close("forces (direct)", f2.cpu().numpy(), rec["forces"], 0.0, F_ATOL)
     with pytest.raises(ValueError):
         model((torch.full_like(z, 15).to(DEV), c), cell_d, pbc_d)  # phosphorus is not an ANI-2x element
+
+
+def test_host_calculator_matches_oracle_and_repeats():
+    """calculator.HostCalculator (counterpart of ase.py:75-173): host positions in, host E/F out;
+    repeated calls replay the captured CUDA graph and must keep giving the oracle's answer."""
+    from torchani_b200 import models
+    from torchani_b200.calculator import HostCalculator
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    om = oracle_model("2x", torch.float32)
+    model = models.from_weight_lists("2x", om.weights, device=DEV, periodic_table_index=True)
+    znum = torch.tensor([orc.ATOMIC_NUMBERS[s] for s in orc.SYMBOLS_2X])
+    calc = HostCalculator(model, znum[species[0]].numpy(), cell.numpy(), pbc=True)
+    sae = float(orc.self_energies(orc.SYMBOLS_2X, orc.GSAES_WB97X_631GD, species, torch.float64).sum())
+    for it in range(6):  # eager x3, capture, replay, replay
+        e, f = calc.calculate(coords[0].numpy())
+        assert abs(e - (float(rec["energy_nn"][0]) + sae)) < 1e-5
+        assert_close("forces", f, rec["forces"][0], 0.0, F_ATOL)
+    # moved atoms: the replayed graph must see the new positions
+    moved = coords[0].numpy().copy()
+    moved[3] += np.array([0.05, -0.02, 0.01], dtype=np.float32)
+    e2, f2 = calc.calculate(moved)
+    ref = orc.compute(oracle_model("2x", torch.float64, "cell_list"), species, torch.tensor(moved).double().unsqueeze(0),
+                      cell.double(), pbc)
+    assert abs(e2 - float(ref["energy"][0])) < 1e-5
+    assert_close("forces moved", f2, ref["forces"][0].numpy(), 0.0, F_ATOL)
+    calc.check_status()

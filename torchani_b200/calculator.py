@@ -1,0 +1,82 @@
+"""Host-buffer calculator: the B200 counterpart of ``torchani.ase.Calculator.calculate``
+(ase.py:75-173) without the ``ase`` dependency.
+
+An MD driver owns positions on the HOST (numpy / pinned torch tensors).  Per step the
+reference converts numpy -> tensors, copies to the GPU, runs the model, calls ``energy.item()``
+and ``forces.cpu().numpy()`` (two blocking D2H syncs).  Here the positions go straight into the
+engine's persistent input buffer (one async H2D), the captured CUDA graph of the step is
+replayed, energy and forces come back through pinned buffers (async D2H) and ONE stream
+synchronisation ends the step.
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .models import ANI
+
+HARTREE_TO_EV = 27.211386024367243  # units.py (CODATA 2014, as used by the reference's ASE interface)
+
+
+class HostCalculator:
+    """Energy + forces for a fixed set of atoms from host coordinates.
+
+    Args:
+        model: a ``torchani_b200.models.ANI`` on a CUDA device
+        atomic_numbers: (A,) or (1, A) integer array (atomic numbers, or element indices if the
+            model was built with ``periodic_table_index=False``)
+        cell: (3, 3) lattice vectors as rows, or None for a non-periodic system
+        pbc: periodic in all three directions (partial periodicity is not supported)
+    """
+
+    def __init__(self, model: ANI, atomic_numbers, cell=None, pbc: bool = False, shard: tp.Tuple[int, int] = (0, 1)):
+        dev = next(model.buffers()).device
+        if dev.type != "cuda":
+            raise ValueError("HostCalculator needs a model on a CUDA device")
+        self.model, self.device, self.pbc, self.shard = model, dev, bool(pbc), shard
+        z = torch.as_tensor(np.asarray(atomic_numbers)).reshape(1, -1).to(dev)
+        self.elem_idxs = model.species_converter(z, nop=not model.periodic_table_index)   # validated once
+        self.n = z.shape[1]
+        self.engine = model.engine(dev)
+        self.ws = self.engine.workspace(1, self.n)
+        self.ws.species_i32.copy_(self.elem_idxs.reshape(-1))
+        self.h_coords = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
+        self.h_cell = torch.zeros(9, dtype=torch.float32).pin_memory()
+        self.h_grad = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
+        self.h_energy = torch.empty(1, dtype=torch.float64).pin_memory()
+        if pbc and cell is None:
+            raise ValueError("If pbc is not None, cell should be present")
+        if cell is not None:
+            self.set_cell(cell)
+        self.h2d_bytes = self.h_coords.numel() * 4 + (36 if pbc else 0)
+        self.d2h_bytes = self.h_grad.numel() * 4 + 8
+
+    def set_cell(self, cell) -> None:
+        self.h_cell.copy_(torch.as_tensor(np.asarray(cell, dtype=np.float32)).reshape(-1))
+
+    def calculate(self, positions, cell=None) -> tp.Tuple[float, np.ndarray]:
+        """positions: (A, 3) float array on the host (Angstrom).  Returns (energy [Hartree],
+        forces (A, 3) [Hartree/Angstrom]) -- multiply by HARTREE_TO_EV for ASE units."""
+        if cell is not None:
+            self.set_cell(cell)
+        if isinstance(positions, Tensor):
+            self.h_coords.copy_(positions.reshape(self.n, 3))
+        else:
+            self.h_coords.numpy()[...] = np.asarray(positions, dtype=np.float32).reshape(self.n, 3)
+        ws = self.ws
+        ws.coords.copy_(self.h_coords, non_blocking=True)
+        if self.pbc:
+            ws.cell.copy_(self.h_cell, non_blocking=True)
+        res = self.engine.run(ws, self.pbc, want_grad=True, shard=self.shard)
+        self.h_grad.copy_(res.grad.view(self.n, 3), non_blocking=True)
+        self.h_energy.copy_(res.energies, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        forces = self.h_grad.numpy()
+        np.negative(forces, out=forces)
+        return float(self.h_energy[0]), forces
+
+    def check_status(self) -> None:
+        self.engine.check_status(self.ws)

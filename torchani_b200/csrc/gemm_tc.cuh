@@ -12,12 +12,12 @@
 //   * A (activations) is split on the fly by the producer warps: coalesced 16-byte loads, the
 //     loads of K-block k+1 are in flight while K-block k is split and stored.
 //
-// Roles (13 warps, one CTA per SM, persistent over the device-side tile list):
+// Roles (9 warps, one CTA per SM, persistent over the device-side tile list):
 //   warps 0-3  epilogue : tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..32w+31);
 //                         global traffic is staged through a 32x32 shared-memory transpose so
 //                         that loads (old activation for CELU') and stores are 128-byte rows
 //   warp  4    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
-//   warps 5-12 producer : A split + swizzled st.shared + fence.proxy.async; thread 0 also
+//   warps 5-8  producer : A split + swizzled st.shared + fence.proxy.async; thread 0 also
 //                         issues the bulk copies of B (mbarrier expect_tx / complete_tx)
 // Pipelines: smem full/empty (4 stages x 48 KB: three K-blocks in flight cover the L2/HBM latency
 // of the one being multiplied) and TMEM full/empty (2 x 256 columns), so the
@@ -40,7 +40,7 @@ constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi+lo of A 
 constexpr int EPI_LD = 36;                                  // padded row of the 32x32 transpose buffer (floats)
 constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;               // one buffer per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, FIRST_PROD_WARP = 5, NUM_PROD_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, FIRST_PROD_WARP = 5, NUM_PROD_WARPS = 4;
 constexpr int NPT = NUM_PROD_WARPS * 32;  // producer threads
 constexpr int THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 288
 constexpr int TMEM_COLS = 512;
@@ -71,6 +71,7 @@ struct Args {
   const int32_t* row_atom;      // [rows_cap], -1 for padding rows
   int rows_cap;
   int want_backward;
+  int debug;                    // bring-up only (ANI_B200_GEMM_DEBUG): 1 no A stores, 2 no B copies, 4 no MMA, 8 no epilogue, 16 no A loads
   float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
 };
@@ -244,22 +245,6 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-__device__ __forceinline__ void split_store(unsigned char* st_hi, unsigned char* st_lo, int c, float4 v) {
-  const int row = c >> 2, ch = c & 3;
-  float4 hi, lo;
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-  lo.x = v.x - hi.x;
-  lo.y = v.y - hi.y;
-  lo.z = v.z - hi.z;
-  lo.w = v.w - hi.w;
-  const uint32_t off = swz_off(row, ch);
-  *reinterpret_cast<float4*>(st_hi + off) = hi;
-  *reinterpret_cast<float4*>(st_lo + off) = lo;
-}
-
 // position of a producer in the flattened (tile, K-block) sequence of its CTA
 struct KItem {
   int t, kb, nkb, K;
@@ -308,8 +293,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
 
   if (warp >= FIRST_PROD_WARP) {
     // ================================ producers ================================
+    // Thread pt owns 16-byte chunk (pt & 3) of rows (pt >> 2) + 32*i, i = 0..3, of every K-block:
+    // its global pointer advances by k0 only and its four swizzled smem offsets are constants.
     const int pt = threadIdx.x - FIRST_PROD_WARP * 32;  // 0..NPT-1
-    constexpr int A_IT = (TM * 4) / NPT;                // 16-byte chunks of A per thread per K-block (2)
+    constexpr int A_IT = (TM * 4) / NPT;                // chunks per thread per K-block (4)
+    const int my_row = pt >> 2, my_ch = pt & 3;
+    const uint32_t my_off = swz_off(my_row, my_ch);     // + i * 32 rows = + i * 4 groups = + i * 2048 B
+    const size_t row_stride = (size_t)32 * args.lda;
 
     auto set_tile = [&](KItem& it) {
       it.valid = it.t < total_tiles;
@@ -317,13 +307,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         it.tl = decode_tile(args, tm, it.t);
         it.K = args.sp[it.tl.s].K;
         it.nkb = num_kb(it.K);
-        it.A = args.A + (size_t)it.tl.rt * TM * args.lda + (size_t)it.tl.mem * args.sp[it.tl.s].a_moff;
+        it.A = args.A + (size_t)it.tl.rt * TM * args.lda + (size_t)it.tl.mem * args.sp[it.tl.s].a_moff +
+               (size_t)my_row * args.lda + my_ch * 4;
         it.kb = 0;
       }
     };
     auto advance = [&](KItem& it) {
-      if (!it.valid) return;
-      if (++it.kb >= it.nkb) {
+      if (++it.kb >= it.nkb && it.valid) {
         it.t += gridDim.x;
         set_tile(it);
       }
@@ -331,14 +321,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     auto load_a = [&](float4 (&dst)[A_IT], const KItem& it) {
       if (!it.valid) return;
       const int k0 = kb_id(it.kb) * TK;
+      const bool in_k = (k0 + my_ch * 4 < it.K) && !(args.debug & 16);
+      const float* p = it.A + k0;
 #pragma unroll
-      for (int i = 0; i < A_IT; ++i) {
-        const int c = pt + i * NPT;
-        const int row = c >> 2, ch = c & 3;
-        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + ch * 4 < it.K)
-          dst[i] = *reinterpret_cast<const float4*>(it.A + (size_t)row * args.lda + k0 + ch * 4);
-      }
+      for (int i = 0; i < A_IT; ++i)
+        dst[i] = in_k ? *reinterpret_cast<const float4*>(p + i * row_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
 
     KItem cur, pf;
@@ -362,37 +349,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         if (cur.valid) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = smem + stage * STAGE_BYTES;
-          {
+          if (pt < 16) {
             // B: TMA bulk copies, one per thread (dense: hi, lo; gathered column blocks: 2 per block)
             const Species& sp = args.sp[cur.tl.s];
-            const int nkb_all = (cur.K + TK - 1) / TK;  // K-blocks of the stored operand
-            const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) +
-                                      (size_t)cur.tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
-            const int kbi = kb_id(cur.kb);
             const uint32_t b_bytes = (uint32_t)cur.tl.bn * ROW_BYTES;
-            if (pt == 0) mbar_arrive_expect_tx(&full[stage], 2 * b_bytes);
-            if (tm.nb_count < 0) {
-              // [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
-              if (pt < 2) {
+            if (pt == 0) mbar_arrive_expect_tx(&full[stage], (args.debug & 2) ? 0u : 2 * b_bytes);
+            const bool dense = tm.nb_count < 0;
+            if (!(args.debug & 2) && pt < (dense ? 2 : 2 * (cur.tl.bn / 32))) {
+              const int nkb_all = (cur.K + TK - 1) / TK;  // K-blocks of the stored operand
+              const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) +
+                                        (size_t)cur.tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
+              const int kbi = kb_id(cur.kb);
+              if (dense) {
+                // [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
                 const unsigned char* src = Bm +
                                            ((size_t)cur.tl.n0 * nkb_all + (size_t)kbi * cur.tl.bn) * (2 * ROW_BYTES) +
                                            (size_t)pt * b_bytes;
                 bulk_g2s(st + 2 * A_TILE_BYTES + pt * B_TILE_BYTES, src, b_bytes, &full[stage]);
+              } else {
+                // gathered column blocks: 32 rows (2 KB) of the stored operand per live block and part
+                const int q = pt >> 1, part = pt & 1;
+                const int row0 = tm.nb[cur.tl.n0 / 32 + q] * 32;
+                const int n0s = row0 / TN_MAX * TN_MAX;
+                const int bns = min(TN_MAX, sp.N - n0s);
+                const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * (2 * ROW_BYTES) +
+                                           (size_t)(row0 - n0s) * ROW_BYTES + (size_t)part * bns * ROW_BYTES;
+                bulk_g2s(st + 2 * A_TILE_BYTES + part * B_TILE_BYTES + q * 32 * ROW_BYTES, src, 32 * ROW_BYTES,
+                         &full[stage]);
               }
-            } else if (pt < 2 * (cur.tl.bn / 32)) {
-              // gathered column blocks: 32 rows (2 KB) of the stored operand per live block and part
-              const int q = pt >> 1, part = pt & 1;
-              const int row0 = tm.nb[cur.tl.n0 / 32 + q] * 32;
-              const int n0s = row0 / TN_MAX * TN_MAX;
-              const int bns = min(TN_MAX, sp.N - n0s);
-              const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * (2 * ROW_BYTES) +
-                                         (size_t)(row0 - n0s) * ROW_BYTES + (size_t)part * bns * ROW_BYTES;
-              bulk_g2s(st + 2 * A_TILE_BYTES + part * B_TILE_BYTES + q * 32 * ROW_BYTES, src, 32 * ROW_BYTES,
-                       &full[stage]);
             }
           }
+          if (!(args.debug & 1)) {
 #pragma unroll
-          for (int i = 0; i < A_IT; ++i) split_store(st, st + A_TILE_BYTES, pt + i * NPT, ring[k][i]);
+            for (int i = 0; i < A_IT; ++i) {
+              const float4 v = ring[k][i];
+              float4 hi, lo;
+              hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+              hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+              hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+              hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+              lo.x = v.x - hi.x;
+              lo.y = v.y - hi.y;
+              lo.z = v.z - hi.z;
+              lo.w = v.w - hi.w;
+              *reinterpret_cast<float4*>(st + my_off + i * (4 * GROUP_BYTES)) = hi;
+              *reinterpret_cast<float4*>(st + A_TILE_BYTES + my_off + i * (4 * GROUP_BYTES)) = lo;
+            }
+          }
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[stage]);
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < TK / 8; ++k) {
+            if (args.debug & 4) break;
             const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 B = 2 x 16 B along the swizzle row
             umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
             umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
@@ -487,6 +491,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TN_MAX;
       for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+        if (args.debug & 8) break;
         const int ncol = min(32, tl.bn - c0);  // 32 or 16 (bn is a multiple of 16)
         float* __restrict__ cbase = chunk_ptr(c0);
         if (EPI == EPI_MUL_DCELU) {

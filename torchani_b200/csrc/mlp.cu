@@ -127,6 +127,11 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   ta.row_atom = row_atom;
   ta.rows_cap = rows_cap;
   ta.want_backward = want_backward;
+  static const int gemm_debug = []() {
+    const char* e = getenv("ANI_B200_GEMM_DEBUG");  // timing experiments only: results are wrong when set
+    return e ? atoi(e) : 0;
+  }();
+  ta.debug = gemm_debug;
   for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ta.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
   for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
 

@@ -279,6 +279,7 @@ class Engine:
             self.sae = torch.tensor(list(sae), dtype=torch.float64, device=self.device)
         self._ws: tp.Dict[tp.Tuple[int, int], Workspace] = {}
         self.cuda_graph = cuda_graph
+        self.graph_after = 3   # eager launches of a problem shape before its CUDA graph is captured
         self._graphs: tp.Dict[tp.Any, torch.cuda.CUDAGraph] = {}
         self._graph_seen: tp.Dict[tp.Any, int] = {}
         self.lib = _lib.lib()
@@ -320,7 +321,7 @@ class Engine:
         ``shard = (rank, world)``: only atoms whose bucket-sorted position falls into this
         rank's slice are evaluated; gradients/energies are partial sums to be all-reduced.
 
-        The launch sequence of a given problem shape is captured into a CUDA graph on its second
+        The launch sequence of a given problem shape is captured into a CUDA graph on its fourth
         use and replayed afterwards (``cuda_graph=False`` at construction disables this)."""
         dev = self.device
         n_conf, n_per_conf = species.shape
@@ -333,12 +334,18 @@ class Engine:
         if pbc and n_conf != 1:
             raise NotImplementedError("periodic batches (C > 1 with one shared cell) are not supported yet")
         ws = self.workspace(n_conf, n_per_conf)
-        n = ws.n
         # inputs -> persistent buffers (what the graph reads)
         ws.species_i32.copy_(species.reshape(-1))
         ws.coords.copy_(coords.reshape(-1, 3))
         if pbc:
             ws.cell.copy_(cell.reshape(-1))
+        return self.run(ws, bool(pbc), want_grad, shard)
+
+    def run(self, ws: Workspace, pbc: bool, want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1)) -> StepResult:
+        """One step on inputs that are ALREADY in the workspace buffers (``ws.species_i32``,
+        ``ws.coords``, ``ws.cell``) -- the entry point of host-driven loops that copy straight into
+        them (calculator.HostCalculator).  The results alias workspace buffers."""
+        n, n_conf, n_per_conf = ws.n, ws.n_conf, ws.n_per_conf
         rank, world = shard
         lo = (n * rank) // world
         hi = (n * (rank + 1)) // world
@@ -349,8 +356,9 @@ class Engine:
             graph = self._graphs.get(key)
             if graph is not None:
                 graph.replay()
-            elif self._graph_seen.get(key, 0) < 1:
-                self._graph_seen[key] = 1          # first use: eager (also sets kernel attributes)
+            elif self._graph_seen.get(key, 0) < self.graph_after:
+                # the first few uses of a shape run eagerly (one-off shapes never pay for a capture)
+                self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
                 self._launch(ws, bool(pbc), want_grad, lo, hi)
             else:
                 graph = torch.cuda.CUDAGraph()

@@ -155,6 +155,7 @@ class AtomicContainer(torch.nn.Module):
         self.register_buffer("atomic_numbers", torch.tensor([0], dtype=torch.long), persistent=False)
         self._packed: tp.Optional[PackedNetworks] = None
         self._packed_key: tp.Any = None
+        self._packed_frozen = False
 
     @property
     def symbols(self) -> tp.Tuple[str, ...]:
@@ -178,7 +179,22 @@ class AtomicContainer(torch.nn.Module):
     def member_networks(self) -> tp.List["ANINetworks"]:
         raise NotImplementedError
 
+    def invalidate_packed(self) -> None:
+        """Forget the kernel-layout copy of the weights (call after editing parameters in place)."""
+        self._packed_key = None
+
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float() ...
+        self._packed_key = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs) -> None:
+        self._packed_key = None
+        super()._load_from_state_dict(*args, **kwargs)
+
     def packed(self, device: torch.device) -> PackedNetworks:
+        if self._packed is not None and self._packed_key is not None and self._packed_key[0] == str(device) \
+                and self._packed_frozen:
+            return self._packed   # inference fast path: frozen weights (requires_grad False) are not re-hashed
         members = self.member_networks()
         params = [p for m in members for p in m.parameters()]
         key = (str(device), tuple((p.data_ptr(), p._version) for p in params))
@@ -188,6 +204,7 @@ class AtomicContainer(torch.nn.Module):
             self._packed = PackedNetworks(weights, in_dim, device)
             self._packed.set_active_members(self.active_members_idxs)
             self._packed_key = key
+            self._packed_frozen = all(not p.requires_grad for p in params)
         return self._packed
 
     def _run(self, elem_idxs: Tensor, aevs: Tensor, atomic: bool, ensemble_values: bool) -> Tensor:
