@@ -129,12 +129,14 @@ int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, i
 /* 3. Fused neighbour search + AEV forward for sorted atoms lo..hi-1.                      */
 /*      row_of     row of the output matrix for each sorted atom (species-grouped rows for   */
 /*                 the fused engine, flat input index for the AEVComputer API)               */
-/*      aev        f32[rows][ldx]; columns 0..out_dim-1 of the atom's row are overwritten    */
+/*      aev        layout 0: f32[rows][ldx], columns 0..out_dim-1 of the atom's row are      */
+/*                 overwritten.  layout 1: the "tiled operand" form the MLP consumes          */
+/*                 (see below; 2*rows_cap*ldx floats, rows_cap % 128 == 0, ldx % 16 == 0)      */
 /*      nbr_cnt    i32[n]; nbr_list i32[n*nbr_cap]: neighbours within Rcr of every processed  */
 /*                 atom as (sorted index | image code << 26); kept for the backward pass      */
 int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
                          const int32_t* bin_start, const float* spos, const int32_t* sbin, int n,
-                         int lo, int hi, const int32_t* row_of, float* aev, int ldx,
+                         int lo, int hi, const int32_t* row_of, float* aev, int ldx, int layout,
                          int32_t* nbr_cnt, int32_t* nbr_list, int nbr_cap, int32_t* status,
                          void* stream);
 
@@ -160,14 +162,17 @@ int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, 
 
 /* 6. Ensemble MLP forward + backward-to-input on the species-grouped AEV matrix.           */
 /*    Layer widths: in -> h1 -> h2 -> h3 -> 1, CELU(alpha) after the three hidden layers.    */
-/*    "tiled B operand" of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K]):     */
-/*    K is zero-padded to a multiple of 16, every value is split into hi = x & 0xffffe000 and    */
-/*    lo = x - hi, and the result is stored as                                                    */
-/*        [member][n tile (256 rows, the last one shorter)][k block (16 floats)]                   */
-/*        [hi: bn rows x 64 B][lo: bn rows x 64 B]                                                */
-/*    where every 8-row x 64-byte group is written in the tcgen05 SWIZZLE_64B order (16-byte       */
-/*    chunk c of row r sits at chunk position c ^ ((r >> 1) & 3)).  One K-block of one tile is     */
-/*    therefore two contiguous byte ranges that a single cp.async.bulk moves into shared memory.  */
+/*    "Tiled operand" layout (both GEMM operands; fp32 accuracy on the tensor cores = 3xTF32):  */
+/*    every value is split into hi = x & 0xffffe000 (an exact TF32) and lo = x - hi.             */
+/*    * A operand / activation matrix [rows][cols] (rows % 128 == 0, cols % 16 == 0):            */
+/*        [row tile of 128][16-column block][hi: 128 rows x 64 B | lo: 128 rows x 64 B]          */
+/*    * B operand of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K], K padded    */
+/*      to a multiple of 16 with zeros):                                                         */
+/*        [member][n tile (256 rows, the last one shorter)][16-column block][hi bn x 64 B | lo]  */
+/*    In both, every 8-row x 64-byte group is in the tcgen05 SWIZZLE_64B order (16-byte chunk c  */
+/*    of row r sits at chunk position c ^ ((r >> 1) & 3)), i.e. exactly the shared-memory image  */
+/*    a K-major UMMA descriptor expects: one K-block of one tile is a contiguous byte range      */
+/*    that a single cp.async.bulk (TMA) moves into shared memory.                                */
 typedef struct ani_mlp_species {
   int32_t h1, h2, h3, pad_;
   const float* b1;   /* [M*h1]                                                                  */
@@ -191,18 +196,18 @@ typedef struct ani_mlp_model {
   ani_mlp_species sp[ANI_MAX_SPECIES];
 } ani_mlp_model;
 
-/*    x            f32[rows_cap][ldx]   in: AEVs; out: dE/dAEV (in place)                     */
-/*    tile_species / row_atom / layout_info: outputs of ani_b200_species_layout              */
-/*    act1/2/3     f32[rows_cap][M*h{1,2,3}_max]  workspaces (activations, then gradients)    */
-/*    e_member     f32[M][rows_cap]     per-member atomic energies                            */
-/*    aev_blocks   output of ani_b200_active_aev_blocks or NULL (= every column is live).   */
-/*                 With a block list, layer 1 skips the dead K-blocks and dE/dAEV is written   */
-/*                 only for the live column blocks (the others keep their previous content).   */
-int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
-                                  const int32_t* tile_species, const int32_t* row_atom,
-                                  const int32_t* layout_info, const int32_t* aev_blocks, float* act1,
-                                  float* act2, float* act3, float* e_member, int want_backward,
-                                  void* stream);
+/*    x            tiled operand, in: AEVs (ani_b200_aev_forward layout 1), 2*rows_cap*ldx f32 */
+/*    dx           f32[rows_cap][ldx] plain rows, out: dE/dAEV (may be NULL if !want_backward)  */
+/*    row_atom / layout_info: outputs of ani_b200_species_layout                                */
+/*    aev_blocks   output of ani_b200_active_aev_blocks or NULL (= every column is live).       */
+/*                 With a block list, layer 1 skips the dead K-blocks and dE/dAEV is written     */
+/*                 only for the live column blocks (the others keep their previous content).     */
+/*    act1/2/3     tiled operands 2*rows_cap*M*h{1,2,3}_max f32 (activations, then gradients)    */
+/*    e_member     f32[M][rows_cap]     per-member atomic energies                               */
+int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const float* x, float* dx, int rows_cap,
+                                  const int32_t* row_atom, const int32_t* layout_info,
+                                  const int32_t* aev_blocks, float* act1, float* act2, float* act3,
+                                  float* e_member, int want_backward, void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
 /*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */

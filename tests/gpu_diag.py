@@ -119,12 +119,10 @@ def run_case(name, engines):
         print(f"  pair sets equal: {same}; max |dist - golden| = {np.abs(d_m[order] - gd[gorder]).max():.3e}")
 
     # ---- AEV forward (x was overwritten by dE/dAEV in the step -> recompute the forward only)
-    check(L.ani_b200_aev_forward(C.byref(eng.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos),
-                                 ptr(ws.sbin), n, 0, n, ptr(ws.row_of), ptr(ws.x), eng.nets.ldx,
-                                 ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st))
-    torch.cuda.synchronize()
+    from torchani_b200.engine import untile_a_operand
+    xt = untile_a_operand(ws.x.reshape(-1), ws.rows_cap, eng.nets.ldx)   # AEVs of the step (tiled -> plain)
     row_of = ws.row_of.cpu().numpy()
-    x = ws.x.cpu().numpy()
+    x = xt.cpu().numpy()
     D = eng.consts.out_dim
     aev_mine = np.zeros((n, D))
     for i in range(n_real):
@@ -145,12 +143,8 @@ def run_case(name, engines):
     e_tot = res.energies.cpu().numpy()
     print(f"  energies (NN+SAE) mine {e_tot[:3]} ref {ref['energy'].numpy()[:3]} "
           f"max-abs {np.abs(e_tot - ref['energy'].numpy()).max():.3e}")
-    # dE/dAEV: rerun fwd+mlp (x currently holds fresh AEVs)
-    check(L.ani_b200_mlp_forward_backward(C.byref(eng.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species),
-                                          ptr(ws.row_atom), ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3),
-                                          ptr(ws.e_member), 1, st))
-    torch.cuda.synchronize()
-    gx = ws.x.cpu().numpy()
+    # dE/dAEV of the step (plain rows)
+    gx = ws.dx.cpu().numpy()
     g_mine = np.zeros((n, D))
     for i in range(n_real):
         g_mine[so[i]] = gx[row_of[i], :D]

@@ -36,8 +36,9 @@ def gpu_aev(eng, species, coords, cell, pbc):
     ws = eng.workspace(*species.shape)
     n = species.numel()
     st = torch.cuda.current_stream().cuda_stream
+    plain = torch.zeros(ws.rows_cap, eng.nets.ldx, device=dev)
     check(lib().ani_b200_aev_forward(C.byref(eng.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos),
-                                     ptr(ws.sbin), n, 0, n, ptr(ws.row_of), ptr(ws.x), eng.nets.ldx,
+                                     ptr(ws.sbin), n, 0, n, ptr(ws.row_of), ptr(plain), eng.nets.ldx, 0,
                                      ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st))
     torch.cuda.synchronize()
     eng.check_status(ws)
@@ -45,8 +46,12 @@ def gpu_aev(eng, species, coords, cell, pbc):
     n_real = int((species >= 0).sum())
     so = ws.sorted_orig[:n_real].long()
     rows = ws.row_of[:n_real].long()
+    # the engine's own AEV buffer holds the same numbers in the tiled hi/lo form
+    from torchani_b200.engine import untile_a_operand
+    tiled = untile_a_operand(ws.x.reshape(-1), ws.rows_cap, eng.nets.ldx)
+    assert torch.equal(tiled[rows, :D], plain[rows, :D]), "tiled and plain AEV outputs differ"
     aev = torch.zeros(n, D, device=dev)
-    aev[so] = ws.x[rows, :D]
+    aev[so] = plain[rows, :D]
     return aev.view(*species.shape, D).cpu(), res
 
 

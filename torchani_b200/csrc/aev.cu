@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     k_aev_forward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                   const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
                   const int32_t* __restrict__ sbin, int lo, int hi, const int32_t* __restrict__ row_of,
-                  float* __restrict__ aev, int ldx, int32_t* __restrict__ nbr_cnt,
+                  float* __restrict__ aev, int ldx, int layout, int32_t* __restrict__ nbr_cnt,
                   int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -208,6 +208,19 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const int i = lo + blockIdx.x * AEV_WARPS + warp;
   if (i >= hi) return;
   const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, false);
+  // output: plain row-major rows, or the hi/lo-split tiled operand layout the GEMM consumes
+  const int out_row = row_of[i];
+  const int kblocks = ldx >> 4;
+  auto store_feature = [&](int col, float v) {
+    if (layout == 0) {
+      aev[(size_t)out_row * ldx + col] = v;
+    } else {
+      const size_t idx = opnd_index(out_row, col, kblocks);
+      const float vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      aev[idx] = vh;
+      aev[idx + OPND_PART_BYTES / 4] = v - vh;
+    }
+  };
   const int S = P.num_species;
   const int nR = P.n_shf_r;
   const int RL = S * nR;
@@ -271,8 +284,6 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   for (int t = lane; t < 2 * RL; t += 32) s.rad[t] = 0.f;
   __syncwarp();
 
-  const size_t row = (size_t)row_of[i] * ldx;
-
   // ---- 2. radial block: lane = (shift m, neighbour parity h); the two parities own separate
   //         accumulator arrays, lanes of one parity hit distinct addresses -> no atomics
   {
@@ -287,7 +298,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
       if (m < nR) s.rad[h * RL + s.nsp[n] * nR + m] += v;
     }
     __syncwarp();
-    for (int t = lane; t < RL; t += 32) aev[row + t] = s.rad[t] + (halves == 2 ? s.rad[RL + t] : 0.f);
+    for (int t = lane; t < RL; t += 32) store_feature(t, s.rad[t] + (halves == 2 ? s.rad[RL + t] : 0.f));
   }
 
   // ---- 3. angular block
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
         }
         out = transpose_reduce32(acc, lane);
       }
-      aev[row + RL + p * 32 + lane] = out;
+      store_feature(RL + p * 32 + lane, out);
     }
   }
 }
@@ -663,7 +674,7 @@ using namespace ani;
 
 extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
                                     const float* spos, const int32_t* sbin, int n, int lo, int hi,
-                                    const int32_t* row_of, float* aev, int ldx, int32_t* nbr_cnt,
+                                    const int32_t* row_of, float* aev, int ldx, int layout, int32_t* nbr_cnt,
                                     int32_t* nbr_list, int nbr_cap, int32_t* status, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
@@ -674,6 +685,8 @@ extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid
   const int out_dim = params->num_species * params->n_shf_r +
                       params->num_species * (params->num_species + 1) / 2 * 32;
   if (ldx < out_dim) return ANI_ERR_BAD_ARG;
+  if (layout != 0 && layout != 1) return ANI_ERR_BAD_ARG;
+  if (layout == 1 && ldx % 16) return ANI_ERR_BAD_ARG;
   if (hi == lo) return ANI_OK;
   const int RL = params->num_species * params->n_shf_r;
   const size_t wb = warp_smem_bytes(nbr_cap, 2 * RL, false);
@@ -684,12 +697,12 @@ extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid
   if (params->n_shf_a == 8) {
     auto k = k_aev_forward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx,
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx, layout,
                                             nbr_cnt, nbr_list, nbr_cap, status, wb);
   } else {
     auto k = k_aev_forward<4, 8>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx,
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx, layout,
                                             nbr_cnt, nbr_list, nbr_cap, status, wb);
   }
   ANI_CUDA_CHECK_LAUNCH();

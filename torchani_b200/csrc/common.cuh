@@ -76,4 +76,21 @@ __device__ __forceinline__ float3 image_shift(const ani_grid& g, int code) {
   return s;
 }
 
+// ---- "tiled operand" layout shared by the AEV kernel (producer) and the tensor-core GEMM ----
+// An activation matrix [rows][cols] is stored per 128-row tile and 16-column block as
+// [hi 128 rows x 64 B | lo 128 rows x 64 B] (16 KB), every 8-row group in SWIZZLE_64B order.
+constexpr int OPND_ROW_BYTES = 64;
+constexpr int OPND_PART_BYTES = ANI_TILE_ROWS * OPND_ROW_BYTES;  // 8 KB
+constexpr int OPND_BLOCK_BYTES = 2 * OPND_PART_BYTES;            // 16 KB
+// byte offset of 16-byte chunk `ch` (0..3) of row `row` (0..127) inside the hi (or lo) part
+__device__ __forceinline__ uint32_t swz_off(int row, int ch) {
+  return (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u + (uint32_t)((ch ^ ((row >> 1) & 3)) << 4);
+}
+// float index of element (row, col) of a tiled matrix with `kblocks` = cols/16 blocks per row tile;
+// the lo part is OPND_PART_BYTES/4 floats further
+__device__ __forceinline__ size_t opnd_index(int row, int col, int kblocks) {
+  const int rt = row / ANI_TILE_ROWS, r = row % ANI_TILE_ROWS;
+  return ((size_t)rt * kblocks + (col >> 4)) * (OPND_BLOCK_BYTES / 4) + (swz_off(r, (col & 15) >> 2) >> 2) + (col & 3);
+}
+
 }  // namespace ani

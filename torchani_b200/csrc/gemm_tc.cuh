@@ -1,26 +1,29 @@
-// Persistent, warp-specialised tcgen05 grouped GEMM for the ensemble MLP (sm_100a).
+// Persistent, warp-specialised, TMA-fed tcgen05 grouped GEMM for the ensemble MLP (sm_100a).
 //
 //   C[128-row tile, bn] = epilogue( A[128, K] x B[bn, K]^T )        both operands K-major fp32
 //
-// fp32 accuracy on the tensor cores ("3xTF32"): every fp32 operand is split into
+// fp32 accuracy on the tensor cores ("3xTF32"): every fp32 operand is stored split into
 // hi = x & 0xffffe000 (exact TF32) and lo = x - hi (exact in fp32); the MMA thread issues three
 // kind::tf32 products per K-step (lo*hi, hi*lo, hi*hi) into one fp32 accumulator in tensor
 // memory.  The dropped lo*lo term is ~2^-22 relative.
-//   * B (weights) is split, tiled and swizzled ONCE at model-pack time (ani_b200.h, "tiled B
-//     operand"); a K-block of a tile is two contiguous byte ranges that one thread moves with
-//     cp.async.bulk (TMA) straight into the SWIZZLE_128B shared-memory layout.
-//   * A (activations) is split on the fly by the producer warps: coalesced 16-byte loads, the
-//     loads of K-block k+1 are in flight while K-block k is split and stored.
 //
-// Roles (9 warps, one CTA per SM, persistent over the device-side tile list):
-//   warps 0-3  epilogue : tcgen05.ld accumulator rows (warp w owns TMEM lanes 32w..32w+31);
-//                         global traffic is staged through a 32x32 shared-memory transpose so
-//                         that loads (old activation for CELU') and stores are 128-byte rows
-//   warp  4    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
-//   warps 5-8  producer : A split + swizzled st.shared + fence.proxy.async; thread 0 also
-//                         issues the bulk copies of B (mbarrier expect_tx / complete_tx)
-// Pipelines: smem full/empty (4 stages x 48 KB: three K-blocks in flight cover the L2/HBM latency
-// of the one being multiplied) and TMEM full/empty (2 x 256 columns), so the
+// BOTH operands live in global memory in the "tiled operand" layout of include/ani_b200.h:
+// 16-float K-blocks, [hi rows x 64 B | lo rows x 64 B], every 8-row group in SWIZZLE_64B order.
+//   * B (weights) is tiled once at model-pack time,
+//   * A (activations / gradients) is written in that layout by the epilogue of the GEMM (or by
+//     the AEV kernel) that produces it -- the split costs nothing extra there.
+// A K-block of a tile is therefore 1 + 1 contiguous byte ranges that ONE thread moves with
+// cp.async.bulk (TMA) straight into the shared-memory layout the MMA descriptors expect; no
+// thread ever touches operand data.  (An earlier version split A on the fly in 8 producer warps:
+// ablation showed 40 % of the GEMM time was the instruction chain of that loop.)
+//
+// Roles (10 warps, one CTA per SM, persistent over the device-side tile list):
+//   warps 0-7  epilogue : tcgen05.ld (thread = row; warps w and w+4 share TMEM lanes and take
+//                         alternate 16-column groups), bias + CELU | * CELU'(stored activation) |
+//                         final layer + gradient seed | plain, hi/lo split, 16-byte stores
+//   warp  8    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
+//   warp  9    producer : one lane arms the mbarrier (expect_tx) and issues the bulk copies
+// Pipelines: smem full/empty (4 stages x 48 KB) and TMEM full/empty (2 x 256 columns), so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #pragma once
 #include "common.cuh"
@@ -34,33 +37,33 @@ constexpr int TK = 16;                   // fp32 per K-block = one 64-byte swizz
 constexpr int ROW_BYTES = TK * 4;        // 64
 constexpr int GROUP_BYTES = 8 * ROW_BYTES;       // 8-row swizzle group = 512 B (descriptor SBO)
 constexpr int STAGES = 4;
-constexpr int A_TILE_BYTES = TM * ROW_BYTES;     // 8 KB
+constexpr int A_PART_BYTES = TM * ROW_BYTES;     // 8 KB (hi or lo of one A K-block)
+constexpr int A_BLOCK_BYTES = 2 * A_PART_BYTES;  // 16 KB: [hi | lo], contiguous in global memory
 constexpr int B_TILE_BYTES = TN_MAX * ROW_BYTES; // 16 KB
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi+lo of A and B = 48 KB
-constexpr int EPI_LD = 36;                                  // padded row of the 32x32 transpose buffer (floats)
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;               // one buffer per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int NUM_EPI_WARPS = 4, MMA_WARP = 4, FIRST_PROD_WARP = 5, NUM_PROD_WARPS = 4;
-constexpr int NPT = NUM_PROD_WARPS * 32;  // producer threads
-constexpr int THREADS = (NUM_EPI_WARPS + 1 + NUM_PROD_WARPS) * 32;  // 288
+constexpr int STAGE_BYTES = A_BLOCK_BYTES + 2 * B_TILE_BYTES;  // 48 KB
+constexpr int EPI_STAGE_BYTES = 2 * 32 * ROW_BYTES;           // per epilogue warp: 32 rows x 64 B, hi + lo = 4 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, PROD_WARP = 9;
+constexpr int THREADS = (NUM_EPI_WARPS + 2) * 32;  // 320
 constexpr int TMEM_COLS = 512;
 
 enum { EPI_BIAS_CELU = 0, EPI_MUL_DCELU = 1, EPI_PLAIN = 2, EPI_HEAD = 3 };
 
 struct Species {
-  const float* Bt;    // tiled B operand (hi/lo split, swizzled), see ani_b200.h
+  const float* Bt;    // tiled B operand
   const float* bias;  // [N] (+ member * bias_mstride) or nullptr
   int K, N;
-  int a_moff, c_moff, bias_mstride;
+  int a_moff, c_moff, bias_mstride;  // per-member column offsets into A / C (multiples of 16)
   const float* w4;    // EPI_HEAD: final layer weights [M][N] and biases [M]
   const float* b4;
 };
 
 struct Args {
-  const float* A;
-  float* C;
-  int lda, ldc;
-  int members;                  // GEMMs per row tile (grid z of the SIMT version)
+  const float* A;               // tiled activation matrix [row tile][a_kblocks][hi 128x64B | lo 128x64B]
+  float* C;                     // tiled activation matrix (EPI_PLAIN: plain row-major [rows][ldc])
+  int a_kblocks, c_kblocks;     // 16-column blocks per row of A / C  (= leading dimension / 16)
+  int ldc;                      // EPI_PLAIN only
+  int members;                  // GEMMs per row tile
   const int32_t* layout_info;   // [4 + S + 1]: ..., first row tile of species s, total row tiles
   const int32_t* kblocks;       // optional list of live 32-wide K-blocks: [count, ids...]  (layer-1 forward)
   const int32_t* nblocks;       // optional list of live 32-wide column blocks of C          (layer-1 backward)
@@ -71,7 +74,7 @@ struct Args {
   const int32_t* row_atom;      // [rows_cap], -1 for padding rows
   int rows_cap;
   int want_backward;
-  int debug;                    // bring-up only (ANI_B200_GEMM_DEBUG): 1 no A stores, 2 no B copies, 4 no MMA, 8 no epilogue, 16 no A loads
+  int debug;                    // timing experiments only (ANI_B200_GEMM_DEBUG): 2 no copies, 4 no MMA, 8 no epilogue
   float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
 };
@@ -95,6 +98,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// TMA bulk store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -109,7 +121,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -163,10 +174,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
   d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
   return d;
-}
-// byte offset of 16-byte chunk `ch` (0..3) of row `row` inside a K-major SWIZZLE_64B tile
-__device__ __forceinline__ uint32_t swz_off(int row, int ch) {
-  return (uint32_t)(row >> 3) * GROUP_BYTES + (uint32_t)(row & 7) * ROW_BYTES + (uint32_t)((ch ^ ((row >> 1) & 3)) << 4);
 }
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
@@ -245,34 +252,38 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-// position of a producer in the flattened (tile, K-block) sequence of its CTA
-struct KItem {
-  int t, kb, nkb, K;
-  Tile tl;
-  const float* A;
-  bool valid;
-};
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+  lo.x = v.x - hi.x;
+  lo.y = v.y - hi.y;
+  lo.z = v.z - hi.z;
+  lo.w = v.w - hi.w;
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Args args) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned operand tiles (swizzle groups are 8 rows x 64 B)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* epi_buf = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);
-  uint64_t* full = bars;                     // [STAGES]  producers (+ TMA bytes) -> MMA
-  uint64_t* empty = bars + STAGES;           // [STAGES]  MMA (commit) -> producers
+  unsigned char* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 x 4 KB store staging (epilogue warps)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 8 * EPI_STAGE_BYTES);
+  uint64_t* full = bars;                     // [STAGES]  TMA bytes -> MMA
+  uint64_t* empty = bars + STAGES;           // [STAGES]  MMA (commit) -> producer
   uint64_t* tfull = bars + 2 * STAGES;       // [2]       MMA (commit) -> epilogue
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   __shared__ TileMap tm;
+  __shared__ float e_part[NUM_EPI_WARPS * 32];  // EPI_HEAD: partial row energies of the two column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     build_tile_map(args, tm);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], NUM_PROD_WARPS + 1);  // one arrival per producer warp + the expect_tx arrival
+      mbar_init(&full[i], 1);   // the expect_tx arrival of the producer lane (+ the transaction bytes)
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -291,121 +302,57 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   auto num_kb = [&](int K) { return tm.kb_count >= 0 ? 2 * tm.kb_count : (K + TK - 1) / TK; };
   auto kb_id = [&](int i) { return tm.kb_count >= 0 ? tm.kb[i >> 1] * 2 + (i & 1) : i; };
 
-  if (warp >= FIRST_PROD_WARP) {
-    // ================================ producers ================================
-    // Thread pt owns 16-byte chunk (pt & 3) of rows (pt >> 2) + 32*i, i = 0..3, of every K-block:
-    // its global pointer advances by k0 only and its four swizzled smem offsets are constants.
-    const int pt = threadIdx.x - FIRST_PROD_WARP * 32;  // 0..NPT-1
-    constexpr int A_IT = (TM * 4) / NPT;                // chunks per thread per K-block (4)
-    const int my_row = pt >> 2, my_ch = pt & 3;
-    const uint32_t my_off = swz_off(my_row, my_ch);     // + i * 32 rows = + i * 4 groups = + i * 2048 B
-    const size_t row_stride = (size_t)32 * args.lda;
-
-    auto set_tile = [&](KItem& it) {
-      it.valid = it.t < total_tiles;
-      if (it.valid) {
-        it.tl = decode_tile(args, tm, it.t);
-        it.K = args.sp[it.tl.s].K;
-        it.nkb = num_kb(it.K);
-        it.A = args.A + (size_t)it.tl.rt * TM * args.lda + (size_t)it.tl.mem * args.sp[it.tl.s].a_moff +
-               (size_t)my_row * args.lda + my_ch * 4;
-        it.kb = 0;
-      }
-    };
-    auto advance = [&](KItem& it) {
-      if (++it.kb >= it.nkb && it.valid) {
-        it.t += gridDim.x;
-        set_tile(it);
-      }
-    };
-    auto load_a = [&](float4 (&dst)[A_IT], const KItem& it) {
-      if (!it.valid) return;
-      const int k0 = kb_id(it.kb) * TK;
-      const bool in_k = (k0 + my_ch * 4 < it.K) && !(args.debug & 16);
-      const float* p = it.A + k0;
-#pragma unroll
-      for (int i = 0; i < A_IT; ++i)
-        dst[i] = in_k ? *reinterpret_cast<const float4*>(p + i * row_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-
-    KItem cur, pf;
-    cur.t = blockIdx.x;
-    set_tile(cur);
-    pf = cur;
-    // register ring with STATIC slots: slot k holds the A chunks of the K-block that is RING
-    // iterations ahead; it is consumed (split + stored) and immediately refilled.  No register of an
-    // in-flight load is ever moved, so RING K-blocks of HBM/L2 latency really overlap.
-    constexpr int RING = 6;
-    float4 ring[RING][A_IT];
-#pragma unroll
-    for (int d = 0; d < RING; ++d) {
-      load_a(ring[d], pf);
-      advance(pf);
-    }
+  if (warp == PROD_WARP) {
+    // ================================ producer (TMA) ================================
     uint32_t stage = 0, phase = 0;
-    while (cur.valid) {
-#pragma unroll
-      for (int k = 0; k < RING; ++k) {
-        if (cur.valid) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          unsigned char* st = smem + stage * STAGE_BYTES;
-          if (pt < 16) {
-            // B: TMA bulk copies, one per thread (dense: hi, lo; gathered column blocks: 2 per block)
-            const Species& sp = args.sp[cur.tl.s];
-            const uint32_t b_bytes = (uint32_t)cur.tl.bn * ROW_BYTES;
-            if (pt == 0) mbar_arrive_expect_tx(&full[stage], (args.debug & 2) ? 0u : 2 * b_bytes);
-            const bool dense = tm.nb_count < 0;
-            if (!(args.debug & 2) && pt < (dense ? 2 : 2 * (cur.tl.bn / 32))) {
-              const int nkb_all = (cur.K + TK - 1) / TK;  // K-blocks of the stored operand
-              const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) +
-                                        (size_t)cur.tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
-              const int kbi = kb_id(cur.kb);
-              if (dense) {
-                // [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
-                const unsigned char* src = Bm +
-                                           ((size_t)cur.tl.n0 * nkb_all + (size_t)kbi * cur.tl.bn) * (2 * ROW_BYTES) +
-                                           (size_t)pt * b_bytes;
-                bulk_g2s(st + 2 * A_TILE_BYTES + pt * B_TILE_BYTES, src, b_bytes, &full[stage]);
-              } else {
-                // gathered column blocks: 32 rows (2 KB) of the stored operand per live block and part
-                const int q = pt >> 1, part = pt & 1;
-                const int row0 = tm.nb[cur.tl.n0 / 32 + q] * 32;
-                const int n0s = row0 / TN_MAX * TN_MAX;
-                const int bns = min(TN_MAX, sp.N - n0s);
-                const unsigned char* src = Bm + ((size_t)n0s * nkb_all + (size_t)kbi * bns) * (2 * ROW_BYTES) +
-                                           (size_t)(row0 - n0s) * ROW_BYTES + (size_t)part * bns * ROW_BYTES;
-                bulk_g2s(st + 2 * A_TILE_BYTES + part * B_TILE_BYTES + q * 32 * ROW_BYTES, src, 32 * ROW_BYTES,
-                         &full[stage]);
-              }
-            }
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile tl = decode_tile(args, tm, t);
+      const Species& sp = args.sp[tl.s];
+      const int nkb = num_kb(sp.K);
+      const int nkb_all = (sp.K + TK - 1) / TK;  // K-blocks of the stored B operand
+      // A: [row tile][16-column block][hi | lo]; this GEMM starts at column member * a_moff
+      const unsigned char* At = reinterpret_cast<const unsigned char*>(args.A) +
+                                ((size_t)tl.rt * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
+      // B: [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
+      const unsigned char* Bm =
+          reinterpret_cast<const unsigned char*>(sp.Bt) + (size_t)tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
+      const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
+      const bool dense = tm.nb_count < 0;
+      // gathered column blocks (layer-1 backward): lane -> (live block q, part hi/lo)
+      const int gq = lane >> 1, gpart = lane & 1;
+      size_t g_src = 0;
+      int g_bns = 0;
+      const bool g_active = !dense && lane < 2 * (tl.bn / 32);
+      if (g_active) {
+        const int row0 = tm.nb[tl.n0 / 32 + gq] * 32;
+        const int n0s = row0 / TN_MAX * TN_MAX;
+        g_bns = min(TN_MAX, sp.N - n0s);
+        g_src = (size_t)n0s * nkb_all * (2 * ROW_BYTES) + (size_t)(row0 - n0s) * ROW_BYTES +
+                (size_t)gpart * g_bns * ROW_BYTES;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        unsigned char* st = smem + stage * STAGE_BYTES;
+        const int kbi = kb_id(kb);
+        if (!(args.debug & 2)) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + 2 * b_bytes);
+            bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
+            if (dense)  // hi and lo are adjacent in global memory and in shared memory: one copy
+              bulk_g2s(st + A_BLOCK_BYTES, Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbi * tl.bn) * (2 * ROW_BYTES),
+                       2 * b_bytes, &full[stage]);
           }
-          if (!(args.debug & 1)) {
-#pragma unroll
-            for (int i = 0; i < A_IT; ++i) {
-              const float4 v = ring[k][i];
-              float4 hi, lo;
-              hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-              hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-              hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-              hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-              lo.x = v.x - hi.x;
-              lo.y = v.y - hi.y;
-              lo.z = v.z - hi.z;
-              lo.w = v.w - hi.w;
-              *reinterpret_cast<float4*>(st + my_off + i * (4 * GROUP_BYTES)) = hi;
-              *reinterpret_cast<float4*>(st + A_TILE_BYTES + my_off + i * (4 * GROUP_BYTES)) = lo;
-            }
-          }
-          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full[stage]);
-          load_a(ring[k], pf);  // refill this slot for the K-block RING iterations ahead
-          advance(pf);
-          advance(cur);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (g_active)
+            bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,
+                     Bm + g_src + (size_t)kbi * g_bns * (2 * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
+        } else if (lane == 0) {
+          mbar_arrive(&full[stage]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
@@ -416,6 +363,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       const Tile tl = decode_tile(args, tm, t);
       const int nkb = num_kb(args.sp[tl.s].K);
       const uint32_t idesc = make_idesc(tl.bn);
+      const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * TN_MAX;
@@ -424,8 +372,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_TILE_BYTES);
-          const uint64_t b_hi = make_desc(sa + 2 * A_TILE_BYTES), b_lo = make_desc(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PART_BYTES);
+          const uint64_t b_hi = make_desc(sa + A_BLOCK_BYTES), b_lo = make_desc(sa + A_BLOCK_BYTES + b_bytes);
 #pragma unroll
           for (int k = 0; k < TK / 8; ++k) {
             if (args.debug & 4) break;
@@ -450,113 +398,128 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
   } else {
     // ================================ epilogue ================================
-    // Per 32-column chunk: (CELU' only) the stored activation arrives through a coalesced,
-    // one-chunk-ahead prefetch into the warp's 32x32 buffer; tcgen05.ld (thread = row);
-    // elementwise op; result back into the buffer; coalesced 128-byte-row stores.
+    // Thread = accumulator row (TMEM lane).  Warps w and w+4 share the 32 lanes of quadrant w & 3
+    // and take alternate 16-column groups.  Results are written hi/lo-split into the tiled operand
+    // layout of the next GEMM (EPI_PLAIN: plain rows for the AEV backward kernel).
     uint32_t acc = 0, acc_phase = 0;
     const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
-    float* buf = epi_buf + warp * 32 * EPI_LD;
-    const int cr = lane >> 3, cq = (lane & 7) * 4;  // coalesced phase: rows cr + 4*i, columns cq..cq+3
+    const int quad = warp & 3, half = warp >> 2;
+    const int r_tile = quad * 32 + lane;  // row inside the 128-row tile
+    uint32_t my_off[4], st_off[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      my_off[ch] = swz_off(r_tile, ch);   // inside a 128-row block (global)
+      st_off[ch] = swz_off(lane, ch);     // inside this warp's 32-row staging image (shared)
+    }
+    // The warp's 32 rows x 64 B of one 16-column group are a contiguous 2 KB range of the tiled
+    // layout (hi) plus another one 8 KB further (lo): stage them in shared memory in that very
+    // byte order and let the TMA write them (full lines, no partial-sector stores).
+    unsigned char* sb = epi_stage + warp * EPI_STAGE_BYTES;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
-      float* __restrict__ crow0 = args.C + (size_t)(tl.rt * TM + warp * 32) * args.ldc + (size_t)tl.mem * sp.c_moff;
       const float* __restrict__ bias = (EPI == EPI_BIAS_CELU || EPI == EPI_HEAD)
                                            ? sp.bias + (size_t)tl.mem * sp.bias_mstride + tl.n0
                                            : nullptr;
-      // EPI_HEAD: this thread's row produces one atomic energy e = w4 . celu(z3) + b4
       const float* __restrict__ w4 = (EPI == EPI_HEAD) ? sp.w4 + (size_t)tl.mem * sp.N : nullptr;
-      const int my_row = tl.rt * TM + warp * 32 + lane;
+      const int my_row = tl.rt * TM + r_tile;
       float e_acc = 0.f, seed = 0.f;
       bool row_valid = false;
       if (EPI == EPI_HEAD) {
         row_valid = args.row_atom[my_row] >= 0;
         seed = row_valid ? args.member_scale[tl.mem] : 0.f;
       }
-      // first column of chunk c0 in C (compacted column blocks map back to their place)
-      auto chunk_ptr = [&](int c0) {
-        return crow0 + (tm.nb_count >= 0 ? tm.nb[(tl.n0 + c0) / 32] * 32 : tl.n0 + c0);
-      };
-      float4 yreg[8];
-      auto load_y = [&](int c0) {
-        const int ncol = min(32, tl.bn - c0);
-        if (cq < ncol) {
-          const float* p = chunk_ptr(c0);
+      // tiled C: the block of 16-column group g is [row tile][(member*c_moff + n0)/16 + g]
+      unsigned char* ct = reinterpret_cast<unsigned char*>(args.C) +
+                          ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
+      float* cplain = args.C + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
+      const int ngroups = tl.bn / 16;
+      float4 yh[4], yl[4];
+      auto load_y = [&](int g) {  // stored activation (hi + lo) of 16-column group g, this thread's row
+        const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) yreg[i] = *reinterpret_cast<const float4*>(p + (size_t)(cr + 4 * i) * args.ldc + cq);
+        for (int ch = 0; ch < 4; ++ch) {
+          yh[ch] = *reinterpret_cast<const float4*>(blk + my_off[ch]);
+          yl[ch] = *reinterpret_cast<const float4*>(blk + A_PART_BYTES + my_off[ch]);
         }
       };
-      if (EPI == EPI_MUL_DCELU) load_y(0);  // independent of the accumulator: overlaps the MMA wait
+      if (EPI == EPI_MUL_DCELU && half < ngroups && !(args.debug & 128)) load_y(half);  // overlaps the wait for the accumulator
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * TN_MAX;
-      for (int c0 = 0; c0 < tl.bn; c0 += 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
+      for (int g = half; g < ngroups; g += 2) {
         if (args.debug & 8) break;
-        const int ncol = min(32, tl.bn - c0);  // 32 or 16 (bn is a multiple of 16)
-        float* __restrict__ cbase = chunk_ptr(c0);
-        if (EPI == EPI_MUL_DCELU) {
-          if (cq < ncol) {
+        float v[16];
+        if (!(args.debug & 64)) {
+          tmem_ld16(taddr + g * 16, v);
+        } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&buf[(cr + 4 * i) * EPI_LD + cq]) = yreg[i];
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        float4 y[4];
+        if (EPI == EPI_MUL_DCELU) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+            y[ch] = make_float4(yh[ch].x + yl[ch].x, yh[ch].y + yl[ch].y, yh[ch].z + yl[ch].z, yh[ch].w + yl[ch].w);
+          if (g + 2 < ngroups && !(args.debug & 128)) load_y(g + 2);  // prefetch the next group this warp handles
+        }
+        unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float4 o = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          if (EPI == EPI_BIAS_CELU) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + g * 16 + 4 * ch);
+            o.x = celu(o.x + b.x, cc);
+            o.y = celu(o.y + b.y, cc);
+            o.z = celu(o.z + b.z, cc);
+            o.w = celu(o.w + b.w, cc);
+          } else if (EPI == EPI_MUL_DCELU) {
+            o.x *= dcelu_from_out(y[ch].x, cc);
+            o.y *= dcelu_from_out(y[ch].y, cc);
+            o.z *= dcelu_from_out(y[ch].z, cc);
+            o.w *= dcelu_from_out(y[ch].w, cc);
+          } else if (EPI == EPI_HEAD) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + g * 16 + 4 * ch);
+            const float4 w = *reinterpret_cast<const float4*>(w4 + g * 16 + 4 * ch);
+            float a;
+            a = celu(o.x + b.x, cc); e_acc = fmaf(a, w.x, e_acc); o.x = seed * w.x * dcelu_from_out(a, cc);
+            a = celu(o.y + b.y, cc); e_acc = fmaf(a, w.y, e_acc); o.y = seed * w.y * dcelu_from_out(a, cc);
+            a = celu(o.z + b.z, cc); e_acc = fmaf(a, w.z, e_acc); o.z = seed * w.z * dcelu_from_out(a, cc);
+            a = celu(o.w + b.w, cc); e_acc = fmaf(a, w.w, e_acc); o.w = seed * w.w * dcelu_from_out(a, cc);
+          }
+          if (args.debug & 32) continue;
+          if (EPI == EPI_PLAIN) {
+            // compacted column blocks map back to their place: group g lies in live block (n0 + 16 g) / 32
+            const int col = (tm.nb_count >= 0 ? tm.nb[(tl.n0 + g * 16) / 32] * 32 + ((g * 16) & 16) : tl.n0 + g * 16) + 4 * ch;
+            *reinterpret_cast<float4*>(cplain + col) = o;
+          } else if (EPI != EPI_HEAD || args.want_backward) {
+            float4 hi, lo;
+            split4(o, hi, lo);
+            *reinterpret_cast<float4*>(sb + st_off[ch]) = hi;
+            *reinterpret_cast<float4*>(sb + 32 * ROW_BYTES + st_off[ch]) = lo;
+          }
+        }
+        if (EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward) && !(args.debug & 32)) {
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA
+          __syncwarp();
+          if (lane == 0) {
+            bulk_s2g(blk + quad * 32 * ROW_BYTES, sb, 32 * ROW_BYTES);
+            bulk_s2g(blk + A_PART_BYTES + quad * 32 * ROW_BYTES, sb + 32 * ROW_BYTES, 32 * ROW_BYTES);
+            bulk_commit();
+            bulk_wait_read();  // the staging buffer may be overwritten once the TMA has read it
           }
           __syncwarp();
-          if (c0 + 32 < tl.bn) load_y(c0 + 32);
         }
-        float v[32];
-        {
-          float lo16[16];
-          tmem_ld16(taddr + c0, lo16);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = lo16[j];
-          if (ncol > 16) {
-            float hi16[16];
-            tmem_ld16(taddr + c0 + 16, hi16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[16 + j] = hi16[j];
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (4 * q < ncol) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            float4* slot = reinterpret_cast<float4*>(&buf[lane * EPI_LD + 4 * q]);
-            if (EPI == EPI_BIAS_CELU) {
-              const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-              o.x = celu(o.x + b.x, cc);
-              o.y = celu(o.y + b.y, cc);
-              o.z = celu(o.z + b.z, cc);
-              o.w = celu(o.w + b.w, cc);
-            } else if (EPI == EPI_MUL_DCELU) {
-              const float4 y = *slot;
-              o.x *= dcelu_from_out(y.x, cc);
-              o.y *= dcelu_from_out(y.y, cc);
-              o.z *= dcelu_from_out(y.z, cc);
-              o.w *= dcelu_from_out(y.w, cc);
-            } else if (EPI == EPI_HEAD) {
-              const float4 b = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-              const float4 w = *reinterpret_cast<const float4*>(w4 + c0 + 4 * q);
-              float a;
-              a = celu(o.x + b.x, cc); e_acc = fmaf(a, w.x, e_acc); o.x = seed * w.x * dcelu_from_out(a, cc);
-              a = celu(o.y + b.y, cc); e_acc = fmaf(a, w.y, e_acc); o.y = seed * w.y * dcelu_from_out(a, cc);
-              a = celu(o.z + b.z, cc); e_acc = fmaf(a, w.z, e_acc); o.z = seed * w.z * dcelu_from_out(a, cc);
-              a = celu(o.w + b.w, cc); e_acc = fmaf(a, w.w, e_acc); o.w = seed * w.w * dcelu_from_out(a, cc);
-            }
-            *slot = o;
-          }
-        }
-        __syncwarp();
-        if (cq < ncol && (EPI != EPI_HEAD || args.want_backward)) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = cr + 4 * i;
-            *reinterpret_cast<float4*>(cbase + (size_t)r * args.ldc + cq) =
-                *reinterpret_cast<const float4*>(&buf[r * EPI_LD + cq]);
-          }
-        }
-        __syncwarp();
       }
-      if (EPI == EPI_HEAD)
-        args.e_member[(size_t)tl.mem * args.rows_cap + my_row] = row_valid ? e_acc + sp.b4[tl.mem] : 0.f;
+      if (EPI == EPI_HEAD) {
+        // the two warps of a row hold the even / odd 16-column groups: combine through shared memory
+        e_part[warp * 32 + lane] = e_acc;
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // epilogue warps only
+        if (half == 0)
+          args.e_member[(size_t)tl.mem * args.rows_cap + my_row] =
+              row_valid ? e_part[warp * 32 + lane] + e_part[(warp + 4) * 32 + lane] + sp.b4[tl.mem] : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+      }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       if (++acc == 2) {
@@ -567,6 +530,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   }
 
   // ---- teardown
+  if (warp < NUM_EPI_WARPS && lane == 0) bulk_wait_all();  // outstanding TMA stores are complete
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {

@@ -95,13 +95,12 @@ static void launch_gemm_tc(const tc::Args& a, cudaStream_t st) {
   k<<<num_sms, tc::THREADS, tc::SMEM_BYTES, st>>>(a);
 }
 
-extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* x, int rows_cap,
-                                             const int32_t* tile_species, const int32_t* row_atom,
-                                             const int32_t* layout_info, const int32_t* aev_blocks, float* act1,
-                                             float* act2, float* act3, float* e_member, int want_backward,
-                                             void* stream) {
-  if (!model || !x || !tile_species || !row_atom || !layout_info || !act1 || !act2 || !act3 || !e_member)
-    return ANI_ERR_BAD_ARG;
+extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const float* x, float* dx, int rows_cap,
+                                             const int32_t* row_atom, const int32_t* layout_info,
+                                             const int32_t* aev_blocks, float* act1, float* act2, float* act3,
+                                             float* e_member, int want_backward, void* stream) {
+  if (!model || !x || !row_atom || !layout_info || !act1 || !act2 || !act3 || !e_member) return ANI_ERR_BAD_ARG;
+  if (want_backward && !dx) return ANI_ERR_BAD_ARG;
   const int S = model->num_species, M = model->num_members;
   if (S < 1 || S > ANI_MAX_SPECIES || M < 1 || M > ANI_MAX_MEMBERS) return ANI_ERR_BAD_ARG;
   if (rows_cap < ANI_TILE_ROWS || rows_cap % ANI_TILE_ROWS) return ANI_ERR_BAD_ARG;
@@ -116,7 +115,8 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
       return ANI_ERR_BAD_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int ld1 = M * model->h1_max, ld2 = M * model->h2_max, ld3 = M * model->h3_max;
+  // 16-column blocks per row of the tiled activation matrices
+  const int kb1 = M * model->h1_max / 16, kb2 = M * model->h2_max / 16, kb3 = M * model->h3_max / 16, kbx = ldx / 16;
   tc::Args ta;
   ta.layout_info = layout_info;
   ta.kblocks = nullptr;
@@ -127,6 +127,7 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   ta.row_atom = row_atom;
   ta.rows_cap = rows_cap;
   ta.want_backward = want_backward;
+  ta.ldc = 0;
   static const int gemm_debug = []() {
     const char* e = getenv("ANI_B200_GEMM_DEBUG");  // timing experiments only: results are wrong when set
     return e ? atoi(e) : 0;
@@ -136,7 +137,7 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
 
   // ---- forward.  Layer 1: the members share the input -> one GEMM with N = M*h1.
-  ta.A = x; ta.lda = ldx; ta.C = act1; ta.ldc = ld1; ta.members = 1;
+  ta.A = x; ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
     ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr};
@@ -144,13 +145,13 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   ta.kblocks = aev_blocks;  // dead AEV column blocks contribute exact zeros: skip them
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
   ta.kblocks = nullptr;
-  ta.A = act1; ta.lda = ld1; ta.C = act2; ta.ldc = ld2; ta.members = M;
+  ta.A = act1; ta.a_kblocks = kb1; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
     ta.sp[s] = tc::Species{p.t_f2, p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr};
   }
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
-  ta.A = act2; ta.lda = ld2; ta.C = act3; ta.ldc = ld3; ta.members = M;
+  ta.A = act2; ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
     ta.sp[s] = tc::Species{p.t_f3, p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4};
@@ -160,19 +161,19 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, float* 
   launch_gemm_tc<tc::EPI_HEAD>(ta, st);
   if (want_backward) {
     // ---- backward: G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
-    ta.A = act3; ta.lda = ld3; ta.C = act2; ta.ldc = ld2; ta.members = M;
+    ta.A = act3; ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
       ta.sp[s] = tc::Species{p.t_b3, nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
-    ta.A = act2; ta.lda = ld2; ta.C = act1; ta.ldc = ld1; ta.members = M;
+    ta.A = act2; ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
       ta.sp[s] = tc::Species{p.t_b2, nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
-    ta.A = act1; ta.lda = ld1; ta.C = x; ta.ldc = ldx; ta.members = 1;
+    ta.A = act1; ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = 1;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
       ta.sp[s] = tc::Species{p.t_b1, nullptr, M * p.h1, ldx, 0, 0, 0, nullptr, nullptr};

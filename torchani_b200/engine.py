@@ -122,6 +122,35 @@ def tile_b_operand(b: Tensor) -> Tensor:
     return torch.cat(out).contiguous()
 
 
+def tile_a_operand(x: Tensor) -> Tensor:
+    """Plain ``[rows][cols]`` float32 (rows % 128 == 0, cols % 16 == 0) -> flat "tiled operand"
+    (A-operand form of include/ani_b200.h).  Plumbing for the API paths that receive plain AEVs."""
+    rows, cols = x.shape
+    assert rows % 128 == 0 and cols % 16 == 0
+    nkb = cols // 16
+    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+    lo = x - hi
+    r = torch.arange(8, device=x.device).view(8, 1)
+    pos = torch.arange(4, device=x.device).view(1, 4)
+    idx = (pos ^ ((r >> 1) & 3)).view(1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 16, 8, 4, 4)
+    parts = []
+    for part in (hi, lo):
+        v = part.view(rows // 128, 16, 8, nkb, 4, 4).permute(0, 3, 1, 2, 4, 5)   # [rt][kb][grp][row][ch][4]
+        parts.append(torch.gather(v, 4, idx).reshape(rows // 128, nkb, 2048))
+    return torch.stack(parts, 2).reshape(-1).contiguous()                          # [rt][kb][hi|lo][2048]
+
+
+def untile_a_operand(t: Tensor, rows: int, cols: int) -> Tensor:
+    """Inverse of ``tile_a_operand`` (returns hi + lo as plain ``[rows][cols]``)."""
+    nkb = cols // 16
+    v = t.view(rows // 128, nkb, 2, 16, 8, 4, 4)                                   # [rt][kb][part][grp][row][pos][4]
+    r = torch.arange(8, device=t.device).view(8, 1)
+    ch = torch.arange(4, device=t.device).view(1, 4)
+    idx = (ch ^ ((r >> 1) & 3)).view(1, 1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 2, 16, 8, 4, 4)
+    w = torch.gather(v, 5, idx).sum(2)                                              # [rt][kb][grp][row][ch][4]
+    return w.permute(0, 2, 3, 1, 4, 5).reshape(rows, cols).contiguous()
+
+
 class PackedNetworks:
     """Device-resident, kernel-layout copy of an ensemble of per-element MLPs.
 
@@ -239,10 +268,12 @@ class Workspace:
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
-        self.x = torch.zeros(self.rows_cap, ldx, **f32)
-        self.act1 = torch.zeros(self.rows_cap, ld[0], **f32)
-        self.act2 = torch.zeros(self.rows_cap, ld[1], **f32)
-        self.act3 = torch.zeros(self.rows_cap, ld[2], **f32)
+        # x / act*: "tiled operand" form (hi + lo parts -> twice the plain size); dx: plain rows
+        self.x = torch.zeros(self.rows_cap, 2 * ldx, **f32)
+        self.dx = torch.zeros(self.rows_cap, ldx, **f32)
+        self.act1 = torch.zeros(self.rows_cap, 2 * ld[0], **f32)
+        self.act2 = torch.zeros(self.rows_cap, 2 * ld[1], **f32)
+        self.act3 = torch.zeros(self.rows_cap, 2 * ld[2], **f32)
         self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
         self.species_i32 = torch.zeros(n, **i32)
         self.coords = torch.zeros(n, 3, **f32)
@@ -394,17 +425,17 @@ class Engine:
             self.nets.ldx, ptr(ws.aev_blocks), ptr(ws.scratch), st))
         self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
             C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin), n, lo, hi,
-            ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
+            ptr(ws.row_of), ptr(ws.x), self.nets.ldx, 1, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
             ptr(ws.status), st))
         self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
-            C.byref(self.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.tile_species), ptr(ws.row_atom),
+            C.byref(self.nets.model), ptr(ws.x), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom),
             ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
             int(want_grad), st))
         if want_grad:
             ws.grad.zero_()
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig), n, lo, hi,
-                ptr(ws.row_of), ptr(ws.x), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
+                ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
                 ptr(ws.grad), ptr(ws.status), st))
         self._timed("reduce_energies", lambda: L.ani_b200_reduce_energies(
             C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),

@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import Grid, check, ptr
-from .engine import PackedNetworks, TILE
+from .engine import PackedNetworks, TILE, tile_a_operand
 
 PERIODIC_TABLE = ("Dummy H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga "
                   "Ge As Se Br Kr Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe").split()
@@ -95,19 +95,21 @@ class _MLPFunction(torch.autograd.Function):
         L = _lib.lib()
         check(L.ani_b200_species_layout(ptr(spos), ptr(grid), n, 0, n, S, rows_cap, ptr(row_of), ptr(row_atom),
                                         ptr(tile_species), ptr(layout_info), ptr(scratch), st), "species_layout")
-        x = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)
+        xp = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)
         real = (sp_sorted >= 0)
         rows = torch.where(real, row_of, torch.zeros_like(row_of)).long()
         src = aevs.detach().reshape(n, D).to(torch.float32).index_select(0, order)
         src = src * real.view(-1, 1)
         # padding atoms all map to row 0 with zero contribution -> index_add keeps row 0 intact
-        x[:, :D].index_add_(0, rows, src)
+        xp[:, :D].index_add_(0, rows, src)
+        x_tiled = tile_a_operand(xp)                    # the GEMM consumes the hi/lo-split tiled form
+        x = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)   # dE/dAEV comes back as plain rows
         ld = nets.ld
-        act1 = torch.empty(rows_cap, ld[0], dtype=torch.float32, device=dev)
-        act2 = torch.empty(rows_cap, ld[1], dtype=torch.float32, device=dev)
-        act3 = torch.empty(rows_cap, ld[2], dtype=torch.float32, device=dev)
+        act1 = torch.empty(rows_cap, 2 * ld[0], dtype=torch.float32, device=dev)
+        act2 = torch.empty(rows_cap, 2 * ld[1], dtype=torch.float32, device=dev)
+        act3 = torch.empty(rows_cap, 2 * ld[2], dtype=torch.float32, device=dev)
         e_member = torch.zeros(M, rows_cap, dtype=torch.float32, device=dev)
-        check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x), rows_cap, ptr(tile_species),
+        check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x_tiled), ptr(x), rows_cap,
                                               ptr(row_atom), ptr(layout_info), None, ptr(act1), ptr(act2), ptr(act3),
                                               ptr(e_member), int(want_grad), st), "mlp_forward_backward")
         em_sorted = e_member[:, rows] * real.view(1, -1)          # (M, n) in `order` order
