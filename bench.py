@@ -101,6 +101,7 @@ def cpu_reference_step(orc, model, idx, coords, cell, pbc):
 
 def run_cpu_baseline(idx, coords, cell, pbc, steps: int, warmup: int):
     """The reference algorithm's CPU port (oracle/ani_oracle.py, float32, all host threads)."""
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1: undo that for the CPU arm
     orc = load_oracle()
     model = orc.ani2x_model(seed=1234, members=8, neighborlist="cell_list")
     for _ in range(warmup):
@@ -155,6 +156,8 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     import torch.distributed as dist
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
