@@ -98,11 +98,14 @@ const char* ani_b200_last_cuda_error(void);
 /*      sbin            i32[n]           bucket of each sorted atom                         */
 /*      orig_to_sorted  i32[n]           inverse of sorted_orig                             */
 /*    Scratch: scratch_i32[3*n + max_bins + 2].                                             */
+/*      bucket_ranges   f32[(max_bins-1)*27*8] or NULL: for every bucket the 27 neighbouring  */
+/*                      buckets as {first atom, end atom, image code, -} + image shift vector   */
+/*                      (mode 0 only; lets the AEV kernel skip the index / shift arithmetic)     */
 int ani_b200_build_cells(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
                          const float* cell, int pbc, int mode, float cutoff, int max_bins,
                          ani_grid* grid, int32_t* bin_start, int32_t* sorted_orig,
-                         int32_t* orig_to_sorted, float* spos, int32_t* sbin, int32_t* scratch_i32,
-                         int32_t* status, void* stream);
+                         int32_t* orig_to_sorted, float* spos, int32_t* sbin, float* bucket_ranges,
+                         int32_t* scratch_i32, int32_t* status, void* stream);
 
 /* 2. Species-grouped row layout for the MLP: atoms lo..hi-1 (bucket-sorted positions,     */
 /*    clipped to the real atoms) get rows grouped by species, every species block padded    */
@@ -121,7 +124,9 @@ int ani_b200_species_layout(const float* spos, const ani_grid* grid, int n, int 
 /* 2b. Active 32-column blocks of the AEV matrix: blocks[0] = count, blocks[1..] = ascending */
 /*    block ids whose columns belong to an element / element pair present among the real      */
 /*    atoms.  All other AEV columns are identically zero for every atom (and their gradient   */
-/*    is never consumed), so the MLP may skip them.  blocks i32[ldx/32 + 1]; scratch i32[1].   */
+/*    is never consumed), so the MLP may skip them.  blocks i32[ldx/32 + 3]: the last two words */
+/*    hold the element-presence bit mask and a "mask changed since the previous call" flag      */
+/*    (together: ani_b200_aev_forward's species_mask); scratch i32[1].                           */
 int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, int num_species,
                                int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* blocks,
                                int32_t* scratch_i32, void* stream);
@@ -134,9 +139,14 @@ int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, i
 /*                 (see below; 2*rows_cap*ldx floats, rows_cap % 128 == 0, ldx % 16 == 0)      */
 /*      nbr_cnt    i32[n]; nbr_list i32[n*nbr_cap]: neighbours within Rcr of every processed  */
 /*                 atom as (sorted index | image code << 26); kept for the backward pass      */
+/*      bucket_ranges  output of ani_b200_build_cells or NULL (ranges are then derived on the   */
+/*                 fly); species_mask: {bit per element present in the system, changed flag} or   */
+/*                 NULL: angular blocks of absent element pairs are not rewritten while the       */
+/*                 composition is unchanged (they hold zeros from the first call)                 */
 int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
-                         const int32_t* bin_start, const float* spos, const int32_t* sbin, int n,
-                         int lo, int hi, const int32_t* row_of, float* aev, int ldx, int layout,
+                         const int32_t* bin_start, const float* spos, const int32_t* sbin,
+                         const float* bucket_ranges, const int32_t* species_mask, int n, int lo,
+                         int hi, const int32_t* row_of, float* aev, int ldx, int layout,
                          int32_t* nbr_cnt, int32_t* nbr_list, int nbr_cap, int32_t* status,
                          void* stream);
 

@@ -67,9 +67,9 @@ _PROTOTYPES = {
     "ani_b200_abi_version": (C.c_int, []),
     "ani_b200_error_string": (C.c_char_p, [_I]),
     "ani_b200_last_cuda_error": (C.c_char_p, []),
-    "ani_b200_build_cells": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ani_b200_build_cells": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ani_b200_species_layout": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
+    "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
     "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "ani_b200_half_neighbor_fill": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),

@@ -105,7 +105,7 @@ class _AEVFunction(torch.autograd.Function):
         params = computer._params()
         # rows of the output are the flat input indices: row_of == sorted_orig
         check(_lib.lib().ani_b200_aev_forward(C.byref(params), ptr(g.grid), ptr(g.bin_start), ptr(g.spos),
-                                              ptr(g.sbin), n, 0, n, ptr(g.sorted_orig), ptr(out),
+                                              ptr(g.sbin), None, None, n, 0, n, ptr(g.sorted_orig), ptr(out),
                                               consts.out_dim, 0, ptr(nbr_cnt), ptr(nbr_list), cap, ptr(g.status),
                                               g.stream), "aev_forward")
         ctx.g, ctx.nbr_cnt, ctx.nbr_list, ctx.computer = g, nbr_cnt, nbr_list, computer

@@ -197,7 +197,8 @@ template <int NA, int NZ>
 __global__ void __launch_bounds__(AEV_WARPS * 32)
     k_aev_forward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                   const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
-                  const int32_t* __restrict__ sbin, int lo, int hi, const int32_t* __restrict__ row_of,
+                  const int32_t* __restrict__ sbin, const float4* __restrict__ ranges,
+                  const int32_t* __restrict__ species_mask, int lo, int hi, const int32_t* __restrict__ row_of,
                   float* __restrict__ aev, int ldx, int layout, int32_t* __restrict__ nbr_cnt,
                   int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
@@ -232,44 +233,55 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   int cnt = 0;
   {
     const int b = sbin[i];
-    int ix = 0, iy = 0, iz = 0, span = 0;
-    if (g.mode == 0) {
-      iz = b % g.dims[2];
-      iy = (b / g.dims[2]) % g.dims[1];
-      ix = b / (g.dims[2] * g.dims[1]);
-      span = 1;
-    }
-    for (int ox = -span; ox <= span; ++ox)
-      for (int oy = -span; oy <= span; ++oy)
-        for (int oz = -span; oz <= span; ++oz) {
-          NeighbourRange r;
-          if (g.mode == 0) {
-            if (!neighbour_bucket(g, bin_start, ix, iy, iz, ox, oy, oz, r)) continue;
-          } else {
-            r.lo = bin_start[b];
-            r.hi = bin_start[b + 1];
-            r.code = 13;
-          }
-          const float3 sh = (r.code == 13) ? make_float3(0.f, 0.f, 0.f) : image_shift(g, r.code);
-          for (int base = r.lo; base < r.hi; base += 32) {
-            const int c = base + lane;
-            const bool valid = c < r.hi;
-            const float4 p = valid ? spos[c] : pi;
-            const float dx = (p.x + sh.x) - pi.x, dy = (p.y + sh.y) - pi.y, dz = (p.z + sh.z) - pi.z;
-            const float r2 = dx * dx + dy * dy + dz * dz;
-            const bool keep = valid && r2 <= rcr2 && !(c == i && r.code == 13);
-            const unsigned m = __ballot_sync(ANI_FULL_MASK, keep);
-            if (keep) {
-              const int pos = cnt + __popc(m & lt);
-              if (pos < cap) {
-                s.nd[pos] = make_float4(dx, dy, dz, sqrtf(r2));
-                s.nj[pos] = c | (r.code << ANI_IMG_SHIFT);
-                s.nsp[pos] = (unsigned char)__float_as_int(p.w);
-              }
-            }
-            cnt += __popc(m);
+    // one candidate range: compact the atoms within Rcr into shared memory
+    auto scan_range = [&](int rlo, int rhi, int code, float shx, float shy, float shz) {
+      for (int base = rlo; base < rhi; base += 32) {
+        const int c = base + lane;
+        const bool valid = c < rhi;
+        const float4 p = valid ? spos[c] : pi;
+        const float dx = (p.x + shx) - pi.x, dy = (p.y + shy) - pi.y, dz = (p.z + shz) - pi.z;
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        const bool keep = valid && r2 <= rcr2 && !(c == i && code == 13);
+        const unsigned m = __ballot_sync(ANI_FULL_MASK, keep);
+        if (keep) {
+          const int pos = cnt + __popc(m & lt);
+          if (pos < cap) {
+            s.nd[pos] = make_float4(dx, dy, dz, sqrtf(r2));
+            s.nj[pos] = c | (code << ANI_IMG_SHIFT);
+            s.nsp[pos] = (unsigned char)__float_as_int(p.w);
           }
         }
+        cnt += __popc(m);
+      }
+    };
+    if (g.mode != 0) {
+      scan_range(bin_start[b], bin_start[b + 1], 13, 0.f, 0.f, 0.f);
+    } else if (ranges) {
+      // precomputed table: lane o holds the record of neighbouring bucket o
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+      if (lane < 27) {
+        r0 = ranges[2 * ((size_t)b * 27 + lane)];
+        r1 = ranges[2 * ((size_t)b * 27 + lane) + 1];
+      }
+      for (int o = 0; o < 27; ++o) {
+        const int rlo = __float_as_int(__shfl_sync(ANI_FULL_MASK, r0.x, o));
+        const int rhi = __float_as_int(__shfl_sync(ANI_FULL_MASK, r0.y, o));
+        if (rhi <= rlo) continue;
+        const int code = __float_as_int(__shfl_sync(ANI_FULL_MASK, r0.z, o));
+        scan_range(rlo, rhi, code, __shfl_sync(ANI_FULL_MASK, r1.x, o), __shfl_sync(ANI_FULL_MASK, r1.y, o),
+                   __shfl_sync(ANI_FULL_MASK, r1.z, o));
+      }
+    } else {
+      const int iz = b % g.dims[2], iy = (b / g.dims[2]) % g.dims[1], ix = b / (g.dims[2] * g.dims[1]);
+      for (int ox = -1; ox <= 1; ++ox)
+        for (int oy = -1; oy <= 1; ++oy)
+          for (int oz = -1; oz <= 1; ++oz) {
+            NeighbourRange r;
+            if (!neighbour_bucket(g, bin_start, ix, iy, iz, ox, oy, oz, r)) continue;
+            const float3 sh = (r.code == 13) ? make_float3(0.f, 0.f, 0.f) : image_shift(g, r.code);
+            scan_range(r.lo, r.hi, r.code, sh.x, sh.y, sh.z);
+          }
+    }
   }
   if (cnt > cap) {
     if (lane == 0) atomicOr(status, ANI_STATUS_NBR_OVERFLOW);
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     for (int n = h; n < cnt; n += halves) {
       const float R = s.nd[n].w;
       const float d = R - shf;
-      const float v = 0.25f * expf(-P.eta_r * d * d) * s.nfc[n];
+      const float v = 0.25f * fast_exp(-P.eta_r * d * d) * s.nfc[n];
       if (m < nR) s.rad[h * RL + s.nsp[n] * nR + m] += v;
     }
     __syncwarp();
@@ -312,10 +324,18 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     cz[z] = P.cos_z[z];
     sz[z] = P.sin_z[z];
   }
+  // element pairs that do not occur anywhere in the system are never read by the MLP: skip them
+  // (species_mask[1] != 0: the composition changed since the last call -> zero-fill them once)
+  const unsigned present = (species_mask && !species_mask[1]) ? (unsigned)species_mask[0] : 0xffffffffu;
   int p = 0;
   for (int s1 = 0; s1 < S; ++s1) {
+    if (!((present >> s1) & 1u)) {
+      p += S - s1;
+      continue;
+    }
     const int a0 = s.seg[s1], na = s.seg[s1 + 1] - a0;
     for (int s2 = s1; s2 < S; ++s2, ++p) {
+      if (!((present >> s2) & 1u)) continue;
       const int b0 = s.seg[s2], nb = s.seg[s2 + 1] - b0;
       const int count = (s1 == s2) ? na * (na - 1) / 2 : na * nb;
       float out = 0.f;
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
             const float d = rbar - shfA[a];
-            const float f2 = expf(-P.eta_a * d * d) * w2;
+            const float f2 = fast_exp(-P.eta_a * d * d) * w2;
 #pragma unroll
             for (int z = 0; z < NZ; ++z) acc[a * NZ + z] += f1[z] * f2;
           }
@@ -401,9 +421,15 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     float3 sh = make_float3(0.f, 0.f, 0.f);
     if (code != 13) sh = image_shift(g, code);
     const float dx = (p.x + sh.x) - pi.x, dy = (p.y + sh.y) - pi.y, dz = (p.z + sh.z) - pi.z;
-    s.nd[n] = make_float4(dx, dy, dz, sqrtf(dx * dx + dy * dy + dz * dz));
+    const float R = sqrtf(dx * dx + dy * dy + dz * dz);
+    s.nd[n] = make_float4(dx, dy, dz, R);
     s.nj[n] = j;
     s.nsp[n] = (unsigned char)__float_as_int(p.w);
+    // radial cutoff and its derivative once per neighbour (not once per (neighbour, shift) lane)
+    float fc, dfc;
+    cutoff_value_grad(R, P.rcr, P.cutoff_kind, fc, dfc);
+    s.nfc[n] = fc;
+    s.fgrad[3 * n] = dfc;  // parked here until the radial loop overwrites fgrad[3n..3n+2]
   }
   __syncwarp();
 
@@ -420,10 +446,9 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
       float4 d = make_float4(0.f, 0.f, 0.f, 1.f);
       if (valid) {
         d = s.nd[n];
-        float fc, dfc;
-        cutoff_value_grad(d.w, P.rcr, P.cutoff_kind, fc, dfc);
+        const float fc = s.nfc[n], dfc = s.fgrad[3 * n];
         const float x = d.w - shf;
-        const float G = 0.25f * expf(-P.eta_r * x * x);
+        const float G = 0.25f * fast_exp(-P.eta_r * x * x);
         if (m < nR) contrib = g_rad[s.nsp[n] * nR + m] * G * (-2.0f * P.eta_r * x * fc + dfc);
       }
       for (int o = lpn / 2; o > 0; o >>= 1) contrib += __shfl_xor_sync(ANI_FULL_MASK, contrib, o);
@@ -479,7 +504,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
             const float d = rbar - shfA[a];
-            f2[a] = expf(-P.eta_a * d * d);
+            f2[a] = fast_exp(-P.eta_a * d * d);
             f2p[a] = -2.0f * P.eta_a * d * f2[a];
           }
           float S0 = 0.f, S1 = 0.f, S2 = 0.f;
@@ -673,9 +698,10 @@ static int check_params(const ani_aev_params* p) {
 using namespace ani;
 
 extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
-                                    const float* spos, const int32_t* sbin, int n, int lo, int hi,
-                                    const int32_t* row_of, float* aev, int ldx, int layout, int32_t* nbr_cnt,
-                                    int32_t* nbr_list, int nbr_cap, int32_t* status, void* stream) {
+                                    const float* spos, const int32_t* sbin, const float* bucket_ranges,
+                                    const int32_t* species_mask, int n, int lo, int hi, const int32_t* row_of,
+                                    float* aev, int ldx, int layout, int32_t* nbr_cnt, int32_t* nbr_list,
+                                    int nbr_cap, int32_t* status, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!grid || !bin_start || !spos || !sbin || !row_of || !aev || !nbr_cnt || !nbr_list || !status)
@@ -694,15 +720,18 @@ extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid
   const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
   cudaStream_t st = (cudaStream_t)stream;
   const float4* sp4 = reinterpret_cast<const float4*>(spos);
+  const float4* rng4 = reinterpret_cast<const float4*>(bucket_ranges);
   if (params->n_shf_a == 8) {
     auto k = k_aev_forward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx, layout,
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
+                                            aev, ldx, layout,
                                             nbr_cnt, nbr_list, nbr_cap, status, wb);
   } else {
     auto k = k_aev_forward<4, 8>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, lo, hi, row_of, aev, ldx, layout,
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
+                                            aev, ldx, layout,
                                             nbr_cnt, nbr_list, nbr_cap, status, wb);
   }
   ANI_CUDA_CHECK_LAUNCH();

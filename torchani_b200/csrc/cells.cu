@@ -243,6 +243,43 @@ __global__ void k_bin_finalize(const float* __restrict__ coords, const int32_t* 
   spos[i] = make_float4(p.x, p.y, p.z, __int_as_float(sp));
 }
 
+// Per-bucket table of the 27 neighbouring buckets: {first atom, end atom, image code, exists} and
+// the image shift vector.  The AEV kernel then reads 27 records instead of redoing the index
+// wrapping and shift arithmetic for every central atom.
+__global__ void k_bucket_ranges(const ani_grid* __restrict__ grid, const int32_t* __restrict__ bin_start,
+                                float4* __restrict__ ranges) {
+  const ani_grid g = *grid;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = idx / 27, o = idx % 27;
+  if (b >= g.nbins || g.mode != 0) return;
+  const int iz = b % g.dims[2], iy = (b / g.dims[2]) % g.dims[1], ix = b / (g.dims[2] * g.dims[1]);
+  int j[3] = {ix + o / 9 - 1, iy + (o / 3) % 3 - 1, iz + o % 3 - 1};
+  int w[3];
+  for (int d = 0; d < 3; ++d) {
+    w[d] = 0;
+    if (j[d] < 0) {
+      w[d] = -1;
+      j[d] += g.dims[d];
+    } else if (j[d] >= g.dims[d]) {
+      w[d] = 1;
+      j[d] -= g.dims[d];
+    }
+  }
+  const bool exists = g.pbc || !(w[0] | w[1] | w[2]);
+  int lo = 0, hi = 0;
+  const int code = (w[0] + 1) * 9 + (w[1] + 1) * 3 + (w[2] + 1);
+  if (exists) {
+    const int nb = (j[0] * g.dims[1] + j[1]) * g.dims[2] + j[2];
+    lo = bin_start[nb];
+    hi = bin_start[nb + 1];
+  }
+  const float wx = (float)w[0], wy = (float)w[1], wz = (float)w[2];
+  ranges[2 * (size_t)idx] = make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), 0.f);
+  ranges[2 * (size_t)idx + 1] = make_float4(wx * g.cell[0] + wy * g.cell[3] + wz * g.cell[6],
+                                            wx * g.cell[1] + wy * g.cell[4] + wz * g.cell[7],
+                                            wx * g.cell[2] + wy * g.cell[5] + wz * g.cell[8], 0.f);
+}
+
 // ---------------------------------------------------------------------------------------
 // species-grouped row layout (three kernels, deterministic):
 //   1. per-chunk species histogram of the owned sorted atoms
@@ -383,7 +420,13 @@ __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int 
       ++count;
     }
   }
-  if (lane == 0) blocks[0] = count;
+  if (lane == 0) {
+    blocks[0] = count;
+    // element-presence bits + "changed since the previous call" flag, read by the AEV kernel: dead
+    // element pairs are skipped, but zero-filled once whenever the composition changes
+    blocks[ldx / 32 + 2] = (blocks[ldx / 32 + 1] != (int)mask);
+    blocks[ldx / 32 + 1] = (int)mask;
+  }
 }
 
 }  // namespace ani
@@ -407,8 +450,8 @@ extern "C" int ani_b200_active_aev_blocks(const float* spos, const ani_grid* gri
 extern "C" int ani_b200_build_cells(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
                                     const float* cell, int pbc, int mode, float cutoff, int max_bins,
                                     ani_grid* grid, int32_t* bin_start, int32_t* sorted_orig,
-                                    int32_t* orig_to_sorted, float* spos, int32_t* sbin, int32_t* scratch_i32,
-                                    int32_t* status, void* stream) {
+                                    int32_t* orig_to_sorted, float* spos, int32_t* sbin, float* bucket_ranges,
+                                    int32_t* scratch_i32, int32_t* status, void* stream) {
   if (!coords || !species || !grid || !bin_start || !sorted_orig || !orig_to_sorted || !spos || !sbin ||
       !scratch_i32 || !status)
     return ANI_ERR_BAD_ARG;
@@ -434,6 +477,11 @@ extern "C" int ani_b200_build_cells(const float* coords, const int32_t* species,
   k_bin_scatter<<<nb, 256, 0, st>>>(n, bin_of, slot, bin_start, tmp_list);
   k_bin_finalize<<<nb, 256, 0, st>>>(coords, species, n, grid, bin_of, bin_start, tmp_list, sorted_orig,
                                      orig_to_sorted, reinterpret_cast<float4*>(spos), sbin);
+  if (bucket_ranges && mode == 0) {
+    // nbins is only known on the device: cover the caller's bucket capacity, surplus threads exit
+    const long long threads = (long long)(max_bins - 1) * 27;
+    k_bucket_ranges<<<(int)((threads + 255) / 256), 256, 0, st>>>(grid, bin_start, reinterpret_cast<float4*>(bucket_ranges));
+  }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

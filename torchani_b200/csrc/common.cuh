@@ -31,6 +31,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// exp(x) for x <= 0 through ex2.approx (relative error ~2^-22 plus |x| * 2^-24 from the scaling):
+// used for the Gaussian factors of the AEV, whose relevant range is x in [-16, 0]
+__device__ __forceinline__ float fast_exp(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+  return e;
+}
+
 // index of the unordered species pair (a, b) in the row-major upper triangle of an SxS
 // matrix (aev/_computer.py:184-191 == csrc/aev.cu:23-29)
 __device__ __forceinline__ int pair_index(int a, int b, int S) {

@@ -264,7 +264,9 @@ class Workspace:
         self.row_atom = torch.zeros(self.rows_cap, **i32)
         self.tile_species = torch.zeros(self.rows_cap // TILE, **i32)
         self.layout_info = torch.zeros(16, **i32)
-        self.aev_blocks = torch.zeros(ldx // 32 + 1, **i32)
+        self.aev_blocks = torch.zeros(ldx // 32 + 3, **i32)   # [count, ids..., element mask, changed flag]
+        self.n_blocks = ldx // 32
+        self.bucket_ranges = torch.zeros((self.max_bins - 1) * 27 * 8, **f32) if n_conf == 1 else None
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
@@ -415,7 +417,8 @@ class Engine:
         self._timed("build_cells", lambda: L.ani_b200_build_cells(
             ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
             self.consts.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
-            ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.scratch), ptr(ws.status), st))
+            ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges), ptr(ws.scratch),
+            ptr(ws.status), st))
         self._timed("species_layout", lambda: L.ani_b200_species_layout(
             ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species, ws.rows_cap, ptr(ws.row_of),
             ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info), ptr(ws.scratch), st))
@@ -424,7 +427,8 @@ class Engine:
             ptr(ws.spos), ptr(ws.grid), n, c.num_species, len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim,
             self.nets.ldx, ptr(ws.aev_blocks), ptr(ws.scratch), st))
         self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
-            C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin), n, lo, hi,
+            C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin),
+            ptr(ws.bucket_ranges), ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
             ptr(ws.row_of), ptr(ws.x), self.nets.ldx, 1, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
             ptr(ws.status), st))
         self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(

@@ -88,7 +88,7 @@ class BucketGrid:
         check(_lib.lib().ani_b200_build_cells(
             ptr(coords_f), ptr(self.species_i32), n_conf, n_per_conf, ptr(cell_f), int(pbc),
             0 if n_conf == 1 else 1, float(cutoff), self.max_bins, ptr(self.grid), ptr(self.bin_start),
-            ptr(self.sorted_orig), ptr(self.orig_to_sorted), ptr(self.spos), ptr(self.sbin), ptr(scratch),
+            ptr(self.sorted_orig), ptr(self.orig_to_sorted), ptr(self.spos), ptr(self.sbin), None, ptr(scratch),
             ptr(self.status), self.stream), "build_cells")
 
     def raise_on_status(self) -> None:
