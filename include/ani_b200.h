@@ -17,6 +17,7 @@
  *                               csrc/cuaev.cpp:189-246 (cuaev::run / run_with_half_nbrlist),
  *                               csrc/aev.cu:323-472,768-834 (K8/K9), :975-1039 (K4)
  *   ani_b200_aev_backward       csrc/cuaev.cpp:134-163, csrc/aev.cu:474-766,837-967 (K10/K11)
+ *   ani_b200_pairs_to_rows, ani_b200_aev_*_rows   aev/_computer.py:251-272, csrc/aev.cu:1128-1208 (K6)
  *   ani_b200_half_neighbor_*    neighbors.py:366-415 (cell_list), :187-212 (all_pairs) -> Neighbors
  *   ani_b200_mlp_forward_backward  nn/_containers.py:377-421,608-651, nn/_core.py:146-167,
  *                               nn/_infer.py:61-216 (BmmEnsemble), csrc/mnp.cpp:63-236 (mnp::run)
@@ -157,6 +158,28 @@ int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, co
                           const float* grad_aev, int ldx, const int32_t* nbr_cnt,
                           const int32_t* nbr_list, int nbr_cap, float* grad_coords,
                           int32_t* status, void* stream);
+
+/* 4b. The same AEV kernels fed by an externally supplied HALF pair list (the reference's    */
+/*    Neighbors tuple; AEVComputer.compute_from_neighbors, aev/_computer.py:251-272 ->          */
+/*    cuaev::run_with_half_nbrlist, csrc/aev.cu:1128-1208,1779-1866).  ani_b200_pairs_to_rows     */
+/*    expands the list into per-atom rows (both directions): row_start i32[n+1], row_j i32[2P],  */
+/*    row_d f32[2P][4] = (r_j - r_i, R); scratch i32[2n].  diff_vectors follow the reference:     */
+/*    x[idx0] - x[idx1] + shift.  The *_rows entry points then take any `grid` whose n_real == n  */
+/*    and an `spos` that only needs the species in .w (atoms in input order, padding = -1).       */
+/*    Gradients go to the coordinates only, as in csrc/cuaev.cpp:158-163.                          */
+int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, const float* diff_vectors,
+                           int64_t num_pairs, int n, int nbr_cap, int32_t* row_start,
+                           int32_t* row_j, float* row_d, int32_t* scratch_i32, int32_t* status,
+                           void* stream);
+int ani_b200_aev_forward_rows(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                              const int32_t* row_start, const int32_t* row_j, const float* row_d,
+                              int n, const int32_t* row_of, float* aev, int ldx, int layout,
+                              int nbr_cap, int32_t* status, void* stream);
+int ani_b200_aev_backward_rows(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                               const int32_t* sorted_orig, const int32_t* row_start,
+                               const int32_t* row_j, const float* row_d, int n, const int32_t* row_of,
+                               const float* grad_aev, int ldx, int nbr_cap, float* grad_coords,
+                               int32_t* status, void* stream);
 
 /* 5. Reference-format half neighbour list (neighbors.py:13-18) from the bucket grid.       */
 /*    Two calls: count (fills pair_start i32[n+1], exclusive scan, total in pair_start[n]),  */

@@ -172,3 +172,32 @@ def test_host_calculator_matches_oracle_and_repeats():
     assert abs(e2 - float(ref["energy"][0])) < 1e-5
     assert_close("forces moved", f2, ref["forces"][0].numpy(), 0.0, F_ATOL)
     calc.check_status()
+
+
+@pytest.mark.parametrize("name", ["water30_pbc_ani2x", "randbatch_ani2x"])
+def test_compute_from_neighbors_split_api(name):
+    """The reference's split call: neighbors = nl(cutoff, idxs, coords, cell, pbc);
+    aevs = aevc.compute_from_neighbors(idxs, coords, neighbors)  (aev/_computer.py:251-272)."""
+    from torchani_b200.aev import AEVComputer
+    from torchani_b200.neighbors import AllPairs, CellList, discard_outside_cutoff
+    rec = load_golden(name)
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    aevc = AEVComputer.like_2x().to(DEV)
+    nl = CellList() if species.shape[0] == 1 else AllPairs()
+    c = coords.to(DEV).requires_grad_(True)
+    cell_d = None if cell is None else cell.to(DEV)
+    pbc_d = None if pbc is None else pbc.to(DEV)
+    nb = nl(5.1, species.to(DEV), c, cell_d, pbc_d)
+    aev = aevc.compute_from_neighbors(species.to(DEV), c, nb)
+    assert_close("aev", aev.detach().cpu().numpy(), rec["aev"], AEV_RTOL, AEV_ATOL)
+    fused = aevc(species.to(DEV), c.detach(), cell_d, pbc_d)
+    assert float((fused - aev.detach()).abs().max()) < 2e-5
+    w = torch.randn(aev.shape, generator=torch.Generator().manual_seed(5)).to(DEV) * 1e-2
+    (g1,) = torch.autograd.grad((aev * w).sum(), c)
+    c2 = coords.to(DEV).requires_grad_(True)
+    (g2,) = torch.autograd.grad((aevc(species.to(DEV), c2, cell_d, pbc_d) * w).sum(), c2)
+    assert float((g1 - g2).abs().max()) < 2e-5
+    # a filtered list (here: a larger cutoff list narrowed back) is honoured as given
+    nb_big = nl(6.0, species.to(DEV), coords.to(DEV), cell_d, pbc_d)
+    aev2 = aevc.compute_from_neighbors(species.to(DEV), coords.to(DEV), discard_outside_cutoff(nb_big, 5.1))
+    assert float((aev2 - aev.detach()).abs().max()) < 2e-5

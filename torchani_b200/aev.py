@@ -127,6 +127,64 @@ class _AEVFunction(torch.autograd.Function):
         return grad.view(g.n_conf, g.n_per_conf, 3), None, None, None, None
 
 
+class _AEVFromNeighbors(torch.autograd.Function):
+    """AEVs from a caller-supplied half pair list (``Neighbors``), gradient to coords only."""
+
+    @staticmethod
+    def forward(ctx, coords: Tensor, species: Tensor, indices: Tensor, diff_vectors: Tensor,
+                computer: "AEVComputer") -> Tensor:
+        consts = computer.constants
+        dev = coords.device
+        n_conf, n_per_conf = species.shape
+        n = n_conf * n_per_conf
+        num_pairs = int(indices.shape[1])
+        i32 = dict(dtype=torch.int32, device=dev)
+        spos = torch.zeros(n, 4, dtype=torch.float32, device=dev)
+        spos[:, 3] = species.reshape(-1).to(torch.int32).view(torch.float32)   # only the species is read
+        grid = torch.zeros(C.sizeof(_lib.Grid) // 4, **i32)
+        grid[_lib.Grid.n_real.offset // 4] = n
+        ident = torch.arange(n, **i32)
+        row_start = torch.zeros(n + 1, **i32)
+        row_j = torch.zeros(max(2 * num_pairs, 1), **i32)
+        row_d = torch.zeros(max(2 * num_pairs, 1), 4, dtype=torch.float32, device=dev)
+        scratch = torch.zeros(2 * n, **i32)
+        status = torch.zeros(1, **i32)
+        idx = indices.to(torch.int64).contiguous()
+        dv = diff_vectors.detach().to(torch.float32).contiguous()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        L = _lib.lib()
+        params = computer._params()
+        cap = computer.nbr_cap
+        check(L.ani_b200_pairs_to_rows(idx[0].data_ptr(), idx[1].data_ptr(), ptr(dv), num_pairs, n, cap,
+                                       ptr(row_start), ptr(row_j), ptr(row_d), ptr(scratch), ptr(status), st),
+              "pairs_to_rows")
+        out = torch.zeros(n, consts.out_dim, dtype=torch.float32, device=dev)
+        check(L.ani_b200_aev_forward_rows(C.byref(params), ptr(grid), ptr(spos), ptr(row_start), ptr(row_j),
+                                          ptr(row_d), n, ptr(ident), ptr(out), consts.out_dim, 0, cap, ptr(status),
+                                          st), "aev_forward_rows")
+        ctx.saved = (grid, spos, ident, row_start, row_j, row_d, status)
+        ctx.computer, ctx.shape = computer, (n_conf, n_per_conf)
+        computer._last_status = status
+        return out.view(n_conf, n_per_conf, consts.out_dim)
+
+    @staticmethod
+    def backward(ctx, grad_aev: Tensor):
+        grid, spos, ident, row_start, row_j, row_d, status = ctx.saved
+        computer = ctx.computer
+        consts = computer.constants
+        n_conf, n_per_conf = ctx.shape
+        n = n_conf * n_per_conf
+        g = grad_aev.reshape(n, consts.out_dim).to(torch.float32).contiguous()
+        grad = torch.zeros(n, 3, dtype=torch.float32, device=g.device)
+        st = torch.cuda.current_stream(g.device).cuda_stream
+        params = computer._params()
+        check(_lib.lib().ani_b200_aev_backward_rows(C.byref(params), ptr(grid), ptr(spos), ptr(ident), ptr(row_start),
+                                                    ptr(row_j), ptr(row_d), n, ptr(ident), ptr(g), consts.out_dim,
+                                                    computer.nbr_cap, ptr(grad), ptr(status), st),
+              "aev_backward_rows")
+        return grad.view(n_conf, n_per_conf, 3), None, None, None, None
+
+
 class AEVComputer(torch.nn.Module):
     r"""Computes atomic environment vectors on a B200 (interface of aev/_computer.py:42-272).
 
@@ -167,6 +225,7 @@ class AEVComputer(torch.nn.Module):
         self._struct = None
         self._consts: tp.Optional[AEVConstants] = None
         self._last_grid: tp.Optional[BucketGrid] = None
+        self._last_status: tp.Optional[Tensor] = None
         self.constants.to_struct()  # validates the configuration early
 
     # -- strategy strings (aev/_computer.py:120-149) ---------------------------------------
@@ -226,10 +285,21 @@ class AEVComputer(torch.nn.Module):
         return aev
 
     def compute_from_neighbors(self, elem_idxs: Tensor, coords: Tensor, neighbors: Neighbors) -> Tensor:
-        raise NotImplementedError(
-            "AEVs from an externally filtered pair list are not implemented on the B200 path yet; "
-            "call forward(elem_idxs, coords, cell, pbc) (fused neighbour search) instead"
-        )
+        r"""Compute the AEVs from the result of a neighborlist calculation (aev/_computer.py:251-272).
+
+        Like the reference's cuAEV half-neighbour-list path (csrc/cuaev.cpp:141-163) the pairs and
+        ``diff_vectors`` are taken as given (pairs beyond the radial cutoff must already be gone) and
+        the gradient goes to ``coords`` only."""
+        assert elem_idxs.dim() == 2 and coords.shape == (elem_idxs.shape[0], elem_idxs.shape[1], 3)
+        if coords.device.type != "cuda":
+            raise ValueError("torchani_b200 runs on CUDA tensors only (there is no CPU path)")
+        aev = _AEVFromNeighbors.apply(coords, elem_idxs, neighbors.indices, neighbors.diff_vectors, self)
+        code = int(self._last_status.item())
+        if code & _lib.STATUS_NBR_OVERFLOW:
+            raise RuntimeError(f"an atom has more than nbr_cap={self.nbr_cap} neighbours in the given list")
+        if code & _lib.STATUS_ANG_OVERFLOW:
+            raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within the angular cutoff")
+        return aev
 
     # -- constructors (aev/_computer.py:498-666) -------------------------------------------
     @classmethod

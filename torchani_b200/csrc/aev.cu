@@ -21,6 +21,14 @@ struct NeighbourRange {
   int lo, hi, code;
 };
 
+// Explicit per-atom neighbour rows (compute_from_neighbors path): atom i owns entries
+// start[i] .. start[i+1]-1, each with the neighbour's atom index and (dx, dy, dz, R) = r_j - r_i.
+struct ExplicitNbrs {
+  const int32_t* start;
+  const int32_t* j;
+  const float4* d;
+};
+
 // bucket range + image code for offset (ox, oy, oz) around bucket (ix, iy, iz); false if it
 // does not exist (non-periodic boundary)
 __device__ __forceinline__ bool neighbour_bucket(const ani_grid& g, const int32_t* __restrict__ bin_start,
@@ -198,7 +206,8 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     k_aev_forward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                   const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
                   const int32_t* __restrict__ sbin, const float4* __restrict__ ranges,
-                  const int32_t* __restrict__ species_mask, int lo, int hi, const int32_t* __restrict__ row_of,
+                  const int32_t* __restrict__ species_mask, const ExplicitNbrs ex, int lo, int hi,
+                  const int32_t* __restrict__ row_of,
                   float* __restrict__ aev, int ldx, int layout, int32_t* __restrict__ nbr_cnt,
                   int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
@@ -228,11 +237,12 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 
   // ---- 1. neighbours within Rcr -> shared memory
   const float4 pi = spos[i];
+  if (__float_as_int(pi.w) < 0) return;  // padding atom (only reachable with explicit neighbour rows)
   const float rcr2 = P.rcr * P.rcr;
   const unsigned lt = (1u << lane) - 1u;
   int cnt = 0;
   {
-    const int b = sbin[i];
+    const int b = ex.start ? 0 : sbin[i];
     // one candidate range: compact the atoms within Rcr into shared memory
     auto scan_range = [&](int rlo, int rhi, int code, float shx, float shy, float shz) {
       for (int base = rlo; base < rhi; base += 32) {
@@ -254,7 +264,17 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
         cnt += __popc(m);
       }
     };
-    if (g.mode != 0) {
+    if (ex.start) {
+      // neighbours handed in by the caller (already screened to Rcr): copy the row
+      const int e0 = ex.start[i];
+      cnt = ex.start[i + 1] - e0;
+      for (int n = lane; n < min(cnt, cap); n += 32) {
+        const int j = ex.j[e0 + n];
+        s.nd[n] = ex.d[e0 + n];
+        s.nj[n] = j | (13 << ANI_IMG_SHIFT);
+        s.nsp[n] = (unsigned char)__float_as_int(spos[j].w);
+      }
+    } else if (g.mode != 0) {
       scan_range(bin_start[b], bin_start[b + 1], 13, 0.f, 0.f, 0.f);
     } else if (ranges) {
       // precomputed table: lane o holds the record of neighbouring bucket o
@@ -288,9 +308,9 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     cnt = cap;
   }
   __syncwarp();
-  if (lane == 0) nbr_cnt[i] = cnt;
+  if (lane == 0 && nbr_cnt) nbr_cnt[i] = cnt;
   for (int n = lane; n < cnt; n += 32) {
-    nbr_list[(size_t)i * cap + n] = s.nj[n];
+    if (nbr_list) nbr_list[(size_t)i * cap + n] = s.nj[n];
     s.nfc[n] = cutoff_value(s.nd[n].w, P.rcr, P.cutoff_kind);
   }
   for (int t = lane; t < 2 * RL; t += 32) s.rad[t] = 0.f;
@@ -388,8 +408,8 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     k_aev_backward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                    const float4* __restrict__ spos, const int32_t* __restrict__ sorted_orig, int lo, int hi,
                    const int32_t* __restrict__ row_of, const float* __restrict__ gaev, int ldx,
-                   const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ nbr_list, int cap,
-                   float* __restrict__ grad_coords, int32_t* __restrict__ status, size_t warp_bytes) {
+                   const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ nbr_list, const ExplicitNbrs ex,
+                   int cap, float* __restrict__ grad_coords, int32_t* __restrict__ status, size_t warp_bytes) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -413,21 +433,31 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 
   // ---- 2. geometry of the stored neighbours
   const float4 pi = spos[i];
-  const int cnt = nbr_cnt[i];
+  if (__float_as_int(pi.w) < 0) return;  // padding atom (explicit neighbour rows only)
+  const int e0 = ex.start ? ex.start[i] : 0;
+  const int cnt = ex.start ? min(ex.start[i + 1] - e0, cap) : nbr_cnt[i];
   for (int n = lane; n < cnt; n += 32) {
-    const int word = nbr_list[(size_t)i * cap + n];
-    const int j = word & ANI_IDX_MASK, code = (unsigned)word >> ANI_IMG_SHIFT;
-    const float4 p = spos[j];
-    float3 sh = make_float3(0.f, 0.f, 0.f);
-    if (code != 13) sh = image_shift(g, code);
-    const float dx = (p.x + sh.x) - pi.x, dy = (p.y + sh.y) - pi.y, dz = (p.z + sh.z) - pi.z;
-    const float R = sqrtf(dx * dx + dy * dy + dz * dz);
-    s.nd[n] = make_float4(dx, dy, dz, R);
+    int j;
+    float4 dR;
+    if (ex.start) {
+      j = ex.j[e0 + n];
+      dR = ex.d[e0 + n];
+    } else {
+      const int word = nbr_list[(size_t)i * cap + n];
+      j = word & ANI_IDX_MASK;
+      const int code = (unsigned)word >> ANI_IMG_SHIFT;
+      const float4 p = spos[j];
+      float3 sh = make_float3(0.f, 0.f, 0.f);
+      if (code != 13) sh = image_shift(g, code);
+      const float dx = (p.x + sh.x) - pi.x, dy = (p.y + sh.y) - pi.y, dz = (p.z + sh.z) - pi.z;
+      dR = make_float4(dx, dy, dz, sqrtf(dx * dx + dy * dy + dz * dz));
+    }
+    s.nd[n] = dR;
     s.nj[n] = j;
-    s.nsp[n] = (unsigned char)__float_as_int(p.w);
+    s.nsp[n] = (unsigned char)__float_as_int(spos[j].w);
     // radial cutoff and its derivative once per neighbour (not once per (neighbour, shift) lane)
     float fc, dfc;
-    cutoff_value_grad(R, P.rcr, P.cutoff_kind, fc, dfc);
+    cutoff_value_grad(dR.w, P.rcr, P.cutoff_kind, fc, dfc);
     s.nfc[n] = fc;
     s.fgrad[3 * n] = dfc;  // parked here until the radial loop overwrites fgrad[3n..3n+2]
   }
@@ -693,19 +723,15 @@ static int check_params(const ani_aev_params* p) {
   return ANI_OK;
 }
 
-}  // namespace ani
-
-using namespace ani;
-
-extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
-                                    const float* spos, const int32_t* sbin, const float* bucket_ranges,
-                                    const int32_t* species_mask, int n, int lo, int hi, const int32_t* row_of,
-                                    float* aev, int ldx, int layout, int32_t* nbr_cnt, int32_t* nbr_list,
-                                    int nbr_cap, int32_t* status, void* stream) {
+// ---- launchers shared by the bucket-grid and the explicit-pair-list entry points -----------
+static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
+                              const float* spos, const int32_t* sbin, const float* bucket_ranges,
+                              const int32_t* species_mask, ExplicitNbrs ex, int n, int lo, int hi,
+                              const int32_t* row_of, float* aev, int ldx, int layout, int32_t* nbr_cnt,
+                              int32_t* nbr_list, int nbr_cap, int32_t* status, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
-  if (!grid || !bin_start || !spos || !sbin || !row_of || !aev || !nbr_cnt || !nbr_list || !status)
-    return ANI_ERR_BAD_ARG;
+  if (!grid || !spos || !row_of || !aev || !status) return ANI_ERR_BAD_ARG;
   if (lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
   if (nbr_cap < 32 || nbr_cap > 256 || nbr_cap % 32) return ANI_ERR_BAD_ARG;
   const int out_dim = params->num_species * params->n_shf_r +
@@ -724,29 +750,25 @@ extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid
   if (params->n_shf_a == 8) {
     auto k = k_aev_forward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
-                                            aev, ldx, layout,
-                                            nbr_cnt, nbr_list, nbr_cap, status, wb);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, ex, lo, hi, row_of,
+                                            aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
   } else {
     auto k = k_aev_forward<4, 8>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
-                                            aev, ldx, layout,
-                                            nbr_cnt, nbr_list, nbr_cap, status, wb);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, ex, lo, hi, row_of,
+                                            aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }
 
-extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
-                                     const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
-                                     const float* grad_aev, int ldx, const int32_t* nbr_cnt,
-                                     const int32_t* nbr_list, int nbr_cap, float* grad_coords, int32_t* status,
-                                     void* stream) {
+static int launch_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                               const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
+                               const float* grad_aev, int ldx, const int32_t* nbr_cnt, const int32_t* nbr_list,
+                               ExplicitNbrs ex, int nbr_cap, float* grad_coords, int32_t* status, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
-  if (!grid || !spos || !sorted_orig || !row_of || !grad_aev || !nbr_cnt || !nbr_list || !grad_coords || !status)
-    return ANI_ERR_BAD_ARG;
+  if (!grid || !spos || !sorted_orig || !row_of || !grad_aev || !grad_coords || !status) return ANI_ERR_BAD_ARG;
   if (lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
   if (nbr_cap < 32 || nbr_cap > 256 || nbr_cap % 32) return ANI_ERR_BAD_ARG;
   if (hi == lo) return ANI_OK;
@@ -762,15 +784,115 @@ extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_gri
     auto k = k_aev_backward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, nbr_cap, grad_coords, status, wb);
+                                            nbr_cnt, nbr_list, ex, nbr_cap, grad_coords, status, wb);
   } else {
     auto k = k_aev_backward<4, 8>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, nbr_cap, grad_coords, status, wb);
+                                            nbr_cnt, nbr_list, ex, nbr_cap, grad_coords, status, wb);
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
+}
+
+// ---- half pair list -> per-atom rows (both directions) ------------------------------------
+__global__ void k_pairs_count(const int64_t* __restrict__ idx0, const int64_t* __restrict__ idx1, long long P,
+                              int32_t* __restrict__ counts) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  atomicAdd(&counts[idx0[p]], 1);
+  atomicAdd(&counts[idx1[p]], 1);
+}
+
+__global__ void k_pairs_fill(const int64_t* __restrict__ idx0, const int64_t* __restrict__ idx1,
+                             const float* __restrict__ diff, long long P, const int32_t* __restrict__ start,
+                             int32_t* __restrict__ cursor, int32_t* __restrict__ csr_j, float4* __restrict__ csr_d) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int a = (int)idx0[p], b = (int)idx1[p];
+  // reference convention (neighbors.py:107-111): diff = x[idx0] - x[idx1] + shift
+  const float dx = diff[3 * p], dy = diff[3 * p + 1], dz = diff[3 * p + 2];
+  const float R = sqrtf(dx * dx + dy * dy + dz * dz);
+  const int sa = start[a] + atomicAdd(&cursor[a], 1);
+  csr_j[sa] = b;
+  csr_d[sa] = make_float4(-dx, -dy, -dz, R);  // seen from a: neighbour b sits at r_b - r_a = -diff
+  const int sb = start[b] + atomicAdd(&cursor[b], 1);
+  csr_j[sb] = a;
+  csr_d[sb] = make_float4(dx, dy, dz, R);
+}
+
+__global__ void k_row_overflow(const int32_t* __restrict__ start, int n, int cap, int32_t* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && start[i + 1] - start[i] > cap) atomicOr(status, ANI_STATUS_NBR_OVERFLOW);
+}
+
+}  // namespace ani
+
+using namespace ani;
+
+extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
+                                    const float* spos, const int32_t* sbin, const float* bucket_ranges,
+                                    const int32_t* species_mask, int n, int lo, int hi, const int32_t* row_of,
+                                    float* aev, int ldx, int layout, int32_t* nbr_cnt, int32_t* nbr_list,
+                                    int nbr_cap, int32_t* status, void* stream) {
+  int rc = check_params(params);
+  if (rc != ANI_OK) return rc;
+  if (!bin_start || !sbin || !nbr_cnt || !nbr_list) return ANI_ERR_BAD_ARG;
+  return launch_aev_forward(params, grid, bin_start, spos, sbin, bucket_ranges, species_mask,
+                            ExplicitNbrs{nullptr, nullptr, nullptr}, n, lo, hi, row_of, aev, ldx, layout, nbr_cnt,
+                            nbr_list, nbr_cap, status, stream);
+}
+
+extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                                     const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
+                                     const float* grad_aev, int ldx, const int32_t* nbr_cnt,
+                                     const int32_t* nbr_list, int nbr_cap, float* grad_coords, int32_t* status,
+                                     void* stream) {
+  int rc = check_params(params);
+  if (rc != ANI_OK) return rc;
+  if (!nbr_cnt || !nbr_list) return ANI_ERR_BAD_ARG;
+  return launch_aev_backward(params, grid, spos, sorted_orig, n, lo, hi, row_of, grad_aev, ldx, nbr_cnt, nbr_list,
+                             ExplicitNbrs{nullptr, nullptr, nullptr}, nbr_cap, grad_coords, status, stream);
+}
+
+extern "C" int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, const float* diff_vectors,
+                                      int64_t num_pairs, int n, int nbr_cap, int32_t* row_start, int32_t* row_j,
+                                      float* row_d, int32_t* scratch_i32, int32_t* status, void* stream) {
+  if (!row_start || !row_j || !row_d || !scratch_i32 || !status || n < 1 || num_pairs < 0) return ANI_ERR_BAD_ARG;
+  if (num_pairs > 0 && (!idx0 || !idx1 || !diff_vectors)) return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* counts = scratch_i32;            // [n]
+  int32_t* cursor = scratch_i32 + n;        // [n]
+  cudaMemsetAsync(scratch_i32, 0, sizeof(int32_t) * 2 * (size_t)n, st);
+  const int pb = (int)((num_pairs + 255) / 256);
+  if (num_pairs > 0) k_pairs_count<<<pb, 256, 0, st>>>(idx0, idx1, (long long)num_pairs, counts);
+  k_scan_i32<<<1, 1024, 0, st>>>(counts, n, row_start);
+  if (num_pairs > 0)
+    k_pairs_fill<<<pb, 256, 0, st>>>(idx0, idx1, diff_vectors, (long long)num_pairs, row_start, cursor, row_j,
+                                     reinterpret_cast<float4*>(row_d));
+  k_row_overflow<<<(n + 255) / 256, 256, 0, st>>>(row_start, n, nbr_cap, status);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_aev_forward_rows(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                                         const int32_t* row_start, const int32_t* row_j, const float* row_d, int n,
+                                         const int32_t* row_of, float* aev, int ldx, int layout, int nbr_cap,
+                                         int32_t* status, void* stream) {
+  if (!row_start || !row_j || !row_d) return ANI_ERR_BAD_ARG;
+  return launch_aev_forward(params, grid, nullptr, spos, nullptr, nullptr, nullptr,
+                            ExplicitNbrs{row_start, row_j, reinterpret_cast<const float4*>(row_d)}, n, 0, n, row_of,
+                            aev, ldx, layout, nullptr, nullptr, nbr_cap, status, stream);
+}
+
+extern "C" int ani_b200_aev_backward_rows(const ani_aev_params* params, const ani_grid* grid, const float* spos,
+                                          const int32_t* sorted_orig, const int32_t* row_start, const int32_t* row_j,
+                                          const float* row_d, int n, const int32_t* row_of, const float* grad_aev,
+                                          int ldx, int nbr_cap, float* grad_coords, int32_t* status, void* stream) {
+  if (!row_start || !row_j || !row_d) return ANI_ERR_BAD_ARG;
+  return launch_aev_backward(params, grid, spos, sorted_orig, n, 0, n, row_of, grad_aev, ldx, nullptr, nullptr,
+                             ExplicitNbrs{row_start, row_j, reinterpret_cast<const float4*>(row_d)}, nbr_cap,
+                             grad_coords, status, stream);
 }
 
 extern "C" int ani_b200_half_neighbor_count(const ani_grid* grid, const int32_t* bin_start, const float* spos,

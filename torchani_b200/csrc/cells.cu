@@ -313,15 +313,26 @@ __global__ void k_layout_scan(int n_chunks, int S, int rows_cap, int32_t* __rest
   __shared__ int s_tot[ANI_MAX_SPECIES];
   __shared__ int s_base[ANI_MAX_SPECIES + 1];
   const int tid = threadIdx.x;
-  if (tid < S) {
-    int run = 0;
-    for (int c = 0; c < n_chunks; ++c) {
-      int v = chunk_hist[c * ANI_MAX_SPECIES + tid];
-      chunk_hist[c * ANI_MAX_SPECIES + tid] = run;
-      run += v;
+  // exclusive scan over chunks, per species; the histogram is staged through shared memory in
+  // slabs so that the serial scan does not pay a global-memory round trip per chunk
+  __shared__ int s_slab[128 * ANI_MAX_SPECIES];
+  int run = 0;
+  for (int c0 = 0; c0 < n_chunks; c0 += 128) {
+    const int nc = min(128, n_chunks - c0);
+    for (int k = tid; k < nc * ANI_MAX_SPECIES; k += blockDim.x) s_slab[k] = chunk_hist[c0 * ANI_MAX_SPECIES + k];
+    __syncthreads();
+    if (tid < S) {
+      for (int c = 0; c < nc; ++c) {
+        const int v = s_slab[c * ANI_MAX_SPECIES + tid];
+        s_slab[c * ANI_MAX_SPECIES + tid] = run;
+        run += v;
+      }
     }
-    s_tot[tid] = run;
+    __syncthreads();
+    for (int k = tid; k < nc * ANI_MAX_SPECIES; k += blockDim.x) chunk_hist[c0 * ANI_MAX_SPECIES + k] = s_slab[k];
+    __syncthreads();
   }
+  if (tid < S) s_tot[tid] = run;
   __syncthreads();
   if (tid == 0) {
     int row = 0, owned = 0;
@@ -394,31 +405,34 @@ __global__ void k_species_present(const float4* __restrict__ spos, const ani_gri
 
 __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int n_shf_r, int angular_sub,
                                 int out_dim, int ldx, int32_t* __restrict__ blocks) {
-  // one warp; lane c tests column b*32 + c of block b, the ballot decides, lane 0 appends
+  // one warp; lane b tests the 32 columns of block b (32 blocks per round), a ballot compacts
   const unsigned mask = (unsigned)*present;
   const int RL = S * n_shf_r;
   const int lane = threadIdx.x;
   int count = 0;
-  for (int b = 0; b < ldx / 32; ++b) {
-    const int c = b * 32 + lane;
+  for (int b0 = 0; b0 < ldx / 32; b0 += 32) {
+    const int b = b0 + lane;
     bool active = false;
-    if (c < out_dim) {
-      if (c < RL) {
-        active = (mask >> (c / n_shf_r)) & 1u;
-      } else {
-        // invert the row-major upper-triangle pair index
-        int s1 = 0, rem = (c - RL) / angular_sub;
-        while (rem >= S - s1) {
-          rem -= S - s1;
-          ++s1;
+    if (b < ldx / 32) {
+      // radial columns one by one, angular columns pair block by pair block
+      for (int c = b * 32; c < b * 32 + 32 && c < out_dim && !active;
+           c = (c < RL) ? c + 1 : RL + ((c - RL) / angular_sub + 1) * angular_sub) {
+        if (c < RL) {
+          active = (mask >> (c / n_shf_r)) & 1u;
+        } else {
+          // invert the row-major upper-triangle pair index (one test per pair block is enough)
+          int s1 = 0, rem = (c - RL) / angular_sub;
+          while (rem >= S - s1) {
+            rem -= S - s1;
+            ++s1;
+          }
+          active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
         }
-        active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
       }
     }
-    if (__any_sync(ANI_FULL_MASK, active)) {
-      if (lane == 0) blocks[1 + count] = b;
-      ++count;
-    }
+    const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
+    if (active) blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
+    count += __popc(live);
   }
   if (lane == 0) {
     blocks[0] = count;
