@@ -38,6 +38,11 @@ UNIT = "atom-steps/s"
 # algorithmic bytes per atom of the AEV kernels (fp32, ANI-2x)
 AEV_FWD_BYTES_PER_ATOM = 4276.0
 AEV_BWD_BYTES_PER_ATOM = 4288.0
+# dram__bytes_read.sum + dram__bytes_write.sum from the ncu --set full capture of this build
+# (profiles/), per launch (AEV kernels) / per six-GEMM sequence at the 9999-atom box; None = not captured
+MLP_DRAM_BYTES_PER_STEP = None
+AEV_FWD_DRAM_BYTES = None
+AEV_BWD_DRAM_BYTES = None
 
 
 def workload(n_molecules: int):
@@ -99,18 +104,25 @@ def cpu_reference_step(orc, model, idx, coords, cell, pbc):
     return out["energy"], out["forces"]
 
 
-def run_cpu_baseline(idx, coords, cell, pbc, steps: int, warmup: int):
-    """The reference algorithm's CPU port (oracle/ani_oracle.py, float32, all host threads)."""
+def run_cpu_baseline(idx, coords, cell, pbc, steps: int, warmup: int, budget_s: float = 60.0):
+    """The reference algorithm's CPU port (oracle/ani_oracle.py, float32, all host threads).
+    Bounded: stops early (after at least one timed evaluation) once `budget_s` seconds are spent,
+    warm-up included, so a slow or busy host cannot stretch the run."""
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1: undo that for the CPU arm
     orc = load_oracle()
     model = orc.ani2x_model(seed=1234, members=8, neighborlist="cell_list")
+    t_begin = time.perf_counter()
     for _ in range(warmup):
         cpu_reference_step(orc, model, idx, coords, cell, pbc)
+        if time.perf_counter() - t_begin > budget_s / 2:
+            break
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
         cpu_reference_step(orc, model, idx, coords, cell, pbc)
         times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
     return times
 
 
@@ -140,12 +152,12 @@ def main():
             return
         z, idx, coords, cell, pbc = workload(args.molecules)
         cores = torch.get_num_threads()
-        times = run_cpu_baseline(idx, coords, cell, pbc, args.steps, args.warmup)
+        times = run_cpu_baseline(idx, coords, cell, pbc, args.steps, args.warmup, budget_s=150.0)
         t = sum(times) / len(times)
         value = n_atoms / t
-        sample = f"{args.steps} full energy+force evaluations of the {n_atoms}-atom box (float32, torch CPU ops)"
+        sample = f"{len(times)} full energy+force evaluations of the {n_atoms}-atom box (float32, torch CPU ops)"
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "ns_per_day": 0.0864 / t, "config": config,
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -254,28 +266,35 @@ def main():
     mlp_s = stage.get("mlp_forward_backward", float("nan")) * 1e-3
     fwd_s = stage.get("aev_forward", float("nan")) * 1e-3
     bwd_s = stage.get("aev_backward", float("nan")) * 1e-3
-    roofline = {"kernel": "k_gemm<*> x6 + k_mlp_head (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input",
+    roofline = {"kernel": "tc::k_gemm_tc<EPI> x6 (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input, "
+                          "tcgen05 kind::tf32 with a 3-product hi/lo split (fp32-accurate)",
                 "bound": "tensor", "achieved": flops / mlp_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": None,
+                "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": MLP_DRAM_BYTES_PER_STEP if world == 1 and args.molecules == 3333 else None,
                 "algorithmic_flops_per_launch_sequence": flops, "peak_source": pk["source"],
-                "note": "v1 arithmetic is fp32 FFMA; peak is the measured dense bf16 tensor rate"}
+                "note": "achieved = dense algorithmic FLOPs of SURVEY 8(d) (98.2 GFLOP/step at 10k atoms) / "
+                        "device time of the six GEMM launches; peak = measured dense bf16 rate. The kernel issues 3 TF32 "
+                        "MMAs per product (TF32 peak = bf16/2) but skips the AEV column blocks of absent element "
+                        "pairs in layer 1, so the executed tensor work is 3 x 36% of the dense count for water. "
+                        "traffic = dram bytes of the six launches (ncu, profiles/), null if not captured for this build"}
     roofline_aev = {
         "forward": {"kernel": "k_aev_forward<8,4>", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
                     "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9 / pk["hbm_gbs"], "traffic": None},
+                    "frac": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9 / pk["hbm_gbs"],
+                    "traffic": AEV_FWD_DRAM_BYTES if world == 1 and args.molecules == 3333 else None},
         "backward": {"kernel": "k_aev_backward<8,4>", "bound": "hbm", "achieved": AEV_BWD_BYTES_PER_ATOM * owned / bwd_s / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": AEV_BWD_BYTES_PER_ATOM * owned / bwd_s / 1e9 / pk["hbm_gbs"], "traffic": None},
+                     "frac": AEV_BWD_BYTES_PER_ATOM * owned / bwd_s / 1e9 / pk["hbm_gbs"],
+                     "traffic": AEV_BWD_DRAM_BYTES if world == 1 and args.molecules == 3333 else None},
         "peak_source": pk["source"]}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and args.cpu_steps > 0:
         cores = torch.get_num_threads()
-        times = run_cpu_baseline(idx, coords, cell, pbc, args.cpu_steps, 1)
+        times = run_cpu_baseline(idx, coords, cell, pbc, args.cpu_steps, 1, budget_s=45.0)
         t = sum(times) / len(times)
         cpu = {"value": n_atoms / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_steps} full energy+force evaluations of the same {n_atoms}-atom box with the "
+               "sample": f"{len(times)} full energy+force evaluations of the same {n_atoms}-atom box with the "
                          f"CPU port of the reference algorithm (oracle/ani_oracle.py, float32, {cores} threads)"}
 
     if rank == 0:

@@ -181,6 +181,11 @@ int ani_b200_aev_backward_rows(const ani_aev_params* params, const ani_grid* gri
                                const float* grad_aev, int ldx, int nbr_cap, float* grad_coords,
                                int32_t* status, void* stream);
 
+/* Timing experiments only: the first 4 CTAs of the next `launches` tensor-core GEMM launches    */
+/* write clock64 stamps [launch][cta 4][tile 8][role 3: producer, MMA, epilogue][4] into buf       */
+/* (device memory, launches*384 int64).  NULL switches it off.  No reference counterpart.           */
+int ani_b200_debug_gemm_trace(long long* buf, int launches);
+
 /* 5. Reference-format half neighbour list (neighbors.py:13-18) from the bucket grid.       */
 /*    Two calls: count (fills pair_start i32[n+1], exclusive scan, total in pair_start[n]),  */
 /*    then fill with capacity `cap` pairs.  indices are flat INPUT indices, idx0 < idx1       */

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   }
   __syncwarp();
 
-  // ---- 4. angular, ordered pairs (j, k): lanes own rows j
+  // ---- 4. angular.  Lanes own rows j of the species-sorted angular list.
   const int n_ang = build_angular_list<true>(P, s, cnt, lane, status);
   if (n_ang >= 2) {
     float shfA[NA], cz[NZ], sz[NZ];
@@ -503,67 +503,109 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
       cz[z] = P.cos_z[z];
       sz[z] = P.sin_z[z];
     }
+    // The three sums every pair needs (symmetric in j <-> k):
+    //   S0 = sum g f1 f2,  S1 = sum g f1' f2 (d/dcos),  S2 = sum g f1 f2' (d/dRbar)
+    auto pair_sums = [&](const float4& dj, const float4& dk, int pidx, float& cosT, float& inv_rr, float& S0,
+                         float& S1, float& S2) {
+      const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
+      inv_rr = 1.0f / fmaxf(dj.w * dk.w, 1e-10f);
+      cosT = dot * inv_rr;
+      const float c = 0.95f * cosT;
+      const float sn = sqrtf(fmaxf(1.0f - c * c, 0.f));
+      const float c_over_s = c / sn;
+      const float rbar = 0.5f * (dj.w + dk.w);
+      float f2[NA], f2p[NA];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const float d = rbar - shfA[a];
+        f2[a] = fast_exp(-P.eta_a * d * d);
+        f2p[a] = -2.0f * P.eta_a * d * f2[a];
+      }
+      S0 = S1 = S2 = 0.f;
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) {
+        float tz = 0.f, uz = 0.f;
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          const float gv = g_ang[(a * NZ + z) * gstride + pidx];
+          tz += gv * f2[a];
+          uz += gv * f2p[a];
+        }
+        const float base = fmaxf(0.5f * (1.0f + c * cz[z] + sn * sz[z]), 0.f);
+        const float lg = log2f(base);
+        const float f1 = exp2f(P.zeta * lg);
+        const float pw1 = exp2f((P.zeta - 1.0f) * lg);
+        const float f1p = P.zeta * pw1 * (0.475f * (cz[z] - c_over_s * sz[z]));
+        S0 += f1 * tz;
+        S1 += f1p * tz;
+        S2 += f1 * uz;
+      }
+    };
     int lpr = 1;
     while (lpr * 2 * n_ang <= 32) lpr *= 2;
-    const int rows_per_pass = 32 / lpr;
     const int sub = lane % lpr;
-    for (int row0 = 0; row0 < n_ang; row0 += rows_per_pass) {
-      const int j = row0 + lane / lpr;
+    if (n_ang <= 32) {
+      // Rotation over UNORDERED pairs: in step t row j evaluates the pair (j, (j + t) mod n) once,
+      // keeps its own share and hands the partner's share to the lane that owns row k with one
+      // shuffle (every row receives from row j - t at the same step).  t runs to n/2; for even n
+      // the last step would see every pair from both ends, so only rows j < n/2 take part in it.
+      // The lpr lanes of a row split the steps.  Half the transcendental work of ordered pairs.
+      const int j = lane / lpr;
       const bool jvalid = j < n_ang;
+      const int half_n = n_ang >> 1;
+      const bool even = (n_ang & 1) == 0;
       float gx = 0.f, gy = 0.f, gz = 0.f;
+      int nj_ = 0, sj = 0;
+      float4 dj = make_float4(0.f, 0.f, 0.f, 1.f);
+      float fcj = 0.f, dfcj = 0.f, inv_rj = 0.f;
       if (jvalid) {
-        const int nj_ = s.aidx[j];
-        const float4 dj = s.nd[nj_];
-        const float fcj = s.afc[j], dfcj = s.afcd[j];
-        const int sj = s.nsp[nj_];
-        const float inv_rj = dj.w > 1e-10f ? 1.0f / dj.w : 0.f;
-        for (int k = sub; k < n_ang; k += lpr) {
-          if (k == j) continue;
+        nj_ = s.aidx[j];
+        dj = s.nd[nj_];
+        fcj = s.afc[j];
+        dfcj = s.afcd[j];
+        sj = s.nsp[nj_];
+        inv_rj = dj.w > 1e-10f ? 1.0f / dj.w : 0.f;
+      }
+      const int steps = (half_n + lpr - 1) / lpr;
+      for (int it = 0; it < steps; ++it) {
+        const int t = 1 + it * lpr + sub;
+        const bool active = jvalid && t <= half_n && !(even && t == half_n && j >= half_n);
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (active) {
+          int k = j + t;
+          if (k >= n_ang) k -= n_ang;
           const int nk_ = s.aidx[k];
           const float4 dk = s.nd[nk_];
-          const float fck = s.afc[k];
-          const int pidx = pair_index(sj, (int)s.nsp[nk_], S);
-          const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
-          const float inv_rr = 1.0f / fmaxf(dj.w * dk.w, 1e-10f);
-          const float cosT = dot * inv_rr;
-          const float c = 0.95f * cosT;
-          const float sn = sqrtf(fmaxf(1.0f - c * c, 0.f));
-          const float c_over_s = c / sn;
-          const float rbar = 0.5f * (dj.w + dk.w);
-          float f2[NA], f2p[NA];
-#pragma unroll
-          for (int a = 0; a < NA; ++a) {
-            const float d = rbar - shfA[a];
-            f2[a] = fast_exp(-P.eta_a * d * d);
-            f2p[a] = -2.0f * P.eta_a * d * f2[a];
-          }
-          float S0 = 0.f, S1 = 0.f, S2 = 0.f;
-#pragma unroll
-          for (int z = 0; z < NZ; ++z) {
-            float tz = 0.f, uz = 0.f;
-#pragma unroll
-            for (int a = 0; a < NA; ++a) {
-              const float gv = g_ang[(a * NZ + z) * gstride + pidx];
-              tz += gv * f2[a];
-              uz += gv * f2p[a];
-            }
-            const float base = fmaxf(0.5f * (1.0f + c * cz[z] + sn * sz[z]), 0.f);
-            const float lg = log2f(base);
-            const float f1 = exp2f(P.zeta * lg);
-            const float pw1 = exp2f((P.zeta - 1.0f) * lg);
-            const float f1p = P.zeta * pw1 * (0.475f * (cz[z] - c_over_s * sz[z]));
-            S0 += f1 * tz;
-            S1 += f1p * tz;
-            S2 += f1 * uz;
-          }
+          const float fck = s.afc[k], dfck = s.afcd[k];
+          const float inv_rk = dk.w > 1e-10f ? 1.0f / dk.w : 0.f;
+          float cosT, inv_rr, S0, S1, S2;
+          pair_sums(dj, dk, pair_index(sj, (int)s.nsp[nk_], S), cosT, inv_rr, S0, S1, S2);
+          // feature = 2 f1 f2 fcj fck (once per unordered pair): its derivative with respect to
+          // r_j is this lane's share, the one with respect to r_k goes to the partner row
           const float W = fcj * fck;
-          const float dEdRj = S2 * W + 2.0f * S0 * dfcj * fck;  // 2*(0.5*S2*W + S0*fcj'*fck)
           const float dEdcos = 2.0f * W * S1;
+          const float dEdRj = S2 * W + 2.0f * S0 * dfcj * fck;
+          const float dEdRk = S2 * W + 2.0f * S0 * fcj * dfck;
           const float coefj = (dEdRj - dEdcos * cosT * inv_rj) * inv_rj;
-          const float coefk = dEdcos * inv_rr;
-          gx += coefj * dj.x + coefk * dk.x;
-          gy += coefj * dj.y + coefk * dk.y;
-          gz += coefj * dj.z + coefk * dk.z;
+          const float coefk = (dEdRk - dEdcos * cosT * inv_rk) * inv_rk;
+          const float coefx = dEdcos * inv_rr;
+          gx += coefj * dj.x + coefx * dk.x;
+          gy += coefj * dj.y + coefx * dk.y;
+          gz += coefj * dj.z + coefx * dk.z;
+          px = coefk * dk.x + coefx * dj.x;
+          py = coefk * dk.y + coefx * dj.y;
+          pz = coefk * dk.z + coefx * dj.z;
+        }
+        int src_row = j - t;
+        if (src_row < 0) src_row += n_ang;
+        const int src_lane = jvalid ? src_row * lpr + sub : lane;
+        const float rx = __shfl_sync(ANI_FULL_MASK, px, src_lane);
+        const float ry = __shfl_sync(ANI_FULL_MASK, py, src_lane);
+        const float rz = __shfl_sync(ANI_FULL_MASK, pz, src_lane);
+        if (jvalid) {  // inactive sources sent zeros
+          gx += rx;
+          gy += ry;
+          gz += rz;
         }
       }
       for (int o = lpr / 2; o > 0; o >>= 1) {
@@ -572,12 +614,42 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
         gz += __shfl_xor_sync(ANI_FULL_MASK, gz, o);
       }
       if (jvalid && sub == 0) {
-        const int nj_ = s.aidx[j];
         s.fgrad[3 * nj_ + 0] += gx;
         s.fgrad[3 * nj_ + 1] += gy;
         s.fgrad[3 * nj_ + 2] += gz;
       }
-      __syncwarp();
+    } else {
+      // more rows than lanes: ordered pairs (j, k), several passes of 32 rows
+      for (int row0 = 0; row0 < n_ang; row0 += 32) {
+        const int j = row0 + lane;
+        float gx = 0.f, gy = 0.f, gz = 0.f;
+        if (j < n_ang) {
+          const int nj_ = s.aidx[j];
+          const float4 dj = s.nd[nj_];
+          const float fcj = s.afc[j], dfcj = s.afcd[j];
+          const int sj = s.nsp[nj_];
+          const float inv_rj = dj.w > 1e-10f ? 1.0f / dj.w : 0.f;
+          for (int k = 0; k < n_ang; ++k) {
+            if (k == j) continue;
+            const int nk_ = s.aidx[k];
+            const float4 dk = s.nd[nk_];
+            const float fck = s.afc[k];
+            float cosT, inv_rr, S0, S1, S2;
+            pair_sums(dj, dk, pair_index(sj, (int)s.nsp[nk_], S), cosT, inv_rr, S0, S1, S2);
+            const float W = fcj * fck;
+            const float dEdRj = S2 * W + 2.0f * S0 * dfcj * fck;  // 2*(0.5*S2*W + S0*fcj'*fck)
+            const float dEdcos = 2.0f * W * S1;
+            const float coefj = (dEdRj - dEdcos * cosT * inv_rj) * inv_rj;
+            const float coefk = dEdcos * inv_rr;
+            gx += coefj * dj.x + coefk * dk.x;
+            gy += coefj * dj.y + coefk * dk.y;
+            gz += coefj * dj.z + coefk * dk.z;
+          }
+          s.fgrad[3 * nj_ + 0] += gx;
+          s.fgrad[3 * nj_ + 1] += gy;
+          s.fgrad[3 * nj_ + 2] += gz;
+        }
+      }
     }
   }
   __syncwarp();

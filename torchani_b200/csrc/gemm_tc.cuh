@@ -23,8 +23,11 @@
 //                         final layer + gradient seed | plain, hi/lo split, 16-byte stores
 //   warp  8    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
 //   warp  9    producer : one lane arms the mbarrier (expect_tx) and issues the bulk copies
-// Pipelines: smem full/empty (4 stages x 48 KB) and TMEM full/empty (2 x 256 columns), so the
-// epilogue of tile i overlaps the main loop of tile i+1.
+// Pipelines: smem full/empty (3-6 stages of 16 KB + 2 x bn x 64 B, sized per launch) and TMEM
+// full/empty (2 x 256 columns), so the epilogue of tile i overlaps the main loop of tile i+1.
+// The epilogue itself is pipelined too: TMEM loads run one column group ahead, and every warp
+// owns two store-staging buffers so the TMA store of group g drains while group g+1 is computed
+// (with one buffer and a wait per group the epilogue, not the MMA or HBM, bounded every GEMM).
 #pragma once
 #include "common.cuh"
 
@@ -36,14 +39,19 @@ constexpr int TN_MAX = 256;              // UMMA N (columns of one accumulator)
 constexpr int TK = 16;                   // fp32 per K-block = one 64-byte swizzle row (SWIZZLE_64B)
 constexpr int ROW_BYTES = TK * 4;        // 64
 constexpr int GROUP_BYTES = 8 * ROW_BYTES;       // 8-row swizzle group = 512 B (descriptor SBO)
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int A_PART_BYTES = TM * ROW_BYTES;     // 8 KB (hi or lo of one A K-block)
 constexpr int A_BLOCK_BYTES = 2 * A_PART_BYTES;  // 16 KB: [hi | lo], contiguous in global memory
 constexpr int B_TILE_BYTES = TN_MAX * ROW_BYTES; // 16 KB
-constexpr int STAGE_BYTES = A_BLOCK_BYTES + 2 * B_TILE_BYTES;  // 48 KB
-constexpr int EPI_STAGE_BYTES = 2 * 32 * ROW_BYTES;           // per epilogue warp: 32 rows x 64 B, hi + lo = 4 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int STAGE_BYTES_MAX = A_BLOCK_BYTES + 2 * B_TILE_BYTES;  // 48 KB (bn = 256)
+constexpr int EPI_STAGE_BYTES = 2 * 32 * ROW_BYTES;           // per epilogue warp and buffer: 32 rows x 64 B, hi + lo = 4 KB
+constexpr int EPI_BUFS = 2;
 constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, PROD_WARP = 9;
+constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS * EPI_STAGE_BYTES;  // 64 KB
+// always (almost) the whole SM: the pipeline depth adapts on the device.  6 KB of the 227 KB are
+// left for the static shared memory (tile map, barriers, bias staging, EPI_HEAD partial sums)
+constexpr int SMEM_BYTES = 227 * 1024 - 6144;
+constexpr int SMEM_FIXED = EPI_BYTES + 1024 /*align*/;
 constexpr int THREADS = (NUM_EPI_WARPS + 2) * 32;  // 320
 constexpr int TMEM_COLS = 512;
 
@@ -56,6 +64,9 @@ struct Species {
   int a_moff, c_moff, bias_mstride;  // per-member column offsets into A / C (multiples of 16)
   const float* w4;    // EPI_HEAD: final layer weights [M][N] and biases [M]
   const float* b4;
+  // split-K over the members (layer-1 backward): all members share ONE B operand with b_kblocks
+  // K-blocks, member m starts at K-block m * b_kb_moff.  0: one B operand per member.
+  int b_kblocks, b_kb_moff;
 };
 
 struct Args {
@@ -74,6 +85,8 @@ struct Args {
   const int32_t* row_atom;      // [rows_cap], -1 for padding rows
   int rows_cap;
   int want_backward;
+  int c_accumulate;             // EPI_PLAIN: C += tile (vector RED), C zeroed by the caller
+  long long* trace;             // optional clock64 stamps [cta < 4][tile < 8][role 3][4] (ani_b200_debug_gemm_trace)
   int debug;                    // timing experiments only (ANI_B200_GEMM_DEBUG): 2 no copies, 4 no MMA, 8 no epilogue
   float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
@@ -104,7 +117,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void red_add_v4(float* dst, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -151,18 +169,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// 16 consecutive accumulator columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// 16 consecutive accumulator columns of this thread's TMEM lane: asynchronous issue ...
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// ... and the wait; the registers are threaded through the asm so no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_64B, 8-row groups 512 B apart
@@ -204,6 +226,7 @@ struct TileMap {
   int n_eff[ANI_MAX_SPECIES];          // columns actually computed (compacted when nblocks is given)
   int kb_count, nb_count;              // live K-blocks (-1: dense) / live column blocks (-1: dense)
   int kb[MAX_BLOCKS], nb[MAX_BLOCKS];
+  int stages, stage_bytes;             // shared-memory pipeline: as deep as the widest accumulator of this launch allows
 };
 
 struct Tile {
@@ -233,6 +256,11 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm) {
     run += (tm.first_rt[s + 1] - tm.first_rt[s]) * a.members * tm.ntn[s];
   }
   tm.prefix[S] = run;
+  int bn_max = 16;
+  for (int s = 0; s < S; ++s)
+    if (tm.first_rt[s + 1] > tm.first_rt[s]) bn_max = max(bn_max, min(TN_MAX, tm.n_eff[s]));
+  tm.stage_bytes = A_BLOCK_BYTES + 2 * bn_max * ROW_BYTES;
+  tm.stages = min(MAX_STAGES, (SMEM_BYTES - SMEM_FIXED) / tm.stage_bytes);
 }
 
 __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, int t) {
@@ -268,20 +296,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned operand tiles (swizzle groups are 8 rows x 64 B)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 x 4 KB store staging (epilogue warps)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 8 * EPI_STAGE_BYTES);
-  uint64_t* full = bars;                     // [STAGES]  TMA bytes -> MMA
-  uint64_t* empty = bars + STAGES;           // [STAGES]  MMA (commit) -> producer
-  uint64_t* tfull = bars + 2 * STAGES;       // [2]       MMA (commit) -> epilogue
-  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   __shared__ TileMap tm;
   __shared__ float e_part[NUM_EPI_WARPS * 32];  // EPI_HEAD: partial row energies of the two column halves
+  __shared__ __align__(16) float s_bias[2][TN_MAX];  // bias (and final-layer weights) of the tile in flight,
+  __shared__ __align__(16) float s_w4[2][TN_MAX];    // double-buffered by tile parity
+  auto stamp = [&](int tile_local, int role, int slot) {
+    if (args.trace && blockIdx.x < 4 && tile_local < 8)
+      args.trace[(((size_t)blockIdx.x * 8 + tile_local) * 3 + role) * 4 + slot] = clock64();
+  };
+  if (threadIdx.x == 0) build_tile_map(args, tm);
+  __syncthreads();
+  const int STAGES = tm.stages, STAGE_BYTES = tm.stage_bytes;
+  unsigned char* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 warps x 2 x 4 KB store staging (epilogue warps)
+  __shared__ uint64_t bars[2 * MAX_STAGES + 5];
+  uint64_t* full = bars;                         // [STAGES]  TMA bytes -> MMA
+  uint64_t* empty = bars + MAX_STAGES;           // [STAGES]  MMA (commit) -> producer
+  uint64_t* tfull = bars + 2 * MAX_STAGES;       // [2]       MMA (commit) -> epilogue
+  uint64_t* tempty = bars + 2 * MAX_STAGES + 2;  // [2]       epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    build_tile_map(args, tm);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);   // the expect_tx arrival of the producer lane (+ the transaction bytes)
       mbar_init(&empty[i], 1);
@@ -305,17 +341,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   if (warp == PROD_WARP) {
     // ================================ producer (TMA) ================================
     uint32_t stage = 0, phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int tloc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
       const int nkb = num_kb(sp.K);
-      const int nkb_all = (sp.K + TK - 1) / TK;  // K-blocks of the stored B operand
+      if (lane == 0) stamp(tloc, 0, 0);
+      const int nkb_all = sp.b_kb_moff ? sp.b_kblocks : (sp.K + TK - 1) / TK;  // K-blocks of the stored B operand
+      const int kb_boff = tl.mem * sp.b_kb_moff;                               // split-K: this member's first K-block
       // A: [row tile][16-column block][hi | lo]; this GEMM starts at column member * a_moff
       const unsigned char* At = reinterpret_cast<const unsigned char*>(args.A) +
                                 ((size_t)tl.rt * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
       // B: [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
-      const unsigned char* Bm =
-          reinterpret_cast<const unsigned char*>(sp.Bt) + (size_t)tl.mem * sp.N * nkb_all * (2 * ROW_BYTES);
+      const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) +
+                                (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (2 * ROW_BYTES));
       const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
       const bool dense = tm.nb_count < 0;
       // gathered column blocks (layer-1 backward): lane -> (live block q, part hi/lo)
@@ -334,42 +373,49 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         mbar_wait(&empty[stage], phase ^ 1);
         unsigned char* st = smem + stage * STAGE_BYTES;
         const int kbi = kb_id(kb);
+        const int kbb = kbi + kb_boff;
         if (!(args.debug & 2)) {
           if (lane == 0) {
             mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + 2 * b_bytes);
             bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
             if (dense)  // hi and lo are adjacent in global memory and in shared memory: one copy
-              bulk_g2s(st + A_BLOCK_BYTES, Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbi * tl.bn) * (2 * ROW_BYTES),
+              bulk_g2s(st + A_BLOCK_BYTES, Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (2 * ROW_BYTES),
                        2 * b_bytes, &full[stage]);
           }
           __syncwarp();
           if (g_active)
             bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,
-                     Bm + g_src + (size_t)kbi * g_bns * (2 * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
+                     Bm + g_src + (size_t)kbb * g_bns * (2 * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
         } else if (lane == 0) {
           mbar_arrive(&full[stage]);
         }
         __syncwarp();
+        if (lane == 0 && kb == 0) stamp(tloc, 0, 1);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
+      if (lane == 0) stamp(tloc, 0, 2);
     }
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ================================
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int tloc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
       const Tile tl = decode_tile(args, tm, t);
       const int nkb = num_kb(args.sp[tl.s].K);
       const uint32_t idesc = make_idesc(tl.bn);
       const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
+      if (lane == 0) stamp(tloc, 1, 0);
       mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
+      if (lane == 0) stamp(tloc, 1, 1);
       const uint32_t d_tmem = tmem_base + acc * TN_MAX;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (lane == 0 && kb == 0) stamp(tloc, 1, 2);
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PART_BYTES);
@@ -383,7 +429,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
           }
           umma_commit(&empty[stage]);                   // smem slot free once these MMAs retire
-          if (kb == nkb - 1) umma_commit(&tfull[acc]);  // accumulator complete
+          if (kb == nkb - 1) {
+            umma_commit(&tfull[acc]);  // accumulator complete
+            stamp(tloc, 1, 3);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -401,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     // Thread = accumulator row (TMEM lane).  Warps w and w+4 share the 32 lanes of quadrant w & 3
     // and take alternate 16-column groups.  Results are written hi/lo-split into the tiled operand
     // layout of the next GEMM (EPI_PLAIN: plain rows for the AEV backward kernel).
-    uint32_t acc = 0, acc_phase = 0;
+    uint32_t acc = 0, acc_phase = 0, buf = 0;
     const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
     const int quad = warp & 3, half = warp >> 2;
     const int r_tile = quad * 32 + lane;  // row inside the 128-row tile
@@ -413,15 +462,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     }
     // The warp's 32 rows x 64 B of one 16-column group are a contiguous 2 KB range of the tiled
     // layout (hi) plus another one 8 KB further (lo): stage them in shared memory in that very
-    // byte order and let the TMA write them (full lines, no partial-sector stores).
-    unsigned char* sb = epi_stage + warp * EPI_STAGE_BYTES;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    // byte order and let the TMA write them (full lines, no partial-sector stores).  Two staging
+    // buffers per warp: the store of one group drains while the next group is computed.
+    unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
+    const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward) && !(args.debug & 32);
+    int tloc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
-      const float* __restrict__ bias = (EPI == EPI_BIAS_CELU || EPI == EPI_HEAD)
-                                           ? sp.bias + (size_t)tl.mem * sp.bias_mstride + tl.n0
-                                           : nullptr;
-      const float* __restrict__ w4 = (EPI == EPI_HEAD) ? sp.w4 + (size_t)tl.mem * sp.N : nullptr;
+      if (threadIdx.x == 0) stamp(tloc, 2, 0);
+      // bias (and final-layer weights) of this tile -> shared memory while the main loop runs: the
+      // per-group float4 global loads sat on the critical path of every column group
+      const float* __restrict__ bias = s_bias[acc];
+      const float* __restrict__ w4 = s_w4[acc];
+      if (EPI == EPI_BIAS_CELU || EPI == EPI_HEAD) {
+        const int c = threadIdx.x;  // 256 epilogue threads == TN_MAX columns
+        if (c < tl.bn) {
+          s_bias[acc][c] = sp.bias[(size_t)tl.mem * sp.bias_mstride + tl.n0 + c];
+          if (EPI == EPI_HEAD) s_w4[acc][c] = sp.w4[(size_t)tl.mem * sp.N + c];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // epilogue warps only
+      }
       const int my_row = tl.rt * TM + r_tile;
       float e_acc = 0.f, seed = 0.f;
       bool row_valid = false;
@@ -446,16 +507,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       if (EPI == EPI_MUL_DCELU && half < ngroups && !(args.debug & 128)) load_y(half);  // overlaps the wait for the accumulator
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (threadIdx.x == 0) stamp(tloc, 2, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
-      for (int g = half; g < ngroups; g += 2) {
-        if (args.debug & 8) break;
-        float v[16];
-        if (!(args.debug & 64)) {
-          tmem_ld16(taddr + g * 16, v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
+
+      // one 16-column group: raw accumulator registers -> epilogue math -> store
+      auto process = [&](int g, const uint32_t (&r)[16]) {
         float4 y[4];
         if (EPI == EPI_MUL_DCELU) {
 #pragma unroll
@@ -463,10 +519,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             y[ch] = make_float4(yh[ch].x + yl[ch].x, yh[ch].y + yl[ch].y, yh[ch].z + yl[ch].z, yh[ch].w + yl[ch].w);
           if (g + 2 < ngroups && !(args.debug & 128)) load_y(g + 2);  // prefetch the next group this warp handles
         }
-        unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
+        unsigned char* sb = sb0 + buf * EPI_STAGE_BYTES;
+        if (tiled_out) {
+          // this buffer was handed to the TMA two groups ago: its read must be complete
+          if (lane == 0) bulk_wait_read<EPI_BUFS - 1>();
+          __syncwarp();
+        }
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          float4 o = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+          float4 o = make_float4(__uint_as_float(r[4 * ch]), __uint_as_float(r[4 * ch + 1]),
+                                 __uint_as_float(r[4 * ch + 2]), __uint_as_float(r[4 * ch + 3]));
           if (EPI == EPI_BIAS_CELU) {
             const float4 b = *reinterpret_cast<const float4*>(bias + g * 16 + 4 * ch);
             o.x = celu(o.x + b.x, cc);
@@ -491,24 +553,43 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           if (EPI == EPI_PLAIN) {
             // compacted column blocks map back to their place: group g lies in live block (n0 + 16 g) / 32
             const int col = (tm.nb_count >= 0 ? tm.nb[(tl.n0 + g * 16) / 32] * 32 + ((g * 16) & 16) : tl.n0 + g * 16) + 4 * ch;
-            *reinterpret_cast<float4*>(cplain + col) = o;
-          } else if (EPI != EPI_HEAD || args.want_backward) {
+            if (args.c_accumulate)
+              red_add_v4(cplain + col, o);
+            else
+              *reinterpret_cast<float4*>(cplain + col) = o;
+          } else if (tiled_out) {
             float4 hi, lo;
             split4(o, hi, lo);
             *reinterpret_cast<float4*>(sb + st_off[ch]) = hi;
             *reinterpret_cast<float4*>(sb + 32 * ROW_BYTES + st_off[ch]) = lo;
           }
         }
-        if (EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward) && !(args.debug & 32)) {
+        if (tiled_out) {
+          unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA
           __syncwarp();
           if (lane == 0) {
             bulk_s2g(blk + quad * 32 * ROW_BYTES, sb, 32 * ROW_BYTES);
             bulk_s2g(blk + A_PART_BYTES + quad * 32 * ROW_BYTES, sb + 32 * ROW_BYTES, 32 * ROW_BYTES);
             bulk_commit();
-            bulk_wait_read();  // the staging buffer may be overwritten once the TMA has read it
           }
-          __syncwarp();
+          buf ^= 1;
+        }
+      };
+
+      // TMEM loads run one group ahead of the math (two statically indexed register sets)
+      if (!(args.debug & 8)) {
+        uint32_t r0[16], r1[16];
+        if (half < ngroups) tmem_ld16_issue(taddr + half * 16, r0);
+        for (int g = half; g < ngroups; g += 4) {
+          tmem_ld_wait(r0);
+          if (g + 2 < ngroups) tmem_ld16_issue(taddr + (g + 2) * 16, r1);
+          process(g, r0);
+          if (g + 2 < ngroups) {
+            tmem_ld_wait(r1);
+            if (g + 4 < ngroups) tmem_ld16_issue(taddr + (g + 4) * 16, r0);
+            process(g + 2, r1);
+          }
         }
       }
       if (EPI == EPI_HEAD) {
@@ -522,6 +603,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      if (threadIdx.x == 0) stamp(tloc, 2, 2);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

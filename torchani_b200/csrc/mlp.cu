@@ -73,13 +73,44 @@ __global__ void __launch_bounds__(256) k_reduce_energies(const __grid_constant__
   }
 }
 
+// zero the live 32-column blocks of the plain gradient matrix (the split-K layer-1 backward
+// accumulates into it; dead blocks are never read by the AEV backward kernel)
+__global__ void __launch_bounds__(256) k_zero_live_blocks(float* dx, int ldx, const int32_t* layout_info, int num_species,
+                                                          const int32_t* blocks) {
+  const int rows = layout_info[4 + num_species] * ANI_TILE_ROWS;
+  const int count = blocks ? blocks[0] : ldx / 32;  // no list: every block is live
+  const long long total = (long long)rows * count * 8;  // float4 stores
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i & 7);
+    const long long rb = i >> 3;
+    const int b = (int)(rb % count);
+    const long long row = rb / count;
+    *reinterpret_cast<float4*>(dx + row * ldx + (blocks ? blocks[1 + b] : b) * 32 + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 }  // namespace ani
 
 using namespace ani;
 
+// timing experiments: clock64 stamps of the first CTAs of the next GEMM launches
+static long long* g_trace = nullptr;
+static int g_trace_launches = 0, g_trace_next = 0;
+constexpr int TRACE_WORDS_PER_LAUNCH = 4 * 8 * 3 * 4;
+
+extern "C" int ani_b200_debug_gemm_trace(long long* buf, int launches) {
+  g_trace = buf;
+  g_trace_launches = buf ? launches : 0;
+  g_trace_next = 0;
+  return ANI_OK;
+}
+
 // tensor-core launch: one persistent CTA per SM walks the device-side tile list
 template <int EPI>
-static void launch_gemm_tc(const tc::Args& a, cudaStream_t st) {
+static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st) {
+  tc::Args a = a_in;
+  a.trace = nullptr;
+  if (g_trace && g_trace_next < g_trace_launches) a.trace = g_trace + (size_t)(g_trace_next++) * TRACE_WORDS_PER_LAUNCH;
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -128,19 +159,20 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const f
   ta.rows_cap = rows_cap;
   ta.want_backward = want_backward;
   ta.ldc = 0;
+  ta.c_accumulate = 0;
   static const int gemm_debug = []() {
     const char* e = getenv("ANI_B200_GEMM_DEBUG");  // timing experiments only: results are wrong when set
     return e ? atoi(e) : 0;
   }();
   ta.debug = gemm_debug;
   for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ta.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
-  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr};
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, 0, 0};
 
   // ---- forward.  Layer 1: the members share the input -> one GEMM with N = M*h1.
   ta.A = x; ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr};
+    ta.sp[s] = tc::Species{p.t_f1, p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr, 0, 0};
   }
   ta.kblocks = aev_blocks;  // dead AEV column blocks contribute exact zeros: skip them
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
@@ -148,13 +180,13 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const f
   ta.A = act1; ta.a_kblocks = kb1; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{p.t_f2, p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr};
+    ta.sp[s] = tc::Species{p.t_f2, p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr, 0, 0};
   }
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
   ta.A = act2; ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{p.t_f3, p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4};
+    ta.sp[s] = tc::Species{p.t_f3, p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4, 0, 0};
   }
   // layer 3 + final layer (h3 -> 1) + gradient seed, fused in the epilogue: act3 receives
   // G3 = scale_m * w4 * celu'(a3) directly, e_member the per-member atomic energies
@@ -164,23 +196,29 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const f
     ta.A = act3; ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{p.t_b3, nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr};
+      ta.sp[s] = tc::Species{p.t_b3, nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
     ta.A = act2; ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{p.t_b2, nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr};
+      ta.sp[s] = tc::Species{p.t_b2, nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
-    ta.A = act1; ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = 1;
+    // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
+    // all SMs are busy even when there are fewer row tiles than SMs); the partial tiles are
+    // accumulated with vector REDs into the zeroed live column blocks of dx
+    ta.A = act1; ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{p.t_b1, nullptr, M * p.h1, ldx, 0, 0, 0, nullptr, nullptr};
+      ta.sp[s] = tc::Species{p.t_b1, nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr, M * p.h1 / 16, p.h1 / 16};
     }
     ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
+    ta.c_accumulate = M > 1;
+    if (ta.c_accumulate) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
     launch_gemm_tc<tc::EPI_PLAIN>(ta, st);
     ta.nblocks = nullptr;
+    ta.c_accumulate = 0;
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;

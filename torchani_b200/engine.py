@@ -401,7 +401,8 @@ class Engine:
                 graph.replay()
         # kernels launched by this library in one step (memsets excluded):
         #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 3 (+3 bwd), aev bwd 1, reduce 1
-        self.launches_per_step = 5 + 5 + 1 + 3 + (4 if want_grad else 0) + 1
+        # grid 6, layout 3, live blocks 2, AEV fwd 1, GEMM fwd 3, (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
+        self.launches_per_step = 6 + 3 + 2 + 1 + 3 + (5 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
                           ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
