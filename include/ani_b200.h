@@ -181,6 +181,20 @@ int ani_b200_aev_backward_rows(const ani_aev_params* params, const ani_grid* gri
                                const float* grad_aev, int ldx, int nbr_cap, float* grad_coords,
                                int32_t* status, void* stream);
 
+/* 3b. Fused per-step preparation: build_cells + species_layout + active_aev_blocks in five       */
+/*     launches instead of twelve (same outputs, same determinism; what the fused engine calls).   */
+/*     Also zero-fills zero_f32[0..count) (the force accumulator) and zero_f64[0..count) (the      */
+/*     conformer energies) so that no separate memset launches are needed.                          */
+/*     scratch_i32: 3 n + max_bins + 4 + (ceil((hi-lo)/256) + 2) * ANI_MAX_SPECIES + 16 ints.       */
+int ani_b200_prepare_step(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
+                          const float* cell, int pbc, int mode, float cutoff, int max_bins, ani_grid* grid,
+                          int32_t* bin_start, int32_t* sorted_orig, int32_t* orig_to_sorted, float* spos,
+                          int32_t* sbin, float* bucket_ranges, int lo, int hi, int num_species, int rows_cap,
+                          int32_t* row_of, int32_t* row_atom, int32_t* tile_species, int32_t* layout_info,
+                          int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* aev_blocks,
+                          float* zero_f32, int zero_f32_count, double* zero_f64, int zero_f64_count,
+                          int32_t* scratch_i32, int32_t* status, void* stream);
+
 /* Timing experiments only: the first 4 CTAs of the next `launches` tensor-core GEMM launches    */
 /* write clock64 stamps [launch][cta 4][tile 8][role 3: producer, MMA, epilogue][4] into buf       */
 /* (device memory, launches*384 int64).  NULL switches it off.  No reference counterpart.           */

@@ -5,42 +5,12 @@
 
 namespace ani {
 
-// ---------------------------------------------------------------------------------------
-// grid setup: one block.  mode 0 + pbc: buckets from the perpendicular widths of the cell
-// (>= 1 bucket per cutoff, neighbors.py:618-662 uses edge lengths; widths are the safe
-// choice for triclinic cells).  mode 0 without pbc: bounding box of the real atoms.
-// ---------------------------------------------------------------------------------------
-__global__ void k_grid_setup(const float* __restrict__ coords, const int32_t* __restrict__ species,
-                             int n, int n_conf, int n_per_conf, const float* __restrict__ cell, int pbc,
-                             int mode, float cutoff, int max_bins, ani_grid* __restrict__ grid,
-                             int32_t* __restrict__ status) {
-  __shared__ float s_min[3][32], s_max[3][32];
-  const int tid = threadIdx.x;
-  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-  if (mode == 0 && !pbc) {
-    for (int a = tid; a < n; a += blockDim.x) {
-      if (species[a] < 0) continue;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        float v = coords[3 * a + d];
-        lo[d] = fminf(lo[d], v);
-        hi[d] = fmaxf(hi[d], v);
-      }
-    }
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      for (int o = 16; o > 0; o >>= 1) {
-        lo[d] = fminf(lo[d], __shfl_xor_sync(ANI_FULL_MASK, lo[d], o));
-        hi[d] = fmaxf(hi[d], __shfl_xor_sync(ANI_FULL_MASK, hi[d], o));
-      }
-      if ((tid & 31) == 0) {
-        s_min[d][tid >> 5] = lo[d];
-        s_max[d][tid >> 5] = hi[d];
-      }
-    }
-  }
-  __syncthreads();
-  if (tid != 0) return;
+// The grid of one call (executed by one thread).  mode 0 + pbc: buckets from the perpendicular
+// widths of the cell (>= 1 bucket per cutoff, neighbors.py:618-662 uses edge lengths; widths are
+// the safe choice for triclinic cells).  mode 0 without pbc: bounding box of the real atoms.
+__device__ ani_grid compute_grid(int n_conf, int n_per_conf, const float* __restrict__ cell, int pbc, int mode,
+                                 float cutoff, int max_bins, const float* box_min, const float* box_max,
+                                 int32_t* __restrict__ status) {
   ani_grid g;
   for (int k = 0; k < 9; ++k) g.cell[k] = g.inv[k] = 0.f;
   g.origin[0] = g.origin[1] = g.origin[2] = 0.f;
@@ -89,12 +59,8 @@ __global__ void k_grid_setup(const float* __restrict__ coords, const int32_t* __
     } else {
       float mn[3], mx[3];
       for (int d = 0; d < 3; ++d) {
-        mn[d] = 1e30f;
-        mx[d] = -1e30f;
-        for (int w = 0; w < (blockDim.x >> 5); ++w) {
-          mn[d] = fminf(mn[d], s_min[d][w]);
-          mx[d] = fmaxf(mx[d], s_max[d][w]);
-        }
+        mn[d] = box_min[d];
+        mx[d] = box_max[d];
         if (mn[d] > mx[d]) mn[d] = mx[d] = 0.f;  // no real atoms
         float ext = (mx[d] - mn[d]) + 2e-3f;
         g.origin[d] = mn[d] - 1e-3f;
@@ -114,7 +80,55 @@ __global__ void k_grid_setup(const float* __restrict__ coords, const int32_t* __
     }
     g.nbins = g.dims[0] * g.dims[1] * g.dims[2];
   }
-  *grid = g;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------
+// grid setup: one block.  mode 0 + pbc: buckets from the perpendicular widths of the cell
+// (>= 1 bucket per cutoff, neighbors.py:618-662 uses edge lengths; widths are the safe
+// choice for triclinic cells).  mode 0 without pbc: bounding box of the real atoms.
+// ---------------------------------------------------------------------------------------
+__global__ void k_grid_setup(const float* __restrict__ coords, const int32_t* __restrict__ species,
+                             int n, int n_conf, int n_per_conf, const float* __restrict__ cell, int pbc,
+                             int mode, float cutoff, int max_bins, ani_grid* __restrict__ grid,
+                             int32_t* __restrict__ status) {
+  __shared__ float s_min[3][32], s_max[3][32];
+  const int tid = threadIdx.x;
+  float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+  if (mode == 0 && !pbc) {
+    for (int a = tid; a < n; a += blockDim.x) {
+      if (species[a] < 0) continue;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        float v = coords[3 * a + d];
+        lo[d] = fminf(lo[d], v);
+        hi[d] = fmaxf(hi[d], v);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[d] = fminf(lo[d], __shfl_xor_sync(ANI_FULL_MASK, lo[d], o));
+        hi[d] = fmaxf(hi[d], __shfl_xor_sync(ANI_FULL_MASK, hi[d], o));
+      }
+      if ((tid & 31) == 0) {
+        s_min[d][tid >> 5] = lo[d];
+        s_max[d][tid >> 5] = hi[d];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  float mn[3], mx[3];
+  for (int d = 0; d < 3; ++d) {
+    mn[d] = 1e30f;
+    mx[d] = -1e30f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) {
+      mn[d] = fminf(mn[d], s_min[d][w]);
+      mx[d] = fmaxf(mx[d], s_max[d][w]);
+    }
+  }
+  *grid = compute_grid(n_conf, n_per_conf, cell, pbc, mode, cutoff, max_bins, mn, mx, status);
 }
 
 __device__ __forceinline__ void wrapped_position(const ani_grid& g, const float* __restrict__ coords, int a,
@@ -443,6 +457,273 @@ __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fused per-step preparation (ani_b200_prepare_step): the same work as build_cells +
+// species_layout + active_aev_blocks in five launches instead of twelve --
+//   P1 grid (inline) + bucket assignment, the last block to finish scans the bucket counts
+//   P2 scatter into buckets  +  per-bucket neighbour-range table
+//   P3 deterministic order inside buckets, sorted arrays, per-chunk species histogram, element
+//      presence mask, zero-fill of the force accumulator
+//   P4 (one block) chunk scan, species row bases, tile table, live AEV column blocks
+//   P5 row assignment
+// Every launch boundary is a grid-wide dependency; nothing is synchronised with the host.
+// ---------------------------------------------------------------------------------------
+struct PrepArgs {
+  const float* coords;
+  const int32_t* species;
+  int n, n_conf, n_per_conf;
+  const float* cell;
+  int pbc, mode;
+  float cutoff;
+  int max_bins;
+  ani_grid* grid;
+  int32_t *bin_start, *sorted_orig, *orig_to_sorted;
+  float4* spos;
+  int32_t* sbin;
+  float4* ranges;
+  int lo, hi, S, rows_cap;
+  int32_t *row_of, *row_atom, *tile_species, *layout_info;
+  int n_shf_r, angular_sub, out_dim, ldx;
+  int32_t* blocks;
+  int32_t *bin_of, *slot, *tmp_list, *bin_count, *counter, *present, *chunk_hist, *species_base;
+  int n_chunks, inline_setup;
+  float* zero_f32;
+  int zero_f32_count;
+  double* zero_f64;
+  int zero_f64_count;
+  int32_t* status;
+};
+
+__global__ void __launch_bounds__(256) k_prep_assign(const __grid_constant__ PrepArgs A) {
+  __shared__ ani_grid sg;
+  __shared__ bool s_last;
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    if (A.inline_setup) {
+      const float none[3] = {0.f, 0.f, 0.f};
+      sg = compute_grid(A.n_conf, A.n_per_conf, A.cell, A.pbc, A.mode, A.cutoff, A.max_bins, none, none, A.status);
+      if (blockIdx.x == 0) *A.grid = sg;
+    } else {
+      sg = *A.grid;  // written by k_grid_setup (bounding box of an open system)
+    }
+  }
+  __syncthreads();
+  const int a = blockIdx.x * blockDim.x + tid;
+  if (a < A.n) {
+    int bin;
+    if (A.species[a] < 0) {
+      bin = sg.nbins;  // padding atoms: trash bucket, never a neighbour, never a centre
+    } else {
+      float3 p;
+      wrapped_position(sg, A.coords, a, p, bin);
+    }
+    A.bin_of[a] = bin;
+    A.slot[a] = atomicAdd(&A.bin_count[bin], 1);
+  }
+  // the last block to get here scans the bucket counts (exclusive) -> bin_start
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(A.counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int m = sg.nbins + 1;
+  const int lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < m; base += blockDim.x) {
+    const int i = base + tid;
+    const int v = (i < m) ? __ldcg(&A.bin_count[i]) : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(ANI_FULL_MASK, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = (lane < 8) ? s_warp[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const int y = __shfl_up_sync(ANI_FULL_MASK, t, o);
+        if (lane >= o) t += y;
+      }
+      if (lane < 8) s_warp[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    const int incl = x + ((w == 0) ? 0 : s_warp[w - 1]) + s_carry;
+    if (i < m) A.bin_start[i] = incl - v;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    A.bin_start[m] = s_carry;
+    A.grid->n_real = s_carry - __ldcg(&A.bin_count[m - 1]);  // everything before the trash bucket
+  }
+}
+
+__global__ void __launch_bounds__(256) k_prep_scatter(const __grid_constant__ PrepArgs A) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < A.n) A.tmp_list[A.bin_start[A.bin_of[idx]] + A.slot[idx]] = idx;
+  // per-bucket table of the 27 neighbouring buckets (see k_bucket_ranges)
+  if (!A.ranges) return;
+  const ani_grid g = *A.grid;
+  const int b = idx / 27, o = idx % 27;
+  if (b >= g.nbins || g.mode != 0) return;
+  const int iz = b % g.dims[2], iy = (b / g.dims[2]) % g.dims[1], ix = b / (g.dims[2] * g.dims[1]);
+  int j[3] = {ix + o / 9 - 1, iy + (o / 3) % 3 - 1, iz + o % 3 - 1};
+  int w[3];
+  for (int d = 0; d < 3; ++d) {
+    w[d] = 0;
+    if (j[d] < 0) {
+      w[d] = -1;
+      j[d] += g.dims[d];
+    } else if (j[d] >= g.dims[d]) {
+      w[d] = 1;
+      j[d] -= g.dims[d];
+    }
+  }
+  const bool exists = g.pbc || !(w[0] | w[1] | w[2]);
+  int lo = 0, hi = 0;
+  const int code = (w[0] + 1) * 9 + (w[1] + 1) * 3 + (w[2] + 1);
+  if (exists) {
+    const int nb = (j[0] * g.dims[1] + j[1]) * g.dims[2] + j[2];
+    lo = A.bin_start[nb];
+    hi = A.bin_start[nb + 1];
+  }
+  const float wx = (float)w[0], wy = (float)w[1], wz = (float)w[2];
+  A.ranges[2 * (size_t)idx] = make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), 0.f);
+  A.ranges[2 * (size_t)idx + 1] = make_float4(wx * g.cell[0] + wy * g.cell[3] + wz * g.cell[6],
+                                              wx * g.cell[1] + wy * g.cell[4] + wz * g.cell[7],
+                                              wx * g.cell[2] + wy * g.cell[5] + wz * g.cell[8], 0.f);
+}
+
+__global__ void __launch_bounds__(256) k_prep_finalize(const __grid_constant__ PrepArgs A) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const ani_grid g = *A.grid;
+  int sp = -1, i = -1;
+  if (a < A.n) {
+    const int b = A.bin_of[a];
+    const int lo = A.bin_start[b], hi = A.bin_start[b + 1];
+    int rank = 0;
+    for (int e = lo; e < hi; ++e) rank += (A.tmp_list[e] < a);  // rank by input index: deterministic order
+    i = lo + rank;
+    A.sorted_orig[i] = a;
+    A.orig_to_sorted[a] = i;
+    A.sbin[i] = b;
+    float3 p = make_float3(0.f, 0.f, 0.f);
+    sp = A.species[a];
+    if (sp >= 0) {
+      int bb;
+      wrapped_position(g, A.coords, a, p, bb);
+    }
+    A.spos[i] = make_float4(p.x, p.y, p.z, __int_as_float(sp));
+    // species histogram of the owned slice, per 256-atom chunk of the SORTED order
+    const int hi_real = min(A.hi, g.n_real);
+    if (sp >= 0 && i >= A.lo && i < hi_real)
+      atomicAdd(&A.chunk_hist[((i - A.lo) / LAYOUT_CHUNK) * ANI_MAX_SPECIES + sp], 1);
+  }
+  unsigned mask = 0;
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s)
+    if (__any_sync(ANI_FULL_MASK, sp == s)) mask |= 1u << s;
+  if ((threadIdx.x & 31) == 0 && mask) atomicOr(A.present, (int)mask);
+  if (A.zero_f32)
+    for (int k = a; k < A.zero_f32_count; k += gridDim.x * blockDim.x) A.zero_f32[k] = 0.f;
+}
+
+__global__ void __launch_bounds__(1024) k_prep_layout(const __grid_constant__ PrepArgs A) {
+  __shared__ int s_tot[ANI_MAX_SPECIES];
+  __shared__ int s_base[ANI_MAX_SPECIES + 1];
+  __shared__ int s_slab[128 * ANI_MAX_SPECIES];
+  const int tid = threadIdx.x, S = A.S;
+  // ---- live AEV column blocks (warp 31; independent of the scan below)
+  if (tid >= 992) {
+    const unsigned mask = (unsigned)*A.present;
+    const int RL = S * A.n_shf_r;
+    const int lane = tid & 31;
+    int count = 0;
+    for (int b0 = 0; b0 < A.ldx / 32; b0 += 32) {
+      const int b = b0 + lane;
+      bool active = false;
+      if (b < A.ldx / 32) {
+        for (int c = b * 32; c < b * 32 + 32 && c < A.out_dim && !active;
+             c = (c < RL) ? c + 1 : RL + ((c - RL) / A.angular_sub + 1) * A.angular_sub) {
+          if (c < RL) {
+            active = (mask >> (c / A.n_shf_r)) & 1u;
+          } else {
+            int s1 = 0, rem = (c - RL) / A.angular_sub;
+            while (rem >= S - s1) {
+              rem -= S - s1;
+              ++s1;
+            }
+            active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
+          }
+        }
+      }
+      const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
+      if (active) A.blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
+      count += __popc(live);
+    }
+    if (lane == 0) {
+      A.blocks[0] = count;
+      A.blocks[A.ldx / 32 + 2] = (A.blocks[A.ldx / 32 + 1] != (int)mask);
+      A.blocks[A.ldx / 32 + 1] = (int)mask;
+    }
+  }
+  // ---- exclusive scan of the chunk histograms per species (in place)
+  int run = 0;
+  for (int c0 = 0; c0 < A.n_chunks; c0 += 128) {
+    const int nc = min(128, A.n_chunks - c0);
+    for (int k = tid; k < nc * ANI_MAX_SPECIES; k += blockDim.x) s_slab[k] = A.chunk_hist[c0 * ANI_MAX_SPECIES + k];
+    __syncthreads();
+    if (tid < S) {
+      for (int c = 0; c < nc; ++c) {
+        const int v = s_slab[c * ANI_MAX_SPECIES + tid];
+        s_slab[c * ANI_MAX_SPECIES + tid] = run;
+        run += v;
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < nc * ANI_MAX_SPECIES; k += blockDim.x) A.chunk_hist[c0 * ANI_MAX_SPECIES + k] = s_slab[k];
+    __syncthreads();
+  }
+  if (tid < S) s_tot[tid] = run;
+  __syncthreads();
+  if (tid == 0) {
+    int row = 0, owned = 0;
+    for (int s = 0; s < S; ++s) {
+      s_base[s] = row;
+      A.species_base[s] = row;
+      owned += s_tot[s];
+      row += (s_tot[s] + ANI_TILE_ROWS - 1) / ANI_TILE_ROWS * ANI_TILE_ROWS;
+    }
+    s_base[S] = row;
+    A.layout_info[0] = row / ANI_TILE_ROWS;
+    A.layout_info[1] = row;
+    A.layout_info[2] = owned;
+    A.layout_info[3] = 0;
+    for (int s = 0; s <= S; ++s) A.layout_info[4 + s] = s_base[s] / ANI_TILE_ROWS;
+    for (int s = S + 1; s <= ANI_MAX_SPECIES; ++s) A.layout_info[4 + s] = row / ANI_TILE_ROWS;
+  }
+  __syncthreads();
+  const int n_tiles_cap = A.rows_cap / ANI_TILE_ROWS;
+  for (int t = tid; t < n_tiles_cap; t += blockDim.x) {
+    const int r = t * ANI_TILE_ROWS;
+    int sp = -1;
+    for (int s = 0; s < S; ++s)
+      if (r >= s_base[s] && r < s_base[s + 1] && r < s_base[s] + s_tot[s]) sp = s;
+    A.tile_species[t] = sp;
+  }
+  for (int r = tid; r < A.rows_cap; r += blockDim.x) A.row_atom[r] = -1;
+  if (A.zero_f64)
+    for (int k = tid; k < A.zero_f64_count; k += blockDim.x) A.zero_f64[k] = 0.0;
+}
+
 }  // namespace ani
 
 using namespace ani;
@@ -521,6 +802,72 @@ extern "C" int ani_b200_species_layout(const float* spos, const ani_grid* grid, 
                                     row_atom, layout_info);
   k_layout_assign<<<n_chunks, LAYOUT_CHUNK, 0, st>>>(sp4, grid, lo, hi, num_species, chunk_hist, species_base,
                                                      row_of, row_atom);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
+                                     const float* cell, int pbc, int mode, float cutoff, int max_bins,
+                                     ani_grid* grid, int32_t* bin_start, int32_t* sorted_orig,
+                                     int32_t* orig_to_sorted, float* spos, int32_t* sbin, float* bucket_ranges,
+                                     int lo, int hi, int num_species, int rows_cap, int32_t* row_of,
+                                     int32_t* row_atom, int32_t* tile_species, int32_t* layout_info, int n_shf_r,
+                                     int angular_sub, int out_dim, int ldx, int32_t* aev_blocks, float* zero_f32,
+                                     int zero_f32_count, double* zero_f64, int zero_f64_count,
+                                     int32_t* scratch_i32, int32_t* status, void* stream) {
+  if (!coords || !species || !grid || !bin_start || !sorted_orig || !orig_to_sorted || !spos || !sbin ||
+      !row_of || !row_atom || !tile_species || !layout_info || !aev_blocks || !scratch_i32 || !status)
+    return ANI_ERR_BAD_ARG;
+  if (n_conf < 1 || n_per_conf < 1 || cutoff <= 0.f || max_bins < 2) return ANI_ERR_BAD_ARG;
+  if (mode == 0 && n_conf != 1) return ANI_ERR_UNSUPPORTED;
+  if (mode == 1 && (pbc || n_conf + 1 > max_bins)) return ANI_ERR_UNSUPPORTED;
+  if (mode != 0 && mode != 1) return ANI_ERR_BAD_ARG;
+  if (pbc && !cell) return ANI_ERR_BAD_ARG;
+  const long long n_ll = (long long)n_conf * n_per_conf;
+  if (n_ll >= (1ll << ANI_IMG_SHIFT)) return ANI_ERR_UNSUPPORTED;
+  const int n = (int)n_ll;
+  if (num_species < 1 || num_species > ANI_MAX_SPECIES || lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
+  if (rows_cap % ANI_TILE_ROWS != 0) return ANI_ERR_BAD_ARG;
+  if ((long long)rows_cap < (long long)(hi - lo) + (long long)num_species * (ANI_TILE_ROWS - 1)) return ANI_ERR_BAD_ARG;
+  if (n_shf_r < 1 || angular_sub < 1 || ldx % 32 || out_dim > ldx) return ANI_ERR_BAD_ARG;
+  if ((zero_f32_count > 0 && !zero_f32) || (zero_f64_count > 0 && !zero_f64)) return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PrepArgs A;
+  A.coords = coords; A.species = species; A.n = n; A.n_conf = n_conf; A.n_per_conf = n_per_conf;
+  A.cell = cell; A.pbc = pbc; A.mode = mode; A.cutoff = cutoff; A.max_bins = max_bins;
+  A.grid = grid; A.bin_start = bin_start; A.sorted_orig = sorted_orig; A.orig_to_sorted = orig_to_sorted;
+  A.spos = reinterpret_cast<float4*>(spos); A.sbin = sbin;
+  A.ranges = (bucket_ranges && mode == 0) ? reinterpret_cast<float4*>(bucket_ranges) : nullptr;
+  A.lo = lo; A.hi = hi; A.S = num_species; A.rows_cap = rows_cap;
+  A.row_of = row_of; A.row_atom = row_atom; A.tile_species = tile_species; A.layout_info = layout_info;
+  A.n_shf_r = n_shf_r; A.angular_sub = angular_sub; A.out_dim = out_dim; A.ldx = ldx; A.blocks = aev_blocks;
+  A.n_chunks = max(1, (hi - lo + LAYOUT_CHUNK - 1) / LAYOUT_CHUNK);
+  // scratch: bin_of[n] slot[n] tmp_list[n] | zeroed: bin_count[max_bins+1] counter present chunk_hist | species_base
+  A.bin_of = scratch_i32;
+  A.slot = scratch_i32 + n;
+  A.tmp_list = scratch_i32 + 2 * (size_t)n;
+  A.bin_count = scratch_i32 + 3 * (size_t)n;
+  A.counter = A.bin_count + max_bins + 1;
+  A.present = A.counter + 1;
+  A.chunk_hist = A.present + 1;
+  A.species_base = A.chunk_hist + (size_t)(A.n_chunks + 1) * ANI_MAX_SPECIES;
+  A.zero_f32 = zero_f32_count > 0 ? zero_f32 : nullptr; A.zero_f32_count = zero_f32_count;
+  A.zero_f64 = zero_f64_count > 0 ? zero_f64 : nullptr; A.zero_f64_count = zero_f64_count;
+  A.status = status;
+  A.inline_setup = (mode == 1 || pbc) ? 1 : 0;
+  const size_t zeroed = (size_t)(max_bins + 1) + 2 + (size_t)(A.n_chunks + 1) * ANI_MAX_SPECIES;
+  cudaMemsetAsync(A.bin_count, 0, sizeof(int32_t) * zeroed, st);
+  if (!A.inline_setup)
+    k_grid_setup<<<1, 1024, 0, st>>>(coords, species, n, n_conf, n_per_conf, cell, pbc, mode, cutoff, max_bins,
+                                     grid, status);
+  const int nb = (n + 255) / 256;
+  k_prep_assign<<<nb, 256, 0, st>>>(A);
+  const long long t2 = A.ranges ? max((long long)n, (long long)(max_bins - 1) * 27) : (long long)n;
+  k_prep_scatter<<<(int)((t2 + 255) / 256), 256, 0, st>>>(A);
+  k_prep_finalize<<<nb, 256, 0, st>>>(A);
+  k_prep_layout<<<1, 1024, 0, st>>>(A);
+  k_layout_assign<<<A.n_chunks, LAYOUT_CHUNK, 0, st>>>(A.spos, grid, lo, hi, num_species, A.chunk_hist, A.species_base,
+                                                      row_of, row_atom);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

@@ -400,9 +400,9 @@ class Engine:
                 self._graphs[key] = graph
                 graph.replay()
         # kernels launched by this library in one step (memsets excluded):
-        #   build_cells 5, layout 3 + 2 (active blocks), aev fwd 1, mlp 3 (+3 bwd), aev bwd 1, reduce 1
-        # grid 6, layout 3, live blocks 2, AEV fwd 1, GEMM fwd 3, (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
-        self.launches_per_step = 6 + 3 + 2 + 1 + 3 + (5 if want_grad else 0) + 1
+        # prepare 5 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
+        # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
+        self.launches_per_step = 5 + (0 if (pbc or n_conf > 1) else 1) + 1 + 3 + (5 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
                           ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
@@ -415,18 +415,17 @@ class Engine:
         st = torch.cuda.current_stream(self.device).cuda_stream
         cell_ptr = ptr(ws.cell) if pbc else None
         mode = 0 if n_conf == 1 else 1
-        self._timed("build_cells", lambda: L.ani_b200_build_cells(
-            ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
-            self.consts.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
-            ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges), ptr(ws.scratch),
-            ptr(ws.status), st))
-        self._timed("species_layout", lambda: L.ani_b200_species_layout(
-            ptr(ws.spos), ptr(ws.grid), n, lo, hi, self.consts.num_species, ws.rows_cap, ptr(ws.row_of),
-            ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info), ptr(ws.scratch), st))
         c = self.consts
-        self._timed("species_layout", lambda: L.ani_b200_active_aev_blocks(
-            ptr(ws.spos), ptr(ws.grid), n, c.num_species, len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim,
-            self.nets.ldx, ptr(ws.aev_blocks), ptr(ws.scratch), st))
+        # bucket grid + species-grouped row layout + live AEV column blocks (+ zero-fill of the force
+        # accumulator): one fused entry point, five launches
+        self._timed("prepare_step", lambda: L.ani_b200_prepare_step(
+            ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
+            c.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
+            ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges),
+            lo, hi, c.num_species, ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
+            ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
+            ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0, None, 0,
+            ptr(ws.scratch), ptr(ws.status), st))
         self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
             C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin),
             ptr(ws.bucket_ranges), ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
@@ -437,7 +436,6 @@ class Engine:
             ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
             int(want_grad), st))
         if want_grad:
-            ws.grad.zero_()
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
