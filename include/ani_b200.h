@@ -153,9 +153,13 @@ int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
 
 /* 4. AEV backward: grad_aev (same row layout as the forward output) -> dE/dcoords,         */
 /*    accumulated (+=, float atomics) into grad_coords f32[n*3] in flat INPUT order.         */
+/*    species_mask (as in the forward, or NULL): the gradient blocks of element pairs that   */
+/*    do not occur in the system are not read (the block-sparse MLP backward leaves them     */
+/*    unwritten).                                                                             */
 int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
-                          const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
-                          const float* grad_aev, int ldx, const int32_t* nbr_cnt,
+                          const int32_t* sorted_orig, const int32_t* species_mask, int n, int lo,
+                          int hi, const int32_t* row_of, const float* grad_aev, int ldx,
+                          const int32_t* nbr_cnt,
                           const int32_t* nbr_list, int nbr_cap, float* grad_coords,
                           int32_t* status, void* stream);
 

@@ -66,7 +66,9 @@ struct WarpSmem {
   float* afc;            // [ANI_MAX_ANG] fc(R; Rca)
   float* afcd;           // [ANI_MAX_ANG] d fc / dR (backward)
   int32_t* seg;          // [ANI_MAX_SPECIES + 1] species segments of aidx
-  float* rad;            // forward: [2*RL] accumulators; backward: g_rad [RL] + g_ang [32*gstride]
+  int32_t* seg_all;      // [ANI_MAX_SPECIES + 1] species segments of ord (forward)
+  unsigned char* ord;    // [cap] all neighbours, species-sorted (forward)
+  float* rad;            // forward: [2*RL] accumulators; backward: g_rad [RL] + g_ang [pairs][36]
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(int cap, int rad_floats, bool backward) {
@@ -76,7 +78,8 @@ __host__ __device__ inline size_t warp_smem_bytes(int cap, int rad_floats, bool 
   b += ANI_MAX_ANG;                          // aidx
   b = (b + 15) / 16 * 16;
   b += (size_t)ANI_MAX_ANG * 4 * 2;          // afc, afcd
-  b += 16 * 4;                               // seg (padded)
+  b += 2 * 16 * 4;                           // seg, seg_all (padded)
+  b += ((size_t)cap + 15) / 16 * 16;         // ord
   b += (size_t)rad_floats * 4;
   return (b + 15) / 16 * 16;
 }
@@ -103,6 +106,10 @@ __device__ __forceinline__ WarpSmem carve(unsigned char* base, int cap, bool bac
   p += ANI_MAX_ANG * 4;
   s.seg = reinterpret_cast<int32_t*>(p);
   p += 16 * 4;
+  s.seg_all = reinterpret_cast<int32_t*>(p);
+  p += 16 * 4;
+  s.ord = p;
+  p += ((size_t)cap + 15) / 16 * 16;
   s.rad = reinterpret_cast<float*>(p);
   return s;
 }
@@ -173,6 +180,48 @@ __device__ __forceinline__ int build_angular_list(const ani_aev_params& P, const
   }
   __syncwarp();
   return total;
+}
+
+// Counting sort (by species) of ALL neighbours: ord[] = neighbour indices grouped by species,
+// seg_all[] = segment starts.  The radial block then accumulates one species segment at a time in
+// registers (no shared-memory read-modify-write chain).
+__device__ __forceinline__ void build_species_order(const ani_aev_params& P, const WarpSmem& s, int cnt, int lane) {
+  const int S = P.num_species;
+  int seg_cnt[ANI_MAX_SPECIES];
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) seg_cnt[k] = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int n = base + lane;
+    const int sp = n < cnt ? (int)s.nsp[n] : -1;
+#pragma unroll
+    for (int k = 0; k < ANI_MAX_SPECIES; ++k) seg_cnt[k] += __popc(__ballot_sync(ANI_FULL_MASK, sp == k));
+  }
+  int seg_start[ANI_MAX_SPECIES + 1];
+  seg_start[0] = 0;
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) seg_start[k + 1] = seg_start[k] + seg_cnt[k];
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k <= ANI_MAX_SPECIES; ++k)
+      if (k <= S) s.seg_all[k] = seg_start[k];
+  }
+  int run[ANI_MAX_SPECIES];
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) run[k] = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  for (int base = 0; base < cnt; base += 32) {
+    const int n = base + lane;
+    const int sp = n < cnt ? (int)s.nsp[n] : -1;
+    int pos = -1;
+#pragma unroll
+    for (int k = 0; k < ANI_MAX_SPECIES; ++k) {
+      const unsigned m = __ballot_sync(ANI_FULL_MASK, sp == k);
+      if (sp == k) pos = seg_start[k] + run[k] + __popc(m & lt);
+      run[k] += __popc(m);
+    }
+    if (pos >= 0) s.ord[pos] = (unsigned char)n;
+  }
+  __syncwarp();
 }
 
 // q-th unordered pair (a < b) of a triangle
@@ -313,24 +362,28 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     if (nbr_list) nbr_list[(size_t)i * cap + n] = s.nj[n];
     s.nfc[n] = cutoff_value(s.nd[n].w, P.rcr, P.cutoff_kind);
   }
-  for (int t = lane; t < 2 * RL; t += 32) s.rad[t] = 0.f;
   __syncwarp();
 
-  // ---- 2. radial block: lane = (shift m, neighbour parity h); the two parities own separate
-  //         accumulator arrays, lanes of one parity hit distinct addresses -> no atomics
+  // ---- 2. radial block: lane = (shift m, neighbour parity h).  The neighbours are grouped by
+  //         species first, so each (species, shift) sum lives in a register and goes straight to
+  //         the output: no shared-memory accumulators, no atomics
+  build_species_order(P, s, cnt, lane);
   {
     const int lpn = (nR <= 16) ? 16 : 32;
     const int halves = 32 / lpn;
     const int m = lane % lpn, h = lane / lpn;
     const float shf = P.shf_r[m < nR ? m : 0];
-    for (int n = h; n < cnt; n += halves) {
-      const float R = s.nd[n].w;
-      const float d = R - shf;
-      const float v = 0.25f * fast_exp(-P.eta_r * d * d) * s.nfc[n];
-      if (m < nR) s.rad[h * RL + s.nsp[n] * nR + m] += v;
+    for (int sp = 0; sp < S; ++sp) {
+      const int k1 = s.seg_all[sp + 1];
+      float acc = 0.f;
+      for (int k = s.seg_all[sp] + h; k < k1; k += halves) {
+        const int n = s.ord[k];
+        const float d = s.nd[n].w - shf;
+        acc = fmaf(fast_exp(-P.eta_r * d * d), s.nfc[n], acc);
+      }
+      if (halves == 2) acc += __shfl_xor_sync(ANI_FULL_MASK, acc, 16);
+      if (h == 0 && m < nR) store_feature(sp * nR + m, 0.25f * acc);
     }
-    __syncwarp();
-    for (int t = lane; t < RL; t += 32) store_feature(t, s.rad[t] + (halves == 2 ? s.rad[RL + t] : 0.f));
   }
 
   // ---- 3. angular block
@@ -376,14 +429,14 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
           const float4 dj = s.nd[s.aidx[ja]], dk = s.nd[s.aidx[jb]];
           const float w2 = 2.0f * s.afc[ja] * s.afc[jb];
           const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
-          const float c = 0.95f * dot / fmaxf(dj.w * dk.w, 1e-10f);
-          const float sn = sqrtf(fmaxf(1.0f - c * c, 0.f));
+          const float c = 0.95f * dot * fast_rcp(fmaxf(dj.w * dk.w, 1e-10f));
+          const float sn = fast_sqrt(fmaxf(1.0f - c * c, 0.f));
           const float rbar = 0.5f * (dj.w + dk.w);
           float f1[NZ];
 #pragma unroll
           for (int z = 0; z < NZ; ++z) {
             const float base = fmaxf(0.5f * (1.0f + c * cz[z] + sn * sz[z]), 0.f);
-            f1[z] = exp2f(P.zeta * log2f(base));
+            f1[z] = fast_exp2(P.zeta * fast_log2(base));  // base^zeta; base = 0 -> ex2(-inf) = 0
           }
 #pragma unroll
           for (int a = 0; a < NA; ++a) {
@@ -409,7 +462,8 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
                    const float4* __restrict__ spos, const int32_t* __restrict__ sorted_orig, int lo, int hi,
                    const int32_t* __restrict__ row_of, const float* __restrict__ gaev, int ldx,
                    const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ nbr_list, const ExplicitNbrs ex,
-                   int cap, float* __restrict__ grad_coords, int32_t* __restrict__ status, size_t warp_bytes) {
+                   const int32_t* __restrict__ species_mask, int cap, float* __restrict__ grad_coords,
+                   int32_t* __restrict__ status, size_t warp_bytes) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -421,15 +475,21 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const int S = P.num_species;
   const int nR = P.n_shf_r;
   const int RL = S * nR;
-  const int NP = S * (S + 1) / 2;
-  const int gstride = NP | 1;  // odd stride -> conflict-free lane-varying species-pair lookups
+  constexpr int GSTRIDE = 36;  // floats per species-pair row: 16-byte aligned, rows 4 banks apart
   float* g_rad = s.rad;
-  float* g_ang = s.rad + RL;
+  float* g_ang = s.rad + ((RL + 3) & ~3);
 
-  // ---- 1. upstream gradient row -> shared memory (angular part transposed: [feature][pair])
+  // ---- 1. upstream gradient row -> shared memory ([pair][32 features]); element pairs that do
+  //         not occur in the system are never looked up (and never written by the MLP backward)
   const size_t row = (size_t)row_of[i] * ldx;
   for (int t = lane; t < RL; t += 32) g_rad[t] = gaev[row + t];
-  for (int pp = 0; pp < NP; ++pp) g_ang[lane * gstride + pp] = gaev[row + RL + pp * 32 + lane];
+  {
+    const unsigned present = species_mask ? (unsigned)species_mask[0] : 0xffffffffu;
+    int pp = 0;
+    for (int s1 = 0; s1 < S; ++s1)
+      for (int s2 = s1; s2 < S; ++s2, ++pp)
+        if ((present >> s1) & (present >> s2) & 1u) g_ang[pp * GSTRIDE + lane] = gaev[row + RL + pp * 32 + lane];
+  }
 
   // ---- 2. geometry of the stored neighbours
   const float4 pi = spos[i];
@@ -463,32 +523,23 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   }
   __syncwarp();
 
-  // ---- 3. radial: dE/dR_n = sum_m g[s_n, m] * (G' fc + G fc'), then along the unit vector
-  {
-    const int lpn = (nR <= 16) ? 16 : 32;
-    const int halves = 32 / lpn;
-    const int m = lane % lpn, h = lane / lpn;
-    const float shf = P.shf_r[m < nR ? m : 0];
-    for (int base = 0; base < cnt; base += halves) {
-      const int n = base + h;
-      const bool valid = n < cnt;
-      float contrib = 0.f;
-      float4 d = make_float4(0.f, 0.f, 0.f, 1.f);
-      if (valid) {
-        d = s.nd[n];
-        const float fc = s.nfc[n], dfc = s.fgrad[3 * n];
-        const float x = d.w - shf;
-        const float G = 0.25f * fast_exp(-P.eta_r * x * x);
-        if (m < nR) contrib = g_rad[s.nsp[n] * nR + m] * G * (-2.0f * P.eta_r * x * fc + dfc);
-      }
-      for (int o = lpn / 2; o > 0; o >>= 1) contrib += __shfl_xor_sync(ANI_FULL_MASK, contrib, o);
-      if (valid && m == 0) {
-        const float sc = d.w > 1e-10f ? contrib / d.w : 0.f;
-        s.fgrad[3 * n + 0] = sc * d.x;
-        s.fgrad[3 * n + 1] = sc * d.y;
-        s.fgrad[3 * n + 2] = sc * d.z;
-      }
+  // ---- 3. radial: dE/dR_n = sum_m g[s_n, m] * (G' fc + G fc'), then along the unit vector.
+  //         Lane = neighbour, serial over the shifts: no cross-lane reduction at all.
+  for (int n = lane; n < cnt; n += 32) {
+    const float4 d = s.nd[n];
+    const float fc = s.nfc[n], dfc = s.fgrad[3 * n];
+    const float* __restrict__ gr = g_rad + s.nsp[n] * nR;
+    float acc = 0.f;
+#pragma unroll 4
+    for (int m = 0; m < nR; ++m) {
+      const float x = d.w - P.shf_r[m];
+      const float G = 0.25f * fast_exp(-P.eta_r * x * x);
+      acc = fmaf(gr[m] * G, fmaf(-2.0f * P.eta_r * x, fc, dfc), acc);
     }
+    const float sc = d.w > 1e-10f ? acc * fast_rcp(d.w) : 0.f;
+    s.fgrad[3 * n + 0] = sc * d.x;
+    s.fgrad[3 * n + 1] = sc * d.y;
+    s.fgrad[3 * n + 2] = sc * d.z;
   }
   __syncwarp();
 
@@ -508,37 +559,47 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     auto pair_sums = [&](const float4& dj, const float4& dk, int pidx, float& cosT, float& inv_rr, float& S0,
                          float& S1, float& S2) {
       const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
-      inv_rr = 1.0f / fmaxf(dj.w * dk.w, 1e-10f);
+      inv_rr = fast_rcp(fmaxf(dj.w * dk.w, 1e-10f));
       cosT = dot * inv_rr;
       const float c = 0.95f * cosT;
-      const float sn = sqrtf(fmaxf(1.0f - c * c, 0.f));
-      const float c_over_s = c / sn;
+      const float sn = fast_sqrt(fmaxf(1.0f - c * c, 0.f));
+      const float c_over_s = c * fast_rcp(sn);
       const float rbar = 0.5f * (dj.w + dk.w);
-      float f2[NA], f2p[NA];
+      // t_z = sum_a g[a,z] f2[a],  u_z = sum_a g[a,z] f2'[a]: the 32 upstream values of this pair are
+      // one 16-byte-aligned row -> 8 vector loads
+      const float4* __restrict__ gp = reinterpret_cast<const float4*>(g_ang + pidx * GSTRIDE);
+      float tz[NZ], uz[NZ];
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) tz[z] = uz[z] = 0.f;
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const float d = rbar - shfA[a];
-        f2[a] = fast_exp(-P.eta_a * d * d);
-        f2p[a] = -2.0f * P.eta_a * d * f2[a];
+        const float f2 = fast_exp(-P.eta_a * d * d);
+        const float f2p = -2.0f * P.eta_a * d * f2;
+#pragma unroll
+        for (int q = 0; q < NZ / 4; ++q) {
+          const float4 gv = gp[a * (NZ / 4) + q];
+          tz[4 * q + 0] = fmaf(gv.x, f2, tz[4 * q + 0]);
+          tz[4 * q + 1] = fmaf(gv.y, f2, tz[4 * q + 1]);
+          tz[4 * q + 2] = fmaf(gv.z, f2, tz[4 * q + 2]);
+          tz[4 * q + 3] = fmaf(gv.w, f2, tz[4 * q + 3]);
+          uz[4 * q + 0] = fmaf(gv.x, f2p, uz[4 * q + 0]);
+          uz[4 * q + 1] = fmaf(gv.y, f2p, uz[4 * q + 1]);
+          uz[4 * q + 2] = fmaf(gv.z, f2p, uz[4 * q + 2]);
+          uz[4 * q + 3] = fmaf(gv.w, f2p, uz[4 * q + 3]);
+        }
       }
       S0 = S1 = S2 = 0.f;
 #pragma unroll
       for (int z = 0; z < NZ; ++z) {
-        float tz = 0.f, uz = 0.f;
-#pragma unroll
-        for (int a = 0; a < NA; ++a) {
-          const float gv = g_ang[(a * NZ + z) * gstride + pidx];
-          tz += gv * f2[a];
-          uz += gv * f2p[a];
-        }
         const float base = fmaxf(0.5f * (1.0f + c * cz[z] + sn * sz[z]), 0.f);
-        const float lg = log2f(base);
-        const float f1 = exp2f(P.zeta * lg);
-        const float pw1 = exp2f((P.zeta - 1.0f) * lg);
+        const float lg = fast_log2(base);
+        const float f1 = fast_exp2(P.zeta * lg);
+        const float pw1 = fast_exp2((P.zeta - 1.0f) * lg);
         const float f1p = P.zeta * pw1 * (0.475f * (cz[z] - c_over_s * sz[z]));
-        S0 += f1 * tz;
-        S1 += f1p * tz;
-        S2 += f1 * uz;
+        S0 = fmaf(f1, tz[z], S0);
+        S1 = fmaf(f1p, tz[z], S1);
+        S2 = fmaf(f1, uz[z], S2);
       }
     };
     int lpr = 1;
@@ -564,7 +625,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
         fcj = s.afc[j];
         dfcj = s.afcd[j];
         sj = s.nsp[nj_];
-        inv_rj = dj.w > 1e-10f ? 1.0f / dj.w : 0.f;
+        inv_rj = dj.w > 1e-10f ? fast_rcp(dj.w) : 0.f;
       }
       const int steps = (half_n + lpr - 1) / lpr;
       for (int it = 0; it < steps; ++it) {
@@ -577,7 +638,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
           const int nk_ = s.aidx[k];
           const float4 dk = s.nd[nk_];
           const float fck = s.afc[k], dfck = s.afcd[k];
-          const float inv_rk = dk.w > 1e-10f ? 1.0f / dk.w : 0.f;
+          const float inv_rk = dk.w > 1e-10f ? fast_rcp(dk.w) : 0.f;
           float cosT, inv_rr, S0, S1, S2;
           pair_sums(dj, dk, pair_index(sj, (int)s.nsp[nk_], S), cosT, inv_rr, S0, S1, S2);
           // feature = 2 f1 f2 fcj fck (once per unordered pair): its derivative with respect to
@@ -628,7 +689,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
           const float4 dj = s.nd[nj_];
           const float fcj = s.afc[j], dfcj = s.afcd[j];
           const int sj = s.nsp[nj_];
-          const float inv_rj = dj.w > 1e-10f ? 1.0f / dj.w : 0.f;
+          const float inv_rj = dj.w > 1e-10f ? fast_rcp(dj.w) : 0.f;
           for (int k = 0; k < n_ang; ++k) {
             if (k == j) continue;
             const int nk_ = s.aidx[k];
@@ -813,7 +874,7 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
   if (layout == 1 && ldx % 16) return ANI_ERR_BAD_ARG;
   if (hi == lo) return ANI_OK;
   const int RL = params->num_species * params->n_shf_r;
-  const size_t wb = warp_smem_bytes(nbr_cap, 2 * RL, false);
+  const size_t wb = warp_smem_bytes(nbr_cap, 0, false);
   const size_t smem = wb * AEV_WARPS;
   const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
   cudaStream_t st = (cudaStream_t)stream;
@@ -837,7 +898,8 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
 static int launch_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
                                const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
                                const float* grad_aev, int ldx, const int32_t* nbr_cnt, const int32_t* nbr_list,
-                               ExplicitNbrs ex, int nbr_cap, float* grad_coords, int32_t* status, void* stream) {
+                               ExplicitNbrs ex, const int32_t* species_mask, int nbr_cap, float* grad_coords,
+                               int32_t* status, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!grid || !spos || !sorted_orig || !row_of || !grad_aev || !grad_coords || !status) return ANI_ERR_BAD_ARG;
@@ -847,7 +909,7 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
   const int S = params->num_species;
   const int RL = S * params->n_shf_r;
   const int NP = S * (S + 1) / 2;
-  const size_t wb = warp_smem_bytes(nbr_cap, RL + 32 * (NP | 1), true);
+  const size_t wb = warp_smem_bytes(nbr_cap, ((RL + 3) & ~3) + 36 * NP, true);
   const size_t smem = wb * AEV_WARPS;
   const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
   cudaStream_t st = (cudaStream_t)stream;
@@ -856,12 +918,12 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
     auto k = k_aev_backward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, ex, nbr_cap, grad_coords, status, wb);
+                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb);
   } else {
     auto k = k_aev_backward<4, 8>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, ex, nbr_cap, grad_coords, status, wb);
+                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb);
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
@@ -916,15 +978,16 @@ extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid
 }
 
 extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
-                                     const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
-                                     const float* grad_aev, int ldx, const int32_t* nbr_cnt,
+                                     const int32_t* sorted_orig, const int32_t* species_mask, int n, int lo, int hi,
+                                     const int32_t* row_of, const float* grad_aev, int ldx, const int32_t* nbr_cnt,
                                      const int32_t* nbr_list, int nbr_cap, float* grad_coords, int32_t* status,
                                      void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!nbr_cnt || !nbr_list) return ANI_ERR_BAD_ARG;
   return launch_aev_backward(params, grid, spos, sorted_orig, n, lo, hi, row_of, grad_aev, ldx, nbr_cnt, nbr_list,
-                             ExplicitNbrs{nullptr, nullptr, nullptr}, nbr_cap, grad_coords, status, stream);
+                             ExplicitNbrs{nullptr, nullptr, nullptr}, species_mask, nbr_cap, grad_coords, status,
+                             stream);
 }
 
 extern "C" int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, const float* diff_vectors,
@@ -963,8 +1026,8 @@ extern "C" int ani_b200_aev_backward_rows(const ani_aev_params* params, const an
                                           int ldx, int nbr_cap, float* grad_coords, int32_t* status, void* stream) {
   if (!row_start || !row_j || !row_d) return ANI_ERR_BAD_ARG;
   return launch_aev_backward(params, grid, spos, sorted_orig, n, 0, n, row_of, grad_aev, ldx, nullptr, nullptr,
-                             ExplicitNbrs{row_start, row_j, reinterpret_cast<const float4*>(row_d)}, nbr_cap,
-                             grad_coords, status, stream);
+                             ExplicitNbrs{row_start, row_j, reinterpret_cast<const float4*>(row_d)}, nullptr,
+                             nbr_cap, grad_coords, status, stream);
 }
 
 extern "C" int ani_b200_half_neighbor_count(const ani_grid* grid, const int32_t* bin_start, const float* spos,

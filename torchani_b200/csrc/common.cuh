@@ -39,6 +39,29 @@ __device__ __forceinline__ float fast_exp(float x) {
   return e;
 }
 
+// single-instruction MUFU forms (1-2 ulp): the IEEE-exact library versions cost 8-35 instructions
+// each and sat on the issue-bound inner loops of the AEV kernels
+__device__ __forceinline__ float fast_exp2(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float fast_log2(float x) {
+  float e;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float e;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x));
+  return e;
+}
+
 // index of the unordered species pair (a, b) in the row-major upper triangle of an SxS
 // matrix (aev/_computer.py:184-191 == csrc/aev.cu:23-29)
 __device__ __forceinline__ int pair_index(int a, int b, int S) {
@@ -48,7 +71,7 @@ __device__ __forceinline__ int pair_index(int a, int b, int S) {
 
 // cutoff function and derivative (cutoffs.py:70-101; derivative forms as aev.cu:141-178)
 __device__ __forceinline__ float cutoff_value(float r, float rc, int kind) {
-  if (kind == 0) return 0.5f * cosf(r * (3.14159265358979323846f / rc)) + 0.5f;
+  if (kind == 0) return 0.5f * __cosf(r * (3.14159265358979323846f / rc)) + 0.5f;  // argument in [0, pi]: |err| < 5e-7
   float x = r / rc;
   float den = fmaxf(1e-10f, 1.0f - x * x);
   return expf(1.0f - 1.0f / den);
@@ -58,7 +81,7 @@ __device__ __forceinline__ void cutoff_value_grad(float r, float rc, int kind, f
   if (kind == 0) {
     float s, c;
     float a = 3.14159265358979323846f / rc;
-    sincosf(r * a, &s, &c);
+    __sincosf(r * a, &s, &c);  // argument in [0, pi]
     f = 0.5f * c + 0.5f;
     df = -0.5f * a * s;
   } else {

@@ -437,7 +437,8 @@ class Engine:
             int(want_grad), st))
         if want_grad:
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
-                C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig), n, lo, hi,
+                C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
+                ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
                 ptr(ws.grad), ptr(ws.status), st))
         self._timed("reduce_energies", lambda: L.ani_b200_reduce_energies(
