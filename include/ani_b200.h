@@ -137,7 +137,7 @@ int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, i
 /*                 the fused engine, flat input index for the AEVComputer API)               */
 /*      aev        layout 0: f32[rows][ldx], columns 0..out_dim-1 of the atom's row are      */
 /*                 overwritten.  layout 1: the "tiled operand" form the MLP consumes          */
-/*                 (see below; 2*rows_cap*ldx floats, rows_cap % 128 == 0, ldx % 16 == 0)      */
+/*                 (see below; 6*rows_cap*ldx bytes, rows_cap % 128 == 0, ldx % 32 == 0)      */
 /*      nbr_cnt    i32[n]; nbr_list i32[n*nbr_cap]: neighbours within Rcr of every processed  */
 /*                 atom as (sorted index | image code << 26); kept for the backward pass      */
 /*      bucket_ranges  output of ani_b200_build_cells or NULL (ranges are then derived on the   */
@@ -218,17 +218,18 @@ int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, 
 
 /* 6. Ensemble MLP forward + backward-to-input on the species-grouped AEV matrix.           */
 /*    Layer widths: in -> h1 -> h2 -> h3 -> 1, CELU(alpha) after the three hidden layers.    */
-/*    "Tiled operand" layout (both GEMM operands; fp32 accuracy on the tensor cores = 3xTF32):  */
-/*    every value is split into hi = x & 0xffffe000 (an exact TF32) and lo = x - hi.             */
-/*    * A operand / activation matrix [rows][cols] (rows % 128 == 0, cols % 16 == 0):            */
-/*        [row tile of 128][16-column block][hi: 128 rows x 64 B | lo: 128 rows x 64 B]          */
-/*    * B operand of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K], K padded    */
-/*      to a multiple of 16 with zeros):                                                         */
-/*        [member][n tile (256 rows, the last one shorter)][16-column block][hi bn x 64 B | lo]  */
-/*    In both, every 8-row x 64-byte group is in the tcgen05 SWIZZLE_64B order (16-byte chunk c  */
-/*    of row r sits at chunk position c ^ ((r >> 1) & 3)), i.e. exactly the shared-memory image  */
-/*    a K-major UMMA descriptor expects: one K-block of one tile is a contiguous byte range      */
-/*    that a single cp.async.bulk (TMA) moves into shared memory.                                */
+/*    "Tiled operand" layout (both GEMM operands; fp32 accuracy on the tensor cores = 3 x bf16):  */
+/*    every value is stored as three bfloat16 pieces x = p1 + p2 + p3 (round to nearest).         */
+/*    * A operand / activation matrix [rows][cols] (rows % 128 == 0, cols % 32 == 0), 6 B/element: */
+/*        [row tile of 128][32-column block][p1: 128 rows x 64 B | p2 | p3]          (24 KB blocks) */
+/*    * B operand of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K], N % 32 == 0,  */
+/*      K padded to a multiple of 32 with zeros):                                                  */
+/*        [member][n tile (256 rows, the last one shorter)][32-column block][p1 bn x 64 B | p2 | p3] */
+/*    In both, every 8-row x 64-byte group is in the tcgen05 SWIZZLE_64B order (16-byte chunk c    */
+/*    of row r sits at chunk position c ^ ((r >> 1) & 3)), i.e. exactly the shared-memory image    */
+/*    a K-major UMMA descriptor expects: one K-block of one tile is a contiguous byte range        */
+/*    that a single cp.async.bulk (TMA) moves into shared memory.  Hidden widths that are not       */
+/*    multiples of 32 are zero-padded by the packer (zero weights and biases: CELU(0) = 0).         */
 typedef struct ani_mlp_species {
   int32_t h1, h2, h3, pad_;
   const float* b1;   /* [M*h1]                                                                  */
@@ -236,12 +237,12 @@ typedef struct ani_mlp_species {
   const float* b3;   /* [M*h3]                                                                  */
   const float* w4;   /* [M][h3]                                                                 */
   const float* b4;   /* [M]                                                                     */
-  const float* t_f1; /* forward  layer 1: B = W1 stacked over members [M*h1][in_dim -> ldx]    */
-  const float* t_f2; /* forward  layer 2: per member B = W2_m [h2][h1]                          */
-  const float* t_f3; /* forward  layer 3: per member B = W3_m [h3][h2]                          */
-  const float* t_b3; /* backward layer 3: per member B = W3_m^T [h2][h3]                        */
-  const float* t_b2; /* backward layer 2: per member B = W2_m^T [h1][h2]                        */
-  const float* t_b1; /* backward layer 1: B = W1^T [ldx][M*h1]                                  */
+  const void* t_f1;  /* forward  layer 1: B = W1 stacked over members [M*h1][in_dim -> ldx]    */
+  const void* t_f2;  /* forward  layer 2: per member B = W2_m [h2][h1]                          */
+  const void* t_f3;  /* forward  layer 3: per member B = W3_m [h3][h2]                          */
+  const void* t_b3;  /* backward layer 3: per member B = W3_m^T [h2][h3]                        */
+  const void* t_b2;  /* backward layer 2: per member B = W2_m^T [h1][h2]                        */
+  const void* t_b1;  /* backward layer 1: B = W1^T [ldx][M*h1]                                  */
 } ani_mlp_species;
 
 typedef struct ani_mlp_model {
@@ -252,17 +253,17 @@ typedef struct ani_mlp_model {
   ani_mlp_species sp[ANI_MAX_SPECIES];
 } ani_mlp_model;
 
-/*    x            tiled operand, in: AEVs (ani_b200_aev_forward layout 1), 2*rows_cap*ldx f32 */
+/*    x            tiled operand, in: AEVs (ani_b200_aev_forward layout 1), 6*rows_cap*ldx bytes */
 /*    dx           f32[rows_cap][ldx] plain rows, out: dE/dAEV (may be NULL if !want_backward)  */
 /*    row_atom / layout_info: outputs of ani_b200_species_layout                                */
 /*    aev_blocks   output of ani_b200_active_aev_blocks or NULL (= every column is live).       */
 /*                 With a block list, layer 1 skips the dead K-blocks and dE/dAEV is written     */
 /*                 only for the live column blocks (the others keep their previous content).     */
-/*    act1/2/3     tiled operands 2*rows_cap*M*h{1,2,3}_max f32 (activations, then gradients)    */
+/*    act1/2/3     tiled operands, 6*rows_cap*M*h{1,2,3}_max bytes (activations, then gradients) */
 /*    e_member     f32[M][rows_cap]     per-member atomic energies                               */
-int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const float* x, float* dx, int rows_cap,
+int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
                                   const int32_t* row_atom, const int32_t* layout_info,
-                                  const int32_t* aev_blocks, float* act1, float* act2, float* act3,
+                                  const int32_t* aev_blocks, void* act1, void* act2, void* act3,
                                   float* e_member, int want_backward, void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */

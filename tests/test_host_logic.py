@@ -40,57 +40,78 @@ def test_unsupported_configurations_are_rejected_loudly():
         AtomicNetwork((1008, 256, 192, 160, 1), activation="gelu")
 
 
+def _bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
 def _untile(t, n, k):
-    """Inverse of engine.tile_b_operand (numpy, element-wise from the documented layout)."""
-    kp = (k + 15) // 16 * 16
-    nkb = kp // 16
-    t = t.numpy()
-    hi = np.zeros((n, kp), np.float32)
-    lo = np.zeros((n, kp), np.float32)
+    """Inverse of engine.tile_b_operand (numpy, element-wise from the documented layout of
+    include/ani_b200.h): returns the three bfloat16 pieces as float32 arrays."""
+    kp = (k + 31) // 32 * 32
+    nkb = kp // 32
+    t = t.view(torch.int16).numpy().view(np.uint16)
+    parts = [np.zeros((n, kp), np.float32) for _ in range(3)]
     for r in range(n):
         n0 = r // 256 * 256
         bn = min(256, n - n0)
         rr = r - n0
         for kb in range(nkb):
             for ch in range(4):
-                base = n0 * nkb * 32 + kb * bn * 32 + (rr // 8) * 128 + (rr % 8) * 16 + ((ch ^ ((rr >> 1) & 3)) * 4)
-                hi[r, kb * 16 + ch * 4: kb * 16 + ch * 4 + 4] = t[base: base + 4]
-                lo[r, kb * 16 + ch * 4: kb * 16 + ch * 4 + 4] = t[base + bn * 16: base + bn * 16 + 4]
-    return hi, lo
+                # element offsets: n tile base, K-block base (3 pieces of bn x 32), 8-row group, row, swizzled chunk
+                base = n0 * nkb * 96 + kb * bn * 96 + (rr // 8) * 256 + (rr % 8) * 32 + ((ch ^ ((rr >> 1) & 3)) * 8)
+                for p in range(3):
+                    parts[p][r, kb * 32 + ch * 8: kb * 32 + ch * 8 + 8] = _bf16_to_f32(
+                        t[base + p * bn * 32: base + p * bn * 32 + 8])
+    return parts
 
 
 def test_weight_packing_layout():
-    from torchani_b200.engine import PackedNetworks, tile_b_operand
-    # the tiled / split / swizzled B operand round-trips and hi + lo == x exactly
-    b = torch.randn(272, 40, generator=torch.Generator().manual_seed(0))
-    hi, lo = _untile(tile_b_operand(b), 272, 40)
-    assert hi.shape == (272, 48)                                      # K padded to a multiple of 16
-    assert np.array_equal((hi + lo)[:, :40], b.numpy()) and float(np.abs(hi[:, 40:]).max()) == 0.0
-    assert np.array_equal(hi.view(np.int32) & 0x1fff, np.zeros_like(hi, dtype=np.int32))  # exact TF32
-    assert np.abs(lo[:, :40]).max() <= np.abs(b.numpy()).max() * 2.0 ** -10
+    from torchani_b200.engine import PackedNetworks, tile_a_operand, tile_b_operand, untile_a_operand
+    # the tiled / split / swizzled B operand round-trips and p1 + p2 + p3 == x to fp32 rounding
+    b = torch.randn(288, 40, generator=torch.Generator().manual_seed(0))
+    p1, p2, p3 = _untile(tile_b_operand(b), 288, 40)
+    assert p1.shape == (288, 64)                                      # K padded to a multiple of 32
+    total = (p1.astype(np.float64) + p2 + p3)[:, :40]
+    assert np.abs(total - b.numpy()).max() <= np.abs(b.numpy()).max() * 2.0 ** -24
+    assert float(np.abs(p1[:, 40:]).max()) == 0.0
+    assert np.abs(p2).max() <= np.abs(b.numpy()).max() * 2.0 ** -8
+    assert np.abs(p3).max() <= np.abs(b.numpy()).max() * 2.0 ** -16
+    # A operand: tile / untile round trip
+    x = torch.randn(256, 96, generator=torch.Generator().manual_seed(1))
+    back = untile_a_operand(tile_a_operand(x), 256, 96)
+    assert float((back - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -23
     m = oracle_model("2x", members=3)
     w = [[wm[s] for s in m.symbols] for wm in m.weights]
     nets = PackedNetworks(w, 1008, torch.device("cpu"))
     assert nets.ldx == 1024 and nets.num_members == 3 and nets.dims[0] == (256, 192, 160)
     names = ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
     sp0 = dict(zip(names, nets._keep[:11]))
+
+    def close(parts, ref):
+        tot = parts[0].astype(np.float64) + parts[1] + parts[2]
+        return np.abs(tot - ref).max() <= max(np.abs(ref).max(), 1e-30) * 2.0 ** -24
+
     # layer 1: members stacked along N, K padded to ldx with zeros
-    hi, lo = _untile(sp0["t_f1"][: 256 * 64 * 32], 256, 1024)       # first n tile = member 0
-    assert np.array_equal((hi + lo)[:, :1008], m.weights[0]["H"][0][0].numpy())
-    assert float(np.abs(hi[:, 1008:]).max()) == 0.0
+    parts = _untile(sp0["t_f1"][: 256 * 32 * 96], 256, 1024)         # first n tile = member 0
+    assert close([q[:, :1008] for q in parts], m.weights[0]["H"][0][0].numpy())
+    assert float(np.abs(parts[0][:, 1008:]).max()) == 0.0
     # per-member layer 2 (forward: W2 [h2][h1]; backward: W2^T [h1][h2])
-    per = 192 * 16 * 32
-    hi, lo = _untile(sp0["t_f2"][2 * per: 3 * per], 192, 256)
-    assert np.array_equal(hi + lo, m.weights[2]["H"][1][0].numpy())
-    per = 256 * 12 * 32
-    hi, lo = _untile(sp0["t_b2"][per: 2 * per], 256, 192)
-    assert np.array_equal(hi + lo, m.weights[1]["H"][1][0].t().numpy())
+    per = 192 * 8 * 96
+    assert close(_untile(sp0["t_f2"][2 * per: 3 * per], 192, 256), m.weights[2]["H"][1][0].numpy())
+    per = 256 * 6 * 96
+    assert close(_untile(sp0["t_b2"][per: 2 * per], 256, 192), m.weights[1]["H"][1][0].t().numpy())
     assert torch.equal(sp0["w4"][2], m.weights[2]["H"][3][0][0])
-    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 16) * 32
+    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 32) * 96
     nets.set_active_members([0, 2])
     assert list(nets.model.member_scale)[:3] == [0.5, 0.0, 0.5]
     with pytest.raises(IndexError):
         nets.set_active_members([5])
+    # hidden widths that are not multiples of 32 (ANI-1x carbon: 144, 112, 96) are zero-padded
+    m1 = oracle_model("1x", members=2)
+    nets1 = PackedNetworks([[wm[s] for s in m1.symbols] for wm in m1.weights], 384, torch.device("cpu"))
+    c = list(m1.symbols).index("C")
+    assert nets1.dims[c] == (144, 112, 96)
+    assert (nets1.model.sp[c].h1, nets1.model.sp[c].h2, nets1.model.sp[c].h3) == (160, 128, 96)
 
 
 def test_model_tree_and_reference_state_dict_keys():

@@ -267,17 +267,19 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const int i = lo + blockIdx.x * AEV_WARPS + warp;
   if (i >= hi) return;
   const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, false);
-  // output: plain row-major rows, or the hi/lo-split tiled operand layout the GEMM consumes
+  // output: plain row-major rows, or the 3 x bf16 tiled operand layout the GEMM consumes
   const int out_row = row_of[i];
-  const int kblocks = ldx >> 4;
+  const int kblocks = ldx >> 5;
   auto store_feature = [&](int col, float v) {
     if (layout == 0) {
       aev[(size_t)out_row * ldx + col] = v;
     } else {
-      const size_t idx = opnd_index(out_row, col, kblocks);
-      const float vh = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-      aev[idx] = vh;
-      aev[idx + OPND_PART_BYTES / 4] = v - vh;
+      unsigned char* dst = reinterpret_cast<unsigned char*>(aev) + opnd_offset(out_row, col, kblocks);
+      unsigned short p1, p2, p3;
+      split3(v, p1, p2, p3);
+      *reinterpret_cast<unsigned short*>(dst) = p1;
+      *reinterpret_cast<unsigned short*>(dst + OPND_PART_BYTES) = p2;
+      *reinterpret_cast<unsigned short*>(dst + 2 * OPND_PART_BYTES) = p3;
     }
   };
   const int S = P.num_species;
@@ -871,7 +873,7 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
                       params->num_species * (params->num_species + 1) / 2 * 32;
   if (ldx < out_dim) return ANI_ERR_BAD_ARG;
   if (layout != 0 && layout != 1) return ANI_ERR_BAD_ARG;
-  if (layout == 1 && ldx % 16) return ANI_ERR_BAD_ARG;
+  if (layout == 1 && ldx % 32) return ANI_ERR_BAD_ARG;
   if (hi == lo) return ANI_OK;
   const int RL = params->num_species * params->n_shf_r;
   const size_t wb = warp_smem_bytes(nbr_cap, 0, false);

@@ -108,20 +108,36 @@ __device__ __forceinline__ float3 image_shift(const ani_grid& g, int code) {
 }
 
 // ---- "tiled operand" layout shared by the AEV kernel (producer) and the tensor-core GEMM ----
-// An activation matrix [rows][cols] is stored per 128-row tile and 16-column block as
-// [hi 128 rows x 64 B | lo 128 rows x 64 B] (16 KB), every 8-row group in SWIZZLE_64B order.
-constexpr int OPND_ROW_BYTES = 64;
+// A matrix [rows][cols] is stored per 128-row tile and 32-column K-block as three bfloat16 pieces
+// (x = p1 + p2 + p3): [p1 128 rows x 64 B | p2 128 x 64 B | p3 128 x 64 B] (24 KB), every 8-row
+// group in SWIZZLE_64B order (16-byte chunk c of row r sits at position c ^ ((r >> 1) & 3)).
+constexpr int OPND_KB = 32;                                      // columns per K-block
+constexpr int OPND_PARTS = 3;
+constexpr int OPND_ROW_BYTES = 64;                               // 32 bf16
 constexpr int OPND_PART_BYTES = ANI_TILE_ROWS * OPND_ROW_BYTES;  // 8 KB
-constexpr int OPND_BLOCK_BYTES = 2 * OPND_PART_BYTES;            // 16 KB
-// byte offset of 16-byte chunk `ch` (0..3) of row `row` (0..127) inside the hi (or lo) part
+constexpr int OPND_BLOCK_BYTES = OPND_PARTS * OPND_PART_BYTES;   // 24 KB
+// byte offset of 16-byte chunk `ch` (0..3) of row `row` (0..127) inside one piece
 __device__ __forceinline__ uint32_t swz_off(int row, int ch) {
   return (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u + (uint32_t)((ch ^ ((row >> 1) & 3)) << 4);
 }
-// float index of element (row, col) of a tiled matrix with `kblocks` = cols/16 blocks per row tile;
-// the lo part is OPND_PART_BYTES/4 floats further
-__device__ __forceinline__ size_t opnd_index(int row, int col, int kblocks) {
+// byte offset of element (row, col), piece 0, of a tiled matrix with `kblocks` = cols/32 blocks
+// per row tile; pieces 1 and 2 are OPND_PART_BYTES and 2*OPND_PART_BYTES further
+__device__ __forceinline__ size_t opnd_offset(int row, int col, int kblocks) {
   const int rt = row / ANI_TILE_ROWS, r = row % ANI_TILE_ROWS;
-  return ((size_t)rt * kblocks + (col >> 4)) * (OPND_BLOCK_BYTES / 4) + (swz_off(r, (col & 15) >> 2) >> 2) + (col & 3);
+  return ((size_t)rt * kblocks + (col >> 5)) * OPND_BLOCK_BYTES + swz_off(r, (col & 31) >> 3) + (size_t)(col & 7) * 2;
+}
+// x = p1 + p2 + p3, bfloat16 pieces rounded to nearest (bit patterns)
+__device__ __forceinline__ void split3(float v, unsigned short& p1, unsigned short& p2, unsigned short& p3) {
+  auto rn = [](float x) -> unsigned short {
+    unsigned short h;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+  };
+  p1 = rn(v);
+  v -= __uint_as_float((uint32_t)p1 << 16);
+  p2 = rn(v);
+  v -= __uint_as_float((uint32_t)p2 << 16);
+  p3 = rn(v);
 }
 
 }  // namespace ani

@@ -1,34 +1,38 @@
 // Persistent, warp-specialised, TMA-fed tcgen05 grouped GEMM for the ensemble MLP (sm_100a).
 //
-//   C[128-row tile, bn] = epilogue( A[128, K] x B[bn, K]^T )        both operands K-major fp32
+//   C[128-row tile, bn] = epilogue( A[128, K] x B[bn, K]^T )        both operands K-major
 //
-// fp32 accuracy on the tensor cores ("3xTF32"): every fp32 operand is stored split into
-// hi = x & 0xffffe000 (exact TF32) and lo = x - hi (exact in fp32); the MMA thread issues three
-// kind::tf32 products per K-step (lo*hi, hi*lo, hi*hi) into one fp32 accumulator in tensor
-// memory.  The dropped lo*lo term is ~2^-22 relative.
+// fp32 accuracy on the tensor cores ("3 x bf16"): every fp32 operand x is stored as three
+// bfloat16 pieces x = p1 + p2 + p3 (round to nearest, residual < 2^-26 |x|); the MMA thread issues
+// six kind::f16 (bf16 x bf16 -> fp32) products per K-step,
+//     a3 b1, a1 b3, a2 b2, a2 b1, a1 b2, a1 b1      (the dropped ones are < 2^-26 relative),
+// into one fp32 accumulator in tensor memory.  Same tensor time as a 3-product TF32 split (bf16
+// runs at twice the TF32 rate) at 6 instead of 8 bytes per element: the six launches of a step
+// are bound by the bytes they move through the L2, not by the MMAs.
 //
 // BOTH operands live in global memory in the "tiled operand" layout of include/ani_b200.h:
-// 16-float K-blocks, [hi rows x 64 B | lo rows x 64 B], every 8-row group in SWIZZLE_64B order.
+// 32-column K-blocks, [p1 rows x 64 B | p2 rows x 64 B | p3 rows x 64 B], every 8-row group in
+// SWIZZLE_64B order.
 //   * B (weights) is tiled once at model-pack time,
 //   * A (activations / gradients) is written in that layout by the epilogue of the GEMM (or by
-//     the AEV kernel) that produces it -- the split costs nothing extra there.
-// A K-block of a tile is therefore 1 + 1 contiguous byte ranges that ONE thread moves with
+//     the AEV kernel) that produces it.
+// A K-block of a tile is therefore ONE contiguous byte range that one thread moves with
 // cp.async.bulk (TMA) straight into the shared-memory layout the MMA descriptors expect; no
-// thread ever touches operand data.  (An earlier version split A on the fly in 8 producer warps:
-// ablation showed 40 % of the GEMM time was the instruction chain of that loop.)
+// thread ever touches operand data.
 //
 // Roles (10 warps, one CTA per SM, persistent over the device-side tile list):
 //   warps 0-7  epilogue : tcgen05.ld (thread = row; warps w and w+4 share TMEM lanes and take
-//                         alternate 16-column groups), bias + CELU | * CELU'(stored activation) |
-//                         final layer + gradient seed | plain, hi/lo split, 16-byte stores
+//                         alternate 32-column groups), bias + CELU | * CELU'(stored activation) |
+//                         final layer + gradient seed | plain; 3-way split, staged in shared
+//                         memory in the final byte order and written by TMA bulk stores
 //   warp  8    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
 //   warp  9    producer : one lane arms the mbarrier (expect_tx) and issues the bulk copies
-// Pipelines: smem full/empty (3-6 stages of 16 KB + 2 x bn x 64 B, sized per launch) and TMEM
-// full/empty (2 x 256 columns), so the epilogue of tile i overlaps the main loop of tile i+1.
-// The epilogue itself is pipelined too: TMEM loads run one column group ahead, and every warp
-// owns two store-staging buffers so the TMA store of group g drains while group g+1 is computed
-// (with one buffer and a wait per group the epilogue, not the MMA or HBM, bounded every GEMM).
+// Pipelines: smem full/empty (2-6 stages of 24 KB + 3 x bn x 64 B, sized on the device from the
+// widest accumulator of the launch) and TMEM full/empty (2 x 256 columns), so the epilogue of
+// tile i overlaps the main loop of tile i+1; TMEM loads run one half group ahead of the math.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace ani {
@@ -36,32 +40,29 @@ namespace tc {
 
 constexpr int TM = ANI_TILE_ROWS;        // 128 rows per tile == UMMA M
 constexpr int TN_MAX = 256;              // UMMA N (columns of one accumulator)
-constexpr int TK = 16;                   // fp32 per K-block = one 64-byte swizzle row (SWIZZLE_64B)
-constexpr int ROW_BYTES = TK * 4;        // 64
+constexpr int TK = OPND_KB;              // 32 columns per K-block = one 64-byte swizzle row of bf16
+constexpr int ROW_BYTES = OPND_ROW_BYTES;        // 64
 constexpr int GROUP_BYTES = 8 * ROW_BYTES;       // 8-row swizzle group = 512 B (descriptor SBO)
+constexpr int PARTS = OPND_PARTS;                // 3
 constexpr int MAX_STAGES = 6;
-constexpr int A_PART_BYTES = TM * ROW_BYTES;     // 8 KB (hi or lo of one A K-block)
-constexpr int A_BLOCK_BYTES = 2 * A_PART_BYTES;  // 16 KB: [hi | lo], contiguous in global memory
-constexpr int B_TILE_BYTES = TN_MAX * ROW_BYTES; // 16 KB
-constexpr int STAGE_BYTES_MAX = A_BLOCK_BYTES + 2 * B_TILE_BYTES;  // 48 KB (bn = 256)
-constexpr int EPI_STAGE_BYTES = 2 * 32 * ROW_BYTES;           // per epilogue warp and buffer: 32 rows x 64 B, hi + lo = 4 KB
-constexpr int EPI_BUFS = 2;
+constexpr int A_PART_BYTES = OPND_PART_BYTES;    // 8 KB (one piece of one A K-block)
+constexpr int A_BLOCK_BYTES = OPND_BLOCK_BYTES;  // 24 KB: [p1 | p2 | p3], contiguous in global memory
+constexpr int EPI_PART_BYTES = 32 * ROW_BYTES;   // one piece of a warp's 32 rows x 32 columns = 2 KB
+constexpr int EPI_STAGE_BYTES = PARTS * EPI_PART_BYTES;  // 6 KB per epilogue warp and buffer
 constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, PROD_WARP = 9;
-constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_BUFS * EPI_STAGE_BYTES;  // 64 KB
 // always (almost) the whole SM: the pipeline depth adapts on the device.  6 KB of the 227 KB are
 // left for the static shared memory (tile map, barriers, bias staging, EPI_HEAD partial sums)
 constexpr int SMEM_BYTES = 227 * 1024 - 6144;
-constexpr int SMEM_FIXED = EPI_BYTES + 1024 /*align*/;
 constexpr int THREADS = (NUM_EPI_WARPS + 2) * 32;  // 320
 constexpr int TMEM_COLS = 512;
 
 enum { EPI_BIAS_CELU = 0, EPI_MUL_DCELU = 1, EPI_PLAIN = 2, EPI_HEAD = 3 };
 
 struct Species {
-  const float* Bt;    // tiled B operand
+  const unsigned char* Bt;  // tiled B operand
   const float* bias;  // [N] (+ member * bias_mstride) or nullptr
   int K, N;
-  int a_moff, c_moff, bias_mstride;  // per-member column offsets into A / C (multiples of 16)
+  int a_moff, c_moff, bias_mstride;  // per-member column offsets into A / C (multiples of 32)
   const float* w4;    // EPI_HEAD: final layer weights [M][N] and biases [M]
   const float* b4;
   // split-K over the members (layer-1 backward): all members share ONE B operand with b_kblocks
@@ -70,9 +71,9 @@ struct Species {
 };
 
 struct Args {
-  const float* A;               // tiled activation matrix [row tile][a_kblocks][hi 128x64B | lo 128x64B]
-  float* C;                     // tiled activation matrix (EPI_PLAIN: plain row-major [rows][ldc])
-  int a_kblocks, c_kblocks;     // 16-column blocks per row of A / C  (= leading dimension / 16)
+  const unsigned char* A;       // tiled activation matrix [row tile][a_kblocks][p1 | p2 | p3]
+  void* C;                      // tiled activation matrix (EPI_PLAIN: plain row-major float [rows][ldc])
+  int a_kblocks, c_kblocks;     // 32-column blocks per row of A / C  (= leading dimension / 32)
   int ldc;                      // EPI_PLAIN only
   int members;                  // GEMMs per row tile
   const int32_t* layout_info;   // [4 + S + 1]: ..., first row tile of species s, total row tiles
@@ -151,14 +152,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, single CTA
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate), single CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -197,9 +198,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
   return d;
 }
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=bn
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
 // CELU(x) = max(0,x) + min(0, alpha*(exp(x/alpha)-1)) with exp via ex2.approx (rel. error ~2^-22:
@@ -226,7 +227,7 @@ struct TileMap {
   int n_eff[ANI_MAX_SPECIES];          // columns actually computed (compacted when nblocks is given)
   int kb_count, nb_count;              // live K-blocks (-1: dense) / live column blocks (-1: dense)
   int kb[MAX_BLOCKS], nb[MAX_BLOCKS];
-  int stages, stage_bytes;             // shared-memory pipeline: as deep as the widest accumulator of this launch allows
+  int stages, stage_bytes, epi_bufs;   // shared-memory budget of this launch
 };
 
 struct Tile {
@@ -256,11 +257,14 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm) {
     run += (tm.first_rt[s + 1] - tm.first_rt[s]) * a.members * tm.ntn[s];
   }
   tm.prefix[S] = run;
-  int bn_max = 16;
+  int bn_max = 32;
   for (int s = 0; s < S; ++s)
     if (tm.first_rt[s + 1] > tm.first_rt[s]) bn_max = max(bn_max, min(TN_MAX, tm.n_eff[s]));
-  tm.stage_bytes = A_BLOCK_BYTES + 2 * bn_max * ROW_BYTES;
-  tm.stages = min(MAX_STAGES, (SMEM_BYTES - SMEM_FIXED) / tm.stage_bytes);
+  tm.stage_bytes = A_BLOCK_BYTES + PARTS * bn_max * ROW_BYTES;
+  // two store-staging buffers per epilogue warp if that still leaves a double-buffered main loop
+  const int avail = SMEM_BYTES - 1024;
+  tm.epi_bufs = (avail - 2 * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes >= 2 ? 2 : 1;
+  tm.stages = min(MAX_STAGES, (avail - tm.epi_bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes);
 }
 
 __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, int t) {
@@ -279,18 +283,31 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
   return x;
 }
 
-// ---- the kernel -----------------------------------------------------------------------------
-__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-  lo.x = v.x - hi.x;
-  lo.y = v.y - hi.y;
-  lo.z = v.z - hi.z;
-  lo.w = v.w - hi.w;
+// ---- 3-way bf16 split of two adjacent fp32 values -> three packed bf16x2 words (low half = a)
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  w1 = *reinterpret_cast<uint32_t*>(&p);
+  a -= __uint_as_float(w1 << 16);
+  b -= __uint_as_float(w1 & 0xffff0000u);
+  p = __floats2bfloat162_rn(a, b);
+  w2 = *reinterpret_cast<uint32_t*>(&p);
+  a -= __uint_as_float(w2 << 16);
+  b -= __uint_as_float(w2 & 0xffff0000u);
+  p = __floats2bfloat162_rn(a, b);
+  w3 = *reinterpret_cast<uint32_t*>(&p);
+}
+// sum of the three pieces of 8 consecutive columns (three 16-byte chunks) -> 8 floats
+__device__ __forceinline__ void join3_chunk(const uint4& q1, const uint4& q2, const uint4& q3, float* y) {
+  const uint32_t a[4] = {q1.x, q1.y, q1.z, q1.w}, b[4] = {q2.x, q2.y, q2.z, q2.w}, c[4] = {q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    y[2 * i] = __uint_as_float(a[i] << 16) + __uint_as_float(b[i] << 16) + __uint_as_float(c[i] << 16);
+    y[2 * i + 1] = __uint_as_float(a[i] & 0xffff0000u) + __uint_as_float(b[i] & 0xffff0000u) +
+                   __uint_as_float(c[i] & 0xffff0000u);
+  }
 }
 
+// ---- the kernel -----------------------------------------------------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Args args) {
   extern __shared__ unsigned char smem_raw[];
@@ -306,8 +323,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   };
   if (threadIdx.x == 0) build_tile_map(args, tm);
   __syncthreads();
-  const int STAGES = tm.stages, STAGE_BYTES = tm.stage_bytes;
-  unsigned char* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 warps x 2 x 4 KB store staging (epilogue warps)
+  const int STAGES = tm.stages, STAGE_BYTES = tm.stage_bytes, EPI_BUFS = tm.epi_bufs;
+  unsigned char* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 warps x EPI_BUFS x 6 KB store staging
   __shared__ uint64_t bars[2 * MAX_STAGES + 5];
   uint64_t* full = bars;                         // [STAGES]  TMA bytes -> MMA
   uint64_t* empty = bars + MAX_STAGES;           // [STAGES]  MMA (commit) -> producer
@@ -334,9 +351,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = tm.prefix[args.num_species];
-  // K-blocks are 16 floats; the optional live-block lists are in 32-column AEV blocks
-  auto num_kb = [&](int K) { return tm.kb_count >= 0 ? 2 * tm.kb_count : (K + TK - 1) / TK; };
-  auto kb_id = [&](int i) { return tm.kb_count >= 0 ? tm.kb[i >> 1] * 2 + (i & 1) : i; };
+  // K-blocks are 32 columns, the same granularity as the optional live-block lists
+  auto num_kb = [&](int K) { return tm.kb_count >= 0 ? tm.kb_count : (K + TK - 1) / TK; };
+  auto kb_id = [&](int i) { return tm.kb_count >= 0 ? tm.kb[i] : i; };
 
   if (warp == PROD_WARP) {
     // ================================ producer (TMA) ================================
@@ -349,24 +366,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       if (lane == 0) stamp(tloc, 0, 0);
       const int nkb_all = sp.b_kb_moff ? sp.b_kblocks : (sp.K + TK - 1) / TK;  // K-blocks of the stored B operand
       const int kb_boff = tl.mem * sp.b_kb_moff;                               // split-K: this member's first K-block
-      // A: [row tile][16-column block][hi | lo]; this GEMM starts at column member * a_moff
-      const unsigned char* At = reinterpret_cast<const unsigned char*>(args.A) +
-                                ((size_t)tl.rt * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
-      // B: [member][n tile][k block][hi bn x 64 B | lo bn x 64 B]
-      const unsigned char* Bm = reinterpret_cast<const unsigned char*>(sp.Bt) +
-                                (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (2 * ROW_BYTES));
+      // A: [row tile][32-column block][p1 | p2 | p3]; this GEMM starts at column member * a_moff
+      const unsigned char* At =
+          args.A + ((size_t)tl.rt * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
+      // B: [member][n tile][k block][p1 bn x 64 B | p2 | p3]
+      const unsigned char* Bm =
+          sp.Bt + (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (PARTS * ROW_BYTES));
       const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
       const bool dense = tm.nb_count < 0;
-      // gathered column blocks (layer-1 backward): lane -> (live block q, part hi/lo)
-      const int gq = lane >> 1, gpart = lane & 1;
+      // gathered column blocks (layer-1 backward): lane -> (live block q, piece)
+      const int gq = lane / PARTS, gpart = lane % PARTS;
       size_t g_src = 0;
       int g_bns = 0;
-      const bool g_active = !dense && lane < 2 * (tl.bn / 32);
+      const bool g_active = !dense && lane < PARTS * (tl.bn / 32);
       if (g_active) {
         const int row0 = tm.nb[tl.n0 / 32 + gq] * 32;
         const int n0s = row0 / TN_MAX * TN_MAX;
         g_bns = min(TN_MAX, sp.N - n0s);
-        g_src = (size_t)n0s * nkb_all * (2 * ROW_BYTES) + (size_t)(row0 - n0s) * ROW_BYTES +
+        g_src = (size_t)n0s * nkb_all * (PARTS * ROW_BYTES) + (size_t)(row0 - n0s) * ROW_BYTES +
                 (size_t)gpart * g_bns * ROW_BYTES;
       }
       for (int kb = 0; kb < nkb; ++kb) {
@@ -376,16 +393,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         const int kbb = kbi + kb_boff;
         if (!(args.debug & 2)) {
           if (lane == 0) {
-            mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + 2 * b_bytes);
+            mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + PARTS * b_bytes);
             bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
-            if (dense)  // hi and lo are adjacent in global memory and in shared memory: one copy
-              bulk_g2s(st + A_BLOCK_BYTES, Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (2 * ROW_BYTES),
-                       2 * b_bytes, &full[stage]);
+            if (dense)  // the three pieces are adjacent in global memory and in shared memory: one copy
+              bulk_g2s(st + A_BLOCK_BYTES, Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES),
+                       PARTS * b_bytes, &full[stage]);
           }
           __syncwarp();
           if (g_active)
             bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,
-                     Bm + g_src + (size_t)kbb * g_bns * (2 * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
+                     Bm + g_src + (size_t)kbb * g_bns * (PARTS * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
         } else if (lane == 0) {
           mbar_arrive(&full[stage]);
         }
@@ -418,15 +435,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         if (lane == 0 && kb == 0) stamp(tloc, 1, 2);
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_PART_BYTES);
-          const uint64_t b_hi = make_desc(sa + A_BLOCK_BYTES), b_lo = make_desc(sa + A_BLOCK_BYTES + b_bytes);
+          const uint32_t sb = sa + A_BLOCK_BYTES;
+          const uint64_t a1 = make_desc(sa), a2 = make_desc(sa + A_PART_BYTES), a3 = make_desc(sa + 2 * A_PART_BYTES);
+          const uint64_t b1 = make_desc(sb), b2 = make_desc(sb + b_bytes), b3 = make_desc(sb + 2 * b_bytes);
 #pragma unroll
-          for (int k = 0; k < TK / 8; ++k) {
+          for (int k = 0; k < TK / 16; ++k) {
             if (args.debug & 4) break;
-            const uint64_t adv = (uint64_t)(k * 2);  // 8 tf32 = 32 B = 2 x 16 B along the swizzle row
-            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B along the swizzle row
+            umma_bf16(d_tmem, a3 + adv, b1 + adv, idesc, (kb | k) != 0);  // smallest terms first
+            umma_bf16(d_tmem, a1 + adv, b3 + adv, idesc, 1);
+            umma_bf16(d_tmem, a2 + adv, b2 + adv, idesc, 1);
+            umma_bf16(d_tmem, a2 + adv, b1 + adv, idesc, 1);
+            umma_bf16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
+            umma_bf16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
           }
           umma_commit(&empty[stage]);                   // smem slot free once these MMAs retire
           if (kb == nkb - 1) {
@@ -448,8 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   } else {
     // ================================ epilogue ================================
     // Thread = accumulator row (TMEM lane).  Warps w and w+4 share the 32 lanes of quadrant w & 3
-    // and take alternate 16-column groups.  Results are written hi/lo-split into the tiled operand
-    // layout of the next GEMM (EPI_PLAIN: plain rows for the AEV backward kernel).
+    // and take alternate 32-column groups (= K-blocks of the next GEMM), each as two 16-column halves.
     uint32_t acc = 0, acc_phase = 0, buf = 0;
     const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
     const int quad = warp & 3, half = warp >> 2;
@@ -457,13 +477,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     uint32_t my_off[4], st_off[4];
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
-      my_off[ch] = swz_off(r_tile, ch);   // inside a 128-row block (global)
+      my_off[ch] = swz_off(r_tile, ch);   // inside a 128-row piece (global)
       st_off[ch] = swz_off(lane, ch);     // inside this warp's 32-row staging image (shared)
     }
-    // The warp's 32 rows x 64 B of one 16-column group are a contiguous 2 KB range of the tiled
-    // layout (hi) plus another one 8 KB further (lo): stage them in shared memory in that very
-    // byte order and let the TMA write them (full lines, no partial-sector stores).  Two staging
-    // buffers per warp: the store of one group drains while the next group is computed.
+    // The warp's 32 rows x 64 B of one 32-column group are a contiguous 2 KB range of the tiled
+    // layout per piece (pieces 8 KB apart): stage them in shared memory in that very byte order and
+    // let the TMA write them (full lines, no partial-sector stores).
     unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
     const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward) && !(args.debug & 32);
     int tloc = 0;
@@ -471,8 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
       if (threadIdx.x == 0) stamp(tloc, 2, 0);
-      // bias (and final-layer weights) of this tile -> shared memory while the main loop runs: the
-      // per-group float4 global loads sat on the critical path of every column group
+      // bias (and final-layer weights) of this tile -> shared memory while the main loop runs
       const float* __restrict__ bias = s_bias[acc];
       const float* __restrict__ w4 = s_w4[acc];
       if (EPI == EPI_BIAS_CELU || EPI == EPI_HEAD) {
@@ -490,110 +508,120 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         row_valid = args.row_atom[my_row] >= 0;
         seed = row_valid ? args.member_scale[tl.mem] : 0.f;
       }
-      // tiled C: the block of 16-column group g is [row tile][(member*c_moff + n0)/16 + g]
+      // tiled C: the block of 32-column group g is [row tile][(member*c_moff + n0)/32 + g]
       unsigned char* ct = reinterpret_cast<unsigned char*>(args.C) +
                           ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
-      float* cplain = args.C + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
-      const int ngroups = tl.bn / 16;
-      float4 yh[4], yl[4];
-      auto load_y = [&](int g) {  // stored activation (hi + lo) of 16-column group g, this thread's row
+      float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
+      const int ngroups = tl.bn / 32;
+      // stored activation (three pieces) of 16 columns = chunks 2*hh, 2*hh+1 of group g, this thread's row
+      uint4 yq[6];
+      auto load_y = [&](int g, int hh) {
         const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          yh[ch] = *reinterpret_cast<const float4*>(blk + my_off[ch]);
-          yl[ch] = *reinterpret_cast<const float4*>(blk + A_PART_BYTES + my_off[ch]);
+        for (int p = 0; p < PARTS; ++p) {
+          yq[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]);
+          yq[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]);
         }
       };
-      if (EPI == EPI_MUL_DCELU && half < ngroups && !(args.debug & 128)) load_y(half);  // overlaps the wait for the accumulator
+      if (EPI == EPI_MUL_DCELU && half < ngroups && !(args.debug & 128)) load_y(half, 0);  // overlaps the wait for the accumulator
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 0) stamp(tloc, 2, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
 
-      // one 16-column group: raw accumulator registers -> epilogue math -> store
-      auto process = [&](int g, const uint32_t (&r)[16]) {
-        float4 y[4];
+      // one 16-column half of group g: raw accumulator registers -> epilogue math -> staging / store
+      auto process = [&](int g, int hh, const uint32_t (&r)[16]) {
+        float y[16];
         if (EPI == EPI_MUL_DCELU) {
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch)
-            y[ch] = make_float4(yh[ch].x + yl[ch].x, yh[ch].y + yl[ch].y, yh[ch].z + yl[ch].z, yh[ch].w + yl[ch].w);
-          if (g + 2 < ngroups && !(args.debug & 128)) load_y(g + 2);  // prefetch the next group this warp handles
+          join3_chunk(yq[0], yq[2], yq[4], y);
+          join3_chunk(yq[1], yq[3], yq[5], y + 8);
+          if (!(args.debug & 128)) {  // prefetch the next half this warp handles
+            if (hh == 0)
+              load_y(g, 1);
+            else if (g + 2 < ngroups)
+              load_y(g + 2, 0);
+          }
         }
         unsigned char* sb = sb0 + buf * EPI_STAGE_BYTES;
-        if (tiled_out) {
-          // this buffer was handed to the TMA two groups ago: its read must be complete
-          if (lane == 0) bulk_wait_read<EPI_BUFS - 1>();
-          __syncwarp();
-        }
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float4 o = make_float4(__uint_as_float(r[4 * ch]), __uint_as_float(r[4 * ch + 1]),
-                                 __uint_as_float(r[4 * ch + 2]), __uint_as_float(r[4 * ch + 3]));
-          if (EPI == EPI_BIAS_CELU) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + g * 16 + 4 * ch);
-            o.x = celu(o.x + b.x, cc);
-            o.y = celu(o.y + b.y, cc);
-            o.z = celu(o.z + b.z, cc);
-            o.w = celu(o.w + b.w, cc);
-          } else if (EPI == EPI_MUL_DCELU) {
-            o.x *= dcelu_from_out(y[ch].x, cc);
-            o.y *= dcelu_from_out(y[ch].y, cc);
-            o.z *= dcelu_from_out(y[ch].z, cc);
-            o.w *= dcelu_from_out(y[ch].w, cc);
-          } else if (EPI == EPI_HEAD) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + g * 16 + 4 * ch);
-            const float4 w = *reinterpret_cast<const float4*>(w4 + g * 16 + 4 * ch);
-            float a;
-            a = celu(o.x + b.x, cc); e_acc = fmaf(a, w.x, e_acc); o.x = seed * w.x * dcelu_from_out(a, cc);
-            a = celu(o.y + b.y, cc); e_acc = fmaf(a, w.y, e_acc); o.y = seed * w.y * dcelu_from_out(a, cc);
-            a = celu(o.z + b.z, cc); e_acc = fmaf(a, w.z, e_acc); o.z = seed * w.z * dcelu_from_out(a, cc);
-            a = celu(o.w + b.w, cc); e_acc = fmaf(a, w.w, e_acc); o.w = seed * w.w * dcelu_from_out(a, cc);
-          }
-          if (args.debug & 32) continue;
-          if (EPI == EPI_PLAIN) {
-            // compacted column blocks map back to their place: group g lies in live block (n0 + 16 g) / 32
-            const int col = (tm.nb_count >= 0 ? tm.nb[(tl.n0 + g * 16) / 32] * 32 + ((g * 16) & 16) : tl.n0 + g * 16) + 4 * ch;
-            if (args.c_accumulate)
-              red_add_v4(cplain + col, o);
-            else
-              *reinterpret_cast<float4*>(cplain + col) = o;
-          } else if (tiled_out) {
-            float4 hi, lo;
-            split4(o, hi, lo);
-            *reinterpret_cast<float4*>(sb + st_off[ch]) = hi;
-            *reinterpret_cast<float4*>(sb + 32 * ROW_BYTES + st_off[ch]) = lo;
-          }
-        }
-        if (tiled_out) {
-          unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA
-          __syncwarp();
+        if (tiled_out && hh == 0) {
+          // this buffer was handed to the TMA EPI_BUFS groups ago: its read must be complete
           if (lane == 0) {
-            bulk_s2g(blk + quad * 32 * ROW_BYTES, sb, 32 * ROW_BYTES);
-            bulk_s2g(blk + A_PART_BYTES + quad * 32 * ROW_BYTES, sb + 32 * ROW_BYTES, 32 * ROW_BYTES);
-            bulk_commit();
+            if (EPI_BUFS == 2)
+              bulk_wait_read<1>();
+            else
+              bulk_wait_read<0>();
           }
-          buf ^= 1;
+          __syncwarp();
+        }
+        const int c0 = g * 32 + hh * 16;  // first column of this half inside the tile
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = __uint_as_float(r[j]);
+          if (EPI == EPI_BIAS_CELU) {
+            v = celu(v + bias[c0 + j], cc);
+          } else if (EPI == EPI_MUL_DCELU) {
+            v *= dcelu_from_out(y[j], cc);
+          } else if (EPI == EPI_HEAD) {
+            const float w = w4[c0 + j];
+            const float a = celu(v + bias[c0 + j], cc);
+            e_acc = fmaf(a, w, e_acc);
+            v = seed * w * dcelu_from_out(a, cc);
+          }
+          o[j] = v;
+        }
+        if (args.debug & 32) return;
+        if (EPI == EPI_PLAIN) {
+          // compacted column blocks map back to their place: group g is live block n0/32 + g
+          const int col = (tm.nb_count >= 0 ? tm.nb[tl.n0 / 32 + g] * 32 : tl.n0 + g * 32) + hh * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v4 = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            if (args.c_accumulate)
+              red_add_v4(cplain + col + 4 * q, v4);
+            else
+              *reinterpret_cast<float4*>(cplain + col + 4 * q) = v4;
+          }
+        } else if (tiled_out) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {  // chunk 2*hh + c = columns 8c .. 8c+7 of this half
+            uint32_t w1[4], w2[4], w3[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split3_pair(o[8 * c + 2 * i], o[8 * c + 2 * i + 1], w1[i], w2[i], w3[i]);
+            const uint32_t off = st_off[2 * hh + c];
+            *reinterpret_cast<uint4*>(sb + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+            *reinterpret_cast<uint4*>(sb + EPI_PART_BYTES + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+            *reinterpret_cast<uint4*>(sb + 2 * EPI_PART_BYTES + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+          }
+          if (hh == 1) {
+            unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES + quad * EPI_PART_BYTES;
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int p = 0; p < PARTS; ++p) bulk_s2g(blk + p * A_PART_BYTES, sb + p * EPI_PART_BYTES, EPI_PART_BYTES);
+              bulk_commit();
+            }
+            if (EPI_BUFS == 2) buf ^= 1;
+          }
         }
       };
 
-      // TMEM loads run one group ahead of the math (two statically indexed register sets)
+      // TMEM loads run one half group ahead of the math (two statically indexed register sets)
       if (!(args.debug & 8)) {
         uint32_t r0[16], r1[16];
-        if (half < ngroups) tmem_ld16_issue(taddr + half * 16, r0);
-        for (int g = half; g < ngroups; g += 4) {
+        if (half < ngroups) tmem_ld16_issue(taddr + half * 32, r0);
+        for (int g = half; g < ngroups; g += 2) {
           tmem_ld_wait(r0);
-          if (g + 2 < ngroups) tmem_ld16_issue(taddr + (g + 2) * 16, r1);
-          process(g, r0);
-          if (g + 2 < ngroups) {
-            tmem_ld_wait(r1);
-            if (g + 4 < ngroups) tmem_ld16_issue(taddr + (g + 4) * 16, r0);
-            process(g + 2, r1);
-          }
+          tmem_ld16_issue(taddr + g * 32 + 16, r1);
+          process(g, 0, r0);
+          tmem_ld_wait(r1);
+          if (g + 2 < ngroups) tmem_ld16_issue(taddr + (g + 2) * 32, r0);
+          process(g, 1, r1);
         }
       }
       if (EPI == EPI_HEAD) {
-        // the two warps of a row hold the even / odd 16-column groups: combine through shared memory
+        // the two warps of a row hold the even / odd column groups: combine through shared memory
         e_part[warp * 32 + lane] = e_acc;
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // epilogue warps only
         if (half == 0)

@@ -94,65 +94,74 @@ def constants_1x(num_species: int = 4, cutoff_fn: str = "cosine") -> AEVConstant
                         _linspace(0.9, 3.5, 4), _linspace(a0, math.pi + a0, 8), cutoff_fn)
 
 
+def _split3(x: Tensor) -> tp.List[Tensor]:
+    """x (float32) -> three bfloat16 pieces with x = p1 + p2 + p3 (each rounded to nearest)."""
+    p1 = x.to(torch.bfloat16)
+    r = x - p1.to(torch.float32)
+    p2 = r.to(torch.bfloat16)
+    r = r - p2.to(torch.float32)
+    return [p1, p2, r.to(torch.bfloat16)]
+
+
+def _swizzle_index(device) -> Tensor:
+    """idx[row in 8-row group][position] = the 16-byte chunk stored at that position (SWIZZLE_64B)."""
+    rows = torch.arange(8, device=device).view(8, 1)
+    pos = torch.arange(4, device=device).view(1, 4)
+    return pos ^ ((rows >> 1) & 3)
+
+
 def tile_b_operand(b: Tensor) -> Tensor:
-    """``B[N][K]`` (float32, K-major) -> the "tiled B operand" byte layout of include/ani_b200.h:
-    K zero-padded to 16, hi/lo TF32 split, [n tile of 256 rows][k block of 16][hi bn x 64 B | lo bn x 64 B]
-    with every 8-row group in tcgen05 SWIZZLE_64B order.  Returned as a flat float32 tensor."""
+    """``B[N][K]`` (float32, K-major, N % 32 == 0) -> the "tiled B operand" byte layout of
+    include/ani_b200.h: K zero-padded to 32, three bfloat16 pieces,
+    [n tile of 256 rows][k block of 32][p1 bn x 64 B | p2 | p3] with every 8-row group in tcgen05
+    SWIZZLE_64B order.  Returned as a flat bfloat16 tensor."""
     n, k = b.shape
-    assert n % 8 == 0, "rows of a B operand must come in groups of 8"
-    kp = (k + 15) // 16 * 16
-    nkb = kp // 16
+    assert n % 32 == 0, "rows of a B operand must come in groups of 32"
+    kp = (k + 31) // 32 * 32
+    nkb = kp // 32
     bp = torch.zeros(n, kp, dtype=torch.float32, device=b.device)
     bp[:, :k] = b
-    hi = (bp.view(torch.int32) & -8192).view(torch.float32)   # 0xffffe000
-    lo = bp - hi
-    rows = torch.arange(8, device=b.device).view(8, 1)
-    pos = torch.arange(4, device=b.device).view(1, 4)
-    src_chunk = pos ^ ((rows >> 1) & 3)                         # chunk stored at position p of row r
+    pieces = _split3(bp)
+    src_chunk = _swizzle_index(b.device)
     out = []
     for n0 in range(0, n, 256):
         bn = min(256, n - n0)
         parts = []
-        for part in (hi, lo):
-            x = part[n0:n0 + bn].view(bn // 8, 8, nkb, 4, 4)           # [group][row][kb][chunk][4]
-            x = x.permute(2, 0, 1, 3, 4)                                # [kb][group][row][chunk][4]
-            idx = src_chunk.view(1, 1, 8, 4, 1).expand(nkb, bn // 8, 8, 4, 4)
-            parts.append(torch.gather(x, 3, idx).reshape(nkb, bn * 16))
-        out.append(torch.stack(parts, 1).reshape(-1))                  # [kb][hi|lo][bn*16]
+        idx = src_chunk.view(1, 1, 8, 4, 1).expand(nkb, bn // 8, 8, 4, 8)
+        for part in pieces:
+            x = part[n0:n0 + bn].view(bn // 8, 8, nkb, 4, 8)           # [group][row][kb][chunk][8]
+            x = x.permute(2, 0, 1, 3, 4)                                # [kb][group][row][chunk][8]
+            parts.append(torch.gather(x, 3, idx).reshape(nkb, bn * 32))
+        out.append(torch.stack(parts, 1).reshape(-1))                  # [kb][piece][bn*32]
     return torch.cat(out).contiguous()
 
 
 def tile_a_operand(x: Tensor) -> Tensor:
-    """Plain ``[rows][cols]`` float32 (rows % 128 == 0, cols % 16 == 0) -> flat "tiled operand"
-    (A-operand form of include/ani_b200.h).  Plumbing for the API paths that receive plain AEVs."""
+    """Plain ``[rows][cols]`` float32 (rows % 128 == 0, cols % 32 == 0) -> flat "tiled operand"
+    (A-operand form of include/ani_b200.h, bfloat16).  Plumbing for the API paths that receive plain AEVs."""
     rows, cols = x.shape
-    assert rows % 128 == 0 and cols % 16 == 0
-    nkb = cols // 16
-    hi = (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
-    lo = x - hi
-    r = torch.arange(8, device=x.device).view(8, 1)
-    pos = torch.arange(4, device=x.device).view(1, 4)
-    idx = (pos ^ ((r >> 1) & 3)).view(1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 16, 8, 4, 4)
+    assert rows % 128 == 0 and cols % 32 == 0
+    nkb = cols // 32
+    idx = _swizzle_index(x.device).view(1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 16, 8, 4, 8)
     parts = []
-    for part in (hi, lo):
-        v = part.view(rows // 128, 16, 8, nkb, 4, 4).permute(0, 3, 1, 2, 4, 5)   # [rt][kb][grp][row][ch][4]
-        parts.append(torch.gather(v, 4, idx).reshape(rows // 128, nkb, 2048))
-    return torch.stack(parts, 2).reshape(-1).contiguous()                          # [rt][kb][hi|lo][2048]
+    for part in _split3(x.contiguous().to(torch.float32)):
+        v = part.view(rows // 128, 16, 8, nkb, 4, 8).permute(0, 3, 1, 2, 4, 5)   # [rt][kb][grp][row][ch][8]
+        parts.append(torch.gather(v, 4, idx).reshape(rows // 128, nkb, 4096))
+    return torch.stack(parts, 2).reshape(-1).contiguous()                          # [rt][kb][piece][4096]
 
 
 def untile_a_operand(t: Tensor, rows: int, cols: int) -> Tensor:
-    """Inverse of ``tile_a_operand`` (returns hi + lo as plain ``[rows][cols]``)."""
-    nkb = cols // 16
-    v = t.view(rows // 128, nkb, 2, 16, 8, 4, 4)                                   # [rt][kb][part][grp][row][pos][4]
-    r = torch.arange(8, device=t.device).view(8, 1)
-    ch = torch.arange(4, device=t.device).view(1, 4)
-    idx = (ch ^ ((r >> 1) & 3)).view(1, 1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 2, 16, 8, 4, 4)
-    w = torch.gather(v, 5, idx).sum(2)                                              # [rt][kb][grp][row][ch][4]
+    """Inverse of ``tile_a_operand`` (returns p1 + p2 + p3 as plain float32 ``[rows][cols]``)."""
+    nkb = cols // 32
+    v = t.view(torch.bfloat16).view(rows // 128, nkb, 3, 16, 8, 4, 8)            # [rt][kb][piece][grp][row][pos][8]
+    idx = _swizzle_index(t.device).view(1, 1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 3, 16, 8, 4, 8)
+    w = torch.gather(v.to(torch.float32), 5, idx).sum(2)                           # [rt][kb][grp][row][ch][8]
     return w.permute(0, 2, 3, 1, 4, 5).reshape(rows, cols).contiguous()
 
 
 class PackedNetworks:
-    """Device-resident, kernel-layout copy of an ensemble of per-element MLPs.
+    """Device-resident, kernel-layout copy of an ensemble of per-element MLPs (``dims`` keeps the
+    true layer widths, the kernel model the widths padded to multiples of 32).
 
     ``weights[member][species_index] = [(W [out,in], b [out]) x 4]`` in ``torch.nn.Linear``
     layout (nn/_core.py:117-149).  All members must share the layer widths of a species.
@@ -184,8 +193,6 @@ class PackedNetworks:
                 raise ValueError("out_dim != 1 is not supported")
             if layers0[0][0].shape[1] != in_dim:
                 raise ValueError("first layer width does not match the AEV length")
-            if any(h % 16 for h in (h1, h2, h3)):
-                raise ValueError("hidden widths must be multiples of 16")
             self.dims.append((h1, h2, h3))
             W = [[weights[m][s][k][0].detach().to(**f32) for m in range(M)] for k in range(4)]
             Bv = [[weights[m][s][k][1].detach().to(**f32) for m in range(M)] for k in range(4)]
@@ -193,6 +200,20 @@ class PackedNetworks:
                 if tuple(W[0][m].shape) != (h1, in_dim) or tuple(W[1][m].shape) != (h2, h1) \
                         or tuple(W[2][m].shape) != (h3, h2) or tuple(W[3][m].shape) != (1, h3):
                     raise ValueError("all ensemble members must share the layer widths of an element")
+            # the kernels work on 32-column blocks: pad the hidden widths with zero weights and biases
+            # (CELU(0) = 0 and the padded inputs of the next layer meet zero weights: results unchanged)
+            ins, outs = (in_dim, h1, h2, h3), (h1, h2, h3, 1)
+            pad = lambda v: (v + 31) // 32 * 32  # noqa: E731
+            pin = (in_dim, pad(h1), pad(h2), pad(h3))
+            pout = (pad(h1), pad(h2), pad(h3), 1)
+            for k in range(4):
+                for m in range(M):
+                    w = torch.zeros(pout[k], pin[k], **f32)
+                    w[:outs[k], :ins[k]] = W[k][m]
+                    bb = torch.zeros(pout[k], **f32)
+                    bb[:outs[k]] = Bv[k][m]
+                    W[k][m], Bv[k][m] = w, bb
+            h1, h2, h3 = pout[:3]
             w1n = torch.zeros(M * h1, self.ldx, **f32)
             w1n[:, :in_dim] = torch.cat(W[0], 0)
             t = {
@@ -270,12 +291,13 @@ class Workspace:
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
-        # x / act*: "tiled operand" form (hi + lo parts -> twice the plain size); dx: plain rows
-        self.x = torch.zeros(self.rows_cap, 2 * ldx, **f32)
+        # x / act*: "tiled operand" form (three bfloat16 pieces per value); dx: plain float32 rows
+        bf16 = dict(dtype=torch.bfloat16, device=device)
+        self.x = torch.zeros(self.rows_cap, 3 * ldx, **bf16)
         self.dx = torch.zeros(self.rows_cap, ldx, **f32)
-        self.act1 = torch.zeros(self.rows_cap, 2 * ld[0], **f32)
-        self.act2 = torch.zeros(self.rows_cap, 2 * ld[1], **f32)
-        self.act3 = torch.zeros(self.rows_cap, 2 * ld[2], **f32)
+        self.act1 = torch.zeros(self.rows_cap, 3 * ld[0], **bf16)
+        self.act2 = torch.zeros(self.rows_cap, 3 * ld[1], **bf16)
+        self.act3 = torch.zeros(self.rows_cap, 3 * ld[2], **bf16)
         self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
         self.species_i32 = torch.zeros(n, **i32)
         self.coords = torch.zeros(n, 3, **f32)

@@ -102,12 +102,12 @@ class _MLPFunction(torch.autograd.Function):
         src = src * real.view(-1, 1)
         # padding atoms all map to row 0 with zero contribution -> index_add keeps row 0 intact
         xp[:, :D].index_add_(0, rows, src)
-        x_tiled = tile_a_operand(xp)                    # the GEMM consumes the hi/lo-split tiled form
+        x_tiled = tile_a_operand(xp)                    # the GEMM consumes the 3 x bf16 tiled form
         x = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)   # dE/dAEV comes back as plain rows
         ld = nets.ld
-        act1 = torch.empty(rows_cap, 2 * ld[0], dtype=torch.float32, device=dev)
-        act2 = torch.empty(rows_cap, 2 * ld[1], dtype=torch.float32, device=dev)
-        act3 = torch.empty(rows_cap, 2 * ld[2], dtype=torch.float32, device=dev)
+        act1 = torch.empty(rows_cap, 3 * ld[0], dtype=torch.bfloat16, device=dev)
+        act2 = torch.empty(rows_cap, 3 * ld[1], dtype=torch.bfloat16, device=dev)
+        act3 = torch.empty(rows_cap, 3 * ld[2], dtype=torch.bfloat16, device=dev)
         e_member = torch.zeros(M, rows_cap, dtype=torch.float32, device=dev)
         check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x_tiled), ptr(x), rows_cap,
                                               ptr(row_atom), ptr(layout_info), None, ptr(act1), ptr(act2), ptr(act3),
