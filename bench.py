@@ -267,14 +267,14 @@ def main():
     fwd_s = stage.get("aev_forward", float("nan")) * 1e-3
     bwd_s = stage.get("aev_backward", float("nan")) * 1e-3
     roofline = {"kernel": "tc::k_gemm_tc<EPI> x6 (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input, "
-                          "tcgen05 kind::tf32 with a 3-product hi/lo split (fp32-accurate)",
+                          "tcgen05 kind::f16 on a 3 x bf16 split of every fp32 operand, 6 products (fp32-accurate)",
                 "bound": "tensor", "achieved": flops / mlp_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": MLP_DRAM_BYTES_PER_STEP if world == 1 and args.molecules == 3333 else None,
                 "algorithmic_flops_per_launch_sequence": flops, "peak_source": pk["source"],
                 "note": "achieved = dense algorithmic FLOPs of SURVEY 8(d) (98.2 GFLOP/step at 10k atoms) / "
-                        "device time of the six GEMM launches; peak = measured dense bf16 rate. The kernel issues 3 TF32 "
-                        "MMAs per product (TF32 peak = bf16/2) but skips the AEV column blocks of absent element "
-                        "pairs in layer 1, so the executed tensor work is 3 x 36% of the dense count for water. "
+                        "device time of the six GEMM launches; peak = measured dense bf16 rate. The kernel issues 6 bf16 "
+                        "MMAs per product (3 x bf16 split) but skips the AEV column blocks of absent element "
+                        "pairs in layer 1, so the executed tensor work is 6 x 36% of the dense count for water. "
                         "traffic = dram bytes of the six launches (ncu, profiles/), null if not captured for this build"}
     roofline_aev = {
         "forward": {"kernel": "k_aev_forward<8,4>", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
