@@ -80,6 +80,9 @@ class ClockSampler:
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:   # nvidia-smi takes a moment to start sampling
+                time.sleep(0.05)
         except OSError:
             self.proc = None
 
@@ -266,15 +269,21 @@ def main():
     mlp_s = stage.get("mlp_forward_backward", float("nan")) * 1e-3
     fwd_s = stage.get("aev_forward", float("nan")) * 1e-3
     bwd_s = stage.get("aev_backward", float("nan")) * 1e-3
+    from torchani_b200._lib import operand_format
+    fmt = operand_format()
+    split = ("2 x fp16 split of every (power-of-two scaled) fp32 operand, 3 products" if fmt.parts == 2
+             else "3 x bf16 split of every fp32 operand, 6 products")
+    nprod = 3 if fmt.parts == 2 else 6
     roofline = {"kernel": "tc::k_gemm_tc<EPI> x6 (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input, "
-                          "tcgen05 kind::f16 on a 3 x bf16 split of every fp32 operand, 6 products (fp32-accurate)",
+                          f"tcgen05 kind::f16 on a {split} (fp32-accurate)",
                 "bound": "tensor", "achieved": flops / mlp_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": MLP_DRAM_BYTES_PER_STEP if world == 1 and args.molecules == 3333 else None,
                 "algorithmic_flops_per_launch_sequence": flops, "peak_source": pk["source"],
                 "note": "achieved = dense algorithmic FLOPs of SURVEY 8(d) (98.2 GFLOP/step at 10k atoms) / "
-                        "device time of the six GEMM launches; peak = measured dense bf16 rate. The kernel issues 6 bf16 "
-                        "MMAs per product (3 x bf16 split) but skips the AEV column blocks of absent element "
-                        "pairs in layer 1, so the executed tensor work is 6 x 36% of the dense count for water. "
+                        "device time of the six GEMM launches; peak = measured dense bf16 rate (= the fp16 rate). The "
+                        f"kernel issues {nprod} 16-bit MMAs per product but skips the AEV column blocks of absent "
+                        f"element pairs in layer 1, so the executed tensor work is {nprod} x 36% of the dense count "
+                        "for water. "
                         "traffic = dram bytes of the six launches (ncu, profiles/), null if not captured for this build"}
     roofline_aev = {
         "forward": {"kernel": "k_aev_forward<8,4>", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
@@ -307,6 +316,7 @@ def main():
                         "api": "torchani_b200.calculator.HostCalculator.calculate (host positions in, host "
                                "energy+forces out; counterpart of torchani.ase.Calculator.calculate)"},
                 "gpu_launches": eng.launches_per_step * args.steps,
+                "operand_format": {"parts": fmt.parts, "bytes_per_element": 2 * fmt.parts},
                 "stage_ms": stage, "roofline": roofline, "roofline_aev": roofline_aev, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

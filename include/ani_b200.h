@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ANI_B200_ABI_VERSION 1
+#define ANI_B200_ABI_VERSION 2
 
 #define ANI_MAX_SPECIES 8
 #define ANI_MAX_SHFR 32
@@ -52,6 +52,7 @@ extern "C" {
 #define ANI_STATUS_ANG_OVERFLOW 2   /* an atom has more angular neighbours than ANI_MAX_ANG */
 #define ANI_STATUS_CELL_TOO_SMALL 4 /* periodic cell thinner than the cutoff (neighbors.py:402-403) */
 #define ANI_STATUS_PAIR_OVERFLOW 8  /* half neighbour list exceeds the caller's capacity */
+#define ANI_STATUS_OPERAND_RANGE 16 /* a value left the range of the half-precision GEMM operand pieces */
 
 #define ANI_MAX_ANG 96 /* angular neighbours (<= Rca) one central atom may have */
 
@@ -82,6 +83,13 @@ typedef struct ani_grid {
 } ani_grid;
 
 int ani_b200_abi_version(void);
+
+/* Format of the "tiled operand" matrices this build was compiled for (section 6):             */
+/*   parts        16-bit pieces per value: 2 = IEEE half pieces of scale*x, 3 = bfloat16 pieces  */
+/*   value_scale  power-of-two scale of AEV / activation operands (1 for bfloat16 pieces)        */
+/*   grad_scale   power-of-two scale of gradient operands                                        */
+/* No reference counterpart (the reference runs cuBLAS sgemm / TF32 on plain fp32 rows).         */
+int ani_b200_operand_format(int32_t* parts, float* value_scale, float* grad_scale);
 const char* ani_b200_error_string(int code);
 /* Last CUDA error string seen by this library on the calling thread (for ANI_ERR_CUDA). */
 const char* ani_b200_last_cuda_error(void);
@@ -218,13 +226,18 @@ int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, 
 
 /* 6. Ensemble MLP forward + backward-to-input on the species-grouped AEV matrix.           */
 /*    Layer widths: in -> h1 -> h2 -> h3 -> 1, CELU(alpha) after the three hidden layers.    */
-/*    "Tiled operand" layout (both GEMM operands; fp32 accuracy on the tensor cores = 3 x bf16):  */
-/*    every value is stored as three bfloat16 pieces x = p1 + p2 + p3 (round to nearest).         */
-/*    * A operand / activation matrix [rows][cols] (rows % 128 == 0, cols % 32 == 0), 6 B/element: */
-/*        [row tile of 128][32-column block][p1: 128 rows x 64 B | p2 | p3]          (24 KB blocks) */
+/*    "Tiled operand" layout (both GEMM operands; fp32 accuracy on the tensor cores from 16-bit    */
+/*    pieces, see ani_b200_operand_format): every value x of an operand with power-of-two scale s   */
+/*    is stored as P pieces with s*x = p1 + ... + pP, each rounded to nearest:                       */
+/*      P = 2 IEEE half pieces (default build; 4 B/element; s = 64 for AEVs/activations, 4096 for    */
+/*            gradients, ani_mlp_species::w_scale for weights; |s*x| must stay below 65504, else     */
+/*            ANI_STATUS_OPERAND_RANGE is raised and the results are inf/NaN),                       */
+/*      P = 3 bfloat16 pieces (-DANI_OPND_FP16X2=0; 6 B/element; s = 1).                             */
+/*    * A operand / activation matrix [rows][cols] (rows % 128 == 0, cols % 32 == 0):                */
+/*        [row tile of 128][32-column block][p1: 128 rows x 64 B | p2 (| p3)]    (16 / 24 KB blocks) */
 /*    * B operand of a layer GEMM  C[rows, N] = A[rows, K] x W  (W given as B[N][K], N % 32 == 0,  */
 /*      K padded to a multiple of 32 with zeros):                                                  */
-/*        [member][n tile (256 rows, the last one shorter)][32-column block][p1 bn x 64 B | p2 | p3] */
+/*        [member][n tile (256 rows, the last one shorter)][32-column block][p1 bn x 64 B | p2 (| p3)] */
 /*    In both, every 8-row x 64-byte group is in the tcgen05 SWIZZLE_64B order (16-byte chunk c    */
 /*    of row r sits at chunk position c ^ ((r >> 1) & 3)), i.e. exactly the shared-memory image    */
 /*    a K-major UMMA descriptor expects: one K-block of one tile is a contiguous byte range        */
@@ -232,6 +245,7 @@ int ani_b200_half_neighbor_fill(const ani_grid* grid, const int32_t* bin_start, 
 /*    multiples of 32 are zero-padded by the packer (zero weights and biases: CELU(0) = 0).         */
 typedef struct ani_mlp_species {
   int32_t h1, h2, h3, pad_;
+  float w_scale[4];  /* [0..2]: power-of-two scale the packer multiplied W1, W2, W3 by (fp16 pieces) */
   const float* b1;   /* [M*h1]                                                                  */
   const float* b2;   /* [M*h2]                                                                  */
   const float* b3;   /* [M*h3]                                                                  */
@@ -253,18 +267,19 @@ typedef struct ani_mlp_model {
   ani_mlp_species sp[ANI_MAX_SPECIES];
 } ani_mlp_model;
 
-/*    x            tiled operand, in: AEVs (ani_b200_aev_forward layout 1), 6*rows_cap*ldx bytes */
+/*    x            tiled operand, in: AEVs (ani_b200_aev_forward layout 1), 2*P*rows_cap*ldx bytes */
 /*    dx           f32[rows_cap][ldx] plain rows, out: dE/dAEV (may be NULL if !want_backward)  */
 /*    row_atom / layout_info: outputs of ani_b200_species_layout                                */
 /*    aev_blocks   output of ani_b200_active_aev_blocks or NULL (= every column is live).       */
 /*                 With a block list, layer 1 skips the dead K-blocks and dE/dAEV is written     */
 /*                 only for the live column blocks (the others keep their previous content).     */
-/*    act1/2/3     tiled operands, 6*rows_cap*M*h{1,2,3}_max bytes (activations, then gradients) */
+/*    act1/2/3     tiled operands, 2*P*rows_cap*M*h{1,2,3}_max bytes (activations, then gradients) */
 /*    e_member     f32[M][rows_cap]     per-member atomic energies                               */
+/*    status       i32[1] device word, ANI_STATUS_OPERAND_RANGE is OR-ed in (may be NULL)        */
 int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
                                   const int32_t* row_atom, const int32_t* layout_info,
                                   const int32_t* aev_blocks, void* act1, void* act2, void* act3,
-                                  float* e_member, int want_backward, void* stream);
+                                  float* e_member, int want_backward, int32_t* status, void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
 /*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */

@@ -46,11 +46,12 @@ def gpu_aev(eng, species, coords, cell, pbc):
     n_real = int((species >= 0).sum())
     so = ws.sorted_orig[:n_real].long()
     rows = ws.row_of[:n_real].long()
-    # the engine's own AEV buffer holds the same numbers as three bfloat16 pieces (sum exact to ~2^-24)
+    # the engine's own AEV buffer holds the same numbers as 16-bit pieces (2 x fp16 of 64*x: 22 bits and an
+    # absolute floor of 2^-31; 3 x bf16: 24 bits)
     from torchani_b200.engine import untile_a_operand
     tiled = untile_a_operand(ws.x.reshape(-1), ws.rows_cap, eng.nets.ldx)
     err = (tiled[rows, :D] - plain[rows, :D]).abs()
-    assert bool((err <= plain[rows, :D].abs() * 2.0 ** -22 + 1e-37).all()), "tiled and plain AEV outputs differ"
+    assert bool((err <= plain[rows, :D].abs() * 2.0 ** -21 + 2.0 ** -30).all()), "tiled and plain AEV outputs differ"
     aev = torch.zeros(n, D, device=dev)
     aev[so] = plain[rows, :D]
     return aev.view(*species.shape, D).cpu(), res

@@ -40,46 +40,58 @@ def test_unsupported_configurations_are_rejected_loudly():
         AtomicNetwork((1008, 256, 192, 160, 1), activation="gelu")
 
 
-def _bf16_to_f32(u16):
+def _piece_to_f32(u16, parts):
+    if parts == 2:
+        return u16.view(np.float16).astype(np.float32)
     return (u16.astype(np.uint32) << 16).view(np.float32)
 
 
 def _untile(t, n, k):
     """Inverse of engine.tile_b_operand (numpy, element-wise from the documented layout of
-    include/ani_b200.h): returns the three bfloat16 pieces as float32 arrays."""
+    include/ani_b200.h): returns the 16-bit pieces (still scaled) as float32 arrays."""
+    from torchani_b200._lib import operand_format
+    P = operand_format().parts
     kp = (k + 31) // 32 * 32
     nkb = kp // 32
     t = t.view(torch.int16).numpy().view(np.uint16)
-    parts = [np.zeros((n, kp), np.float32) for _ in range(3)]
+    parts = [np.zeros((n, kp), np.float32) for _ in range(P)]
     for r in range(n):
         n0 = r // 256 * 256
         bn = min(256, n - n0)
         rr = r - n0
         for kb in range(nkb):
             for ch in range(4):
-                # element offsets: n tile base, K-block base (3 pieces of bn x 32), 8-row group, row, swizzled chunk
-                base = n0 * nkb * 96 + kb * bn * 96 + (rr // 8) * 256 + (rr % 8) * 32 + ((ch ^ ((rr >> 1) & 3)) * 8)
-                for p in range(3):
-                    parts[p][r, kb * 32 + ch * 8: kb * 32 + ch * 8 + 8] = _bf16_to_f32(
-                        t[base + p * bn * 32: base + p * bn * 32 + 8])
+                # element offsets: n tile base, K-block base (P pieces of bn x 32), 8-row group, row, swizzled chunk
+                base = n0 * nkb * 32 * P + kb * bn * 32 * P + (rr // 8) * 256 + (rr % 8) * 32 + ((ch ^ ((rr >> 1) & 3)) * 8)
+                for p in range(P):
+                    parts[p][r, kb * 32 + ch * 8: kb * 32 + ch * 8 + 8] = _piece_to_f32(
+                        t[base + p * bn * 32: base + p * bn * 32 + 8], P)
     return parts
 
 
 def test_weight_packing_layout():
-    from torchani_b200.engine import PackedNetworks, tile_a_operand, tile_b_operand, untile_a_operand
-    # the tiled / split / swizzled B operand round-trips and p1 + p2 + p3 == x to fp32 rounding
+    from torchani_b200._lib import operand_format
+    from torchani_b200.engine import (PackedNetworks, tile_a_operand, tile_b_operand, untile_a_operand,
+                                      weight_scale)
+    P = operand_format().parts
+    # the tiled / split / swizzled B operand round-trips and the pieces add up to scale * x
     b = torch.randn(288, 40, generator=torch.Generator().manual_seed(0))
-    p1, p2, p3 = _untile(tile_b_operand(b), 288, 40)
-    assert p1.shape == (288, 64)                                      # K padded to a multiple of 32
-    total = (p1.astype(np.float64) + p2 + p3)[:, :40]
-    assert np.abs(total - b.numpy()).max() <= np.abs(b.numpy()).max() * 2.0 ** -24
-    assert float(np.abs(p1[:, 40:]).max()) == 0.0
-    assert np.abs(p2).max() <= np.abs(b.numpy()).max() * 2.0 ** -8
-    assert np.abs(p3).max() <= np.abs(b.numpy()).max() * 2.0 ** -16
+    sc = weight_scale([b])
+    assert sc == (1.0 if P == 3 else 2.0 ** np.floor(np.log2(16384.0 / float(b.abs().max()))))
+    parts = _untile(tile_b_operand(b, sc), 288, 40)
+    assert parts[0].shape == (288, 64)                                # K padded to a multiple of 32
+    total = sum(q.astype(np.float64) for q in parts)[:, :40] / sc
+    # 3 x bf16: 24 significant bits; 2 x fp16: 22 bits, absolute floor 2^-25 / scale (half subnormals)
+    tol = np.abs(b.numpy()) * (2.0 ** -24 if P == 3 else 2.0 ** -22) + (0.0 if P == 3 else 2.0 ** -25 / sc)
+    assert (np.abs(total - b.numpy()) <= tol).all()
+    assert float(np.abs(parts[0][:, 40:]).max()) == 0.0
+    step = 2.0 ** -8 if P == 3 else 2.0 ** -11
+    for k in range(1, P):
+        assert np.abs(parts[k]).max() <= np.abs(b.numpy()).max() * sc * step ** k
     # A operand: tile / untile round trip
     x = torch.randn(256, 96, generator=torch.Generator().manual_seed(1))
     back = untile_a_operand(tile_a_operand(x), 256, 96)
-    assert float((back - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -23
+    assert float((back - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -22
     m = oracle_model("2x", members=3)
     w = [[wm[s] for s in m.symbols] for wm in m.weights]
     nets = PackedNetworks(w, 1008, torch.device("cpu"))
@@ -87,21 +99,26 @@ def test_weight_packing_layout():
     names = ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
     sp0 = dict(zip(names, nets._keep[:11]))
 
-    def close(parts, ref):
-        tot = parts[0].astype(np.float64) + parts[1] + parts[2]
-        return np.abs(tot - ref).max() <= max(np.abs(ref).max(), 1e-30) * 2.0 ** -24
+    E = 32 * P   # 16-bit elements per row of a K-block (all pieces)
 
+    def close(parts, ref, sc):
+        tot = sum(q.astype(np.float64) for q in parts) / sc
+        tol = np.abs(ref) * (2.0 ** -24 if P == 3 else 2.0 ** -22) + (0.0 if P == 3 else 2.0 ** -25 / sc)
+        return bool((np.abs(tot - ref) <= tol).all())
+
+    wsc = list(nets.model.sp[0].w_scale)
+    assert all(v == 1.0 for v in wsc[:3]) if P == 3 else all(v >= 1.0 and np.log2(v) % 1 == 0 for v in wsc[:3])
     # layer 1: members stacked along N, K padded to ldx with zeros
-    parts = _untile(sp0["t_f1"][: 256 * 32 * 96], 256, 1024)         # first n tile = member 0
-    assert close([q[:, :1008] for q in parts], m.weights[0]["H"][0][0].numpy())
+    parts = _untile(sp0["t_f1"][: 256 * 32 * E], 256, 1024)          # first n tile = member 0
+    assert close([q[:, :1008] for q in parts], m.weights[0]["H"][0][0].numpy(), wsc[0])
     assert float(np.abs(parts[0][:, 1008:]).max()) == 0.0
     # per-member layer 2 (forward: W2 [h2][h1]; backward: W2^T [h1][h2])
-    per = 192 * 8 * 96
-    assert close(_untile(sp0["t_f2"][2 * per: 3 * per], 192, 256), m.weights[2]["H"][1][0].numpy())
-    per = 256 * 6 * 96
-    assert close(_untile(sp0["t_b2"][per: 2 * per], 256, 192), m.weights[1]["H"][1][0].t().numpy())
+    per = 192 * 8 * E
+    assert close(_untile(sp0["t_f2"][2 * per: 3 * per], 192, 256), m.weights[2]["H"][1][0].numpy(), wsc[1])
+    per = 256 * 6 * E
+    assert close(_untile(sp0["t_b2"][per: 2 * per], 256, 192), m.weights[1]["H"][1][0].t().numpy(), wsc[1])
     assert torch.equal(sp0["w4"][2], m.weights[2]["H"][3][0][0])
-    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 32) * 96
+    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 32) * E
     nets.set_active_members([0, 2])
     assert list(nets.model.member_scale)[:3] == [0.5, 0.0, 0.5]
     with pytest.raises(IndexError):

@@ -7,9 +7,11 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import typing as tp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libani_b200.so")
+# ANI_B200_LIB selects another build of the same library (e.g. the 3 x bf16 operand variant)
+LIB_PATH = os.environ.get("ANI_B200_LIB") or os.path.join(HERE, "libani_b200.so")
 
 ANI_MAX_SPECIES = 8
 ANI_MAX_SHFR = 32
@@ -23,6 +25,7 @@ STATUS_NBR_OVERFLOW = 1
 STATUS_ANG_OVERFLOW = 2
 STATUS_CELL_TOO_SMALL = 4
 STATUS_PAIR_OVERFLOW = 8
+STATUS_OPERAND_RANGE = 16
 
 
 class AEVParams(C.Structure):
@@ -45,7 +48,8 @@ class Grid(C.Structure):
 
 
 class MLPSpecies(C.Structure):
-    _fields_ = [("h1", C.c_int32), ("h2", C.c_int32), ("h3", C.c_int32), ("pad_", C.c_int32)] + [
+    _fields_ = [("h1", C.c_int32), ("h2", C.c_int32), ("h3", C.c_int32), ("pad_", C.c_int32),
+                ("w_scale", C.c_float * 4)] + [
         (k, C.c_void_p) for k in ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
     ]
 
@@ -65,6 +69,7 @@ _F = C.c_float
 
 _PROTOTYPES = {
     "ani_b200_abi_version": (C.c_int, []),
+    "ani_b200_operand_format": (C.c_int, [_P, _P, _P]),
     "ani_b200_error_string": (C.c_char_p, [_I]),
     "ani_b200_last_cuda_error": (C.c_char_p, []),
     "ani_b200_build_cells": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -79,7 +84,7 @@ _PROTOTYPES = {
     "ani_b200_debug_gemm_trace": (C.c_int, [_P, _I]),
     "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "ani_b200_half_neighbor_fill": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
-    "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ani_b200_active_aev_blocks": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ani_b200_reduce_energies": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
@@ -102,7 +107,7 @@ def _load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ani_b200_abi_version() != 1:
+    if lib.ani_b200_abi_version() != 2:
         raise ImportError("libani_b200.so ABI version mismatch")
     return lib
 
@@ -115,6 +120,25 @@ def lib() -> C.CDLL:
     if _lib is None:
         _lib = _load()
     return _lib
+
+
+class OperandFormat(tp.NamedTuple):
+    parts: int           # 16-bit pieces per value: 2 = IEEE half, 3 = bfloat16
+    value_scale: float   # power-of-two scale of AEV / activation operands
+    grad_scale: float    # power-of-two scale of gradient operands
+
+
+_fmt = None
+
+
+def operand_format() -> OperandFormat:
+    """The tiled-operand format the loaded library was compiled for (ani_b200_operand_format)."""
+    global _fmt
+    if _fmt is None:
+        parts, vs, gs = C.c_int32(0), C.c_float(0), C.c_float(0)
+        check(lib().ani_b200_operand_format(C.byref(parts), C.byref(vs), C.byref(gs)), "operand_format")
+        _fmt = OperandFormat(int(parts.value), float(vs.value), float(gs.value))
+    return _fmt
 
 
 def check(rc: int, what: str = "") -> None:

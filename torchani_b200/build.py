@@ -3,6 +3,10 @@
 The library has no torch / python dependency: plain ``extern "C"`` entry points declared in
 ``include/ani_b200.h``.  ``python -m torchani_b200.build`` (or ``__graft_entry__.build()``)
 compiles every ``csrc/*.cu`` and links them next to this file.
+
+Variants: the default library uses 2 x fp16 GEMM operand pieces; ``build(variant="bf16x3")``
+(``python -m torchani_b200.build --variant bf16x3``) compiles the same sources with
+``-DANI_OPND_FP16X2=0`` into ``libani_b200_bf16x3.so`` (select it with ``ANI_B200_LIB=<path>``).
 """
 from __future__ import annotations
 
@@ -36,30 +40,40 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _fingerprint() -> str:
+VARIANTS = {"": [], "bf16x3": ["-DANI_OPND_FP16X2=0"]}
+
+
+def lib_path(variant: str = "") -> str:
+    return LIB if not variant else os.path.join(HERE, f"libani_b200_{variant}.so")
+
+
+def _fingerprint(extra=()) -> str:
     h = hashlib.sha256()
     files = _sources() + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
     files.append(os.path.join(os.path.dirname(HERE), "include", "ani_b200.h"))
     for f in files:
         with open(f, "rb") as fh:
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(list(NVCC_FLAGS) + list(extra)).encode())
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(BUILD, exist_ok=True)
-    stamp = os.path.join(BUILD, "fingerprint.txt")
-    fp = _fingerprint()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
-        return LIB
+def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
+    extra = VARIANTS[variant]
+    bdir = BUILD if not variant else BUILD + "_" + variant
+    lib = lib_path(variant)
+    os.makedirs(bdir, exist_ok=True)
+    stamp = os.path.join(bdir, "fingerprint.txt")
+    fp = _fingerprint(extra)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == fp:
+        return lib
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", src, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(BUILD, os.path.basename(src)[:-3] + ".ptxas.log")
+        log = os.path.join(bdir, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as fh:
             fh.write(res.stdout + res.stderr)
         if res.returncode != 0:
@@ -70,14 +84,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "--cudart", "shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "--cudart", "shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     with open(stamp, "w") as fh:
         fh.write(fp)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=_variant))

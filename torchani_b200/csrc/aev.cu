@@ -267,19 +267,21 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const int i = lo + blockIdx.x * AEV_WARPS + warp;
   if (i >= hi) return;
   const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, false);
-  // output: plain row-major rows, or the 3 x bf16 tiled operand layout the GEMM consumes
+  // output: plain row-major rows, or the tiled operand layout (16-bit pieces) the GEMM consumes
   const int out_row = row_of[i];
   const int kblocks = ldx >> 5;
+  float vmax = 0.f;  // largest scaled feature this lane wrote (operand range check, fp16 pieces)
   auto store_feature = [&](int col, float v) {
     if (layout == 0) {
       aev[(size_t)out_row * ldx + col] = v;
     } else {
       unsigned char* dst = reinterpret_cast<unsigned char*>(aev) + opnd_offset(out_row, col, kblocks);
-      unsigned short p1, p2, p3;
-      split3(v, p1, p2, p3);
-      *reinterpret_cast<unsigned short*>(dst) = p1;
-      *reinterpret_cast<unsigned short*>(dst + OPND_PART_BYTES) = p2;
-      *reinterpret_cast<unsigned short*>(dst + 2 * OPND_PART_BYTES) = p3;
+      unsigned short pc[OPND_PARTS];
+      v *= OPND_SCALE_VALUE;
+      vmax = fmaxf(vmax, v);  // AEV features are >= 0
+      opnd_split(v, pc);
+#pragma unroll
+      for (int k = 0; k < OPND_PARTS; ++k) *reinterpret_cast<unsigned short*>(dst + k * OPND_PART_BYTES) = pc[k];
     }
   };
   const int S = P.num_species;
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
       store_feature(RL + p * 32 + lane, out);
     }
   }
+  if (ANI_OPND_FP16X2 && !(vmax <= OPND_HALF_MAX)) atomicOr(status, ANI_STATUS_OPERAND_RANGE);
 }
 
 // ---------------------------------------------------------------------------------------

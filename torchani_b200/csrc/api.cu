@@ -15,6 +15,13 @@ void set_cuda_error(cudaError_t e) {
 
 extern "C" int ani_b200_abi_version(void) { return ANI_B200_ABI_VERSION; }
 
+extern "C" int ani_b200_operand_format(int32_t* parts, float* value_scale, float* grad_scale) {
+  if (parts) *parts = ani::OPND_PARTS;
+  if (value_scale) *value_scale = ani::OPND_SCALE_VALUE;
+  if (grad_scale) *grad_scale = ani::OPND_SCALE_GRAD;
+  return ANI_OK;
+}
+
 extern "C" const char* ani_b200_error_string(int code) {
   switch (code) {
     case ANI_OK: return "ok";

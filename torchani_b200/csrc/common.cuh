@@ -108,36 +108,68 @@ __device__ __forceinline__ float3 image_shift(const ani_grid& g, int code) {
 }
 
 // ---- "tiled operand" layout shared by the AEV kernel (producer) and the tensor-core GEMM ----
-// A matrix [rows][cols] is stored per 128-row tile and 32-column K-block as three bfloat16 pieces
-// (x = p1 + p2 + p3): [p1 128 rows x 64 B | p2 128 x 64 B | p3 128 x 64 B] (24 KB), every 8-row
-// group in SWIZZLE_64B order (16-byte chunk c of row r sits at position c ^ ((r >> 1) & 3)).
+// A matrix [rows][cols] is stored per 128-row tile and 32-column K-block as OPND_PARTS 16-bit
+// pieces: [p1 128 rows x 64 B | p2 128 x 64 B (| p3)], every 8-row group in SWIZZLE_64B order
+// (16-byte chunk c of row r sits at position c ^ ((r >> 1) & 3)).
+//   ANI_OPND_FP16X2 = 1 (default): two IEEE half pieces of s*x (s = a power of two per operand
+//     class, below), s*x = p1 + p2 with |residual| < 2^-22 |s*x| (two 11-bit significands):
+//     4 B/element, three MMAs per product.  The scale keeps p2 out of the half subnormals for
+//     every value that matters (absolute error < 2^-25 / s) and is divided out, exactly, in the
+//     epilogue of the consuming GEMM.
+//   ANI_OPND_FP16X2 = 0: three bfloat16 pieces x = p1 + p2 + p3 (no scale needed, 8-bit exponent):
+//     6 B/element, six MMAs per product.
+#ifndef ANI_OPND_FP16X2
+#define ANI_OPND_FP16X2 1
+#endif
 constexpr int OPND_KB = 32;                                      // columns per K-block
-constexpr int OPND_PARTS = 3;
-constexpr int OPND_ROW_BYTES = 64;                               // 32 bf16
+constexpr int OPND_PARTS = ANI_OPND_FP16X2 ? 2 : 3;
+constexpr int OPND_ROW_BYTES = 64;                               // 32 halves / bfloat16
 constexpr int OPND_PART_BYTES = ANI_TILE_ROWS * OPND_ROW_BYTES;  // 8 KB
-constexpr int OPND_BLOCK_BYTES = OPND_PARTS * OPND_PART_BYTES;   // 24 KB
+constexpr int OPND_BLOCK_BYTES = OPND_PARTS * OPND_PART_BYTES;   // 16 KB (24 KB for 3 x bf16)
+// operand scales (powers of two).  Values: AEVs and CELU activations (|v| < 1023 representable);
+// gradients dE/d(activation) (|g| < 16 representable).  Weights carry a per-tensor scale chosen by
+// the packer (ani_mlp_species::w_scale).  Out-of-range values become inf/NaN downstream and raise
+// ANI_STATUS_OPERAND_RANGE.
+constexpr float OPND_SCALE_VALUE = ANI_OPND_FP16X2 ? 64.0f : 1.0f;
+constexpr float OPND_SCALE_GRAD = ANI_OPND_FP16X2 ? 4096.0f : 1.0f;
+constexpr float OPND_HALF_MAX = 65504.0f;
 // byte offset of 16-byte chunk `ch` (0..3) of row `row` (0..127) inside one piece
 __device__ __forceinline__ uint32_t swz_off(int row, int ch) {
   return (uint32_t)(row >> 3) * 512u + (uint32_t)(row & 7) * 64u + (uint32_t)((ch ^ ((row >> 1) & 3)) << 4);
 }
 // byte offset of element (row, col), piece 0, of a tiled matrix with `kblocks` = cols/32 blocks
-// per row tile; pieces 1 and 2 are OPND_PART_BYTES and 2*OPND_PART_BYTES further
+// per row tile; piece k is k * OPND_PART_BYTES further
 __device__ __forceinline__ size_t opnd_offset(int row, int col, int kblocks) {
   const int rt = row / ANI_TILE_ROWS, r = row % ANI_TILE_ROWS;
   return ((size_t)rt * kblocks + (col >> 5)) * OPND_BLOCK_BYTES + swz_off(r, (col & 31) >> 3) + (size_t)(col & 7) * 2;
 }
-// x = p1 + p2 + p3, bfloat16 pieces rounded to nearest (bit patterns)
-__device__ __forceinline__ void split3(float v, unsigned short& p1, unsigned short& p2, unsigned short& p3) {
+// one value (already multiplied by its operand scale) -> OPND_PARTS 16-bit pieces (bit patterns)
+__device__ __forceinline__ void opnd_split(float v, unsigned short (&p)[OPND_PARTS]) {
+#if ANI_OPND_FP16X2
+  auto rn = [](float x) -> unsigned short {
+    unsigned short h;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+  };
+  auto up = [](unsigned short h) -> float {
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f;
+  };
+  p[0] = rn(v);
+  p[1] = rn(v - up(p[0]));
+#else
   auto rn = [](float x) -> unsigned short {
     unsigned short h;
     asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
     return h;
   };
-  p1 = rn(v);
-  v -= __uint_as_float((uint32_t)p1 << 16);
-  p2 = rn(v);
-  v -= __uint_as_float((uint32_t)p2 << 16);
-  p3 = rn(v);
+  p[0] = rn(v);
+  v -= __uint_as_float((uint32_t)p[0] << 16);
+  p[1] = rn(v);
+  v -= __uint_as_float((uint32_t)p[1] << 16);
+  p[2] = rn(v);
+#endif
 }
 
 }  // namespace ani

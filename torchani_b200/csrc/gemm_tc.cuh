@@ -2,16 +2,20 @@
 //
 //   C[128-row tile, bn] = epilogue( A[128, K] x B[bn, K]^T )        both operands K-major
 //
-// fp32 accuracy on the tensor cores ("3 x bf16"): every fp32 operand x is stored as three
-// bfloat16 pieces x = p1 + p2 + p3 (round to nearest, residual < 2^-26 |x|); the MMA thread issues
-// six kind::f16 (bf16 x bf16 -> fp32) products per K-step,
-//     a3 b1, a1 b3, a2 b2, a2 b1, a1 b2, a1 b1      (the dropped ones are < 2^-26 relative),
-// into one fp32 accumulator in tensor memory.  Same tensor time as a 3-product TF32 split (bf16
-// runs at twice the TF32 rate) at 6 instead of 8 bytes per element: the six launches of a step
-// are bound by the bytes they move through the L2, not by the MMAs.
+// fp32 accuracy on the tensor cores from 16-bit pieces (common.cuh, ANI_OPND_FP16X2):
+//   * default "2 x fp16": every fp32 operand x is stored as two IEEE half pieces of s*x
+//     (s*x = p1 + p2, residual < 2^-22 |s*x|; s = a power of two per operand class that keeps p2 a
+//     normal half); the MMA thread issues three kind::f16 products per K-step,
+//         a2 b1, a1 b2, a1 b1          (the dropped a2 b2 is < 2^-22 relative),
+//     into one fp32 accumulator in tensor memory; the epilogue multiplies by 1/(s_a s_b) (exact).
+//     4 bytes per element and half the tensor time of the alternative:
+//   * "3 x bf16": x = p1 + p2 + p3 bfloat16 pieces, six products (a3b1, a1b3, a2b2, a2b1, a1b2,
+//     a1b1), 6 bytes per element, no scale.
+// The six launches of a step are bound by the bytes they move through the L2, not by the MMAs
+// (DESIGN.md 4.1), so bytes per element is the figure of merit.
 //
 // BOTH operands live in global memory in the "tiled operand" layout of include/ani_b200.h:
-// 32-column K-blocks, [p1 rows x 64 B | p2 rows x 64 B | p3 rows x 64 B], every 8-row group in
+// 32-column K-blocks, [p1 rows x 64 B | p2 rows x 64 B (| p3 rows x 64 B)], every 8-row group in
 // SWIZZLE_64B order.
 //   * B (weights) is tiled once at model-pack time,
 //   * A (activations / gradients) is written in that layout by the epilogue of the GEMM (or by
@@ -23,15 +27,16 @@
 // Roles (10 warps, one CTA per SM, persistent over the device-side tile list):
 //   warps 0-7  epilogue : tcgen05.ld (thread = row; warps w and w+4 share TMEM lanes and take
 //                         alternate 32-column groups), bias + CELU | * CELU'(stored activation) |
-//                         final layer + gradient seed | plain; 3-way split, staged in shared
+//                         final layer + gradient seed | plain; split into pieces, staged in shared
 //                         memory in the final byte order and written by TMA bulk stores
 //   warp  8    MMA      : TMEM alloc, one lane issues tcgen05.mma / tcgen05.commit
 //   warp  9    producer : one lane arms the mbarrier (expect_tx) and issues the bulk copies
-// Pipelines: smem full/empty (2-6 stages of 24 KB + 3 x bn x 64 B, sized on the device from the
+// Pipelines: smem full/empty (2-6 stages of PARTS x (8 KB + bn x 64 B), sized on the device from the
 // widest accumulator of the launch) and TMEM full/empty (2 x 256 columns), so the epilogue of
 // tile i overlaps the main loop of tile i+1; TMEM loads run one half group ahead of the math.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -40,15 +45,15 @@ namespace tc {
 
 constexpr int TM = ANI_TILE_ROWS;        // 128 rows per tile == UMMA M
 constexpr int TN_MAX = 256;              // UMMA N (columns of one accumulator)
-constexpr int TK = OPND_KB;              // 32 columns per K-block = one 64-byte swizzle row of bf16
+constexpr int TK = OPND_KB;              // 32 columns per K-block = one 64-byte swizzle row of 16-bit pieces
 constexpr int ROW_BYTES = OPND_ROW_BYTES;        // 64
 constexpr int GROUP_BYTES = 8 * ROW_BYTES;       // 8-row swizzle group = 512 B (descriptor SBO)
-constexpr int PARTS = OPND_PARTS;                // 3
+constexpr int PARTS = OPND_PARTS;                // 2 (fp16) or 3 (bf16)
 constexpr int MAX_STAGES = 6;
 constexpr int A_PART_BYTES = OPND_PART_BYTES;    // 8 KB (one piece of one A K-block)
-constexpr int A_BLOCK_BYTES = OPND_BLOCK_BYTES;  // 24 KB: [p1 | p2 | p3], contiguous in global memory
+constexpr int A_BLOCK_BYTES = OPND_BLOCK_BYTES;  // 16 / 24 KB: [p1 | p2 (| p3)], contiguous in global memory
 constexpr int EPI_PART_BYTES = 32 * ROW_BYTES;   // one piece of a warp's 32 rows x 32 columns = 2 KB
-constexpr int EPI_STAGE_BYTES = PARTS * EPI_PART_BYTES;  // 6 KB per epilogue warp and buffer
+constexpr int EPI_STAGE_BYTES = PARTS * EPI_PART_BYTES;  // 4 / 6 KB per epilogue warp and buffer
 constexpr int NUM_EPI_WARPS = 8, MMA_WARP = 8, PROD_WARP = 9;
 // always (almost) the whole SM: the pipeline depth adapts on the device.  6 KB of the 227 KB are
 // left for the static shared memory (tile map, barriers, bias staging, EPI_HEAD partial sums)
@@ -68,10 +73,11 @@ struct Species {
   // split-K over the members (layer-1 backward): all members share ONE B operand with b_kblocks
   // K-blocks, member m starts at K-block m * b_kb_moff.  0: one B operand per member.
   int b_kblocks, b_kb_moff;
+  float acc_scale;  // 1 / (scale of A x scale of this B operand): multiplies the raw accumulator
 };
 
 struct Args {
-  const unsigned char* A;       // tiled activation matrix [row tile][a_kblocks][p1 | p2 | p3]
+  const unsigned char* A;       // tiled activation matrix [row tile][a_kblocks][p1 | p2 (| p3)]
   void* C;                      // tiled activation matrix (EPI_PLAIN: plain row-major float [rows][ldc])
   int a_kblocks, c_kblocks;     // 32-column blocks per row of A / C  (= leading dimension / 32)
   int ldc;                      // EPI_PLAIN only
@@ -88,6 +94,9 @@ struct Args {
   int want_backward;
   int c_accumulate;             // EPI_PLAIN: C += tile (vector RED), C zeroed by the caller
   long long* trace;             // optional clock64 stamps [cta < 4][tile < 8][role 3][4] (ani_b200_debug_gemm_trace)
+  float out_scale;              // operand scale of a tiled C (OPND_SCALE_VALUE activations / OPND_SCALE_GRAD gradients)
+  float y_inv_scale;            // EPI_MUL_DCELU: 1 / scale of the stored activation that C overwrites
+  int32_t* status;              // ANI_STATUS_OPERAND_RANGE is raised here (may be NULL)
   int debug;                    // timing experiments only (ANI_B200_GEMM_DEBUG): 2 no copies, 4 no MMA, 8 no epilogue
   float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
@@ -152,8 +161,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 inputs, fp32 accumulate), single CTA
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (half or bf16 inputs per the instruction
+// descriptor, fp32 accumulate), single CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -198,9 +208,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;                        // SWIZZLE_64B
   return d;
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=bn
+// instruction descriptor: D=f32, A=B=f16 (format 0) or bf16 (format 1), both K-major, M=128, N=bn
 __device__ __forceinline__ uint32_t make_idesc(int bn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  constexpr uint32_t fmt = ANI_OPND_FP16X2 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
 // CELU(x) = max(0,x) + min(0, alpha*(exp(x/alpha)-1)) with exp via ex2.approx (rel. error ~2^-22:
@@ -283,27 +294,45 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
   return x;
 }
 
-// ---- 3-way bf16 split of two adjacent fp32 values -> three packed bf16x2 words (low half = a)
-__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& w1, uint32_t& w2, uint32_t& w3) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  w1 = *reinterpret_cast<uint32_t*>(&p);
-  a -= __uint_as_float(w1 << 16);
-  b -= __uint_as_float(w1 & 0xffff0000u);
-  p = __floats2bfloat162_rn(a, b);
-  w2 = *reinterpret_cast<uint32_t*>(&p);
-  a -= __uint_as_float(w2 << 16);
-  b -= __uint_as_float(w2 & 0xffff0000u);
-  p = __floats2bfloat162_rn(a, b);
-  w3 = *reinterpret_cast<uint32_t*>(&p);
+// ---- split of two adjacent (already scaled) fp32 values into PARTS packed 16-bit pairs (low half = a)
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t (&w)[PARTS]) {
+#if ANI_OPND_FP16X2
+  __half2 h = __floats2half2_rn(a, b);
+  w[0] = *reinterpret_cast<uint32_t*>(&h);
+  const float2 f = __half22float2(h);
+  h = __floats2half2_rn(a - f.x, b - f.y);
+  w[1] = *reinterpret_cast<uint32_t*>(&h);
+#else
+#pragma unroll
+  for (int p = 0; p < PARTS; ++p) {
+    __nv_bfloat162 q = __floats2bfloat162_rn(a, b);
+    w[p] = *reinterpret_cast<uint32_t*>(&q);
+    a -= __uint_as_float(w[p] << 16);
+    b -= __uint_as_float(w[p] & 0xffff0000u);
+  }
+#endif
 }
-// sum of the three pieces of 8 consecutive columns (three 16-byte chunks) -> 8 floats
-__device__ __forceinline__ void join3_chunk(const uint4& q1, const uint4& q2, const uint4& q3, float* y) {
-  const uint32_t a[4] = {q1.x, q1.y, q1.z, q1.w}, b[4] = {q2.x, q2.y, q2.z, q2.w}, c[4] = {q3.x, q3.y, q3.z, q3.w};
+// sum of the pieces of 8 consecutive columns (one 16-byte chunk per piece; q[2 * p]) -> 8 floats
+// (still multiplied by the operand scale)
+__device__ __forceinline__ void join_chunk(const uint4* q, float* y) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    y[2 * i] = __uint_as_float(a[i] << 16) + __uint_as_float(b[i] << 16) + __uint_as_float(c[i] << 16);
-    y[2 * i + 1] = __uint_as_float(a[i] & 0xffff0000u) + __uint_as_float(b[i] & 0xffff0000u) +
-                   __uint_as_float(c[i] & 0xffff0000u);
+    float lo = 0.f, hi = 0.f;
+#pragma unroll
+    for (int p = PARTS - 1; p >= 0; --p) {  // smallest piece first
+      const uint4& v = q[2 * p];
+      const uint32_t word = i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+#if ANI_OPND_FP16X2
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&word));
+      lo += f.x;
+      hi += f.y;
+#else
+      lo += __uint_as_float(word << 16);
+      hi += __uint_as_float(word & 0xffff0000u);
+#endif
+    }
+    y[2 * i] = lo;
+    y[2 * i + 1] = hi;
   }
 }
 
@@ -436,18 +465,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BLOCK_BYTES;
-          const uint64_t a1 = make_desc(sa), a2 = make_desc(sa + A_PART_BYTES), a3 = make_desc(sa + 2 * A_PART_BYTES);
-          const uint64_t b1 = make_desc(sb), b2 = make_desc(sb + b_bytes), b3 = make_desc(sb + 2 * b_bytes);
+          const uint64_t a1 = make_desc(sa), a2 = make_desc(sa + A_PART_BYTES);
+          const uint64_t b1 = make_desc(sb), b2 = make_desc(sb + b_bytes);
+#if !ANI_OPND_FP16X2
+          const uint64_t a3 = make_desc(sa + 2 * A_PART_BYTES), b3 = make_desc(sb + 2 * b_bytes);
+#endif
 #pragma unroll
           for (int k = 0; k < TK / 16; ++k) {
             if (args.debug & 4) break;
-            const uint64_t adv = (uint64_t)(k * 2);  // 16 bf16 = 32 B = 2 x 16 B along the swizzle row
-            umma_bf16(d_tmem, a3 + adv, b1 + adv, idesc, (kb | k) != 0);  // smallest terms first
-            umma_bf16(d_tmem, a1 + adv, b3 + adv, idesc, 1);
-            umma_bf16(d_tmem, a2 + adv, b2 + adv, idesc, 1);
-            umma_bf16(d_tmem, a2 + adv, b1 + adv, idesc, 1);
-            umma_bf16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
-            umma_bf16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
+            const uint64_t adv = (uint64_t)(k * 2);  // 16 pieces = 32 B = 2 x 16 B along the swizzle row
+            // smallest terms first
+#if ANI_OPND_FP16X2
+            umma_f16(d_tmem, a2 + adv, b1 + adv, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
+            umma_f16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
+#else
+            umma_f16(d_tmem, a3 + adv, b1 + adv, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a1 + adv, b3 + adv, idesc, 1);
+            umma_f16(d_tmem, a2 + adv, b2 + adv, idesc, 1);
+            umma_f16(d_tmem, a2 + adv, b1 + adv, idesc, 1);
+            umma_f16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
+            umma_f16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
+#endif
           }
           umma_commit(&empty[stage]);                   // smem slot free once these MMAs retire
           if (kb == nkb - 1) {
@@ -471,6 +510,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     // Thread = accumulator row (TMEM lane).  Warps w and w+4 share the 32 lanes of quadrant w & 3
     // and take alternate 32-column groups (= K-blocks of the next GEMM), each as two 16-column halves.
     uint32_t acc = 0, acc_phase = 0, buf = 0;
+    float omax = 0.f;  // largest |scaled value| this thread handed to the half-precision split
     const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
     const int quad = warp & 3, half = warp >> 2;
     const int r_tile = quad * 32 + lane;  // row inside the 128-row tile
@@ -489,6 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
       const Tile tl = decode_tile(args, tm, t);
       const Species& sp = args.sp[tl.s];
+      const float acc_scale = sp.acc_scale;
       if (threadIdx.x == 0) stamp(tloc, 2, 0);
       // bias (and final-layer weights) of this tile -> shared memory while the main loop runs
       const float* __restrict__ bias = s_bias[acc];
@@ -513,8 +554,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
                           ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
       float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
       const int ngroups = tl.bn / 32;
-      // stored activation (three pieces) of 16 columns = chunks 2*hh, 2*hh+1 of group g, this thread's row
-      uint4 yq[6];
+      // stored activation (all pieces) of 16 columns = chunks 2*hh, 2*hh+1 of group g, this thread's row
+      uint4 yq[2 * PARTS];
       auto load_y = [&](int g, int hh) {
         const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
 #pragma unroll
@@ -533,8 +574,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       auto process = [&](int g, int hh, const uint32_t (&r)[16]) {
         float y[16];
         if (EPI == EPI_MUL_DCELU) {
-          join3_chunk(yq[0], yq[2], yq[4], y);
-          join3_chunk(yq[1], yq[3], yq[5], y + 8);
+          join_chunk(yq, y);
+          join_chunk(yq + 1, y + 8);
           if (!(args.debug & 128)) {  // prefetch the next half this warp handles
             if (hh == 0)
               load_y(g, 1);
@@ -557,16 +598,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v = __uint_as_float(r[j]);
+          float v = __uint_as_float(r[j]) * acc_scale;
           if (EPI == EPI_BIAS_CELU) {
             v = celu(v + bias[c0 + j], cc);
           } else if (EPI == EPI_MUL_DCELU) {
-            v *= dcelu_from_out(y[j], cc);
+            v *= dcelu_from_out(y[j] * args.y_inv_scale, cc);
           } else if (EPI == EPI_HEAD) {
             const float w = w4[c0 + j];
             const float a = celu(v + bias[c0 + j], cc);
             e_acc = fmaf(a, w, e_acc);
             v = seed * w * dcelu_from_out(a, cc);
+          }
+          if (EPI != EPI_PLAIN) {
+            v *= args.out_scale;
+            omax = fmaxf(omax, fabsf(v));
           }
           o[j] = v;
         }
@@ -585,13 +630,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         } else if (tiled_out) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {  // chunk 2*hh + c = columns 8c .. 8c+7 of this half
-            uint32_t w1[4], w2[4], w3[4];
+            uint32_t w[4][PARTS];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split3_pair(o[8 * c + 2 * i], o[8 * c + 2 * i + 1], w1[i], w2[i], w3[i]);
+            for (int i = 0; i < 4; ++i) split_pair(o[8 * c + 2 * i], o[8 * c + 2 * i + 1], w[i]);
             const uint32_t off = st_off[2 * hh + c];
-            *reinterpret_cast<uint4*>(sb + off) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
-            *reinterpret_cast<uint4*>(sb + EPI_PART_BYTES + off) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-            *reinterpret_cast<uint4*>(sb + 2 * EPI_PART_BYTES + off) = make_uint4(w3[0], w3[1], w3[2], w3[3]);
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p)
+              *reinterpret_cast<uint4*>(sb + p * EPI_PART_BYTES + off) = make_uint4(w[0][p], w[1][p], w[2][p], w[3][p]);
           }
           if (hh == 1) {
             unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES + quad * EPI_PART_BYTES;
@@ -637,6 +682,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         acc_phase ^= 1;
       }
     }
+    if (ANI_OPND_FP16X2 && args.status && !(omax <= OPND_HALF_MAX)) atomicOr(args.status, ANI_STATUS_OPERAND_RANGE);
   }
 
   // ---- teardown

@@ -10,7 +10,8 @@
 // Backward-to-input runs the same kernel on the transposed weights; CELU'(x) is recovered
 // from the stored activation y as (y > 0 ? 1 : (y + alpha) / alpha)  (csrc/mnp.cpp:206-209).
 //
-// Arithmetic: tcgen05 tensor cores with an fp32-accurate 3 x bf16 split (gemm_tc.cuh).
+// Arithmetic: tcgen05 tensor cores on fp32-accurate 16-bit operand pieces (2 x fp16 with power-of-two
+// operand scales, or 3 x bf16; gemm_tc.cuh / common.cuh).
 #include <stdlib.h>
 #include <string.h>
 
@@ -129,7 +130,7 @@ static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st) {
 extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
                                              const int32_t* row_atom, const int32_t* layout_info,
                                              const int32_t* aev_blocks, void* act1, void* act2, void* act3,
-                                             float* e_member, int want_backward, void* stream) {
+                                             float* e_member, int want_backward, int32_t* status, void* stream) {
   if (!model || !x || !row_atom || !layout_info || !act1 || !act2 || !act3 || !e_member) return ANI_ERR_BAD_ARG;
   if (want_backward && !dx) return ANI_ERR_BAD_ARG;
   const int S = model->num_species, M = model->num_members;
@@ -144,6 +145,8 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
     if (p.h3 > tc::TN_MAX) return ANI_ERR_UNSUPPORTED;  // the fused final layer needs h3 in one accumulator
     if (!p.b1 || !p.b2 || !p.b3 || !p.w4 || !p.b4 || !p.t_f1 || !p.t_f2 || !p.t_f3 || !p.t_b3 || !p.t_b2 || !p.t_b1)
       return ANI_ERR_BAD_ARG;
+    for (int l = 0; l < 3; ++l)
+      if (ANI_OPND_FP16X2 && !(p.w_scale[l] > 0.f)) return ANI_ERR_BAD_ARG;
   }
   cudaStream_t st = (cudaStream_t)stream;
   // 32-column blocks per row of the tiled activation matrices
@@ -166,13 +169,21 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
   }();
   ta.debug = gemm_debug;
   for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ta.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
-  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, 0, 0};
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, 0, 0, 1.0f};
+  ta.status = status;
+  // operand scales (common.cuh): activations / AEVs carry sv, gradients sg, weights their per-tensor
+  // w_scale; every GEMM divides the product of its two operand scales out of the accumulator
+  const float sv = OPND_SCALE_VALUE, sg = OPND_SCALE_GRAD;
+  auto wsc = [&](const ani_mlp_species& p, int layer) { return ANI_OPND_FP16X2 ? p.w_scale[layer] : 1.0f; };
+  ta.out_scale = sv;
+  ta.y_inv_scale = 1.0f / sv;
 
   // ---- forward.  Layer 1: the members share the input -> one GEMM with N = M*h1.
   ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr, 0, 0};
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr, 0, 0,
+                            1.0f / (sv * wsc(p, 0))};
   }
   ta.kblocks = aev_blocks;  // dead AEV column blocks contribute exact zeros: skip them
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
@@ -180,29 +191,34 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
   ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f2), p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr, 0, 0};
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f2), p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr, 0, 0,
+                            1.0f / (sv * wsc(p, 1))};
   }
   launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
   ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f3), p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4, 0, 0};
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f3), p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4, 0, 0,
+                            1.0f / (sv * wsc(p, 2))};
   }
   // layer 3 + final layer (h3 -> 1) + gradient seed, fused in the epilogue: act3 receives
   // G3 = scale_m * w4 * celu'(a3) directly, e_member the per-member atomic energies
+  ta.out_scale = sg;  // act3 receives the gradient seed
   launch_gemm_tc<tc::EPI_HEAD>(ta, st);
   if (want_backward) {
     // ---- backward: G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
     ta.A = static_cast<const unsigned char*>(act3); ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b3), nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0};
+      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b3), nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0,
+                              1.0f / (sg * wsc(p, 2))};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
     ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0};
+      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0,
+                              1.0f / (sg * wsc(p, 1))};
     }
     launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
     // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
@@ -211,7 +227,8 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
     ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr, M * p.h1 / 32, p.h1 / 32};
+      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr, M * p.h1 / 32, p.h1 / 32,
+                              1.0f / (sg * wsc(p, 0))};
     }
     ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
     ta.c_accumulate = M > 1;

@@ -94,13 +94,32 @@ def constants_1x(num_species: int = 4, cutoff_fn: str = "cosine") -> AEVConstant
                         _linspace(0.9, 3.5, 4), _linspace(a0, math.pi + a0, 8), cutoff_fn)
 
 
-def _split3(x: Tensor) -> tp.List[Tensor]:
-    """x (float32) -> three bfloat16 pieces with x = p1 + p2 + p3 (each rounded to nearest)."""
-    p1 = x.to(torch.bfloat16)
-    r = x - p1.to(torch.float32)
-    p2 = r.to(torch.bfloat16)
-    r = r - p2.to(torch.float32)
-    return [p1, p2, r.to(torch.bfloat16)]
+def _split(x: Tensor, scale: float = 1.0) -> tp.List[Tensor]:
+    """x (float32) -> the 16-bit pieces of ``scale * x`` in the library's operand format
+    (``_lib.operand_format``): two IEEE half pieces or three bfloat16 pieces, each rounded to
+    nearest, ``scale * x = p1 + p2 (+ p3)``."""
+    fmt = _lib.operand_format()
+    dt = torch.float16 if fmt.parts == 2 else torch.bfloat16
+    r = x.to(torch.float32) * scale
+    out = []
+    for _ in range(fmt.parts):
+        p = r.to(dt)
+        out.append(p)
+        r = r - p.to(torch.float32)
+    return out
+
+
+def weight_scale(ws: tp.Sequence[Tensor]) -> float:
+    """Power-of-two operand scale for a group of weight matrices (half pieces: the largest
+    |scale * w| stays below 2^14, the scale below 2^12; bfloat16 pieces need none)."""
+    if _lib.operand_format().parts != 2:
+        return 1.0
+    top = max(float(w.abs().max()) for w in ws)
+    if not math.isfinite(top):
+        raise ValueError("network weights contain inf/NaN")
+    if top == 0.0:
+        return 4096.0
+    return float(min(4096.0, max(1.0, 2.0 ** math.floor(math.log2(16384.0 / top)))))
 
 
 def _swizzle_index(device) -> Tensor:
@@ -110,18 +129,18 @@ def _swizzle_index(device) -> Tensor:
     return pos ^ ((rows >> 1) & 3)
 
 
-def tile_b_operand(b: Tensor) -> Tensor:
+def tile_b_operand(b: Tensor, scale: float = 1.0) -> Tensor:
     """``B[N][K]`` (float32, K-major, N % 32 == 0) -> the "tiled B operand" byte layout of
-    include/ani_b200.h: K zero-padded to 32, three bfloat16 pieces,
-    [n tile of 256 rows][k block of 32][p1 bn x 64 B | p2 | p3] with every 8-row group in tcgen05
-    SWIZZLE_64B order.  Returned as a flat bfloat16 tensor."""
+    include/ani_b200.h: K zero-padded to 32, the 16-bit pieces of ``scale * B``,
+    [n tile of 256 rows][k block of 32][p1 bn x 64 B | p2 (| p3)] with every 8-row group in tcgen05
+    SWIZZLE_64B order.  Returned as a flat 16-bit tensor."""
     n, k = b.shape
     assert n % 32 == 0, "rows of a B operand must come in groups of 32"
     kp = (k + 31) // 32 * 32
     nkb = kp // 32
     bp = torch.zeros(n, kp, dtype=torch.float32, device=b.device)
     bp[:, :k] = b
-    pieces = _split3(bp)
+    pieces = _split(bp, scale)
     src_chunk = _swizzle_index(b.device)
     out = []
     for n0 in range(0, n, 256):
@@ -136,27 +155,42 @@ def tile_b_operand(b: Tensor) -> Tensor:
     return torch.cat(out).contiguous()
 
 
-def tile_a_operand(x: Tensor) -> Tensor:
+def tile_a_operand(x: Tensor, scale: tp.Optional[float] = None) -> Tensor:
     """Plain ``[rows][cols]`` float32 (rows % 128 == 0, cols % 32 == 0) -> flat "tiled operand"
-    (A-operand form of include/ani_b200.h, bfloat16).  Plumbing for the API paths that receive plain AEVs."""
+    (A-operand form of include/ani_b200.h; ``scale`` defaults to the library's value scale).
+    Plumbing for the API paths that receive plain AEVs."""
     rows, cols = x.shape
     assert rows % 128 == 0 and cols % 32 == 0
     nkb = cols // 32
+    if scale is None:
+        scale = _lib.operand_format().value_scale
     idx = _swizzle_index(x.device).view(1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 16, 8, 4, 8)
     parts = []
-    for part in _split3(x.contiguous().to(torch.float32)):
+    for part in _split(x.contiguous().to(torch.float32), scale):
         v = part.view(rows // 128, 16, 8, nkb, 4, 8).permute(0, 3, 1, 2, 4, 5)   # [rt][kb][grp][row][ch][8]
         parts.append(torch.gather(v, 4, idx).reshape(rows // 128, nkb, 4096))
     return torch.stack(parts, 2).reshape(-1).contiguous()                          # [rt][kb][piece][4096]
 
 
-def untile_a_operand(t: Tensor, rows: int, cols: int) -> Tensor:
-    """Inverse of ``tile_a_operand`` (returns p1 + p2 + p3 as plain float32 ``[rows][cols]``)."""
+def untile_a_operand(t: Tensor, rows: int, cols: int, scale: tp.Optional[float] = None) -> Tensor:
+    """Inverse of ``tile_a_operand`` (returns (p1 + p2 (+ p3)) / scale as plain float32 ``[rows][cols]``)."""
+    fmt = _lib.operand_format()
+    if scale is None:
+        scale = fmt.value_scale
     nkb = cols // 32
-    v = t.view(torch.bfloat16).view(rows // 128, nkb, 3, 16, 8, 4, 8)            # [rt][kb][piece][grp][row][pos][8]
-    idx = _swizzle_index(t.device).view(1, 1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 3, 16, 8, 4, 8)
-    w = torch.gather(v.to(torch.float32), 5, idx).sum(2)                           # [rt][kb][grp][row][ch][8]
+    P = fmt.parts
+    dt = torch.float16 if P == 2 else torch.bfloat16
+    v = t.view(dt).view(rows // 128, nkb, P, 16, 8, 4, 8)                        # [rt][kb][piece][grp][row][pos][8]
+    idx = _swizzle_index(t.device).view(1, 1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, P, 16, 8, 4, 8)
+    w = torch.gather(v.to(torch.float32), 5, idx).flip(2).sum(2) / scale           # [rt][kb][grp][row][ch][8]
     return w.permute(0, 2, 3, 1, 4, 5).reshape(rows, cols).contiguous()
+
+
+def operand_buffer(rows: int, cols: int, device) -> Tensor:
+    """Zeroed storage of a tiled operand matrix with ``rows x cols`` values."""
+    fmt = _lib.operand_format()
+    return torch.zeros(rows, fmt.parts * cols, dtype=torch.float16 if fmt.parts == 2 else torch.bfloat16,
+                       device=device)
 
 
 class PackedNetworks:
@@ -216,6 +250,7 @@ class PackedNetworks:
             h1, h2, h3 = pout[:3]
             w1n = torch.zeros(M * h1, self.ldx, **f32)
             w1n[:, :in_dim] = torch.cat(W[0], 0)
+            sc = [weight_scale(W[k]) for k in range(3)]   # one scale per layer, shared by W and W^T
             t = {
                 "b1": torch.cat(Bv[0]).contiguous(),
                 "b2": torch.cat(Bv[1]).contiguous(),
@@ -223,15 +258,18 @@ class PackedNetworks:
                 "w4": torch.cat(W[3], 0).contiguous(),                        # [M][h3]
                 "b4": torch.cat(Bv[3]).contiguous(),                          # [M]
                 # B operands [N][K] (K-major) of the six GEMMs, tiled for the tensor-core kernel
-                "t_f1": tile_b_operand(w1n),                                          # N = M*h1, K = ldx
-                "t_f2": torch.cat([tile_b_operand(w) for w in W[1]]),                 # per member [h2][h1]
-                "t_f3": torch.cat([tile_b_operand(w) for w in W[2]]),                 # per member [h3][h2]
-                "t_b3": torch.cat([tile_b_operand(w.t().contiguous()) for w in W[2]]),  # [h2][h3]
-                "t_b2": torch.cat([tile_b_operand(w.t().contiguous()) for w in W[1]]),  # [h1][h2]
-                "t_b1": tile_b_operand(w1n.t().contiguous()),                         # N = ldx, K = M*h1
+                "t_f1": tile_b_operand(w1n, sc[0]),                                        # N = M*h1, K = ldx
+                "t_f2": torch.cat([tile_b_operand(w, sc[1]) for w in W[1]]),                 # per member [h2][h1]
+                "t_f3": torch.cat([tile_b_operand(w, sc[2]) for w in W[2]]),                 # per member [h3][h2]
+                "t_b3": torch.cat([tile_b_operand(w.t().contiguous(), sc[2]) for w in W[2]]),  # [h2][h3]
+                "t_b2": torch.cat([tile_b_operand(w.t().contiguous(), sc[1]) for w in W[1]]),  # [h1][h2]
+                "t_b1": tile_b_operand(w1n.t().contiguous(), sc[0]),                       # N = ldx, K = M*h1
             }
             sp = mdl.sp[s]
             sp.h1, sp.h2, sp.h3 = h1, h2, h3
+            for k in range(3):
+                sp.w_scale[k] = sc[k]
+            sp.w_scale[3] = 1.0
             for k, v in t.items():
                 self._keep.append(v)
                 setattr(sp, k, v.data_ptr())
@@ -291,13 +329,12 @@ class Workspace:
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
-        # x / act*: "tiled operand" form (three bfloat16 pieces per value); dx: plain float32 rows
-        bf16 = dict(dtype=torch.bfloat16, device=device)
-        self.x = torch.zeros(self.rows_cap, 3 * ldx, **bf16)
+        # x / act*: "tiled operand" form (16-bit pieces of every value); dx: plain float32 rows
+        self.x = operand_buffer(self.rows_cap, ldx, device)
         self.dx = torch.zeros(self.rows_cap, ldx, **f32)
-        self.act1 = torch.zeros(self.rows_cap, 3 * ld[0], **bf16)
-        self.act2 = torch.zeros(self.rows_cap, 3 * ld[1], **bf16)
-        self.act3 = torch.zeros(self.rows_cap, 3 * ld[2], **bf16)
+        self.act1 = operand_buffer(self.rows_cap, ld[0], device)
+        self.act2 = operand_buffer(self.rows_cap, ld[1], device)
+        self.act3 = operand_buffer(self.rows_cap, ld[2], device)
         self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
         self.species_i32 = torch.zeros(n, **i32)
         self.coords = torch.zeros(n, 3, **f32)
@@ -456,7 +493,7 @@ class Engine:
         self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
             C.byref(self.nets.model), ptr(ws.x), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom),
             ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
-            int(want_grad), st))
+            int(want_grad), ptr(ws.status), st))
         if want_grad:
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
@@ -485,6 +522,10 @@ class Engine:
                 raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within Rca")
             if code & _lib.STATUS_PAIR_OVERFLOW:
                 raise RuntimeError("half neighbour list capacity exceeded")
+            if code & _lib.STATUS_OPERAND_RANGE:
+                raise RuntimeError("an AEV, activation or gradient left the range of the half-precision GEMM "
+                                   "operand pieces (inf/NaN input, or |value| >= 1023 / |gradient| >= 16); "
+                                   "build the library with -DANI_OPND_FP16X2=0 for such models")
 
     def grid_info(self, ws: Workspace) -> Grid:
         g = Grid()

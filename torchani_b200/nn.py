@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import Grid, check, ptr
-from .engine import PackedNetworks, TILE, tile_a_operand
+from .engine import PackedNetworks, TILE, operand_buffer, tile_a_operand
 
 PERIODIC_TABLE = ("Dummy H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga "
                   "Ge As Se Br Kr Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe").split()
@@ -102,16 +102,19 @@ class _MLPFunction(torch.autograd.Function):
         src = src * real.view(-1, 1)
         # padding atoms all map to row 0 with zero contribution -> index_add keeps row 0 intact
         xp[:, :D].index_add_(0, rows, src)
-        x_tiled = tile_a_operand(xp)                    # the GEMM consumes the 3 x bf16 tiled form
+        x_tiled = tile_a_operand(xp)                    # the GEMM consumes the tiled form
         x = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)   # dE/dAEV comes back as plain rows
         ld = nets.ld
-        act1 = torch.empty(rows_cap, 3 * ld[0], dtype=torch.bfloat16, device=dev)
-        act2 = torch.empty(rows_cap, 3 * ld[1], dtype=torch.bfloat16, device=dev)
-        act3 = torch.empty(rows_cap, 3 * ld[2], dtype=torch.bfloat16, device=dev)
+        act1, act2, act3 = (operand_buffer(rows_cap, w, dev) for w in ld)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
         e_member = torch.zeros(M, rows_cap, dtype=torch.float32, device=dev)
         check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x_tiled), ptr(x), rows_cap,
                                               ptr(row_atom), ptr(layout_info), None, ptr(act1), ptr(act2), ptr(act3),
-                                              ptr(e_member), int(want_grad), st), "mlp_forward_backward")
+                                              ptr(e_member), int(want_grad), ptr(status), st),
+              "mlp_forward_backward")
+        if int(status.item()) & _lib.STATUS_OPERAND_RANGE:   # this module-level path synchronises anyway
+            raise RuntimeError("an AEV, activation or gradient left the range of the half-precision GEMM operand "
+                               "pieces (inf/NaN input, or |value| >= 1023 / |gradient| >= 16)")
         em_sorted = e_member[:, rows] * real.view(1, -1)          # (M, n) in `order` order
         out = torch.zeros(M, n, dtype=torch.float32, device=dev)
         out[:, order] = em_sorted
