@@ -11,6 +11,8 @@
 // evaluates dE/dr_j for every ORDERED pair (j, k) so that each neighbour's gradient is owned by
 // a group of lanes (register accumulation, shuffle reduce, plain shared-memory add); only the
 // final per-neighbour vectors go to global memory (fire-and-forget float reductions).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ani {
@@ -459,6 +461,376 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------
+// forward, CTA-staged neighbourhood (the bucket-grid path)
+//
+// The AEV_WARPS consecutive (bucket-sorted) atoms of a CTA almost always share one bucket, so the
+// candidates of its 27 neighbouring buckets are staged ONCE per CTA in shared memory -- shifted by
+// their lattice image and ordered species-major (the buckets are species-sorted, so the place of
+// every candidate follows from a 27 x S table of counts) -- instead of every warp walking the 27
+// ranges in global memory.  A warp then compacts its neighbours with one ballot per 32 candidates,
+// species segment by species segment: the neighbour list and the angular sub-list come out
+// grouped by species, which the two counting sorts of k_aev_forward used to establish.
+// CTAs that straddle a bucket boundary run one staging phase per distinct bucket; neighbourhoods
+// larger than CAND_CAP candidates are staged in windows of the species-major order.
+// ---------------------------------------------------------------------------------------
+constexpr int CAND_CAP = 1024;
+constexpr int NRANGE = 27;
+
+struct CtaStage {
+  float4 cand[CAND_CAP];  // shifted position; .w = neighbour word (sorted index | image code << 26)
+  float4 r_shift[NRANGE];
+  int r_lo[NRANGE], r_code[NRANGE];
+  int r_off[NRANGE + 1];                       // exclusive prefix of the range lengths
+  int cnt[ANI_MAX_SPECIES][NRANGE];            // candidates per (species, range)
+  int off[ANI_MAX_SPECIES * NRANGE + 1];       // exclusive prefix of cnt in species-major order
+  int wbin[AEV_WARPS];
+};
+
+template <int NA, int NZ>
+__global__ void __launch_bounds__(AEV_WARPS * 32, 6)
+    k_aev_forward_cta(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
+                      const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
+                      const int32_t* __restrict__ sbin, const float4* __restrict__ ranges,
+                      const int32_t* __restrict__ species_mask, int lo, int hi, const int32_t* __restrict__ row_of,
+                      float* __restrict__ aev, int ldx, int layout, int32_t* __restrict__ nbr_cnt,
+                      int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes) {
+  static_assert(NA * NZ == 32, "one lane per angular feature");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ CtaStage C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ani_grid g = *grid;
+  hi = min(hi, g.n_real);
+  const int i = lo + blockIdx.x * AEV_WARPS + warp;
+  const bool has = i < hi;  // warps without an atom still help with the staging
+  const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, false);
+  const int S = P.num_species;
+  const int nR = P.n_shf_r;
+  const int RL = S * nR;
+  float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+  int myb = 0x7fffffff;
+  if (has) {
+    pi = spos[i];
+    myb = sbin[i];
+  }
+  if (lane == 0) C.wbin[warp] = myb;
+  __syncthreads();
+
+  // ---- 1. neighbours within Rcr (and the sub-list within Rca), species segment by species segment
+  const float rcr2 = P.rcr * P.rcr;
+  const unsigned lt = (1u << lane) - 1u;
+  int cnt = 0, cnt_a = 0;
+  if (lane == 0) {
+    s.seg_all[0] = 0;
+    s.seg[0] = 0;
+  }
+  int prev = -1;
+  while (true) {
+    int cur = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < AEV_WARPS; ++w) {
+      const int b = C.wbin[w];
+      if (b > prev && b < cur) cur = b;
+    }
+    if (cur == 0x7fffffff) break;
+    prev = cur;
+    __syncthreads();  // every warp has chosen `cur`; the tables of the previous phase may be rewritten
+    // (a) the 27 candidate ranges of bucket `cur`
+    if (tid < NRANGE) {
+      int rlo = 0, rhi = 0, code = 13;
+      float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g.mode != 0) {
+        if (tid == 13) {
+          rlo = bin_start[cur];
+          rhi = bin_start[cur + 1];
+        }
+      } else if (ranges) {
+        const float4 r0 = ranges[2 * ((size_t)cur * NRANGE + tid)];
+        const float4 r1 = ranges[2 * ((size_t)cur * NRANGE + tid) + 1];
+        rlo = __float_as_int(r0.x);
+        rhi = __float_as_int(r0.y);
+        code = __float_as_int(r0.z);
+        sh = r1;
+      } else {
+        const int iz = cur % g.dims[2], iy = (cur / g.dims[2]) % g.dims[1], ix = cur / (g.dims[2] * g.dims[1]);
+        NeighbourRange r;
+        if (neighbour_bucket(g, bin_start, ix, iy, iz, tid / 9 - 1, (tid / 3) % 3 - 1, tid % 3 - 1, r)) {
+          rlo = r.lo;
+          rhi = r.hi;
+          code = r.code;
+          if (code != 13) {
+            const float3 v = image_shift(g, code);
+            sh = make_float4(v.x, v.y, v.z, 0.f);
+          }
+        }
+      }
+      C.r_lo[tid] = rlo;
+      C.r_code[tid] = code;
+      C.r_shift[tid] = sh;
+      C.r_off[tid + 1] = max(rhi - rlo, 0);  // length for now, prefix below
+    }
+    for (int q = tid; q < ANI_MAX_SPECIES * NRANGE; q += AEV_WARPS * 32) (&C.cnt[0][0])[q] = 0;
+    __syncthreads();
+    if (warp == 0) {
+      // inclusive scan of the 27 lengths (lane o holds range o)
+      int v = lane < NRANGE ? C.r_off[lane + 1] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(ANI_FULL_MASK, v, o);
+        if (lane >= o) v += y;
+      }
+      if (lane < NRANGE) C.r_off[lane + 1] = v;
+      if (lane == 0) C.r_off[0] = 0;
+    }
+    __syncthreads();
+    const int T = C.r_off[NRANGE];
+    // flat (range-major) candidate number -> range: branch-free binary search over the prefix
+    auto find_range = [&](int t) {
+      int o = 0;
+#pragma unroll
+      for (int step = 16; step >= 1; step >>= 1)
+        if (o + step < NRANGE && C.r_off[o + step] <= t) o += step;
+      return o;
+    };
+    // (b) candidates per (species, range)
+    for (int t = tid; t < T; t += AEV_WARPS * 32) {
+      const int o = find_range(t);
+      const int c = C.r_lo[o] + (t - C.r_off[o]);
+      const int sp = __float_as_int(spos[c].w);
+      atomicAdd(&C.cnt[sp][o], 1);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // exclusive prefix over q = species * 27 + range: 7 consecutive entries per lane
+      constexpr int PER = (ANI_MAX_SPECIES * NRANGE + 31) / 32;
+      int loc[PER];
+      int sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int q = lane * PER + k;
+        loc[k] = q < ANI_MAX_SPECIES * NRANGE ? (&C.cnt[0][0])[q] : 0;
+        sum += loc[k];
+      }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(ANI_FULL_MASK, incl, o);
+        if (lane >= o) incl += y;
+      }
+      int run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int q = lane * PER + k;
+        if (q <= ANI_MAX_SPECIES * NRANGE) C.off[q] = run;
+        run += loc[k];
+      }
+    }
+    __syncthreads();
+    const bool mine = has && myb == cur;
+    for (int F0 = 0; F0 < T; F0 += CAND_CAP) {
+      // (c) place the candidates whose species-major position falls into this window
+      for (int t = tid; t < T; t += AEV_WARPS * 32) {
+        const int o = find_range(t);
+        const int k = t - C.r_off[o];
+        const int c = C.r_lo[o] + k;
+        const float4 p = spos[c];
+        const int sp = __float_as_int(p.w);
+        int before = 0;  // candidates of lower species in this (species-sorted) range
+        for (int s2 = 0; s2 < sp; ++s2) before += C.cnt[s2][o];
+        const int dest = C.off[sp * NRANGE + o] + (k - before) - F0;
+        if (dest >= 0 && dest < CAND_CAP) {
+          const float4 sh = C.r_shift[o];
+          C.cand[dest] = make_float4(p.x + sh.x, p.y + sh.y, p.z + sh.z,
+                                     __int_as_float(c | (C.r_code[o] << ANI_IMG_SHIFT)));
+        }
+      }
+      __syncthreads();
+      // (d) the warps of this bucket compact their neighbours out of the window
+      if (mine) {
+        for (int sp = 0; sp < S; ++sp) {
+          const int a = max(F0, C.off[sp * NRANGE]);
+          const int b = min(F0 + CAND_CAP, C.off[(sp + 1) * NRANGE]);
+          for (int base = a; base < b; base += 32) {
+            const int idx = base + lane;
+            const bool valid = idx < b;
+            const float4 p = C.cand[valid ? idx - F0 : 0];
+            const int word = __float_as_int(p.w);
+            const float dx = p.x - pi.x, dy = p.y - pi.y, dz = p.z - pi.z;
+            const float r2 = dx * dx + dy * dy + dz * dz;
+            const bool keep = valid && r2 <= rcr2 && word != (i | (13 << ANI_IMG_SHIFT));
+            const float R = sqrtf(r2);
+            const unsigned m = __ballot_sync(ANI_FULL_MASK, keep);
+            const int pos = cnt + __popc(m & lt);
+            const bool stored = keep && pos < cap;
+            // (an angular neighbour beyond the stored radial rows could not be addressed: the radial
+            // overflow is reported instead)
+            const bool keep_a = stored && R <= P.rca;
+            const unsigned ma = __ballot_sync(ANI_FULL_MASK, keep_a);
+            if (stored) {
+              s.nd[pos] = make_float4(dx, dy, dz, R);
+              s.nj[pos] = word;
+              if (keep_a) {
+                const int pa = cnt_a + __popc(ma & lt);
+                if (pa < ANI_MAX_ANG) s.aidx[pa] = (unsigned char)pos;
+              }
+            }
+            cnt += __popc(m);
+            cnt_a += __popc(ma);
+          }
+          // (partial while the species continues in the next window; rewritten then)
+          if (lane == 0) {
+            s.seg_all[sp + 1] = min(cnt, cap);
+            s.seg[sp + 1] = min(cnt_a, ANI_MAX_ANG);
+          }
+        }
+      }
+      __syncthreads();  // before the next window / phase overwrites the staging area
+    }
+  }
+  if (!has) return;
+  if (cnt > cap) {
+    if (lane == 0) atomicOr(status, ANI_STATUS_NBR_OVERFLOW);
+    cnt = cap;
+  }
+  if (cnt_a > ANI_MAX_ANG) {
+    if (lane == 0) atomicOr(status, ANI_STATUS_ANG_OVERFLOW);
+    cnt_a = ANI_MAX_ANG;
+  }
+  __syncwarp();
+
+  // output: plain row-major rows, or the tiled operand layout (16-bit pieces) the GEMM consumes
+  const int out_row = row_of[i];
+  const int kblocks = ldx >> 5;
+  float vmax = 0.f;
+  auto store_feature = [&](int col, float v) {
+    if (layout == 0) {
+      aev[(size_t)out_row * ldx + col] = v;
+    } else {
+      unsigned char* dst = reinterpret_cast<unsigned char*>(aev) + opnd_offset(out_row, col, kblocks);
+      unsigned short pc[OPND_PARTS];
+      v *= OPND_SCALE_VALUE;
+      vmax = fmaxf(vmax, v);
+      opnd_split(v, pc);
+#pragma unroll
+      for (int k = 0; k < OPND_PARTS; ++k) *reinterpret_cast<unsigned short*>(dst + k * OPND_PART_BYTES) = pc[k];
+    }
+  };
+
+  if (lane == 0 && nbr_cnt) nbr_cnt[i] = cnt;
+  // per neighbour: (c R, fc(R)) with c = sqrt(eta_r log2 e), so that a Gaussian factor is
+  // ex2(-(c R - c ShfR)^2); the neighbour words go to the list the backward kernel reads
+  const float cr = sqrtf(P.eta_r * 1.4426950408889634f);
+  if (nbr_list)
+    for (int n = lane; n < cnt; n += 32) nbr_list[(size_t)i * cap + n] = s.nj[n];
+  __syncwarp();
+  // [cap] float2 over nfc and nj (adjacent, 8-byte aligned; the words were just copied out)
+  float2* rf = reinterpret_cast<float2*>(s.nfc);
+  for (int n = lane; n < cnt; n += 32) {
+    const float R = s.nd[n].w;
+    rf[n] = make_float2(cr * R, cutoff_value(R, P.rcr, P.cutoff_kind));
+  }
+  __syncwarp();
+
+  // element pairs / elements that do not occur anywhere in the system are never read by the MLP:
+  // skip them (species_mask[1] != 0: the composition changed since the last call -> write them once)
+  const unsigned present = (species_mask && !species_mask[1]) ? (unsigned)species_mask[0] : 0xffffffffu;
+
+  // ---- 2. radial block: lane = (shift m, neighbour parity h); one species segment at a time, the
+  //         (species, shift) sum lives in a register: no shared-memory accumulators, no atomics
+  {
+    const int lpn = (nR <= 16) ? 16 : 32;
+    const int halves = 32 / lpn;
+    const int m = lane % lpn, h = lane / lpn;
+    const float cshf = cr * P.shf_r[m < nR ? m : 0];
+    for (int sp = 0; sp < S; ++sp) {
+      if (!((present >> sp) & 1u)) continue;
+      const int k1 = s.seg_all[sp + 1];
+      float acc = 0.f;
+#pragma unroll 2
+      for (int k = s.seg_all[sp] + h; k < k1; k += halves) {
+        const float2 v = rf[k];
+        const float d = v.x - cshf;
+        acc = fmaf(fast_exp2(-d * d), v.y, acc);
+      }
+      if (halves == 2) acc += __shfl_xor_sync(ANI_FULL_MASK, acc, 16);
+      if (h == 0 && m < nR) store_feature(sp * nR + m, 0.25f * acc);
+    }
+  }
+
+  // ---- 3. angular block
+  const int n_ang = cnt_a;
+  for (int q = lane; q < n_ang; q += 32) s.afc[q] = cutoff_value(s.nd[s.aidx[q]].w, P.rca, P.cutoff_kind);
+  __syncwarp();
+  // f2[a] * w = ex2(-(ca rbar - ca ShfA)^2 + lg2 w),  f1[z] = (0.5 + c (cz/2) + s (sz/2))^zeta
+  const float ca = sqrtf(P.eta_a * 1.4426950408889634f);
+  float cshfA[NA], hcz[NZ], hsz[NZ];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) cshfA[a] = ca * P.shf_a[a];
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) {
+    hcz[z] = 0.5f * P.cos_z[z];
+    hsz[z] = 0.5f * P.sin_z[z];
+  }
+  int p = 0;
+  for (int s1 = 0; s1 < S; ++s1) {
+    if (!((present >> s1) & 1u)) {
+      p += S - s1;
+      continue;
+    }
+    const int a0 = s.seg[s1], na = s.seg[s1 + 1] - a0;
+    for (int s2 = s1; s2 < S; ++s2, ++p) {
+      if (!((present >> s2) & 1u)) continue;
+      const int b0 = s.seg[s2], nb = s.seg[s2 + 1] - b0;
+      const int count = (s1 == s2) ? na * (na - 1) / 2 : na * nb;
+      float out = 0.f;
+      if (count > 0) {
+        float acc[32];
+#pragma unroll
+        for (int f = 0; f < 32; ++f) acc[f] = 0.f;
+        const float inv_nb = 1.0f / (float)nb;
+        for (int q = lane; q < count; q += 32) {
+          int ja, jb;
+          if (s1 == s2) {
+            // q-th pair (a < b) of the triangle: b = floor((1 + sqrt(1 + 8 q)) / 2), one fix-up each way
+            int bb = (int)(0.5f + 0.5f * fast_sqrt(1.0f + 8.0f * (float)q));
+            if (bb * (bb - 1) / 2 > q) --bb;
+            if ((bb + 1) * bb / 2 <= q) ++bb;
+            ja = a0 + q - bb * (bb - 1) / 2;
+            jb = a0 + bb;
+          } else {
+            // q / nb for q < 2^13, nb <= 96: the float quotient of (q + 0.5) is never within rounding of an integer
+            const int qa = (int)(((float)q + 0.5f) * inv_nb);
+            ja = a0 + qa;
+            jb = b0 + q - qa * nb;
+          }
+          const float4 dj = s.nd[s.aidx[ja]], dk = s.nd[s.aidx[jb]];
+          const float lw = fast_log2(2.0f * s.afc[ja] * s.afc[jb]);  // -inf at the cutoff: every term 0
+          const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
+          const float c = 0.95f * dot * fast_rcp(fmaxf(dj.w * dk.w, 1e-10f));
+          const float sn = fast_sqrt(fmaxf(1.0f - c * c, 0.f));
+          const float rbar = ca * 0.5f * (dj.w + dk.w);
+          float f1[NZ];
+#pragma unroll
+          for (int z = 0; z < NZ; ++z) {
+            const float base = fmaxf(fmaf(sn, hsz[z], fmaf(c, hcz[z], 0.5f)), 0.f);
+            f1[z] = fast_exp2(P.zeta * fast_log2(base));  // base^zeta; base = 0 -> ex2(-inf) = 0
+          }
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const float d = rbar - cshfA[a];
+            const float f2 = fast_exp2(fmaf(-d, d, lw));
+#pragma unroll
+            for (int z = 0; z < NZ; ++z) acc[a * NZ + z] = fmaf(f1[z], f2, acc[a * NZ + z]);
+          }
+        }
+        out = transpose_reduce32(acc, lane);
+      }
+      store_feature(RL + p * 32 + lane, out);
+    }
+  }
+  if (ANI_OPND_FP16X2 && !(vmax <= OPND_HALF_MAX)) atomicOr(status, ANI_STATUS_OPERAND_RANGE);
+}
+
+// ---------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------
 template <int NA, int NZ>
@@ -489,11 +861,16 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const size_t row = (size_t)row_of[i] * ldx;
   for (int t = lane; t < RL; t += 32) g_rad[t] = gaev[row + t];
   {
-    const unsigned present = species_mask ? (unsigned)species_mask[0] : 0xffffffffu;
-    int pp = 0;
-    for (int s1 = 0; s1 < S; ++s1)
-      for (int s2 = s1; s2 < S; ++s2, ++pp)
-        if ((present >> s1) & (present >> s2) & 1u) g_ang[pp * GSTRIDE + lane] = gaev[row + RL + pp * 32 + lane];
+    // walk the set bits of the element mask: (s1, s2 >= s1) pairs of present elements only
+    const unsigned present = (species_mask ? (unsigned)species_mask[0] : 0xffffffffu) & ((1u << S) - 1u);
+    for (unsigned m1 = present; m1; m1 &= m1 - 1) {
+      const int s1 = __ffs(m1) - 1;
+      const int base = s1 * (2 * S - s1 + 1) / 2 - s1;  // pair_index(s1, s2) = base + s2
+      for (unsigned m2 = m1; m2; m2 &= m2 - 1) {
+        const int pp = base + __ffs(m2) - 1;
+        g_ang[pp * GSTRIDE + lane] = gaev[row + RL + pp * 32 + lane];
+      }
+    }
   }
 
   // ---- 2. geometry of the stored neighbours
@@ -885,6 +1262,27 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
   cudaStream_t st = (cudaStream_t)stream;
   const float4* sp4 = reinterpret_cast<const float4*>(spos);
   const float4* rng4 = reinterpret_cast<const float4*>(bucket_ranges);
+  // bucket-grid path: CTA-staged neighbourhoods (ANI_B200_AEV_LEGACY=1 keeps the warp-per-atom search
+  // of k_aev_forward, which also serves the explicit neighbour rows)
+  static const bool legacy = []() {
+    const char* e = getenv("ANI_B200_AEV_LEGACY");
+    return e && atoi(e) != 0;
+  }();
+  if (!ex.start && !legacy) {
+    if (params->n_shf_a == 8) {
+      auto k = k_aev_forward_cta<8, 4>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
+                                              aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
+    } else {
+      auto k = k_aev_forward_cta<4, 8>;
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
+                                              aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
+    }
+    ANI_CUDA_CHECK_LAUNCH();
+    return ANI_OK;
+  }
   if (params->n_shf_a == 8) {
     auto k = k_aev_forward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

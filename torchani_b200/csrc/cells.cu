@@ -230,8 +230,8 @@ __global__ void k_bin_scatter(int n, const int32_t* __restrict__ bin_of, const i
   tmp_list[bin_start[bin_of[a]] + slot[a]] = a;
 }
 
-// the atomics above give an arbitrary order inside a bucket; rank by input index to make the
-// sorted order (and with it every later summation order) deterministic
+// the atomics above give an arbitrary order inside a bucket; rank by (species, input index) to make
+// the sorted order (and with it every later summation order) deterministic and species-grouped
 __global__ void k_bin_finalize(const float* __restrict__ coords, const int32_t* __restrict__ species, int n,
                                const ani_grid* __restrict__ grid, const int32_t* __restrict__ bin_of,
                                const int32_t* __restrict__ bin_start, const int32_t* __restrict__ tmp_list,
@@ -242,8 +242,15 @@ __global__ void k_bin_finalize(const float* __restrict__ coords, const int32_t* 
   const ani_grid g = *grid;
   int b = bin_of[a];
   int lo = bin_start[b], hi = bin_start[b + 1];
+  // order inside a bucket: by species, then by input index (deterministic; the AEV kernel relies on
+  // every bucket being species-sorted)
+  const int spa = species[a];
   int rank = 0;
-  for (int e = lo; e < hi; ++e) rank += (tmp_list[e] < a);
+  for (int e = lo; e < hi; ++e) {
+    const int t = tmp_list[e];
+    const int spt = species[t];
+    rank += (spt < spa) || (spt == spa && t < a);
+  }
   int i = lo + rank;
   sorted_orig[i] = a;
   orig_to_sorted[a] = i;
@@ -463,7 +470,7 @@ __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int 
 // species_layout + active_aev_blocks in five launches instead of twelve --
 //   P1 grid (inline) + bucket assignment, the last block to finish scans the bucket counts
 //   P2 scatter into buckets  +  per-bucket neighbour-range table
-//   P3 deterministic order inside buckets, sorted arrays, per-chunk species histogram, element
+//   P3 deterministic (species, input index) order inside buckets, sorted arrays, per-chunk species histogram, element
 //      presence mask, zero-fill of the force accumulator
 //   P4 (one block) chunk scan, species row bases, tile table, live AEV column blocks
 //   P5 row assignment
@@ -610,8 +617,14 @@ __global__ void __launch_bounds__(256) k_prep_finalize(const __grid_constant__ P
   if (a < A.n) {
     const int b = A.bin_of[a];
     const int lo = A.bin_start[b], hi = A.bin_start[b + 1];
+    // rank by (species, input index): deterministic order, every bucket species-sorted
+    const int spa = A.species[a];
     int rank = 0;
-    for (int e = lo; e < hi; ++e) rank += (A.tmp_list[e] < a);  // rank by input index: deterministic order
+    for (int e = lo; e < hi; ++e) {
+      const int t = A.tmp_list[e];
+      const int spt = A.species[t];
+      rank += (spt < spa) || (spt == spa && t < a);
+    }
     i = lo + rank;
     A.sorted_orig[i] = a;
     A.orig_to_sorted[a] = i;
