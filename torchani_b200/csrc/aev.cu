@@ -676,8 +676,9 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
             cnt += __popc(m);
             cnt_a += __popc(ma);
           }
-          // (partial while the species continues in the next window; rewritten then)
-          if (lane == 0) {
+          // segment ends: partial while the species continues in the next window (rewritten then);
+          // a species that ended before this window keeps the value it got there
+          if (lane == 0 && C.off[(sp + 1) * NRANGE] >= F0) {
             s.seg_all[sp + 1] = min(cnt, cap);
             s.seg[sp + 1] = min(cnt_a, ANI_MAX_ANG);
           }
