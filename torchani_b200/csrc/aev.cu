@@ -473,8 +473,9 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 // CTAs that straddle a bucket boundary run one staging phase per distinct bucket; neighbourhoods
 // larger than CAND_CAP candidates are staged in windows of the species-major order.
 // ---------------------------------------------------------------------------------------
-constexpr int CAND_CAP = 1024;
+constexpr int CAND_CAP = 768;
 constexpr int NRANGE = 27;
+constexpr int T2O_CAP = 1024;
 
 struct CtaStage {
   float4 cand[CAND_CAP];  // shifted position; .w = neighbour word (sorted index | image code << 26)
@@ -483,7 +484,9 @@ struct CtaStage {
   int r_off[NRANGE + 1];                       // exclusive prefix of the range lengths
   int cnt[ANI_MAX_SPECIES][NRANGE];            // candidates per (species, range)
   int off[ANI_MAX_SPECIES * NRANGE + 1];       // exclusive prefix of cnt in species-major order
+  int adj[ANI_MAX_SPECIES][NRANGE];            // off[s][o] - (candidates of lower species in range o)
   int wbin[AEV_WARPS];
+  unsigned char t2o[T2O_CAP];                  // range of the t-th candidate (range-major numbering)
 };
 
 template <int NA, int NZ>
@@ -516,7 +519,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
   __syncthreads();
 
   // ---- 1. neighbours within Rcr (and the sub-list within Rca), species segment by species segment
-  const float rcr2 = P.rcr * P.rcr;
+  const float rcr2 = P.rcr * P.rcr, rca2 = P.rca * P.rca;
   const unsigned lt = (1u << lane) - 1u;
   int cnt = 0, cnt_a = 0;
   if (lane == 0) {
@@ -591,12 +594,25 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
         if (o + step < NRANGE && C.r_off[o + step] <= t) o += step;
       return o;
     };
-    // (b) candidates per (species, range)
-    for (int t = tid; t < T; t += AEV_WARPS * 32) {
-      const int o = find_range(t);
-      const int c = C.r_lo[o] + (t - C.r_off[o]);
-      const int sp = __float_as_int(spos[c].w);
-      atomicAdd(&C.cnt[sp][o], 1);
+    // (b) candidates per (species, range); the range of every candidate is remembered for (c)
+    // (four candidates per thread and round: the global loads are issued together)
+    constexpr int NT = AEV_WARPS * 32, BATCH = 4;
+    for (int t0 = tid; t0 < T; t0 += NT * BATCH) {
+      int oo[BATCH], spv[BATCH];
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j) {
+        const int t = t0 + j * NT;
+        oo[j] = -1;
+        if (t < T) {
+          const int o = find_range(t);
+          oo[j] = o;
+          if (t < T2O_CAP) C.t2o[t] = (unsigned char)o;
+          spv[j] = __float_as_int(spos[C.r_lo[o] + (t - C.r_off[o])].w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BATCH; ++j)
+        if (oo[j] >= 0) atomicAdd(&C.cnt[spv[j]][oo[j]], 1);
     }
     __syncthreads();
     if (warp == 0) {
@@ -623,24 +639,46 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
         if (q <= ANI_MAX_SPECIES * NRANGE) C.off[q] = run;
         run += loc[k];
       }
+      __syncwarp();
+      // place of a candidate = adj[species][range] + its offset inside the (species-sorted) range
+      if (lane < NRANGE) {
+        int lower = 0;
+#pragma unroll
+        for (int sp = 0; sp < ANI_MAX_SPECIES; ++sp) {
+          C.adj[sp][lane] = C.off[sp * NRANGE + lane] - lower;
+          lower += C.cnt[sp][lane];
+        }
+      }
     }
     __syncthreads();
     const bool mine = has && myb == cur;
     for (int F0 = 0; F0 < T; F0 += CAND_CAP) {
       // (c) place the candidates whose species-major position falls into this window
-      for (int t = tid; t < T; t += AEV_WARPS * 32) {
-        const int o = find_range(t);
-        const int k = t - C.r_off[o];
-        const int c = C.r_lo[o] + k;
-        const float4 p = spos[c];
-        const int sp = __float_as_int(p.w);
-        int before = 0;  // candidates of lower species in this (species-sorted) range
-        for (int s2 = 0; s2 < sp; ++s2) before += C.cnt[s2][o];
-        const int dest = C.off[sp * NRANGE + o] + (k - before) - F0;
-        if (dest >= 0 && dest < CAND_CAP) {
-          const float4 sh = C.r_shift[o];
-          C.cand[dest] = make_float4(p.x + sh.x, p.y + sh.y, p.z + sh.z,
-                                     __int_as_float(c | (C.r_code[o] << ANI_IMG_SHIFT)));
+      for (int t0 = tid; t0 < T; t0 += NT * BATCH) {
+        int oo[BATCH], cc[BATCH];
+        float4 pp[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+          const int t = t0 + j * NT;
+          oo[j] = -1;
+          if (t < T) {
+            const int o = t < T2O_CAP ? (int)C.t2o[t] : find_range(t);
+            oo[j] = o;
+            cc[j] = C.r_lo[o] + (t - C.r_off[o]);
+            pp[j] = spos[cc[j]];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+          if (oo[j] < 0) continue;
+          const int o = oo[j], c = cc[j];
+          const float4 p = pp[j];
+          const int dest = C.adj[__float_as_int(p.w)][o] + (c - C.r_lo[o]) - F0;
+          if (dest >= 0 && dest < CAND_CAP) {
+            const float4 sh = C.r_shift[o];
+            C.cand[dest] = make_float4(p.x + sh.x, p.y + sh.y, p.z + sh.z,
+                                       __int_as_float(c | (C.r_code[o] << ANI_IMG_SHIFT)));
+          }
         }
       }
       __syncthreads();
@@ -657,16 +695,15 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
             const float dx = p.x - pi.x, dy = p.y - pi.y, dz = p.z - pi.z;
             const float r2 = dx * dx + dy * dy + dz * dz;
             const bool keep = valid && r2 <= rcr2 && word != (i | (13 << ANI_IMG_SHIFT));
-            const float R = sqrtf(r2);
             const unsigned m = __ballot_sync(ANI_FULL_MASK, keep);
             const int pos = cnt + __popc(m & lt);
             const bool stored = keep && pos < cap;
             // (an angular neighbour beyond the stored radial rows could not be addressed: the radial
             // overflow is reported instead)
-            const bool keep_a = stored && R <= P.rca;
+            const bool keep_a = stored && r2 <= rca2;
             const unsigned ma = __ballot_sync(ANI_FULL_MASK, keep_a);
             if (stored) {
-              s.nd[pos] = make_float4(dx, dy, dz, R);
+              s.nd[pos] = make_float4(dx, dy, dz, r2);  // the square root is taken once per neighbour below
               s.nj[pos] = word;
               if (keep_a) {
                 const int pa = cnt_a + __popc(ma & lt);
@@ -726,7 +763,8 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
   // [cap] float2 over nfc and nj (adjacent, 8-byte aligned; the words were just copied out)
   float2* rf = reinterpret_cast<float2*>(s.nfc);
   for (int n = lane; n < cnt; n += 32) {
-    const float R = s.nd[n].w;
+    const float R = sqrtf(s.nd[n].w);
+    s.nd[n].w = R;
     rf[n] = make_float2(cr * R, cutoff_value(R, P.rcr, P.cutoff_kind));
   }
   __syncwarp();
@@ -771,15 +809,14 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
     hcz[z] = 0.5f * P.cos_z[z];
     hsz[z] = 0.5f * P.sin_z[z];
   }
-  int p = 0;
-  for (int s1 = 0; s1 < S; ++s1) {
-    if (!((present >> s1) & 1u)) {
-      p += S - s1;
-      continue;
-    }
+  // walk the set bits of the element mask: pairs (s1, s2 >= s1) of present elements only
+  for (unsigned m1 = present & ((1u << S) - 1u); m1; m1 &= m1 - 1) {
+    const int s1 = __ffs(m1) - 1;
     const int a0 = s.seg[s1], na = s.seg[s1 + 1] - a0;
-    for (int s2 = s1; s2 < S; ++s2, ++p) {
-      if (!((present >> s2) & 1u)) continue;
+    const int pbase = s1 * (2 * S - s1 + 1) / 2 - s1;  // pair_index(s1, s2) = pbase + s2
+    for (unsigned m2 = m1; m2; m2 &= m2 - 1) {
+      const int s2 = __ffs(m2) - 1;
+      const int p = pbase + s2;
       const int b0 = s.seg[s2], nb = s.seg[s2 + 1] - b0;
       const int count = (s1 == s2) ? na * (na - 1) / 2 : na * nb;
       float out = 0.f;
@@ -859,8 +896,13 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 
   // ---- 1. upstream gradient row -> shared memory ([pair][32 features]); element pairs that do
   //         not occur in the system are never looked up (and never written by the MLP backward)
+  //         cp.async: the copies are all in flight while the neighbour geometry below is rebuilt
+  auto copy_async4 = [](float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+  };
   const size_t row = (size_t)row_of[i] * ldx;
-  for (int t = lane; t < RL; t += 32) g_rad[t] = gaev[row + t];
+  for (int t = lane; t < RL; t += 32) copy_async4(g_rad + t, gaev + row + t);
   {
     // walk the set bits of the element mask: (s1, s2 >= s1) pairs of present elements only
     const unsigned present = (species_mask ? (unsigned)species_mask[0] : 0xffffffffu) & ((1u << S) - 1u);
@@ -869,9 +911,10 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
       const int base = s1 * (2 * S - s1 + 1) / 2 - s1;  // pair_index(s1, s2) = base + s2
       for (unsigned m2 = m1; m2; m2 &= m2 - 1) {
         const int pp = base + __ffs(m2) - 1;
-        g_ang[pp * GSTRIDE + lane] = gaev[row + RL + pp * 32 + lane];
+        copy_async4(g_ang + pp * GSTRIDE + lane, gaev + row + RL + pp * 32 + lane);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
 
   // ---- 2. geometry of the stored neighbours
@@ -904,6 +947,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     s.nfc[n] = fc;
     s.fgrad[3 * n] = dfc;  // parked here until the radial loop overwrites fgrad[3n..3n+2]
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");  // the upstream gradient row has landed
   __syncwarp();
 
   // ---- 3. radial: dE/dR_n = sum_m g[s_n, m] * (G' fc + G fc'), then along the unit vector.

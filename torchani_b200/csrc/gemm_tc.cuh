@@ -379,6 +379,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: the next kernel of the stream may start scheduling its CTAs from
+  // here on (they find room when CTAs of this grid exit); everything above did not touch data the
+  // previous kernel writes (layout_info / block lists are older), everything below may: wait for
+  // the previous grid to complete and flush.  Both are no-ops in a plain launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int total_tiles = tm.prefix[args.num_species];
   // K-blocks are 32 columns, the same granularity as the optional live-block lists
   auto num_kb = [&](int K) { return tm.kb_count >= 0 ? tm.kb_count : (K + TK - 1) / TK; };

@@ -107,8 +107,12 @@ extern "C" int ani_b200_debug_gemm_trace(long long* buf, int launches) {
 }
 
 // tensor-core launch: one persistent CTA per SM walks the device-side tile list
+// `dependent`: launch with programmatic stream serialisation (PDL) -- the CTAs of this launch may be
+// scheduled while the previous kernel of the stream drains (its CTAs occupy a whole SM each, so a
+// new CTA starts as soon as one of them exits), run their prologue (barriers, tensor memory, tile
+// map) and block in griddepcontrol.wait until the previous grid has completed and flushed.
 template <int EPI>
-static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st) {
+static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st, bool dependent = false) {
   tc::Args a = a_in;
   a.trace = nullptr;
   if (g_trace && g_trace_next < g_trace_launches) a.trace = g_trace + (size_t)(g_trace_next++) * TRACE_WORDS_PER_LAUNCH;
@@ -124,7 +128,21 @@ static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st) {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     attr_set = true;
   }
-  k<<<num_sms, tc::THREADS, tc::SMEM_BYTES, st>>>(a);
+  static const bool pdl = []() {
+    const char* e = getenv("ANI_B200_PDL");  // ANI_B200_PDL=0: plain stream order
+    return !e || atoi(e) != 0;
+  }();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_sms);
+  cfg.blockDim = dim3(tc::THREADS);
+  cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (dependent && pdl) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, k, a);
 }
 
 extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
@@ -194,7 +212,7 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
     ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f2), p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr, 0, 0,
                             1.0f / (sv * wsc(p, 1))};
   }
-  launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st);
+  launch_gemm_tc<tc::EPI_BIAS_CELU>(ta, st, true);
   ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
@@ -204,7 +222,7 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
   // layer 3 + final layer (h3 -> 1) + gradient seed, fused in the epilogue: act3 receives
   // G3 = scale_m * w4 * celu'(a3) directly, e_member the per-member atomic energies
   ta.out_scale = sg;  // act3 receives the gradient seed
-  launch_gemm_tc<tc::EPI_HEAD>(ta, st);
+  launch_gemm_tc<tc::EPI_HEAD>(ta, st, true);
   if (want_backward) {
     // ---- backward: G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
     ta.A = static_cast<const unsigned char*>(act3); ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
@@ -213,14 +231,14 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
       ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b3), nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0,
                               1.0f / (sg * wsc(p, 2))};
     }
-    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
+    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st, true);
     ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
     for (int s = 0; s < S; ++s) {
       const ani_mlp_species& p = model->sp[s];
       ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0,
                               1.0f / (sg * wsc(p, 1))};
     }
-    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st);
+    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st, true);
     // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
     // all SMs are busy even when there are fewer row tiles than SMs); the partial tiles are
     // accumulated with vector REDs into the zeroed live column blocks of dx
@@ -233,7 +251,7 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
     ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
     ta.c_accumulate = M > 1;
     if (ta.c_accumulate) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
-    launch_gemm_tc<tc::EPI_PLAIN>(ta, st);
+    launch_gemm_tc<tc::EPI_PLAIN>(ta, st, true);
     ta.nblocks = nullptr;
     ta.c_accumulate = 0;
   }
