@@ -163,13 +163,16 @@ int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
 /*    accumulated (+=, float atomics) into grad_coords f32[n*3] in flat INPUT order.         */
 /*    species_mask (as in the forward, or NULL): the gradient blocks of element pairs that   */
 /*    do not occur in the system are not read (the block-sparse MLP backward leaves them     */
-/*    unwritten).                                                                             */
+/*    unwritten).  max_elements (0 = num_species): how many distinct elements the caller      */
+/*    expects in the system; it only sizes the kernel's shared-memory gradient table (higher   */
+/*    occupancy for few-element systems) -- pairs beyond it are read from global memory, the   */
+/*    result never depends on it.                                                               */
 int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
                           const int32_t* sorted_orig, const int32_t* species_mask, int n, int lo,
                           int hi, const int32_t* row_of, const float* grad_aev, int ldx,
                           const int32_t* nbr_cnt,
                           const int32_t* nbr_list, int nbr_cap, float* grad_coords,
-                          int32_t* status, void* stream);
+                          int32_t* status, int max_elements, void* stream);
 
 /* 4b. The same AEV kernels fed by an externally supplied HALF pair list (the reference's    */
 /*    Neighbors tuple; AEVComputer.compute_from_neighbors, aev/_computer.py:251-272 ->          */
@@ -280,6 +283,23 @@ int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, flo
                                   const int32_t* row_atom, const int32_t* layout_info,
                                   const int32_t* aev_blocks, void* act1, void* act2, void* act3,
                                   float* e_member, int want_backward, int32_t* status, void* stream);
+
+/*    The same work as two calls, so that a caller can run independent work beside the backward      */
+/*    GEMMs (engine.py: ani_b200_reduce_energies only needs e_member, i.e. the forward half) and      */
+/*    zero dE/dAEV ahead of time on another stream:                                                    */
+/*      ani_b200_mlp_forward       layers 1-3 + final layer + gradient seed (act3)                    */
+/*      ani_b200_zero_live_blocks  dx[rows][live column blocks] = 0 (the layer-1 backward accumulates  */
+/*                                 the members into dx; only needed when num_members > 1)              */
+/*      ani_b200_mlp_backward      the three backward-to-input GEMMs; dx_zeroed != 0: the caller has   */
+/*                                 already run ani_b200_zero_live_blocks for this step                 */
+int ani_b200_mlp_forward(const ani_mlp_model* model, const void* x, int rows_cap, const int32_t* row_atom,
+                         const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2,
+                         void* act3, float* e_member, int want_backward, int32_t* status, void* stream);
+int ani_b200_zero_live_blocks(const ani_mlp_model* model, float* dx, const int32_t* layout_info,
+                              const int32_t* aev_blocks, void* stream);
+int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int rows_cap, const int32_t* row_atom,
+                          const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2,
+                          void* act3, int dx_zeroed, int32_t* status, void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
 /*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */

@@ -40,7 +40,14 @@ def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-VARIANTS = {"": [], "bf16x3": ["-DANI_OPND_FP16X2=0"]}
+VARIANTS = {
+    "": [],
+    "bf16x3": ["-DANI_OPND_FP16X2=0"],
+    # tuning experiments (occupancy of the AEV kernels); not built by default
+    "bwd5": ["-DANI_AEV_BWD_MIN_CTAS=5"],
+    "bwd6": ["-DANI_AEV_BWD_MIN_CTAS=6"],
+    "fwd7": ["-DANI_AEV_FWD_MIN_CTAS=7", "-DANI_AEV_CAND_CAP=640"],
+}
 
 
 def lib_path(variant: str = "") -> str:

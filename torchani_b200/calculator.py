@@ -6,7 +6,8 @@ reference converts numpy -> tensors, copies to the GPU, runs the model, calls ``
 and ``forces.cpu().numpy()`` (two blocking D2H syncs).  Here the positions go straight into the
 engine's persistent input buffer (one async H2D), the captured CUDA graph of the step is
 replayed, energy and forces come back through pinned buffers (async D2H) and ONE stream
-synchronisation ends the step.
+synchronisation ends the step.  After a few eager steps the copies themselves are captured too
+(the pinned host buffers are persistent): a step is then ONE graph launch + ONE synchronisation.
 """
 from __future__ import annotations
 
@@ -53,6 +54,10 @@ class HostCalculator:
             self.set_cell(cell)
         self.h2d_bytes = self.h_coords.numel() * 4 + (36 if pbc else 0)
         self.d2h_bytes = self.h_grad.numel() * 4 + 8
+        self.graph_after = 3          # eager host-driven steps before copies + kernels are captured as one graph
+        self._calls = 0
+        self._graph: tp.Optional[torch.cuda.CUDAGraph] = None
+        self._graph_version = -1
 
     def set_cell(self, cell) -> None:
         self.h_cell.copy_(torch.as_tensor(np.asarray(cell, dtype=np.float32)).reshape(-1))
@@ -67,16 +72,39 @@ class HostCalculator:
         else:
             self.h_coords.numpy()[...] = np.asarray(positions, dtype=np.float32).reshape(self.n, 3)
         ws = self.ws
-        ws.coords.copy_(self.h_coords, non_blocking=True)
-        if self.pbc:
-            ws.cell.copy_(self.h_cell, non_blocking=True)
-        res = self.engine.run(ws, self.pbc, want_grad=True, shard=self.shard)
-        self.h_grad.copy_(res.grad.view(self.n, 3), non_blocking=True)
-        self.h_energy.copy_(res.energies, non_blocking=True)
+        eng = self.engine
+        self._calls += 1
+        if self._graph is not None and self._graph_version != eng.nets.version:
+            self._graph = None   # the active ensemble members changed: the captured scales are stale
+        if self._graph is None and eng.cuda_graph and not eng.profile and self._calls > self.graph_after:
+            rank, world = self.shard
+            lo, hi = (self.n * rank) // world, (self.n * (rank + 1)) // world
+            eng.note_composition(ws)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._copies_in()
+                eng._launch(ws, self.pbc, True, lo, hi)
+                self._copies_out()
+            self._graph, self._graph_version = graph, eng.nets.version
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._copies_in()
+            eng.run(ws, self.pbc, want_grad=True, shard=self.shard)
+            self._copies_out()
         torch.cuda.current_stream(self.device).synchronize()
         forces = self.h_grad.numpy()
         np.negative(forces, out=forces)
         return float(self.h_energy[0]), forces
+
+    def _copies_in(self) -> None:
+        self.ws.coords.copy_(self.h_coords, non_blocking=True)
+        if self.pbc:
+            self.ws.cell.copy_(self.h_cell, non_blocking=True)
+
+    def _copies_out(self) -> None:
+        self.h_grad.copy_(self.ws.grad.view(self.n, 3), non_blocking=True)
+        self.h_energy.copy_(self.ws.energies, non_blocking=True)
 
     def check_status(self) -> None:
         self.engine.check_status(self.ws)

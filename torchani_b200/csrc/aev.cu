@@ -18,6 +18,9 @@
 namespace ani {
 
 constexpr int AEV_WARPS = 4;  // warps (= central atoms) per CTA
+#ifndef ANI_AEV_BWD_MIN_CTAS
+#define ANI_AEV_BWD_MIN_CTAS 7  // register budget of the backward kernel: 7 CTAs (28 warps) per SM
+#endif
 
 struct NeighbourRange {
   int lo, hi, code;
@@ -473,7 +476,13 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 // CTAs that straddle a bucket boundary run one staging phase per distinct bucket; neighbourhoods
 // larger than CAND_CAP candidates are staged in windows of the species-major order.
 // ---------------------------------------------------------------------------------------
-constexpr int CAND_CAP = 768;
+#ifndef ANI_AEV_CAND_CAP
+#define ANI_AEV_CAND_CAP 768
+#endif
+#ifndef ANI_AEV_FWD_MIN_CTAS
+#define ANI_AEV_FWD_MIN_CTAS 6
+#endif
+constexpr int CAND_CAP = ANI_AEV_CAND_CAP;
 constexpr int NRANGE = 27;
 constexpr int T2O_CAP = 1024;
 
@@ -490,7 +499,7 @@ struct CtaStage {
 };
 
 template <int NA, int NZ>
-__global__ void __launch_bounds__(AEV_WARPS * 32, 6)
+__global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     k_aev_forward_cta(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                       const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
                       const int32_t* __restrict__ sbin, const float4* __restrict__ ranges,
@@ -872,13 +881,13 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, 6)
 // backward
 // ---------------------------------------------------------------------------------------
 template <int NA, int NZ>
-__global__ void __launch_bounds__(AEV_WARPS * 32)
+__global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
     k_aev_backward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                    const float4* __restrict__ spos, const int32_t* __restrict__ sorted_orig, int lo, int hi,
                    const int32_t* __restrict__ row_of, const float* __restrict__ gaev, int ldx,
                    const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ nbr_list, const ExplicitNbrs ex,
                    const int32_t* __restrict__ species_mask, int cap, float* __restrict__ grad_coords,
-                   int32_t* __restrict__ status, size_t warp_bytes) {
+                   int32_t* __restrict__ status, size_t warp_bytes, int pair_cap) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -891,6 +900,8 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const int nR = P.n_shf_r;
   const int RL = S * nR;
   constexpr int GSTRIDE = 36;  // floats per species-pair row: 16-byte aligned, rows 4 banks apart
+  const unsigned present = (species_mask ? (unsigned)species_mask[0] : 0xffffffffu) & ((1u << S) - 1u);
+  const int n_present = __popc(present);
   float* g_rad = s.rad;
   float* g_ang = s.rad + ((RL + 3) & ~3);
 
@@ -904,14 +915,19 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
   const size_t row = (size_t)row_of[i] * ldx;
   for (int t = lane; t < RL; t += 32) copy_async4(g_rad + t, gaev + row + t);
   {
-    // walk the set bits of the element mask: (s1, s2 >= s1) pairs of present elements only
-    const unsigned present = (species_mask ? (unsigned)species_mask[0] : 0xffffffffu) & ((1u << S) - 1u);
-    for (unsigned m1 = present; m1; m1 &= m1 - 1) {
+    // walk the set bits of the element mask: (s1, s2 >= s1) pairs of present elements only.  The
+    // shared-memory table is COMPACT: row = pair index among the present elements (c1 <= c2 ranks),
+    // `pair_cap` rows; pairs beyond it (more elements than the launch was sized for) are read from
+    // global memory by pair_sums
+    int c1 = 0;
+    for (unsigned m1 = present; m1; m1 &= m1 - 1, ++c1) {
       const int s1 = __ffs(m1) - 1;
       const int base = s1 * (2 * S - s1 + 1) / 2 - s1;  // pair_index(s1, s2) = base + s2
-      for (unsigned m2 = m1; m2; m2 &= m2 - 1) {
+      int c2 = c1;
+      for (unsigned m2 = m1; m2; m2 &= m2 - 1, ++c2) {
         const int pp = base + __ffs(m2) - 1;
-        copy_async4(g_ang + pp * GSTRIDE + lane, gaev + row + RL + pp * 32 + lane);
+        const int cp = c1 * (2 * n_present - c1 + 1) / 2 + (c2 - c1);
+        if (cp < pair_cap) copy_async4(g_ang + cp * GSTRIDE + lane, gaev + row + RL + pp * 32 + lane);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -983,7 +999,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
     }
     // The three sums every pair needs (symmetric in j <-> k):
     //   S0 = sum g f1 f2,  S1 = sum g f1' f2 (d/dcos),  S2 = sum g f1 f2' (d/dRbar)
-    auto pair_sums = [&](const float4& dj, const float4& dk, int pidx, float& cosT, float& inv_rr, float& S0,
+    auto pair_sums = [&](const float4& dj, const float4& dk, int sj, int sk, float& cosT, float& inv_rr, float& S0,
                          float& S1, float& S2) {
       const float dot = dj.x * dk.x + dj.y * dk.y + dj.z * dk.z;
       inv_rr = fast_rcp(fmaxf(dj.w * dk.w, 1e-10f));
@@ -994,7 +1010,14 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
       const float rbar = 0.5f * (dj.w + dk.w);
       // t_z = sum_a g[a,z] f2[a],  u_z = sum_a g[a,z] f2'[a]: the 32 upstream values of this pair are
       // one 16-byte-aligned row -> 8 vector loads
-      const float4* __restrict__ gp = reinterpret_cast<const float4*>(g_ang + pidx * GSTRIDE);
+      // compact table row of the element pair (ranks among the present elements) or, beyond the
+      // table, the upstream row in global memory
+      const int cj = __popc(present & ((1u << sj) - 1u)), ck = __popc(present & ((1u << sk) - 1u));
+      const int clo = min(cj, ck), chi = max(cj, ck);
+      const int cp = clo * (2 * n_present - clo + 1) / 2 + (chi - clo);
+      const float4* __restrict__ gp =
+          cp < pair_cap ? reinterpret_cast<const float4*>(g_ang + cp * GSTRIDE)
+                        : reinterpret_cast<const float4*>(gaev + row + RL + pair_index(sj, sk, S) * 32);
       float tz[NZ], uz[NZ];
 #pragma unroll
       for (int z = 0; z < NZ; ++z) tz[z] = uz[z] = 0.f;
@@ -1067,7 +1090,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
           const float fck = s.afc[k], dfck = s.afcd[k];
           const float inv_rk = dk.w > 1e-10f ? fast_rcp(dk.w) : 0.f;
           float cosT, inv_rr, S0, S1, S2;
-          pair_sums(dj, dk, pair_index(sj, (int)s.nsp[nk_], S), cosT, inv_rr, S0, S1, S2);
+          pair_sums(dj, dk, sj, (int)s.nsp[nk_], cosT, inv_rr, S0, S1, S2);
           // feature = 2 f1 f2 fcj fck (once per unordered pair): its derivative with respect to
           // r_j is this lane's share, the one with respect to r_k goes to the partner row
           const float W = fcj * fck;
@@ -1123,7 +1146,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
             const float4 dk = s.nd[nk_];
             const float fck = s.afc[k];
             float cosT, inv_rr, S0, S1, S2;
-            pair_sums(dj, dk, pair_index(sj, (int)s.nsp[nk_], S), cosT, inv_rr, S0, S1, S2);
+            pair_sums(dj, dk, sj, (int)s.nsp[nk_], cosT, inv_rr, S0, S1, S2);
             const float W = fcj * fck;
             const float dEdRj = S2 * W + 2.0f * S0 * dfcj * fck;  // 2*(0.5*S2*W + S0*fcj'*fck)
             const float dEdcos = 2.0f * W * S1;
@@ -1347,7 +1370,7 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
                                const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
                                const float* grad_aev, int ldx, const int32_t* nbr_cnt, const int32_t* nbr_list,
                                ExplicitNbrs ex, const int32_t* species_mask, int nbr_cap, float* grad_coords,
-                               int32_t* status, void* stream) {
+                               int32_t* status, void* stream, int max_elements = 0) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!grid || !spos || !sorted_orig || !row_of || !grad_aev || !grad_coords || !status) return ANI_ERR_BAD_ARG;
@@ -1357,7 +1380,12 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
   const int S = params->num_species;
   const int RL = S * params->n_shf_r;
   const int NP = S * (S + 1) / 2;
-  const size_t wb = warp_smem_bytes(nbr_cap, ((RL + 3) & ~3) + 36 * NP, true);
+  // rows of the shared-memory gradient table: every element pair, or the pairs of `max_elements`
+  // elements when the caller knows the composition (more elements at run time still work: those
+  // pairs are read from global memory)
+  const int E = (max_elements > 0 && max_elements < S) ? max_elements : S;
+  const int pair_cap = species_mask ? E * (E + 1) / 2 : NP;
+  const size_t wb = warp_smem_bytes(nbr_cap, ((RL + 3) & ~3) + 36 * pair_cap, true);
   const size_t smem = wb * AEV_WARPS;
   const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1366,12 +1394,14 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
     auto k = k_aev_backward<8, 4>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb);
+                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb,
+                                            pair_cap);
   } else {
     auto k = k_aev_backward<4, 8>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb);
+                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb,
+                                            pair_cap);
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
@@ -1429,13 +1459,13 @@ extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_gri
                                      const int32_t* sorted_orig, const int32_t* species_mask, int n, int lo, int hi,
                                      const int32_t* row_of, const float* grad_aev, int ldx, const int32_t* nbr_cnt,
                                      const int32_t* nbr_list, int nbr_cap, float* grad_coords, int32_t* status,
-                                     void* stream) {
+                                     int max_elements, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!nbr_cnt || !nbr_list) return ANI_ERR_BAD_ARG;
   return launch_aev_backward(params, grid, spos, sorted_orig, n, lo, hi, row_of, grad_aev, ldx, nbr_cnt, nbr_list,
                              ExplicitNbrs{nullptr, nullptr, nullptr}, species_mask, nbr_cap, grad_coords, status,
-                             stream);
+                             stream, max_elements);
 }
 
 extern "C" int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, const float* diff_vectors,

@@ -145,12 +145,10 @@ static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st, bool dependent
   cudaLaunchKernelEx(&cfg, k, a);
 }
 
-extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
-                                             const int32_t* row_atom, const int32_t* layout_info,
-                                             const int32_t* aev_blocks, void* act1, void* act2, void* act3,
-                                             float* e_member, int want_backward, int32_t* status, void* stream) {
-  if (!model || !x || !row_atom || !layout_info || !act1 || !act2 || !act3 || !e_member) return ANI_ERR_BAD_ARG;
-  if (want_backward && !dx) return ANI_ERR_BAD_ARG;
+// shared argument checks + the launch-invariant part of the GEMM arguments
+static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* row_atom, const int32_t* layout_info,
+                      void* act1, void* act2, void* act3, int32_t* status, tc::Args& ta) {
+  if (!model || !row_atom || !layout_info || !act1 || !act2 || !act3) return ANI_ERR_BAD_ARG;
   const int S = model->num_species, M = model->num_members;
   if (S < 1 || S > ANI_MAX_SPECIES || M < 1 || M > ANI_MAX_MEMBERS) return ANI_ERR_BAD_ARG;
   if (rows_cap < ANI_TILE_ROWS || rows_cap % ANI_TILE_ROWS) return ANI_ERR_BAD_ARG;
@@ -166,19 +164,15 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
     for (int l = 0; l < 3; ++l)
       if (ANI_OPND_FP16X2 && !(p.w_scale[l] > 0.f)) return ANI_ERR_BAD_ARG;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  // 32-column blocks per row of the tiled activation matrices
-  const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32, kbx = ldx / 32;
-  tc::Args ta;
   ta.layout_info = layout_info;
   ta.kblocks = nullptr;
   ta.nblocks = nullptr;
   ta.num_species = S;
   ta.alpha = model->celu_alpha;
-  ta.e_member = e_member;
+  ta.e_member = nullptr;
   ta.row_atom = row_atom;
   ta.rows_cap = rows_cap;
-  ta.want_backward = want_backward;
+  ta.want_backward = 0;
   ta.ldc = 0;
   ta.c_accumulate = 0;
   static const int gemm_debug = []() {
@@ -189,14 +183,30 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
   for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ta.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
   for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, 0, 0, 1.0f};
   ta.status = status;
-  // operand scales (common.cuh): activations / AEVs carry sv, gradients sg, weights their per-tensor
-  // w_scale; every GEMM divides the product of its two operand scales out of the accumulator
-  const float sv = OPND_SCALE_VALUE, sg = OPND_SCALE_GRAD;
-  auto wsc = [&](const ani_mlp_species& p, int layer) { return ANI_OPND_FP16X2 ? p.w_scale[layer] : 1.0f; };
-  ta.out_scale = sv;
-  ta.y_inv_scale = 1.0f / sv;
+  ta.out_scale = OPND_SCALE_VALUE;
+  ta.y_inv_scale = 1.0f / OPND_SCALE_VALUE;
+  return ANI_OK;
+}
 
-  // ---- forward.  Layer 1: the members share the input -> one GEMM with N = M*h1.
+// operand scales (common.cuh): activations / AEVs carry sv, gradients sg, weights their per-tensor
+// w_scale; every GEMM divides the product of its two operand scales out of the accumulator
+static inline float wsc(const ani_mlp_species& p, int layer) { return ANI_OPND_FP16X2 ? p.w_scale[layer] : 1.0f; }
+
+extern "C" int ani_b200_mlp_forward(const ani_mlp_model* model, const void* x, int rows_cap, const int32_t* row_atom,
+                                    const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2,
+                                    void* act3, float* e_member, int want_backward, int32_t* status, void* stream) {
+  if (!x || !e_member) return ANI_ERR_BAD_ARG;
+  tc::Args ta;
+  const int rc = mlp_common(model, rows_cap, row_atom, layout_info, act1, act2, act3, status, ta);
+  if (rc != ANI_OK) return rc;
+  const int S = model->num_species, M = model->num_members, ldx = model->ldx;
+  const float sv = OPND_SCALE_VALUE, sg = OPND_SCALE_GRAD;
+  cudaStream_t st = (cudaStream_t)stream;
+  // 32-column blocks per row of the tiled activation matrices
+  const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32, kbx = ldx / 32;
+  ta.e_member = e_member;
+  ta.want_backward = want_backward;
+  // Layer 1: the members share the input -> one GEMM with N = M*h1.
   ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
@@ -223,40 +233,74 @@ extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const v
   // G3 = scale_m * w4 * celu'(a3) directly, e_member the per-member atomic energies
   ta.out_scale = sg;  // act3 receives the gradient seed
   launch_gemm_tc<tc::EPI_HEAD>(ta, st, true);
-  if (want_backward) {
-    // ---- backward: G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
-    ta.A = static_cast<const unsigned char*>(act3); ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
-    for (int s = 0; s < S; ++s) {
-      const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b3), nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0,
-                              1.0f / (sg * wsc(p, 2))};
-    }
-    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st, true);
-    ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
-    for (int s = 0; s < S; ++s) {
-      const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0,
-                              1.0f / (sg * wsc(p, 1))};
-    }
-    launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st, true);
-    // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
-    // all SMs are busy even when there are fewer row tiles than SMs); the partial tiles are
-    // accumulated with vector REDs into the zeroed live column blocks of dx
-    ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M;
-    for (int s = 0; s < S; ++s) {
-      const ani_mlp_species& p = model->sp[s];
-      ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr, M * p.h1 / 32, p.h1 / 32,
-                              1.0f / (sg * wsc(p, 0))};
-    }
-    ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
-    ta.c_accumulate = M > 1;
-    if (ta.c_accumulate) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
-    launch_gemm_tc<tc::EPI_PLAIN>(ta, st, true);
-    ta.nblocks = nullptr;
-    ta.c_accumulate = 0;
-  }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
+}
+
+extern "C" int ani_b200_zero_live_blocks(const ani_mlp_model* model, float* dx, const int32_t* layout_info,
+                                         const int32_t* aev_blocks, void* stream) {
+  if (!model || !dx || !layout_info) return ANI_ERR_BAD_ARG;
+  k_zero_live_blocks<<<592, 256, 0, (cudaStream_t)stream>>>(dx, model->ldx, layout_info, model->num_species, aev_blocks);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int rows_cap, const int32_t* row_atom,
+                                     const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2,
+                                     void* act3, int dx_zeroed, int32_t* status, void* stream) {
+  if (!dx) return ANI_ERR_BAD_ARG;
+  tc::Args ta;
+  const int rc = mlp_common(model, rows_cap, row_atom, layout_info, act1, act2, act3, status, ta);
+  if (rc != ANI_OK) return rc;
+  const int S = model->num_species, M = model->num_members, ldx = model->ldx;
+  const float sg = OPND_SCALE_GRAD;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32;
+  ta.want_backward = 1;
+  ta.out_scale = sg;
+  // G2 = (G3 x W3) * celu'(A2), G1 = (G2 x W2) * celu'(A1), dX = G1 x W1
+  ta.A = static_cast<const unsigned char*>(act3); ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
+  for (int s = 0; s < S; ++s) {
+    const ani_mlp_species& p = model->sp[s];
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b3), nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0,
+                            1.0f / (sg * wsc(p, 2))};
+  }
+  // (after a cross-stream join -- the caller zeroed dx elsewhere -- the first launch is a plain one)
+  launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st, !dx_zeroed);
+  ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
+  for (int s = 0; s < S; ++s) {
+    const ani_mlp_species& p = model->sp[s];
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0,
+                            1.0f / (sg * wsc(p, 1))};
+  }
+  launch_gemm_tc<tc::EPI_MUL_DCELU>(ta, st, true);
+  // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
+  // all SMs are busy even when there are fewer row tiles than SMs); the partial tiles are
+  // accumulated with vector REDs into the zeroed live column blocks of dx
+  ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M;
+  for (int s = 0; s < S; ++s) {
+    const ani_mlp_species& p = model->sp[s];
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr, M * p.h1 / 32, p.h1 / 32,
+                            1.0f / (sg * wsc(p, 0))};
+  }
+  ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
+  ta.c_accumulate = M > 1;
+  if (ta.c_accumulate && !dx_zeroed) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
+  launch_gemm_tc<tc::EPI_PLAIN>(ta, st, true);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_mlp_forward_backward(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
+                                             const int32_t* row_atom, const int32_t* layout_info,
+                                             const int32_t* aev_blocks, void* act1, void* act2, void* act3,
+                                             float* e_member, int want_backward, int32_t* status, void* stream) {
+  if (want_backward && !dx) return ANI_ERR_BAD_ARG;
+  int rc = ani_b200_mlp_forward(model, x, rows_cap, row_atom, layout_info, aev_blocks, act1, act2, act3, e_member,
+                                want_backward, status, stream);
+  if (rc != ANI_OK || !want_backward) return rc;
+  return ani_b200_mlp_backward(model, dx, rows_cap, row_atom, layout_info, aev_blocks, act1, act2, act3, 0, status,
+                               stream);
 }
 
 extern "C" int ani_b200_reduce_energies(const ani_mlp_model* model, const float* e_member, int rows_cap,

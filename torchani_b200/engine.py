@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import typing as tp
 
 import numpy as np
@@ -343,6 +344,9 @@ class Workspace:
         self.atomic = torch.zeros(n, **f32)
         self.member_atomic = torch.zeros(num_members, n, **f32)
         self.energies = torch.zeros(n_conf, dtype=torch.float64, device=device)
+        # distinct elements seen at graph-capture time (0 = not known): sizes the shared-memory gradient
+        # table of the AEV backward kernel; the results never depend on it (Engine.note_composition)
+        self.max_elements = 0
 
 
 class StepResult(tp.NamedTuple):
@@ -378,6 +382,10 @@ class Engine:
         self.launches_per_step = 0
         # per-stage CUDA-event timing (bench.py's roofline leg); off by default
         self.profile = False
+        # zero-fill of dE/dAEV and the energy reduction on a forked side stream (see _launch)
+        self.side_stream = os.environ.get("ANI_B200_SIDE_STREAM", "1") != "0"
+        self._side_stream: tp.Optional[torch.cuda.Stream] = None
+        self._ev: tp.List[torch.cuda.Event] = []
         self.stage_events: tp.Dict[str, tp.List[tp.Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
 
     def _timed(self, name: str, fn: tp.Callable[[], int]) -> None:
@@ -453,6 +461,7 @@ class Engine:
                 self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
                 self._launch(ws, bool(pbc), want_grad, lo, hi)
             else:
+                self.note_composition(ws)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     self._launch(ws, bool(pbc), want_grad, lo, hi)
@@ -485,25 +494,75 @@ class Engine:
             ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
             ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0, None, 0,
             ptr(ws.scratch), ptr(ws.status), st))
+        # Two small kernels leave the critical path on a side stream (forked and joined with events, so
+        # the whole thing still captures into one CUDA graph): the zero-fill of dE/dAEV runs beside the
+        # AEV forward / forward GEMMs, the energy reduction beside the backward GEMMs / AEV backward.
+        main = torch.cuda.current_stream(self.device)
+        side = main if (self.profile or not self.side_stream) else self._side()
+        split = side is not main
+        zero_first = want_grad and self.nets.num_members > 1
+        if split and zero_first:
+            self._ev[0].record(main)
+            side.wait_event(self._ev[0])
+            check(L.ani_b200_zero_live_blocks(C.byref(self.nets.model), ptr(ws.dx), ptr(ws.layout_info),
+                                              ptr(ws.aev_blocks), side.cuda_stream), "zero_live_blocks")
+            self._ev[1].record(side)
         self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
             C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin),
             ptr(ws.bucket_ranges), ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
             ptr(ws.row_of), ptr(ws.x), self.nets.ldx, 1, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
             ptr(ws.status), st))
-        self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
-            C.byref(self.nets.model), ptr(ws.x), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom),
-            ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
-            int(want_grad), ptr(ws.status), st))
+
+        def reduce_on(stream_handle):
+            return L.ani_b200_reduce_energies(
+                C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),
+                ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
+                ptr(ws.member_atomic), ptr(ws.energies), stream_handle)
+
+        if not split:
+            self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
+                C.byref(self.nets.model), ptr(ws.x), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom),
+                ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
+                int(want_grad), ptr(ws.status), st))
+        else:
+            check(L.ani_b200_mlp_forward(
+                C.byref(self.nets.model), ptr(ws.x), ws.rows_cap, ptr(ws.row_atom), ptr(ws.layout_info),
+                ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), int(want_grad),
+                ptr(ws.status), st), "mlp_forward")
+            self._ev[2].record(main)
+            side.wait_event(self._ev[2])
+            check(reduce_on(side.cuda_stream), "reduce_energies")
+            self._ev[3].record(side)
+            if want_grad:
+                if zero_first:
+                    main.wait_event(self._ev[1])
+                check(L.ani_b200_mlp_backward(
+                    C.byref(self.nets.model), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom), ptr(ws.layout_info),
+                    ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), int(zero_first), ptr(ws.status), st),
+                    "mlp_backward")
         if want_grad:
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
                 ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
-                ptr(ws.grad), ptr(ws.status), st))
-        self._timed("reduce_energies", lambda: L.ani_b200_reduce_energies(
-            C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),
-            ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
-            ptr(ws.member_atomic), ptr(ws.energies), st))
+                ptr(ws.grad), ptr(ws.status), ws.max_elements, st))
+        if not split:
+            self._timed("reduce_energies", lambda: reduce_on(st))
+        else:
+            main.wait_event(self._ev[3])
+
+    def note_composition(self, ws: Workspace) -> None:
+        """Before a graph capture (the shape has already run eagerly): read the element mask of the last
+        step once and let the AEV backward size its shared-memory gradient table for that many elements
+        (more elements at replay time still give the right answer, from global memory)."""
+        mask = int(ws.aev_blocks[ws.n_blocks + 1].item())
+        ws.max_elements = bin(mask).count("1")
+
+    def _side(self) -> "torch.cuda.Stream":
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.device)
+            self._ev = [torch.cuda.Event() for _ in range(4)]
+        return self._side_stream
 
     # -- status ----------------------------------------------------------------------------
     def check_status(self, ws: tp.Optional[Workspace] = None) -> None:
