@@ -39,10 +39,12 @@ UNIT = "atom-steps/s"
 AEV_FWD_BYTES_PER_ATOM = 4276.0
 AEV_BWD_BYTES_PER_ATOM = 4288.0
 # dram__bytes_read.sum + dram__bytes_write.sum from the ncu --set full capture of this build
-# (profiles/), per launch (AEV kernels) / per six-GEMM sequence at the 9999-atom box; None = not captured
-MLP_DRAM_BYTES_PER_STEP = None
-AEV_FWD_DRAM_BYTES = None
-AEV_BWD_DRAM_BYTES = None
+# (profiles/r01_ncu_full_v10_selected.csv), per launch (AEV kernels) / per six-GEMM sequence at the
+# 9999-atom box.  ncu flushes the caches before every kernel, so these are COLD-cache figures: inside
+# a step the activations a GEMM reads were just written by the previous launch and sit in the L2.
+MLP_DRAM_BYTES_PER_STEP = 574.1e6      # reads 494.6 MB + writes 79.5 MB over the six launches
+AEV_FWD_DRAM_BYTES = 0.93e6            # reads; its 6.4 MB of live AEV blocks stay in the L2 (write-back)
+AEV_BWD_DRAM_BYTES = 14.5e6            # reads (live blocks of dE/dAEV)
 
 
 def workload(n_molecules: int):
@@ -286,7 +288,7 @@ def main():
                         "for water. "
                         "traffic = dram bytes of the six launches (ncu, profiles/), null if not captured for this build"}
     roofline_aev = {
-        "forward": {"kernel": "k_aev_forward<8,4>", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
+        "forward": {"kernel": "k_aev_forward_cta<8,4>", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
                     "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9 / pk["hbm_gbs"],
                     "traffic": AEV_FWD_DRAM_BYTES if world == 1 and args.molecules == 3333 else None},
