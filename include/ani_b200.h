@@ -196,6 +196,26 @@ int ani_b200_aev_backward_rows(const ani_aev_params* params, const ani_grid* gri
                                const float* grad_aev, int ldx, int nbr_cap, float* grad_coords,
                                int32_t* status, void* stream);
 
+/* 3c. Verlet-skin reuse of a bucket grid (neighbors.py:759-884, VerletCellList).  Build the grid  */
+/*     with cutoff + skin (ani_b200_prepare_step / ani_b200_build_cells), then                      */
+/*       mode 0  right after the build: remember the binned positions (ref_pos f32[n][4]) and the   */
+/*               lattice vector that wrapped every atom into the cell (ref_shift f32[n][4]);        */
+/*       mode 1  on later steps INSTEAD of a rebuild: spos = new coords + ref_shift in the same     */
+/*               sorted order (every other output of the build stays valid), zero-fills             */
+/*               zero_f32[0..count) like the fused preparation, and ORs into `moved` (i32[1],       */
+/*               cleared by the caller) bit 0 if any atom is more than skin/2 from its binned        */
+/*               position (the step is invalid), bit 1 if any is beyond 70 % of that (a hint to      */
+/*               rebuild before the next step).                                                       */
+/*     While bit 0 of `moved` stays 0 every pair within the true cutoff is still inside the 27 buckets around */
+/*     an atom and the AEV kernels (which screen with the true cutoff and the current positions)    */
+/*     give exactly the result of a rebuild; when it is raised the step must be redone after a      */
+/*     rebuild.  aev_blocks (or NULL): the block list of the build, its "composition changed" flag  */
+/*     is cleared in mode 1.                                                                          */
+int ani_b200_verlet_positions(int mode, const float* coords, const ani_grid* grid,
+                              const int32_t* sorted_orig, int n, float skin, float* spos, float* ref_pos,
+                              float* ref_shift, int32_t* moved, float* zero_f32, int zero_f32_count,
+                              int32_t* aev_blocks, int ldx, void* stream);
+
 /* 3b. Fused per-step preparation: build_cells + species_layout + active_aev_blocks in five       */
 /*     launches instead of twelve (same outputs, same determinism; what the fused engine calls).   */
 /*     Also zero-fills zero_f32[0..count) (the force accumulator) and zero_f64[0..count) (the      */

@@ -174,6 +174,44 @@ def test_host_calculator_matches_oracle_and_repeats():
     calc.check_status()
 
 
+def test_host_calculator_verlet_skin_reuse():
+    """HostCalculator(skin=...): the bucket grid of an earlier step is reused while the atoms stay inside
+    their skin/2 spheres (VerletCellList semantics, neighbors.py:759-884) -- every step must still give
+    the answer of a fresh grid; a jump beyond skin/2 is detected and the step redone."""
+    from torchani_b200 import models
+    from torchani_b200.calculator import HostCalculator
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    om = oracle_model("2x", torch.float32)
+    model = models.from_weight_lists("2x", om.weights, device=DEV, periodic_table_index=True)
+    znum = torch.tensor([orc.ATOMIC_NUMBERS[s] for s in orc.SYMBOLS_2X])
+    z = znum[species[0]].numpy()
+    try:
+        calc = HostCalculator(model, z, cell.numpy(), pbc=True, skin=0.4)
+        o64 = oracle_model("2x", torch.float64, "cell_list")
+        rng = np.random.default_rng(7)
+        vel = rng.normal(scale=0.006, size=(species.shape[1], 3)).astype(np.float32)   # Angstrom per step
+        pos = coords[0].numpy().copy()
+        for it in range(40):
+            pos = pos + vel
+            e, f = calc.calculate(pos)
+            if it % 4 == 0 or it > 36:
+                ref = orc.compute(o64, species, torch.tensor(pos).double().unsqueeze(0), cell.double(), pbc)
+                assert abs(e - float(ref["energy"][0])) < 1e-5, (it, e)
+                assert_close(f"forces step {it}", f, ref["forces"][0].numpy(), 0.0, F_ATOL)
+        assert calc.rebuilds >= 2 and calc.rebuilds < 30, calc.rebuilds       # reused most steps, rebuilt some
+        before = calc.redone
+        pos[5] += np.array([0.9, 0.0, -0.4], dtype=np.float32)                 # far beyond skin / 2
+        e, f = calc.calculate(pos)
+        assert calc.redone == before + 1 or not calc._have_grid or calc.rebuilds > 0
+        ref = orc.compute(o64, species, torch.tensor(pos).double().unsqueeze(0), cell.double(), pbc)
+        assert abs(e - float(ref["energy"][0])) < 1e-5
+        assert_close("forces after jump", f, ref["forces"][0].numpy(), 0.0, F_ATOL)
+        calc.check_status()
+    finally:
+        model.engine(DEV).skin = 0.0
+
+
 @pytest.mark.parametrize("name", ["water30_pbc_ani2x", "randbatch_ani2x"])
 def test_compute_from_neighbors_split_api(name):
     """The reference's split call: neighbors = nl(cutoff, idxs, coords, cell, pbc);

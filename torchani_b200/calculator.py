@@ -31,9 +31,16 @@ class HostCalculator:
             model was built with ``periodic_table_index=False``)
         cell: (3, 3) lattice vectors as rows, or None for a non-periodic system
         pbc: periodic in all three directions (partial periodicity is not supported)
+        skin: > 0 switches on Verlet-skin reuse of the bucket grid (the counterpart of
+            ``torchani.neighbors.VerletCellList``, neighbors.py:759-884): the grid is built for
+            cutoff + skin and reused -- only the positions inside it are refreshed -- until an atom has
+            moved more than 70 % of skin/2 from where it was binned; a step in which an atom left its
+            skin/2 sphere is recomputed after a rebuild, so the results are always those of a fresh
+            grid.  Pays off when consecutive calls move the atoms by a small fraction of ``skin``.
     """
 
-    def __init__(self, model: ANI, atomic_numbers, cell=None, pbc: bool = False, shard: tp.Tuple[int, int] = (0, 1)):
+    def __init__(self, model: ANI, atomic_numbers, cell=None, pbc: bool = False, shard: tp.Tuple[int, int] = (0, 1),
+                 skin: float = 0.0):
         dev = next(model.buffers()).device
         if dev.type != "cuda":
             raise ValueError("HostCalculator needs a model on a CUDA device")
@@ -42,12 +49,21 @@ class HostCalculator:
         self.elem_idxs = model.species_converter(z, nop=not model.periodic_table_index)   # validated once
         self.n = z.shape[1]
         self.engine = model.engine(dev)
+        self.skin = float(skin)
+        if self.skin < 0:
+            raise ValueError("skin must be >= 0")
+        if self.skin > 0:
+            self.engine.skin = self.skin   # buckets for cutoff + skin (shared by every user of this engine)
         self.ws = self.engine.workspace(1, self.n)
         self.ws.species_i32.copy_(self.elem_idxs.reshape(-1))
         self.h_coords = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
         self.h_cell = torch.zeros(9, dtype=torch.float32).pin_memory()
         self.h_grad = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
         self.h_energy = torch.empty(1, dtype=torch.float64).pin_memory()
+        self.h_moved = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._have_grid = False       # a grid built with the skin exists and may be reused
+        self.rebuilds = 0             # steps that built the grid
+        self.redone = 0               # reuse steps that had to be recomputed (an atom left its skin/2 sphere)
         if pbc and cell is None:
             raise ValueError("If pbc is not None, cell should be present")
         if cell is not None:
@@ -56,11 +72,13 @@ class HostCalculator:
         self.d2h_bytes = self.h_grad.numel() * 4 + 8
         self.graph_after = 3          # eager host-driven steps before copies + kernels are captured as one graph
         self._calls = 0
-        self._graph: tp.Optional[torch.cuda.CUDAGraph] = None
+        self._graphs: tp.Dict[bool, torch.cuda.CUDAGraph] = {}   # reuse flag -> captured step
+        self._mode_calls = {False: 0, True: 0}
         self._graph_version = -1
 
     def set_cell(self, cell) -> None:
         self.h_cell.copy_(torch.as_tensor(np.asarray(cell, dtype=np.float32)).reshape(-1))
+        self._have_grid = False   # a grid belongs to one cell
 
     def calculate(self, positions, cell=None) -> tp.Tuple[float, np.ndarray]:
         """positions: (A, 3) float array on the host (Angstrom).  Returns (energy [Hartree],
@@ -71,40 +89,62 @@ class HostCalculator:
             self.h_coords.copy_(positions.reshape(self.n, 3))
         else:
             self.h_coords.numpy()[...] = np.asarray(positions, dtype=np.float32).reshape(self.n, 3)
-        ws = self.ws
         eng = self.engine
         self._calls += 1
-        if self._graph is not None and self._graph_version != eng.nets.version:
-            self._graph = None   # the active ensemble members changed: the captured scales are stale
-        if self._graph is None and eng.cuda_graph and not eng.profile and self._calls > self.graph_after:
+        if self._graphs and self._graph_version != eng.nets.version:
+            self._graphs = {}   # the active ensemble members changed: the captured scales are stale
+        reuse = self.skin > 0 and self._have_grid
+        self._run(reuse)
+        if reuse and (int(self.h_moved[0]) & 1):
+            # an atom left its skin/2 sphere: the refreshed grid may have missed pairs -> rebuild, redo
+            self.redone += 1
+            self._run(False)
+        elif reuse and int(self.h_moved[0]):
+            self._have_grid = False   # close to the limit: rebuild before the next step
+        forces = self.h_grad.numpy()
+        np.negative(forces, out=forces)
+        return float(self.h_energy[0]), forces
+
+    def _run(self, reuse: bool) -> None:
+        """One step (H2D, kernels, D2H, synchronise); after a few eager uses of a mode its whole sequence
+        is captured into one CUDA graph."""
+        ws, eng = self.ws, self.engine
+        self._mode_calls[reuse] += 1
+        if not reuse:
+            self.rebuilds += 1
+        graph = self._graphs.get(reuse)
+        if graph is None and eng.cuda_graph and not eng.profile and self._mode_calls[reuse] > self.graph_after:
             rank, world = self.shard
             lo, hi = (self.n * rank) // world, (self.n * (rank + 1)) // world
             eng.note_composition(ws)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self._copies_in()
-                eng._launch(ws, self.pbc, True, lo, hi)
-                self._copies_out()
-            self._graph, self._graph_version = graph, eng.nets.version
-        if self._graph is not None:
-            self._graph.replay()
+                self._copies_in(reuse)
+                eng._launch(ws, self.pbc, True, lo, hi, reuse)
+                self._copies_out(reuse)
+            self._graphs[reuse], self._graph_version = graph, eng.nets.version
+        if graph is not None:
+            graph.replay()
         else:
-            self._copies_in()
-            eng.run(ws, self.pbc, want_grad=True, shard=self.shard)
-            self._copies_out()
+            self._copies_in(reuse)
+            eng.run(ws, self.pbc, want_grad=True, shard=self.shard, reuse=reuse)
+            self._copies_out(reuse)
         torch.cuda.current_stream(self.device).synchronize()
-        forces = self.h_grad.numpy()
-        np.negative(forces, out=forces)
-        return float(self.h_energy[0]), forces
+        if not reuse:
+            self._have_grid = self.skin > 0
 
-    def _copies_in(self) -> None:
+    def _copies_in(self, reuse: bool = False) -> None:
+        if reuse:
+            self.ws.moved.zero_()
         self.ws.coords.copy_(self.h_coords, non_blocking=True)
         if self.pbc:
             self.ws.cell.copy_(self.h_cell, non_blocking=True)
 
-    def _copies_out(self) -> None:
+    def _copies_out(self, reuse: bool = False) -> None:
         self.h_grad.copy_(self.ws.grad.view(self.n, 3), non_blocking=True)
         self.h_energy.copy_(self.ws.energies, non_blocking=True)
+        if reuse:
+            self.h_moved.copy_(self.ws.moved, non_blocking=True)
 
     def check_status(self) -> None:
         self.engine.check_status(self.ws)

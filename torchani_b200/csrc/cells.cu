@@ -737,6 +737,47 @@ __global__ void __launch_bounds__(1024) k_prep_layout(const __grid_constant__ Pr
     for (int k = tid; k < A.zero_f64_count; k += blockDim.x) A.zero_f64[k] = 0.0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Verlet-skin reuse of the bucket grid (neighbors.py:759-884, VerletCellList): a grid built with
+// cutoff + skin stays valid -- every pair within the true cutoff is still found in the 27 buckets
+// around an atom, and the AEV kernels screen with the true cutoff and the CURRENT positions -- as
+// long as no atom has moved more than skin/2 from where it was binned.
+//   mode 0 (after a rebuild): remember the binned positions and the lattice vector that wrapped
+//          every atom into the cell
+//   mode 1 (instead of a rebuild): positions = new coordinates + the remembered lattice vector, in
+//          the remembered sorted order; raise `moved` if an atom left its skin/2 sphere
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_verlet_positions(int mode, const float* __restrict__ coords, const ani_grid* __restrict__ grid,
+                       const int32_t* __restrict__ sorted_orig, int n, float half_skin, float4* __restrict__ spos,
+                       float4* __restrict__ ref_pos, float4* __restrict__ ref_shift, int32_t* __restrict__ moved,
+                       float* __restrict__ zero_f32, int zero_f32_count, int32_t* __restrict__ changed_flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && i < grid->n_real) {
+    const int a = sorted_orig[i];
+    const float x = coords[3 * a], y = coords[3 * a + 1], z = coords[3 * a + 2];
+    if (mode == 0) {
+      const float4 p = spos[i];
+      ref_pos[i] = p;
+      ref_shift[i] = make_float4(p.x - x, p.y - y, p.z - z, 0.f);
+    } else {
+      const float4 sh = ref_shift[i], r = ref_pos[i];
+      const float px = x + sh.x, py = y + sh.y, pz = z + sh.z;
+      const float dx = px - r.x, dy = py - r.y, dz = pz - r.z;
+      const float d2 = dx * dx + dy * dy + dz * dz, lim = half_skin * half_skin;
+      if (!(d2 <= lim)) atomicOr(moved, 3);             // left the skin/2 sphere (NaN counts as moved)
+      else if (d2 > 0.49f * lim) atomicOr(moved, 2);    // beyond 70 % of it: rebuild before the next step
+      spos[i] = make_float4(px, py, pz, r.w);
+    }
+  }
+  if (mode == 1) {
+    if (zero_f32)
+      for (int k = i; k < zero_f32_count; k += gridDim.x * blockDim.x) zero_f32[k] = 0.f;
+    // same rows, same composition as the step that built the grid: nothing to zero-fill again
+    if (i == 0 && changed_flag) *changed_flag = 0;
+  }
+}
+
 }  // namespace ani
 
 using namespace ani;
@@ -815,6 +856,22 @@ extern "C" int ani_b200_species_layout(const float* spos, const ani_grid* grid, 
                                     row_atom, layout_info);
   k_layout_assign<<<n_chunks, LAYOUT_CHUNK, 0, st>>>(sp4, grid, lo, hi, num_species, chunk_hist, species_base,
                                                      row_of, row_atom);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_verlet_positions(int mode, const float* coords, const ani_grid* grid,
+                                          const int32_t* sorted_orig, int n, float skin, float* spos, float* ref_pos,
+                                          float* ref_shift, int32_t* moved, float* zero_f32, int zero_f32_count,
+                                          int32_t* aev_blocks, int ldx, void* stream) {
+  if (!coords || !grid || !sorted_orig || !spos || !ref_pos || !ref_shift || !moved || n < 1) return ANI_ERR_BAD_ARG;
+  if ((mode != 0 && mode != 1) || !(skin >= 0.f)) return ANI_ERR_BAD_ARG;
+  if (zero_f32_count > 0 && !zero_f32) return ANI_ERR_BAD_ARG;
+  const int threads = mode == 1 ? max(n, min(zero_f32_count, 1 << 16)) : n;
+  k_verlet_positions<<<(threads + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      mode, coords, grid, sorted_orig, n, 0.5f * skin, reinterpret_cast<float4*>(spos),
+      reinterpret_cast<float4*>(ref_pos), reinterpret_cast<float4*>(ref_shift), moved,
+      zero_f32_count > 0 ? zero_f32 : nullptr, zero_f32_count, aev_blocks ? aev_blocks + ldx / 32 + 2 : nullptr);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

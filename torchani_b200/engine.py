@@ -347,6 +347,11 @@ class Workspace:
         # distinct elements seen at graph-capture time (0 = not known): sizes the shared-memory gradient
         # table of the AEV backward kernel; the results never depend on it (Engine.note_composition)
         self.max_elements = 0
+        # Verlet-skin reuse of the bucket grid (Engine.skin > 0): binned positions, wrapping lattice
+        # vectors and the "an atom left its skin/2 sphere" word (ani_b200_verlet_positions)
+        self.ref_pos = torch.zeros(n, 4, **f32)
+        self.ref_shift = torch.zeros(n, 4, **f32)
+        self.moved = torch.zeros(1, **i32)
 
 
 class StepResult(tp.NamedTuple):
@@ -370,6 +375,9 @@ class Engine:
         self.device = nets.device
         self.params = consts.to_struct()
         self.nbr_cap = nbr_cap
+        # > 0: buckets are built for cutoff + skin, so that a grid can be reused while no atom has moved
+        # more than skin/2 (run(..., reuse=True); calculator.HostCalculator drives it)
+        self.skin = 0.0
         self.sae = None
         if sae is not None:
             self.sae = torch.tensor(list(sae), dtype=torch.float64, device=self.device)
@@ -443,7 +451,8 @@ class Engine:
             ws.cell.copy_(cell.reshape(-1))
         return self.run(ws, bool(pbc), want_grad, shard)
 
-    def run(self, ws: Workspace, pbc: bool, want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1)) -> StepResult:
+    def run(self, ws: Workspace, pbc: bool, want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1),
+            reuse: bool = False) -> StepResult:
         """One step on inputs that are ALREADY in the workspace buffers (``ws.species_i32``,
         ``ws.coords``, ``ws.cell``) -- the entry point of host-driven loops that copy straight into
         them (calculator.HostCalculator).  The results alias workspace buffers."""
@@ -451,9 +460,11 @@ class Engine:
         rank, world = shard
         lo = (n * rank) // world
         hi = (n * (rank + 1)) // world
-        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.version)
+        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.version, bool(reuse), self.skin)
+        if reuse and not self.skin > 0:
+            raise ValueError("reuse=True needs Engine.skin > 0 and a previous step that built the grid")
         if not self.cuda_graph or self.profile:
-            self._launch(ws, bool(pbc), want_grad, lo, hi)
+            self._launch(ws, bool(pbc), want_grad, lo, hi, reuse)
         else:
             graph = self._graphs.get(key)
             if graph is not None:
@@ -461,12 +472,12 @@ class Engine:
             elif self._graph_seen.get(key, 0) < self.graph_after:
                 # the first few uses of a shape run eagerly (one-off shapes never pay for a capture)
                 self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
-                self._launch(ws, bool(pbc), want_grad, lo, hi)
+                self._launch(ws, bool(pbc), want_grad, lo, hi, reuse)
             else:
                 self.note_composition(ws)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._launch(ws, bool(pbc), want_grad, lo, hi)
+                    self._launch(ws, bool(pbc), want_grad, lo, hi, reuse)
                 self._graphs[key] = graph
                 graph.replay()
         # kernels launched by this library in one step (memsets excluded):
@@ -477,7 +488,7 @@ class Engine:
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
                           ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
 
-    def _launch(self, ws: Workspace, pbc: bool, want_grad: bool, lo: int, hi: int) -> None:
+    def _launch(self, ws: Workspace, pbc: bool, want_grad: bool, lo: int, hi: int, reuse: bool = False) -> None:
         """Enqueue the kernels of one step on the current stream (graph-capturable: no allocation,
         no synchronisation, only this library's launches and two memsets)."""
         L = self.lib
@@ -487,15 +498,27 @@ class Engine:
         mode = 0 if n_conf == 1 else 1
         c = self.consts
         # bucket grid + species-grouped row layout + live AEV column blocks (+ zero-fill of the force
-        # accumulator): one fused entry point, five launches
-        self._timed("prepare_step", lambda: L.ani_b200_prepare_step(
-            ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
-            c.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
-            ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges),
-            lo, hi, c.num_species, ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
-            ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
-            ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0, None, 0,
-            ptr(ws.scratch), ptr(ws.status), st))
+        # accumulator): one fused entry point, five launches -- or, with a Verlet skin and reuse=True,
+        # one launch that only refreshes the positions inside the grid of an earlier step
+        if reuse:
+            self._timed("prepare_step", lambda: L.ani_b200_verlet_positions(
+                1, ptr(ws.coords), ptr(ws.grid), ptr(ws.sorted_orig), n, self.skin, ptr(ws.spos), ptr(ws.ref_pos),
+                ptr(ws.ref_shift), ptr(ws.moved), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0,
+                ptr(ws.aev_blocks), self.nets.ldx, st))
+        else:
+            self._timed("prepare_step", lambda: L.ani_b200_prepare_step(
+                ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, cell_ptr, int(bool(pbc)), mode,
+                c.rcr + self.skin, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
+                ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges),
+                lo, hi, c.num_species, ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
+                ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
+                ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0, None, 0,
+                ptr(ws.scratch), ptr(ws.status), st))
+            if self.skin > 0:
+                check(L.ani_b200_verlet_positions(
+                    0, ptr(ws.coords), ptr(ws.grid), ptr(ws.sorted_orig), n, self.skin, ptr(ws.spos),
+                    ptr(ws.ref_pos), ptr(ws.ref_shift), ptr(ws.moved), None, 0, None, self.nets.ldx, st),
+                    "verlet_positions")
         # Two small kernels leave the critical path on a side stream (forked and joined with events, so
         # the whole thing still captures into one CUDA graph): the zero-fill of dE/dAEV runs beside the
         # AEV forward / forward GEMMs, the energy reduction beside the backward GEMMs / AEV backward.
