@@ -139,6 +139,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--molecules", type=int, default=3333, help="water molecules (3333 -> the 10k-atom box)")
     ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--skin", type=float, default=0.0,
+                    help="experiment: Verlet skin (A) of the end-to-end arm; the atoms then move ballistically "
+                         "(300 K Maxwell-Boltzmann velocities, 1 fs per step) so that grid reuse is exercised")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -226,10 +229,17 @@ def main():
     # ---- end to end through the public API with HOST buffers: calculator.HostCalculator.calculate
     #      (host positions in, host energy + forces out; H2D, graph replay, D2H and the sync inside)
     from torchani_b200.calculator import HostCalculator
-    calc = HostCalculator(model, z[0].numpy(), cell.numpy(), pbc=True, shard=(rank, world))
+    calc = HostCalculator(model, z[0].numpy(), cell.numpy(), pbc=True, shard=(rank, world), skin=args.skin)
     h_pos = coords[0].numpy().copy()
+    h_vel = None
+    if args.skin > 0:   # A/fs: sqrt(kT/m), kT = 0.02585 eV, 1 amu A^2/fs^2 = 103.6427 eV
+        import numpy as np
+        mass = np.where(z[0].numpy() == 1, 1.008, 15.999)[:, None]
+        h_vel = (np.random.default_rng(0).normal(size=h_pos.shape) * np.sqrt(0.02585 / (103.6427 * mass))).astype("float32")
 
     def e2e_step():
+        if h_vel is not None:
+            h_pos[...] += h_vel
         e, f = calc.calculate(h_pos)
         if world > 1:  # partial results of this rank's atom slice -> one all-reduce (as in ShardedEngine)
             buf = torch.cat([torch.from_numpy(f).reshape(-1).double(), torch.tensor([e], dtype=torch.float64)]).to(dev)
@@ -316,7 +326,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": float(t_e2e.item()) / args.steps,
                         "api": "torchani_b200.calculator.HostCalculator.calculate (host positions in, host "
-                               "energy+forces out; counterpart of torchani.ase.Calculator.calculate)"},
+                               "energy+forces out; counterpart of torchani.ase.Calculator.calculate)",
+                        **({"verlet_skin_A": args.skin, "grid_rebuilds": calc.rebuilds, "steps_redone": calc.redone,
+                            "calls": calc._calls} if args.skin > 0 else {})},
                 "gpu_launches": eng.launches_per_step * args.steps,
                 "operand_format": {"parts": fmt.parts, "bytes_per_element": 2 * fmt.parts},
                 "stage_ms": stage, "roofline": roofline, "roofline_aev": roofline_aev, "cpu_baseline": cpu}
