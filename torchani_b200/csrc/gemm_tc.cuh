@@ -174,6 +174,70 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster work on a 256-row tile; each loads its own 128
+// rows of A and HALF of B, the tensor cores of both SMs read both halves; one thread of the leader
+// (cluster rank 0) issues the MMAs and signals the barriers of both CTAs
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// wait with cluster-scope acquire (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP_C:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE_C;\n\t"
+      "bra.uni WAIT_LOOP_C;\n\t"
+      "WAIT_DONE_C:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const unsigned short mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -209,9 +273,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 // instruction descriptor: D=f32, A=B=f16 (format 0) or bf16 (format 1), both K-major, M=128, N=bn
-__device__ __forceinline__ uint32_t make_idesc(int bn) {
+__device__ __forceinline__ uint32_t make_idesc(int bn, int m = TM) {
   constexpr uint32_t fmt = ANI_OPND_FP16X2 ? 0u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // CELU(x) = max(0,x) + min(0, alpha*(exp(x/alpha)-1)) with exp via ex2.approx (rel. error ~2^-22:
@@ -243,9 +307,11 @@ struct TileMap {
 
 struct Tile {
   int s, rt, mem, n0, bn;
+  int rt_last;  // last row tile of the species (a CTA pair may own one row tile too many)
 };
 
-__device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm) {
+// pair: the unit of work is a PAIR of row tiles (rank r of the cluster takes row tile rt + r)
+__device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool pair = false) {
   const int S = a.num_species;
   int run = 0;
   tm.kb_count = tm.nb_count = -1;
@@ -265,20 +331,21 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm) {
   tm.first_rt[S] = a.layout_info[4 + S];
   for (int s = 0; s < S; ++s) {
     tm.prefix[s] = run;
-    run += (tm.first_rt[s + 1] - tm.first_rt[s]) * a.members * tm.ntn[s];
+    const int nrt = tm.first_rt[s + 1] - tm.first_rt[s];
+    run += (pair ? (nrt + 1) / 2 : nrt) * a.members * tm.ntn[s];
   }
   tm.prefix[S] = run;
   int bn_max = 32;
   for (int s = 0; s < S; ++s)
     if (tm.first_rt[s + 1] > tm.first_rt[s]) bn_max = max(bn_max, min(TN_MAX, tm.n_eff[s]));
-  tm.stage_bytes = A_BLOCK_BYTES + PARTS * bn_max * ROW_BYTES;
+  tm.stage_bytes = A_BLOCK_BYTES + PARTS * (pair ? bn_max / 2 : bn_max) * ROW_BYTES;  // a pair member holds half of B
   // two store-staging buffers per epilogue warp if that still leaves a double-buffered main loop
   const int avail = SMEM_BYTES - 1024;
   tm.epi_bufs = (avail - 2 * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes >= 2 ? 2 : 1;
   tm.stages = min(MAX_STAGES, (avail - tm.epi_bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes);
 }
 
-__device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, int t) {
+__device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, int t, bool pair = false) {
   Tile x;
   int s = 0;
   while (t >= tm.prefix[s + 1]) ++s;
@@ -288,7 +355,8 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
   const int rm = local / ntn;
   x.s = s;
   x.mem = rm % a.members;
-  x.rt = tm.first_rt[s] + rm / a.members;
+  x.rt = tm.first_rt[s] + (pair ? 2 : 1) * (rm / a.members);
+  x.rt_last = tm.first_rt[s + 1] - 1;
   x.n0 = nt * TN_MAX;
   x.bn = min(TN_MAX, tm.n_eff[s] - x.n0);
   return x;
@@ -337,7 +405,7 @@ __device__ __forceinline__ void join_chunk(const uint4* q, float* y) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int EPI>
+template <int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ Args args) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte aligned operand tiles (swizzle groups are 8 rows x 64 B)
@@ -350,16 +418,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     if (args.trace && blockIdx.x < 4 && tile_local < 8)
       args.trace[(((size_t)blockIdx.x * 8 + tile_local) * 3 + role) * 4 + slot] = clock64();
   };
-  if (threadIdx.x == 0) build_tile_map(args, tm);
+  if (threadIdx.x == 0) build_tile_map(args, tm, PAIR);
   __syncthreads();
+  // CTA pair: cluster of two consecutive CTAs; both walk the same list of row-tile pairs
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int STAGES = tm.stages, STAGE_BYTES = tm.stage_bytes, EPI_BUFS = tm.epi_bufs;
   unsigned char* epi_stage = smem + STAGES * STAGE_BYTES;  // 8 warps x EPI_BUFS x 6 KB store staging
-  __shared__ uint64_t bars[2 * MAX_STAGES + 5];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
   uint64_t* full = bars;                         // [STAGES]  TMA bytes -> MMA
   uint64_t* empty = bars + MAX_STAGES;           // [STAGES]  MMA (commit) -> producer
   uint64_t* tfull = bars + 2 * MAX_STAGES;       // [2]       MMA (commit) -> epilogue
   uint64_t* tempty = bars + 2 * MAX_STAGES + 2;  // [2]       epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  __shared__ uint64_t pfull[MAX_STAGES];         // pair mode, leader: "the peer's operands of this stage have landed"
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -367,16 +440,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);   // the expect_tx arrival of the producer lane (+ the transaction bytes)
       mbar_init(&empty[i], 1);
+      mbar_init(&pfull[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], NUM_EPI_WARPS * 32);
+      // one elected arrival per epilogue warp; in pair mode the leader also counts the peer's warps
+      mbar_init(&tempty[i], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is signalled across
+  if (warp == MMA_WARP) {
+    if (PAIR)
+      tmem_alloc2(tmem_slot, TMEM_COLS);
+    else
+      tmem_alloc(tmem_slot, TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: the next kernel of the stream may start scheduling its CTAs from
@@ -394,20 +478,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     // ================================ producer (TMA) ================================
     uint32_t stage = 0, phase = 0;
     int tloc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
-      const Tile tl = decode_tile(args, tm, t);
+    for (int t = unit0; t < total_tiles; t += unit_stride, ++tloc) {
+      const Tile tl = decode_tile(args, tm, t, PAIR);
       const Species& sp = args.sp[tl.s];
       const int nkb = num_kb(sp.K);
+      const int rt_mine = min(tl.rt + (int)rank, tl.rt_last);  // odd species: the last pair has one real row tile
       if (lane == 0) stamp(tloc, 0, 0);
       const int nkb_all = sp.b_kb_moff ? sp.b_kblocks : (sp.K + TK - 1) / TK;  // K-blocks of the stored B operand
       const int kb_boff = tl.mem * sp.b_kb_moff;                               // split-K: this member's first K-block
       // A: [row tile][32-column block][p1 | p2 | p3]; this GEMM starts at column member * a_moff
       const unsigned char* At =
-          args.A + ((size_t)tl.rt * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
+          args.A + ((size_t)rt_mine * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
       // B: [member][n tile][k block][p1 bn x 64 B | p2 | p3]
       const unsigned char* Bm =
           sp.Bt + (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (PARTS * ROW_BYTES));
-      const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
+      // one piece of this CTA's B rows: all bn rows, or half of them in a CTA pair
+      const uint32_t b_bytes = (uint32_t)(PAIR ? tl.bn / 2 : tl.bn) * ROW_BYTES;
       const bool dense = tm.nb_count < 0;
       // gathered column blocks (layer-1 backward): lane -> (live block q, piece)
       const int gq = lane / PARTS, gpart = lane % PARTS;
@@ -430,9 +516,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           if (lane == 0) {
             mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + PARTS * b_bytes);
             bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
-            if (dense)  // the three pieces are adjacent in global memory and in shared memory: one copy
-              bulk_g2s(st + A_BLOCK_BYTES, Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES),
-                       PARTS * b_bytes, &full[stage]);
+            if (dense) {
+              const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
+              if (!PAIR) {  // the pieces are adjacent in global memory and in shared memory: one copy
+                bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[stage]);
+              } else {      // this CTA's half of the rows of every piece
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p)
+                  bulk_g2s(st + A_BLOCK_BYTES + p * b_bytes, bsrc + (size_t)p * tl.bn * ROW_BYTES + (size_t)rank * b_bytes,
+                           b_bytes, &full[stage]);
+              }
+            }
           }
           __syncwarp();
           if (g_active)
@@ -454,61 +548,97 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     // ================================ MMA issuer ================================
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     int tloc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
-      const Tile tl = decode_tile(args, tm, t);
-      const int nkb = num_kb(args.sp[tl.s].K);
-      const uint32_t idesc = make_idesc(tl.bn);
-      const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
-      if (lane == 0) stamp(tloc, 1, 0);
-      mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after();
-      if (lane == 0) stamp(tloc, 1, 1);
-      const uint32_t d_tmem = tmem_base + acc * TN_MAX;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (lane == 0 && kb == 0) stamp(tloc, 1, 2);
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BLOCK_BYTES;
-          const uint64_t a1 = make_desc(sa), a2 = make_desc(sa + A_PART_BYTES);
-          const uint64_t b1 = make_desc(sb), b2 = make_desc(sb + b_bytes);
-#if !ANI_OPND_FP16X2
-          const uint64_t a3 = make_desc(sa + 2 * A_PART_BYTES), b3 = make_desc(sb + 2 * b_bytes);
-#endif
-#pragma unroll
-          for (int k = 0; k < TK / 16; ++k) {
-            if (args.debug & 4) break;
-            const uint64_t adv = (uint64_t)(k * 2);  // 16 pieces = 32 B = 2 x 16 B along the swizzle row
-            // smallest terms first
-#if ANI_OPND_FP16X2
-            umma_f16(d_tmem, a2 + adv, b1 + adv, idesc, (kb | k) != 0);
-            umma_f16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
-            umma_f16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
-#else
-            umma_f16(d_tmem, a3 + adv, b1 + adv, idesc, (kb | k) != 0);
-            umma_f16(d_tmem, a1 + adv, b3 + adv, idesc, 1);
-            umma_f16(d_tmem, a2 + adv, b2 + adv, idesc, 1);
-            umma_f16(d_tmem, a2 + adv, b1 + adv, idesc, 1);
-            umma_f16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
-            umma_f16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
-#endif
+    if (PAIR && rank != 0) {
+      // peer of a CTA pair: no MMAs to issue (the leader's instructions drive both tensor cores); relay
+      // "my operands of this stage have landed" to the leader
+      for (int t = unit0; t < total_tiles; t += unit_stride) {
+        const Tile tl = decode_tile(args, tm, t, PAIR);
+        const int nkb = num_kb(args.sp[tl.s].K);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (lane == 0) mbar_arrive_remote(&pfull[stage], 0);
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
-          umma_commit(&empty[stage]);                   // smem slot free once these MMAs retire
-          if (kb == nkb - 1) {
-            umma_commit(&tfull[acc]);  // accumulator complete
-            stamp(tloc, 1, 3);
-          }
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
         }
       }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+    } else {
+      for (int t = unit0; t < total_tiles; t += unit_stride, ++tloc) {
+        const Tile tl = decode_tile(args, tm, t, PAIR);
+        const int nkb = num_kb(args.sp[tl.s].K);
+        const uint32_t idesc = make_idesc(tl.bn, PAIR ? 2 * TM : TM);
+        const uint32_t b_bytes = (uint32_t)(PAIR ? tl.bn / 2 : tl.bn) * ROW_BYTES;
+        if (lane == 0) stamp(tloc, 1, 0);
+        // the epilogue (of both CTAs in a pair) has drained this accumulator
+        if (PAIR)
+          mbar_wait_cluster(&tempty[acc], acc_phase ^ 1);
+        else
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        if (lane == 0) stamp(tloc, 1, 1);
+        const uint32_t d_tmem = tmem_base + acc * TN_MAX;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (PAIR) mbar_wait_cluster(&pfull[stage], phase);
+          tc_fence_after();
+          if (lane == 0 && kb == 0) stamp(tloc, 1, 2);
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint32_t sb = sa + A_BLOCK_BYTES;
+            const uint64_t a1 = make_desc(sa), a2 = make_desc(sa + A_PART_BYTES);
+            const uint64_t b1 = make_desc(sb), b2 = make_desc(sb + b_bytes);
+#if !ANI_OPND_FP16X2
+            const uint64_t a3 = make_desc(sa + 2 * A_PART_BYTES), b3 = make_desc(sb + 2 * b_bytes);
+#endif
+            auto mma = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
+              if (PAIR)
+                umma_f16_pair(d_tmem, da, db, idesc, accumulate);
+              else
+                umma_f16(d_tmem, da, db, idesc, accumulate);
+            };
+#pragma unroll
+            for (int k = 0; k < TK / 16; ++k) {
+              if (args.debug & 4) break;
+              const uint64_t adv = (uint64_t)(k * 2);  // 16 pieces = 32 B = 2 x 16 B along the swizzle row
+              // smallest terms first
+#if ANI_OPND_FP16X2
+              mma(a2 + adv, b1 + adv, (kb | k) != 0);
+              mma(a1 + adv, b2 + adv, 1);
+              mma(a1 + adv, b1 + adv, 1);
+#else
+              mma(a3 + adv, b1 + adv, (kb | k) != 0);
+              mma(a1 + adv, b3 + adv, 1);
+              mma(a2 + adv, b2 + adv, 1);
+              mma(a2 + adv, b1 + adv, 1);
+              mma(a1 + adv, b2 + adv, 1);
+              mma(a1 + adv, b1 + adv, 1);
+#endif
+            }
+            // smem slot free once these MMAs retire (in both CTAs of a pair)
+            if (PAIR)
+              umma_commit_pair(&empty[stage]);
+            else
+              umma_commit(&empty[stage]);
+            if (kb == nkb - 1) {  // accumulator complete
+              if (PAIR)
+                umma_commit_pair(&tfull[acc]);
+              else
+                umma_commit(&tfull[acc]);
+              stamp(tloc, 1, 3);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {
@@ -532,10 +662,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
     unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
     const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward) && !(args.debug & 32);
     int tloc = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tloc) {
-      const Tile tl = decode_tile(args, tm, t);
+    for (int t = unit0; t < total_tiles; t += unit_stride, ++tloc) {
+      const Tile tl = decode_tile(args, tm, t, PAIR);
       const Species& sp = args.sp[tl.s];
       const float acc_scale = sp.acc_scale;
+      // CTA pair: rank r owns row tile rt + r; the last pair of a species with an odd number of row
+      // tiles has a second member without rows (it fed a copy of the last tile to the MMAs): no output
+      const int rt_mine = min(tl.rt + (int)rank, tl.rt_last);
+      const bool valid = !PAIR || tl.rt + (int)rank <= tl.rt_last;
       if (threadIdx.x == 0) stamp(tloc, 2, 0);
       // bias (and final-layer weights) of this tile -> shared memory while the main loop runs
       const float* __restrict__ bias = s_bias[acc];
@@ -548,7 +682,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // epilogue warps only
       }
-      const int my_row = tl.rt * TM + r_tile;
+      if (valid) {
+      const int my_row = rt_mine * TM + r_tile;
       float e_acc = 0.f, seed = 0.f;
       bool row_valid = false;
       if (EPI == EPI_HEAD) {
@@ -557,7 +692,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       }
       // tiled C: the block of 32-column group g is [row tile][(member*c_moff + n0)/32 + g]
       unsigned char* ct = reinterpret_cast<unsigned char*>(args.C) +
-                          ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
+                          ((size_t)rt_mine * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
       float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
       const int ngroups = tl.bn / 32;
       // stored activation (all pieces) of 16 columns = chunks 2*hh, 2*hh+1 of group g, this thread's row
@@ -680,8 +815,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
               row_valid ? e_part[warp * 32 + lane] + e_part[(warp + 4) * 32 + lane] + sp.b4[tl.mem] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
       }
+      } else {
+        mbar_wait(&tfull[acc], acc_phase);  // nothing to drain, but the accumulator hand-shake goes on
+        tc_fence_after();
+      }
+      // hand the accumulator back: one elected arrival per warp (on the leader's barrier in a pair)
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR && rank != 0)
+          mbar_arrive_remote(&tempty[acc], 0);
+        else
+          mbar_arrive(&tempty[acc]);
+      }
       if (threadIdx.x == 0) stamp(tloc, 2, 2);
       if (++acc == 2) {
         acc = 0;
@@ -694,10 +840,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
   // ---- teardown
   if (warp < NUM_EPI_WARPS && lane == 0) bulk_wait_all();  // outstanding TMA stores are complete
   tc_fence_before();
-  __syncthreads();
+  if (PAIR)
+    cluster_sync_all();  // neither CTA leaves (or frees tensor memory) while the other still works
+  else
+    __syncthreads();
   if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR)
+      tmem_dealloc2(tmem_base, TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -112,7 +112,7 @@ extern "C" int ani_b200_debug_gemm_trace(long long* buf, int launches) {
 // new CTA starts as soon as one of them exits), run their prologue (barriers, tensor memory, tile
 // map) and block in griddepcontrol.wait until the previous grid has completed and flushed.
 template <int EPI>
-static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st, bool dependent = false) {
+static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st, bool dependent = false, bool allow_pair = true) {
   tc::Args a = a_in;
   a.trace = nullptr;
   if (g_trace && g_trace_next < g_trace_launches) a.trace = g_trace + (size_t)(g_trace_next++) * TRACE_WORDS_PER_LAUNCH;
@@ -122,27 +122,51 @@ static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st, bool dependent
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  auto k = tc::k_gemm_tc<EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    attr_set = true;
-  }
   static const bool pdl = []() {
     const char* e = getenv("ANI_B200_PDL");  // ANI_B200_PDL=0: plain stream order
     return !e || atoi(e) != 0;
   }();
+  // CTA pairs (cta_group::2, clusters of 2): each SM loads half of B.  ANI_B200_GEMM_PAIR=1 switches
+  // it on for the dense launches (the block-sparse layer-1 backward gathers B in 32-row blocks and
+  // stays single)
+  static const bool pair_env = []() {
+    const char* e = getenv("ANI_B200_GEMM_PAIR");
+    return e && atoi(e) != 0;
+  }();
+  const bool pair = pair_env && allow_pair && EPI != tc::EPI_PLAIN && a.nblocks == nullptr;
+  auto k1 = tc::k_gemm_tc<EPI, false>;
+  auto k2 = tc::k_gemm_tc<(EPI == tc::EPI_PLAIN ? tc::EPI_BIAS_CELU : EPI), true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    attr_set = true;
+  }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(num_sms);
+  cfg.gridDim = dim3(pair ? (num_sms & ~1) : num_sms);
   cfg.blockDim = dim3(tc::THREADS);
   cfg.dynamicSmemBytes = tc::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (dependent && pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (dependent && pdl) ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, k, a);
+  cfg.numAttrs = na;
+  if (pair)
+    cudaLaunchKernelEx(&cfg, k2, a);
+  else
+    cudaLaunchKernelEx(&cfg, k1, a);
 }
 
 // shared argument checks + the launch-invariant part of the GEMM arguments
