@@ -342,6 +342,8 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool 
   // two store-staging buffers per epilogue warp if that still leaves a double-buffered main loop
   const int avail = SMEM_BYTES - 1024;
   tm.epi_bufs = (avail - 2 * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes >= 2 ? 2 : 1;
+  // (a single store buffer per warp would buy one more main-loop stage: measured on B200, no gain --
+  // 0.2374 vs 0.2358 ms for the six launches)
   tm.stages = min(MAX_STAGES, (avail - tm.epi_bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes);
 }
 
