@@ -147,6 +147,46 @@ def test_ani_model_energy_and_autograd_forces(name):
         model((torch.full_like(z, 15).to(DEV), c), cell_d, pbc_d)  # phosphorus is not an ANI-2x element
 
 
+def test_ani_model_member_forces_qbc_and_neighbor_entry():
+    """arch.py:354-576: members_forces / energies_qbcs / atomic_stdev / force_qbc and the
+    compute_from_neighbors entry point of the model, against per-member oracle runs."""
+    from torchani_b200 import models, neighbors
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    om = oracle_model("2x", torch.float32)
+    o64 = oracle_model("2x", torch.float64, "cell_list")
+    model = models.from_weight_lists("2x", om.weights, device=DEV, periodic_table_index=True)
+    znum = torch.tensor([orc.ATOMIC_NUMBERS[s] for s in orc.SYMBOLS_2X])
+    z = znum[species].to(DEV)
+    c, cell_d, pbc_d = coords.to(DEV), cell.to(DEV), pbc.to(DEV)
+    sf = model.members_forces((z, c), cell_d, pbc_d)
+    assert sf.energies.shape == (8, 1) and sf.forces.shape == (8, 1, species.shape[1], 3)
+    for m in (0, 5):
+        ref = orc.compute(o64, species, coords.double(), cell.double(), pbc, members=[m])
+        assert abs(float(sf.energies[m, 0]) - float(ref["energy"][0])) < 5e-3      # float32 at |E| ~ 760 Ha
+        assert_close(f"member {m} forces", sf.forces[m].cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+    assert_close("mean of member forces", sf.forces.mean(0).cpu().numpy(), rec["forces"], 0.0, F_ATOL)
+    assert list(model.neural_networks.active_members_idxs) == list(range(8))       # restored
+    ev = model((z, c), cell_d, pbc_d, ensemble_values=True).energies
+    q = model.energies_qbcs((z, c), cell_d, pbc_d)
+    assert_close("qbc", q.qbcs.cpu().numpy(), (ev.std(0) / np.sqrt(species.shape[1])).cpu().numpy(), 1e-6, 1e-9)
+    st = model.atomic_stdev((z, c), cell_d, pbc_d)
+    ref_std = np.std(rec["member_atomic"], axis=0, ddof=1)
+    assert_close("atomic stdev", st.stdev_atomic_energies.cpu().numpy(), ref_std, 1e-3, 1e-6)
+    fq = model.force_qbc((z, c), cell_d, pbc_d)
+    mags = sf.forces.norm(dim=-1)
+    assert_close("force magnitudes", fq.magnitudes.cpu().numpy(), mags.mean(0).cpu().numpy(), 1e-6, 1e-9)
+    assert fq.relative_stdev.shape == mags.shape[1:] and bool((fq.relative_range > 0).all())
+    # neighbour-list entry point of the model: a list built with a LARGER cutoff is narrowed down first
+    idx = model.species_converter(z)
+    nl = neighbors.CellList()(6.0, idx, c, cell_d, pbc_d)
+    e_nb = model.compute_from_neighbors(idx, c, nl)
+    sae = float(orc.self_energies(orc.SYMBOLS_2X, orc.GSAES_WB97X_631GD, species, torch.float64).sum())
+    assert abs(float(e_nb[0]) - (float(rec["energy_nn"][0]) + sae)) < 5e-3
+    e_at = model.compute_from_neighbors(idx, c, nl, atomic=True)
+    assert e_at.shape == species.shape
+
+
 def test_host_calculator_matches_oracle_and_repeats():
     """calculator.HostCalculator (counterpart of ase.py:75-173): host positions in, host E/F out;
     repeated calls replay the captured CUDA graph and must keep giving the oracle's answer."""

@@ -21,7 +21,7 @@ from torch import Tensor
 
 from .aev import AEVComputer
 from .engine import Engine, StepResult
-from .neighbors import NeighborlistArg, _validate_inputs
+from .neighbors import Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff
 from .nn import (ANINetworks, ATOMIC_NUMBER, AtomicContainer, AtomicNetwork, Ensemble, SpeciesConverter,
                  SpeciesEnergies)
 
@@ -30,6 +30,36 @@ SYMBOLS_2X = ("H", "C", "N", "O", "S", "F", "Cl")
 # constants.py:88-96 (wb97x-631gd ground-state atomic energies, Hartree)
 GSAES_WB97X_631GD = {"H": -0.4993212, "C": -37.8338334, "N": -54.5732825, "O": -75.0424519,
                      "S": -398.0814169, "F": -99.6949007, "Cl": -460.1167008}
+
+
+class SpeciesForces(tp.NamedTuple):        # tuples.py of the reference
+    species: Tensor
+    energies: Tensor
+    forces: Tensor
+
+
+class SpeciesEnergiesQBC(tp.NamedTuple):
+    species: Tensor
+    energies: Tensor
+    qbcs: Tensor
+
+
+class AtomicStdev(tp.NamedTuple):
+    species: Tensor
+    energies: Tensor
+    stdev_atomic_energies: Tensor
+
+
+class ForceMagnitudes(tp.NamedTuple):
+    species: Tensor
+    magnitudes: Tensor
+
+
+class ForceStdev(tp.NamedTuple):
+    species: Tensor
+    magnitudes: Tensor
+    relative_stdev: Tensor
+    relative_range: Tensor
 
 
 class SelfEnergy(torch.nn.Module):
@@ -165,6 +195,93 @@ class ANI(torch.nn.Module):
         else:
             energies = e.to(coords.dtype)
         return SpeciesEnergies(elem_idxs, energies)
+
+    # -- entry point with a caller-supplied neighbour list (arch.py:354-381, potentials/nnp.py:20-32) ----
+    def compute_from_neighbors(self, elem_idxs: Tensor, coords: Tensor, neighbors: Neighbors, charge: int = 0,
+                               atomic: bool = False, ensemble_values: bool = False) -> Tensor:
+        """Energies from element indices, coordinates and the result of a neighbour-list calculation
+        (pairs beyond the radial cutoff are discarded first, as ``discard_outside_cutoff`` does for
+        every potential of the reference).  Shape: (C,), (C, A), (M, C) or (M, C, A)."""
+        self._check_inputs(elem_idxs, coords, charge)
+        neighbors = discard_outside_cutoff(neighbors, self.cutoff)
+        aevs = self.aev_computer.compute_from_neighbors(elem_idxs, coords, neighbors)
+        energies = self.neural_networks(elem_idxs, aevs, atomic, ensemble_values)
+        if self.energy_shifter._enabled:
+            energies = energies + self.energy_shifter(elem_idxs, atomic=atomic).to(energies.dtype)
+        return energies
+
+    # -- ensemble statistics (arch.py:385-576; query-by-committee active learning) ---------------------
+    def atomic_energies(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                        pbc: tp.Optional[Tensor] = None, charge: int = 0,
+                        ensemble_values: bool = False) -> SpeciesEnergies:
+        return self(species_coordinates, cell, pbc, charge, True, ensemble_values)
+
+    def members_forces(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                       pbc: tp.Optional[Tensor] = None, charge: int = 0) -> SpeciesForces:
+        """Energies (M, C) and forces (M, C, A, 3) of every active ensemble member (arch.py:403-436).
+        The reference differentiates each member's energy by autograd; here the engine is run once per
+        member with only that member active (same kernels, analytic forces)."""
+        species, coords = species_coordinates
+        self._check_inputs(species, coords, charge)
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        _validate_inputs(self.cutoff, elem_idxs, coords, cell, pbc)
+        eng = self.engine(coords.device)
+        active = list(self.neural_networks.active_members_idxs)
+        energies, forces = [], []
+        try:
+            for m in active:
+                self.neural_networks.set_active_members([m])
+                res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True)
+                energies.append(res.energies.clone())
+                forces.append(-res.grad.clone())
+        finally:
+            self.neural_networks.set_active_members(active)
+        eng.check_status()
+        return SpeciesForces(elem_idxs, torch.stack(energies).to(coords.dtype), torch.stack(forces))
+
+    def energies_qbcs(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                      pbc: tp.Optional[Tensor] = None, unbiased: bool = True, charge: int = 0) -> SpeciesEnergiesQBC:
+        """Mean energies and query-by-committee factors std_m(E_m) / sqrt(num_atoms) (arch.py:439-485)."""
+        elem_idxs, energies = self(species_coordinates, cell, pbc, charge, False, True)
+        if energies.shape[0] == 1:
+            qbc = torch.zeros_like(energies).squeeze(0)
+        else:
+            qbc = energies.std(0, unbiased=unbiased)
+        qbc = qbc / (elem_idxs >= 0).sum(dim=1, dtype=energies.dtype).sqrt()
+        return SpeciesEnergiesQBC(elem_idxs, energies.mean(dim=0), qbc)
+
+    def atomic_stdev(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                     pbc: tp.Optional[Tensor] = None, charge: int = 0, ensemble_values: bool = False,
+                     unbiased: bool = True) -> AtomicStdev:
+        elem_idxs, energies = self(species_coordinates, cell, pbc, charge, True, True)
+        stdev = torch.zeros_like(energies).squeeze(0) if energies.shape[0] == 1 else energies.std(0, unbiased=unbiased)
+        if not ensemble_values:
+            energies = energies.mean(0)
+        return AtomicStdev(elem_idxs, energies, stdev)
+
+    def force_magnitudes(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                         pbc: tp.Optional[Tensor] = None, ensemble_values: bool = False) -> ForceMagnitudes:
+        species, _, members_forces = self.members_forces(species_coordinates, cell, pbc)
+        magnitudes = members_forces.norm(dim=-1)
+        if not ensemble_values:
+            magnitudes = magnitudes.mean(0)
+        return ForceMagnitudes(species, magnitudes)
+
+    def force_qbc(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
+                  pbc: tp.Optional[Tensor] = None, ensemble_values: bool = False, unbiased: bool = True) -> ForceStdev:
+        """Mean force magnitudes, relative std and relative range across the ensemble (arch.py:543-576)."""
+        species, mags = self.force_magnitudes(species_coordinates, cell, pbc, True)
+        eps = 1e-8
+        mean_mags = mags.mean(0)
+        if mags.shape[0] == 1:
+            relative_std = torch.zeros_like(mags).squeeze(0)
+            relative_range = torch.ones_like(mags).squeeze(0)
+        else:
+            relative_std = (mags.std(0, unbiased=unbiased) + eps) / (mean_mags + eps)
+            relative_range = ((mags.max(dim=0).values - mags.min(dim=0).values) + eps) / (mean_mags + eps)
+        if not ensemble_values:
+            mags = mean_mags
+        return ForceStdev(species, mags, relative_std, relative_range)
 
     def energies_f64(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
                      pbc: tp.Optional[Tensor] = None) -> Tensor:
