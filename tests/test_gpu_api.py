@@ -40,6 +40,42 @@ def test_neighborlists_match_reference_pairs(name):
     assert bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
 
 
+def test_verlet_cell_list_matches_cell_list():
+    """neighbors.VerletCellList: cached pairs within cutoff + skin, re-screened every call; the pair set
+    must equal a fresh CellList at every step, and the cache must be rebuilt after a large move."""
+    from torchani_b200 import neighbors
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    sp, c, cell_d, pbc_d = species.to(DEV), coords.to(DEV), cell.to(DEV), pbc.to(DEV)
+    vl, cl = neighbors.VerletCellList(skin=0.6), neighbors.CellList()
+    g = torch.Generator(device="cpu").manual_seed(3)
+
+    def canon(nb):
+        i = nb.indices.cpu().numpy()
+        d = nb.distances.detach().cpu().numpy()
+        lo, hi = np.minimum(i[0], i[1]), np.maximum(i[0], i[1])
+        order = np.lexsort((np.round(d, 4), hi, lo))
+        return lo[order], hi[order], d[order]
+
+    for it in range(8):
+        c = c + (torch.randn(c.shape, generator=g) * 0.03).to(DEV)
+        a, b = canon(vl(5.1, sp, c, cell_d, pbc_d)), canon(cl(5.1, sp, c, cell_d, pbc_d))
+        assert a[0].shape == b[0].shape and (a[0] == b[0]).all() and (a[1] == b[1]).all()
+        assert np.abs(a[2] - b[2]).max() < 1e-5
+    assert 1 <= vl.rebuilds < 8
+    before = vl.rebuilds
+    c = c.clone()
+    c[0, 4] += torch.tensor([1.5, 0.0, 0.0], device=DEV)
+    a, b = canon(vl(5.1, sp, c, cell_d, pbc_d)), canon(cl(5.1, sp, c, cell_d, pbc_d))
+    assert vl.rebuilds == before + 1 and (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    c2 = c.clone().requires_grad_(True)
+    nb = vl(5.1, sp, c2, cell_d, pbc_d)
+    (gr,) = torch.autograd.grad(nb.distances.sum(), c2)            # autograd edge to the coordinates
+    assert gr.shape == c2.shape and bool(torch.isfinite(gr).all())
+    with pytest.raises(ValueError):
+        neighbors.VerletCellList(skin=0.0)
+
+
 def test_neighborlist_validation():
     from torchani_b200.neighbors import CellList
     nl = CellList()

@@ -178,6 +178,57 @@ class AdaptiveList(Neighborlist):
         return _half_list(cutoff, species, coords, cell, pbc)
 
 
+class VerletCellList(CellList):
+    r"""Cell list with a Verlet skin (neighbors.py:759-884): the pairs within ``cutoff + skin`` are
+    cached together with their lattice shifts and only re-screened with the true cutoff and the
+    current coordinates, until an atom has moved ``skin / 2`` or the cell changes.  (The fused engine
+    caches the bucket grid instead of a pair list: ``calculator.HostCalculator(skin=...)``.)"""
+
+    def __init__(self, skin: float = 1.0):
+        super().__init__()
+        if skin <= 0.0:
+            raise ValueError("skin must be a positive float")
+        self.skin = skin
+        self.reset_cached_values()
+
+    def reset_cached_values(self) -> None:
+        self._prev_idx: tp.Optional[Tensor] = None       # (2, P) pairs within cutoff + skin
+        self._prev_shift: tp.Optional[Tensor] = None     # (P, 3) lattice shift of every cached pair
+        self._prev_coords: tp.Optional[Tensor] = None
+        self._prev_cell: tp.Optional[Tensor] = None
+        self._prev_cutoff = 0.0
+        self.rebuilds = 0
+
+    def _can_use_prev_list(self, cutoff: float, coords: Tensor, cell: tp.Optional[Tensor]) -> bool:
+        if self._prev_idx is None or self._prev_coords is None or self._prev_coords.shape != coords.shape:
+            return False
+        if cutoff > self._prev_cutoff or (cell is None) != (self._prev_cell is None):
+            return False
+        if cell is not None and not torch.equal(cell.detach(), self._prev_cell):
+            return False
+        moved2 = (coords.detach() - self._prev_coords).pow(2).sum(-1)
+        return bool((moved2 < (self.skin / 2) ** 2).all())
+
+    def forward(self, cutoff, species, coords, cell=None, pbc=None) -> Neighbors:
+        _validate_inputs(cutoff, species, coords, cell, pbc, supports_batches=False)
+        flat = coords.reshape(-1, 3)
+        if not self._can_use_prev_list(cutoff, coords, cell):
+            wide = _half_list(cutoff + self.skin, species, coords.detach(), cell, pbc)
+            i0, i1 = wide.indices[0], wide.indices[1]
+            # diff = x[i0] - x[i1] + shift (neighbors.py:107-111): the shift is what stays constant
+            self._prev_shift = wide.diff_vectors - (flat.detach().index_select(0, i0) - flat.detach().index_select(0, i1))
+            self._prev_idx = wide.indices
+            self._prev_coords = coords.detach().clone()
+            self._prev_cell = None if cell is None else cell.detach().clone()
+            self._prev_cutoff = float(cutoff)
+            self.rebuilds += 1
+        idx, shift = self._prev_idx, self._prev_shift
+        diff = flat.index_select(0, idx[0]) - flat.index_select(0, idx[1]) + shift
+        dist = diff.norm(2, -1)
+        keep = (dist.detach() <= cutoff).nonzero().flatten()      # narrow_down (neighbors.py:64-113)
+        return Neighbors(idx.index_select(1, keep), dist.index_select(0, keep), diff.index_select(0, keep))
+
+
 NeighborlistArg = tp.Union[str, Neighborlist]
 
 
@@ -186,7 +237,7 @@ def _parse_neighborlist(neighborlist: NeighborlistArg = "cell_list") -> Neighbor
     if isinstance(neighborlist, Neighborlist):
         return neighborlist
     table = {"all_pairs": AllPairs, "cell_list": CellList, "adaptive": AdaptiveList,
-             "fast_cell_list": CellList, "base": Neighborlist}
+             "fast_cell_list": CellList, "verlet_cell_list": VerletCellList, "base": Neighborlist}
     if neighborlist not in table:
         raise ValueError(f"Unsupported neighborlist: {neighborlist}")
     return table[neighborlist]()
