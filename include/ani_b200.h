@@ -52,6 +52,7 @@ extern "C" {
 #define ANI_STATUS_ANG_OVERFLOW 2   /* an atom has more angular neighbours than ANI_MAX_ANG */
 #define ANI_STATUS_CELL_TOO_SMALL 4 /* periodic cell thinner than the cutoff (neighbors.py:402-403) */
 #define ANI_STATUS_PAIR_OVERFLOW 8  /* half neighbour list exceeds the caller's capacity */
+#define ANI_VIRIAL_SLOTS 64         /* partial virial sums (ani_b200_aev_backward)          */
 #define ANI_STATUS_OPERAND_RANGE 16 /* a value left the range of the half-precision GEMM operand pieces */
 
 #define ANI_MAX_ANG 96 /* angular neighbours (<= Rca) one central atom may have */
@@ -166,13 +167,15 @@ int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
 /*    unwritten).  max_elements (0 = num_species): how many distinct elements the caller      */
 /*    expects in the system; it only sizes the kernel's shared-memory gradient table (higher   */
 /*    occupancy for few-element systems) -- pairs beyond it are read from global memory, the   */
-/*    result never depends on it.                                                               */
+/*    result never depends on it.  virial (or NULL): f64[ANI_VIRIAL_SLOTS][9], zeroed by the     */
+/*    caller; the kernel adds partial sums of W_ab = sum_pairs (dE/dDelta)_a Delta_b, the "f dot r" */
+/*    virial of ase.py:164-168 (stress = sum over the slots / volume), row-major a, b.             */
 int ani_b200_aev_backward(const ani_aev_params* params, const ani_grid* grid, const float* spos,
                           const int32_t* sorted_orig, const int32_t* species_mask, int n, int lo,
                           int hi, const int32_t* row_of, const float* grad_aev, int ldx,
                           const int32_t* nbr_cnt,
                           const int32_t* nbr_list, int nbr_cap, float* grad_coords,
-                          int32_t* status, int max_elements, void* stream);
+                          int32_t* status, int max_elements, double* virial, void* stream);
 
 /* 4b. The same AEV kernels fed by an externally supplied HALF pair list (the reference's    */
 /*    Neighbors tuple; AEVComputer.compute_from_neighbors, aev/_computer.py:251-272 ->          */

@@ -490,12 +490,21 @@ def ani1x_model(seed: int = 1234, members: int = 8, neighborlist: str = "all_pai
 def compute(
     model: Model, species: Tensor, coords: Tensor,
     cell: tp.Optional[Tensor] = None, pbc: tp.Optional[Tensor] = None,
-    forces: bool = True, members: tp.Optional[tp.List[int]] = None,
+    forces: bool = True, members: tp.Optional[tp.List[int]] = None, stress: bool = False,
 ) -> tp.Dict[str, Tensor]:
     """arch.py:302-381 (+ grad.py:42-64 for forces).  ``species`` are element indices
     (0..S-1, -1 padding).  Returns aev, per-member atomic NN energies, NN energies (C,),
     total energies (C,) and forces (C, A, 3)."""
     coords = coords.detach().clone().requires_grad_(forces)
+    scaling = None
+    coords_in = coords
+    if stress:
+        # ase.py:110-121 ("scaling" stress): coordinates and cell are multiplied by a 3x3 matrix that
+        # starts as the identity; stress = dE/d(scaling) / volume (ase.py:170-173)
+        assert cell is not None and pbc is not None, "stress needs a periodic cell"
+        scaling = torch.eye(3, dtype=coords.dtype, requires_grad=True)
+        coords = coords @ scaling
+        cell = cell @ scaling
     nb = neighborlist(model.neighborlist, model.spec.rcr, species, coords, cell, pbc)
     aev = aev_from_neighbors(model.spec, species, nb)
     e_m = ensemble_atomic_energies(model.symbols, model.weights, species, aev, members)
@@ -508,7 +517,10 @@ def compute(
         "num_pairs": torch.tensor(nb.indices.shape[1]),
     }
     if forces:
-        out["forces"] = -torch.autograd.grad(e_nn.sum(), coords)[0]
+        out["forces"] = -torch.autograd.grad(e_nn.sum(), coords_in, retain_graph=stress)[0]
+    if stress:
+        volume = torch.det(cell.detach()).abs()
+        out["stress"] = (torch.autograd.grad(e_nn.sum(), scaling)[0] / volume).detach()   # Hartree / A^3
     return out
 
 

@@ -223,6 +223,27 @@ def test_ani_model_member_forces_qbc_and_neighbor_entry():
     assert e_at.shape == species.shape
 
 
+@pytest.mark.parametrize("name", ["water30_pbc_ani2x", "water999_pbc_ani2x"])
+def test_stress_from_the_force_kernel(name):
+    """ase.py:164-173: stress = virial / volume.  The GPU accumulates the f-dot-r virial in the force
+    kernel; the oracle differentiates the energy with respect to a strain of coordinates and cell."""
+    from torchani_b200 import models
+    rec = load_golden(name)
+    species, coords, cell, pbc = golden_inputs(rec, torch.float32)
+    om = oracle_model("2x", torch.float32)
+    model = models.from_weight_lists("2x", om.weights, device=DEV, periodic_table_index=True)
+    znum = torch.tensor([orc.ATOMIC_NUMBERS[s] for s in orc.SYMBOLS_2X])
+    e, f, stress = model.energies_forces_stress(znum[species].to(DEV), coords.to(DEV), cell.to(DEV), pbc.to(DEV))
+    # the strain derivative of the reference needs wrapped atoms (map_to_central uses a detached cell)
+    c64, cell64 = coords.double(), cell.double()
+    wrapped = c64 - torch.floor(c64 @ torch.linalg.inv(cell64)) @ cell64
+    ref = orc.compute(oracle_model("2x", torch.float64, "cell_list"), species, wrapped, cell64, pbc, stress=True)
+    assert_close("forces", f.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+    s_gpu, s_ref = stress.cpu().numpy(), ref["stress"].numpy()
+    assert np.abs(s_gpu - s_gpu.T).max() < 1e-7
+    assert_close("stress", s_gpu, s_ref, 1e-4, 1e-8)     # |stress| ~ 2e-4 Ha/A^3
+
+
 def test_host_calculator_matches_oracle_and_repeats():
     """calculator.HostCalculator (counterpart of ase.py:75-173): host positions in, host E/F out;
     repeated calls replay the captured CUDA graph and must keep giving the oracle's answer."""

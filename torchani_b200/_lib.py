@@ -20,6 +20,7 @@ ANI_MAX_SHFZ = 8
 ANI_MAX_MEMBERS = 16
 ANI_TILE_ROWS = 128
 ANI_MAX_ANG = 96
+ANI_VIRIAL_SLOTS = 64
 
 STATUS_NBR_OVERFLOW = 1
 STATUS_ANG_OVERFLOW = 2
@@ -75,7 +76,7 @@ _PROTOTYPES = {
     "ani_b200_build_cells": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ani_b200_species_layout": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
-    "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P]),
+    "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
     "ani_b200_pairs_to_rows": (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ani_b200_aev_forward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "ani_b200_aev_backward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),

@@ -123,7 +123,7 @@ class _AEVFunction(torch.autograd.Function):
         check(_lib.lib().ani_b200_aev_backward(C.byref(params), ptr(g.grid), ptr(g.spos), ptr(g.sorted_orig),
                                                None, g.n, 0, g.n, ptr(g.sorted_orig), ptr(grad_aev), consts.out_dim,
                                                ptr(ctx.nbr_cnt), ptr(ctx.nbr_list), computer.nbr_cap, ptr(grad),
-                                               ptr(g.status), 0, st), "aev_backward")
+                                               ptr(g.status), 0, None, st), "aev_backward")
         return grad.view(g.n_conf, g.n_per_conf, 3), None, None, None, None
 
 

@@ -880,14 +880,14 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
 // ---------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------
-template <int NA, int NZ>
+template <int NA, int NZ, bool VIRIAL = false>
 __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
     k_aev_backward(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                    const float4* __restrict__ spos, const int32_t* __restrict__ sorted_orig, int lo, int hi,
                    const int32_t* __restrict__ row_of, const float* __restrict__ gaev, int ldx,
                    const int32_t* __restrict__ nbr_cnt, const int32_t* __restrict__ nbr_list, const ExplicitNbrs ex,
                    const int32_t* __restrict__ species_mask, int cap, float* __restrict__ grad_coords,
-                   int32_t* __restrict__ status, size_t warp_bytes, int pair_cap) {
+                   int32_t* __restrict__ status, size_t warp_bytes, int pair_cap, double* __restrict__ virial) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1166,7 +1166,12 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
   __syncwarp();
 
   // ---- 5. scatter: neighbour j gets +dE_i/dr_j, the centre gets minus the sum
+  //         VIRIAL: W_ab += (dE_i/dDelta_in)_a (Delta_in)_b, the "f dot r" virial of ase.py:164-168
+  //         (dE/dDelta^T @ Delta over the pairs); ANI_VIRIAL_SLOTS partial sums keep the atomics apart
   float sx = 0.f, sy = 0.f, sz_ = 0.f;
+  float vir[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) vir[k] = 0.f;
   for (int n = lane; n < cnt; n += 32) {
     const float fx = s.fgrad[3 * n], fy = s.fgrad[3 * n + 1], fz = s.fgrad[3 * n + 2];
     const int oj = sorted_orig[s.nj[n]];
@@ -1176,6 +1181,19 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
     sx += fx;
     sy += fy;
     sz_ += fz;
+    if (VIRIAL) {
+      const float4 d = s.nd[n];
+      vir[0] = fmaf(fx, d.x, vir[0]); vir[1] = fmaf(fx, d.y, vir[1]); vir[2] = fmaf(fx, d.z, vir[2]);
+      vir[3] = fmaf(fy, d.x, vir[3]); vir[4] = fmaf(fy, d.y, vir[4]); vir[5] = fmaf(fy, d.z, vir[5]);
+      vir[6] = fmaf(fz, d.x, vir[6]); vir[7] = fmaf(fz, d.y, vir[7]); vir[8] = fmaf(fz, d.z, vir[8]);
+    }
+  }
+  if (VIRIAL && virial) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float v = warp_sum(vir[k]);
+      if (lane == 0) atomicAdd(&virial[(blockIdx.x % ANI_VIRIAL_SLOTS) * 9 + k], (double)v);
+    }
   }
   sx = warp_sum(sx);
   sy = warp_sum(sy);
@@ -1370,7 +1388,7 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
                                const int32_t* sorted_orig, int n, int lo, int hi, const int32_t* row_of,
                                const float* grad_aev, int ldx, const int32_t* nbr_cnt, const int32_t* nbr_list,
                                ExplicitNbrs ex, const int32_t* species_mask, int nbr_cap, float* grad_coords,
-                               int32_t* status, void* stream, int max_elements = 0) {
+                               int32_t* status, void* stream, int max_elements = 0, double* virial = nullptr) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!grid || !spos || !sorted_orig || !row_of || !grad_aev || !grad_coords || !status) return ANI_ERR_BAD_ARG;
@@ -1390,18 +1408,22 @@ static int launch_aev_backward(const ani_aev_params* params, const ani_grid* gri
   const int blocks = (hi - lo + AEV_WARPS - 1) / AEV_WARPS;
   cudaStream_t st = (cudaStream_t)stream;
   const float4* sp4 = reinterpret_cast<const float4*>(spos);
+  auto go = [&](auto k) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx, nbr_cnt,
+                                            nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb, pair_cap,
+                                            virial);
+  };
   if (params->n_shf_a == 8) {
-    auto k = k_aev_backward<8, 4>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb,
-                                            pair_cap);
+    if (virial)
+      go(k_aev_backward<8, 4, true>);
+    else
+      go(k_aev_backward<8, 4, false>);
   } else {
-    auto k = k_aev_backward<4, 8>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, sp4, sorted_orig, lo, hi, row_of, grad_aev, ldx,
-                                            nbr_cnt, nbr_list, ex, species_mask, nbr_cap, grad_coords, status, wb,
-                                            pair_cap);
+    if (virial)
+      go(k_aev_backward<4, 8, true>);
+    else
+      go(k_aev_backward<4, 8, false>);
   }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
@@ -1459,13 +1481,13 @@ extern "C" int ani_b200_aev_backward(const ani_aev_params* params, const ani_gri
                                      const int32_t* sorted_orig, const int32_t* species_mask, int n, int lo, int hi,
                                      const int32_t* row_of, const float* grad_aev, int ldx, const int32_t* nbr_cnt,
                                      const int32_t* nbr_list, int nbr_cap, float* grad_coords, int32_t* status,
-                                     int max_elements, void* stream) {
+                                     int max_elements, double* virial, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!nbr_cnt || !nbr_list) return ANI_ERR_BAD_ARG;
   return launch_aev_backward(params, grid, spos, sorted_orig, n, lo, hi, row_of, grad_aev, ldx, nbr_cnt, nbr_list,
                              ExplicitNbrs{nullptr, nullptr, nullptr}, species_mask, nbr_cap, grad_coords, status,
-                             stream, max_elements);
+                             stream, max_elements, virial);
 }
 
 extern "C" int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, const float* diff_vectors,

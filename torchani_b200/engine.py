@@ -352,6 +352,8 @@ class Workspace:
         self.ref_pos = torch.zeros(n, 4, **f32)
         self.ref_shift = torch.zeros(n, 4, **f32)
         self.moved = torch.zeros(1, **i32)
+        # partial sums of the virial W_ab = sum_pairs (dE/dDelta)_a Delta_b (ani_b200_aev_backward)
+        self.virial = torch.zeros(_lib.ANI_VIRIAL_SLOTS, 9, dtype=torch.float64, device=device)
 
 
 class StepResult(tp.NamedTuple):
@@ -359,6 +361,7 @@ class StepResult(tp.NamedTuple):
     atomic_energies: Tensor   # (C, A) float32: NN atomic energies (ensemble mean), 0 for padding
     member_atomic: Tensor     # (M, C, A) float32 per-member NN atomic energies
     grad: tp.Optional[Tensor]  # (C, A, 3) float32 dE/dcoords (forces = -grad) or None
+    virial: tp.Optional[Tensor] = None  # (3, 3) float64 sum_pairs (dE/dDelta)_a Delta_b (stress = virial / volume)
 
 
 class Engine:
@@ -426,7 +429,7 @@ class Engine:
 
     # -- one step --------------------------------------------------------------------------
     def step(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None, pbc: bool = False,
-             want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1)) -> StepResult:
+             want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1), want_virial: bool = False) -> StepResult:
         """species (C, A) int (element indices, -1 padding), coords (C, A, 3) on this device.
         ``shard = (rank, world)``: only atoms whose bucket-sorted position falls into this
         rank's slice are evaluated; gradients/energies are partial sums to be all-reduced.
@@ -449,10 +452,10 @@ class Engine:
         ws.coords.copy_(coords.reshape(-1, 3))
         if pbc:
             ws.cell.copy_(cell.reshape(-1))
-        return self.run(ws, bool(pbc), want_grad, shard)
+        return self.run(ws, bool(pbc), want_grad, shard, want_virial=want_virial)
 
     def run(self, ws: Workspace, pbc: bool, want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1),
-            reuse: bool = False) -> StepResult:
+            reuse: bool = False, want_virial: bool = False) -> StepResult:
         """One step on inputs that are ALREADY in the workspace buffers (``ws.species_i32``,
         ``ws.coords``, ``ws.cell``) -- the entry point of host-driven loops that copy straight into
         them (calculator.HostCalculator).  The results alias workspace buffers."""
@@ -460,11 +463,14 @@ class Engine:
         rank, world = shard
         lo = (n * rank) // world
         hi = (n * (rank + 1)) // world
-        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.version, bool(reuse), self.skin)
+        if want_virial and (not want_grad or reuse or n_conf != 1):
+            raise ValueError("the virial comes out of the force pass of a single system with a freshly built grid")
+        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.version, bool(reuse), self.skin,
+               bool(want_virial))
         if reuse and not self.skin > 0:
             raise ValueError("reuse=True needs Engine.skin > 0 and a previous step that built the grid")
         if not self.cuda_graph or self.profile:
-            self._launch(ws, bool(pbc), want_grad, lo, hi, reuse)
+            self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
         else:
             graph = self._graphs.get(key)
             if graph is not None:
@@ -472,12 +478,12 @@ class Engine:
             elif self._graph_seen.get(key, 0) < self.graph_after:
                 # the first few uses of a shape run eagerly (one-off shapes never pay for a capture)
                 self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
-                self._launch(ws, bool(pbc), want_grad, lo, hi, reuse)
+                self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
             else:
                 self.note_composition(ws)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
-                    self._launch(ws, bool(pbc), want_grad, lo, hi, reuse)
+                    self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
                 self._graphs[key] = graph
                 graph.replay()
         # kernels launched by this library in one step (memsets excluded):
@@ -485,10 +491,12 @@ class Engine:
         # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
         self.launches_per_step = 5 + (0 if (pbc or n_conf > 1) else 1) + 1 + 3 + (5 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
+        virial = ws.virial.sum(0).view(3, 3) if want_virial else None
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
-                          ws.member_atomic.view(-1, n_conf, n_per_conf), grad)
+                          ws.member_atomic.view(-1, n_conf, n_per_conf), grad, virial)
 
-    def _launch(self, ws: Workspace, pbc: bool, want_grad: bool, lo: int, hi: int, reuse: bool = False) -> None:
+    def _launch(self, ws: Workspace, pbc: bool, want_grad: bool, lo: int, hi: int, reuse: bool = False,
+                want_virial: bool = False) -> None:
         """Enqueue the kernels of one step on the current stream (graph-capturable: no allocation,
         no synchronisation, only this library's launches and two memsets)."""
         L = self.lib
@@ -512,7 +520,8 @@ class Engine:
                 ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges),
                 lo, hi, c.num_species, ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
                 ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
-                ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0, None, 0,
+                ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0,
+                ptr(ws.virial) if want_virial else None, ws.virial.numel() if want_virial else 0,
                 ptr(ws.scratch), ptr(ws.status), st))
             if self.skin > 0:
                 check(L.ani_b200_verlet_positions(
@@ -570,7 +579,7 @@ class Engine:
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
                 ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
-                ptr(ws.grad), ptr(ws.status), ws.max_elements, st))
+                ptr(ws.grad), ptr(ws.status), ws.max_elements, ptr(ws.virial) if want_virial else None, st))
         if not split:
             self._timed("reduce_energies", lambda: reduce_on(st))
         else:

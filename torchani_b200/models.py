@@ -300,6 +300,19 @@ class ANI(torch.nn.Module):
         res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True)
         return res.energies.clone(), -res.grad
 
+    def energies_forces_stress(self, species: Tensor, coords: Tensor, cell: Tensor,
+                               pbc: tp.Optional[Tensor] = None) -> tp.Tuple[Tensor, Tensor, Tensor]:
+        """(energies f64 (1,), forces f32 (1, A, 3), stress f64 (3, 3) in Hartree/A^3) of one periodic
+        system.  The stress is the "f dot r" virial of ase.py:164-168 -- sum over the pairs of
+        (dE/dDelta)_a Delta_b, accumulated by the force kernel -- divided by the cell volume; it equals
+        the strain derivative dE/d(scaling)/V of ase.py:170-173 and, unlike that one, does not need the
+        atoms to be wrapped into the cell."""
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        eng = self.engine(coords.device)
+        res = eng.step(elem_idxs, coords.detach(), cell, True, want_grad=True, want_virial=True)
+        volume = torch.det(cell.detach().double()).abs()
+        return res.energies.clone(), -res.grad, res.virial / volume
+
     # -- state dicts of the reference (arch.py:278-290) ------------------------------------
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs) -> None:
         for old in list(state_dict.keys()):
