@@ -47,6 +47,8 @@ VARIANTS = {
     "bwd5": ["-DANI_AEV_BWD_MIN_CTAS=5"],
     "bwd6": ["-DANI_AEV_BWD_MIN_CTAS=6"],
     "fwd7": ["-DANI_AEV_FWD_MIN_CTAS=7", "-DANI_AEV_CAND_CAP=640"],
+    "fwd8w": ["-DANI_AEV_FWD_WARPS=8", "-DANI_AEV_FWD_MIN_CTAS=3"],
+    "fwd6w": ["-DANI_AEV_FWD_WARPS=6", "-DANI_AEV_FWD_MIN_CTAS=4"],
 }
 
 

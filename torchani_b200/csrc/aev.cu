@@ -483,6 +483,10 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
 #define ANI_AEV_FWD_MIN_CTAS 6
 #endif
 constexpr int CAND_CAP = ANI_AEV_CAND_CAP;
+#ifndef ANI_AEV_FWD_WARPS
+#define ANI_AEV_FWD_WARPS 4
+#endif
+constexpr int AEV_FWD_WARPS = ANI_AEV_FWD_WARPS;  // atoms (= warps) per CTA of the staged forward kernel
 constexpr int NRANGE = 27;
 constexpr int T2O_CAP = 1024;
 
@@ -494,12 +498,12 @@ struct CtaStage {
   int cnt[ANI_MAX_SPECIES][NRANGE];            // candidates per (species, range)
   int off[ANI_MAX_SPECIES * NRANGE + 1];       // exclusive prefix of cnt in species-major order
   int adj[ANI_MAX_SPECIES][NRANGE];            // off[s][o] - (candidates of lower species in range o)
-  int wbin[AEV_WARPS];
+  int wbin[AEV_FWD_WARPS];
   unsigned char t2o[T2O_CAP];                  // range of the t-th candidate (range-major numbering)
 };
 
 template <int NA, int NZ>
-__global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
+__global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     k_aev_forward_cta(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                       const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
                       const int32_t* __restrict__ sbin, const float4* __restrict__ ranges,
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ani_grid g = *grid;
   hi = min(hi, g.n_real);
-  const int i = lo + blockIdx.x * AEV_WARPS + warp;
+  const int i = lo + blockIdx.x * AEV_FWD_WARPS + warp;
   const bool has = i < hi;  // warps without an atom still help with the staging
   const WarpSmem s = carve(smem_raw + warp * warp_bytes, cap, false);
   const int S = P.num_species;
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
   while (true) {
     int cur = 0x7fffffff;
 #pragma unroll
-    for (int w = 0; w < AEV_WARPS; ++w) {
+    for (int w = 0; w < AEV_FWD_WARPS; ++w) {
       const int b = C.wbin[w];
       if (b > prev && b < cur) cur = b;
     }
@@ -580,7 +584,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
       C.r_shift[tid] = sh;
       C.r_off[tid + 1] = max(rhi - rlo, 0);  // length for now, prefix below
     }
-    for (int q = tid; q < ANI_MAX_SPECIES * NRANGE; q += AEV_WARPS * 32) (&C.cnt[0][0])[q] = 0;
+    for (int q = tid; q < ANI_MAX_SPECIES * NRANGE; q += AEV_FWD_WARPS * 32) (&C.cnt[0][0])[q] = 0;
     __syncthreads();
     if (warp == 0) {
       // inclusive scan of the 27 lengths (lane o holds range o)
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     };
     // (b) candidates per (species, range); the range of every candidate is remembered for (c)
     // (four candidates per thread and round: the global loads are issued together)
-    constexpr int NT = AEV_WARPS * 32, BATCH = 4;
+    constexpr int NT = AEV_FWD_WARPS * 32, BATCH = 4;
     for (int t0 = tid; t0 < T; t0 += NT * BATCH) {
       int oo[BATCH], spv[BATCH];
 #pragma unroll
@@ -1355,16 +1359,18 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
     return e && atoi(e) != 0;
   }();
   if (!ex.start && !legacy) {
+    const size_t smem_f = wb * AEV_FWD_WARPS;
+    const int blocks_f = (hi - lo + AEV_FWD_WARPS - 1) / AEV_FWD_WARPS;
     if (params->n_shf_a == 8) {
       auto k = k_aev_forward_cta<8, 4>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
-                                              aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+      k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
+                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
     } else {
       auto k = k_aev_forward_cta<4, 8>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<blocks, AEV_WARPS * 32, smem, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi, row_of,
-                                              aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+      k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
+                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
     }
     ANI_CUDA_CHECK_LAUNCH();
     return ANI_OK;
