@@ -10,7 +10,7 @@ import pytest
 import torch
 
 import oracle.ani_oracle as orc
-from helpers import ROOT, oracle_model
+from helpers import ROOT, golden_inputs, load_golden, oracle_model
 
 
 def test_constants_match_oracle_spec():
@@ -220,3 +220,66 @@ def test_synthetic_generators_agree_with_the_oracle_copies():
     wa = synthetic.make_weights(("H", "O"), synthetic.DIMS_2X, 1008, 2, seed=9)
     wb = orc.make_weights(("H", "O"), orc.DIMS_2X, 1008, 2, seed=9)
     assert torch.equal(wa[1]["O"][2][0], wb[1]["O"][2][0])
+
+
+def test_operand_format_and_weight_scales():
+    """The GEMM operand format of the loaded build and the per-tensor power-of-two weight scales."""
+    from torchani_b200 import _lib
+    from torchani_b200.engine import weight_scale
+    fmt = _lib.operand_format()
+    assert fmt.parts in (2, 3)
+    if fmt.parts == 2:
+        assert fmt.value_scale == 64.0 and fmt.grad_scale == 4096.0
+        assert weight_scale([torch.full((4, 4), 0.03)]) == 4096.0            # capped at 2^12
+        assert weight_scale([torch.full((4, 4), 100.0)]) == 128.0            # 100 * 128 < 2^14 <= 100 * 256
+        assert weight_scale([torch.zeros(2, 2)]) == 4096.0
+        with pytest.raises(ValueError):
+            weight_scale([torch.tensor([[float("nan")]])])
+    else:
+        assert fmt.value_scale == 1.0 and weight_scale([torch.ones(2, 2)]) == 1.0
+
+
+def test_neighborlist_table_and_verlet_arguments():
+    from torchani_b200 import neighbors
+    assert isinstance(neighbors._parse_neighborlist("verlet_cell_list"), neighbors.VerletCellList)
+    assert isinstance(neighbors._parse_neighborlist("adaptive"), neighbors.AdaptiveList)
+    with pytest.raises(ValueError):
+        neighbors.VerletCellList(skin=-1.0)
+    with pytest.raises(ValueError):
+        neighbors._parse_neighborlist("octree")
+
+
+def test_oracle_stress_is_the_strain_derivative():
+    """oracle stress (ase.py:110-121,170-173, 'scaling'): symmetric for wrapped atoms and equal to the
+    finite-difference strain derivative of the energy."""
+    rec = load_golden("water30_pbc_ani2x")
+    sp, co, cell, pbc = golden_inputs(rec, torch.float64)
+    co = co - torch.floor(co @ torch.linalg.inv(cell)) @ cell
+    m = oracle_model("2x", torch.float64, "cell_list", members=2)
+    out = orc.compute(m, sp, co, cell, pbc, stress=True)
+    s = out["stress"]
+    assert float((s - s.T).abs().max()) < 1e-12
+    eps = 1e-5
+    sc = torch.eye(3, dtype=torch.float64)
+    sc[0, 1] += eps
+    ep = float(orc.compute(m, sp, co @ sc, cell @ sc, pbc, forces=False)["energy_nn"][0])
+    sc[0, 1] -= 2 * eps
+    em = float(orc.compute(m, sp, co @ sc, cell @ sc, pbc, forces=False)["energy_nn"][0])
+    assert abs((ep - em) / (2 * eps) / float(torch.det(cell)) - float(s[0, 1])) < 1e-9
+
+
+def test_bench_reference_arm_line(tmp_path):
+    """bench.py --impl reference: one JSON line with the contract's keys (tiny box so that it runs in seconds)."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--molecules", "20",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
