@@ -21,7 +21,11 @@
  *   ani_b200_half_neighbor_*    neighbors.py:366-415 (cell_list), :187-212 (all_pairs) -> Neighbors
  *   ani_b200_mlp_forward_backward  nn/_containers.py:377-421,608-651, nn/_core.py:146-167,
  *                               nn/_infer.py:61-216 (BmmEnsemble), csrc/mnp.cpp:63-236 (mnp::run)
+ *   ani_b200_mlp_forward / _zero_live_blocks / _mlp_backward   the same, as separate halves
  *   ani_b200_reduce_energies    nn/_containers.py:418-421,633-636, sae.py:54-64
+ *   ani_b200_verlet_positions   neighbors.py:759-884 (VerletCellList: reuse of a list built with a skin)
+ *   ani_b200_aev_backward(..., virial, ...)   ase.py:164-168 (the "f dot r" virial of the stress)
+ *   ani_b200_operand_format     (no counterpart: format of the tensor-core GEMM operands of this build)
  */
 #ifndef ANI_B200_H
 #define ANI_B200_H

@@ -1,16 +1,21 @@
 // Fused neighbour search + AEV forward, and AEV backward (forces), one warp per central atom.
 //
 // Forward (replaces neighbors.py:64-113,968-1002 + aev/_computer.py:274-350; the reference's
-// GPU path is csrc/aev.cu K1-K9): the warp walks the 27 buckets around its atom, compacts the
-// neighbours within Rcr into shared memory with ballots, accumulates the radial block with a
-// (shift x neighbour-parity) lane layout, counting-sorts the neighbours within Rca by species
-// and then, for each species pair, every lane evaluates whole triples (32 angular features in
-// registers) followed by one warp transpose-reduce.  No atomics anywhere in the forward pass.
+// GPU path is csrc/aev.cu K1-K9).  Two kernels:
+//   * k_aev_forward_cta (the bucket-grid path): the AEV_FWD_WARPS consecutive atoms of a CTA share the
+//     27-bucket neighbourhood, staged once per CTA in shared memory in species-major order; a warp
+//     compacts its neighbours with one ballot per 32 candidates and gets the neighbour list and the
+//     angular sub-list grouped by species for free; radial sums in registers, per species pair
+//     every lane evaluates whole triples (32 angular features in registers) + one warp
+//     transpose-reduce.  No atomics in the forward pass.
+//   * k_aev_forward (explicit neighbour rows handed in by the caller, and ANI_B200_AEV_LEGACY=1): every
+//     warp walks its own candidate ranges in global memory and counting-sorts the neighbours by species.
 //
-// Backward (csrc/aev.cu K10/K11): recomputes the geometry from the stored neighbour words and
-// evaluates dE/dr_j for every ORDERED pair (j, k) so that each neighbour's gradient is owned by
-// a group of lanes (register accumulation, shuffle reduce, plain shared-memory add); only the
-// final per-neighbour vectors go to global memory (fire-and-forget float reductions).
+// Backward (csrc/aev.cu K10/K11): recomputes the geometry from the stored neighbour words, copies the
+// live blocks of the upstream gradient row with cp.async into a compact per-composition table, and
+// evaluates dE/dr_j over UNORDERED pairs by rotation (row j handles (j, j + t) once and hands the
+// partner's share over with one shuffle); only the final per-neighbour vectors go to global memory
+// (fire-and-forget float reductions), optionally with the f.r virial (stress) of ase.py:164-168.
 #include <stdlib.h>
 
 #include "common.cuh"
