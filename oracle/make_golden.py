@@ -209,5 +209,48 @@ def main():
     assert np.abs(loop - vec).max() < 1e-12
 
 
+def main_stress():
+    """Stress fixture: the reference's "f dot r" stress (ase.py:118-131,164-168) computed with the real
+    reference modules on its periodic test structures, and the pin of the oracle's strain-derivative
+    stress (ani_oracle.compute(..., stress=True), ase.py:110-121,170-173) against it.
+    Usage:  python oracle/make_golden.py --stress   (writes tests/golden/stress_pbc_ani2x.npz)"""
+    torchani = import_reference()
+    from torchani.neighbors import Neighbors
+    import oracle.ani_oracle as orc
+
+    sym2 = {s: i for i, s in enumerate(orc.SYMBOLS_2X)}
+    pbc3 = torch.tensor([True, True, True])
+    w2 = orc.make_weights(orc.SYMBOLS_2X, orc.DIMS_2X, 1008, 8, 1234, torch.float64)
+    aevc, ens = build_reference(torchani, "2x", w2, "cell_list", orc.SYMBOLS_2X, orc.DIMS_2X)
+    sae = {s_: orc.GSAES_WB97X_631GD[s_] for s_ in orc.SYMBOLS_2X}
+    model = orc.Model(orc.aev_spec_2x(), orc.SYMBOLS_2X, w2, sae, "cell_list")
+    rec = {}
+    for fname, name in [("water-0.8nm.xyz", "water30_pbc_ani2x"), ("benzene.xyz", "benzene_pbc_ani2x"),
+                        ("tight_cell.xyz", "tightcell_pbc_ani2x")]:
+        s, x, cell = read_xyz(os.path.join(RES, fname))
+        idx = torch.tensor([[sym2[a] for a in s]])
+        coords = torch.tensor(x).unsqueeze(0).double()
+        cell_t = torch.tensor(cell).double()
+        nb = aevc.neighborlist(aevc.radial.cutoff, idx, coords, cell_t, pbc3)
+        diff = nb.diff_vectors.detach().clone().requires_grad_(True)
+        nb2 = Neighbors(nb.indices, diff.norm(2, -1), diff)
+        aev = aevc.compute_from_neighbors(idx, coords, nb2)
+        energy = ens(idx, aev).sum()
+        (dEdR,) = torch.autograd.grad(energy, diff)
+        volume = torch.det(cell_t).abs()
+        stress_ref = (dEdR.transpose(0, 1) @ diff.detach() / volume).detach()     # ase.py:164-168
+        # oracle: strain derivative on the atoms wrapped into the cell (map_to_central detaches the cell)
+        wrapped = coords - torch.floor(coords @ torch.linalg.inv(cell_t)) @ cell_t
+        mine = orc.compute(model, idx, wrapped, cell_t, pbc3, stress=True)["stress"]
+        err = float((mine - stress_ref).abs().max())
+        print(f"{name:24s} |stress|max {float(stress_ref.abs().max()):.3e}  oracle-vs-reference max-abs {err:.2e}")
+        assert err < 1e-12, (name, err)
+        rec[name] = stress_ref.numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "stress_pbc_ani2x.npz"), **rec)
+
+
 if __name__ == "__main__":
-    main()
+    if "--stress" in sys.argv:
+        main_stress()
+    else:
+        main()

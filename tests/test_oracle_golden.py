@@ -1,11 +1,13 @@
 """The CPU oracle against the committed golden vectors (generated from the REAL reference by
 oracle/make_golden.py).  Runs everywhere, no GPU, no /root/reference."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import oracle.ani_oracle as orc
-from helpers import GOLDEN_CASES, golden_inputs, load_golden, oracle_model
+from helpers import GOLD, GOLDEN_CASES, golden_inputs, load_golden, oracle_model
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -53,3 +55,16 @@ def test_oracle_fp32_close_to_fp64():
     out = orc.compute(oracle_model("2x", torch.float32, "cell_list"), species, coords, cell, pbc)
     assert np.abs(out["forces"].numpy() - rec["forces"]).max() < 1e-5
     assert np.abs(out["aev"].numpy() - rec["aev"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["water30_pbc_ani2x", "benzene_pbc_ani2x", "tightcell_pbc_ani2x"])
+def test_oracle_stress_matches_reference_fdotr(name):
+    """tests/golden/stress_pbc_ani2x.npz holds the reference's own "f dot r" stress (ase.py:164-168, computed by
+    oracle/make_golden.py --stress with the real reference modules); the oracle's strain-derivative stress must
+    reproduce it."""
+    fix = np.load(os.path.join(GOLD, "stress_pbc_ani2x.npz"))
+    rec = load_golden(name)
+    sp, co, cell, pbc = golden_inputs(rec, torch.float64)
+    co = co - torch.floor(co @ torch.linalg.inv(cell)) @ cell
+    out = orc.compute(oracle_model("2x", torch.float64, "cell_list"), sp, co, cell, pbc, stress=True)
+    assert float(np.abs(out["stress"].numpy() - fix[name]).max()) < 1e-12
