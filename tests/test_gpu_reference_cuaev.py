@@ -107,6 +107,8 @@ def test_reference_gpu_path_pieces_beside_ours():
     """The other two stages of the reference's GPU path on the same box and inputs: its C++/ATen cell list
     (csrc/cell_list.cpp, built into oracle/_ref) and the BmmEnsemble network path (restated with torch.baddbmm in
     oracle/gpu_baseline.py).  Checks that they agree with ours and records their times."""
+    if os.environ.get("ANI_B200_REF_PATH_TEST", "0") == "0":
+        pytest.skip("measurement of the reference's GPU path pieces: set ANI_B200_REF_PATH_TEST=1 to run it")
     from torchani_b200 import models, neighbors, synthetic
     from torchani_b200.engine import constants_2x
     import oracle.gpu_baseline as gb
