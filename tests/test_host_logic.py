@@ -283,3 +283,56 @@ def test_bench_reference_arm_line(tmp_path):
               "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_species_major_staging_arithmetic():
+    """The index arithmetic of k_aev_forward_cta's staging (csrc/aev.cu, steps (b)-(d)) restated in numpy:
+    from the 27 species-sorted candidate ranges, counts per (species, range) -> exclusive prefix in species-major
+    order -> adj[s][o] = off[s][o] - (candidates of lower species in range o) -> place = adj + offset in range.
+    The places must be a permutation that groups the candidates by species and keeps range-major order inside a
+    species; the windowed scan must visit every species segment exactly once and report the right segment ends."""
+    rng = np.random.default_rng(11)
+    S, R, CAP = 7, 27, 64          # a small window capacity forces several staging windows
+    for trial in range(20):
+        lens = rng.integers(0, 9, size=R)
+        lens[rng.integers(0, R, size=5)] = 0
+        species = [np.sort(rng.integers(0, S, size=n)) for n in lens]       # every range is species-sorted
+        r_off = np.concatenate([[0], np.cumsum(lens)])
+        T = int(r_off[-1])
+        cnt = np.zeros((S, R), dtype=int)
+        for o in range(R):
+            for sp in species[o]:
+                cnt[sp, o] += 1
+        off = np.concatenate([[0], np.cumsum(cnt.reshape(-1))])            # q = s * R + o
+        adj = np.zeros((S, R), dtype=int)
+        for o in range(R):
+            lower = 0
+            for s in range(S):
+                adj[s, o] = off[s * R + o] - lower
+                lower += cnt[s, o]
+        dest, sp_of, key = np.zeros(T, dtype=int), np.zeros(T, dtype=int), []
+        for t in range(T):
+            o = int(np.searchsorted(r_off, t, side="right") - 1)
+            while lens[o] == 0:                                             # (the kernel's search never lands here)
+                o += 1
+            k = t - r_off[o]
+            sp = species[o][k]
+            dest[t], sp_of[t] = adj[sp, o] + k, sp
+            key.append((sp, o, k))
+        assert sorted(dest.tolist()) == list(range(T))                      # a permutation
+        order = np.argsort(dest)
+        assert [key[i] for i in order] == sorted(key)                       # species-major, then range, then offset
+        # windows of CAP places: the segment of species s inside window [F0, F0 + CAP) is [max(F0, a), min(F0 + CAP, b))
+        seen = np.zeros(T, dtype=int)
+        seg_end = np.zeros(S + 1, dtype=int)
+        count = 0
+        for F0 in range(0, max(T, 1), CAP):
+            for s in range(S):
+                a, b = max(F0, off[s * R]), min(F0 + CAP, off[(s + 1) * R])
+                for p in range(a, b):
+                    seen[p] += 1
+                    count += 1
+                if off[(s + 1) * R] >= F0:                                  # the rule that fixed the benzene case
+                    seg_end[s + 1] = count
+        assert (seen == 1).all()
+        assert seg_end[1:].tolist() == [int(off[(s + 1) * R]) for s in range(S)]
