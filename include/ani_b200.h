@@ -297,6 +297,16 @@ typedef struct ani_mlp_model {
   ani_mlp_species sp[ANI_MAX_SPECIES];
 } ani_mlp_model;
 
+/* 6a. Model-pack time: plain fp32 weights -> the tiled B operand above (one launch per operand; `batch`   */
+/*     operands of the same shape, e.g. the members of an ensemble, src/dst `*_batch_stride` elements/bytes     */
+/*     apart).  src is [n][ld_src] (B[n][k] = src[n][k]) or, with transpose != 0, [k][ld_src] (B[n][k] =       */
+/*     src[k][n]: the backward operands are the transposed weights); n % 32 == 0; K is zero-padded to a        */
+/*     multiple of 32; every value is multiplied by the power-of-two `scale` first.                             */
+/*     dst: batch * n * ceil32(k) * 2 * P bytes.  Replaces BmmLinear.__init__ (nn/_infer.py:171-203), the       */
+/*     reference's own inference-time re-layout of the weights.                                                 */
+int ani_b200_pack_b_operand(const float* src, int n, int k, int ld_src, int transpose, float scale, int batch,
+                            long long src_batch_stride, void* dst, long long dst_batch_stride, void* stream);
+
 /*    x            tiled operand, in: AEVs (ani_b200_aev_forward layout 1), 2*P*rows_cap*ldx bytes */
 /*    dx           f32[rows_cap][ldx] plain rows, out: dE/dAEV (may be NULL if !want_backward)  */
 /*    row_atom / layout_info: outputs of ani_b200_species_layout                                */

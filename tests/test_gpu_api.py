@@ -341,3 +341,56 @@ def test_compute_from_neighbors_split_api(name):
     nb_big = nl(6.0, species.to(DEV), coords.to(DEV), cell_d, pbc_d)
     aev2 = aevc.compute_from_neighbors(species.to(DEV), coords.to(DEV), discard_outside_cutoff(nb_big, 5.1))
     assert float((aev2 - aev.detach()).abs().max()) < 2e-5
+
+
+def test_weight_packing_kernel_matches_the_python_tiler():
+    """ani_b200_pack_b_operand (the library's own model-pack kernel) against engine.tile_b_operand (the python
+    statement of the tiled B operand layout, itself checked on the CPU in tests/test_host_logic.py): every operand
+    of every species byte for byte, incl. hidden widths that need zero padding (ANI-1x carbon: 144, 112)."""
+    from torchani_b200 import _lib
+    from torchani_b200.engine import PackedNetworks, tile_b_operand
+    dev = torch.device("cuda", 0)
+    P2 = 2 * _lib.operand_format().parts
+    for kind, in_dim, members in (("2x", 1008, 3), ("1x", 384, 2)):
+        m = oracle_model(kind, members=members)
+        w = [[wm[s] for s in m.symbols] for wm in m.weights]
+        nets = PackedNetworks(w, in_dim, dev)
+        src, dst = nets._keep
+        torch.cuda.synchronize()
+        M, ldx = nets.num_members, nets.ldx
+        pad = lambda v: (v + 31) // 32 * 32  # noqa: E731
+        for s, sym in enumerate(m.symbols):
+            q, sp = nets._plan[s], nets.model.sp[s]
+            h1, h2, h3 = nets.dims[s]
+            p1, p2, p3 = pad(h1), pad(h2), pad(h3)
+            assert (sp.h1, sp.h2, sp.h3) == (p1, p2, p3)
+            Wp = []
+            for k, (po, pi) in enumerate(((p1, ldx), (p2, p1), (p3, p2))):
+                layer = []
+                for mem in range(M):
+                    z = torch.zeros(po, pi)
+                    wt = m.weights[mem][sym][k][0].float()
+                    z[:wt.shape[0], :wt.shape[1]] = wt
+                    layer.append(z)
+                Wp.append(layer)
+            sc = list(sp.w_scale)
+            w1n = torch.cat(Wp[0], 0)
+            expect = {
+                "d_f1": tile_b_operand(w1n, sc[0]),
+                "d_f2": torch.cat([tile_b_operand(x, sc[1]) for x in Wp[1]]),
+                "d_f3": torch.cat([tile_b_operand(x, sc[2]) for x in Wp[2]]),
+                "d_b3": torch.cat([tile_b_operand(x.t().contiguous(), sc[2]) for x in Wp[2]]),
+                "d_b2": torch.cat([tile_b_operand(x.t().contiguous(), sc[1]) for x in Wp[1]]),
+                "d_b1": tile_b_operand(w1n.t().contiguous(), sc[0]),
+            }
+            for name, ref in expect.items():
+                ref_bytes = ref.view(torch.uint8).reshape(-1)
+                got = dst[q[name]: q[name] + ref_bytes.numel()].cpu()
+                assert torch.equal(got, ref_bytes), (kind, sym, name)
+            b4 = src[q["s_b4"]: q["s_b4"] + M].cpu()
+            assert torch.equal(b4, torch.stack([m.weights[mem][sym][3][1].float().view(()) for mem in range(M)]))
+        assert P2 in (4, 6)
+        nets.set_active_members([0, 1])
+        assert list(nets.model.member_scale)[:2] == [0.5, 0.5]
+        with pytest.raises(IndexError):
+            nets.set_active_members([7])

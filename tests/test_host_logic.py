@@ -71,8 +71,7 @@ def _untile(t, n, k):
 
 def test_weight_packing_layout():
     from torchani_b200._lib import operand_format
-    from torchani_b200.engine import (PackedNetworks, tile_a_operand, tile_b_operand, untile_a_operand,
-                                      weight_scale)
+    from torchani_b200.engine import tile_a_operand, tile_b_operand, untile_a_operand, weight_scale
     P = operand_format().parts
     # the tiled / split / swizzled B operand round-trips and the pieces add up to scale * x
     b = torch.randn(288, 40, generator=torch.Generator().manual_seed(0))
@@ -92,43 +91,8 @@ def test_weight_packing_layout():
     x = torch.randn(256, 96, generator=torch.Generator().manual_seed(1))
     back = untile_a_operand(tile_a_operand(x), 256, 96)
     assert float((back - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -22
-    m = oracle_model("2x", members=3)
-    w = [[wm[s] for s in m.symbols] for wm in m.weights]
-    nets = PackedNetworks(w, 1008, torch.device("cpu"))
-    assert nets.ldx == 1024 and nets.num_members == 3 and nets.dims[0] == (256, 192, 160)
-    names = ("b1", "b2", "b3", "w4", "b4", "t_f1", "t_f2", "t_f3", "t_b3", "t_b2", "t_b1")
-    sp0 = dict(zip(names, nets._keep[:11]))
-
-    E = 32 * P   # 16-bit elements per row of a K-block (all pieces)
-
-    def close(parts, ref, sc):
-        tot = sum(q.astype(np.float64) for q in parts) / sc
-        tol = np.abs(ref) * (2.0 ** -24 if P == 3 else 2.0 ** -22) + (0.0 if P == 3 else 2.0 ** -25 / sc)
-        return bool((np.abs(tot - ref) <= tol).all())
-
-    wsc = list(nets.model.sp[0].w_scale)
-    assert all(v == 1.0 for v in wsc[:3]) if P == 3 else all(v >= 1.0 and np.log2(v) % 1 == 0 for v in wsc[:3])
-    # layer 1: members stacked along N, K padded to ldx with zeros
-    parts = _untile(sp0["t_f1"][: 256 * 32 * E], 256, 1024)          # first n tile = member 0
-    assert close([q[:, :1008] for q in parts], m.weights[0]["H"][0][0].numpy(), wsc[0])
-    assert float(np.abs(parts[0][:, 1008:]).max()) == 0.0
-    # per-member layer 2 (forward: W2 [h2][h1]; backward: W2^T [h1][h2])
-    per = 192 * 8 * E
-    assert close(_untile(sp0["t_f2"][2 * per: 3 * per], 192, 256), m.weights[2]["H"][1][0].numpy(), wsc[1])
-    per = 256 * 6 * E
-    assert close(_untile(sp0["t_b2"][per: 2 * per], 256, 192), m.weights[1]["H"][1][0].t().numpy(), wsc[1])
-    assert torch.equal(sp0["w4"][2], m.weights[2]["H"][3][0][0])
-    assert sp0["t_b1"].numel() == 1024 * (3 * 256 // 32) * E
-    nets.set_active_members([0, 2])
-    assert list(nets.model.member_scale)[:3] == [0.5, 0.0, 0.5]
-    with pytest.raises(IndexError):
-        nets.set_active_members([5])
-    # hidden widths that are not multiples of 32 (ANI-1x carbon: 144, 112, 96) are zero-padded
-    m1 = oracle_model("1x", members=2)
-    nets1 = PackedNetworks([[wm[s] for s in m1.symbols] for wm in m1.weights], 384, torch.device("cpu"))
-    c = list(m1.symbols).index("C")
-    assert nets1.dims[c] == (144, 112, 96)
-    assert (nets1.model.sp[c].h1, nets1.model.sp[c].h2, nets1.model.sp[c].h3) == (160, 128, 96)
+    # (the device-side packer ani_b200_pack_b_operand is compared with this tiler byte for byte in
+    # tests/test_gpu_api.py::test_weight_packing_kernel_matches_the_python_tiler)
 
 
 def test_model_tree_and_reference_state_dict_keys():

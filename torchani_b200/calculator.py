@@ -61,6 +61,7 @@ class HostCalculator:
         self.h_grad = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
         self.h_energy = torch.empty(1, dtype=torch.float64).pin_memory()
         self.h_moved = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._have_grid = False       # a grid built with the skin exists and may be reused
         self.rebuilds = 0             # steps that built the grid
         self.redone = 0               # reuse steps that had to be recomputed (an atom left its skin/2 sphere)
@@ -69,12 +70,12 @@ class HostCalculator:
         if cell is not None:
             self.set_cell(cell)
         self.h2d_bytes = self.h_coords.numel() * 4 + (36 if pbc else 0)
-        self.d2h_bytes = self.h_grad.numel() * 4 + 8
+        self.d2h_bytes = self.h_grad.numel() * 4 + 8 + 4
         self.graph_after = 3          # eager host-driven steps before copies + kernels are captured as one graph
         self._calls = 0
         self._graphs: tp.Dict[bool, torch.cuda.CUDAGraph] = {}   # reuse flag -> captured step
         self._mode_calls = {False: 0, True: 0}
-        self._graph_version = -1
+        self._graph_version: tp.Any = None
 
     def set_cell(self, cell) -> None:
         self.h_cell.copy_(torch.as_tensor(np.asarray(cell, dtype=np.float32)).reshape(-1))
@@ -91,7 +92,7 @@ class HostCalculator:
             self.h_coords.numpy()[...] = np.asarray(positions, dtype=np.float32).reshape(self.n, 3)
         eng = self.engine
         self._calls += 1
-        if self._graphs and self._graph_version != eng.nets.version:
+        if self._graphs and self._graph_version != eng.nets.active_key:
             self._graphs = {}   # the active ensemble members changed: the captured scales are stale
         reuse = self.skin > 0 and self._have_grid
         self._run(reuse)
@@ -101,9 +102,10 @@ class HostCalculator:
             self._run(False)
         elif reuse and int(self.h_moved[0]):
             self._have_grid = False   # close to the limit: rebuild before the next step
-        forces = self.h_grad.numpy()
-        np.negative(forces, out=forces)
-        return float(self.h_energy[0]), forces
+        if int(self.h_status[0]):   # came back with the results: raise what the reference raises
+            eng.check_status(self.ws)
+        # a fresh array: h_grad is the persistent pinned D2H buffer and is overwritten by the next call
+        return float(self.h_energy[0]), np.negative(self.h_grad.numpy())
 
     def _run(self, reuse: bool) -> None:
         """One step (H2D, kernels, D2H, synchronise); after a few eager uses of a mode its whole sequence
@@ -122,7 +124,7 @@ class HostCalculator:
                 self._copies_in(reuse)
                 eng._launch(ws, self.pbc, True, lo, hi, reuse)
                 self._copies_out(reuse)
-            self._graphs[reuse], self._graph_version = graph, eng.nets.version
+            self._graphs[reuse], self._graph_version = graph, eng.nets.active_key
         if graph is not None:
             graph.replay()
         else:
@@ -143,6 +145,7 @@ class HostCalculator:
     def _copies_out(self, reuse: bool = False) -> None:
         self.h_grad.copy_(self.ws.grad.view(self.n, 3), non_blocking=True)
         self.h_energy.copy_(self.ws.energies, non_blocking=True)
+        self.h_status.copy_(self.ws.status, non_blocking=True)
         if reuse:
             self.h_moved.copy_(self.ws.moved, non_blocking=True)
 

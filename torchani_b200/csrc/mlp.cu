@@ -90,6 +90,41 @@ __global__ void __launch_bounds__(256) k_zero_live_blocks(float* dx, int ldx, co
   }
 }
 
+
+// ---- model-pack time: plain fp32 weights -> tiled B operand (include/ani_b200.h section 6) ----
+// One thread per (output row n, 8-column chunk of K): splits scale * W into the 16-bit pieces and stores one
+// 16-byte chunk per piece at its swizzled place.  `transpose`: B[n][k] = src[k][n] (the backward operands are the
+// transposed weights); K is zero-padded to a multiple of 32; blockIdx.z = ensemble member (batched operands).
+__global__ void __launch_bounds__(256) k_pack_b_operand(const float* __restrict__ src, int N, int K, int ld_src,
+                                                        int transpose, float scale, long long src_batch_stride,
+                                                        unsigned char* __restrict__ dst, long long dst_batch_stride) {
+  const int kp = (K + 31) / 32 * 32, nkb = kp / 32, chunks = kp / 8;
+  const long long total = (long long)N * chunks;
+  const float* s = src + (long long)blockIdx.z * src_batch_stride;
+  unsigned char* d = dst + (long long)blockIdx.z * dst_batch_stride;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(t / chunks), c8 = (int)(t % chunks);
+    const int n0 = n / 256 * 256, bn = min(256, N - n0), r = n - n0;
+    const int kb = c8 >> 2, ch = c8 & 3;
+    uint32_t w[4][OPND_PARTS];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float v[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = c8 * 8 + 2 * i + j;
+        v[j] = k < K ? scale * (transpose ? s[(long long)k * ld_src + n] : s[(long long)n * ld_src + k]) : 0.f;
+      }
+      tc::split_pair(v[0], v[1], w[i]);
+    }
+    unsigned char* blk = d + ((size_t)n0 * nkb + (size_t)kb * bn) * (OPND_PARTS * OPND_ROW_BYTES);
+    const uint32_t off = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)((ch ^ ((r >> 1) & 3)) << 4);
+#pragma unroll
+    for (int p = 0; p < OPND_PARTS; ++p)
+      *reinterpret_cast<uint4*>(blk + (size_t)p * bn * OPND_ROW_BYTES + off) = make_uint4(w[0][p], w[1][p], w[2][p], w[3][p]);
+  }
+}
+
 }  // namespace ani
 
 using namespace ani;
@@ -167,6 +202,20 @@ static void launch_gemm_tc(const tc::Args& a_in, cudaStream_t st, bool dependent
     cudaLaunchKernelEx(&cfg, k2, a);
   else
     cudaLaunchKernelEx(&cfg, k1, a);
+}
+
+extern "C" int ani_b200_pack_b_operand(const float* src, int n, int k, int ld_src, int transpose, float scale,
+                                       int batch, long long src_batch_stride, void* dst, long long dst_batch_stride,
+                                       void* stream) {
+  if (!src || !dst || n < 32 || n % 32 || k < 1 || batch < 1 || !(scale > 0.f)) return ANI_ERR_BAD_ARG;
+  const long long total = (long long)n * ((k + 31) / 32 * 4);
+  const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  k_pack_b_operand<<<dim3(blocks, 1, batch), 256, 0, (cudaStream_t)stream>>>(src, n, k, ld_src, transpose, scale,
+                                                                              src_batch_stride,
+                                                                              static_cast<unsigned char*>(dst),
+                                                                              dst_batch_stride);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
 }
 
 // shared argument checks + the launch-invariant part of the GEMM arguments

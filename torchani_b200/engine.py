@@ -218,7 +218,28 @@ class PackedNetworks:
         mdl = self.model
         mdl.num_species, mdl.num_members, mdl.in_dim, mdl.ldx = S, M, in_dim, self.ldx
         mdl.celu_alpha = celu_alpha
-        f32 = dict(dtype=torch.float32, device=self.device)
+        # Weights are gathered on the HOST into one flat float32 buffer (zero-padded to 32-column blocks),
+        # uploaded with a single copy and re-laid out into the tiled B operands by this library's own
+        # ani_b200_pack_b_operand kernel: no ATen kernel touches them (one launch per operand kind).
+        pad = lambda v: (v + 31) // 32 * 32  # noqa: E731
+        P2 = 2 * _lib.operand_format().parts          # bytes per operand element
+        plan = []                                     # per species: sizes, scales, source / destination offsets
+        src_off = 0
+        dst_off = 0
+
+        def take_src(count: int) -> int:
+            nonlocal src_off
+            o = src_off
+            src_off += (count + 63) // 64 * 64         # 256-byte aligned float32 blocks
+            return o
+
+        def take_dst(nbytes: int) -> int:
+            nonlocal dst_off
+            o = dst_off
+            dst_off += (nbytes + 1023) // 1024 * 1024
+            return o
+
+        host_w = []
         for s in range(S):
             layers0 = weights[0][s]
             if len(layers0) != 4:
@@ -229,54 +250,78 @@ class PackedNetworks:
             if layers0[0][0].shape[1] != in_dim:
                 raise ValueError("first layer width does not match the AEV length")
             self.dims.append((h1, h2, h3))
-            W = [[weights[m][s][k][0].detach().to(**f32) for m in range(M)] for k in range(4)]
-            Bv = [[weights[m][s][k][1].detach().to(**f32) for m in range(M)] for k in range(4)]
+            W = [[weights[m][s][k][0].detach().to("cpu", torch.float32) for m in range(M)] for k in range(4)]
+            Bv = [[weights[m][s][k][1].detach().to("cpu", torch.float32) for m in range(M)] for k in range(4)]
             for m in range(M):
                 if tuple(W[0][m].shape) != (h1, in_dim) or tuple(W[1][m].shape) != (h2, h1) \
                         or tuple(W[2][m].shape) != (h3, h2) or tuple(W[3][m].shape) != (1, h3):
                     raise ValueError("all ensemble members must share the layer widths of an element")
-            # the kernels work on 32-column blocks: pad the hidden widths with zero weights and biases
-            # (CELU(0) = 0 and the padded inputs of the next layer meet zero weights: results unchanged)
-            ins, outs = (in_dim, h1, h2, h3), (h1, h2, h3, 1)
-            pad = lambda v: (v + 31) // 32 * 32  # noqa: E731
-            pin = (in_dim, pad(h1), pad(h2), pad(h3))
-            pout = (pad(h1), pad(h2), pad(h3), 1)
-            for k in range(4):
-                for m in range(M):
-                    w = torch.zeros(pout[k], pin[k], **f32)
-                    w[:outs[k], :ins[k]] = W[k][m]
-                    bb = torch.zeros(pout[k], **f32)
-                    bb[:outs[k]] = Bv[k][m]
-                    W[k][m], Bv[k][m] = w, bb
-            h1, h2, h3 = pout[:3]
-            w1n = torch.zeros(M * h1, self.ldx, **f32)
-            w1n[:, :in_dim] = torch.cat(W[0], 0)
+            host_w.append((W, Bv))
+            p1, p2, p3 = pad(h1), pad(h2), pad(h3)
             sc = [weight_scale(W[k]) for k in range(3)]   # one scale per layer, shared by W and W^T
-            t = {
-                "b1": torch.cat(Bv[0]).contiguous(),
-                "b2": torch.cat(Bv[1]).contiguous(),
-                "b3": torch.cat(Bv[2]).contiguous(),
-                "w4": torch.cat(W[3], 0).contiguous(),                        # [M][h3]
-                "b4": torch.cat(Bv[3]).contiguous(),                          # [M]
-                # B operands [N][K] (K-major) of the six GEMMs, tiled for the tensor-core kernel
-                "t_f1": tile_b_operand(w1n, sc[0]),                                        # N = M*h1, K = ldx
-                "t_f2": torch.cat([tile_b_operand(w, sc[1]) for w in W[1]]),                 # per member [h2][h1]
-                "t_f3": torch.cat([tile_b_operand(w, sc[2]) for w in W[2]]),                 # per member [h3][h2]
-                "t_b3": torch.cat([tile_b_operand(w.t().contiguous(), sc[2]) for w in W[2]]),  # [h2][h3]
-                "t_b2": torch.cat([tile_b_operand(w.t().contiguous(), sc[1]) for w in W[1]]),  # [h1][h2]
-                "t_b1": tile_b_operand(w1n.t().contiguous(), sc[0]),                       # N = ldx, K = M*h1
-            }
-            sp = mdl.sp[s]
-            sp.h1, sp.h2, sp.h3 = h1, h2, h3
-            for k in range(3):
-                sp.w_scale[k] = sc[k]
-            sp.w_scale[3] = 1.0
-            for k, v in t.items():
-                self._keep.append(v)
-                setattr(sp, k, v.data_ptr())
-        mdl.h1_max = max(d[0] for d in self.dims)
-        mdl.h2_max = max(d[1] for d in self.dims)
-        mdl.h3_max = max(d[2] for d in self.dims)
+            plan.append(dict(
+                h=(h1, h2, h3), p=(p1, p2, p3), sc=sc,
+                s_w1=take_src(M * p1 * self.ldx), s_w2=take_src(M * p2 * p1), s_w3=take_src(M * p3 * p2),
+                s_b1=take_src(M * p1), s_b2=take_src(M * p2), s_b3=take_src(M * p3), s_w4=take_src(M * p3),
+                s_b4=take_src(M),
+                d_f1=take_dst(M * p1 * self.ldx * P2), d_f2=take_dst(M * p2 * p1 * P2), d_f3=take_dst(M * p3 * p2 * P2),
+                d_b3=take_dst(M * p2 * p3 * P2), d_b2=take_dst(M * p1 * p2 * P2), d_b1=take_dst(self.ldx * M * p1 * P2)))
+        host = torch.zeros(src_off, dtype=torch.float32)   # zero weights and biases in the padding:
+        for s in range(S):                                   # CELU(0) = 0 meets zero weights: results unchanged
+            (W, Bv), q = host_w[s], plan[s]
+            (h1, h2, h3), (p1, p2, p3) = q["h"], q["p"]
+            w1 = host[q["s_w1"]:q["s_w1"] + M * p1 * self.ldx].view(M, p1, self.ldx)
+            w2 = host[q["s_w2"]:q["s_w2"] + M * p2 * p1].view(M, p2, p1)
+            w3 = host[q["s_w3"]:q["s_w3"] + M * p3 * p2].view(M, p3, p2)
+            b1 = host[q["s_b1"]:q["s_b1"] + M * p1].view(M, p1)
+            b2 = host[q["s_b2"]:q["s_b2"] + M * p2].view(M, p2)
+            b3 = host[q["s_b3"]:q["s_b3"] + M * p3].view(M, p3)
+            w4 = host[q["s_w4"]:q["s_w4"] + M * p3].view(M, p3)
+            b4 = host[q["s_b4"]:q["s_b4"] + M]
+            for m in range(M):
+                w1[m, :h1, :in_dim] = W[0][m]
+                w2[m, :h2, :h1] = W[1][m]
+                w3[m, :h3, :h2] = W[2][m]
+                b1[m, :h1], b2[m, :h2], b3[m, :h3] = Bv[0][m], Bv[1][m], Bv[2][m]
+                w4[m, :h3] = W[3][m].view(-1)
+                b4[m] = Bv[3][m].view(())
+        with torch.cuda.device(self.device):
+            src = host.pin_memory().to(self.device, non_blocking=True)
+            dst = torch.empty(dst_off, dtype=torch.uint8, device=self.device)
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            L = _lib.lib()
+            sp0, dp0 = src.data_ptr(), dst.data_ptr()
+            for s in range(S):
+                q = plan[s]
+                (p1, p2, p3), sc = q["p"], q["sc"]
+                ldx_ = self.ldx
+                jobs = [   # (src, n, k, ld_src, transpose, scale, batch, src stride, dst, dst stride in bytes)
+                    (q["s_w1"], M * p1, ldx_, ldx_, 0, sc[0], 1, 0, q["d_f1"], 0),                      # [M*h1][ldx]
+                    (q["s_w2"], p2, p1, p1, 0, sc[1], M, p2 * p1, q["d_f2"], p2 * p1 * P2),              # per member [h2][h1]
+                    (q["s_w3"], p3, p2, p2, 0, sc[2], M, p3 * p2, q["d_f3"], p3 * p2 * P2),              # per member [h3][h2]
+                    (q["s_w3"], p2, p3, p2, 1, sc[2], M, p3 * p2, q["d_b3"], p2 * p3 * P2),              # W3^T [h2][h3]
+                    (q["s_w2"], p1, p2, p1, 1, sc[1], M, p2 * p1, q["d_b2"], p1 * p2 * P2),              # W2^T [h1][h2]
+                    (q["s_w1"], ldx_, M * p1, ldx_, 1, sc[0], 1, 0, q["d_b1"], 0),                       # W1^T [ldx][M*h1]
+                ]
+                for (so, n_, k_, ld_, tr, scale, batch, sstr, do, dstr) in jobs:
+                    check(L.ani_b200_pack_b_operand(sp0 + 4 * so, n_, k_, ld_, tr, scale, batch, sstr, dp0 + do, dstr, st),
+                          "pack_b_operand")
+                spm = mdl.sp[s]
+                spm.h1, spm.h2, spm.h3 = p1, p2, p3
+                for k in range(3):
+                    spm.w_scale[k] = sc[k]
+                spm.w_scale[3] = 1.0
+                for name, off in (("b1", q["s_b1"]), ("b2", q["s_b2"]), ("b3", q["s_b3"]), ("w4", q["s_w4"]),
+                                  ("b4", q["s_b4"])):
+                    setattr(spm, name, sp0 + 4 * off)
+                for name, off in (("t_f1", q["d_f1"]), ("t_f2", q["d_f2"]), ("t_f3", q["d_f3"]), ("t_b3", q["d_b3"]),
+                                  ("t_b2", q["d_b2"]), ("t_b1", q["d_b1"])):
+                    setattr(spm, name, dp0 + off)
+        self._keep = [src, dst]
+        self._plan = plan
+        mdl.h1_max = max(q["p"][0] for q in plan)
+        mdl.h2_max = max(q["p"][1] for q in plan)
+        mdl.h3_max = max(q["p"][2] for q in plan)
         self.set_active_members(list(range(M)))
 
     def set_active_members(self, idxs: tp.Sequence[int]) -> None:
@@ -285,7 +330,8 @@ class PackedNetworks:
             if not 0 <= i < self.num_members:
                 raise IndexError(f"Idx {i} should be 0 <= idx < {self.num_members}")
         self.active = list(idxs)
-        self.version = getattr(self, "version", 0) + 1   # captured CUDA graphs bake the scales in
+        # captured CUDA graphs bake the member scales in: they are keyed by this tuple (Engine.run)
+        self.active_key = tuple(self.active)
         for m in range(_lib.ANI_MAX_MEMBERS):
             self.model.member_scale[m] = (1.0 / len(self.active)) if m in self.active else 0.0
 
@@ -387,7 +433,8 @@ class Engine:
         self._ws: tp.Dict[tp.Tuple[int, int], Workspace] = {}
         self.cuda_graph = cuda_graph
         self.graph_after = 3   # eager launches of a problem shape before its CUDA graph is captured
-        self._graphs: tp.Dict[tp.Any, torch.cuda.CUDAGraph] = {}
+        self._graphs: tp.Dict[tp.Any, torch.cuda.CUDAGraph] = {}   # insertion order = LRU order
+        self.max_graphs = 16
         self._graph_seen: tp.Dict[tp.Any, int] = {}
         self.lib = _lib.lib()
         self.launches_per_step = 0
@@ -429,7 +476,8 @@ class Engine:
 
     # -- one step --------------------------------------------------------------------------
     def step(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None, pbc: bool = False,
-             want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1), want_virial: bool = False) -> StepResult:
+             want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1), want_virial: bool = False,
+             check: bool = False) -> StepResult:
         """species (C, A) int (element indices, -1 padding), coords (C, A, 3) on this device.
         ``shard = (rank, world)``: only atoms whose bucket-sorted position falls into this
         rank's slice are evaluated; gradients/energies are partial sums to be all-reduced.
@@ -452,7 +500,10 @@ class Engine:
         ws.coords.copy_(coords.reshape(-1, 3))
         if pbc:
             ws.cell.copy_(cell.reshape(-1))
-        return self.run(ws, bool(pbc), want_grad, shard, want_virial=want_virial)
+        res = self.run(ws, bool(pbc), want_grad, shard, want_virial=want_virial)
+        if check:   # one 4-byte D2H read: cell too small / neighbour overflow / operand range raise here
+            self.check_status(ws)
+        return res
 
     def run(self, ws: Workspace, pbc: bool, want_grad: bool = True, shard: tp.Tuple[int, int] = (0, 1),
             reuse: bool = False, want_virial: bool = False) -> StepResult:
@@ -465,27 +516,33 @@ class Engine:
         hi = (n * (rank + 1)) // world
         if want_virial and (not want_grad or reuse or n_conf != 1):
             raise ValueError("the virial comes out of the force pass of a single system with a freshly built grid")
-        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.version, bool(reuse), self.skin,
+        key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.active_key, bool(reuse), self.skin,
                bool(want_virial))
         if reuse and not self.skin > 0:
             raise ValueError("reuse=True needs Engine.skin > 0 and a previous step that built the grid")
-        if not self.cuda_graph or self.profile:
-            self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
-        else:
-            graph = self._graphs.get(key)
-            if graph is not None:
-                graph.replay()
-            elif self._graph_seen.get(key, 0) < self.graph_after:
-                # the first few uses of a shape run eagerly (one-off shapes never pay for a capture)
-                self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
+        with torch.cuda.device(self.device):   # the C-ABI launches on the CURRENT device's stream
+            if not self.cuda_graph or self.profile:
                 self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
             else:
-                self.note_composition(ws)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                graph = self._graphs.get(key)
+                if graph is not None:
+                    self._graphs[key] = self._graphs.pop(key)   # most recently used last
+                    graph.replay()
+                elif self._graph_seen.get(key, 0) < self.graph_after:
+                    # the first few uses of a shape run eagerly (one-off shapes never pay for a capture)
+                    if len(self._graph_seen) > 4 * self.max_graphs:
+                        self._graph_seen.clear()
+                    self._graph_seen[key] = self._graph_seen.get(key, 0) + 1
                     self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
-                self._graphs[key] = graph
-                graph.replay()
+                else:
+                    self.note_composition(ws)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._launch(ws, bool(pbc), want_grad, lo, hi, reuse, want_virial)
+                    while len(self._graphs) >= self.max_graphs:   # evict the least recently used capture
+                        self._graphs.pop(next(iter(self._graphs)))
+                    self._graphs[key] = graph
+                    graph.replay()
         # kernels launched by this library in one step (memsets excluded):
         # prepare 5 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
         # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1

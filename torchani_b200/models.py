@@ -91,7 +91,7 @@ class _FusedEnergy(torch.autograd.Function):
     @staticmethod
     def forward(ctx, coords: Tensor, species: Tensor, cell: tp.Optional[Tensor], pbc: bool, engine: Engine,
                 want_grad: bool):
-        res: StepResult = engine.step(species, coords.detach(), cell, pbc, want_grad=want_grad)
+        res: StepResult = engine.step(species, coords.detach(), cell, pbc, want_grad=want_grad, check=True)
         ctx.want_grad = want_grad
         if want_grad:
             ctx.save_for_backward(res.grad.clone())
@@ -157,7 +157,10 @@ class ANI(torch.nn.Module):
     # -- fused engine ----------------------------------------------------------------------
     def engine(self, device: torch.device) -> Engine:
         nets = self.neural_networks.packed(device)
-        key = (str(device), id(nets))
+        shifter = self.energy_shifter
+        # the engine bakes the self energies in: key it on their values (edits, `_enabled` toggles)
+        key = (str(device), id(nets), bool(shifter._enabled), shifter.self_energies._version,
+               shifter.self_energies.data_ptr())
         if self._engine is None or self._engine_key != key:
             sae = self.energy_shifter.self_energies.tolist() if self.energy_shifter._enabled else None
             self._engine = Engine(self.aev_computer.constants, nets, sae, nbr_cap=self.aev_computer.nbr_cap)
@@ -290,14 +293,14 @@ class ANI(torch.nn.Module):
         species, coords = species_coordinates
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         eng = self.engine(coords.device)
-        return eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=False).energies.clone()
+        return eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=False, check=True).energies.clone()
 
     def energies_and_forces(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None,
                             pbc: tp.Optional[Tensor] = None) -> tp.Tuple[Tensor, Tensor]:
         """grad.py:263-290 without the autograd round trip: (energies f64 (C,), forces f32 (C,A,3))."""
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         eng = self.engine(coords.device)
-        res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True)
+        res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True, check=True)
         return res.energies.clone(), -res.grad
 
     def energies_forces_stress(self, species: Tensor, coords: Tensor, cell: Tensor,
@@ -309,7 +312,7 @@ class ANI(torch.nn.Module):
         atoms to be wrapped into the cell."""
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         eng = self.engine(coords.device)
-        res = eng.step(elem_idxs, coords.detach(), cell, True, want_grad=True, want_virial=True)
+        res = eng.step(elem_idxs, coords.detach(), cell, True, want_grad=True, want_virial=True, check=True)
         volume = torch.det(cell.detach().double()).abs()
         return res.energies.clone(), -res.grad, res.virial / volume
 

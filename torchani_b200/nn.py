@@ -160,7 +160,7 @@ class AtomicContainer(torch.nn.Module):
         self.register_buffer("atomic_numbers", torch.tensor([0], dtype=torch.long), persistent=False)
         self._packed: tp.Optional[PackedNetworks] = None
         self._packed_key: tp.Any = None
-        self._packed_frozen = False
+        self._packed_params: tp.Optional[tp.List[Tensor]] = None
 
     @property
     def symbols(self) -> tp.Tuple[str, ...]:
@@ -185,31 +185,37 @@ class AtomicContainer(torch.nn.Module):
         raise NotImplementedError
 
     def invalidate_packed(self) -> None:
-        """Forget the kernel-layout copy of the weights (call after editing parameters in place)."""
+        """Forget the kernel-layout copy of the weights (needed only after replacing ``p.data`` wholesale;
+        in-place edits are seen through the parameters' version counters)."""
         self._packed_key = None
+        self._packed_params = None
 
     def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .float() ...
         self._packed_key = None
+        self._packed_params = None
         return super()._apply(fn, *args, **kwargs)
 
     def _load_from_state_dict(self, *args, **kwargs) -> None:
         self._packed_key = None
+        self._packed_params = None
         super()._load_from_state_dict(*args, **kwargs)
 
     def packed(self, device: torch.device) -> PackedNetworks:
-        if self._packed is not None and self._packed_key is not None and self._packed_key[0] == str(device) \
-                and self._packed_frozen:
-            return self._packed   # inference fast path: frozen weights (requires_grad False) are not re-hashed
-        members = self.member_networks()
-        params = [p for m in members for p in m.parameters()]
-        key = (str(device), tuple((p.data_ptr(), p._version) for p in params))
+        """Kernel-layout copy of the weights, rebuilt when a parameter was edited in place (the
+        ``_version`` counters: optimizer steps, ``p.copy_()``, ...), replaced or moved."""
+        if self._packed_params is None:
+            self._packed_params = [p for m in self.member_networks() for p in m.parameters()]
+        params = self._packed_params
+        key = (str(device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
         if self._packed is None or self._packed_key != key:
+            members = self.member_networks()
+            params = self._packed_params = [p for m in members for p in m.parameters()]
+            key = (str(device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
             weights = [[m.atomics[s].linear_pairs() for s in m.atomics] for m in members]
             in_dim = members[0].in_dim
             self._packed = PackedNetworks(weights, in_dim, device)
             self._packed.set_active_members(self.active_members_idxs)
             self._packed_key = key
-            self._packed_frozen = all(not p.requires_grad for p in params)
         return self._packed
 
     def _run(self, elem_idxs: Tensor, aevs: Tensor, atomic: bool, ensemble_values: bool) -> Tensor:
