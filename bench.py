@@ -1,25 +1,39 @@
 #!/usr/bin/env python
 """Benchmark of the ANI-2x energy+force hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo)
-    python bench.py --impl reference --steps K --warmup W    # reference arm: CPU port of the
-                                                             # reference algorithm (oracle/)
+    python bench.py --gpus N --steps K --warmup W [--config NAME]     # B200 arm (this repo)
+    python bench.py --impl reference --steps K --warmup W [--config NAME]
+                                      # reference arm: the UNMODIFIED aiqm/torchani on the host cores
 
-One "step" = energy AND forces of the whole system (neighbour search -> AEV -> 8-member MLP
-ensemble -> forces).  Workload = BASELINE.json's metric configuration: ANI-2x x8, periodic
-10k-atom water box (9999 atoms, L = 46.38 A), seeded synthetic coordinates and weights.
-Metric: atom-steps/s (= N_atoms / t_step; ns/day at 1 fs = 0.0864 / t_step is reported too).
-With N > 1 GPUs (torchrun, one rank per GPU) the SAME box is sharded over the ranks (strong
-scaling) and one NCCL all-reduce of 3N+1 float64 values closes every step.
+One "step" = energy AND forces of the whole system (neighbour search -> AEV -> 8-member MLP ensemble ->
+forces).  Configurations (BASELINE.json `configs`), seeded synthetic coordinates and weights:
 
-Timing: W >= 3 warm-up steps, then K steps each bracketed by CUDA events on the launch stream;
-between timed steps a 256 MiB buffer is overwritten (L2 flush, untimed); barrier +
-synchronize on both sides of the region; per-step times are summed, max over ranks.
-Prints ONE JSON line on rank 0.
+    water10k    (default; the configuration the metric is quoted on)  ANI-2x x8, periodic 9999-atom water box
+    water1k     periodic 999-atom water box
+    gdb256      batch of 256 GDB-11-like conformers (9-26 atoms, H/C/N/O, -1 padding, no PBC, all-pairs semantics)
+    protein50k  1C17 protein (H C N O S) + lattice water, 50k atoms, periodic, through the host calculator
+
+Metric: atom-steps/s (= real atoms / t_step; ns/day at 1 fs = 0.0864 / t_step and conformers/s are reported too).
+With N > 1 GPUs (torchrun, one rank per GPU) the SAME system is sharded over the ranks by central atom (strong
+scaling); the partial forces / energies are summed on the device over NVLink peer memory by one kernel inside the
+step's CUDA graph (torchani_b200/csrc/comm.cu).
+
+Timing: W >= 3 warm-up steps, then K steps each bracketed by CUDA events on the launch stream; between timed steps
+a 256 MiB buffer is overwritten (L2 flush, untimed); barrier + synchronize on both sides of the region; per-step
+times are summed, max over ranks.  `e2e` = the same metric through the host-buffer API (pinned host positions in,
+host energy + forces out, copies inside the timed region).  Prints ONE JSON line on rank 0.
+
+Reference arm (`--impl reference`): the real reference package (oracle/_ref/torchani, staged by
+oracle/build_ref.sh) on the CPU -- strategy="pyaev", neighborlist="cell_list" (single periodic system) or
+"all_pairs" (batch), python Ensemble loop, float32, torchani.grad.energies_and_forces -- with one thread per
+PHYSICAL core; every step is one full evaluation of the same workload; the run stops early (>= 1 timed step)
+when its time budget is spent.  Where the staged reference is missing the CPU port of its algorithm
+(oracle/ani_oracle.py) is timed instead and the line says `kind: "port"`.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -38,25 +52,34 @@ UNIT = "atom-steps/s"
 # algorithmic bytes per atom of the AEV kernels (fp32, ANI-2x)
 AEV_FWD_BYTES_PER_ATOM = 4276.0
 AEV_BWD_BYTES_PER_ATOM = 4288.0
-# dram__bytes_read.sum + dram__bytes_write.sum from the ncu --set full capture of this build
-# (profiles/r01_ncu_full_v10_selected.csv), per launch (AEV kernels) / per six-GEMM sequence at the
-# 9999-atom box.  ncu flushes the caches before every kernel, so these are COLD-cache figures: inside
-# a step the activations a GEMM reads were just written by the previous launch and sit in the L2.
-MLP_DRAM_BYTES_PER_STEP = 574.1e6      # reads 494.6 MB + writes 79.5 MB over the six launches
-AEV_FWD_DRAM_BYTES = 0.93e6            # reads; its 6.4 MB of live AEV blocks stay in the L2 (write-back)
-AEV_BWD_DRAM_BYTES = 14.5e6            # reads (live blocks of dE/dAEV)
+
+CONFIGS = {
+    "water10k": "ANI-2x x8 ensemble, periodic water box, 9999 atoms (BASELINE configs[3]), energy+forces per step",
+    "water1k": "ANI-2x x8 ensemble, periodic water box, 999 atoms (BASELINE configs[1]), energy+forces per step",
+    "gdb256": "ANI-2x x8 ensemble, batch of 256 GDB-11-like conformers, 9-26 atoms each, H/C/N/O, -1 padding, no "
+              "PBC (BASELINE configs[2], training-benchmark shapes), energies+forces of the batch per step",
+    "protein50k": "ANI-2x x8 ensemble, 1C17 protein (H C N O S, cut to the box) in lattice water, ~50k atoms, cubic "
+                  "periodic box 79.4 A (BASELINE configs[4]), energy+forces per step through the host calculator",
+}
 
 
-def workload(n_molecules: int):
-    from torchani_b200.synthetic import water_box
-    return water_box(n_molecules, seed=0)
-
-
-def load_oracle():
-    """The CPU port of the reference algorithm: test infrastructure, imported ONLY by the
-    cpu_baseline / --impl reference legs as the thing that is timed beside the GPU path."""
-    import oracle.ani_oracle as orc
-    return orc
+def make_workload(name: str, molecules: int = 0):
+    """-> dict(z, idx, coords, cell, pbc, n_atoms (real), n_conf, batch)"""
+    from torchani_b200 import synthetic
+    if name in ("water10k", "water1k"):
+        n_mol = molecules or (3333 if name == "water10k" else 333)
+        z, idx, coords, cell, pbc = synthetic.water_box(n_mol, seed=0)
+    elif name == "protein50k":
+        z, idx, coords, cell, pbc = synthetic.protein_in_water(50001, seed=0)
+    elif name == "gdb256":
+        idx, coords = synthetic.conformer_batch(256, seed=1234)
+        conv = torch.tensor([1, 6, 7, 8])
+        z = torch.where(idx >= 0, conv[idx.clamp(min=0)], torch.full_like(idx, -1))
+        cell = pbc = None
+    else:
+        raise ValueError(name)
+    return {"z": z, "idx": idx, "coords": coords, "cell": cell, "pbc": pbc, "n_atoms": int((idx >= 0).sum()),
+            "n_conf": int(idx.shape[0]), "batch": name == "gdb256"}
 
 
 def peaks():
@@ -67,8 +90,28 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def library_hash() -> str:
+    from torchani_b200 import _lib
+    h = hashlib.sha256()
+    with open(_lib.LIB_PATH, "rb") as fh:
+        h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(config: str):
+    """dram bytes per launch from an `ncu --set full` capture OF THE LIBRARY BEING RUN: profiles/traffic.json maps
+    library hash -> config -> {mlp, aev_forward, aev_backward}; anything else is null (never a stale literal)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return {}
+    try:
+        return json.load(open(path)).get(library_hash(), {}).get(config, {})
+    except (OSError, ValueError):
+        return {}
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -104,31 +147,63 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_step(orc, model, idx, coords, cell, pbc):
-    out = orc.compute(model, idx, coords, cell, pbc, forces=True)
-    return out["energy"], out["forces"]
+# ---------------------------------------------------------------------------------------------------------
+# the reference on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def physical_cores() -> int:
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
 
 
-def run_cpu_baseline(idx, coords, cell, pbc, steps: int, warmup: int, budget_s: float = 60.0):
-    """The reference algorithm's CPU port (oracle/ani_oracle.py, float32, all host threads).
-    Bounded: stops early (after at least one timed evaluation) once `budget_s` seconds are spent,
-    warm-up included, so a slow or busy host cannot stretch the run."""
-    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1: undo that for the CPU arm
-    orc = load_oracle()
-    model = orc.ani2x_model(seed=1234, members=8, neighborlist="cell_list")
+def run_cpu_reference(work, steps: int, warmup: int, budget_s: float):
+    """Times the reference's own CPU implementation on this workload.  -> (per-step seconds, kind, threads, what)."""
+    threads = physical_cores()
+    torch.set_num_threads(threads)   # torchrun pins OMP_NUM_THREADS=1: undo that for the CPU arm
+    z, coords, cell, pbc = work["z"], work["coords"], work["cell"], work["pbc"]
+    try:
+        import oracle.ref_torchani as rt
+        if not rt.available():
+            raise ImportError("oracle/_ref/torchani is not staged")
+        from torchani_b200 import models, synthetic
+        weights = synthetic.make_weights(models.SYMBOLS_2X, synthetic.DIMS_2X, 1008, 8, seed=1234)
+        nl = "all_pairs" if work["batch"] else "cell_list"
+        model = rt.build_model(weights, "2x", "cpu", strategy="pyaev", neighborlist=nl)
+        kind = "reference"
+        what = (f"unmodified aiqm/torchani (oracle/_ref/torchani): strategy=pyaev, neighborlist={nl}, python Ensemble "
+                f"loop, float32, torchani.grad.energies_and_forces")
+
+        def step():
+            return rt.energies_and_forces(model, z, coords.clone(), cell, pbc)
+    except Exception as exc:   # the staged package is absent on this box: the CPU port of the same algorithm
+        import oracle.ani_oracle as orc
+        model = orc.ani2x_model(seed=1234, members=8, neighborlist="all_pairs" if work["batch"] else "cell_list")
+        kind = "port"
+        what = f"CPU port of the reference algorithm (oracle/ani_oracle.py, float32) [{type(exc).__name__}: {exc}]"
+        idx = work["idx"]
+
+        def step():
+            out = orc.compute(model, idx, coords, cell, pbc, forces=True)
+            return out["energy"], out["forces"]
+
     t_begin = time.perf_counter()
     for _ in range(warmup):
-        cpu_reference_step(orc, model, idx, coords, cell, pbc)
-        if time.perf_counter() - t_begin > budget_s / 2:
+        step()
+        if time.perf_counter() - t_begin > budget_s / 3:
             break
     times = []
-    for _ in range(steps):
+    for _ in range(max(1, steps)):
         t0 = time.perf_counter()
-        cpu_reference_step(orc, model, idx, coords, cell, pbc)
+        step()
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_begin > budget_s:
             break
-    return times
+    return times, kind, torch.get_num_threads(), what
 
 
 def main():
@@ -137,8 +212,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--molecules", type=int, default=3333, help="water molecules (3333 -> the 10k-atom box)")
-    ap.add_argument("--cpu-steps", type=int, default=2, help="steps of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--config", default="water10k", choices=sorted(CONFIGS))
+    ap.add_argument("--molecules", type=int, default=0, help="water configs only: override the number of molecules")
+    ap.add_argument("--cpu-steps", type=int, default=3, help="steps of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--reduce", default="auto", choices=["auto", "peer", "nccl"],
+                    help="multi-GPU reduction of the partial forces: this library's peer-memory kernel or NCCL")
     ap.add_argument("--skin", type=float, default=0.0,
                     help="experiment: Verlet skin (A) of the end-to-end arm; the atoms then move ballistically "
                          "(300 K Maxwell-Boltzmann velocities, 1 fs per step) so that grid reuse is exercised")
@@ -147,30 +225,27 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    n_atoms = 3 * args.molecules
-    config = {"workload": f"ANI-2x x8 ensemble, periodic water box, {n_atoms} atoms (BASELINE configs[3]), "
-                          "energy+forces per step",
-              "atoms": n_atoms, "ensemble": 8, "aev_dim": 1008, "cutoffs_A": [5.1, 3.5],
-              "parallelism": f"atom-range sharding x{world} + 1 all-reduce" if world > 1 else "single GPU",
-              "l2": "256 MiB flush between timed steps (untimed)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        z, idx, coords, cell, pbc = workload(args.molecules)
-        cores = torch.get_num_threads()
-        times = run_cpu_baseline(idx, coords, cell, pbc, args.steps, args.warmup, budget_s=150.0)
-        t = sum(times) / len(times)
+        work = make_workload(args.config, args.molecules)
+        n_atoms = work["n_atoms"]
+        times, kind, threads, what = run_cpu_reference(work, args.steps, args.warmup, budget_s=240.0)
+        t = statistics.median(times)
         value = n_atoms / t
-        sample = f"{len(times)} full energy+force evaluations of the {n_atoms}-atom box (float32, torch CPU ops)"
+        config = {"workload": CONFIGS[args.config], "name": args.config, "atoms": n_atoms, "conformers": work["n_conf"],
+                  "ensemble": 8, "aev_dim": 1008, "cutoffs_A": [5.1, 3.5], "parallelism": f"{threads} CPU threads"}
+        sample = (f"{len(times)} full energy+force evaluations of the workload ({n_atoms} atoms), median; {what}; "
+                  f"{threads} threads = physical cores of this host")
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": len(times), "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "ns_per_day": 0.0864 / t, "config": config,
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "ns_per_day": 0.0864 / t, "conformers_per_s": work["n_conf"] / t, "config": config,
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "step_times_s": [round(x, 4) for x in times], "gpu_launches": 0}
         print(json.dumps(line))
         return
 
@@ -183,16 +258,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from torchani_b200 import models
+    from torchani_b200.calculator import HostCalculator
     from torchani_b200.parallel import ShardedEngine
-
     from torchani_b200.synthetic import DIMS_2X, make_weights
-    z, idx, coords, cell, pbc = workload(args.molecules)
+
+    work = make_workload(args.config, args.molecules)
+    n_atoms, n_conf = work["n_atoms"], work["n_conf"]
+    z, idx, coords, cell, pbc = work["z"], work["idx"], work["coords"], work["cell"], work["pbc"]
+    periodic = pbc is not None
     weights = make_weights(models.SYMBOLS_2X, DIMS_2X, 1008, 8, seed=1234)
     model = models.from_weight_lists("2x", weights, device=dev, periodic_table_index=True)
     eng = model.engine(dev)
-    sharded = ShardedEngine(eng)
-    sp_d, co_d, ce_d = idx.to(dev), coords.to(dev), cell.to(dev)
-    z_d = z.to(dev)
+    sharded = ShardedEngine(eng, reduce=args.reduce)
+    sp_d, co_d = idx.to(dev), coords.to(dev)
+    ce_d = cell.to(dev) if periodic else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -201,11 +280,11 @@ def main():
         torch.cuda.synchronize(dev)
 
     def one_step():
-        return sharded.step(sp_d, co_d, ce_d, True)
+        return sharded.step(sp_d, co_d, ce_d, periodic)
 
     sampler = ClockSampler(local_rank)
     sampler.start()  # sampled from the warm-up to the end of the end-to-end region (GPU under load throughout)
-    for _ in range(warmup):
+    for _ in range(max(warmup, eng.graph_after + 2)):   # eager uses + the graph capture happen here, untimed
         one_step()
     eng.check_status()
     barrier()
@@ -225,29 +304,54 @@ def main():
     ms_per_step = float(t_all.item()) / args.steps
     value = n_atoms / (ms_per_step * 1e-3)
     eng.check_status()
+    launches_per_step = eng.launches_per_step + (1 if sharded.mode == "peer" else 0)
 
-    # ---- end to end through the public API with HOST buffers: calculator.HostCalculator.calculate
-    #      (host positions in, host energy + forces out; H2D, graph replay, D2H and the sync inside)
-    from torchani_b200.calculator import HostCalculator
-    calc = HostCalculator(model, z[0].numpy(), cell.numpy(), pbc=True, shard=(rank, world), skin=args.skin)
-    h_pos = coords[0].numpy().copy()
+    # ---- end to end through the public API with HOST buffers (pinned host inputs -> host energy + forces;
+    #      H2D, kernels, multi-GPU reduction, D2H and the synchronisation inside the timed region)
     h_vel = None
-    if args.skin > 0:   # A/fs: sqrt(kT/m), kT = 0.02585 eV, 1 amu A^2/fs^2 = 103.6427 eV
-        import numpy as np
-        mass = np.where(z[0].numpy() == 1, 1.008, 15.999)[:, None]
-        h_vel = (np.random.default_rng(0).normal(size=h_pos.shape) * np.sqrt(0.02585 / (103.6427 * mass))).astype("float32")
+    if not work["batch"]:
+        calc = HostCalculator(model, z[0].numpy(), cell.numpy() if periodic else None, pbc=periodic,
+                              skin=args.skin, sharded=sharded if world > 1 else None)
+        h_pos = coords[0].numpy().copy()
+        if args.skin > 0:   # A/fs: sqrt(kT/m), kT = 0.02585 eV, 1 amu A^2/fs^2 = 103.6427 eV
+            import numpy as np
+            mass = np.where(z[0].numpy() == 1, 1.008, 15.999)[:, None]
+            h_vel = (np.random.default_rng(0).normal(size=h_pos.shape) * np.sqrt(0.02585 / (103.6427 * mass))).astype("float32")
 
-    def e2e_step():
-        if h_vel is not None:
-            h_pos[...] += h_vel
-        e, f = calc.calculate(h_pos)
-        if world > 1:  # partial results of this rank's atom slice -> one all-reduce (as in ShardedEngine)
-            buf = torch.cat([torch.from_numpy(f).reshape(-1).double(), torch.tensor([e], dtype=torch.float64)]).to(dev)
-            dist.all_reduce(buf)
-            buf.cpu()
-        return e, f
+        def e2e_step():
+            if h_vel is not None:
+                h_pos[...] += h_vel
+            return calc.calculate(h_pos)
 
-    for _ in range(3):
+        api = ("torchani_b200.calculator.HostCalculator.calculate (host positions in, host energy+forces out; "
+               "counterpart of torchani.ase.Calculator.calculate)")
+        h2d, d2h = calc.h2d_bytes, calc.d2h_bytes
+        e2e_warm = calc.graph_after + 3
+    else:
+        # batch of conformers: the model-level call of grad.py:263-290 on pinned host tensors
+        h_z = z.pin_memory()
+        h_c = coords.pin_memory()
+        h_f = torch.empty(coords.shape, dtype=torch.float32).pin_memory()
+        h_e = torch.empty(n_conf, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            zd = h_z.to(dev, non_blocking=True)
+            cd = h_c.to(dev, non_blocking=True)
+            if world > 1:
+                e, g = sharded.step(model.species_converter(zd), cd, None, False)
+                f = -g
+            else:
+                e, f = model.energies_and_forces(zd, cd)
+            h_f.copy_(f.to(torch.float32), non_blocking=True)
+            h_e.copy_(e, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return h_e, h_f
+
+        api = "torchani_b200.models.ANI.energies_and_forces on pinned host tensors (grad.py:263-290), results to the host"
+        h2d = h_z.numel() * 8 + h_c.numel() * 4
+        d2h = h_f.numel() * 4 + h_e.numel() * 8
+        e2e_warm = eng.graph_after + 3
+    for _ in range(e2e_warm):   # incl. the graph capture of the host-driven step
         e2e_step()
     barrier()
     e2e_evs = []
@@ -264,9 +368,8 @@ def main():
     t_e2e = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = n_atoms / (float(t_e2e.item()) / args.steps * 1e-3)
-    h2d = calc.h2d_bytes
-    d2h = calc.d2h_bytes
+    e2e_ms_per_step = float(t_e2e.item()) / args.steps
+    e2e_value = n_atoms / (e2e_ms_per_step * 1e-3)
 
     # ---- per-stage device times for the roofline (separate short run, events per C-ABI call)
     eng.profile = True
@@ -277,7 +380,8 @@ def main():
     eng.profile = False
     pk = peaks()
     owned = n_atoms / world
-    flops = sum(eng.nets.flops_per_atom(3 if k % 3 == 0 else 0) for k in range(3)) / 3.0 * owned  # O,H,H
+    counts = torch.bincount(idx[idx >= 0].flatten(), minlength=7).tolist()
+    flops = sum(eng.nets.flops_per_atom(s) * c for s, c in enumerate(counts)) / world
     mlp_s = stage.get("mlp_forward_backward", float("nan")) * 1e-3
     fwd_s = stage.get("aev_forward", float("nan")) * 1e-3
     bwd_s = stage.get("aev_backward", float("nan")) * 1e-3
@@ -285,52 +389,55 @@ def main():
     fmt = operand_format()
     split = ("2 x fp16 split of every (power-of-two scaled) fp32 operand, 3 products" if fmt.parts == 2
              else "3 x bf16 split of every fp32 operand, 6 products")
-    nprod = 3 if fmt.parts == 2 else 6
-    roofline = {"kernel": "tc::k_gemm_tc<EPI> x6 (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input, "
+    traffic = measured_traffic(args.config) if world == 1 else {}
+    roofline = {"kernel": "tc::k_gemm_tc (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input, "
                           f"tcgen05 kind::f16 on a {split} (fp32-accurate)",
                 "bound": "tensor", "achieved": flops / mlp_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": MLP_DRAM_BYTES_PER_STEP if world == 1 and args.molecules == 3333 else None,
+                "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": traffic.get("mlp"),
                 "algorithmic_flops_per_launch_sequence": flops, "peak_source": pk["source"],
-                "note": "achieved = dense algorithmic FLOPs of SURVEY 8(d) (98.2 GFLOP/step at 10k atoms) / "
-                        "device time of the six GEMM launches; peak = measured dense bf16 rate (= the fp16 rate). The "
-                        f"kernel issues {nprod} 16-bit MMAs per product but skips the AEV column blocks of absent "
-                        f"element pairs in layer 1, so the executed tensor work is {nprod} x 36% of the dense count "
-                        "for water. "
-                        "traffic = dram bytes of the six launches (ncu, profiles/), null if not captured for this build"}
+                "note": "achieved = dense algorithmic FLOPs of SURVEY 8(d) (2 x MACs x 8 members, forward + "
+                        "backward-to-input, per atom by element) / device time of the GEMM launches of one step (CUDA "
+                        "events on the launch stream); peak = measured dense bf16 rate (= the fp16 rate).  traffic = "
+                        "dram bytes of those launches from an ncu --set full capture of THIS library build "
+                        "(profiles/traffic.json, keyed by the library hash) or null"}
     roofline_aev = {
-        "forward": {"kernel": "k_aev_forward_cta<8,4>", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
+        "forward": {"kernel": "k_aev_forward_cta", "bound": "hbm", "achieved": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9,
                     "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": AEV_FWD_BYTES_PER_ATOM * owned / fwd_s / 1e9 / pk["hbm_gbs"],
-                    "traffic": AEV_FWD_DRAM_BYTES if world == 1 and args.molecules == 3333 else None},
-        "backward": {"kernel": "k_aev_backward<8,4>", "bound": "hbm", "achieved": AEV_BWD_BYTES_PER_ATOM * owned / bwd_s / 1e9,
+                    "traffic": traffic.get("aev_forward")},
+        "backward": {"kernel": "k_aev_backward", "bound": "hbm", "achieved": AEV_BWD_BYTES_PER_ATOM * owned / bwd_s / 1e9,
                      "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": AEV_BWD_BYTES_PER_ATOM * owned / bwd_s / 1e9 / pk["hbm_gbs"],
-                     "traffic": AEV_BWD_DRAM_BYTES if world == 1 and args.molecules == 3333 else None},
+                     "traffic": traffic.get("aev_backward")},
         "peak_source": pk["source"]}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload, the real reference
     cpu = None
     if rank == 0 and world == 1 and args.cpu_steps > 0:
-        cores = torch.get_num_threads()
-        times = run_cpu_baseline(idx, coords, cell, pbc, args.cpu_steps, 1, budget_s=45.0)
-        t = sum(times) / len(times)
-        cpu = {"value": n_atoms / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{len(times)} full energy+force evaluations of the same {n_atoms}-atom box with the "
-                         f"CPU port of the reference algorithm (oracle/ani_oracle.py, float32, {cores} threads)"}
+        times, kind, threads, what = run_cpu_reference(work, args.cpu_steps, 1, budget_s=30.0)
+        t = statistics.median(times)
+        cpu = {"value": n_atoms / t, "unit": UNIT, "cores": threads, "kind": kind, "ms_per_step": t * 1e3,
+               "sample": f"{len(times)} full energy+force evaluations of the same workload ({n_atoms} atoms), median; "
+                         f"{what}; {threads} threads = physical cores of this host"}
 
     if rank == 0:
+        config = {"workload": CONFIGS[args.config], "name": args.config, "atoms": n_atoms, "conformers": n_conf,
+                  "ensemble": 8, "aev_dim": 1008, "cutoffs_A": [5.1, 3.5],
+                  "parallelism": (f"central-atom sharding x{world} + one in-graph {sharded.mode} reduction of the "
+                                  "partial forces") if world > 1 else "single GPU",
+                  "l2": "256 MiB flush between timed steps (untimed)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "ns_per_day": 0.0864 / (ms_per_step * 1e-3), "clocks": clocks,
+                "ns_per_day": 0.0864 / (ms_per_step * 1e-3), "conformers_per_s": n_conf / (ms_per_step * 1e-3),
+                "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": float(t_e2e.item()) / args.steps,
-                        "api": "torchani_b200.calculator.HostCalculator.calculate (host positions in, host "
-                               "energy+forces out; counterpart of torchani.ase.Calculator.calculate)",
+                        "ms_per_step": e2e_ms_per_step, "api": api,
                         **({"verlet_skin_A": args.skin, "grid_rebuilds": calc.rebuilds, "steps_redone": calc.redone,
                             "calls": calc._calls} if args.skin > 0 else {})},
-                "gpu_launches": eng.launches_per_step * args.steps,
+                "gpu_launches": launches_per_step * args.steps,
                 "operand_format": {"parts": fmt.parts, "bytes_per_element": 2 * fmt.parts},
+                "library_sha256_16": library_hash(),
                 "stage_ms": stage, "roofline": roofline, "roofline_aev": roofline_aev, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

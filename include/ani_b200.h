@@ -350,6 +350,24 @@ int ani_b200_reduce_energies(const ani_mlp_model* model, const float* e_member, 
                              int n_per_conf, const double* sae, float* atomic_out,
                              float* member_atomic_out, double* energies_out, void* stream);
 
+/* 8. Multi-GPU: one-shot all-reduce of the per-rank partial forces / energies over NVLink peer memory.   */
+/*    The path shards by central atom (one process per GPU); every rank accumulates dE_owned/dx_j into a      */
+/*    full-length f32[n_f32] buffer and its share of the conformer energies into f64[n_f64].  Those partial     */
+/*    buffers live in CUDA-IPC memory owned by the communicator (the ONE place where this library allocates:    */
+/*    IPC-exportable memory must come from cudaMalloc) and are mapped by every peer; ani_b200_comm_allreduce     */
+/*    launches ONE kernel: flag barrier in peer memory, every rank sums the W partials in rank order (bitwise      */
+/*    identical totals everywhere) into its own out buffers, flag barrier.  Graph-capturable; epochs advance on     */
+/*    the device.  The reference has no collective -- this replaces the NCCL all-reduce of         */
+/*    round 1 (parallel.py).  Set-up: create on every rank, exchange the 64-byte handles by any host channel        */
+/*    (torch.distributed all_gather here), connect with the W handles in rank order.  world <= 8, one node.          */
+/*    error_word (device i32): raised by the kernel if a peer does not arrive within ~10 s (no hang).               */
+int ani_b200_comm_create(int rank, int world, long long n_f32, long long n_f64, void** comm_out);
+int ani_b200_comm_handle(void* comm, void* handle64);
+int ani_b200_comm_connect(void* comm, const void* handles);
+int ani_b200_comm_buffers(void* comm, float** partial_f32, double** partial_f64, int32_t** error_word);
+int ani_b200_comm_allreduce(void* comm, float* out_f32, double* out_f64, void* stream);
+int ani_b200_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -394,3 +394,55 @@ def test_weight_packing_kernel_matches_the_python_tiler():
         assert list(nets.model.member_scale)[:2] == [0.5, 0.5]
         with pytest.raises(IndexError):
             nets.set_active_members([7])
+
+
+def test_model_level_calls_raise_device_side_conditions():
+    """The public model paths read the device status word (one 4-byte copy): a periodic cell thinner than the
+    cutoff raises the reference's RuntimeError (neighbors.py:402-403), more neighbours than nbr_cap raises instead
+    of returning energies of a truncated list."""
+    from torchani_b200 import models, synthetic
+    w = synthetic.make_weights(models.SYMBOLS_2X, synthetic.DIMS_2X, 1008, 2, seed=1)
+    model = models.from_weight_lists("2x", w, device=DEV, periodic_table_index=False)
+    z, idx, coords, cell, pbc = synthetic.water_box(20, seed=2)          # L = 8.4 A
+    thin = cell.clone()
+    thin[2, 2] = 4.0                                                       # thinner than Rcr = 5.1 A
+    args = ((idx.to(DEV), coords.to(DEV)), thin.to(DEV), pbc.to(DEV))
+    with pytest.raises(RuntimeError, match="Cell is too small"):
+        model(*args)
+    with pytest.raises(RuntimeError, match="Cell is too small"):
+        model.energies_and_forces(idx.to(DEV), coords.to(DEV), thin.to(DEV), pbc.to(DEV))
+    # the status word is cleared by the raise: the next (valid) call works
+    out = model((idx.to(DEV), coords.to(DEV)), cell.to(DEV), pbc.to(DEV))
+    assert bool(torch.isfinite(out.energies).all())
+    # neighbour overflow: 200 atoms inside a 3 A ball, nbr_cap = 128
+    g = torch.Generator().manual_seed(0)
+    blob = (torch.rand(1, 200, 3, generator=g) * 3.0).to(DEV)
+    sp = torch.zeros(1, 200, dtype=torch.long, device=DEV)
+    with pytest.raises(RuntimeError, match="nbr_cap"):
+        model((sp, blob))
+    # an engine on cuda:0 launches on cuda:0 whatever the current device is (device guard)
+    if torch.cuda.device_count() > 1:
+        with torch.cuda.device(1):
+            out2 = model((idx.to(DEV), coords.to(DEV)), cell.to(DEV), pbc.to(DEV))
+        assert torch.equal(out2.energies, out.energies)
+
+
+def test_packed_weights_follow_in_place_edits():
+    """In-place parameter edits (no invalidate_packed() call) and self-energy edits reach the kernels."""
+    from torchani_b200 import models, synthetic
+    w = synthetic.make_weights(models.SYMBOLS_2X, synthetic.DIMS_2X, 1008, 2, seed=1)
+    model = models.from_weight_lists("2x", w, device=DEV, periodic_table_index=False)
+    _, idx, coords, cell, pbc = synthetic.water_box(20, seed=2)
+    args = ((idx.to(DEV), coords.to(DEV)), cell.to(DEV), pbc.to(DEV))
+    e0 = float(model(*args).energies[0])
+    with torch.no_grad():
+        model.neural_networks.members[0].atomics["H"].final_layer.bias.add_(0.5)     # 40 H atoms, 2 members
+    e1 = float(model(*args).energies[0])
+    assert abs((e1 - e0) - 0.5 * 40 / 2) < 2e-3
+    with torch.no_grad():
+        model.energy_shifter.self_energies[3] += 1.0                                    # 20 O atoms
+    e2 = float(model(*args).energies[0])
+    assert abs((e2 - e1) - 20.0) < 2e-3
+    model.energy_shifter._enabled = False
+    e3 = float(model(*args).energies[0])
+    assert abs(e3) < 50.0 and abs(e3 - e2) > 1e3

@@ -231,3 +231,35 @@ def test_smooth_cutoff_and_active_members(engines):
         assert_close("forces", -res.grad.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
     finally:
         eng.nets.set_active_members(list(range(8)))
+
+
+def test_protein_in_water_50k_properties(engines):
+    """BASELINE config 5 size (1C17 protein, H C N O S, in lattice water, ~50k atoms): five elements live, so the
+    block-sparse layer 1 runs 20 of its 32 AEV column blocks (water: 5).  Size-independent properties at full size;
+    value parity of an all-five-element system is the golden case 1c17_chunk_hcnos_ani2x (real reference)."""
+    from torchani_b200 import synthetic
+    eng = engines["2x"]
+    d = eng.device
+    _, idx, coords, cell, _ = synthetic.protein_in_water(50001, seed=0)
+    n = idx.shape[1]
+    assert 49000 < n <= 50001 and set(idx.unique().tolist()) == {0, 1, 2, 3, 4}
+    sp, co, ce = idx.to(d), coords.to(d), cell.to(d)
+    r0 = eng.step(sp, co, ce, True)
+    e0, g0, at0 = r0.energies.clone(), r0.grad.clone(), r0.atomic_energies.clone()
+    eng.check_status()
+    assert bool(torch.isfinite(g0).all()) and bool(torch.isfinite(at0).all())
+    scale = float(g0.abs().max())
+    assert float(g0.double().sum(1).abs().max()) < 1e-6 * n * max(1.0, scale)          # Newton's third law
+    sae = torch.tensor([orc.GSAES_WB97X_631GD[s] for s in orc.SYMBOLS_2X], dtype=torch.float64, device=d)
+    assert abs(float(at0.double().sum() + sae[sp].sum() - e0[0])) < 1e-6 * n
+    shift = torch.tensor([13.7, -80.2, 5.5], device=d)                                   # translation, re-wrapping
+    r1 = eng.step(sp, co + shift, ce, True)
+    assert abs(float(r1.energies[0] - e0[0])) < 2e-3
+    assert float((r1.grad - g0).abs().max()) < 1e-4 * max(1.0, scale)
+    parts_e, parts_g = 0.0, torch.zeros_like(g0)                                         # what 8 ranks would compute
+    for r in range(8):
+        rr = eng.step(sp, co, ce, True, shard=(r, 8))
+        parts_e += float(rr.energies[0])
+        parts_g += rr.grad
+    assert abs(parts_e - float(e0[0])) < 1e-4
+    assert float((parts_g - g0).abs().max()) < 1e-4 * max(1.0, scale)

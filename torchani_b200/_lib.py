@@ -91,6 +91,12 @@ _PROTOTYPES = {
     "ani_b200_zero_live_blocks": (C.c_int, [_P, _P, _P, _P, _P]),
     "ani_b200_mlp_backward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ani_b200_pack_b_operand": (C.c_int, [_P, _I, _I, _I, _I, _F, _I, C.c_longlong, _P, C.c_longlong, _P]),
+    "ani_b200_comm_create": (C.c_int, [_I, _I, C.c_longlong, C.c_longlong, _P]),
+    "ani_b200_comm_handle": (C.c_int, [_P, _P]),
+    "ani_b200_comm_connect": (C.c_int, [_P, _P]),
+    "ani_b200_comm_buffers": (C.c_int, [_P, _P, _P, _P]),
+    "ani_b200_comm_allreduce": (C.c_int, [_P, _P, _P, _P]),
+    "ani_b200_comm_destroy": (C.c_int, [_P]),
     "ani_b200_active_aev_blocks": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ani_b200_reduce_energies": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }

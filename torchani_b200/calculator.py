@@ -40,7 +40,7 @@ class HostCalculator:
     """
 
     def __init__(self, model: ANI, atomic_numbers, cell=None, pbc: bool = False, shard: tp.Tuple[int, int] = (0, 1),
-                 skin: float = 0.0):
+                 skin: float = 0.0, sharded: tp.Any = None):
         dev = next(model.buffers()).device
         if dev.type != "cuda":
             raise ValueError("HostCalculator needs a model on a CUDA device")
@@ -54,7 +54,20 @@ class HostCalculator:
             raise ValueError("skin must be >= 0")
         if self.skin > 0:
             self.engine.skin = self.skin   # buckets for cutoff + skin (shared by every user of this engine)
-        self.ws = self.engine.workspace(1, self.n)
+        # multi-GPU (one process per GPU): `sharded` = parallel.ShardedEngine over this model's engine.  This rank
+        # evaluates its slice of the atoms; the partial forces / energies are summed over the ranks ON THE DEVICE
+        # (peer-memory reduction inside the captured graph) before the single D2H copy, so every rank returns the
+        # full result
+        self.sharded = sharded
+        if sharded is not None:
+            if sharded.engine is not self.engine:
+                raise ValueError("`sharded` must wrap this model's engine")
+            if self.skin > 0:
+                raise ValueError("Verlet-skin reuse is not combined with multi-GPU sharding")
+            self.shard = shard = (sharded.rank, sharded.world)
+            self.ws = sharded.attach(1, self.n)
+        else:
+            self.ws = self.engine.workspace(1, self.n)
         self.ws.species_i32.copy_(self.elem_idxs.reshape(-1))
         self.h_coords = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
         self.h_cell = torch.zeros(9, dtype=torch.float32).pin_memory()
@@ -80,6 +93,29 @@ class HostCalculator:
     def set_cell(self, cell) -> None:
         self.h_cell.copy_(torch.as_tensor(np.asarray(cell, dtype=np.float32)).reshape(-1))
         self._have_grid = False   # a grid belongs to one cell
+
+    def calculate_with_stress(self, positions, cell=None) -> tp.Tuple[float, np.ndarray, np.ndarray]:
+        """(energy [Ha], forces (A, 3) [Ha/A], stress (3, 3) [Ha/A^3]) of a periodic system: the "f dot r"
+        virial of ase.py:164-168 accumulated by the force kernel, divided by the cell volume.  Runs the
+        step eagerly with a freshly built grid (the virial slots are not part of the captured graph)."""
+        if not self.pbc:
+            raise ValueError("the stress needs a periodic cell")
+        if cell is not None:
+            self.set_cell(cell)
+        if isinstance(positions, Tensor):
+            self.h_coords.copy_(positions.reshape(self.n, 3))
+        else:
+            self.h_coords.numpy()[...] = np.asarray(positions, dtype=np.float32).reshape(self.n, 3)
+        with torch.cuda.device(self.device):
+            self._copies_in(False)
+            res = self.engine.run(self.ws, True, want_grad=True, shard=self.shard, want_virial=True)
+            self._copies_out(False)
+            virial = res.virial.cpu()
+        self._have_grid = False
+        if int(self.h_status[0]):
+            self.engine.check_status(self.ws)
+        volume = abs(float(np.linalg.det(self.h_cell.numpy().reshape(3, 3).astype(np.float64))))
+        return float(self.h_energy[0]), np.negative(self.h_grad.numpy()), virial.numpy() / volume
 
     def calculate(self, positions, cell=None) -> tp.Tuple[float, np.ndarray]:
         """positions: (A, 3) float array on the host (Angstrom).  Returns (energy [Hartree],
@@ -110,11 +146,26 @@ class HostCalculator:
     def _run(self, reuse: bool) -> None:
         """One step (H2D, kernels, D2H, synchronise); after a few eager uses of a mode its whole sequence
         is captured into one CUDA graph."""
+        with torch.cuda.device(self.device):   # the C-ABI launches on the current device's stream
+            self._run_on_device(reuse)
+
+    def _run_on_device(self, reuse: bool) -> None:
         ws, eng = self.ws, self.engine
         self._mode_calls[reuse] += 1
         if not reuse:
             self.rebuilds += 1
         graph = self._graphs.get(reuse)
+        nccl_fallback = self.sharded is not None and self.sharded.world > 1 and self.sharded.mode == "nccl"
+        if nccl_fallback:
+            # peer memory could not be mapped: eager step, library all-reduce of the partials on the device
+            import torch.distributed as dist
+            self._copies_in(reuse)
+            eng.run(ws, self.pbc, want_grad=True, shard=self.shard, reuse=reuse)
+            dist.all_reduce(ws.grad, group=self.sharded.group)
+            dist.all_reduce(ws.energies, group=self.sharded.group)
+            self._copies_out(reuse)
+            torch.cuda.current_stream(self.device).synchronize()
+            return
         if graph is None and eng.cuda_graph and not eng.profile and self._mode_calls[reuse] > self.graph_after:
             rank, world = self.shard
             lo, hi = (self.n * rank) // world, (self.n * (rank + 1)) // world

@@ -390,6 +390,12 @@ class Workspace:
         self.atomic = torch.zeros(n, **f32)
         self.member_atomic = torch.zeros(num_members, n, **f32)
         self.energies = torch.zeros(n_conf, dtype=torch.float64, device=device)
+        # where the step's kernels ACCUMULATE forces / conformer energies: these buffers, or -- multi-GPU,
+        # parallel.ShardedEngine.attach -- partial-sum buffers in peer-mapped memory whose reduction over the
+        # ranks (reducer.launch, the last launch of the step) lands in `grad` / `energies`
+        self.grad_ptr = self.grad.data_ptr()
+        self.energies_ptr = self.energies.data_ptr()
+        self.reducer: tp.Any = None
         # distinct elements seen at graph-capture time (0 = not known): sizes the shared-memory gradient
         # table of the AEV backward kernel; the results never depend on it (Engine.note_composition)
         self.max_elements = 0
@@ -568,7 +574,7 @@ class Engine:
         if reuse:
             self._timed("prepare_step", lambda: L.ani_b200_verlet_positions(
                 1, ptr(ws.coords), ptr(ws.grid), ptr(ws.sorted_orig), n, self.skin, ptr(ws.spos), ptr(ws.ref_pos),
-                ptr(ws.ref_shift), ptr(ws.moved), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0,
+                ptr(ws.ref_shift), ptr(ws.moved), ws.grad_ptr if want_grad else None, 3 * n if want_grad else 0,
                 ptr(ws.aev_blocks), self.nets.ldx, st))
         else:
             self._timed("prepare_step", lambda: L.ani_b200_prepare_step(
@@ -577,7 +583,7 @@ class Engine:
                 ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges),
                 lo, hi, c.num_species, ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
                 ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
-                ptr(ws.aev_blocks), ptr(ws.grad) if want_grad else None, 3 * n if want_grad else 0,
+                ptr(ws.aev_blocks), ws.grad_ptr if want_grad else None, 3 * n if want_grad else 0,
                 ptr(ws.virial) if want_virial else None, ws.virial.numel() if want_virial else 0,
                 ptr(ws.scratch), ptr(ws.status), st))
             if self.skin > 0:
@@ -608,7 +614,7 @@ class Engine:
             return L.ani_b200_reduce_energies(
                 C.byref(self.nets.model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),
                 ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
-                ptr(ws.member_atomic), ptr(ws.energies), stream_handle)
+                ptr(ws.member_atomic), ws.energies_ptr, stream_handle)
 
         if not split:
             self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
@@ -636,11 +642,18 @@ class Engine:
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
                 ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
-                ptr(ws.grad), ptr(ws.status), ws.max_elements, ptr(ws.virial) if want_virial else None, st))
+                ws.grad_ptr, ptr(ws.status), ws.max_elements, ptr(ws.virial) if want_virial else None, st))
         if not split:
             self._timed("reduce_energies", lambda: reduce_on(st))
         else:
             main.wait_event(self._ev[3])
+        if ws.reducer is not None:
+            # multi-GPU: sum the partial forces / energies of all ranks over NVLink peer memory (one launch,
+            # part of the captured graph); without forces only the energies matter but the buffer is small
+            def reduce_all() -> int:
+                ws.reducer.launch(ws.grad, ws.energies)
+                return 0
+            self._timed("allreduce", reduce_all)
 
     def note_composition(self, ws: Workspace) -> None:
         """Before a graph capture (the shape has already run eagerly): read the element mask of the last

@@ -154,6 +154,12 @@ class ANI(torch.nn.Module):
     def to_infer_model(self, use_mnp: bool = False) -> "ANI":
         return self
 
+    def ase(self, overwrite: bool = False, stress_kind: str = "scaling", jit: bool = False, skin: float = 0.0):
+        """An ASE ``Calculator`` that uses this model (arch.py:219-241).  ``jit`` is accepted for interface
+        compatibility and ignored (the hot path is a CUDA graph already)."""
+        from .ase import Calculator
+        return Calculator(self, overwrite=overwrite, stress_kind=stress_kind, skin=skin)
+
     # -- fused engine ----------------------------------------------------------------------
     def engine(self, device: torch.device) -> Engine:
         nets = self.neural_networks.packed(device)
@@ -376,40 +382,88 @@ def from_weight_lists(kind: str, weights, device=None, neighborlist: Neighborlis
     return model.to(device) if device is not None else model
 
 
+def aev_computer_from_torchani(aevr, neighborlist: NeighborlistArg = "cell_list") -> AEVComputer:
+    """``torchani.aev.AEVComputer`` (standard ANIRadial / ANIAngular terms, cosine or smooth cutoff:
+    what its own ``_check_cuaev_avail`` accepts, aev/_computer.py:151-168) -> the B200 module with the
+    same constants."""
+    cutoff_fn = getattr(aevr, "_cuaev_cutoff_fn", "") or getattr(aevr.radial.cutoff_fn, "_cuaev_name", "") or ""
+    if cutoff_fn not in ("cosine", "smooth"):
+        raise ValueError("only the cosine and smooth(order=2, eps=1e-10) cutoffs are supported")
+    return AEVComputer.from_constants(
+        aevr.radial.cutoff, aevr.angular.cutoff, float(aevr.radial.eta), aevr.radial.shifts.tolist(),
+        float(aevr.angular.eta), float(aevr.angular.zeta), aevr.angular.shifts.tolist(),
+        aevr.angular.sections.tolist(), aevr.num_species, cutoff_fn=cutoff_fn, neighborlist=neighborlist)
+
+
+def networks_from_torchani(netr) -> AtomicContainer:
+    """``torchani.nn.Ensemble`` / ``ANINetworks`` / ``BmmEnsemble`` (nn/_containers.py:319-660,
+    nn/_infer.py:61-216) -> the B200 container with the same weights and active members."""
+    first = next(iter(netr.atomics.values())) if hasattr(netr, "atomics") else None
+    # (BmmEnsemble does not carry atomic_numbers: the keys of `atomics` are the symbols everywhere)
+    symbols = tuple(netr.atomics.keys()) if first is not None else tuple(netr.members[0].atomics.keys())
+    per_member: tp.List[tp.Dict[str, tp.List[tp.Tuple[Tensor, tp.Optional[Tensor]]]]] = []
+    if hasattr(netr, "members"):
+        for rm in netr.members:
+            per_member.append({s: [(l.weight, l.bias) for l in list(rm.atomics[s].layers) + [rm.atomics[s].final_layer]]
+                               for s in symbols})
+    elif first is not None and hasattr(first, "_num_batched_networks"):
+        # BmmAtomicNetwork: weights stacked as (members, in, out), biases (members, 1, out)
+        for m in range(int(first._num_batched_networks)):
+            per_member.append({s: [(l.weight[m].t(), l.bias[m, 0] if l._beta else None)
+                                   for l in list(netr.atomics[s].layers) + [netr.atomics[s].final_layer]]
+                               for s in symbols})
+    else:
+        per_member.append({s: [(l.weight, l.bias) for l in list(netr.atomics[s].layers) + [netr.atomics[s].final_layer]]
+                           for s in symbols})
+    members = []
+    for layers in per_member:
+        mods = {}
+        for s in symbols:
+            dims = [layers[s][0][0].shape[1]] + [w.shape[0] for w, _ in layers[s]]
+            an = AtomicNetwork(dims)
+            with torch.no_grad():
+                for (w_dst, b_dst), (w, b) in zip(an.linear_pairs(), layers[s]):
+                    if b is None:
+                        raise ValueError("bias-free networks are not supported")
+                    w_dst.copy_(w)
+                    b_dst.copy_(b)
+            mods[s] = an
+        members.append(ANINetworks(mods))
+    nets: AtomicContainer = Ensemble(members) if len(members) > 1 else members[0]
+    if hasattr(netr, "members"):
+        nets.set_active_members(list(netr.active_members_idxs))
+    nets.requires_grad_(False)
+    return nets
+
+
 def from_torchani(ref_model, device=None) -> ANI:
     """Convert a ``torchani.arch.ANI`` instance (reference, e.g. ``torchani.models.ANI2x()``) into
     the B200 model: same symbols, AEV constants, network weights and self energies."""
     aevr = ref_model.potentials["nnp"].aev_computer
     netr = ref_model.potentials["nnp"].neural_networks
-    symbols = tuple(netr.symbols)
-    cutoff_fn = getattr(aevr.radial.cutoff_fn, "_cuaev_name", "") or ""
-    if cutoff_fn not in ("cosine", "smooth"):
-        raise ValueError("only the cosine and smooth(order=2, eps=1e-10) cutoffs are supported")
-    aevc = AEVComputer.from_constants(
-        aevr.radial.cutoff, aevr.angular.cutoff, float(aevr.radial.eta), aevr.radial.shifts.tolist(),
-        float(aevr.angular.eta), float(aevr.angular.zeta), aevr.angular.shifts.tolist(),
-        aevr.angular.sections.tolist(), aevr.num_species, cutoff_fn=cutoff_fn)
-    ref_members = list(netr.members) if hasattr(netr, "members") else [netr]
-    members = []
-    for rm in ref_members:
-        mods = {}
-        for s in symbols:
-            ra = rm.atomics[s]
-            lins = list(ra.layers) + [ra.final_layer]
-            dims = [lins[0].in_features] + [l.out_features for l in lins]
-            an = AtomicNetwork(dims)
-            with torch.no_grad():
-                for (w_dst, b_dst), l in zip(an.linear_pairs(), lins):
-                    if l.bias is None:
-                        raise ValueError("bias-free networks are not supported")
-                    w_dst.copy_(l.weight)
-                    b_dst.copy_(l.bias)
-            mods[s] = an
-        members.append(ANINetworks(mods))
-    nets: AtomicContainer = Ensemble(members) if len(members) > 1 else members[0]
-    nets.set_active_members(list(netr.active_members_idxs))
+    symbols = tuple(ref_model.symbols)
+    aevc = aev_computer_from_torchani(aevr)
+    nets = networks_from_torchani(netr)
     sae = SelfEnergy(symbols, ref_model.energy_shifter.self_energies.double().tolist())
     sae._enabled = bool(ref_model.energy_shifter._enabled)
     model = ANI(symbols, aevc, nets, sae, ref_model.periodic_table_index)
     model.requires_grad_(False)
-    return model.to(device) if device is not None else model
+    if device is None:
+        device = ref_model.energy_shifter.self_energies.device
+    return model.to(device)
+
+
+def accelerate_torchani_(ref_model):
+    """Swap the B200 modules INTO an existing ``torchani.arch.ANI`` in place -- its three plug-in points
+    (arch.py:116-127, 208-217, 264-275): ``model.neighborlist``, ``model.potentials["nnp"].aev_computer`` and
+    ``model.potentials["nnp"].neural_networks`` -- and return it.  Everything else of the reference model
+    (species converter, energy shifter, extra pair potentials, its ``forward`` / ``compute_from_neighbors``
+    / ``ase()``) keeps running unchanged on top of them; CUDA float32 only."""
+    nnp = ref_model.potentials["nnp"]
+    dev = ref_model.energy_shifter.self_energies.device
+    aevc = aev_computer_from_torchani(nnp.aev_computer).to(dev)
+    nets = networks_from_torchani(nnp.neural_networks).to(dev)
+    nnp.aev_computer = aevc
+    nnp.neural_networks = nets
+    ref_model.neighborlist = aevc.neighborlist
+    return ref_model
