@@ -58,6 +58,7 @@ extern "C" {
 #define ANI_STATUS_PAIR_OVERFLOW 8  /* half neighbour list exceeds the caller's capacity */
 #define ANI_VIRIAL_SLOTS 64         /* partial virial sums (ani_b200_aev_backward)          */
 #define ANI_STATUS_OPERAND_RANGE 16 /* a value left the range of the half-precision GEMM operand pieces */
+#define ANI_STATUS_INTERNAL 32      /* a device-side barrier / dependency wait timed out (never expected) */
 
 #define ANI_MAX_ANG 96 /* angular neighbours (<= Rca) one central atom may have */
 
@@ -193,6 +194,18 @@ int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, const float
                            int64_t num_pairs, int n, int nbr_cap, int32_t* row_start,
                            int32_t* row_j, float* row_d, int32_t* scratch_i32, int32_t* status,
                            void* stream);
+/* 4c. FULL neighbour list with ghost atoms, as MD engines hand it over (LAMMPS pair style, pmemd): replaces   */
+/*    cuaev::run_with_full_nbrlist (csrc/cuaev.cpp:225-246, csrc/aev.cu:1048-1126,1868-1956;                      */
+/*    aev/_computer.py:409-438).  coords f32[n_all][3] hold local AND ghost atoms (ghosts at their image          */
+/*    positions, no cell), ilist i32[n_i] the atoms whose AEV is wanted, numneigh i32[n_i] their neighbour         */
+/*    counts, jlist i32[sum numneigh] the neighbours of ilist[0], ilist[1], ... one after the other (built with    */
+/*    cutoff + skin: entries beyond `cutoff` are screened out here).  Output: the per-atom rows of 4b              */
+/*    (row_start i32[n_all+1], row_j / row_d with capacity sum(numneigh)); atoms not in ilist get empty rows, i.e.  */
+/*    all-zero AEVs, as in the reference.  scratch i32[n_all + n_i + 1].  Feed the result to                         */
+/*    ani_b200_aev_forward_rows / _backward_rows (gradients reach local and ghost coordinates alike).                */
+int ani_b200_full_nbrlist_to_rows(const float* coords, int n_all, const int32_t* ilist, const int32_t* numneigh,
+                                  const int32_t* jlist, int n_i, float cutoff, int nbr_cap, int32_t* row_start,
+                                  int32_t* row_j, float* row_d, int32_t* scratch_i32, int32_t* status, void* stream);
 int ani_b200_aev_forward_rows(const ani_aev_params* params, const ani_grid* grid, const float* spos,
                               const int32_t* row_start, const int32_t* row_j, const float* row_d,
                               int n, const int32_t* row_of, float* aev, int ldx, int layout,
@@ -223,11 +236,13 @@ int ani_b200_verlet_positions(int mode, const float* coords, const ani_grid* gri
                               float* ref_shift, int32_t* moved, float* zero_f32, int zero_f32_count,
                               int32_t* aev_blocks, int ldx, void* stream);
 
-/* 3b. Fused per-step preparation: build_cells + species_layout + active_aev_blocks in five       */
-/*     launches instead of twelve (same outputs, same determinism; what the fused engine calls).   */
+/* 3b. Fused per-step preparation: build_cells + species_layout + active_aev_blocks in ONE launch     */
+/*     (a persistent grid with device-wide barriers between its five phases) instead of twelve       */
+/*     (same outputs, same determinism; what the fused engine calls).                                 */
 /*     Also zero-fills zero_f32[0..count) (the force accumulator) and zero_f64[0..count) (the      */
 /*     conformer energies) so that no separate memset launches are needed.                          */
-/*     scratch_i32: 3 n + max_bins + 4 + (ceil((hi-lo)/256) + 2) * ANI_MAX_SPECIES + 16 ints.       */
+/*     scratch_i32: 3 n + max_bins + 4 + (ceil((hi-lo)/256) + 2) * ANI_MAX_SPECIES + 32 ints, ZERO at           */
+/*     allocation (two of them are the state of the device-wide barrier of the single-launch preparation).     */
 int ani_b200_prepare_step(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
                           const float* cell, int pbc, int mode, float cutoff, int max_bins, ani_grid* grid,
                           int32_t* bin_start, int32_t* sorted_orig, int32_t* orig_to_sorted, float* spos,
@@ -337,6 +352,15 @@ int ani_b200_zero_live_blocks(const ani_mlp_model* model, float* dx, const int32
 int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int rows_cap, const int32_t* row_atom,
                           const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2,
                           void* act3, int dx_zeroed, int32_t* status, void* stream);
+
+/*    The same six GEMMs as ONE persistent launch (csrc/gemm_fused.cuh): the (layer, row tile, member, column      */
+/*    tile) units form one list and the launch boundaries are replaced by data-flow waits on per-(layer, row tile)   */
+/*    completion counters -- no ramp / tail per layer, one tile-count quantisation for the whole step, and at small   */
+/*    row counts (multi-GPU shards) no per-launch floor.  sync_i32: 6 * (rows_cap / 128) ints of scratch (zeroed by    */
+/*    the call).  Same arguments and results as ani_b200_mlp_forward_backward otherwise.                               */
+int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, float* dx, int rows_cap, const int32_t* row_atom,
+                      const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2, void* act3,
+                      float* e_member, int want_backward, int32_t* sync_i32, int32_t* status, void* stream);
 
 /* 7. Scatter per-member atomic energies back to input order and reduce per conformer.      */
 /*      atomic_out f32[n] (mean over active members, 0 for padding; flat input order)         */

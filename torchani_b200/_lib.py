@@ -27,6 +27,7 @@ STATUS_ANG_OVERFLOW = 2
 STATUS_CELL_TOO_SMALL = 4
 STATUS_PAIR_OVERFLOW = 8
 STATUS_OPERAND_RANGE = 16
+STATUS_INTERNAL = 32
 
 
 class AEVParams(C.Structure):
@@ -78,6 +79,7 @@ _PROTOTYPES = {
     "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
     "ani_b200_pairs_to_rows": (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ani_b200_full_nbrlist_to_rows": (C.c_int, [_P, _I, _P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P]),
     "ani_b200_aev_forward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "ani_b200_aev_backward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "ani_b200_prepare_step": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, C.c_float, _I, _P, _P, _P, _P, _P, _P, _P,
@@ -87,6 +89,7 @@ _PROTOTYPES = {
     "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "ani_b200_half_neighbor_fill": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "ani_b200_mlp_step": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "ani_b200_mlp_forward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ani_b200_zero_live_blocks": (C.c_int, [_P, _P, _P, _P, _P]),
     "ani_b200_mlp_backward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),

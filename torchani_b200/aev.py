@@ -185,6 +185,62 @@ class _AEVFromNeighbors(torch.autograd.Function):
         return grad.view(n_conf, n_per_conf, 3), None, None, None, None
 
 
+class _AEVFromFullList(torch.autograd.Function):
+    """AEVs of the atoms in ``ilist`` from a full neighbour list over local + ghost atoms (MD-engine format);
+    gradient to all coordinates (csrc/cuaev.cpp:225-246)."""
+
+    @staticmethod
+    def forward(ctx, coords: Tensor, species: Tensor, ilist: Tensor, jlist: Tensor, numneigh: Tensor,
+                computer: "AEVComputer") -> Tensor:
+        consts = computer.constants
+        dev = coords.device
+        n = species.shape[1]
+        i32 = dict(dtype=torch.int32, device=dev)
+        spos = torch.zeros(n, 4, dtype=torch.float32, device=dev)
+        spos[:, 3] = species.reshape(-1).to(torch.int32).view(torch.float32)
+        grid = torch.zeros(C.sizeof(_lib.Grid) // 4, **i32)
+        grid[_lib.Grid.n_real.offset // 4] = n
+        ident = torch.arange(n, **i32)
+        il, jl, nn_ = (t.to(torch.int32).contiguous() for t in (ilist, jlist, numneigh))
+        n_i, cap_rows = int(il.shape[0]), max(int(jl.shape[0]), 1)
+        row_start = torch.zeros(n + 1, **i32)
+        row_j = torch.zeros(cap_rows, **i32)
+        row_d = torch.zeros(cap_rows, 4, dtype=torch.float32, device=dev)
+        scratch = torch.zeros(n + n_i + 2, **i32)
+        status = torch.zeros(1, **i32)
+        xyz = coords.detach().reshape(-1, 3).to(torch.float32).contiguous()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        L = _lib.lib()
+        params = computer._params()
+        cap = computer.nbr_cap
+        check(L.ani_b200_full_nbrlist_to_rows(ptr(xyz), n, ptr(il), ptr(nn_), ptr(jl), n_i, consts.rcr, cap,
+                                              ptr(row_start), ptr(row_j), ptr(row_d), ptr(scratch), ptr(status), st),
+              "full_nbrlist_to_rows")
+        out = torch.zeros(n, consts.out_dim, dtype=torch.float32, device=dev)
+        check(L.ani_b200_aev_forward_rows(C.byref(params), ptr(grid), ptr(spos), ptr(row_start), ptr(row_j),
+                                          ptr(row_d), n, ptr(ident), ptr(out), consts.out_dim, 0, cap, ptr(status),
+                                          st), "aev_forward_rows")
+        ctx.saved = (grid, spos, ident, row_start, row_j, row_d, status)
+        ctx.computer, ctx.n = computer, n
+        computer._last_status = status
+        return out.view(1, n, consts.out_dim)
+
+    @staticmethod
+    def backward(ctx, grad_aev: Tensor):
+        grid, spos, ident, row_start, row_j, row_d, status = ctx.saved
+        computer, n = ctx.computer, ctx.n
+        consts = computer.constants
+        g = grad_aev.reshape(n, consts.out_dim).to(torch.float32).contiguous()
+        grad = torch.zeros(n, 3, dtype=torch.float32, device=g.device)
+        st = torch.cuda.current_stream(g.device).cuda_stream
+        params = computer._params()
+        check(_lib.lib().ani_b200_aev_backward_rows(C.byref(params), ptr(grid), ptr(spos), ptr(ident), ptr(row_start),
+                                                    ptr(row_j), ptr(row_d), n, ptr(ident), ptr(g), consts.out_dim,
+                                                    computer.nbr_cap, ptr(grad), ptr(status), st),
+              "aev_backward_rows")
+        return grad.view(1, n, 3), None, None, None, None, None
+
+
 class AEVComputer(torch.nn.Module):
     r"""Computes atomic environment vectors on a B200 (interface of aev/_computer.py:42-272).
 
@@ -300,6 +356,35 @@ class AEVComputer(torch.nn.Module):
         if code & _lib.STATUS_ANG_OVERFLOW:
             raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within the angular cutoff")
         return aev
+
+    def compute_from_full_neighborlist(self, elem_idxs: Tensor, coords: Tensor, ilist_unique: Tensor, jlist: Tensor,
+                                       numneigh: Tensor) -> Tensor:
+        r"""AEVs from a FULL neighbour list with ghost atoms, the format MD engines (LAMMPS, pmemd) hand over --
+        the reference's ``_compute_cuaev_with_full_nbrlist`` (aev/_computer.py:409-438 ->
+        ``cuaev::run_with_full_nbrlist``, csrc/aev.cu:1048-1126,1868-1956):
+
+        * ``elem_idxs (1, A)`` / ``coords (1, A, 3)`` hold local AND ghost atoms (ghosts at their image positions),
+        * ``ilist_unique (nI,)`` the atoms whose AEV is wanted, ``numneigh (nI,)`` their neighbour counts,
+          ``jlist (sum numneigh,)`` the neighbours of ``ilist[0], ilist[1], ...`` one after the other (indices into
+          the A atoms; a list built with cutoff + skin is screened with the true cutoff here).
+
+        Returns ``(1, A, out_dim)``: rows of ``ilist`` atoms filled, all others zero; autograd reaches the
+        coordinates of local and ghost atoms alike (the MD engine folds ghost forces back).  Single molecule only,
+        as the reference."""
+        if coords.shape[0] != 1:
+            raise ValueError("cuAEV with full neighborlist doesn't support batches")
+        assert elem_idxs.dim() == 2 and coords.shape == (1, elem_idxs.shape[1], 3)
+        if coords.device.type != "cuda":
+            raise ValueError("torchani_b200 runs on CUDA tensors only (there is no CPU path)")
+        aev = _AEVFromFullList.apply(coords, elem_idxs, ilist_unique, jlist, numneigh, self)
+        code = int(self._last_status.item())
+        if code & _lib.STATUS_NBR_OVERFLOW:
+            raise RuntimeError(f"an atom has more than nbr_cap={self.nbr_cap} neighbours in the given list")
+        if code & _lib.STATUS_ANG_OVERFLOW:
+            raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within the angular cutoff")
+        return aev
+
+    _compute_cuaev_with_full_nbrlist = compute_from_full_neighborlist   # the reference's (private) name
 
     # -- constructors (aev/_computer.py:498-666) -------------------------------------------
     @classmethod

@@ -1471,6 +1471,40 @@ __global__ void k_row_overflow(const int32_t* __restrict__ start, int n, int cap
   if (i < n && start[i + 1] - start[i] > cap) atomicOr(status, ANI_STATUS_NBR_OVERFLOW);
 }
 
+
+// ---- full neighbour list with ghost atoms (LAMMPS / pmemd style) -> per-atom rows -------------------
+// ilist[g] = a local atom, its numneigh[g] neighbours follow each other in jlist (built by the MD engine with
+// cutoff + skin, ghost atoms are ordinary entries of coords at their image positions): screen with the true
+// cutoff and compact (csrc/aev.cu:1048-1126 postProcessNbrList2 of the reference).  Thread per local atom.
+template <bool FILL>
+__global__ void k_full_list_rows(const float* __restrict__ coords, const int32_t* __restrict__ ilist,
+                                 const int32_t* __restrict__ jstart, const int32_t* __restrict__ jlist, int n_i,
+                                 int n_all, float rcr, int32_t* __restrict__ counts,
+                                 const int32_t* __restrict__ row_start, int32_t* __restrict__ row_j,
+                                 float4* __restrict__ row_d) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_i) return;
+  const int i = ilist[g];
+  if (i < 0 || i >= n_all) return;
+  const float xi = coords[3 * i], yi = coords[3 * i + 1], zi = coords[3 * i + 2];
+  const float r2c = rcr * rcr;
+  int out = FILL ? row_start[i] : 0, cnt = 0;
+  for (int e = jstart[g]; e < jstart[g + 1]; ++e) {
+    const int j = jlist[e];
+    if (j < 0 || j >= n_all || j == i) continue;
+    const float dx = coords[3 * j] - xi, dy = coords[3 * j + 1] - yi, dz = coords[3 * j + 2] - zi;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 > r2c) continue;
+    if (FILL) {
+      row_j[out] = j;
+      row_d[out] = make_float4(dx, dy, dz, sqrtf(r2));
+      ++out;
+    }
+    ++cnt;
+  }
+  if (!FILL) counts[i] = cnt;
+}
+
 }  // namespace ani
 
 using namespace ani;
@@ -1517,6 +1551,31 @@ extern "C" int ani_b200_pairs_to_rows(const int64_t* idx0, const int64_t* idx1, 
     k_pairs_fill<<<pb, 256, 0, st>>>(idx0, idx1, diff_vectors, (long long)num_pairs, row_start, cursor, row_j,
                                      reinterpret_cast<float4*>(row_d));
   k_row_overflow<<<(n + 255) / 256, 256, 0, st>>>(row_start, n, nbr_cap, status);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+extern "C" int ani_b200_full_nbrlist_to_rows(const float* coords, int n_all, const int32_t* ilist,
+                                             const int32_t* numneigh, const int32_t* jlist, int n_i, float cutoff,
+                                             int nbr_cap, int32_t* row_start, int32_t* row_j, float* row_d,
+                                             int32_t* scratch_i32, int32_t* status, void* stream) {
+  if (!coords || !row_start || !row_j || !row_d || !scratch_i32 || !status || n_all < 1 || n_i < 0 || cutoff <= 0.f)
+    return ANI_ERR_BAD_ARG;
+  if (n_i > 0 && (!ilist || !numneigh || !jlist)) return ANI_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t* counts = scratch_i32;               // [n_all]
+  int32_t* jstart = scratch_i32 + n_all;       // [n_i + 1]
+  cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)n_all, st);
+  k_scan_i32<<<1, 1024, 0, st>>>(numneigh, n_i, jstart);
+  const int nb = (n_i + 127) / 128;
+  if (n_i > 0)
+    k_full_list_rows<false><<<nb, 128, 0, st>>>(coords, ilist, jstart, jlist, n_i, n_all, cutoff, counts, nullptr,
+                                                nullptr, nullptr);
+  k_scan_i32<<<1, 1024, 0, st>>>(counts, n_all, row_start);
+  if (n_i > 0)
+    k_full_list_rows<true><<<nb, 128, 0, st>>>(coords, ilist, jstart, jlist, n_i, n_all, cutoff, nullptr, row_start,
+                                               row_j, reinterpret_cast<float4*>(row_d));
+  k_row_overflow<<<(n_all + 255) / 256, 256, 0, st>>>(row_start, n_all, nbr_cap, status);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

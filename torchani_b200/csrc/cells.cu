@@ -1,6 +1,8 @@
 // Bucket grid construction: wrap atoms into the cell, assign buckets, stable counting sort,
 // species-grouped row layout for the MLP.  Replaces the ATen op chain of
 // neighbors.py:418-507,554-615 / csrc/cell_list.cpp:266-350 with five small sync-free kernels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ani {
@@ -738,6 +740,298 @@ __global__ void __launch_bounds__(1024) k_prep_layout(const __grid_constant__ Pr
 }
 
 // ---------------------------------------------------------------------------------------
+// The same five phases as ONE launch: a persistent grid (every block resident) that separates the
+// phases with a device-wide barrier instead of a launch boundary -- the preparation is pure dependency
+// latency (40 blocks of work at 10 k atoms), so five launch boundaries were most of its 35-44 us.
+// The barrier is self-resetting (arrival counter + epoch word in the scratch area, zero at allocation):
+// the last block to arrive clears the counter and advances the epoch, the others spin on the epoch.  A
+// bounded spin raises ANI_STATUS_INTERNAL instead of hanging the GPU if the state is ever corrupted.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(int32_t* bar, int32_t* status) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile int32_t* epoch = bar + 1;
+    const int e = *epoch;
+    __threadfence();
+    if (atomicAdd(bar, 1) == (int)gridDim.x - 1) {
+      bar[0] = 0;
+      __threadfence();
+      atomicExch(bar + 1, e + 1);
+    } else {
+      const long long t0 = clock64();
+      while (*epoch == e) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s
+          atomicOr(status, ANI_STATUS_INTERNAL);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ PrepArgs A, int32_t* bar, int zeroed) {
+  __shared__ ani_grid sg;
+  __shared__ int s_warp[8];
+  __shared__ int s_carry;
+  __shared__ int s_tot[ANI_MAX_SPECIES];
+  __shared__ int s_base[ANI_MAX_SPECIES + 1];
+  __shared__ int s_slab[128 * ANI_MAX_SPECIES];
+  __shared__ int s_wcnt[LAYOUT_CHUNK / 32][ANI_MAX_SPECIES];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int gstride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int n = A.n, S = A.S;
+  // ---- phase 0: the grid (every block computes its own copy) + zero-fill of the counters
+  if (tid == 0) {
+    if (A.inline_setup) {
+      const float none[3] = {0.f, 0.f, 0.f};
+      sg = compute_grid(A.n_conf, A.n_per_conf, A.cell, A.pbc, A.mode, A.cutoff, A.max_bins, none, none, A.status);
+      if (blockIdx.x == 0) *A.grid = sg;
+    } else {
+      sg = *A.grid;  // written by k_grid_setup (bounding box of an open system)
+    }
+  }
+  for (int k = gtid; k < zeroed; k += gstride) A.bin_count[k] = 0;
+  grid_barrier(bar, A.status);
+  // ---- phase 1: bucket of every atom, slot inside the bucket by atomics
+  for (int a = gtid; a < n; a += gstride) {
+    int bin;
+    if (A.species[a] < 0) {
+      bin = sg.nbins;  // padding atoms: trash bucket, never a neighbour, never a centre
+    } else {
+      float3 p;
+      wrapped_position(sg, A.coords, a, p, bin);
+    }
+    A.bin_of[a] = bin;
+    A.slot[a] = atomicAdd(&A.bin_count[bin], 1);
+  }
+  grid_barrier(bar, A.status);
+  // ---- phase 1b: block 0 scans the bucket counts (exclusive) -> bin_start, n_real
+  if (blockIdx.x == 0) {
+    const int m = sg.nbins + 1;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += blockDim.x) {
+      const int i = base + tid;
+      const int v = (i < m) ? __ldcg(&A.bin_count[i]) : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(ANI_FULL_MASK, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_warp[w] = x;
+      __syncthreads();
+      if (w == 0) {
+        int t = (lane < 8) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          const int y = __shfl_up_sync(ANI_FULL_MASK, t, o);
+          if (lane >= o) t += y;
+        }
+        if (lane < 8) s_warp[lane] = t;
+      }
+      __syncthreads();
+      const int incl = x + ((w == 0) ? 0 : s_warp[w - 1]) + s_carry;
+      if (i < m) A.bin_start[i] = incl - v;
+      __syncthreads();
+      if (tid == blockDim.x - 1) s_carry = incl;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      A.bin_start[m] = s_carry;
+      A.grid->n_real = s_carry - __ldcg(&A.bin_count[m - 1]);  // everything before the trash bucket
+    }
+  }
+  grid_barrier(bar, A.status);
+  const int n_real = __ldcg(&A.grid->n_real);
+  // ---- phase 2: scatter into buckets + per-bucket table of the 27 neighbouring buckets
+  {
+    const long long t2 = A.ranges ? max((long long)n, (long long)sg.nbins * 27) : (long long)n;
+    for (long long idx = gtid; idx < t2; idx += gstride) {
+      if (idx < n) A.tmp_list[__ldcg(&A.bin_start[A.bin_of[idx]]) + A.slot[idx]] = (int)idx;
+      if (!A.ranges || sg.mode != 0) continue;
+      const int b = (int)(idx / 27), o = (int)(idx % 27);
+      if (b >= sg.nbins) continue;
+      const int iz = b % sg.dims[2], iy = (b / sg.dims[2]) % sg.dims[1], ix = b / (sg.dims[2] * sg.dims[1]);
+      int j[3] = {ix + o / 9 - 1, iy + (o / 3) % 3 - 1, iz + o % 3 - 1};
+      int wv[3];
+      for (int d = 0; d < 3; ++d) {
+        wv[d] = 0;
+        if (j[d] < 0) {
+          wv[d] = -1;
+          j[d] += sg.dims[d];
+        } else if (j[d] >= sg.dims[d]) {
+          wv[d] = 1;
+          j[d] -= sg.dims[d];
+        }
+      }
+      const bool exists = sg.pbc || !(wv[0] | wv[1] | wv[2]);
+      int lo = 0, hi = 0;
+      const int code = (wv[0] + 1) * 9 + (wv[1] + 1) * 3 + (wv[2] + 1);
+      if (exists) {
+        const int nb = (j[0] * sg.dims[1] + j[1]) * sg.dims[2] + j[2];
+        lo = __ldcg(&A.bin_start[nb]);
+        hi = __ldcg(&A.bin_start[nb + 1]);
+      }
+      const float wx = (float)wv[0], wy = (float)wv[1], wz = (float)wv[2];
+      A.ranges[2 * (size_t)idx] = make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), 0.f);
+      A.ranges[2 * (size_t)idx + 1] = make_float4(wx * sg.cell[0] + wy * sg.cell[3] + wz * sg.cell[6],
+                                                  wx * sg.cell[1] + wy * sg.cell[4] + wz * sg.cell[7],
+                                                  wx * sg.cell[2] + wy * sg.cell[5] + wz * sg.cell[8], 0.f);
+    }
+  }
+  grid_barrier(bar, A.status);
+  // ---- phase 3: deterministic (species, input index) order inside buckets, sorted arrays, per-chunk species
+  //      histogram, element presence mask, zero-fill of the force accumulator
+  {
+    const int hi_real = min(A.hi, n_real);
+    unsigned mask = 0;
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gstride) {  // warp-uniform trip count
+      const int a = base + tid;
+      int sp = -1;
+      if (a < n) {
+        const int b = A.bin_of[a];
+        const int lo = __ldcg(&A.bin_start[b]), hi = __ldcg(&A.bin_start[b + 1]);
+        const int spa = A.species[a];
+        int rank = 0;
+        for (int e = lo; e < hi; ++e) {
+          const int t = __ldcg(&A.tmp_list[e]);
+          const int spt = A.species[t];
+          rank += (spt < spa) || (spt == spa && t < a);
+        }
+        const int i = lo + rank;
+        A.sorted_orig[i] = a;
+        A.orig_to_sorted[a] = i;
+        A.sbin[i] = b;
+        float3 p = make_float3(0.f, 0.f, 0.f);
+        sp = spa;
+        if (sp >= 0) {
+          int bb;
+          wrapped_position(sg, A.coords, a, p, bb);
+        }
+        A.spos[i] = make_float4(p.x, p.y, p.z, __int_as_float(sp));
+        if (sp >= 0 && i >= A.lo && i < hi_real)
+          atomicAdd(&A.chunk_hist[((i - A.lo) / LAYOUT_CHUNK) * ANI_MAX_SPECIES + sp], 1);
+      }
+      for (int s = 0; s < ANI_MAX_SPECIES; ++s)
+        if (__any_sync(ANI_FULL_MASK, sp == s)) mask |= 1u << s;
+    }
+    if (lane == 0 && mask) atomicOr(A.present, (int)mask);
+    if (A.zero_f32)
+      for (int k = gtid; k < A.zero_f32_count; k += gstride) A.zero_f32[k] = 0.f;
+  }
+  grid_barrier(bar, A.status);
+  // ---- phase 4: block 0: chunk scan, species row bases, tile table, live AEV column blocks;
+  //      every block: row_atom = -1
+  for (int r = gtid; r < A.rows_cap; r += gstride) A.row_atom[r] = -1;
+  if (blockIdx.x == 0) {
+    if (w == 7) {
+      const unsigned mask = (unsigned)__ldcg(A.present);
+      const int RL = S * A.n_shf_r;
+      int count = 0;
+      for (int b0 = 0; b0 < A.ldx / 32; b0 += 32) {
+        const int b = b0 + lane;
+        bool active = false;
+        if (b < A.ldx / 32) {
+          for (int c = b * 32; c < b * 32 + 32 && c < A.out_dim && !active;
+               c = (c < RL) ? c + 1 : RL + ((c - RL) / A.angular_sub + 1) * A.angular_sub) {
+            if (c < RL) {
+              active = (mask >> (c / A.n_shf_r)) & 1u;
+            } else {
+              int s1 = 0, rem = (c - RL) / A.angular_sub;
+              while (rem >= S - s1) {
+                rem -= S - s1;
+                ++s1;
+              }
+              active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
+            }
+          }
+        }
+        const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
+        if (active) A.blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
+        count += __popc(live);
+      }
+      if (lane == 0) {
+        A.blocks[0] = count;
+        A.blocks[A.ldx / 32 + 2] = (A.blocks[A.ldx / 32 + 1] != (int)mask);
+        A.blocks[A.ldx / 32 + 1] = (int)mask;
+      }
+    }
+    int run = 0;
+    for (int c0 = 0; c0 < A.n_chunks; c0 += 128) {
+      const int nc = min(128, A.n_chunks - c0);
+      for (int k = tid; k < nc * ANI_MAX_SPECIES; k += blockDim.x) s_slab[k] = __ldcg(&A.chunk_hist[c0 * ANI_MAX_SPECIES + k]);
+      __syncthreads();
+      if (tid < S) {
+        for (int c = 0; c < nc; ++c) {
+          const int v = s_slab[c * ANI_MAX_SPECIES + tid];
+          s_slab[c * ANI_MAX_SPECIES + tid] = run;
+          run += v;
+        }
+      }
+      __syncthreads();
+      for (int k = tid; k < nc * ANI_MAX_SPECIES; k += blockDim.x) A.chunk_hist[c0 * ANI_MAX_SPECIES + k] = s_slab[k];
+      __syncthreads();
+    }
+    if (tid < S) s_tot[tid] = run;
+    __syncthreads();
+    if (tid == 0) {
+      int row = 0, owned = 0;
+      for (int s = 0; s < S; ++s) {
+        s_base[s] = row;
+        A.species_base[s] = row;
+        owned += s_tot[s];
+        row += (s_tot[s] + ANI_TILE_ROWS - 1) / ANI_TILE_ROWS * ANI_TILE_ROWS;
+      }
+      s_base[S] = row;
+      A.layout_info[0] = row / ANI_TILE_ROWS;
+      A.layout_info[1] = row;
+      A.layout_info[2] = owned;
+      A.layout_info[3] = 0;
+      for (int s = 0; s <= S; ++s) A.layout_info[4 + s] = s_base[s] / ANI_TILE_ROWS;
+      for (int s = S + 1; s <= ANI_MAX_SPECIES; ++s) A.layout_info[4 + s] = row / ANI_TILE_ROWS;
+    }
+    __syncthreads();
+    const int n_tiles_cap = A.rows_cap / ANI_TILE_ROWS;
+    for (int t = tid; t < n_tiles_cap; t += blockDim.x) {
+      const int r = t * ANI_TILE_ROWS;
+      int sp = -1;
+      for (int s = 0; s < S; ++s)
+        if (r >= s_base[s] && r < s_base[s + 1] && r < s_base[s] + s_tot[s]) sp = s;
+      A.tile_species[t] = sp;
+    }
+    if (A.zero_f64)
+      for (int k = tid; k < A.zero_f64_count; k += blockDim.x) A.zero_f64[k] = 0.0;
+  }
+  grid_barrier(bar, A.status);
+  // ---- phase 5: row assignment, one 256-atom chunk of the owned sorted slice at a time
+  {
+    const int hi_real = min(A.hi, n_real);
+    for (int c = blockIdx.x; c < A.n_chunks; c += gridDim.x) {
+      const int i = A.lo + c * LAYOUT_CHUNK + tid;
+      const int sp = (i < hi_real) ? __float_as_int(__ldcg(&A.spos[i]).w) : -1;
+      int my_rank = 0;
+      for (int s = 0; s < S; ++s) {
+        const unsigned m = __ballot_sync(ANI_FULL_MASK, sp == s);
+        if (sp == s) my_rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_wcnt[w][s] = __popc(m);
+      }
+      __syncthreads();
+      if (sp >= 0) {
+        int off = 0;
+        for (int ww = 0; ww < w; ++ww) off += s_wcnt[ww][sp];
+        const int row = __ldcg(&A.species_base[sp]) + __ldcg(&A.chunk_hist[c * ANI_MAX_SPECIES + sp]) + off + my_rank;
+        A.row_of[i] = row;
+        A.row_atom[row] = i;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Verlet-skin reuse of the bucket grid (neighbors.py:759-884, VerletCellList): a grid built with
 // cutoff + skin stays valid -- every pair within the true cutoff is still found in the 27 buckets
 // around an atom, and the AEV kernels screen with the true cutoff and the CURRENT positions -- as
@@ -926,18 +1220,36 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   A.status = status;
   A.inline_setup = (mode == 1 || pbc) ? 1 : 0;
   const size_t zeroed = (size_t)(max_bins + 1) + 2 + (size_t)(A.n_chunks + 1) * ANI_MAX_SPECIES;
-  cudaMemsetAsync(A.bin_count, 0, sizeof(int32_t) * zeroed, st);
   if (!A.inline_setup)
     k_grid_setup<<<1, 1024, 0, st>>>(coords, species, n, n_conf, n_per_conf, cell, pbc, mode, cutoff, max_bins,
                                      grid, status);
   const int nb = (n + 255) / 256;
-  k_prep_assign<<<nb, 256, 0, st>>>(A);
-  const long long t2 = A.ranges ? max((long long)n, (long long)(max_bins - 1) * 27) : (long long)n;
-  k_prep_scatter<<<(int)((t2 + 255) / 256), 256, 0, st>>>(A);
-  k_prep_finalize<<<nb, 256, 0, st>>>(A);
-  k_prep_layout<<<1, 1024, 0, st>>>(A);
-  k_layout_assign<<<A.n_chunks, LAYOUT_CHUNK, 0, st>>>(A.spos, grid, lo, hi, num_species, A.chunk_hist, A.species_base,
-                                                      row_of, row_atom);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static const bool fused = []() {
+    const char* e = getenv("ANI_B200_PREP_FUSED");  // ANI_B200_PREP_FUSED=0: the five-launch sequence
+    return !e || atoi(e) != 0;
+  }();
+  if (fused) {
+    // one persistent launch, device-wide barriers between the phases; every block must be resident:
+    // 2 blocks of 256 threads per SM at most (the kernel allows far more)
+    int32_t* bar = A.species_base + ANI_MAX_SPECIES;  // two words outside the per-step zero-fill
+    const int blocks = min(2 * num_sms, max(1, nb));
+    k_prep_fused<<<blocks, 256, 0, st>>>(A, bar, (int)zeroed);
+  } else {
+    cudaMemsetAsync(A.bin_count, 0, sizeof(int32_t) * zeroed, st);
+    k_prep_assign<<<nb, 256, 0, st>>>(A);
+    const long long t2 = A.ranges ? max((long long)n, (long long)(max_bins - 1) * 27) : (long long)n;
+    k_prep_scatter<<<(int)((t2 + 255) / 256), 256, 0, st>>>(A);
+    k_prep_finalize<<<nb, 256, 0, st>>>(A);
+    k_prep_layout<<<1, 1024, 0, st>>>(A);
+    k_layout_assign<<<A.n_chunks, LAYOUT_CHUNK, 0, st>>>(A.spos, grid, lo, hi, num_species, A.chunk_hist, A.species_base,
+                                                        row_of, row_atom);
+  }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

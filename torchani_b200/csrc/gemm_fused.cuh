@@ -1,0 +1,519 @@
+// The whole ensemble MLP of a step -- three forward layers (+ head) and three backward-to-input layers -- as
+// ONE persistent launch of the tcgen05 GEMM of gemm_tc.cuh.
+//
+// The six launches of round 1 each paid a ramp-up, a tail and their own tile-count quantisation (4.2 tiles per
+// CTA -> 84 % balance), and at small row counts (8 GPUs: 10 row tiles per rank) little else: 13.5 us per launch
+// for 2-3 us of work.  The layers of one 128-row tile are a pure chain (layer k of row tile r needs layer k-1 of
+// row tile r, nothing else), so the launch boundaries are replaced by DATA-FLOW: all (phase, row tile, member,
+// column tile) units of the step form one list, phase-major and row-tile-major inside a phase; CTA c takes units
+// c, c + G, c + 2G, ... in order, and before it touches the inputs of a unit it waits until the counter of
+// (producer phase, row tile) has reached the number of arrivals that phase owes that row tile.  Every producer
+// unit has a smaller list index than its consumers and every CTA walks its units in order, so the wait can
+// always be satisfied (induction over the list index); row tiles finish in list order, so a phase's first units
+// find their inputs long complete and the waits cost nothing except in the last few units.
+//
+//   * completion of a unit = its TMA bulk stores have fully completed (cp.async.bulk.wait_group, not .read),
+//     then fence + one release-add per epilogue warp on sync[phase][row tile].  The wait for the stores is taken
+//     one unit late (the stores of unit k have long landed when unit k+1's epilogue ends) or whenever the
+//     epilogue would idle anyway (accumulator not ready) -- which also rules out the one cycle lagging could
+//     create (a CTA whose next unit depends on its own previous one);
+//   * consumers: the producer lane before its first bulk load of a unit, and the epilogue warps before they read
+//     the stored activation (EPI_MUL_DCELU), acquire the counter and cross into the async proxy with a fence;
+//   * the operand ring changes geometry between phases (stage = 16 KB of A + bn x 128 B of B): the producer
+//     drains the ring at a phase change and both roles restart at slot 0; per-barrier parities are tracked in bit
+//     masks; the store-staging buffers of the epilogue sit at the END of the dynamic shared memory, the ring at
+//     its start, so they never overlap whatever the geometry;
+//   * waits are bounded (status ANI_STATUS_INTERNAL instead of a hung GPU).
+// The single-phase kernel of gemm_tc.cuh remains (ANI_B200_MLP_FUSED=0, and the CTA-pair experiment).
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace ani {
+namespace tc {
+
+constexpr int MAX_PHASES = 6;
+constexpr int FUSED_SMEM_BYTES = 227 * 1024 - 12 * 1024;  // 12 KB left for the static part (six tile maps, staging)
+constexpr long long FUSED_SPIN_LIMIT = 6000000000LL;      // ~3 s of clock64 ticks
+
+struct FusedArgs {
+  int n_phases;
+  int epi[MAX_PHASES];    // epilogue of the phase (EPI_*)
+  int dep[MAX_PHASES];    // phase whose row-tile counters the units of this phase wait on (-1: none)
+  int32_t* sync;          // [MAX_PHASES][sync_stride] arrivals per (phase, row tile); zeroed by the launcher
+  int sync_stride;
+  Args ph[MAX_PHASES];
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(int32_t* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_done() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// bounded wait for `*counter >= need` (one lane); raises the status word instead of hanging
+__device__ __forceinline__ void wait_counter(const int32_t* counter, int need, int32_t* status) {
+  if (ld_acquire_gpu(counter) >= need) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(counter) < need) {
+    if (clock64() - t0 > FUSED_SPIN_LIMIT) {
+      if (status) atomicOr(status, ANI_STATUS_INTERNAL);
+      break;
+    }
+  }
+}
+
+struct UnitRef {
+  int phase, local;
+};
+
+// ---- the epilogue of one tile, one instantiation per EPI (switch at tile granularity) -----------------
+template <int EPI>
+__device__ __forceinline__ void tile_epilogue(const Args& args, const TileMap& tm, const Tile& tl, const Species& sp,
+                                              uint32_t taddr, unsigned char* sb0, int epi_bufs, uint32_t& buf,
+                                              const float* __restrict__ bias, const float* __restrict__ w4,
+                                              float* e_part, int warp, int lane, const uint32_t (&my_off)[4],
+                                              const uint32_t (&st_off)[4], uint64_t* tfull_bar, uint32_t tfull_parity,
+                                              float& omax, int& groups_committed) {
+  const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
+  const int quad = warp & 3, half = warp >> 2;
+  const int r_tile = quad * 32 + lane;
+  const float acc_scale = sp.acc_scale;
+  const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward);
+  const int my_row = tl.rt * TM + r_tile;
+  float e_acc = 0.f, seed = 0.f;
+  bool row_valid = false;
+  if (EPI == EPI_HEAD) {
+    row_valid = args.row_atom[my_row] >= 0;
+    seed = row_valid ? args.member_scale[tl.mem] : 0.f;
+  }
+  unsigned char* ct = reinterpret_cast<unsigned char*>(args.C) +
+                      ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
+  float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
+  const int ngroups = tl.bn / 32;
+  uint4 yq[2 * PARTS];
+  auto load_y = [&](int g, int hh) {
+    const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+      yq[2 * p] = __ldcg(reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]));
+      yq[2 * p + 1] = __ldcg(reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]));
+    }
+  };
+  if (EPI == EPI_MUL_DCELU && half < ngroups) load_y(half, 0);  // overlaps the wait for the accumulator
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+
+  auto process = [&](int g, int hh, const uint32_t (&r)[16]) {
+    float y[16];
+    if (EPI == EPI_MUL_DCELU) {
+      join_chunk(yq, y);
+      join_chunk(yq + 1, y + 8);
+      if (hh == 0)
+        load_y(g, 1);
+      else if (g + 2 < ngroups)
+        load_y(g + 2, 0);
+    }
+    unsigned char* sb = sb0 + buf * EPI_STAGE_BYTES;
+    if (tiled_out && hh == 0) {
+      if (lane == 0) {
+        if (epi_bufs == 2)
+          bulk_wait_read<1>();
+        else
+          bulk_wait_read<0>();
+      }
+      __syncwarp();
+    }
+    const int c0 = g * 32 + hh * 16;
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = __uint_as_float(r[j]) * acc_scale;
+      if (EPI == EPI_BIAS_CELU) {
+        v = celu(v + bias[c0 + j], cc);
+      } else if (EPI == EPI_MUL_DCELU) {
+        v *= dcelu_from_out(y[j] * args.y_inv_scale, cc);
+      } else if (EPI == EPI_HEAD) {
+        const float w = w4[c0 + j];
+        const float a = celu(v + bias[c0 + j], cc);
+        e_acc = fmaf(a, w, e_acc);
+        v = seed * w * dcelu_from_out(a, cc);
+      }
+      if (EPI != EPI_PLAIN) {
+        v *= args.out_scale;
+        omax = fmaxf(omax, fabsf(v));
+      }
+      o[j] = v;
+    }
+    if (EPI == EPI_PLAIN) {
+      const int col = (tm.nb_count >= 0 ? tm.nb[tl.n0 / 32 + g] * 32 : tl.n0 + g * 32) + hh * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v4 = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        if (args.c_accumulate)
+          red_add_v4(cplain + col + 4 * q, v4);
+        else
+          *reinterpret_cast<float4*>(cplain + col + 4 * q) = v4;
+      }
+    } else if (tiled_out) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t w[4][PARTS];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_pair(o[8 * c + 2 * i], o[8 * c + 2 * i + 1], w[i]);
+        const uint32_t off = st_off[2 * hh + c];
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p)
+          *reinterpret_cast<uint4*>(sb + p * EPI_PART_BYTES + off) = make_uint4(w[0][p], w[1][p], w[2][p], w[3][p]);
+      }
+      if (hh == 1) {
+        unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES + quad * EPI_PART_BYTES;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int p = 0; p < PARTS; ++p) bulk_s2g(blk + p * A_PART_BYTES, sb + p * EPI_PART_BYTES, EPI_PART_BYTES);
+          bulk_commit();
+        }
+        ++groups_committed;
+        if (epi_bufs == 2) buf ^= 1;
+      }
+    }
+  };
+
+  {
+    uint32_t r0[16], r1[16];
+    if (half < ngroups) tmem_ld16_issue(taddr + half * 32, r0);
+    for (int g = half; g < ngroups; g += 2) {
+      tmem_ld_wait(r0);
+      tmem_ld16_issue(taddr + g * 32 + 16, r1);
+      process(g, 0, r0);
+      tmem_ld_wait(r1);
+      if (g + 2 < ngroups) tmem_ld16_issue(taddr + (g + 2) * 32, r0);
+      process(g, 1, r1);
+    }
+  }
+  if (EPI == EPI_HEAD) {
+    e_part[warp * 32 + lane] = e_acc;
+    asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+    if (half == 0)
+      args.e_member[(size_t)tl.mem * args.rows_cap + my_row] =
+          row_valid ? e_part[warp * 32 + lane] + e_part[(warp + 4) * 32 + lane] + sp.b4[tl.mem] : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant__ FusedArgs F) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ TileMap tms[MAX_PHASES];
+  __shared__ int phase_base[MAX_PHASES + 1];
+  __shared__ int s_epi_bufs;
+  __shared__ float e_part[NUM_EPI_WARPS * 32];
+  __shared__ __align__(16) float s_bias[2][TN_MAX];
+  __shared__ __align__(16) float s_w4[2][TN_MAX];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tfull = bars + 2 * MAX_STAGES;
+  uint64_t* tempty = bars + 2 * MAX_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NP = F.n_phases;
+  constexpr int AVAIL = FUSED_SMEM_BYTES - 1024;
+
+  if (threadIdx.x == 0) {
+    int run = 0, bufs = 2;
+    for (int p = 0; p < NP; ++p) {
+      build_tile_map(F.ph[p], tms[p]);
+      phase_base[p] = run;
+      run += tms[p].prefix[F.ph[p].num_species];
+      bufs = min(bufs, tms[p].epi_bufs);
+    }
+    for (int p = NP; p <= MAX_PHASES; ++p) phase_base[p] = run;
+    // one store-staging depth for all phases (the region is anchored at the end of the dynamic shared memory)
+    s_epi_bufs = bufs;
+    for (int p = 0; p < NP; ++p)
+      tms[p].stages = max(1, min(MAX_STAGES, (AVAIL - bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tms[p].stage_bytes));
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int EPI_BUFS = s_epi_bufs;
+  unsigned char* epi_stage = smem + AVAIL - EPI_BUFS * NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  const int total_units = phase_base[NP];
+  auto find_phase = [&](int g) {
+    int p = 0;
+    while (g >= phase_base[p + 1]) ++p;
+    return p;
+  };
+  // arrivals the row tile `rt` is owed by phase d: (units of the row tile) x (epilogue warps)
+  auto owed = [&](int d, int s) { return F.ph[d].members * tms[d].ntn[s] * NUM_EPI_WARPS; };
+
+  if (warp == PROD_WARP) {
+    // ================================ producer (TMA) ================================
+    uint32_t stage = 0, empty_par = 0xffffffffu;
+    int cur_phase = -1, STAGES = 1, STAGE_BYTES = 0;
+    for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+      const int p = find_phase(g);
+      const Args& args = F.ph[p];
+      const TileMap& tm = tms[p];
+      if (p != cur_phase) {
+        // new ring geometry: every slot of the old one must have been consumed
+        for (int s = 0; s < STAGES && cur_phase >= 0; ++s) mbar_wait(&empty[s], (empty_par >> s) & 1u);
+        cur_phase = p;
+        STAGES = tm.stages;
+        STAGE_BYTES = tm.stage_bytes;
+        stage = 0;
+      }
+      const Tile tl = decode_tile(args, tm, g - phase_base[p]);
+      const Species& sp = args.sp[tl.s];
+      const int nkb = tm.kb_count >= 0 ? tm.kb_count : (sp.K + TK - 1) / TK;
+      const int nkb_all = sp.b_kb_moff ? sp.b_kblocks : (sp.K + TK - 1) / TK;
+      const int kb_boff = tl.mem * sp.b_kb_moff;
+      const unsigned char* At =
+          args.A + ((size_t)tl.rt * args.a_kblocks + (size_t)(tl.mem * sp.a_moff) / TK) * A_BLOCK_BYTES;
+      const unsigned char* Bm =
+          sp.Bt + (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (PARTS * ROW_BYTES));
+      const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
+      const bool dense = tm.nb_count < 0;
+      const int gq = lane / PARTS, gpart = lane % PARTS;
+      size_t g_src = 0;
+      int g_bns = 0;
+      const bool g_active = !dense && lane < PARTS * (tl.bn / 32);
+      if (g_active) {
+        const int row0 = tm.nb[tl.n0 / 32 + gq] * 32;
+        const int n0s = row0 / TN_MAX * TN_MAX;
+        g_bns = min(TN_MAX, sp.N - n0s);
+        g_src = (size_t)n0s * nkb_all * (PARTS * ROW_BYTES) + (size_t)(row0 - n0s) * ROW_BYTES +
+                (size_t)gpart * g_bns * ROW_BYTES;
+      }
+      // data-flow: the A operand of this unit is the output of phase dep[p] for this row tile
+      if (F.dep[p] >= 0) {
+        if (lane == 0) {
+          wait_counter(F.sync + (size_t)F.dep[p] * F.sync_stride + tl.rt, owed(F.dep[p], tl.s), args.status);
+          fence_proxy_async_all();  // the bulk copies below (async proxy) are ordered after the acquire
+        }
+        __syncwarp();
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], (empty_par >> stage) & 1u);
+        empty_par ^= 1u << stage;
+        unsigned char* st = smem + stage * STAGE_BYTES;
+        const int kbi = tm.kb_count >= 0 ? tm.kb[kb] : kb;
+        const int kbb = kbi + kb_boff;
+        if (lane == 0) {
+          mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + PARTS * b_bytes);
+          bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
+          if (dense) {
+            const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
+            bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[stage]);
+          }
+        }
+        __syncwarp();
+        if (g_active)
+          bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,
+                   Bm + g_src + (size_t)kbb * g_bns * (PARTS * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
+        __syncwarp();
+        if (++stage == (uint32_t)STAGES) stage = 0;
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ================================ MMA issuer ================================
+    uint32_t stage = 0, full_par = 0u, acc = 0, acc_phase = 0;
+    int cur_phase = -1, STAGES = 1, STAGE_BYTES = 0;
+    for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+      const int p = find_phase(g);
+      const Args& args = F.ph[p];
+      const TileMap& tm = tms[p];
+      if (p != cur_phase) {
+        cur_phase = p;
+        STAGES = tm.stages;
+        STAGE_BYTES = tm.stage_bytes;
+        stage = 0;
+      }
+      const Tile tl = decode_tile(args, tm, g - phase_base[p]);
+      const int nkb = tm.kb_count >= 0 ? tm.kb_count : (args.sp[tl.s].K + TK - 1) / TK;
+      const uint32_t idesc = make_idesc(tl.bn, TM);
+      const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * TN_MAX;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], (full_par >> stage) & 1u);
+        full_par ^= 1u << stage;
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BLOCK_BYTES;
+          const uint64_t a1 = make_desc(sa), a2 = make_desc(sa + A_PART_BYTES);
+          const uint64_t b1 = make_desc(sb), b2 = make_desc(sb + b_bytes);
+#if !ANI_OPND_FP16X2
+          const uint64_t a3 = make_desc(sa + 2 * A_PART_BYTES), b3 = make_desc(sb + 2 * b_bytes);
+#endif
+#pragma unroll
+          for (int k = 0; k < TK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+#if ANI_OPND_FP16X2
+            umma_f16(d_tmem, a2 + adv, b1 + adv, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
+            umma_f16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
+#else
+            umma_f16(d_tmem, a3 + adv, b1 + adv, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, a1 + adv, b3 + adv, idesc, 1);
+            umma_f16(d_tmem, a2 + adv, b2 + adv, idesc, 1);
+            umma_f16(d_tmem, a2 + adv, b1 + adv, idesc, 1);
+            umma_f16(d_tmem, a1 + adv, b2 + adv, idesc, 1);
+            umma_f16(d_tmem, a1 + adv, b1 + adv, idesc, 1);
+#endif
+          }
+          umma_commit(&empty[stage]);
+          if (kb == nkb - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == (uint32_t)STAGES) stage = 0;
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================ epilogue ================================
+    uint32_t acc = 0, acc_phase = 0, buf = 0;
+    float omax = 0.f;
+    const int quad = warp & 3;
+    const int r_tile = quad * 32 + lane;
+    uint32_t my_off[4], st_off[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      my_off[ch] = swz_off(r_tile, ch);
+      st_off[ch] = swz_off(lane, ch);
+    }
+    unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
+    // completion bookkeeping: the unit whose stores may still be in flight
+    int32_t* pend_counter = nullptr;
+    int pend_groups = 0;  // bulk groups this warp committed for the pending unit (0: nothing to wait for)
+    // complete the pending unit: its bulk stores have landed (all of this lane's groups except the `newer`
+    // most recent ones, which belong to the unit that was just finished), then one release-add
+    auto flush_pending = [&](int newer) {
+      if (!pend_counter) return;
+      if (lane == 0) {
+        if (pend_groups) {
+          switch (newer) {
+            case 0: bulk_wait_done<0>(); break;
+            case 1: bulk_wait_done<1>(); break;
+            case 2: bulk_wait_done<2>(); break;
+            case 3: bulk_wait_done<3>(); break;
+            default: bulk_wait_done<4>(); break;
+          }
+          fence_proxy_async_all();
+        }
+        __threadfence();
+        red_release_gpu(pend_counter, 1);
+      }
+      __syncwarp();
+      pend_counter = nullptr;
+    };
+    for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+      const int p = find_phase(g);
+      const Args& args = F.ph[p];
+      const TileMap& tm = tms[p];
+      const int epi = F.epi[p];
+      const Tile tl = decode_tile(args, tm, g - phase_base[p]);
+      const Species& sp = args.sp[tl.s];
+      if (epi == EPI_BIAS_CELU || epi == EPI_HEAD) {
+        const int c = threadIdx.x;
+        if (c < tl.bn) {
+          s_bias[acc][c] = sp.bias[(size_t)tl.mem * sp.bias_mstride + tl.n0 + c];
+          if (epi == EPI_HEAD) s_w4[acc][c] = sp.w4[(size_t)tl.mem * sp.N + c];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+      }
+      // about to idle on the accumulator?  then the stores of the previous unit can be completed for free
+      if (pend_counter && !mbar_try(&tfull[acc], acc_phase)) flush_pending(0);
+      if (epi == EPI_MUL_DCELU && F.dep[p] >= 0) {
+        // the stored activation this epilogue reads (and overwrites) was written by an earlier phase of this
+        // row tile; the chain of dependencies implies it is complete once dep[p] is: acquire it here too
+        if (lane == 0) wait_counter(F.sync + (size_t)F.dep[p] * F.sync_stride + tl.rt, owed(F.dep[p], tl.s), args.status);
+        __syncwarp();
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
+      int groups = 0;
+      switch (epi) {
+        case EPI_BIAS_CELU:
+          tile_epilogue<EPI_BIAS_CELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp,
+                                       lane, my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          break;
+        case EPI_MUL_DCELU:
+          tile_epilogue<EPI_MUL_DCELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp,
+                                       lane, my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          break;
+        case EPI_HEAD:
+          tile_epilogue<EPI_HEAD>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                  my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          break;
+        default:
+          tile_epilogue<EPI_PLAIN>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                   my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          break;
+      }
+      // hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      // the previous unit's stores were committed a whole tile ago: complete it, then this unit becomes pending
+      flush_pending(groups);   // (a tile has at most 8 column groups: 4 per warp)
+      pend_counter = F.sync + (size_t)p * F.sync_stride + tl.rt;
+      pend_groups = groups;
+    }
+    flush_pending(0);
+    if (ANI_OPND_FP16X2 && F.ph[0].status && !(omax <= OPND_HALF_MAX)) atomicOr(F.ph[0].status, ANI_STATUS_OPERAND_RANGE);
+  }
+
+  // ---- teardown
+  if (warp < NUM_EPI_WARPS && lane == 0) bulk_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace tc
+}  // namespace ani

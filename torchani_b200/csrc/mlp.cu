@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_fused.cuh"
 
 namespace ani {
 
@@ -360,6 +361,102 @@ extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int 
   ta.c_accumulate = M > 1;
   if (ta.c_accumulate && !dx_zeroed) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
   launch_gemm_tc<tc::EPI_PLAIN>(ta, st, true);
+  ANI_CUDA_CHECK_LAUNCH();
+  return ANI_OK;
+}
+
+// ---- the whole MLP of a step as ONE persistent data-flow launch (gemm_fused.cuh) ----------------------
+// phase p of the list: 0-2 forward layers (2 = head), 3-5 backward-to-input.  `sync`: 6 * (rows_cap / 128) ints.
+static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, const void* x, float* dx, void* act1,
+                       void* act2, void* act3, float* e_member, const int32_t* aev_blocks, int want_backward) {
+  const int S = model->num_species, M = model->num_members, ldx = model->ldx;
+  const float sv = OPND_SCALE_VALUE, sg = OPND_SCALE_GRAD;
+  const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32, kbx = ldx / 32;
+  ta.kblocks = nullptr;
+  ta.nblocks = nullptr;
+  ta.e_member = e_member;
+  ta.want_backward = want_backward;
+  ta.c_accumulate = 0;
+  ta.ldc = 0;
+  ta.out_scale = sv;
+  ta.y_inv_scale = 1.0f / sv;
+  for (int s = 0; s < S; ++s) {
+    const ani_mlp_species& p = model->sp[s];
+    switch (phase) {
+      case 0:
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr, 0, 0,
+                                1.0f / (sv * wsc(p, 0))};
+        break;
+      case 1:
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f2), p.b2, p.h1, p.h2, p.h1, p.h2, p.h2, nullptr, nullptr, 0, 0,
+                                1.0f / (sv * wsc(p, 1))};
+        break;
+      case 2:
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f3), p.b3, p.h2, p.h3, p.h2, p.h3, p.h3, p.w4, p.b4, 0, 0,
+                                1.0f / (sv * wsc(p, 2))};
+        break;
+      case 3:
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b3), nullptr, p.h3, p.h2, p.h3, p.h2, 0, nullptr, nullptr, 0, 0,
+                                1.0f / (sg * wsc(p, 2))};
+        break;
+      case 4:
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0,
+                                1.0f / (sg * wsc(p, 1))};
+        break;
+      default:
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr,
+                                M * p.h1 / 32, p.h1 / 32, 1.0f / (sg * wsc(p, 0))};
+        break;
+    }
+  }
+  switch (phase) {
+    case 0: ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
+            ta.kblocks = aev_blocks; break;
+    case 1: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = act2; ta.c_kblocks = kb2; ta.members = M; break;
+    case 2: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
+            ta.out_scale = sg; break;
+    case 3: ta.A = static_cast<const unsigned char*>(act3); ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
+            ta.out_scale = sg; break;
+    case 4: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
+            ta.out_scale = sg; break;
+    default: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx;
+            ta.members = M; ta.nblocks = aev_blocks; ta.c_accumulate = M > 1; ta.out_scale = sg; break;
+  }
+}
+
+extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
+                                 const int32_t* row_atom, const int32_t* layout_info, const int32_t* aev_blocks,
+                                 void* act1, void* act2, void* act3, float* e_member, int want_backward,
+                                 int32_t* sync_i32, int32_t* status, void* stream) {
+  if (!x || !e_member || !sync_i32 || (want_backward && !dx)) return ANI_ERR_BAD_ARG;
+  static tc::FusedArgs F;   // ~5 KB: built in place, passed by value (__grid_constant__)
+  tc::Args base;
+  const int rc = mlp_common(model, rows_cap, row_atom, layout_info, act1, act2, act3, status, base);
+  if (rc != ANI_OK) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = model->num_members;
+  F.n_phases = want_backward ? 6 : 3;
+  static const int epis[6] = {tc::EPI_BIAS_CELU, tc::EPI_BIAS_CELU, tc::EPI_HEAD, tc::EPI_MUL_DCELU, tc::EPI_MUL_DCELU,
+                              tc::EPI_PLAIN};
+  for (int p = 0; p < tc::MAX_PHASES; ++p) {
+    F.epi[p] = epis[p];
+    F.dep[p] = p - 1;
+    F.ph[p] = base;
+    fill_phase(F.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward);
+  }
+  F.sync = sync_i32;
+  F.sync_stride = rows_cap / ANI_TILE_ROWS;
+  cudaMemsetAsync(sync_i32, 0, sizeof(int32_t) * (size_t)tc::MAX_PHASES * F.sync_stride, st);
+  if (want_backward && M > 1)
+    k_zero_live_blocks<<<592, 256, 0, st>>>(dx, model->ldx, layout_info, model->num_species, aev_blocks);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(tc::k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
+  }
+  tc::k_mlp_fused<<<num_sms, tc::THREADS, tc::FUSED_SMEM_BYTES, st>>>(F);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

@@ -383,6 +383,7 @@ class Workspace:
         self.act2 = operand_buffer(self.rows_cap, ld[1], device)
         self.act3 = operand_buffer(self.rows_cap, ld[2], device)
         self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
+        self.mlp_sync = torch.zeros(6 * (self.rows_cap // TILE) + 8, **i32)   # data-flow counters of ani_b200_mlp_step
         self.species_i32 = torch.zeros(n, **i32)
         self.coords = torch.zeros(n, 3, **f32)
         self.cell = torch.zeros(9, **f32)
@@ -450,6 +451,8 @@ class Engine:
         # default: measured on B200 at 10k atoms it changes the step by < 1 us (0.3899 vs 0.3905 ms) --
         # inside the graph the two kernels cost little more than their dependency edges
         self.side_stream = os.environ.get("ANI_B200_SIDE_STREAM", "0") != "0"
+        # ANI_B200_MLP_FUSED=0: the six separate GEMM launches of round 1 (kept for A/B timing)
+        self.mlp_fused = os.environ.get("ANI_B200_MLP_FUSED", "1") != "0"
         self._side_stream: tp.Optional[torch.cuda.Stream] = None
         self._ev: tp.List[torch.cuda.Event] = []
         self.stage_events: tp.Dict[str, tp.List[tp.Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
@@ -550,9 +553,10 @@ class Engine:
                     self._graphs[key] = graph
                     graph.replay()
         # kernels launched by this library in one step (memsets excluded):
-        # prepare 5 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
+        # prepare 1 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
         # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
-        self.launches_per_step = 5 + (0 if (pbc or n_conf > 1) else 1) + 1 + 3 + (5 if want_grad else 0) + 1
+        mlp = (1 + (1 if want_grad else 0)) if self.mlp_fused else (3 + (4 if want_grad else 0))
+        self.launches_per_step = 1 + (0 if (pbc or n_conf > 1) else 1) + 1 + mlp + (1 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
         virial = ws.virial.sum(0).view(3, 3) if want_virial else None
         return StepResult(ws.energies, ws.atomic.view(n_conf, n_per_conf),
@@ -616,7 +620,13 @@ class Engine:
                 ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
                 ptr(ws.member_atomic), ws.energies_ptr, stream_handle)
 
-        if not split:
+        if not split and self.mlp_fused:
+            # the six GEMMs of the step as ONE persistent data-flow launch (csrc/gemm_fused.cuh)
+            self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_step(
+                C.byref(self.nets.model), ptr(ws.x), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom),
+                ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
+                int(want_grad), ptr(ws.mlp_sync), ptr(ws.status), st))
+        elif not split:
             self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_forward_backward(
                 C.byref(self.nets.model), ptr(ws.x), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom),
                 ptr(ws.layout_info), ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member),
@@ -685,6 +695,8 @@ class Engine:
                 raise RuntimeError(f"an atom has more than {_lib.ANI_MAX_ANG} neighbours within Rca")
             if code & _lib.STATUS_PAIR_OVERFLOW:
                 raise RuntimeError("half neighbour list capacity exceeded")
+            if code & _lib.STATUS_INTERNAL:
+                raise RuntimeError("a device-side barrier of libani_b200 timed out (internal error)")
             if code & _lib.STATUS_OPERAND_RANGE:
                 raise RuntimeError("an AEV, activation or gradient left the range of the half-precision GEMM "
                                    "operand pieces (inf/NaN input, or |value| >= 1023 / |gradient| >= 16); "

@@ -21,7 +21,7 @@ from torch import Tensor
 
 from .aev import AEVComputer
 from .engine import Engine, StepResult
-from .neighbors import Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff
+from .neighbors import Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff, narrow_down
 from .nn import (ANINetworks, ATOMIC_NUMBER, AtomicContainer, AtomicNetwork, Ensemble, SpeciesConverter,
                  SpeciesEnergies)
 
@@ -217,6 +217,35 @@ class ANI(torch.nn.Module):
         energies = self.neural_networks(elem_idxs, aevs, atomic, ensemble_values)
         if self.energy_shifter._enabled:
             energies = energies + self.energy_shifter(elem_idxs, atomic=atomic).to(energies.dtype)
+        return energies
+
+    def compute_from_external_neighbors(self, species: Tensor, coords: Tensor, neighbor_idxs: Tensor,
+                                        shifts: tp.Optional[Tensor], charge: int = 0, atomic: bool = False,
+                                        ensemble_values: bool = False) -> Tensor:
+        r"""Entry point for an EXTERNAL neighbour list (arch.py:171-206), e.g. the Verlet list of an MD engine:
+        ``neighbor_idxs (2, P)`` candidate pairs (possibly built with a skin) and their lattice ``shifts (P, 3)``
+        (None without PBC); pairs beyond the cutoff and pairs with dummy atoms are screened out first
+        (``narrow_down``).  IMPORTANT, as in the reference: coords must be mapped to the central cell."""
+        self._check_inputs(species, coords, charge)
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        neighbors = narrow_down(self.cutoff, elem_idxs, coords, neighbor_idxs, shifts)
+        return self.compute_from_neighbors(elem_idxs, coords, neighbors, charge, atomic, ensemble_values)
+
+    def compute_from_full_neighborlist(self, species: Tensor, coords: Tensor, ilist_unique: Tensor, jlist: Tensor,
+                                       numneigh: Tensor, atomic: bool = False, ensemble_values: bool = False) -> Tensor:
+        r"""Energies of the LOCAL atoms (``ilist_unique``) of a local + ghost atom set with the full neighbour list
+        of an MD engine (LAMMPS ``ilist / jlist / numneigh``; csrc/cuaev.cpp:225-246 + the network pass of
+        potentials/nnp.py:20-32).  Ghost atoms contribute as neighbours only: their energies are masked out, and
+        ``torch.autograd.grad`` of the result gives dE/dx for local and ghost coordinates alike."""
+        self._check_inputs(species, coords, 0)
+        elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        aevs = self.aev_computer.compute_from_full_neighborlist(elem_idxs, coords, ilist_unique, jlist, numneigh)
+        local = torch.zeros_like(elem_idxs, dtype=torch.bool).view(-1)
+        local[ilist_unique.long()] = True
+        masked = torch.where(local.view_as(elem_idxs), elem_idxs, torch.full_like(elem_idxs, -1))
+        energies = self.neural_networks(masked, aevs, atomic, ensemble_values)
+        if self.energy_shifter._enabled:
+            energies = energies + self.energy_shifter(masked, atomic=atomic).to(energies.dtype)
         return energies
 
     # -- ensemble statistics (arch.py:385-576; query-by-committee active learning) ---------------------

@@ -35,6 +35,40 @@ def discard_outside_cutoff(neighbors: Neighbors, cutoff: float) -> Neighbors:
                      neighbors.diff_vectors.index_select(0, keep))
 
 
+def narrow_down(cutoff: float, elem_idxs: Tensor, coords: Tensor, neighbor_idxs: Tensor,
+                shifts: tp.Optional[Tensor] = None) -> Neighbors:
+    r"""Takes a set of potential neighbor idxs (e.g. the Verlet list of an MD engine, built with a skin) and
+    narrows it down to true neighbors (neighbors.py:64-113): pairs with a dummy atom and pairs beyond the cutoff
+    are dropped, ``diff_vectors = x[idx0] - x[idx1] + shift`` keeps its autograd edge to ``coords``.  Plain
+    tensor glue (index_select over the candidate pairs), as in the reference -- the AEV kernels then consume the
+    result through ``ani_b200_pairs_to_rows``."""
+    import math
+    mask = (elem_idxs == -1).view(-1)
+    if bool(mask.any()):
+        pair_mask = mask[neighbor_idxs.view(-1)].view(2, -1)
+        keep = (~pair_mask.any(dim=0)).nonzero().flatten()
+        neighbor_idxs = neighbor_idxs.index_select(1, keep)
+        if shifts is not None:
+            shifts = shifts.index_select(0, keep)
+    flat = coords.view(-1, 3)
+    if cutoff == math.inf:
+        if shifts is not None:
+            raise ValueError("PBC can't use an infinite cutoff")
+    else:
+        det = flat.detach()
+        d = det.index_select(0, neighbor_idxs[0]) - det.index_select(0, neighbor_idxs[1])
+        if shifts is not None:
+            d = d + shifts
+        keep = (d.norm(2, -1) <= cutoff).nonzero().flatten()
+        neighbor_idxs = neighbor_idxs.index_select(1, keep)
+        if shifts is not None:
+            shifts = shifts.index_select(0, keep)
+    diff = flat.index_select(0, neighbor_idxs[0]) - flat.index_select(0, neighbor_idxs[1])
+    if shifts is not None:
+        diff = diff + shifts
+    return Neighbors(neighbor_idxs, diff.norm(2, -1), diff)
+
+
 def _validate_inputs(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor],
                      pbc: tp.Optional[Tensor], supports_batches: bool = True) -> None:
     # neighbors.py:918-949
