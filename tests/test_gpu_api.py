@@ -446,3 +446,47 @@ def test_packed_weights_follow_in_place_edits():
     model.energy_shifter._enabled = False
     e3 = float(model(*args).energies[0])
     assert abs(e3) < 50.0 and abs(e3 - e2) > 1e3
+
+
+def test_operand_range_falls_back_to_the_bf16x3_build():
+    """Weights scaled so that layer-1 activations leave the range of the 2 x fp16 operand pieces (|value| >= 1023):
+    the device raises ANI_STATUS_OPERAND_RANGE, the model switches to the 3 x bfloat16 build of the library (both
+    builds are loaded side by side) and redoes the step; the results agree with the float64 oracle."""
+    import warnings
+    from torchani_b200 import _lib, models
+    if not _lib.available("bf16x3"):
+        pytest.skip("libani_b200_bf16x3.so has not been built")
+    om = oracle_model("2x", torch.float64, members=2)
+    scaled = []
+    for wm in om.weights:
+        per = {}
+        for s, layers in wm.items():
+            (w1, b1), rest = layers[0], layers[1:]
+            # x 3000 into layer 1, x 1/3000 out of layer 2's input side: activations of layer 1 reach ~1e4
+            (w2, b2) = rest[0]
+            per[s] = [(w1 * 3000.0, b1 * 3000.0), (w2 / 3000.0, b2)] + list(rest[1:])
+        scaled.append(per)
+    om_scaled = om._replace(weights=scaled)
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, pbc = golden_inputs(rec, torch.float64)
+    ref = orc.compute(om_scaled, species, coords, cell, pbc)
+    w32 = [{s: [(w.float(), b.float()) for w, b in layers] for s, layers in wm.items()} for wm in scaled]
+    model = models.from_weight_lists("2x", w32, device=DEV, periodic_table_index=False)
+    assert model.neural_networks._variant == ""
+    c = coords.float().to(DEV)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        e, f = model.energies_and_forces(species.to(DEV), c, cell.float().to(DEV), pbc.to(DEV))
+    assert any("bf16" in str(w.message) for w in caught)
+    assert model.neural_networks._variant == "bf16x3" and model.engine(torch.device(DEV)).variant == "bf16x3"
+    scale = float(ref["forces"].abs().max())
+    assert float((f.cpu().double() - ref["forces"]).abs().max()) < 1e-4 * max(1.0, scale)
+    assert abs(float(e[0]) - float(ref["energy"][0])) < 1e-5 * abs(float(ref["energy"][0])) + 1e-3
+    # the module-level container path falls back the same way
+    model2 = models.from_weight_lists("2x", w32, device=DEV, periodic_table_index=False)
+    aev = model2.aev_computer(species.to(DEV), c, cell.float().to(DEV), pbc.to(DEV))
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter("always")
+        e2 = model2.neural_networks(species.to(DEV), aev)
+    assert model2.neural_networks._variant == "bf16x3"
+    assert abs(float(e2[0]) - float(ref["energy_nn"][0])) < 1e-5 * abs(float(ref["energy_nn"][0])) + 1e-3

@@ -16,7 +16,11 @@ import torch
 from helpers import ROOT
 
 pytestmark = pytest.mark.gpu
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "cuaev.so")
+# one copy per process: the staged reference package (oracle/_ref/torchani, used by the drop-in tests) loads its own
+# cuaev.so / cell_list.so; registering a second copy of the same torch classes aborts the interpreter
+_STAGED = os.path.join(ROOT, "oracle", "_ref", "torchani")
+REF_SO = os.path.join(_STAGED, "cuaev.so") if os.path.exists(os.path.join(_STAGED, "cuaev.so")) else \
+    os.path.join(ROOT, "oracle", "_ref", "cuaev.so")
 
 
 def _reference_computer(consts, dev):
@@ -115,7 +119,9 @@ def test_reference_gpu_path_pieces_beside_ours():
     dev = torch.device("cuda", 0)
     consts = constants_2x()
     comp = _reference_computer(consts, dev)
-    cl_so = os.path.join(ROOT, "oracle", "_ref", "cell_list.so")
+    cl_so = os.path.join(_STAGED, "cell_list.so")
+    if not os.path.exists(cl_so):
+        cl_so = os.path.join(ROOT, "oracle", "_ref", "cell_list.so")
     if not os.path.exists(cl_so):
         pytest.skip("oracle/_ref/cell_list.so has not been built")
     try:

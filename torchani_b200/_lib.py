@@ -111,30 +111,46 @@ class ANIB200Error(RuntimeError):
     pass
 
 
-def _load() -> C.CDLL:
-    if not os.path.exists(LIB_PATH):
+VARIANTS = ("", "bf16x3")   # "" = the default build (2 x fp16 operand pieces), "bf16x3" = 3 x bfloat16 pieces
+
+
+def variant_path(variant: str = "") -> str:
+    """Path of a build variant of the library (build.py: same sources, other operand format)."""
+    if not variant:
+        return LIB_PATH
+    return os.path.join(os.path.dirname(LIB_PATH), f"libani_b200_{variant}.so")
+
+
+def available(variant: str = "") -> bool:
+    return os.path.exists(variant_path(variant))
+
+
+def _load(path: str) -> C.CDLL:
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m torchani_b200.build` "
+            f"{path} is missing: build it with `python -m torchani_b200.build` "
             "(nvcc, sm_100a).  torchani_b200 has no CPU / PyTorch fallback."
         )
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)   # RTLD_LOCAL: the variants export the same C symbols side by side
     for name, (res, args) in _PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
     if lib.ani_b200_abi_version() != 2:
-        raise ImportError("libani_b200.so ABI version mismatch")
+        raise ImportError(f"{path}: ABI version mismatch")
     return lib
 
 
-_lib = None
+_libs: tp.Dict[str, C.CDLL] = {}
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        _lib = _load()
-    return _lib
+def lib(variant: tp.Optional[str] = None) -> C.CDLL:
+    """The C-ABI library; ``variant`` selects another operand-format build of the same sources (both can be
+    loaded at once -- the automatic fallback of models.ANI uses that)."""
+    v = variant or ""
+    if v not in _libs:
+        _libs[v] = _load(variant_path(v))
+    return _libs[v]
 
 
 class OperandFormat(tp.NamedTuple):
@@ -143,17 +159,21 @@ class OperandFormat(tp.NamedTuple):
     grad_scale: float    # power-of-two scale of gradient operands
 
 
-_fmt = None
+_fmts: tp.Dict[str, OperandFormat] = {}
 
 
-def operand_format() -> OperandFormat:
-    """The tiled-operand format the loaded library was compiled for (ani_b200_operand_format)."""
-    global _fmt
-    if _fmt is None:
+def operand_format(variant: tp.Optional[str] = None) -> OperandFormat:
+    """The tiled-operand format a library build was compiled for (ani_b200_operand_format)."""
+    v = variant or ""
+    if v not in _fmts:
         parts, vs, gs = C.c_int32(0), C.c_float(0), C.c_float(0)
-        check(lib().ani_b200_operand_format(C.byref(parts), C.byref(vs), C.byref(gs)), "operand_format")
-        _fmt = OperandFormat(int(parts.value), float(vs.value), float(gs.value))
-    return _fmt
+        check(lib(v).ani_b200_operand_format(C.byref(parts), C.byref(vs), C.byref(gs)), "operand_format")
+        _fmts[v] = OperandFormat(int(parts.value), float(vs.value), float(gs.value))
+    return _fmts[v]
+
+
+class OperandRangeError(RuntimeError):
+    """A value left the range of the half-precision GEMM operand pieces (ANI_STATUS_OPERAND_RANGE)."""
 
 
 def check(rc: int, what: str = "") -> None:

@@ -17,6 +17,7 @@ import numpy as np
 import torch
 from torch import Tensor
 
+from . import _lib
 from .models import ANI
 
 HARTREE_TO_EV = 27.211386024367243  # units.py (CODATA 2014, as used by the reference's ASE interface)
@@ -139,7 +140,24 @@ class HostCalculator:
         elif reuse and int(self.h_moved[0]):
             self._have_grid = False   # close to the limit: rebuild before the next step
         if int(self.h_status[0]):   # came back with the results: raise what the reference raises
-            eng.check_status(self.ws)
+            try:
+                eng.check_status(self.ws)
+            except _lib.OperandRangeError:
+                # the 2 x fp16 operand format ran out of range: rebuild on the 3 x bfloat16 build and redo the step
+                nets = self.model.neural_networks
+                if nets._variant == "bf16x3" or not _lib.available("bf16x3") or self.sharded is not None:
+                    raise
+                import warnings
+                warnings.warn("torchani_b200: operand range of the 2 x fp16 GEMM format exceeded; switching this "
+                              "model to the 3 x bfloat16 build of the library")
+                nets.use_variant("bf16x3")
+                self.engine = self.model.engine(self.device)
+                self.engine.skin = self.skin
+                self.ws = self.engine.workspace(1, self.n)
+                self.ws.species_i32.copy_(self.elem_idxs.reshape(-1))
+                self._graphs, self._have_grid = {}, False
+                self._mode_calls = {False: 0, True: 0}
+                return self.calculate(positions)
         # a fresh array: h_grad is the persistent pinned D2H buffer and is overwritten by the next call
         return float(self.h_energy[0]), np.negative(self.h_grad.numpy())
 

@@ -114,8 +114,10 @@ __device__ __forceinline__ void tile_epilogue(const Args& args, const TileMap& t
     const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
 #pragma unroll
     for (int p = 0; p < PARTS; ++p) {
-      yq[2 * p] = __ldcg(reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]));
-      yq[2 * p + 1] = __ldcg(reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]));
+      // (plain cached loads: this SM has not read these lines before in this launch, so the L1 cannot hold a stale
+      // copy of what another SM's TMA stores wrote in an earlier phase; the four chunks of a row share L1 lines)
+      yq[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]);
+      yq[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]);
     }
   };
   if (EPI == EPI_MUL_DCELU && half < ngroups) load_y(half, 0);  // overlaps the wait for the accumulator
@@ -222,12 +224,16 @@ __device__ __forceinline__ void tile_epilogue(const Args& args, const TileMap& t
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant__ FusedArgs F) {
+constexpr int SIGNAL_WARP = NUM_EPI_WARPS + 2;        // warp 10: publishes unit completions (keeps the fences off the epilogue)
+constexpr int FUSED_THREADS = THREADS + 32;           // 352
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_constant__ FusedArgs F) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ TileMap tms[MAX_PHASES];
   __shared__ int phase_base[MAX_PHASES + 1];
   __shared__ int s_epi_bufs;
+  __shared__ int s_done;   // arrivals of epilogue warps: 8 per completed unit (stores landed), monotonic
   __shared__ float e_part[NUM_EPI_WARPS * 32];
   __shared__ __align__(16) float s_bias[2][TN_MAX];
   __shared__ __align__(16) float s_w4[2][TN_MAX];
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
     for (int p = NP; p <= MAX_PHASES; ++p) phase_base[p] = run;
     // one store-staging depth for all phases (the region is anchored at the end of the dynamic shared memory)
     s_epi_bufs = bufs;
+    s_done = 0;
     for (int p = 0; p < NP; ++p)
       tms[p].stages = max(1, min(MAX_STAGES, (AVAIL - bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tms[p].stage_bytes));
     for (int i = 0; i < MAX_STAGES; ++i) {
@@ -277,8 +284,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
     while (g >= phase_base[p + 1]) ++p;
     return p;
   };
-  // arrivals the row tile `rt` is owed by phase d: (units of the row tile) x (epilogue warps)
-  auto owed = [&](int d, int s) { return F.ph[d].members * tms[d].ntn[s] * NUM_EPI_WARPS; };
+  // arrivals the row tile `rt` is owed by phase d: one per unit of the row tile
+  auto owed = [&](int d, int s) { return F.ph[d].members * tms[d].ntn[s]; };
 
   if (warp == PROD_WARP) {
     // ================================ producer (TMA) ================================
@@ -408,6 +415,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
         acc_phase ^= 1;
       }
     }
+  } else if (warp == SIGNAL_WARP) {
+    // ================================ completion signals ================================
+    // unit k of this CTA is complete when all eight epilogue warps have seen its stores land (s_done >= 8 (k+1));
+    // one fence + release-add per unit, off the epilogue's critical path
+    if (lane == 0) {
+      volatile int* done = &s_done;
+      int k = 0;
+      for (int g = blockIdx.x; g < total_units; g += gridDim.x, ++k) {
+        const int p = find_phase(g);
+        const Tile tl = decode_tile(F.ph[p], tms[p], g - phase_base[p]);
+        const long long t0 = clock64();
+        while (*done < NUM_EPI_WARPS * (k + 1)) {
+          __nanosleep(64);
+          if (clock64() - t0 > 4 * FUSED_SPIN_LIMIT) break;
+        }
+        bool consumed = false;   // does any later phase wait on this one?
+        for (int q = p + 1; q < NP; ++q) consumed |= F.dep[q] == p;
+        if (consumed) {
+          fence_proxy_async_all();
+          __threadfence();
+          red_release_gpu(F.sync + (size_t)p * F.sync_stride + tl.rt, 1);
+        }
+      }
+    }
   } else {
     // ================================ epilogue ================================
     uint32_t acc = 0, acc_phase = 0, buf = 0;
@@ -422,12 +453,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
     }
     unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
     // completion bookkeeping: the unit whose stores may still be in flight
-    int32_t* pend_counter = nullptr;
+    bool pending = false;
     int pend_groups = 0;  // bulk groups this warp committed for the pending unit (0: nothing to wait for)
     // complete the pending unit: its bulk stores have landed (all of this lane's groups except the `newer`
-    // most recent ones, which belong to the unit that was just finished), then one release-add
+    // most recent ones, which belong to the unit that was just finished), then one arrival in shared memory
     auto flush_pending = [&](int newer) {
-      if (!pend_counter) return;
+      if (!pending) return;
       if (lane == 0) {
         if (pend_groups) {
           switch (newer) {
@@ -437,13 +468,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
             case 3: bulk_wait_done<3>(); break;
             default: bulk_wait_done<4>(); break;
           }
-          fence_proxy_async_all();
         }
-        __threadfence();
-        red_release_gpu(pend_counter, 1);
+        __threadfence_block();
+        atomicAdd_block(&s_done, 1);   // the signal warp publishes the unit once all eight warps are here
       }
       __syncwarp();
-      pend_counter = nullptr;
+      pending = false;
     };
     for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
       const int p = find_phase(g);
@@ -461,7 +491,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
       }
       // about to idle on the accumulator?  then the stores of the previous unit can be completed for free
-      if (pend_counter && !mbar_try(&tfull[acc], acc_phase)) flush_pending(0);
+      if (pending && !mbar_try(&tfull[acc], acc_phase)) flush_pending(0);
       if (epi == EPI_MUL_DCELU && F.dep[p] >= 0) {
         // the stored activation this epilogue reads (and overwrites) was written by an earlier phase of this
         // row tile; the chain of dependencies implies it is complete once dep[p] is: acquire it here too
@@ -498,7 +528,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_mlp_fused(const __grid_constant_
       }
       // the previous unit's stores were committed a whole tile ago: complete it, then this unit becomes pending
       flush_pending(groups);   // (a tile has at most 8 column groups: 4 per warp)
-      pend_counter = F.sync + (size_t)p * F.sync_stride + tl.rt;
+      pending = true;
       pend_groups = groups;
     }
     flush_pending(0);

@@ -456,7 +456,7 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(tc::k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
   }
-  tc::k_mlp_fused<<<num_sms, tc::THREADS, tc::FUSED_SMEM_BYTES, st>>>(F);
+  tc::k_mlp_fused<<<num_sms, tc::FUSED_THREADS, tc::FUSED_SMEM_BYTES, st>>>(F);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

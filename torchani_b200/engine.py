@@ -95,11 +95,11 @@ def constants_1x(num_species: int = 4, cutoff_fn: str = "cosine") -> AEVConstant
                         _linspace(0.9, 3.5, 4), _linspace(a0, math.pi + a0, 8), cutoff_fn)
 
 
-def _split(x: Tensor, scale: float = 1.0) -> tp.List[Tensor]:
+def _split(x: Tensor, scale: float = 1.0, variant: tp.Optional[str] = None) -> tp.List[Tensor]:
     """x (float32) -> the 16-bit pieces of ``scale * x`` in the library's operand format
     (``_lib.operand_format``): two IEEE half pieces or three bfloat16 pieces, each rounded to
     nearest, ``scale * x = p1 + p2 (+ p3)``."""
-    fmt = _lib.operand_format()
+    fmt = _lib.operand_format(variant)
     dt = torch.float16 if fmt.parts == 2 else torch.bfloat16
     r = x.to(torch.float32) * scale
     out = []
@@ -110,10 +110,10 @@ def _split(x: Tensor, scale: float = 1.0) -> tp.List[Tensor]:
     return out
 
 
-def weight_scale(ws: tp.Sequence[Tensor]) -> float:
+def weight_scale(ws: tp.Sequence[Tensor], variant: tp.Optional[str] = None) -> float:
     """Power-of-two operand scale for a group of weight matrices (half pieces: the largest
     |scale * w| stays below 2^14, the scale below 2^12; bfloat16 pieces need none)."""
-    if _lib.operand_format().parts != 2:
+    if _lib.operand_format(variant).parts != 2:
         return 1.0
     top = max(float(w.abs().max()) for w in ws)
     if not math.isfinite(top):
@@ -130,7 +130,7 @@ def _swizzle_index(device) -> Tensor:
     return pos ^ ((rows >> 1) & 3)
 
 
-def tile_b_operand(b: Tensor, scale: float = 1.0) -> Tensor:
+def tile_b_operand(b: Tensor, scale: float = 1.0, variant: tp.Optional[str] = None) -> Tensor:
     """``B[N][K]`` (float32, K-major, N % 32 == 0) -> the "tiled B operand" byte layout of
     include/ani_b200.h: K zero-padded to 32, the 16-bit pieces of ``scale * B``,
     [n tile of 256 rows][k block of 32][p1 bn x 64 B | p2 (| p3)] with every 8-row group in tcgen05
@@ -141,7 +141,7 @@ def tile_b_operand(b: Tensor, scale: float = 1.0) -> Tensor:
     nkb = kp // 32
     bp = torch.zeros(n, kp, dtype=torch.float32, device=b.device)
     bp[:, :k] = b
-    pieces = _split(bp, scale)
+    pieces = _split(bp, scale, variant)
     src_chunk = _swizzle_index(b.device)
     out = []
     for n0 in range(0, n, 256):
@@ -156,7 +156,7 @@ def tile_b_operand(b: Tensor, scale: float = 1.0) -> Tensor:
     return torch.cat(out).contiguous()
 
 
-def tile_a_operand(x: Tensor, scale: tp.Optional[float] = None) -> Tensor:
+def tile_a_operand(x: Tensor, scale: tp.Optional[float] = None, variant: tp.Optional[str] = None) -> Tensor:
     """Plain ``[rows][cols]`` float32 (rows % 128 == 0, cols % 32 == 0) -> flat "tiled operand"
     (A-operand form of include/ani_b200.h; ``scale`` defaults to the library's value scale).
     Plumbing for the API paths that receive plain AEVs."""
@@ -164,18 +164,19 @@ def tile_a_operand(x: Tensor, scale: tp.Optional[float] = None) -> Tensor:
     assert rows % 128 == 0 and cols % 32 == 0
     nkb = cols // 32
     if scale is None:
-        scale = _lib.operand_format().value_scale
+        scale = _lib.operand_format(variant).value_scale
     idx = _swizzle_index(x.device).view(1, 1, 1, 8, 4, 1).expand(rows // 128, nkb, 16, 8, 4, 8)
     parts = []
-    for part in _split(x.contiguous().to(torch.float32), scale):
+    for part in _split(x.contiguous().to(torch.float32), scale, variant):
         v = part.view(rows // 128, 16, 8, nkb, 4, 8).permute(0, 3, 1, 2, 4, 5)   # [rt][kb][grp][row][ch][8]
         parts.append(torch.gather(v, 4, idx).reshape(rows // 128, nkb, 4096))
     return torch.stack(parts, 2).reshape(-1).contiguous()                          # [rt][kb][piece][4096]
 
 
-def untile_a_operand(t: Tensor, rows: int, cols: int, scale: tp.Optional[float] = None) -> Tensor:
+def untile_a_operand(t: Tensor, rows: int, cols: int, scale: tp.Optional[float] = None,
+                     variant: tp.Optional[str] = None) -> Tensor:
     """Inverse of ``tile_a_operand`` (returns (p1 + p2 (+ p3)) / scale as plain float32 ``[rows][cols]``)."""
-    fmt = _lib.operand_format()
+    fmt = _lib.operand_format(variant)
     if scale is None:
         scale = fmt.value_scale
     nkb = cols // 32
@@ -187,9 +188,9 @@ def untile_a_operand(t: Tensor, rows: int, cols: int, scale: tp.Optional[float] 
     return w.permute(0, 2, 3, 1, 4, 5).reshape(rows, cols).contiguous()
 
 
-def operand_buffer(rows: int, cols: int, device) -> Tensor:
+def operand_buffer(rows: int, cols: int, device, variant: tp.Optional[str] = None) -> Tensor:
     """Zeroed storage of a tiled operand matrix with ``rows x cols`` values."""
-    fmt = _lib.operand_format()
+    fmt = _lib.operand_format(variant)
     return torch.zeros(rows, fmt.parts * cols, dtype=torch.float16 if fmt.parts == 2 else torch.bfloat16,
                        device=device)
 
@@ -203,8 +204,9 @@ class PackedNetworks:
     """
 
     def __init__(self, weights: tp.Sequence[tp.Sequence[tp.Sequence[tp.Tuple[Tensor, Tensor]]]],
-                 in_dim: int, device: torch.device, celu_alpha: float = 0.1):
+                 in_dim: int, device: torch.device, celu_alpha: float = 0.1, variant: tp.Optional[str] = None):
         self.device = torch.device(device)
+        self.variant = variant or ""   # build of the library (operand format) these operands are packed for
         M = len(weights)
         S = len(weights[0])
         if not (1 <= M <= _lib.ANI_MAX_MEMBERS) or not (1 <= S <= _lib.ANI_MAX_SPECIES):
@@ -222,7 +224,7 @@ class PackedNetworks:
         # uploaded with a single copy and re-laid out into the tiled B operands by this library's own
         # ani_b200_pack_b_operand kernel: no ATen kernel touches them (one launch per operand kind).
         pad = lambda v: (v + 31) // 32 * 32  # noqa: E731
-        P2 = 2 * _lib.operand_format().parts          # bytes per operand element
+        P2 = 2 * _lib.operand_format(self.variant).parts          # bytes per operand element
         plan = []                                     # per species: sizes, scales, source / destination offsets
         src_off = 0
         dst_off = 0
@@ -258,7 +260,7 @@ class PackedNetworks:
                     raise ValueError("all ensemble members must share the layer widths of an element")
             host_w.append((W, Bv))
             p1, p2, p3 = pad(h1), pad(h2), pad(h3)
-            sc = [weight_scale(W[k]) for k in range(3)]   # one scale per layer, shared by W and W^T
+            sc = [weight_scale(W[k], self.variant) for k in range(3)]   # one scale per layer, shared by W and W^T
             plan.append(dict(
                 h=(h1, h2, h3), p=(p1, p2, p3), sc=sc,
                 s_w1=take_src(M * p1 * self.ldx), s_w2=take_src(M * p2 * p1), s_w3=take_src(M * p3 * p2),
@@ -289,7 +291,7 @@ class PackedNetworks:
             src = host.pin_memory().to(self.device, non_blocking=True)
             dst = torch.empty(dst_off, dtype=torch.uint8, device=self.device)
             st = torch.cuda.current_stream(self.device).cuda_stream
-            L = _lib.lib()
+            L = _lib.lib(self.variant)
             sp0, dp0 = src.data_ptr(), dst.data_ptr()
             for s in range(S):
                 q = plan[s]
@@ -350,7 +352,8 @@ class Workspace:
     """All device buffers for one (n_conf, n_per_conf) problem shape."""
 
     def __init__(self, n_conf: int, n_per_conf: int, num_species: int, ldx: int, ld: tp.Tuple[int, int, int],
-                 num_members: int, nbr_cap: int, device: torch.device, owned_cap: tp.Optional[int] = None):
+                 num_members: int, nbr_cap: int, device: torch.device, owned_cap: tp.Optional[int] = None,
+                 variant: tp.Optional[str] = None):
         n = n_conf * n_per_conf
         self.n, self.n_conf, self.n_per_conf = n, n_conf, n_per_conf
         owned = n if owned_cap is None else min(n, owned_cap)
@@ -377,11 +380,11 @@ class Workspace:
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
         # x / act*: "tiled operand" form (16-bit pieces of every value); dx: plain float32 rows
-        self.x = operand_buffer(self.rows_cap, ldx, device)
+        self.x = operand_buffer(self.rows_cap, ldx, device, variant)
         self.dx = torch.zeros(self.rows_cap, ldx, **f32)
-        self.act1 = operand_buffer(self.rows_cap, ld[0], device)
-        self.act2 = operand_buffer(self.rows_cap, ld[1], device)
-        self.act3 = operand_buffer(self.rows_cap, ld[2], device)
+        self.act1 = operand_buffer(self.rows_cap, ld[0], device, variant)
+        self.act2 = operand_buffer(self.rows_cap, ld[1], device, variant)
+        self.act3 = operand_buffer(self.rows_cap, ld[2], device, variant)
         self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
         self.mlp_sync = torch.zeros(6 * (self.rows_cap // TILE) + 8, **i32)   # data-flow counters of ani_b200_mlp_step
         self.species_i32 = torch.zeros(n, **i32)
@@ -443,7 +446,8 @@ class Engine:
         self._graphs: tp.Dict[tp.Any, torch.cuda.CUDAGraph] = {}   # insertion order = LRU order
         self.max_graphs = 16
         self._graph_seen: tp.Dict[tp.Any, int] = {}
-        self.lib = _lib.lib()
+        self.variant = nets.variant
+        self.lib = _lib.lib(self.variant)
         self.launches_per_step = 0
         # per-stage CUDA-event timing (bench.py's roofline leg); off by default
         self.profile = False
@@ -479,7 +483,7 @@ class Engine:
         ws = self._ws.get(key)
         if ws is None:
             ws = Workspace(n_conf, n_per_conf, self.consts.num_species, self.nets.ldx, self.nets.ld,
-                           self.nets.num_members, self.nbr_cap, self.device)
+                           self.nets.num_members, self.nbr_cap, self.device, variant=self.variant)
             self._ws[key] = ws
         return ws
 
@@ -698,9 +702,10 @@ class Engine:
             if code & _lib.STATUS_INTERNAL:
                 raise RuntimeError("a device-side barrier of libani_b200 timed out (internal error)")
             if code & _lib.STATUS_OPERAND_RANGE:
-                raise RuntimeError("an AEV, activation or gradient left the range of the half-precision GEMM "
-                                   "operand pieces (inf/NaN input, or |value| >= 1023 / |gradient| >= 16); "
-                                   "build the library with -DANI_OPND_FP16X2=0 for such models")
+                raise _lib.OperandRangeError(
+                    "an AEV, activation or gradient left the range of the half-precision GEMM operand pieces "
+                    "(inf/NaN input, or |value| >= 1023 / |gradient| >= 16); the 3 x bfloat16 build of the library "
+                    "(variant 'bf16x3') has no such limit -- models.ANI switches to it automatically")
 
     def grid_info(self, ws: Workspace) -> Grid:
         g = Grid()

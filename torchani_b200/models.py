@@ -19,6 +19,7 @@ import typing as tp
 import torch
 from torch import Tensor
 
+from . import _lib
 from .aev import AEVComputer
 from .engine import Engine, StepResult
 from .neighbors import Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff, narrow_down
@@ -173,6 +174,22 @@ class ANI(torch.nn.Module):
             self._engine_key = key
         return self._engine
 
+    def _guarded(self, fn: tp.Callable[[], tp.Any]) -> tp.Any:
+        """Run an engine call; if a value left the range of the 2 x fp16 operand pieces
+        (ANI_STATUS_OPERAND_RANGE), switch the networks to the 3 x bfloat16 build of the library -- same kernels,
+        6 instead of 4 bytes per operand element, no range limit -- and redo the call."""
+        try:
+            return fn()
+        except _lib.OperandRangeError:
+            nets = self.neural_networks
+            if nets._variant == "bf16x3" or not _lib.available("bf16x3"):
+                raise
+            import warnings
+            warnings.warn("torchani_b200: operand range of the 2 x fp16 GEMM format exceeded; switching this model "
+                          "to the 3 x bfloat16 build of the library")
+            nets.use_variant("bf16x3")
+            return fn()
+
     @staticmethod
     def _check_inputs(elem_idxs: Tensor, coords: Tensor, charge: int = 0) -> None:
         assert elem_idxs.dim() == 2
@@ -186,9 +203,8 @@ class ANI(torch.nn.Module):
         self._check_inputs(species, coords, charge)
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         _validate_inputs(self.cutoff, elem_idxs, coords, cell, pbc)
-        eng = self.engine(coords.device)
-        e, e_atomic, e_member = _FusedEnergy.apply(coords, elem_idxs, cell, pbc is not None, eng,
-                                                   bool(coords.requires_grad))
+        e, e_atomic, e_member = self._guarded(lambda: _FusedEnergy.apply(
+            coords, elem_idxs, cell, pbc is not None, self.engine(coords.device), bool(coords.requires_grad)))
         energies: Tensor
         if ensemble_values:
             active = self.neural_networks.active_members_idxs
@@ -327,15 +343,15 @@ class ANI(torch.nn.Module):
         ``forward`` loses ~3e-3 Ha at |E| ~ 2.5e4 Ha)."""
         species, coords = species_coordinates
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
-        eng = self.engine(coords.device)
-        return eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=False, check=True).energies.clone()
+        return self._guarded(lambda: self.engine(coords.device).step(
+            elem_idxs, coords.detach(), cell, pbc is not None, want_grad=False, check=True).energies.clone())
 
     def energies_and_forces(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None,
                             pbc: tp.Optional[Tensor] = None) -> tp.Tuple[Tensor, Tensor]:
         """grad.py:263-290 without the autograd round trip: (energies f64 (C,), forces f32 (C,A,3))."""
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
-        eng = self.engine(coords.device)
-        res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True, check=True)
+        res = self._guarded(lambda: self.engine(coords.device).step(
+            elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True, check=True))
         return res.energies.clone(), -res.grad
 
     def energies_forces_stress(self, species: Tensor, coords: Tensor, cell: Tensor,
@@ -346,8 +362,8 @@ class ANI(torch.nn.Module):
         the strain derivative dE/d(scaling)/V of ase.py:170-173 and, unlike that one, does not need the
         atoms to be wrapped into the cell."""
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
-        eng = self.engine(coords.device)
-        res = eng.step(elem_idxs, coords.detach(), cell, True, want_grad=True, want_virial=True, check=True)
+        res = self._guarded(lambda: self.engine(coords.device).step(
+            elem_idxs, coords.detach(), cell, True, want_grad=True, want_virial=True, check=True))
         volume = torch.det(cell.detach().double()).abs()
         return res.energies.clone(), -res.grad, res.virial / volume
 

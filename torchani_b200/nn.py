@@ -92,7 +92,7 @@ class _MLPFunction(torch.autograd.Function):
         layout_info = torch.zeros(16, **i32)
         scratch = torch.zeros((n // 256 + 3) * 8 + 64, **i32)
         st = torch.cuda.current_stream(dev).cuda_stream
-        L = _lib.lib()
+        L = _lib.lib(nets.variant)
         check(L.ani_b200_species_layout(ptr(spos), ptr(grid), n, 0, n, S, rows_cap, ptr(row_of), ptr(row_atom),
                                         ptr(tile_species), ptr(layout_info), ptr(scratch), st), "species_layout")
         xp = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)
@@ -102,10 +102,10 @@ class _MLPFunction(torch.autograd.Function):
         src = src * real.view(-1, 1)
         # padding atoms all map to row 0 with zero contribution -> index_add keeps row 0 intact
         xp[:, :D].index_add_(0, rows, src)
-        x_tiled = tile_a_operand(xp)                    # the GEMM consumes the tiled form
+        x_tiled = tile_a_operand(xp, variant=nets.variant)                    # the GEMM consumes the tiled form
         x = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)   # dE/dAEV comes back as plain rows
         ld = nets.ld
-        act1, act2, act3 = (operand_buffer(rows_cap, w, dev) for w in ld)
+        act1, act2, act3 = (operand_buffer(rows_cap, w, dev, nets.variant) for w in ld)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         e_member = torch.zeros(M, rows_cap, dtype=torch.float32, device=dev)
         check(L.ani_b200_mlp_forward_backward(C.byref(nets.model), ptr(x_tiled), ptr(x), rows_cap,
@@ -113,8 +113,8 @@ class _MLPFunction(torch.autograd.Function):
                                               ptr(e_member), int(want_grad), ptr(status), st),
               "mlp_forward_backward")
         if int(status.item()) & _lib.STATUS_OPERAND_RANGE:   # this module-level path synchronises anyway
-            raise RuntimeError("an AEV, activation or gradient left the range of the half-precision GEMM operand "
-                               "pieces (inf/NaN input, or |value| >= 1023 / |gradient| >= 16)")
+            raise _lib.OperandRangeError("an AEV, activation or gradient left the range of the half-precision GEMM "
+                                         "operand pieces (inf/NaN input, or |value| >= 1023 / |gradient| >= 16)")
         em_sorted = e_member[:, rows] * real.view(1, -1)          # (M, n) in `order` order
         out = torch.zeros(M, n, dtype=torch.float32, device=dev)
         out[:, order] = em_sorted
@@ -161,6 +161,7 @@ class AtomicContainer(torch.nn.Module):
         self._packed: tp.Optional[PackedNetworks] = None
         self._packed_key: tp.Any = None
         self._packed_params: tp.Optional[tp.List[Tensor]] = None
+        self._variant = ""   # operand-format build of the library ("" = 2 x fp16 pieces, "bf16x3"), see use_variant
 
     @property
     def symbols(self) -> tp.Tuple[str, ...]:
@@ -184,6 +185,17 @@ class AtomicContainer(torch.nn.Module):
     def member_networks(self) -> tp.List["ANINetworks"]:
         raise NotImplementedError
 
+    def use_variant(self, variant: str) -> None:
+        """Run this container on another operand-format build of the library ('bf16x3': three bfloat16 pieces per
+        value -- 6 instead of 4 bytes per operand element, no range limit)."""
+        if variant not in _lib.VARIANTS:
+            raise ValueError(f"unknown library variant {variant!r}")
+        if not _lib.available(variant):
+            raise ImportError(f"{_lib.variant_path(variant)} has not been built (python -m torchani_b200.build)")
+        if variant != self._variant:
+            self._variant = variant
+            self._packed_key = None
+
     def invalidate_packed(self) -> None:
         """Forget the kernel-layout copy of the weights (needed only after replacing ``p.data`` wholesale;
         in-place edits are seen through the parameters' version counters)."""
@@ -206,14 +218,15 @@ class AtomicContainer(torch.nn.Module):
         if self._packed_params is None:
             self._packed_params = [p for m in self.member_networks() for p in m.parameters()]
         params = self._packed_params
-        key = (str(device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
+        key = (str(device), self._variant, tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
         if self._packed is None or self._packed_key != key:
             members = self.member_networks()
             params = self._packed_params = [p for m in members for p in m.parameters()]
-            key = (str(device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
+            key = (str(device), self._variant, tuple(p._version for p in params),
+                   tuple(p.data_ptr() for p in params[:2]))
             weights = [[m.atomics[s].linear_pairs() for s in m.atomics] for m in members]
             in_dim = members[0].in_dim
-            self._packed = PackedNetworks(weights, in_dim, device)
+            self._packed = PackedNetworks(weights, in_dim, device, variant=self._variant)
             self._packed.set_active_members(self.active_members_idxs)
             self._packed_key = key
         return self._packed
@@ -222,8 +235,17 @@ class AtomicContainer(torch.nn.Module):
         assert elem_idxs.shape == aevs.shape[:-1]
         if aevs.device.type != "cuda":
             raise ValueError("torchani_b200 runs on CUDA tensors only (there is no CPU path)")
-        nets = self.packed(aevs.device)
-        e_m = _MLPFunction.apply(aevs, elem_idxs, nets, bool(aevs.requires_grad))  # (M, C, A)
+        try:
+            e_m = _MLPFunction.apply(aevs, elem_idxs, self.packed(aevs.device), bool(aevs.requires_grad))  # (M, C, A)
+        except _lib.OperandRangeError:
+            # a value left the range of the fp16 operand pieces: switch to the 3 x bfloat16 build and redo
+            if self._variant == "bf16x3" or not _lib.available("bf16x3"):
+                raise
+            warnings.warn("torchani_b200: operand range of the 2 x fp16 GEMM format exceeded; switching this "
+                          "container to the 3 x bfloat16 build of the library")
+            self.use_variant("bf16x3")
+            e_m = _MLPFunction.apply(aevs, elem_idxs, self.packed(aevs.device), bool(aevs.requires_grad))
+        nets = self._packed
         if ensemble_values:
             out = e_m[self.active_members_idxs]
             return out if atomic else out.sum(-1)
