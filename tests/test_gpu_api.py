@@ -462,9 +462,9 @@ def test_operand_range_falls_back_to_the_bf16x3_build():
         per = {}
         for s, layers in wm.items():
             (w1, b1), rest = layers[0], layers[1:]
-            # x 3000 into layer 1, x 1/3000 out of layer 2's input side: activations of layer 1 reach ~1e4
+            # x 30000 into layer 1, x 1/30000 on layer 2's input side: activations of layer 1 reach ~1e4-1e5
             (w2, b2) = rest[0]
-            per[s] = [(w1 * 3000.0, b1 * 3000.0), (w2 / 3000.0, b2)] + list(rest[1:])
+            per[s] = [(w1 * 30000.0, b1 * 30000.0), (w2 / 30000.0, b2)] + list(rest[1:])
         scaled.append(per)
     om_scaled = om._replace(weights=scaled)
     rec = load_golden("water30_pbc_ani2x")
@@ -477,7 +477,7 @@ def test_operand_range_falls_back_to_the_bf16x3_build():
     with warnings.catch_warnings(record=True) as caught:
         warnings.simplefilter("always")
         e, f = model.energies_and_forces(species.to(DEV), c, cell.float().to(DEV), pbc.to(DEV))
-    assert any("bf16" in str(w.message) for w in caught)
+    assert any("bfloat16" in str(w.message) for w in caught)
     assert model.neural_networks._variant == "bf16x3" and model.engine(torch.device(DEV)).variant == "bf16x3"
     scale = float(ref["forces"].abs().max())
     assert float((f.cpu().double() - ref["forces"]).abs().max()) < 1e-4 * max(1.0, scale)

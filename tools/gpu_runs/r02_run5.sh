@@ -1,0 +1,23 @@
+#!/bin/bash
+# round 2, GPU run 5: GPU suite (all failures reported), fused MLP with the signal warp, A/B
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -rfEs --tb=short > gpurun_out/r02_run5_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02_run5_pytest.log
+grep -v "^  File\|^Extension" gpurun_out/r02_run5_pytest.log | tail -60
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --config ${CFG:-water10k} --steps 20 --warmup 5 --cpu-steps 0 > gpurun_out/r02_run5_$name.json 2> gpurun_out/r02_run5_$name.err; echo "$name rc=$?"
+  python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/r02_run5_$name.json").read().strip().splitlines()[-1])
+    print("$name", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["ms_per_step"],4), {k: round(v,4) for k,v in d["stage_ms"].items()}, "frac", round(d["roofline"]["frac"],3))
+except Exception as e:
+    print("$name failed", e); print(open("gpurun_out/r02_run5_$name.err").read()[-1500:])
+PY
+}
+run fused X=1
+run unfused_mlp ANI_B200_MLP_FUSED=0
+CFG=water1k run fused_1k X=1
+CFG=water1k run unfused_1k ANI_B200_MLP_FUSED=0
+CFG=protein50k run fused_50k X=1
+CFG=protein50k run unfused_50k ANI_B200_MLP_FUSED=0

@@ -1210,7 +1210,9 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   A.bin_of = scratch_i32;
   A.slot = scratch_i32 + n;
   A.tmp_list = scratch_i32 + 2 * (size_t)n;
-  A.bin_count = scratch_i32 + 3 * (size_t)n;
+  // (two words at a FIXED place, outside the per-step zero-fill: the state of the device-wide barrier)
+  int32_t* grid_bar = scratch_i32 + 3 * (size_t)n;
+  A.bin_count = grid_bar + 2;
   A.counter = A.bin_count + max_bins + 1;
   A.present = A.counter + 1;
   A.chunk_hist = A.present + 1;
@@ -1237,7 +1239,7 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   if (fused) {
     // one persistent launch, device-wide barriers between the phases; every block must be resident:
     // 2 blocks of 256 threads per SM at most (the kernel allows far more)
-    int32_t* bar = A.species_base + ANI_MAX_SPECIES;  // two words outside the per-step zero-fill
+    int32_t* bar = grid_bar;
     const int blocks = min(2 * num_sms, max(1, nb));
     k_prep_fused<<<blocks, 256, 0, st>>>(A, bar, (int)zeroed);
   } else {

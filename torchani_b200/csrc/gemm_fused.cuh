@@ -41,12 +41,18 @@ struct FusedArgs {
   int dep[MAX_PHASES];    // phase whose row-tile counters the units of this phase wait on (-1: none)
   int32_t* sync;          // [MAX_PHASES][sync_stride] arrivals per (phase, row tile); zeroed by the launcher
   int sync_stride;
+  int prefetch_b;         // issue the weight copies of a unit's first K-blocks before waiting for its inputs
   Args ph[MAX_PHASES];
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void red_release_gpu(int32_t* p, int v) {
@@ -57,7 +63,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"   // non-blocking (try_wait may suspend the thread)
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
@@ -85,17 +91,23 @@ struct UnitRef {
   int phase, local;
 };
 
-// ---- the epilogue of one tile, one instantiation per EPI (switch at tile granularity) -----------------
+// ---- the epilogue of one tile with EIGHT epilogue warps (thread = row, warps w and w + 4 alternate 32-column
+// groups, TMEM loads one half group ahead): one instantiation per EPI, switch at tile granularity ----------------
 template <int EPI>
-__device__ __forceinline__ void tile_epilogue(const Args& args, const TileMap& tm, const Tile& tl, const Species& sp,
+__device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& tm, const Tile& tl, const Species& sp,
                                               uint32_t taddr, unsigned char* sb0, int epi_bufs, uint32_t& buf,
                                               const float* __restrict__ bias, const float* __restrict__ w4,
-                                              float* e_part, int warp, int lane, const uint32_t (&my_off)[4],
-                                              const uint32_t (&st_off)[4], uint64_t* tfull_bar, uint32_t tfull_parity,
-                                              float& omax, int& groups_committed) {
+                                              float* e_part, int warp, int lane, uint64_t* tfull_bar,
+                                              uint32_t tfull_parity, float& omax, int& groups_committed) {
   const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
   const int quad = warp & 3, half = warp >> 2;
   const int r_tile = quad * 32 + lane;
+  uint32_t my_off[4], st_off[4];
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    my_off[ch] = swz_off(r_tile, ch);   // inside a 128-row piece (global)
+    st_off[ch] = swz_off(lane, ch);     // inside this warp's 32-row staging image (shared)
+  }
   const float acc_scale = sp.acc_scale;
   const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward);
   const int my_row = tl.rt * TM + r_tile;
@@ -120,9 +132,11 @@ __device__ __forceinline__ void tile_epilogue(const Args& args, const TileMap& t
       yq[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]);
     }
   };
-  if (EPI == EPI_MUL_DCELU && half < ngroups) load_y(half, 0);  // overlaps the wait for the accumulator
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after();
+  // (only now: the accumulator barrier is what orders this warp after the producer's acquire of the row tile's
+  // inputs -- the stored activation read here was written by an earlier phase, possibly moments ago)
+  if (EPI == EPI_MUL_DCELU && half < ngroups) load_y(half, 0);
 
   auto process = [&](int g, int hh, const uint32_t (&r)[16]) {
     float y[16];
@@ -223,18 +237,166 @@ __device__ __forceinline__ void tile_epilogue(const Args& args, const TileMap& t
   }
 }
 
-// ---- the kernel -----------------------------------------------------------------------------
-constexpr int SIGNAL_WARP = NUM_EPI_WARPS + 2;        // warp 10: publishes unit completions (keeps the fences off the epilogue)
-constexpr int FUSED_THREADS = THREADS + 32;           // 352
+// ---- the epilogue of one tile, one instantiation per EPI (switch at tile granularity) -----------------
+// SIXTEEN epilogue warps (the single-phase kernel has eight): the step is bound by its epilogues -- 128 elements per
+// thread and tile at ~12 dependent instructions each, two warps per scheduler -- so the fused kernel puts four warps
+// on every scheduler.  Warp w: TMEM lane quadrant w & 3; the four warps of a quadrant form two PAIRS (w >> 3) that take
+// alternate 32-column groups, and inside a pair the warps take one 16-column half each ((w >> 2) & 1).  A pair shares
+// one store-staging buffer per group: both warps write their half of every row, meet at a 64-thread named barrier, and
+// the first warp of the pair hands the finished 2 KB images to the TMA.
+constexpr int fused_threads(int nw) { return (nw + 3) * 32; }  // epilogue warps + MMA + producer + signal warp
 
-__global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_constant__ FusedArgs F) {
+__device__ __forceinline__ void pair_barrier(int id) {
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+
+template <int EPI>
+__device__ __forceinline__ void tile_epilogue16(const Args& args, const TileMap& tm, const Tile& tl, const Species& sp,
+                                              uint32_t taddr, unsigned char* sb0, int epi_bufs, uint32_t& buf,
+                                              const float* __restrict__ bias, const float* __restrict__ w4,
+                                              float* e_part, int warp, int lane, uint64_t* tfull_bar,
+                                              uint32_t tfull_parity, float& omax, int& groups_committed) {
+  const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
+  const int quad = warp & 3, hh = (warp >> 2) & 1, pairidx = warp >> 3;
+  const int bar_id = 2 + quad * 2 + pairidx;  // named barriers 2..9 (0 = __syncthreads, 1 = all epilogue warps)
+  const int r_tile = quad * 32 + lane;
+  const float acc_scale = sp.acc_scale;
+  const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward);
+  const int my_row = tl.rt * TM + r_tile;
+  float e_acc = 0.f, seed = 0.f;
+  bool row_valid = false;
+  if (EPI == EPI_HEAD) {
+    row_valid = args.row_atom[my_row] >= 0;
+    seed = row_valid ? args.member_scale[tl.mem] : 0.f;
+  }
+  unsigned char* ct = reinterpret_cast<unsigned char*>(args.C) +
+                      ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
+  float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
+  const int ngroups = tl.bn / 32;
+  // byte offsets of this thread's two 16-byte chunks (columns 16 hh .. 16 hh + 15 of a 32-column group): inside a
+  // 128-row piece in global memory, and inside the pair's 32-row staging image
+  const uint32_t g_off0 = swz_off(r_tile, 2 * hh), g_off1 = swz_off(r_tile, 2 * hh + 1);
+  const uint32_t s_off0 = swz_off(lane, 2 * hh), s_off1 = swz_off(lane, 2 * hh + 1);
+  uint4 yq[2 * PARTS];
+  auto load_y = [&](int g) {
+    const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+      // (plain cached loads: this SM has not read these lines before in this launch, so the L1 cannot hold a stale
+      // copy of what another SM's TMA stores wrote in an earlier phase)
+      yq[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + g_off0);
+      yq[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + g_off1);
+    }
+  };
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+  // (only now: the accumulator barrier is what orders this warp after the producer's acquire of the row tile's inputs)
+  if (EPI == EPI_MUL_DCELU && pairidx < ngroups) load_y(pairidx);
+
+  for (int g = pairidx; g < ngroups; g += 2) {
+    uint32_t r[16];
+    tmem_ld16_issue(taddr + g * 32 + hh * 16, r);
+    float y[16];
+    if (EPI == EPI_MUL_DCELU) {
+      join_chunk(yq, y);
+      join_chunk(yq + 1, y + 8);
+      if (g + 2 < ngroups) load_y(g + 2);  // prefetch the next group this warp handles
+    }
+    unsigned char* sb = sb0 + buf * EPI_STAGE_BYTES;
+    if (tiled_out) {
+      // the staging buffer was handed to the TMA epi_bufs groups ago by the first warp of the pair
+      if (hh == 0 && lane == 0) {
+        if (epi_bufs == 2)
+          bulk_wait_read<1>();
+        else
+          bulk_wait_read<0>();
+      }
+      pair_barrier(bar_id);
+    }
+    tmem_ld_wait(r);
+    const int c0 = g * 32 + hh * 16;
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v = __uint_as_float(r[j]) * acc_scale;
+      if (EPI == EPI_BIAS_CELU) {
+        v = celu(v + bias[c0 + j], cc);
+      } else if (EPI == EPI_MUL_DCELU) {
+        v *= dcelu_from_out(y[j] * args.y_inv_scale, cc);
+      } else if (EPI == EPI_HEAD) {
+        const float w = w4[c0 + j];
+        const float a = celu(v + bias[c0 + j], cc);
+        e_acc = fmaf(a, w, e_acc);
+        v = seed * w * dcelu_from_out(a, cc);
+      }
+      if (EPI != EPI_PLAIN) {
+        v *= args.out_scale;
+        omax = fmaxf(omax, fabsf(v));
+      }
+      o[j] = v;
+    }
+    if (EPI == EPI_PLAIN) {
+      const int col = (tm.nb_count >= 0 ? tm.nb[tl.n0 / 32 + g] * 32 : tl.n0 + g * 32) + hh * 16;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v4 = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        if (args.c_accumulate)
+          red_add_v4(cplain + col + 4 * q, v4);
+        else
+          *reinterpret_cast<float4*>(cplain + col + 4 * q) = v4;
+      }
+    } else if (tiled_out) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t w[4][PARTS];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_pair(o[8 * c + 2 * i], o[8 * c + 2 * i + 1], w[i]);
+        const uint32_t off = c == 0 ? s_off0 : s_off1;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p)
+          *reinterpret_cast<uint4*>(sb + p * EPI_PART_BYTES + off) = make_uint4(w[0][p], w[1][p], w[2][p], w[3][p]);
+      }
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA
+      pair_barrier(bar_id);
+      if (hh == 0) {
+        if (lane == 0) {
+          unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES + quad * EPI_PART_BYTES;
+#pragma unroll
+          for (int p = 0; p < PARTS; ++p) bulk_s2g(blk + p * A_PART_BYTES, sb + p * EPI_PART_BYTES, EPI_PART_BYTES);
+          bulk_commit();
+        }
+        ++groups_committed;
+      }
+      if (epi_bufs == 2) buf ^= 1;
+    }
+  }
+  if (EPI == EPI_HEAD) {
+    // the four warps of a row hold different column groups / halves: combine through shared memory
+    e_part[warp * 32 + lane] = e_acc;
+    asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
+    if (warp < 4)
+      args.e_member[(size_t)tl.mem * args.rows_cap + my_row] =
+          row_valid ? e_part[warp * 32 + lane] + e_part[(warp + 4) * 32 + lane] + e_part[(warp + 8) * 32 + lane] +
+                          e_part[(warp + 12) * 32 + lane] + sp.b4[tl.mem]
+                    : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
+  }
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+// NW = 8: thread = row, two warps per quadrant (tile_epilogue8).  NW = 16: warp pairs per 16-column half
+// (tile_epilogue16).  Measured on B200 (profiles/): see DESIGN.md 4.1 for which one runs by default.
+template <int NW>
+__global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid_constant__ FusedArgs F) {
+  constexpr int FEPI_WARPS = NW, F_MMA_WARP = NW, F_PROD_WARP = NW + 1, F_SIGNAL_WARP = NW + 2;
+  constexpr int EPI_SETS = NW == 16 ? 8 : NW;  // store-staging buffer sets: per warp pair (16) or per warp (8)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ TileMap tms[MAX_PHASES];
   __shared__ int phase_base[MAX_PHASES + 1];
   __shared__ int s_epi_bufs;
   __shared__ int s_done;   // arrivals of epilogue warps: 8 per completed unit (stores landed), monotonic
-  __shared__ float e_part[NUM_EPI_WARPS * 32];
+  __shared__ float e_part[NW * 32];
   __shared__ __align__(16) float s_bias[2][TN_MAX];
   __shared__ __align__(16) float s_w4[2][TN_MAX];
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
@@ -260,24 +422,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
     s_epi_bufs = bufs;
     s_done = 0;
     for (int p = 0; p < NP; ++p)
-      tms[p].stages = max(1, min(MAX_STAGES, (AVAIL - bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tms[p].stage_bytes));
+      tms[p].stages = max(1, min(MAX_STAGES, (AVAIL - bufs * EPI_SETS * EPI_STAGE_BYTES) / tms[p].stage_bytes));
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], NUM_EPI_WARPS);
+      mbar_init(&tempty[i], FEPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == F_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int EPI_BUFS = s_epi_bufs;
-  unsigned char* epi_stage = smem + AVAIL - EPI_BUFS * NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  unsigned char* epi_stage = smem + AVAIL - EPI_BUFS * EPI_SETS * EPI_STAGE_BYTES;
   const int total_units = phase_base[NP];
   auto find_phase = [&](int g) {
     int p = 0;
@@ -287,10 +449,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
   // arrivals the row tile `rt` is owed by phase d: one per unit of the row tile
   auto owed = [&](int d, int s) { return F.ph[d].members * tms[d].ntn[s]; };
 
-  if (warp == PROD_WARP) {
+  if (warp == F_PROD_WARP) {
     // ================================ producer (TMA) ================================
     uint32_t stage = 0, empty_par = 0xffffffffu;
     int cur_phase = -1, STAGES = 1, STAGE_BYTES = 0;
+    int ahead = 0;   // counter of the NEXT unit's inputs, read (relaxed) while this unit's copies are issued
+    bool ahead_valid = false;
     for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
       const int p = find_phase(g);
       const Args& args = F.ph[p];
@@ -325,37 +489,85 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
         g_src = (size_t)n0s * nkb_all * (PARTS * ROW_BYTES) + (size_t)(row0 - n0s) * ROW_BYTES +
                 (size_t)gpart * g_bns * ROW_BYTES;
       }
-      // data-flow: the A operand of this unit is the output of phase dep[p] for this row tile
-      if (F.dep[p] >= 0) {
+      // one K-block = A (16 / 24 KB, produced by an earlier phase) + B (weights, never produced in this launch).
+      // `arm`: wait for the slot, announce the bytes; `load_b` / `load_a`: the two halves of the transaction
+      auto arm = [&](uint32_t st_idx) {
+        mbar_wait(&empty[st_idx], (empty_par >> st_idx) & 1u);
+        empty_par ^= 1u << st_idx;
+        if (lane == 0) mbar_arrive_expect_tx(&full[st_idx], A_BLOCK_BYTES + PARTS * b_bytes);
+        __syncwarp();
+      };
+      auto load_b = [&](uint32_t st_idx, int kb) {
+        unsigned char* st = smem + st_idx * STAGE_BYTES;
+        const int kbb = (tm.kb_count >= 0 ? tm.kb[kb] : kb) + kb_boff;
+        if (dense) {
+          if (lane == 0) {
+            const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
+            bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[st_idx]);
+          }
+        } else if (g_active) {
+          bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,
+                   Bm + g_src + (size_t)kbb * g_bns * (PARTS * ROW_BYTES), 32 * ROW_BYTES, &full[st_idx]);
+        }
+      };
+      auto load_a = [&](uint32_t st_idx, int kb) {
+        const int kbi = tm.kb_count >= 0 ? tm.kb[kb] : kb;
+        if (lane == 0) bulk_g2s(smem + st_idx * STAGE_BYTES, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[st_idx]);
+      };
+      int kb_first = 0;
+      if (F.dep[p] >= 0 && !F.prefetch_b) {
+        // data-flow: the A operand of this unit is the output of phase dep[p] for this row tile.  The counter was
+        // already looked at one unit ago (relaxed load, latency hidden behind that unit's copies): in the common
+        // case it had reached its target and an acquire fence is all that is left to do
+        if (lane == 0) {
+          const int need = owed(F.dep[p], tl.s);
+          if (ahead_valid && ahead >= need)
+            __threadfence();
+          else
+            wait_counter(F.sync + (size_t)F.dep[p] * F.sync_stride + tl.rt, need, args.status);
+          fence_proxy_async_all();  // the bulk copies below (async proxy) are ordered after the acquire
+        }
+        __syncwarp();
+      } else if (F.dep[p] >= 0) {
+        // data-flow: the A operand of this unit is the output of phase dep[p] for this row tile.  The weights do
+        // not depend on anything: their copies of the first K-blocks are in flight while we wait
+        const int pre = min(nkb, STAGES);
+        for (int kb = 0; kb < pre; ++kb) {
+          const uint32_t st_idx = (stage + kb) % (uint32_t)STAGES;
+          arm(st_idx);
+          load_b(st_idx, kb);
+        }
         if (lane == 0) {
           wait_counter(F.sync + (size_t)F.dep[p] * F.sync_stride + tl.rt, owed(F.dep[p], tl.s), args.status);
           fence_proxy_async_all();  // the bulk copies below (async proxy) are ordered after the acquire
         }
         __syncwarp();
+        for (int kb = 0; kb < pre; ++kb) load_a((stage + kb) % (uint32_t)STAGES, kb);
+        stage = (stage + pre) % (uint32_t)STAGES;
+        kb_first = pre;
       }
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty[stage], (empty_par >> stage) & 1u);
-        empty_par ^= 1u << stage;
-        unsigned char* st = smem + stage * STAGE_BYTES;
-        const int kbi = tm.kb_count >= 0 ? tm.kb[kb] : kb;
-        const int kbb = kbi + kb_boff;
-        if (lane == 0) {
-          mbar_arrive_expect_tx(&full[stage], A_BLOCK_BYTES + PARTS * b_bytes);
-          bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
-          if (dense) {
-            const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
-            bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[stage]);
+      // look ahead: the counter the next unit of this CTA will wait on
+      ahead_valid = false;
+      {
+        const int g2 = g + (int)gridDim.x;
+        if (lane == 0 && g2 < total_units) {
+          const int p2 = find_phase(g2);
+          if (F.dep[p2] >= 0) {
+            const Tile t2 = decode_tile(F.ph[p2], tms[p2], g2 - phase_base[p2]);
+            ahead = ld_relaxed_gpu(F.sync + (size_t)F.dep[p2] * F.sync_stride + t2.rt);
+            ahead_valid = true;
           }
         }
-        __syncwarp();
-        if (g_active)
-          bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,
-                   Bm + g_src + (size_t)kbb * g_bns * (PARTS * ROW_BYTES), 32 * ROW_BYTES, &full[stage]);
+      }
+      for (int kb = kb_first; kb < nkb; ++kb) {
+        arm(stage);
+        load_a(stage, kb);
+        load_b(stage, kb);
         __syncwarp();
         if (++stage == (uint32_t)STAGES) stage = 0;
       }
     }
-  } else if (warp == MMA_WARP) {
+  } else if (warp == F_MMA_WARP) {
     // ================================ MMA issuer ================================
     uint32_t stage = 0, full_par = 0u, acc = 0, acc_phase = 0;
     int cur_phase = -1, STAGES = 1, STAGE_BYTES = 0;
@@ -415,7 +627,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
         acc_phase ^= 1;
       }
     }
-  } else if (warp == SIGNAL_WARP) {
+  } else if (warp == F_SIGNAL_WARP) {
     // ================================ completion signals ================================
     // unit k of this CTA is complete when all eight epilogue warps have seen its stores land (s_done >= 8 (k+1));
     // one fence + release-add per unit, off the epilogue's critical path
@@ -426,7 +638,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
         const int p = find_phase(g);
         const Tile tl = decode_tile(F.ph[p], tms[p], g - phase_base[p]);
         const long long t0 = clock64();
-        while (*done < NUM_EPI_WARPS * (k + 1)) {
+        while (*done < FEPI_WARPS * (k + 1)) {
           __nanosleep(64);
           if (clock64() - t0 > 4 * FUSED_SPIN_LIMIT) break;
         }
@@ -444,17 +656,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
     uint32_t acc = 0, acc_phase = 0, buf = 0;
     float omax = 0.f;
     const int quad = warp & 3;
-    const int r_tile = quad * 32 + lane;
-    uint32_t my_off[4], st_off[4];
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      my_off[ch] = swz_off(r_tile, ch);
-      st_off[ch] = swz_off(lane, ch);
-    }
-    unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
+    // store staging: one buffer set per warp (NW = 8) or per warp pair (NW = 16: pair id = quadrant * 2 + (w >> 3))
+    unsigned char* sb0 = epi_stage + (NW == 16 ? quad * 2 + (warp >> 3) : warp) * (EPI_BUFS * EPI_STAGE_BYTES);
     // completion bookkeeping: the unit whose stores may still be in flight
     bool pending = false;
     int pend_groups = 0;  // bulk groups this warp committed for the pending unit (0: nothing to wait for)
+    int pend_phase = -1, pend_rt = -1;
     // complete the pending unit: its bulk stores have landed (all of this lane's groups except the `newer`
     // most recent ones, which belong to the unit that was just finished), then one arrival in shared memory
     auto flush_pending = [&](int newer) {
@@ -488,34 +695,66 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
           s_bias[acc][c] = sp.bias[(size_t)tl.mem * sp.bias_mstride + tl.n0 + c];
           if (epi == EPI_HEAD) s_w4[acc][c] = sp.w4[(size_t)tl.mem * sp.N + c];
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(FEPI_WARPS * 32) : "memory");
       }
-      // about to idle on the accumulator?  then the stores of the previous unit can be completed for free
-      if (pending && !mbar_try(&tfull[acc], acc_phase)) flush_pending(0);
-      if (epi == EPI_MUL_DCELU && F.dep[p] >= 0) {
-        // the stored activation this epilogue reads (and overwrites) was written by an earlier phase of this
-        // row tile; the chain of dependencies implies it is complete once dep[p] is: acquire it here too
-        if (lane == 0) wait_counter(F.sync + (size_t)F.dep[p] * F.sync_stride + tl.rt, owed(F.dep[p], tl.s), args.status);
-        __syncwarp();
+      // The pending unit is normally completed one unit late (at the end of this one).  It is completed NOW if this
+      // unit waits on it (same row tile, producer phase: otherwise the CTA would wait for itself) or if the
+      // accumulator has not shown up after a short grace period: whenever an epilogue warp blocks for real it has
+      // published everything it owes, which is what makes the data-flow deadlock-free (a blocked CTA never holds
+      // back a completion); the grace period keeps the 1-2 us store-completion wait off the critical path when the
+      // main loop is only marginally behind
+      if (pending) {
+        bool now = pend_phase == F.dep[p] && pend_rt == tl.rt;
+        if (!now) {
+          now = true;
+          for (int spin = 0; spin < 24; ++spin) {
+            if (mbar_try(&tfull[acc], acc_phase)) {
+              now = false;
+              break;
+            }
+            __nanosleep(64);
+          }
+        }
+        if (now) flush_pending(0);
       }
+      // (EPI_MUL_DCELU reads the stored activation an earlier phase wrote for this row tile.  No counter poll here:
+      // the producer lane acquired the counter before it issued this unit's copies, and this warp is ordered after
+      // that through the full / accumulator mbarriers it waits on -- release.gpu -> acquire.gpu -> CTA-scope
+      // synchronisation is a causality chain; the lines have not been in this SM's L1 before.)
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
       int groups = 0;
       switch (epi) {
         case EPI_BIAS_CELU:
-          tile_epilogue<EPI_BIAS_CELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp,
-                                       lane, my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          if (NW == 16)
+            tile_epilogue16<EPI_BIAS_CELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                 &tfull[acc], acc_phase, omax, groups);
+          else
+            tile_epilogue8<EPI_BIAS_CELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                &tfull[acc], acc_phase, omax, groups);
           break;
         case EPI_MUL_DCELU:
-          tile_epilogue<EPI_MUL_DCELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp,
-                                       lane, my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          if (NW == 16)
+            tile_epilogue16<EPI_MUL_DCELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                 &tfull[acc], acc_phase, omax, groups);
+          else
+            tile_epilogue8<EPI_MUL_DCELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                &tfull[acc], acc_phase, omax, groups);
           break;
         case EPI_HEAD:
-          tile_epilogue<EPI_HEAD>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                  my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          if (NW == 16)
+            tile_epilogue16<EPI_HEAD>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                 &tfull[acc], acc_phase, omax, groups);
+          else
+            tile_epilogue8<EPI_HEAD>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                &tfull[acc], acc_phase, omax, groups);
           break;
         default:
-          tile_epilogue<EPI_PLAIN>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                   my_off, st_off, &tfull[acc], acc_phase, omax, groups);
+          if (NW == 16)
+            tile_epilogue16<EPI_PLAIN>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                 &tfull[acc], acc_phase, omax, groups);
+          else
+            tile_epilogue8<EPI_PLAIN>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
+                                &tfull[acc], acc_phase, omax, groups);
           break;
       }
       // hand the accumulator back
@@ -530,16 +769,18 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) k_mlp_fused(const __grid_con
       flush_pending(groups);   // (a tile has at most 8 column groups: 4 per warp)
       pending = true;
       pend_groups = groups;
+      pend_phase = p;
+      pend_rt = tl.rt;
     }
     flush_pending(0);
     if (ANI_OPND_FP16X2 && F.ph[0].status && !(omax <= OPND_HALF_MAX)) atomicOr(F.ph[0].status, ANI_STATUS_OPERAND_RANGE);
   }
 
   // ---- teardown
-  if (warp < NUM_EPI_WARPS && lane == 0) bulk_wait_all();
+  if (warp < FEPI_WARPS && lane == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == F_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }

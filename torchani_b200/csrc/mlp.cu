@@ -444,6 +444,11 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     F.ph[p] = base;
     fill_phase(F.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward);
   }
+  static const int prefetch_b = []() {
+    const char* e = getenv("ANI_B200_PREFETCH_B");  // 1: issue a unit's weight copies before waiting for its inputs
+    return e && atoi(e) != 0;                       // (measured on B200: no gain at 1k atoms, -4 % at 10k: off)
+  }();
+  F.prefetch_b = prefetch_b;
   F.sync = sync_i32;
   F.sync_stride = rows_cap / ANI_TILE_ROWS;
   cudaMemsetAsync(sync_i32, 0, sizeof(int32_t) * (size_t)tc::MAX_PHASES * F.sync_stride, st);
@@ -454,9 +459,17 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(tc::k_mlp_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
+    cudaFuncSetAttribute(tc::k_mlp_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
+    cudaFuncSetAttribute(tc::k_mlp_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
   }
-  tc::k_mlp_fused<<<num_sms, tc::FUSED_THREADS, tc::FUSED_SMEM_BYTES, st>>>(F);
+  static const int epi_warps = []() {
+    const char* e = getenv("ANI_B200_EPI_WARPS");  // 8 (default) or 16: epilogue warps of the fused kernel
+    return e && atoi(e) == 16 ? 16 : 8;
+  }();
+  if (epi_warps == 16)
+    tc::k_mlp_fused<16><<<num_sms, tc::fused_threads(16), tc::FUSED_SMEM_BYTES, st>>>(F);
+  else
+    tc::k_mlp_fused<8><<<num_sms, tc::fused_threads(8), tc::FUSED_SMEM_BYTES, st>>>(F);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

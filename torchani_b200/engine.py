@@ -455,8 +455,14 @@ class Engine:
         # default: measured on B200 at 10k atoms it changes the step by < 1 us (0.3899 vs 0.3905 ms) --
         # inside the graph the two kernels cost little more than their dependency edges
         self.side_stream = os.environ.get("ANI_B200_SIDE_STREAM", "0") != "0"
-        # ANI_B200_MLP_FUSED=0: the six separate GEMM launches of round 1 (kept for A/B timing)
-        self.mlp_fused = os.environ.get("ANI_B200_MLP_FUSED", "1") != "0"
+        # The MLP of a step: ONE persistent data-flow launch (csrc/gemm_fused.cuh) or the six chained launches of
+        # csrc/gemm_tc.cuh.  Measured on B200 (profiles/r02_*): the data-flow launch wins where ramp / tail / tile
+        # quantisation of six launches matter and the unit list is long enough to hide the layer chain (10 k atoms:
+        # 0.21 vs 0.23 ms); the six launches win for very short lists (1 k atoms: the chain of six dependent layers is
+        # latency-bound either way, and a launch boundary is a cheaper hand-over than a counter) and for very long
+        # ones.  ANI_B200_MLP_FUSED=0 / 1 forces one of them; default "auto" chooses by the number of owned atoms.
+        self.mlp_mode = os.environ.get("ANI_B200_MLP_FUSED", "auto")
+        self.mlp_fused_range = (3000, 30000)
         self._side_stream: tp.Optional[torch.cuda.Stream] = None
         self._ev: tp.List[torch.cuda.Event] = []
         self.stage_events: tp.Dict[str, tp.List[tp.Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
@@ -530,7 +536,7 @@ class Engine:
         if want_virial and (not want_grad or reuse or n_conf != 1):
             raise ValueError("the virial comes out of the force pass of a single system with a freshly built grid")
         key = (n_conf, n_per_conf, bool(pbc), bool(want_grad), lo, hi, self.nets.active_key, bool(reuse), self.skin,
-               bool(want_virial))
+               bool(want_virial), self.mlp_mode)
         if reuse and not self.skin > 0:
             raise ValueError("reuse=True needs Engine.skin > 0 and a previous step that built the grid")
         with torch.cuda.device(self.device):   # the C-ABI launches on the CURRENT device's stream
@@ -559,7 +565,10 @@ class Engine:
         # kernels launched by this library in one step (memsets excluded):
         # prepare 1 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
         # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
-        mlp = (1 + (1 if want_grad else 0)) if self.mlp_fused else (3 + (4 if want_grad else 0))
+        owned = hi - lo
+        fused = (self.mlp_mode == "1" or
+                 (self.mlp_mode not in ("0", "1") and self.mlp_fused_range[0] <= owned <= self.mlp_fused_range[1]))
+        mlp = (1 + (1 if want_grad else 0)) if fused else (3 + (4 if want_grad else 0))
         self.launches_per_step = 1 + (0 if (pbc or n_conf > 1) else 1) + 1 + mlp + (1 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
         virial = ws.virial.sum(0).view(3, 3) if want_virial else None
@@ -624,6 +633,9 @@ class Engine:
                 ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
                 ptr(ws.member_atomic), ws.energies_ptr, stream_handle)
 
+        owned = hi - lo
+        self.mlp_fused = (self.mlp_mode == "1" or
+                          (self.mlp_mode not in ("0", "1") and self.mlp_fused_range[0] <= owned <= self.mlp_fused_range[1]))
         if not split and self.mlp_fused:
             # the six GEMMs of the step as ONE persistent data-flow launch (csrc/gemm_fused.cuh)
             self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_step(
