@@ -22,6 +22,35 @@
 
 namespace ani {
 
+// ---- TMA bulk copy global -> shared with mbarrier completion (staging of the bucket ranges) ----------
+__device__ __forceinline__ uint32_t aev_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void aev_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(aev_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void aev_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(aev_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void aev_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   aev_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(aev_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void aev_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "AEV_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni AEV_WAIT_DONE;\n\t"
+      "bra.uni AEV_WAIT_LOOP;\n\t"
+      "AEV_WAIT_DONE:\n\t"
+      "}" ::"r"(aev_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 constexpr int AEV_WARPS = 4;  // warps (= central atoms) per CTA
 #ifndef ANI_AEV_BWD_MIN_CTAS
 #define ANI_AEV_BWD_MIN_CTAS 7  // register budget of the backward kernel: 7 CTAs (28 warps) per SM
@@ -505,6 +534,7 @@ struct CtaStage {
   int adj[ANI_MAX_SPECIES][NRANGE];            // off[s][o] - (candidates of lower species in range o)
   int wbin[AEV_FWD_WARPS];
   unsigned char t2o[T2O_CAP];                  // range of the t-th candidate (range-major numbering)
+  unsigned long long tma_bar;                  // mbarrier of the TMA bulk copies that stage the bucket ranges
 };
 
 template <int NA, int NZ>
@@ -534,17 +564,20 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     myb = sbin[i];
   }
   if (lane == 0) C.wbin[warp] = myb;
+  if (tid == 0) aev_mbar_init(reinterpret_cast<uint64_t*>(&C.tma_bar), 1);
   __syncthreads();
 
   // ---- 1. neighbours within Rcr (and the sub-list within Rca), species segment by species segment
   const float rcr2 = P.rcr * P.rcr, rca2 = P.rca * P.rca;
   const unsigned lt = (1u << lane) - 1u;
   int cnt = 0, cnt_a = 0;
-  if (lane == 0) {
-    s.seg_all[0] = 0;
-    s.seg[0] = 0;
-  }
-  int prev = -1;
+  // TMA staging area: the per-warp arrays of the dynamic shared memory are not in use before the first compaction,
+  // so the raw candidates of the FIRST bucket of the CTA (the only one for most CTAs) land there, range after range,
+  // by cp.async.bulk -- the two staging passes below then read shared memory instead of global memory
+  float4* raw = reinterpret_cast<float4*>(smem_raw);
+  const int raw_cap = (int)min((size_t)CAND_CAP, (AEV_FWD_WARPS * warp_bytes) / sizeof(float4));
+  uint32_t tma_parity = 0;
+  int prev = -1, first_bucket = -1;
   while (true) {
     int cur = 0x7fffffff;
 #pragma unroll
@@ -553,6 +586,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
       if (b > prev && b < cur) cur = b;
     }
     if (cur == 0x7fffffff) break;
+    if (prev == -1) first_bucket = cur;
     prev = cur;
     __syncthreads();  // every warp has chosen `cur`; the tables of the previous phase may be rewritten
     // (a) the 27 candidate ranges of bucket `cur`
@@ -604,6 +638,19 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     }
     __syncthreads();
     const int T = C.r_off[NRANGE];
+    // first bucket of the CTA, neighbourhood fits: one TMA bulk copy per non-empty range (contiguous float4 runs of
+    // the bucket-sorted position array), all completing on one mbarrier
+    const bool staged = prev == first_bucket && T > 0 && T <= raw_cap;
+    if (staged) {
+      if (tid == 0) aev_mbar_expect_tx(reinterpret_cast<uint64_t*>(&C.tma_bar), (uint32_t)T * 16u);
+      if (tid < NRANGE) {
+        const int len = C.r_off[tid + 1] - C.r_off[tid];
+        if (len > 0)
+          aev_bulk_g2s(raw + C.r_off[tid], spos + C.r_lo[tid], (uint32_t)len * 16u, reinterpret_cast<uint64_t*>(&C.tma_bar));
+      }
+      aev_mbar_wait(reinterpret_cast<uint64_t*>(&C.tma_bar), tma_parity);
+      tma_parity ^= 1u;
+    }
     // flat (range-major) candidate number -> range: branch-free binary search over the prefix
     auto find_range = [&](int t) {
       int o = 0;
@@ -625,7 +672,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
           const int o = find_range(t);
           oo[j] = o;
           if (t < T2O_CAP) C.t2o[t] = (unsigned char)o;
-          spv[j] = __float_as_int(spos[C.r_lo[o] + (t - C.r_off[o])].w);
+          spv[j] = __float_as_int(staged ? raw[t].w : spos[C.r_lo[o] + (t - C.r_off[o])].w);
         }
       }
 #pragma unroll
@@ -683,7 +730,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
             const int o = t < T2O_CAP ? (int)C.t2o[t] : find_range(t);
             oo[j] = o;
             cc[j] = C.r_lo[o] + (t - C.r_off[o]);
-            pp[j] = spos[cc[j]];
+            pp[j] = staged ? raw[t] : spos[cc[j]];
           }
         }
 #pragma unroll
@@ -702,6 +749,13 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
       __syncthreads();
       // (d) the warps of this bucket compact their neighbours out of the window
       if (mine) {
+        if (F0 == 0) {
+          if (lane == 0) {
+            s.seg_all[0] = 0;
+            s.seg[0] = 0;
+          }
+          __syncwarp();
+        }
         for (int sp = 0; sp < S; ++sp) {
           const int a = max(F0, C.off[sp * NRANGE]);
           const int b = min(F0 + CAND_CAP, C.off[(sp + 1) * NRANGE]);

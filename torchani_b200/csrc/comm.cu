@@ -63,6 +63,7 @@ __device__ __forceinline__ void peer_barrier(const CommDev& c, int phase, unsign
   const int t = threadIdx.x;
   if (t < c.world) {
     const size_t slot = ((size_t)phase * COMM_BLOCKS + blockIdx.x) * COMM_MAX_WORLD;
+    __threadfence_system();
     st_release_sys(c.flags[t] + slot + c.rank, e);
     const unsigned* mine = c.flags[c.rank] + slot + t;
     const long long t0 = clock64();
@@ -80,9 +81,9 @@ __global__ void __launch_bounds__(COMM_THREADS) k_allreduce_partials(const __gri
                                                                      float* __restrict__ out32,
                                                                      double* __restrict__ out64) {
   const unsigned e = c.epoch[blockIdx.x] + 1u;
-  // the partial sums of this rank were written by earlier kernels of this stream (device-wide visible at the
-  // kernel boundary); make them visible system-wide before telling the peers
-  __threadfence_system();
+  // the partial sums of this rank were written by earlier kernels of this stream: complete and visible in this
+  // GPU's L2 at the kernel boundary, which is where the peers' NVLink reads are served from; the release of the flag
+  // store (peer_barrier) orders them for the peers
   peer_barrier(c, 0, e);
   const long long n4 = c.n32 >> 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {

@@ -456,13 +456,15 @@ class Engine:
         # inside the graph the two kernels cost little more than their dependency edges
         self.side_stream = os.environ.get("ANI_B200_SIDE_STREAM", "0") != "0"
         # The MLP of a step: ONE persistent data-flow launch (csrc/gemm_fused.cuh) or the six chained launches of
-        # csrc/gemm_tc.cuh.  Measured on B200 (profiles/r02_*): the data-flow launch wins where ramp / tail / tile
-        # quantisation of six launches matter and the unit list is long enough to hide the layer chain (10 k atoms:
-        # 0.21 vs 0.23 ms); the six launches win for very short lists (1 k atoms: the chain of six dependent layers is
-        # latency-bound either way, and a launch boundary is a cheaper hand-over than a counter) and for very long
-        # ones.  ANI_B200_MLP_FUSED=0 / 1 forces one of them; default "auto" chooses by the number of owned atoms.
+        # csrc/gemm_tc.cuh -- the same tile code either way.  Measured on B200 over 2 k - 50 k atoms
+        # (profiles/r02_sweep.md): the two are equal except where the chained launches quantise badly -- every one of
+        # the six launches runs (row tiles x members) units on 148 persistent CTAs, e.g. 4.2 units per CTA at 10 k
+        # atoms = 84 % balance, six times -- which the single list of the data-flow launch avoids (10 k atoms: 0.219 vs
+        # 0.235 ms); for short lists (< 3 waves) the chained launches win, a launch boundary being a cheaper hand-over
+        # of a row tile than an L2 counter when the six-layer chain is exposed.  "auto" applies exactly that rule;
+        # ANI_B200_MLP_FUSED=0 / 1 forces one of them.
         self.mlp_mode = os.environ.get("ANI_B200_MLP_FUSED", "auto")
-        self.mlp_fused_range = (3000, 30000)
+        self._num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self._side_stream: tp.Optional[torch.cuda.Stream] = None
         self._ev: tp.List[torch.cuda.Event] = []
         self.stage_events: tp.Dict[str, tp.List[tp.Tuple[torch.cuda.Event, torch.cuda.Event]]] = {}
@@ -565,10 +567,7 @@ class Engine:
         # kernels launched by this library in one step (memsets excluded):
         # prepare 1 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
         # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
-        owned = hi - lo
-        fused = (self.mlp_mode == "1" or
-                 (self.mlp_mode not in ("0", "1") and self.mlp_fused_range[0] <= owned <= self.mlp_fused_range[1]))
-        mlp = (1 + (1 if want_grad else 0)) if fused else (3 + (4 if want_grad else 0))
+        mlp = (1 + (1 if want_grad else 0)) if self._use_dataflow_mlp(hi - lo) else (3 + (4 if want_grad else 0))
         self.launches_per_step = 1 + (0 if (pbc or n_conf > 1) else 1) + 1 + mlp + (1 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
         virial = ws.virial.sum(0).view(3, 3) if want_virial else None
@@ -633,9 +632,7 @@ class Engine:
                 ptr(ws.species_i32), n, lo, hi, n_conf, n_per_conf, ptr(self.sae), ptr(ws.atomic),
                 ptr(ws.member_atomic), ws.energies_ptr, stream_handle)
 
-        owned = hi - lo
-        self.mlp_fused = (self.mlp_mode == "1" or
-                          (self.mlp_mode not in ("0", "1") and self.mlp_fused_range[0] <= owned <= self.mlp_fused_range[1]))
+        self.mlp_fused = self._use_dataflow_mlp(hi - lo)
         if not split and self.mlp_fused:
             # the six GEMMs of the step as ONE persistent data-flow launch (csrc/gemm_fused.cuh)
             self._timed("mlp_forward_backward", lambda: L.ani_b200_mlp_step(
@@ -680,6 +677,14 @@ class Engine:
                 ws.reducer.launch(ws.grad, ws.energies)
                 return 0
             self._timed("allreduce", reduce_all)
+
+    def _use_dataflow_mlp(self, owned: int) -> bool:
+        """One data-flow launch (True) or six chained launches (False) for `owned` atoms; see __init__."""
+        if self.mlp_mode in ("0", "1"):
+            return self.mlp_mode == "1"
+        units = (-(-owned // TILE) + 1) * self.nets.num_members     # per layer: row tiles x members (>= 1 column tile)
+        waves = units / self._num_sms
+        return waves >= 3.0 and waves / math.ceil(waves) < 0.9
 
     def note_composition(self, ws: Workspace) -> None:
         """Before a graph capture (the shape has already run eagerly): read the element mask of the last
