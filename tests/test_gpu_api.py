@@ -490,3 +490,44 @@ def test_operand_range_falls_back_to_the_bf16x3_build():
         e2 = model2.neural_networks(species.to(DEV), aev)
     assert model2.neural_networks._variant == "bf16x3"
     assert abs(float(e2[0]) - float(ref["energy_nn"][0])) < 1e-5 * abs(float(ref["energy_nn"][0])) + 1e-3
+
+
+def test_partial_pbc_and_periodic_batches_match_the_oracle():
+    """`all_pairs` generality (neighbors.py:187-275): PBC in only some directions (slab: image shifts along the
+    periodic lattice vectors only) and a batch of conformers in one shared periodic cell."""
+    from torchani_b200 import models, neighbors
+    rec = load_golden("water30_pbc_ani2x")
+    species, coords, cell, _ = golden_inputs(rec, torch.float64)
+    om = oracle_model("2x", torch.float64, "all_pairs")
+    w32 = [{s: [(w.float(), b.float()) for w, b in layers] for s, layers in wm.items()} for wm in om.weights]
+    model = models.from_weight_lists("2x", w32, device=DEV, periodic_table_index=False)
+    sp_d, cell_d = species.to(DEV), cell.float().to(DEV)
+    # --- slab: periodic in x and y only
+    for flags in ([True, True, False], [False, True, False]):
+        pbc = torch.tensor(flags)
+        ref = orc.compute(om, species, coords, cell, pbc)
+        c = coords.float().to(DEV).requires_grad_(True)
+        e = model((sp_d, c), cell_d, pbc.to(DEV)).energies
+        (g,) = torch.autograd.grad(e.sum(), c)
+        assert abs(float(e[0]) - float(ref["energy"][0])) < 5e-3, flags
+        assert_close(f"forces pbc={flags}", -g.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+        aev = model.aev_computer(sp_d, coords.float().to(DEV), cell_d, pbc.to(DEV))
+        assert_close(f"aev pbc={flags}", aev.cpu().numpy(), ref["aev"].numpy(), AEV_RTOL, AEV_ATOL)
+        nb = neighbors.AllPairs()(5.1, sp_d, coords.float().to(DEV), cell_d, pbc.to(DEV))
+        assert nb.indices.shape[1] == int(ref["num_pairs"])
+    # --- periodic batch: two conformers, one cell
+    pbc = torch.tensor([True, True, True])
+    co2 = torch.cat([coords, coords + 0.05 * torch.randn(coords.shape, generator=torch.Generator().manual_seed(3),
+                                                         dtype=torch.float64)])
+    sp2 = torch.cat([species, species])
+    refs = [orc.compute(om, sp2[k:k + 1], co2[k:k + 1], cell, pbc) for k in range(2)]
+    c = co2.float().to(DEV).requires_grad_(True)
+    e = model((sp2.to(DEV), c), cell_d, pbc.to(DEV)).energies
+    assert e.shape == (2,)
+    (g,) = torch.autograd.grad(e.sum(), c)
+    for k in range(2):
+        assert abs(float(e[k]) - float(refs[k]["energy"][0])) < 5e-3
+        assert_close("forces batch", -g[k:k + 1].cpu().numpy(), refs[k]["forces"].numpy(), 0.0, F_ATOL)
+    nb = neighbors.AllPairs()(5.1, sp2.to(DEV), co2.float().to(DEV), cell_d, pbc.to(DEV))
+    assert nb.indices.shape[1] == int(refs[0]["num_pairs"]) + int(refs[1]["num_pairs"])
+    assert int(nb.indices.max()) >= 30      # indices into the flattened (C * A) atoms

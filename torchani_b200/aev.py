@@ -18,7 +18,8 @@ from torch import Tensor
 from . import _lib
 from ._lib import check, ptr
 from .engine import AEVConstants, _linspace
-from .neighbors import BucketGrid, Neighbors, NeighborlistArg, _parse_neighborlist, _validate_inputs
+from .neighbors import (BucketGrid, Neighbors, NeighborlistArg, _parse_neighborlist, _validate_inputs,
+                        effective_periodic_cell)
 
 
 class SpeciesAEV(tp.NamedTuple):
@@ -335,6 +336,9 @@ class AEVComputer(torch.nn.Module):
         assert elem_idxs.dim() == 2
         assert coords.shape == (elem_idxs.shape[0], elem_idxs.shape[1], 3)
         _validate_inputs(self.radial.cutoff, elem_idxs, coords, cell, pbc)
+        if pbc is not None and elem_idxs.shape[0] > 1:   # periodic batch: one conformer at a time
+            return torch.cat([self(elem_idxs[c:c + 1], coords[c:c + 1], cell, pbc) for c in range(elem_idxs.shape[0])])
+        cell = effective_periodic_cell(coords, cell, pbc, self.radial.cutoff)   # PBC in some directions only
         aev = _AEVFunction.apply(coords, elem_idxs, cell, pbc is not None, self)
         if self._last_grid is not None:
             self._last_grid.raise_on_status()

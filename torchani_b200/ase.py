@@ -74,9 +74,15 @@ class Calculator(AseCalculator):
         cell = np.asarray(self.atoms.get_cell(complete=True).array if hasattr(self.atoms.get_cell(complete=True), "array")
                           else self.atoms.get_cell(complete=True), dtype=np.float64)
         pbc = np.asarray(self.atoms.get_pbc(), dtype=bool)
-        if pbc.any() and not pbc.all():
-            raise ValueError("The B200 neighborlists don't support PBC only in some directions")
-        periodic = bool(pbc.all())
+        periodic = bool(pbc.any())
+        if periodic and not pbc.all():
+            # PBC in some directions only (slabs, wires): an equivalent fully periodic cell whose non-periodic
+            # lattice vectors are long enough that no pair within the cutoff crosses them (neighbors.py:214-275
+            # enumerates image shifts along the periodic vectors only -- same pair set)
+            import torch
+            from .neighbors import effective_periodic_cell
+            cell = effective_periodic_cell(torch.from_numpy(positions), torch.from_numpy(cell), torch.from_numpy(pbc),
+                                           float(self.model.cutoff)).numpy()
         if periodic and self.overwrite:
             warnings.warn("'overwrite' set, info about crossing PBC *will be lost*")
             frac = positions @ np.linalg.inv(cell)

@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
                       const int32_t* __restrict__ sbin, const float4* __restrict__ ranges,
                       const int32_t* __restrict__ species_mask, int lo, int hi, const int32_t* __restrict__ row_of,
                       float* __restrict__ aev, int ldx, int layout, int32_t* __restrict__ nbr_cnt,
-                      int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes) {
+                      int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes,
+                      int tma_stage) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CtaStage C;
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     const int T = C.r_off[NRANGE];
     // first bucket of the CTA, neighbourhood fits: one TMA bulk copy per non-empty range (contiguous float4 runs of
     // the bucket-sorted position array), all completing on one mbarrier
-    const bool staged = prev == first_bucket && T > 0 && T <= raw_cap;
+    const bool staged = tma_stage && prev == first_bucket && T > 0 && T <= raw_cap;
     if (staged) {
       if (tid == 0) aev_mbar_expect_tx(reinterpret_cast<uint64_t*>(&C.tma_bar), (uint32_t)T * 16u);
       if (tid < NRANGE) {
@@ -1417,6 +1418,14 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
     const char* e = getenv("ANI_B200_AEV_LEGACY");
     return e && atoi(e) != 0;
   }();
+  // ANI_B200_AEV_TMA=1: stage the candidate ranges of a CTA's first bucket with TMA bulk copies (cp.async.bulk +
+  // mbarrier) instead of per-thread global loads.  Same results; measured on B200 it is SLOWER (67 vs 62 us at 10 k
+  // atoms, 366 vs 340 us at 50 k): 27 copies of ~220 bytes per CTA are too small for the copy engine and every thread
+  // of the CTA idles on the mbarrier, where the batched per-thread loads overlap with their own bookkeeping.  Off.
+  static const int tma_stage = []() {
+    const char* e = getenv("ANI_B200_AEV_TMA");
+    return e && atoi(e) != 0 ? 1 : 0;
+  }();
   if (!ex.start && !legacy) {
     const size_t smem_f = wb * AEV_FWD_WARPS;
     const int blocks_f = (hi - lo + AEV_FWD_WARPS - 1) / AEV_FWD_WARPS;
@@ -1424,12 +1433,14 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
       auto k = k_aev_forward_cta<8, 4>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
       k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
-                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
+                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb,
+                                                      tma_stage);
     } else {
       auto k = k_aev_forward_cta<4, 8>;
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
       k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
-                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb);
+                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb,
+                                                      tma_stage);
     }
     ANI_CUDA_CHECK_LAUNCH();
     return ANI_OK;

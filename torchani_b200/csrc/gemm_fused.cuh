@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
           sp.Bt + (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (PARTS * ROW_BYTES));
       const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
       const bool dense = tm.nb_count < 0;
+      const int n0p = tl.n0 / TN_MAX * TN_MAX, bnp = min(TN_MAX, sp.N - n0p);  // the packed B tile this one lies in
       const int gq = lane / PARTS, gpart = lane % PARTS;
       size_t g_src = 0;
       int g_bns = 0;
@@ -502,8 +503,17 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
         const int kbb = (tm.kb_count >= 0 ? tm.kb[kb] : kb) + kb_boff;
         if (dense) {
           if (lane == 0) {
-            const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
-            bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[st_idx]);
+            if (tl.bn == bnp) {  // a whole packed B tile: the pieces are adjacent, one copy
+              const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
+              bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[st_idx]);
+            } else {             // a column tile inside a packed 256-row B tile: one copy per piece
+#pragma unroll
+              for (int pc = 0; pc < PARTS; ++pc)
+                bulk_g2s(st + A_BLOCK_BYTES + pc * b_bytes,
+                         Bm + ((size_t)n0p * nkb_all + (size_t)kbb * bnp) * (PARTS * ROW_BYTES) +
+                             (size_t)pc * bnp * ROW_BYTES + (size_t)(tl.n0 - n0p) * ROW_BYTES,
+                         b_bytes, &full[st_idx]);
+            }
           }
         } else if (g_active) {
           bulk_g2s(st + A_BLOCK_BYTES + gpart * b_bytes + gq * 32 * ROW_BYTES,

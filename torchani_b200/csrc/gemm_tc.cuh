@@ -97,6 +97,7 @@ struct Args {
   float out_scale;              // operand scale of a tiled C (OPND_SCALE_VALUE activations / OPND_SCALE_GRAD gradients)
   float y_inv_scale;            // EPI_MUL_DCELU: 1 / scale of the stored activation that C overwrites
   int32_t* status;              // ANI_STATUS_OPERAND_RANGE is raised here (may be NULL)
+  int allow_narrow;             // short tile lists may split every accumulator into two column tiles (not EPI_HEAD)
   int debug;                    // timing experiments only (ANI_B200_GEMM_DEBUG): 2 no copies, 4 no MMA, 8 no epilogue
   float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
@@ -300,6 +301,7 @@ struct TileMap {
   int ntn[ANI_MAX_SPECIES];            // N tiles per (row tile, member)
   int prefix[ANI_MAX_SPECIES + 1];     // exclusive prefix of tile counts
   int n_eff[ANI_MAX_SPECIES];          // columns actually computed (compacted when nblocks is given)
+  int tn[ANI_MAX_SPECIES];             // columns per tile: TN_MAX, or half an accumulator for short lists
   int kb_count, nb_count;              // live K-blocks (-1: dense) / live column blocks (-1: dense)
   int kb[MAX_BLOCKS], nb[MAX_BLOCKS];
   int stages, stage_bytes, epi_bufs;   // shared-memory budget of this launch
@@ -326,18 +328,34 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool 
   for (int s = 0; s < S; ++s) {
     tm.first_rt[s] = a.layout_info[4 + s];
     tm.n_eff[s] = tm.nb_count >= 0 ? tm.nb_count * 32 : a.sp[s].N;
+    tm.tn[s] = TN_MAX;
     tm.ntn[s] = (tm.n_eff[s] + TN_MAX - 1) / TN_MAX;
   }
   tm.first_rt[S] = a.layout_info[4 + S];
-  for (int s = 0; s < S; ++s) {
-    tm.prefix[s] = run;
-    const int nrt = tm.first_rt[s + 1] - tm.first_rt[s];
-    run += (pair ? (nrt + 1) / 2 : nrt) * a.members * tm.ntn[s];
+  auto count = [&]() {
+    int run = 0;
+    for (int s = 0; s < S; ++s) {
+      tm.prefix[s] = run;
+      const int nrt = tm.first_rt[s + 1] - tm.first_rt[s];
+      run += (pair ? (nrt + 1) / 2 : nrt) * a.members * tm.ntn[s];
+    }
+    tm.prefix[S] = run;
+    return run;
+  };
+  const int wide = count();
+  // Short lists (less than half a wave of 256-column tiles: 1 k-atom systems, multi-GPU shards): split every
+  // accumulator into two column tiles -- twice the CTAs at work, each with half the main loop and half the epilogue,
+  // which is what the latency of the layer chain is made of.  (Tiles never straddle a packed 256-row B tile.)
+  if (a.allow_narrow && !pair && wide > 0 && 2 * wide <= (int)gridDim.x) {
+    for (int s = 0; s < S; ++s) {
+      tm.tn[s] = tm.n_eff[s] > TN_MAX ? TN_MAX / 2 : max(32, ((tm.n_eff[s] / 32 + 1) / 2) * 32);
+      tm.ntn[s] = (tm.n_eff[s] + tm.tn[s] - 1) / tm.tn[s];
+    }
+    count();
   }
-  tm.prefix[S] = run;
   int bn_max = 32;
   for (int s = 0; s < S; ++s)
-    if (tm.first_rt[s + 1] > tm.first_rt[s]) bn_max = max(bn_max, min(TN_MAX, tm.n_eff[s]));
+    if (tm.first_rt[s + 1] > tm.first_rt[s]) bn_max = max(bn_max, min(tm.tn[s], tm.n_eff[s]));
   tm.stage_bytes = A_BLOCK_BYTES + PARTS * (pair ? bn_max / 2 : bn_max) * ROW_BYTES;  // a pair member holds half of B
   // two store-staging buffers per epilogue warp if that still leaves a double-buffered main loop
   const int avail = SMEM_BYTES - 1024;
@@ -359,8 +377,8 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
   x.mem = rm % a.members;
   x.rt = tm.first_rt[s] + (pair ? 2 : 1) * (rm / a.members);
   x.rt_last = tm.first_rt[s + 1] - 1;
-  x.n0 = nt * TN_MAX;
-  x.bn = min(TN_MAX, tm.n_eff[s] - x.n0);
+  x.n0 = nt * tm.tn[s];
+  x.bn = min(tm.tn[s], tm.n_eff[s] - x.n0);
   return x;
 }
 
@@ -497,6 +515,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       // one piece of this CTA's B rows: all bn rows, or half of them in a CTA pair
       const uint32_t b_bytes = (uint32_t)(PAIR ? tl.bn / 2 : tl.bn) * ROW_BYTES;
       const bool dense = tm.nb_count < 0;
+      const int n0p = tl.n0 / TN_MAX * TN_MAX, bnp = min(TN_MAX, sp.N - n0p);  // the packed B tile this one lies in
       // gathered column blocks (layer-1 backward): lane -> (live block q, piece)
       const int gq = lane / PARTS, gpart = lane % PARTS;
       size_t g_src = 0;
@@ -520,8 +539,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
             bulk_g2s(st, At + (size_t)kbi * A_BLOCK_BYTES, A_BLOCK_BYTES, &full[stage]);
             if (dense) {
               const unsigned char* bsrc = Bm + ((size_t)tl.n0 * nkb_all + (size_t)kbb * tl.bn) * (PARTS * ROW_BYTES);
-              if (!PAIR) {  // the pieces are adjacent in global memory and in shared memory: one copy
+              if (!PAIR && tl.bn == bnp) {  // the pieces are adjacent in global memory and in shared memory: one copy
                 bulk_g2s(st + A_BLOCK_BYTES, bsrc, PARTS * b_bytes, &full[stage]);
+              } else if (!PAIR) {           // a column tile inside a packed 256-row B tile: one copy per piece
+#pragma unroll
+                for (int p = 0; p < PARTS; ++p)
+                  bulk_g2s(st + A_BLOCK_BYTES + p * b_bytes,
+                           Bm + ((size_t)n0p * nkb_all + (size_t)kbb * bnp) * (PARTS * ROW_BYTES) +
+                               (size_t)p * bnp * ROW_BYTES + (size_t)(tl.n0 - n0p) * ROW_BYTES,
+                           b_bytes, &full[stage]);
               } else {      // this CTA's half of the rows of every piece
 #pragma unroll
                 for (int p = 0; p < PARTS; ++p)

@@ -257,6 +257,11 @@ static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* r
   for (int m = 0; m < ANI_MAX_MEMBERS; ++m) ta.member_scale[m] = m < M ? model->member_scale[m] : 0.f;
   for (int s = 0; s < ANI_MAX_SPECIES; ++s) ta.sp[s] = tc::Species{nullptr, nullptr, 0, 0, 0, 0, 0, nullptr, nullptr, 0, 0, 1.0f};
   ta.status = status;
+  static const int narrow = []() {
+    const char* e = getenv("ANI_B200_NARROW_TILES");  // 0: 256-column tiles whatever the list length
+    return !e || atoi(e) != 0;
+  }();
+  ta.allow_narrow = narrow;
   ta.out_scale = OPND_SCALE_VALUE;
   ta.y_inv_scale = 1.0f / OPND_SCALE_VALUE;
   return ANI_OK;
@@ -306,6 +311,7 @@ extern "C" int ani_b200_mlp_forward(const ani_mlp_model* model, const void* x, i
   // layer 3 + final layer (h3 -> 1) + gradient seed, fused in the epilogue: act3 receives
   // G3 = scale_m * w4 * celu'(a3) directly, e_member the per-member atomic energies
   ta.out_scale = sg;  // act3 receives the gradient seed
+  ta.allow_narrow = 0;  // the fused final layer needs all of h3 in one accumulator
   launch_gemm_tc<tc::EPI_HEAD>(ta, st, true);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
@@ -414,7 +420,7 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
             ta.kblocks = aev_blocks; break;
     case 1: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = act2; ta.c_kblocks = kb2; ta.members = M; break;
     case 2: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
-            ta.out_scale = sg; break;
+            ta.out_scale = sg; ta.allow_narrow = 0; break;
     case 3: ta.A = static_cast<const unsigned char*>(act3); ta.a_kblocks = kb3; ta.C = act2; ta.c_kblocks = kb2; ta.members = M;
             ta.out_scale = sg; break;
     case 4: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;

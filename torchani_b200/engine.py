@@ -455,6 +455,7 @@ class Engine:
         # default: measured on B200 at 10k atoms it changes the step by < 1 us (0.3899 vs 0.3905 ms) --
         # inside the graph the two kernels cost little more than their dependency edges
         self.side_stream = os.environ.get("ANI_B200_SIDE_STREAM", "0") != "0"
+        self.overlap_reduce = os.environ.get("ANI_B200_OVERLAP_REDUCE", "1") != "0"
         # The MLP of a step: ONE persistent data-flow launch (csrc/gemm_fused.cuh) or the six chained launches of
         # csrc/gemm_tc.cuh -- the same tile code either way.  Measured on B200 over 2 k - 50 k atoms
         # (profiles/r02_sweep.md): the two are equal except where the chained launches quantise badly -- every one of
@@ -660,16 +661,25 @@ class Engine:
                     C.byref(self.nets.model), ptr(ws.dx), ws.rows_cap, ptr(ws.row_atom), ptr(ws.layout_info),
                     ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), int(zero_first), ptr(ws.status), st),
                     "mlp_backward")
+        # the energy reduction only needs the MLP's forward outputs: beside the AEV backward (a forked branch of the
+        # captured graph), not after it
+        overlap = want_grad and not split and self.overlap_reduce and not self.profile
+        if overlap:
+            side2 = self._side()
+            self._ev[2].record(main)
+            side2.wait_event(self._ev[2])
+            check(reduce_on(side2.cuda_stream), "reduce_energies")
+            self._ev[3].record(side2)
         if want_grad:
             self._timed("aev_backward", lambda: L.ani_b200_aev_backward(
                 C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig),
                 ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
                 ptr(ws.row_of), ptr(ws.dx), self.nets.ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
                 ws.grad_ptr, ptr(ws.status), ws.max_elements, ptr(ws.virial) if want_virial else None, st))
-        if not split:
-            self._timed("reduce_energies", lambda: reduce_on(st))
-        else:
+        if overlap or split:
             main.wait_event(self._ev[3])
+        else:
+            self._timed("reduce_energies", lambda: reduce_on(st))
         if ws.reducer is not None:
             # multi-GPU: sum the partial forces / energies of all ranks over NVLink peer memory (one launch,
             # part of the captured graph); without forces only the energies matter but the buffer is small

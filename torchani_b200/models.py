@@ -22,7 +22,8 @@ from torch import Tensor
 from . import _lib
 from .aev import AEVComputer
 from .engine import Engine, StepResult
-from .neighbors import Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff, narrow_down
+from .neighbors import (Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff,
+                        effective_periodic_cell, narrow_down)
 from .nn import (ANINetworks, ATOMIC_NUMBER, AtomicContainer, AtomicNetwork, Ensemble, SpeciesConverter,
                  SpeciesEnergies)
 
@@ -203,6 +204,12 @@ class ANI(torch.nn.Module):
         self._check_inputs(species, coords, charge)
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         _validate_inputs(self.cutoff, elem_idxs, coords, cell, pbc)
+        if pbc is not None and elem_idxs.shape[0] > 1:
+            # periodic batch (C conformers in one shared cell): one engine step per conformer
+            parts = [self((species[c:c + 1], coords[c:c + 1]), cell, pbc, charge, atomic, ensemble_values).energies
+                     for c in range(elem_idxs.shape[0])]
+            return SpeciesEnergies(elem_idxs, torch.cat(parts, dim=1 if ensemble_values else 0))
+        cell = effective_periodic_cell(coords, cell, pbc, self.cutoff)   # PBC in some directions only
         e, e_atomic, e_member = self._guarded(lambda: _FusedEnergy.apply(
             coords, elem_idxs, cell, pbc is not None, self.engine(coords.device), bool(coords.requires_grad)))
         energies: Tensor
@@ -279,6 +286,7 @@ class ANI(torch.nn.Module):
         self._check_inputs(species, coords, charge)
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         _validate_inputs(self.cutoff, elem_idxs, coords, cell, pbc)
+        cell = effective_periodic_cell(coords, cell, pbc, self.cutoff)
         eng = self.engine(coords.device)
         active = list(self.neural_networks.active_members_idxs)
         energies, forces = [], []
@@ -343,6 +351,7 @@ class ANI(torch.nn.Module):
         ``forward`` loses ~3e-3 Ha at |E| ~ 2.5e4 Ha)."""
         species, coords = species_coordinates
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        cell = effective_periodic_cell(coords, cell, pbc, self.cutoff)
         return self._guarded(lambda: self.engine(coords.device).step(
             elem_idxs, coords.detach(), cell, pbc is not None, want_grad=False, check=True).energies.clone())
 
@@ -350,6 +359,7 @@ class ANI(torch.nn.Module):
                             pbc: tp.Optional[Tensor] = None) -> tp.Tuple[Tensor, Tensor]:
         """grad.py:263-290 without the autograd round trip: (energies f64 (C,), forces f32 (C,A,3))."""
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
+        cell = effective_periodic_cell(coords, cell, pbc, self.cutoff)
         res = self._guarded(lambda: self.engine(coords.device).step(
             elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True, check=True))
         return res.energies.clone(), -res.grad

@@ -85,14 +85,38 @@ def _validate_inputs(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Op
             )
         if cell is None:
             raise ValueError("If pbc is not None, cell should be present")
-        if not bool(pbc.all()):
-            raise ValueError("The B200 neighborlists don't support PBC only in some directions")
     elif cell is not None:
         raise ValueError("Cell is not supported if not using pbc")
     if coords.device.type != "cuda":
         raise ValueError("torchani_b200 runs on CUDA tensors only (there is no CPU path)")
     if coords.dtype != torch.float32:
         raise ValueError("torchani_b200 kernels are float32; got " + str(coords.dtype))
+
+
+def effective_periodic_cell(coords: Tensor, cell: tp.Optional[Tensor], pbc: tp.Optional[Tensor],
+                            cutoff: float) -> tp.Optional[Tensor]:
+    """PBC in only some directions (neighbors.py:214-275: the reference enumerates image shifts along the periodic
+    lattice vectors only) -> an equivalent FULLY periodic cell for the bucket-grid kernels: every non-periodic lattice
+    vector is replaced by one along the normal of the other two, long enough (extent of the atoms along it + cutoff +
+    1 A) that no pair within the cutoff crosses it.  Same pair set, same shifts along the periodic vectors, zero
+    shift along the others.  One host synchronisation (the extent), only in this case."""
+    if pbc is None or cell is None or bool(pbc.all()):
+        return cell
+    c = cell.detach().to(torch.float64)
+    x = coords.detach().reshape(-1, 3).to(torch.float64)
+    new = c.clone()
+    flags = [bool(v) for v in pbc.tolist()]
+    for d in range(3):
+        if flags[d]:
+            continue
+        a, b = (k for k in range(3) if k != d)
+        n = torch.linalg.cross(new[a], new[b])
+        n = n / n.norm()
+        if float(torch.dot(n, c[d])) < 0:
+            n = -n
+        proj = x @ n
+        new[d] = n * (float(proj.max() - proj.min()) + cutoff + 1.0)
+    return new.to(cell.dtype)
 
 
 class BucketGrid:
@@ -139,6 +163,14 @@ class BucketGrid:
 
 def _half_list(cutoff: float, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor],
                pbc: tp.Optional[Tensor]) -> Neighbors:
+    if pbc is not None and species.shape[0] > 1:
+        # periodic batch (C conformers in one shared cell, neighbors.py:187-212): one grid per conformer, the pair
+        # indices refer to the flattened (C * A) atoms
+        per = [_half_list(cutoff, species[c:c + 1], coords[c:c + 1], cell, pbc) for c in range(species.shape[0])]
+        a = species.shape[1]
+        return Neighbors(torch.cat([nb.indices + c * a for c, nb in enumerate(per)], 1),
+                         torch.cat([nb.distances for nb in per]), torch.cat([nb.diff_vectors for nb in per]))
+    cell = effective_periodic_cell(coords, cell, pbc, cutoff)
     g = BucketGrid(species, coords, cell, pbc is not None, cutoff)
     L = _lib.lib()
     n = g.n
