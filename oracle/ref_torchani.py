@@ -76,7 +76,7 @@ GSAES_WB97X_631GD = {"H": -0.4993212, "C": -37.8338334, "N": -54.5732825, "O": -
 
 def build_model(weights, kind: str = "2x", device="cpu", dtype: torch.dtype = torch.float32,
                 strategy: str = "pyaev", neighborlist: str = "cell_list", infer: bool = False,
-                use_mnp: bool = False, periodic_table_index: bool = True):
+                use_mnp: bool = False, periodic_table_index: bool = True, repulsion: bool = False):
     """A real ``torchani.arch.ANI`` with ``weights[member][symbol] = [(W [out,in], b [out]) x 4]``."""
     ta = load()
     from torchani.aev import AEVComputer
@@ -99,8 +99,12 @@ def build_model(weights, kind: str = "2x", device="cpu", dtype: torch.dtype = to
                     lin.bias.copy_(b)
         members.append(net)
     nets = Ensemble(members) if len(members) > 1 else members[0]
+    extra = None
+    if repulsion:   # the pair potential of ANI-2xr (models.py:255-290): shares the model's neighbour list
+        from torchani.potentials import RepulsionXTB
+        extra = {"repulsion_xtb": RepulsionXTB(symbols, cutoff=aevc.radial.cutoff)}
     model = ANI(symbols, aevc, nets, SelfEnergy(symbols, [GSAES_WB97X_631GD[s] for s in symbols]),
-                periodic_table_index=periodic_table_index)
+                potentials=extra, periodic_table_index=periodic_table_index)
     model = model.to(device=device, dtype=dtype)
     model.requires_grad_(False)
     if infer:

@@ -31,9 +31,9 @@ def _weights(members=8, dtype=torch.float32):
     return synthetic.make_weights(models.SYMBOLS_2X, synthetic.DIMS_2X, 1008, members, seed=1234, dtype=dtype)
 
 
-def _reference_f64(weights64, z, coords, cell, pbc, neighborlist):
+def _reference_f64(weights64, z, coords, cell, pbc, neighborlist, **kw):
     import oracle.ref_torchani as rt
-    ref = rt.build_model(weights64, "2x", "cpu", dtype=torch.float64, strategy="pyaev", neighborlist=neighborlist)
+    ref = rt.build_model(weights64, "2x", "cpu", dtype=torch.float64, strategy="pyaev", neighborlist=neighborlist, **kw)
     c = coords.double().clone()
     e, f = rt.energies_and_forces(ref, z, c, None if cell is None else cell.double(), pbc)
     return e.detach(), f.detach()
@@ -87,7 +87,7 @@ def test_module_swap_inside_a_real_reference_model_periodic():
     assert isinstance(ref.aev_computer, aev.AEVComputer) and isinstance(ref.neural_networks, nn.Ensemble)
     e, f = rt.energies_and_forces(ref, z.to(DEV), coords.to(DEV), cell.to(DEV), pbc.to(DEV))
     assert float((f.cpu().double() - f64).abs().max()) < 1e-4
-    assert abs(float(e[0]) - float(e64[0])) < 5e-3              # float32 total at |E| ~ 7.6e3 Ha (reference arithmetic)
+    assert abs(float(e[0].detach()) - float(e64[0])) < 5e-3     # float32 total at |E| ~ 7.6e3 Ha (reference arithmetic)
     # atomic energies / ensemble values through the reference's own entry points
     at = ref.atomic_energies((z.to(DEV), coords.to(DEV)), cell.to(DEV), pbc.to(DEV)).energies
     assert at.shape == (1, 300) and abs(float(at.sum()) - float(e[0])) < 5e-2
@@ -115,3 +115,23 @@ def test_module_swap_inside_a_real_reference_model_nonperiodic_batch():
     assert float((e.cpu().double() - e64).abs().max()) < 2e-3      # float32 totals at |E| ~ 1e3 Ha
     pad = (z == -1)
     assert float(f.cpu()[pad].abs().max()) == 0.0
+
+
+def test_reference_pair_potential_runs_on_the_swapped_neighbor_list():
+    """SURVEY 8(f4) tail: pair potentials sharing the model's neighbour list.  A real reference model WITH an extra
+    pair potential (RepulsionXTB, as in ANI-2xr, models.py:255-290, potentials/xtb.py) keeps working after the module
+    swap: the reference's own compute_from_neighbors loop (arch.py:354-381) hands the B200 neighbour list to every
+    potential (discard_outside_cutoff per potential) and sums the energies; forces by autograd through both."""
+    import oracle.ref_torchani as rt
+    from torchani_b200 import models
+    z, coords, cell, pbc = _water(100)
+    e64, f64 = _reference_f64(_weights(dtype=torch.float64), z, coords, cell, pbc, "cell_list", repulsion=True)
+    e_plain, _ = _reference_f64(_weights(dtype=torch.float64), z, coords, cell, pbc, "cell_list")
+    assert abs(float(e64[0]) - float(e_plain[0])) > 1e-3          # the repulsion term is really there
+    ref = rt.build_model(_weights(), "2x", DEV, strategy="pyaev", neighborlist="cell_list", repulsion=True)
+    models.accelerate_torchani_(ref)
+    assert set(ref.potentials.keys()) == {"repulsion_xtb", "nnp"}
+    e, f = rt.energies_and_forces(ref, z.to(DEV), coords.to(DEV), cell.to(DEV), pbc.to(DEV))
+    scale = max(1.0, float(f64.abs().max()))
+    assert float((f.cpu().double() - f64).abs().max()) < 1e-4 * scale
+    assert abs(float(e[0].detach()) - float(e64[0])) < 5e-3

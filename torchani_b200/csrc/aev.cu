@@ -537,7 +537,7 @@ struct CtaStage {
   unsigned long long tma_bar;                  // mbarrier of the TMA bulk copies that stage the bucket ranges
 };
 
-template <int NA, int NZ>
+template <int NA, int NZ, bool TMA_STAGE = false>
 __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     k_aev_forward_cta(const __grid_constant__ ani_aev_params P, const ani_grid* __restrict__ grid,
                       const int32_t* __restrict__ bin_start, const float4* __restrict__ spos,
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     myb = sbin[i];
   }
   if (lane == 0) C.wbin[warp] = myb;
-  if (tid == 0) aev_mbar_init(reinterpret_cast<uint64_t*>(&C.tma_bar), 1);
+  if (TMA_STAGE && tid == 0) aev_mbar_init(reinterpret_cast<uint64_t*>(&C.tma_bar), 1);
   __syncthreads();
 
   // ---- 1. neighbours within Rcr (and the sub-list within Rca), species segment by species segment
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     const int T = C.r_off[NRANGE];
     // first bucket of the CTA, neighbourhood fits: one TMA bulk copy per non-empty range (contiguous float4 runs of
     // the bucket-sorted position array), all completing on one mbarrier
-    const bool staged = tma_stage && prev == first_bucket && T > 0 && T <= raw_cap;
+    const bool staged = TMA_STAGE && tma_stage && prev == first_bucket && T > 0 && T <= raw_cap;
     if (staged) {
       if (tid == 0) aev_mbar_expect_tx(reinterpret_cast<uint64_t*>(&C.tma_bar), (uint32_t)T * 16u);
       if (tid < NRANGE) {
@@ -1429,18 +1429,22 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
   if (!ex.start && !legacy) {
     const size_t smem_f = wb * AEV_FWD_WARPS;
     const int blocks_f = (hi - lo + AEV_FWD_WARPS - 1) / AEV_FWD_WARPS;
+    auto go = [&](auto k) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+      k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
+                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb,
+                                                      tma_stage);
+    };
     if (params->n_shf_a == 8) {
-      auto k = k_aev_forward_cta<8, 4>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-      k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
-                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb,
-                                                      tma_stage);
+      if (tma_stage)
+        go(k_aev_forward_cta<8, 4, true>);
+      else
+        go(k_aev_forward_cta<8, 4, false>);
     } else {
-      auto k = k_aev_forward_cta<4, 8>;
-      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
-      k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
-                                                      row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb,
-                                                      tma_stage);
+      if (tma_stage)
+        go(k_aev_forward_cta<4, 8, true>);
+      else
+        go(k_aev_forward_cta<4, 8, false>);
     }
     ANI_CUDA_CHECK_LAUNCH();
     return ANI_OK;
