@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ANI_B200_ABI_VERSION 2
+#define ANI_B200_ABI_VERSION 3
 
 #define ANI_MAX_SPECIES 8
 #define ANI_MAX_SHFR 32
@@ -158,9 +158,12 @@ int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, i
 /*                 fly); species_mask: {bit per element present in the system, changed flag} or   */
 /*                 NULL: angular blocks of absent element pairs are not rewritten while the       */
 /*                 composition is unchanged (they hold zeros from the first call)                 */
+/*      bucket_species  output of ani_b200_prepare_step or NULL (needs bucket_ranges): per bucket the offsets of   */
+/*                 its species inside the (species-sorted) bucket, i32[nbins][8]; lets the kernel skip the pass that  */
+/*                 counts the species of the ~370 staged candidates of a CTA                                          */
 int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid,
                          const int32_t* bin_start, const float* spos, const int32_t* sbin,
-                         const float* bucket_ranges, const int32_t* species_mask, int n, int lo,
+                         const float* bucket_ranges, const int32_t* bucket_species, const int32_t* species_mask, int n, int lo,
                          int hi, const int32_t* row_of, float* aev, int ldx, int layout,
                          int32_t* nbr_cnt, int32_t* nbr_list, int nbr_cap, int32_t* status,
                          void* stream);
@@ -241,6 +244,8 @@ int ani_b200_verlet_positions(int mode, const float* coords, const ani_grid* gri
 /*     (same outputs, same determinism; what the fused engine calls).                                 */
 /*     Also zero-fills zero_f32[0..count) (the force accumulator) and zero_f64[0..count) (the      */
 /*     conformer energies) so that no separate memset launches are needed.                          */
+/*     bucket_species (or NULL): i32[max_bins][8], per bucket the offset of its first atom of species >= s */
+/*     (buckets are species-sorted), consumed by ani_b200_aev_forward.                               */
 /*     scratch_i32: 3 n + max_bins + 4 + (ceil((hi-lo)/256) + 2) * ANI_MAX_SPECIES + 32 ints, ZERO at           */
 /*     allocation (two of them are the state of the device-wide barrier of the single-launch preparation).     */
 int ani_b200_prepare_step(const float* coords, const int32_t* species, int n_conf, int n_per_conf,
@@ -250,7 +255,7 @@ int ani_b200_prepare_step(const float* coords, const int32_t* species, int n_con
                           int32_t* row_of, int32_t* row_atom, int32_t* tile_species, int32_t* layout_info,
                           int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* aev_blocks,
                           float* zero_f32, int zero_f32_count, double* zero_f64, int zero_f64_count,
-                          int32_t* scratch_i32, int32_t* status, void* stream);
+                          int32_t* bucket_species, int32_t* scratch_i32, int32_t* status, void* stream);
 
 /* Timing experiments only: the first 4 CTAs of the next `launches` tensor-core GEMM launches    */
 /* write clock64 stamps [launch][cta 4][tile 8][role 3: producer, MMA, epilogue][4] into buf       */
@@ -357,7 +362,9 @@ int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int rows_cap, c
 /*    tile) units form one list and the launch boundaries are replaced by data-flow waits on per-(layer, row tile)   */
 /*    completion counters -- no ramp / tail per layer, one tile-count quantisation for the whole step, and at small   */
 /*    row counts (multi-GPU shards) no per-launch floor.  sync_i32: 6 * (rows_cap / 128) ints of scratch (zeroed by    */
-/*    the call).  Same arguments and results as ani_b200_mlp_forward_backward otherwise.                               */
+/*    the call).  Same arguments and results as ani_b200_mlp_forward_backward otherwise.  want_backward == 2:          */
+/*    PER-MEMBER gradients (arch.py:403-436, members_forces): dx is f32[M][rows_cap][ldx] and member m's slab receives   */
+/*    d(member_scale[m] * e_m)/dAEV by plain stores (no sum over the members, no zero-fill needed).                      */
 int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, float* dx, int rows_cap, const int32_t* row_atom,
                       const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2, void* act3,
                       float* e_member, int want_backward, int32_t* sync_i32, int32_t* status, void* stream);

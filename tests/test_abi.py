@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in ani_b200.h but not exported"
     from torchani_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes prototypes out of sync with the header"
-    assert _lib.lib().ani_b200_abi_version() == 2
+    assert _lib.lib().ani_b200_abi_version() == 3
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -58,13 +58,13 @@ def test_argument_validation_without_gpu():
     # null pointers
     assert L.ani_b200_build_cells(None, None, 1, 1, None, 0, 0, 5.1, 64, None, None, None, None, None, None,
                                   None, None, None, None) == -1
-    assert L.ani_b200_aev_forward(None, None, None, None, None, None, None, 0, 0, 0, None, None, 0, 0, None, None,
+    assert L.ani_b200_aev_forward(None, None, None, None, None, None, None, None, 0, 0, 0, None, None, 0, 0, None, None,
                                   128, None, None) == -1
     # unsupported AEV configuration (ShfA x ShfZ must be 8x4 or 4x8) is reported as such
     p = _lib.AEVParams()
     p.num_species, p.n_shf_r, p.n_shf_a, p.n_shf_z = 7, 16, 5, 5
     p.rcr, p.rca, p.zeta = 5.1, 3.5, 14.1
-    assert L.ani_b200_aev_forward(C.byref(p), None, None, None, None, None, None, 0, 0, 0, None, None, 0, 0, None,
+    assert L.ani_b200_aev_forward(C.byref(p), None, None, None, None, None, None, None, 0, 0, 0, None, None, 0, 0, None,
                                   None, 128, None, None) == -2
     with pytest.raises(_lib.ANIB200Error):
         _lib.check(-2, "x")

@@ -531,3 +531,34 @@ def test_partial_pbc_and_periodic_batches_match_the_oracle():
     nb = neighbors.AllPairs()(5.1, sp2.to(DEV), co2.float().to(DEV), cell_d, pbc.to(DEV))
     assert nb.indices.shape[1] == int(refs[0]["num_pairs"]) + int(refs[1]["num_pairs"])
     assert int(nb.indices.max()) >= 30      # indices into the flattened (C * A) atoms
+
+
+def test_periodic_cell_thinner_than_the_cutoff_all_pairs_semantics():
+    """neighbors.py:245-275: `all_pairs` pairs every atom with several lattice images when the cell is thinner than
+    the cutoff (a cell list raises instead).  Here: a supercell of translation-equivalent copies."""
+    from torchani_b200 import models
+    from torchani_b200.aev import AEVComputer
+    om = oracle_model("2x", torch.float64, "all_pairs", members=2)
+    w32 = [{s: [(w.float(), b.float()) for w, b in layers] for s, layers in wm.items()} for wm in om.weights]
+    g = torch.Generator().manual_seed(4)
+    species = torch.tensor([[3, 0, 0, 1, 0, 2]])
+    cell = torch.tensor([[4.2, 0.0, 0.0], [0.3, 3.9, 0.0], [0.0, 0.2, 9.0]], dtype=torch.float64)   # two thin directions
+    frac = torch.rand(1, 6, 3, generator=g, dtype=torch.float64)
+    coords = frac @ cell
+    pbc = torch.tensor([True, True, True])
+    ref = orc.compute(om, species, coords, cell, pbc)
+    model = models.from_weight_lists("2x", w32, device=DEV, neighborlist="all_pairs", periodic_table_index=False)
+    c = coords.float().to(DEV).requires_grad_(True)
+    e = model((species.to(DEV), c), cell.float().to(DEV), pbc.to(DEV)).energies
+    (gr,) = torch.autograd.grad(e.sum(), c)
+    assert abs(float(e[0]) - float(ref["energy"][0])) < 2e-3
+    assert_close("forces", -gr.cpu().numpy(), ref["forces"].numpy(), 0.0, F_ATOL)
+    at = model((species.to(DEV), coords.float().to(DEV)), cell.float().to(DEV), pbc.to(DEV), atomic=True).energies
+    assert at.shape == (1, 6)
+    aev = AEVComputer.like_2x(neighborlist="all_pairs").to(DEV)(species.to(DEV), coords.float().to(DEV),
+                                                               cell.float().to(DEV), pbc.to(DEV))
+    assert_close("aev", aev.cpu().numpy(), ref["aev"].numpy(), AEV_RTOL, AEV_ATOL)
+    # the cell-list flavour keeps the reference's error
+    strict = models.from_weight_lists("2x", w32, device=DEV, neighborlist="cell_list", periodic_table_index=False)
+    with pytest.raises(RuntimeError, match="too small"):
+        strict((species.to(DEV), coords.float().to(DEV)), cell.float().to(DEV), pbc.to(DEV))

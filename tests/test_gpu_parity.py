@@ -38,7 +38,7 @@ def gpu_aev(eng, species, coords, cell, pbc):
     st = torch.cuda.current_stream().cuda_stream
     plain = torch.zeros(ws.rows_cap, eng.nets.ldx, device=dev)
     check(lib().ani_b200_aev_forward(C.byref(eng.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos),
-                                     ptr(ws.sbin), None, None, n, 0, n, ptr(ws.row_of), ptr(plain), eng.nets.ldx, 0,
+                                     ptr(ws.sbin), None, None, None, n, 0, n, ptr(ws.row_of), ptr(plain), eng.nets.ldx, 0,
                                      ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st))
     torch.cuda.synchronize()
     eng.check_status(ws)

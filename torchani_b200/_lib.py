@@ -76,14 +76,14 @@ _PROTOTYPES = {
     "ani_b200_last_cuda_error": (C.c_char_p, []),
     "ani_b200_build_cells": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ani_b200_species_layout": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
-    "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
+    "ani_b200_aev_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P, _I, _P, _P]),
     "ani_b200_aev_backward": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _I, _P, _P]),
     "ani_b200_pairs_to_rows": (C.c_int, [_P, _P, _P, C.c_int64, _I, _I, _P, _P, _P, _P, _P, _P]),
     "ani_b200_full_nbrlist_to_rows": (C.c_int, [_P, _I, _P, _P, _P, _I, _F, _I, _P, _P, _P, _P, _P, _P]),
     "ani_b200_aev_forward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "ani_b200_aev_backward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "ani_b200_prepare_step": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, C.c_float, _I, _P, _P, _P, _P, _P, _P, _P,
-                                        _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
+                                        _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "ani_b200_verlet_positions": (C.c_int, [_I, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "ani_b200_debug_gemm_trace": (C.c_int, [_P, _I]),
     "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
@@ -136,7 +136,7 @@ def _load(path: str) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ani_b200_abi_version() != 2:
+    if lib.ani_b200_abi_version() != 3:
         raise ImportError(f"{path}: ABI version mismatch")
     return lib
 

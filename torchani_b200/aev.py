@@ -18,8 +18,8 @@ from torch import Tensor
 from . import _lib
 from ._lib import check, ptr
 from .engine import AEVConstants, _linspace
-from .neighbors import (BucketGrid, Neighbors, NeighborlistArg, _parse_neighborlist, _validate_inputs,
-                        effective_periodic_cell)
+from .neighbors import (BucketGrid, CellList, Neighbors, NeighborlistArg, _parse_neighborlist, _validate_inputs,
+                        effective_periodic_cell, supercell_for_thin_cell)
 
 
 class SpeciesAEV(tp.NamedTuple):
@@ -106,7 +106,7 @@ class _AEVFunction(torch.autograd.Function):
         params = computer._params()
         # rows of the output are the flat input indices: row_of == sorted_orig
         check(_lib.lib().ani_b200_aev_forward(C.byref(params), ptr(g.grid), ptr(g.bin_start), ptr(g.spos),
-                                              ptr(g.sbin), None, None, n, 0, n, ptr(g.sorted_orig), ptr(out),
+                                              ptr(g.sbin), None, None, None, n, 0, n, ptr(g.sorted_orig), ptr(out),
                                               consts.out_dim, 0, ptr(nbr_cnt), ptr(nbr_list), cap, ptr(g.status),
                                               g.stream), "aev_forward")
         ctx.g, ctx.nbr_cnt, ctx.nbr_list, ctx.computer = g, nbr_cnt, nbr_list, computer
@@ -338,6 +338,10 @@ class AEVComputer(torch.nn.Module):
         _validate_inputs(self.radial.cutoff, elem_idxs, coords, cell, pbc)
         if pbc is not None and elem_idxs.shape[0] > 1:   # periodic batch: one conformer at a time
             return torch.cat([self(elem_idxs[c:c + 1], coords[c:c + 1], cell, pbc) for c in range(elem_idxs.shape[0])])
+        sup = None if isinstance(self.neighborlist, CellList) else \
+            supercell_for_thin_cell(elem_idxs, coords, cell, pbc, self.radial.cutoff)
+        if sup is not None:   # periodic cell thinner than the cutoff: AEVs of the original atoms of a supercell
+            return self(sup[0], sup[1], sup[2], pbc)[:, :elem_idxs.shape[1]]
         cell = effective_periodic_cell(coords, cell, pbc, self.radial.cutoff)   # PBC in some directions only
         aev = _AEVFunction.apply(coords, elem_idxs, cell, pbc is not None, self)
         if self._last_grid is not None:

@@ -528,6 +528,7 @@ struct CtaStage {
   float4 cand[CAND_CAP];  // shifted position; .w = neighbour word (sorted index | image code << 26)
   float4 r_shift[NRANGE];
   int r_lo[NRANGE], r_code[NRANGE];
+  int r_len[NRANGE];                           // candidates of every range
   int r_off[NRANGE + 1];                       // exclusive prefix of the range lengths
   int cnt[ANI_MAX_SPECIES][NRANGE];            // candidates per (species, range)
   int off[ANI_MAX_SPECIES * NRANGE + 1];       // exclusive prefix of cnt in species-major order
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
                       const int32_t* __restrict__ species_mask, int lo, int hi, const int32_t* __restrict__ row_of,
                       float* __restrict__ aev, int ldx, int layout, int32_t* __restrict__ nbr_cnt,
                       int32_t* __restrict__ nbr_list, int cap, int32_t* __restrict__ status, size_t warp_bytes,
-                      int tma_stage) {
+                      int tma_stage, const int32_t* __restrict__ bss) {
   static_assert(NA * NZ == 32, "one lane per angular feature");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ CtaStage C;
@@ -579,6 +580,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
   const int raw_cap = (int)min((size_t)CAND_CAP, (AEV_FWD_WARPS * warp_bytes) / sizeof(float4));
   uint32_t tma_parity = 0;
   int prev = -1, first_bucket = -1;
+  const bool use_bss = bss != nullptr;
   while (true) {
     int cur = 0x7fffffff;
 #pragma unroll
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     __syncthreads();  // every warp has chosen `cur`; the tables of the previous phase may be rewritten
     // (a) the 27 candidate ranges of bucket `cur`
     if (tid < NRANGE) {
-      int rlo = 0, rhi = 0, code = 13;
+      int rlo = 0, rhi = 0, code = 13, nbk = cur;
       float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (g.mode != 0) {
         if (tid == 13) {
@@ -605,6 +607,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
         rlo = __float_as_int(r0.x);
         rhi = __float_as_int(r0.y);
         code = __float_as_int(r0.z);
+        nbk = __float_as_int(r0.w);
         sh = r1;
       } else {
         const int iz = cur % g.dims[2], iy = (cur / g.dims[2]) % g.dims[1], ix = cur / (g.dims[2] * g.dims[1]);
@@ -622,13 +625,32 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
       C.r_lo[tid] = rlo;
       C.r_code[tid] = code;
       C.r_shift[tid] = sh;
-      C.r_off[tid + 1] = max(rhi - rlo, 0);  // length for now, prefix below
+      const int len = max(rhi - rlo, 0);
+      C.r_len[tid] = len;
+      if (use_bss) {
+        // candidates per (species, range) straight from the per-bucket species offsets of the preparation kernel
+        // (buckets are species-sorted): no counting pass over the candidates, no shared-memory atomics
+        int off8[ANI_MAX_SPECIES + 1];
+        if (len > 0) {
+          const int4 q0 = reinterpret_cast<const int4*>(bss)[2 * (size_t)nbk], q1 = reinterpret_cast<const int4*>(bss)[2 * (size_t)nbk + 1];
+          off8[0] = q0.x; off8[1] = q0.y; off8[2] = q0.z; off8[3] = q0.w;
+          off8[4] = q1.x; off8[5] = q1.y; off8[6] = q1.z; off8[7] = q1.w;
+          off8[ANI_MAX_SPECIES] = len;
+        } else {
+#pragma unroll
+          for (int k = 0; k <= ANI_MAX_SPECIES; ++k) off8[k] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < ANI_MAX_SPECIES; ++k) C.cnt[k][tid] = off8[k + 1] - off8[k];
+      }
     }
-    for (int q = tid; q < ANI_MAX_SPECIES * NRANGE; q += AEV_FWD_WARPS * 32) (&C.cnt[0][0])[q] = 0;
+    if (!use_bss)
+      for (int q = tid; q < ANI_MAX_SPECIES * NRANGE; q += AEV_FWD_WARPS * 32) (&C.cnt[0][0])[q] = 0;
     __syncthreads();
-    if (warp == 0) {
-      // inclusive scan of the 27 lengths (lane o holds range o)
-      int v = lane < NRANGE ? C.r_off[lane + 1] : 0;
+    // inclusive scan of the 27 lengths (lane o holds range o).  With the bss table EVERY warp computes the (identical)
+    // prefixes itself: no warp idles at a CTA barrier while another one scans
+    if (use_bss || warp == 0) {
+      int v = lane < NRANGE ? C.r_len[lane] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(ANI_FULL_MASK, v, o);
@@ -636,8 +658,9 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
       }
       if (lane < NRANGE) C.r_off[lane + 1] = v;
       if (lane == 0) C.r_off[0] = 0;
+      __syncwarp();
     }
-    __syncthreads();
+    if (!use_bss) __syncthreads();
     const int T = C.r_off[NRANGE];
     // first bucket of the CTA, neighbourhood fits: one TMA bulk copy per non-empty range (contiguous float4 runs of
     // the bucket-sorted position array), all completing on one mbarrier
@@ -663,7 +686,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
     // (b) candidates per (species, range); the range of every candidate is remembered for (c)
     // (four candidates per thread and round: the global loads are issued together)
     constexpr int NT = AEV_FWD_WARPS * 32, BATCH = 4;
-    for (int t0 = tid; t0 < T; t0 += NT * BATCH) {
+    for (int t0 = tid; t0 < T && !use_bss; t0 += NT * BATCH) {
       int oo[BATCH], spv[BATCH];
 #pragma unroll
       for (int j = 0; j < BATCH; ++j) {
@@ -680,8 +703,8 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
       for (int j = 0; j < BATCH; ++j)
         if (oo[j] >= 0) atomicAdd(&C.cnt[spv[j]][oo[j]], 1);
     }
-    __syncthreads();
-    if (warp == 0) {
+    if (!use_bss) __syncthreads();
+    if (use_bss || warp == 0) {
       // exclusive prefix over q = species * 27 + range: 7 consecutive entries per lane
       constexpr int PER = (ANI_MAX_SPECIES * NRANGE + 31) / 32;
       int loc[PER];
@@ -715,8 +738,9 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
           lower += C.cnt[sp][lane];
         }
       }
+      __syncwarp();
     }
-    __syncthreads();
+    if (!use_bss) __syncthreads();
     const bool mine = has && myb == cur;
     for (int F0 = 0; F0 < T; F0 += CAND_CAP) {
       // (c) place the candidates whose species-major position falls into this window
@@ -728,7 +752,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
           const int t = t0 + j * NT;
           oo[j] = -1;
           if (t < T) {
-            const int o = t < T2O_CAP ? (int)C.t2o[t] : find_range(t);
+            const int o = (!use_bss && t < T2O_CAP) ? (int)C.t2o[t] : find_range(t);
             oo[j] = o;
             cc[j] = C.r_lo[o] + (t - C.r_off[o]);
             pp[j] = staged ? raw[t] : spos[cc[j]];
@@ -1391,7 +1415,7 @@ static int check_params(const ani_aev_params* p) {
 // ---- launchers shared by the bucket-grid and the explicit-pair-list entry points -----------
 static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
                               const float* spos, const int32_t* sbin, const float* bucket_ranges,
-                              const int32_t* species_mask, ExplicitNbrs ex, int n, int lo, int hi,
+                              const int32_t* bucket_species, const int32_t* species_mask, ExplicitNbrs ex, int n, int lo, int hi,
                               const int32_t* row_of, float* aev, int ldx, int layout, int32_t* nbr_cnt,
                               int32_t* nbr_list, int nbr_cap, int32_t* status, void* stream) {
   int rc = check_params(params);
@@ -1433,7 +1457,7 @@ static int launch_aev_forward(const ani_aev_params* params, const ani_grid* grid
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
       k<<<blocks_f, AEV_FWD_WARPS * 32, smem_f, st>>>(*params, grid, bin_start, sp4, sbin, rng4, species_mask, lo, hi,
                                                       row_of, aev, ldx, layout, nbr_cnt, nbr_list, nbr_cap, status, wb,
-                                                      tma_stage);
+                                                      tma_stage, bucket_species);
     };
     if (params->n_shf_a == 8) {
       if (tma_stage)
@@ -1580,14 +1604,16 @@ using namespace ani;
 
 extern "C" int ani_b200_aev_forward(const ani_aev_params* params, const ani_grid* grid, const int32_t* bin_start,
                                     const float* spos, const int32_t* sbin, const float* bucket_ranges,
-                                    const int32_t* species_mask, int n, int lo, int hi, const int32_t* row_of,
+                                    const int32_t* bucket_species, const int32_t* species_mask, int n, int lo, int hi,
+                                    const int32_t* row_of,
                                     float* aev, int ldx, int layout, int32_t* nbr_cnt, int32_t* nbr_list,
                                     int nbr_cap, int32_t* status, void* stream) {
   int rc = check_params(params);
   if (rc != ANI_OK) return rc;
   if (!bin_start || !sbin || !nbr_cnt || !nbr_list) return ANI_ERR_BAD_ARG;
-  return launch_aev_forward(params, grid, bin_start, spos, sbin, bucket_ranges, species_mask,
-                            ExplicitNbrs{nullptr, nullptr, nullptr}, n, lo, hi, row_of, aev, ldx, layout, nbr_cnt,
+  // (the species offsets are addressed through the bucket ids stored in the range records)
+  return launch_aev_forward(params, grid, bin_start, spos, sbin, bucket_ranges, bucket_ranges ? bucket_species : nullptr,
+                            species_mask, ExplicitNbrs{nullptr, nullptr, nullptr}, n, lo, hi, row_of, aev, ldx, layout, nbr_cnt,
                             nbr_list, nbr_cap, status, stream);
 }
 
@@ -1654,7 +1680,7 @@ extern "C" int ani_b200_aev_forward_rows(const ani_aev_params* params, const ani
                                          const int32_t* row_of, float* aev, int ldx, int layout, int nbr_cap,
                                          int32_t* status, void* stream) {
   if (!row_start || !row_j || !row_d) return ANI_ERR_BAD_ARG;
-  return launch_aev_forward(params, grid, nullptr, spos, nullptr, nullptr, nullptr,
+  return launch_aev_forward(params, grid, nullptr, spos, nullptr, nullptr, nullptr, nullptr,
                             ExplicitNbrs{row_start, row_j, reinterpret_cast<const float4*>(row_d)}, n, 0, n, row_of,
                             aev, ldx, layout, nullptr, nullptr, nbr_cap, status, stream);
 }

@@ -502,7 +502,32 @@ struct PrepArgs {
   double* zero_f64;
   int zero_f64_count;
   int32_t* status;
+  int32_t* bss;  // [nbins][8] or nullptr: offset inside bucket b of its first atom of species >= s (buckets are species-sorted)
 };
+
+// per-bucket species offsets: bss[b][s] = atoms of bucket b with species < s (s = 0..7; bss[b][0] = 0).  With the
+// species-sorted order inside a bucket this is where species s starts; the AEV forward kernel reads 27 such rows
+// instead of counting the species of ~370 candidates per CTA
+__device__ __forceinline__ void bucket_species_offsets(const PrepArgs& A, int b) {
+  const int lo = __ldcg(&A.bin_start[b]), hi = __ldcg(&A.bin_start[b + 1]);
+  int cnt[ANI_MAX_SPECIES];
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) cnt[k] = 0;
+  for (int e = lo; e < hi; ++e) {
+    const int sp = A.species[__ldcg(&A.tmp_list[e])];
+#pragma unroll
+    for (int k = 0; k < ANI_MAX_SPECIES; ++k) cnt[k] += (sp == k);
+  }
+  int run = 0, off[ANI_MAX_SPECIES];
+#pragma unroll
+  for (int k = 0; k < ANI_MAX_SPECIES; ++k) {
+    off[k] = run;
+    run += cnt[k];
+  }
+  int4* dst = reinterpret_cast<int4*>(A.bss + (size_t)b * ANI_MAX_SPECIES);
+  dst[0] = make_int4(off[0], off[1], off[2], off[3]);
+  dst[1] = make_int4(off[4], off[5], off[6], off[7]);
+}
 
 __global__ void __launch_bounds__(256) k_prep_assign(const __grid_constant__ PrepArgs A) {
   __shared__ ani_grid sg;
@@ -606,7 +631,8 @@ __global__ void __launch_bounds__(256) k_prep_scatter(const __grid_constant__ Pr
     hi = A.bin_start[nb + 1];
   }
   const float wx = (float)w[0], wy = (float)w[1], wz = (float)w[2];
-  A.ranges[2 * (size_t)idx] = make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), 0.f);
+  const int nbk = exists ? (j[0] * g.dims[1] + j[1]) * g.dims[2] + j[2] : 0;
+  A.ranges[2 * (size_t)idx] = make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), __int_as_float(nbk));
   A.ranges[2 * (size_t)idx + 1] = make_float4(wx * g.cell[0] + wy * g.cell[3] + wz * g.cell[6],
                                               wx * g.cell[1] + wy * g.cell[4] + wz * g.cell[7],
                                               wx * g.cell[2] + wy * g.cell[5] + wz * g.cell[8], 0.f);
@@ -649,6 +675,8 @@ __global__ void __launch_bounds__(256) k_prep_finalize(const __grid_constant__ P
   if ((threadIdx.x & 31) == 0 && mask) atomicOr(A.present, (int)mask);
   if (A.zero_f32)
     for (int k = a; k < A.zero_f32_count; k += gridDim.x * blockDim.x) A.zero_f32[k] = 0.f;
+  if (A.bss)
+    for (int b = a; b < g.nbins; b += gridDim.x * blockDim.x) bucket_species_offsets(A, b);
 }
 
 __global__ void __launch_bounds__(1024) k_prep_layout(const __grid_constant__ PrepArgs A) {
@@ -876,7 +904,9 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
         hi = __ldcg(&A.bin_start[nb + 1]);
       }
       const float wx = (float)wv[0], wy = (float)wv[1], wz = (float)wv[2];
-      A.ranges[2 * (size_t)idx] = make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), 0.f);
+      const int nbk = exists ? (j[0] * sg.dims[1] + j[1]) * sg.dims[2] + j[2] : 0;
+      A.ranges[2 * (size_t)idx] =
+          make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), __int_as_float(nbk));
       A.ranges[2 * (size_t)idx + 1] = make_float4(wx * sg.cell[0] + wy * sg.cell[3] + wz * sg.cell[6],
                                                   wx * sg.cell[1] + wy * sg.cell[4] + wz * sg.cell[7],
                                                   wx * sg.cell[2] + wy * sg.cell[5] + wz * sg.cell[8], 0.f);
@@ -921,6 +951,8 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
     if (lane == 0 && mask) atomicOr(A.present, (int)mask);
     if (A.zero_f32)
       for (int k = gtid; k < A.zero_f32_count; k += gstride) A.zero_f32[k] = 0.f;
+    if (A.bss)
+      for (int b = gtid; b < sg.nbins; b += gstride) bucket_species_offsets(A, b);
   }
   grid_barrier(bar, A.status);
   // ---- phase 4: block 0: chunk scan, species row bases, tile table, live AEV column blocks;
@@ -1178,7 +1210,7 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
                                      int32_t* row_atom, int32_t* tile_species, int32_t* layout_info, int n_shf_r,
                                      int angular_sub, int out_dim, int ldx, int32_t* aev_blocks, float* zero_f32,
                                      int zero_f32_count, double* zero_f64, int zero_f64_count,
-                                     int32_t* scratch_i32, int32_t* status, void* stream) {
+                                     int32_t* bucket_species, int32_t* scratch_i32, int32_t* status, void* stream) {
   if (!coords || !species || !grid || !bin_start || !sorted_orig || !orig_to_sorted || !spos || !sbin ||
       !row_of || !row_atom || !tile_species || !layout_info || !aev_blocks || !scratch_i32 || !status)
     return ANI_ERR_BAD_ARG;
@@ -1220,6 +1252,7 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   A.zero_f32 = zero_f32_count > 0 ? zero_f32 : nullptr; A.zero_f32_count = zero_f32_count;
   A.zero_f64 = zero_f64_count > 0 ? zero_f64 : nullptr; A.zero_f64_count = zero_f64_count;
   A.status = status;
+  A.bss = bucket_species;
   A.inline_setup = (mode == 1 || pbc) ? 1 : 0;
   const size_t zeroed = (size_t)(max_bins + 1) + 2 + (size_t)(A.n_chunks + 1) * ANI_MAX_SPECIES;
   if (!A.inline_setup)

@@ -374,7 +374,8 @@ extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int 
 // ---- the whole MLP of a step as ONE persistent data-flow launch (gemm_fused.cuh) ----------------------
 // phase p of the list: 0-2 forward layers (2 = head), 3-5 backward-to-input.  `sync`: 6 * (rows_cap / 128) ints.
 static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, const void* x, float* dx, void* act1,
-                       void* act2, void* act3, float* e_member, const int32_t* aev_blocks, int want_backward) {
+                       void* act2, void* act3, float* e_member, const int32_t* aev_blocks, int want_backward,
+                       int rows_cap = 0) {
   const int S = model->num_species, M = model->num_members, ldx = model->ldx;
   const float sv = OPND_SCALE_VALUE, sg = OPND_SCALE_GRAD;
   const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32, kbx = ldx / 32;
@@ -428,6 +429,11 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
     default: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx;
             ta.members = M; ta.nblocks = aev_blocks; ta.c_accumulate = M > 1; ta.out_scale = sg; break;
   }
+  if (phase == 5 && want_backward == 2) {
+    // per-member dE_m/dAEV: member m writes its own [rows_cap][ldx] slab of dx (plain stores, no accumulation)
+    ta.c_accumulate = 0;
+    for (int s = 0; s < S; ++s) ta.sp[s].c_moff = rows_cap * ldx;
+  }
 }
 
 extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
@@ -448,7 +454,7 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     F.epi[p] = epis[p];
     F.dep[p] = p - 1;
     F.ph[p] = base;
-    fill_phase(F.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward);
+    fill_phase(F.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward, rows_cap);
   }
   static const int prefetch_b = []() {
     const char* e = getenv("ANI_B200_PREFETCH_B");  // 1: issue a unit's weight copies before waiting for its inputs
@@ -458,7 +464,7 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
   F.sync = sync_i32;
   F.sync_stride = rows_cap / ANI_TILE_ROWS;
   cudaMemsetAsync(sync_i32, 0, sizeof(int32_t) * (size_t)tc::MAX_PHASES * F.sync_stride, st);
-  if (want_backward && M > 1)
+  if (want_backward == 1 && M > 1)
     k_zero_live_blocks<<<592, 256, 0, st>>>(dx, model->ldx, layout_info, model->num_species, aev_blocks);
   static int num_sms = 0;
   if (num_sms == 0) {

@@ -376,6 +376,8 @@ class Workspace:
         self.aev_blocks = torch.zeros(ldx // 32 + 3, **i32)   # [count, ids..., element mask, changed flag]
         self.n_blocks = ldx // 32
         self.bucket_ranges = torch.zeros((self.max_bins - 1) * 27 * 8, **f32) if n_conf == 1 else None
+        # per-bucket species offsets (ani_b200_prepare_step -> ani_b200_aev_forward): i32[max_bins][8]
+        self.bucket_species = torch.zeros(self.max_bins * 8, **i32) if n_conf == 1 else None
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
@@ -602,7 +604,7 @@ class Engine:
                 ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
                 ptr(ws.aev_blocks), ws.grad_ptr if want_grad else None, 3 * n if want_grad else 0,
                 ptr(ws.virial) if want_virial else None, ws.virial.numel() if want_virial else 0,
-                ptr(ws.scratch), ptr(ws.status), st))
+                ptr(ws.bucket_species), ptr(ws.scratch), ptr(ws.status), st))
             if self.skin > 0:
                 check(L.ani_b200_verlet_positions(
                     0, ptr(ws.coords), ptr(ws.grid), ptr(ws.sorted_orig), n, self.skin, ptr(ws.spos),
@@ -623,7 +625,8 @@ class Engine:
             self._ev[1].record(side)
         self._timed("aev_forward", lambda: L.ani_b200_aev_forward(
             C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin),
-            ptr(ws.bucket_ranges), ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
+            ptr(ws.bucket_ranges), ptr(ws.bucket_species) if not reuse else None,
+            ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1), n, lo, hi,
             ptr(ws.row_of), ptr(ws.x), self.nets.ldx, 1, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
             ptr(ws.status), st))
 
@@ -687,6 +690,66 @@ class Engine:
                 ws.reducer.launch(ws.grad, ws.energies)
                 return 0
             self._timed("allreduce", reduce_all)
+
+    def step_members(self, species: Tensor, coords: Tensor, cell: tp.Optional[Tensor] = None, pbc: bool = False
+                     ) -> tp.Tuple[Tensor, Tensor]:
+        """Energies (M_active, C) float64 and dE_m/dcoords (M_active, C, A, 3) float32 of every ACTIVE ensemble member
+        in ONE pass (arch.py:403-436 differentiates every member by autograd; round 1 ran the engine once per member):
+        one preparation, one AEV forward, one MLP launch whose layer-1 backward writes a per-member dE_m/dAEV slab
+        (``ani_b200_mlp_step(want_backward=2)``), then the AEV backward once per member on its slab.  Eager (no
+        graph): an analysis call, not the MD loop."""
+        dev = self.device
+        n_conf, n_per_conf = species.shape
+        if pbc and n_conf != 1:
+            raise NotImplementedError("periodic batches: call once per conformer")
+        ws = self.workspace(n_conf, n_per_conf)
+        n, L, c = ws.n, self.lib, self.consts
+        nets = self.nets
+        M, ldx = nets.num_members, nets.ldx
+        active = list(nets.active)
+        if getattr(ws, "dx_members", None) is None:
+            ws.dx_members = torch.zeros(M, ws.rows_cap, ldx, dtype=torch.float32, device=dev)
+        model = _lib.MLPModel.from_buffer_copy(nets.model)     # every active member with weight 1 (not 1 / M)
+        for m in range(_lib.ANI_MAX_MEMBERS):
+            model.member_scale[m] = 1.0 if m in active else 0.0
+        grads = torch.zeros(len(active), n, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            ws.species_i32.copy_(species.reshape(-1))
+            ws.coords.copy_(coords.reshape(-1, 3))
+            if pbc:
+                ws.cell.copy_(cell.reshape(-1))
+            check(L.ani_b200_prepare_step(
+                ptr(ws.coords), ptr(ws.species_i32), n_conf, n_per_conf, ptr(ws.cell) if pbc else None, int(bool(pbc)),
+                0 if n_conf == 1 else 1, c.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
+                ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges), 0, n, c.num_species,
+                ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info),
+                len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, ldx, ptr(ws.aev_blocks), None, 0, None, 0,
+                ptr(ws.bucket_species), ptr(ws.scratch), ptr(ws.status), st), "prepare_step")
+            mask_ptr = ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1)
+            check(L.ani_b200_aev_forward(
+                C.byref(self.params), ptr(ws.grid), ptr(ws.bin_start), ptr(ws.spos), ptr(ws.sbin),
+                ptr(ws.bucket_ranges), ptr(ws.bucket_species), mask_ptr, n, 0, n, ptr(ws.row_of), ptr(ws.x), ldx, 1,
+                ptr(ws.nbr_cnt),
+                ptr(ws.nbr_list), ws.nbr_cap, ptr(ws.status), st), "aev_forward")
+            check(L.ani_b200_mlp_step(
+                C.byref(model), ptr(ws.x), ptr(ws.dx_members), ws.rows_cap, ptr(ws.row_atom), ptr(ws.layout_info),
+                ptr(ws.aev_blocks), ptr(ws.act1), ptr(ws.act2), ptr(ws.act3), ptr(ws.e_member), 2, ptr(ws.mlp_sync),
+                ptr(ws.status), st), "mlp_step")
+            for k, m in enumerate(active):
+                check(L.ani_b200_aev_backward(
+                    C.byref(self.params), ptr(ws.grid), ptr(ws.spos), ptr(ws.sorted_orig), mask_ptr, n, 0, n,
+                    ptr(ws.row_of), ws.dx_members[m].data_ptr(), ldx, ptr(ws.nbr_cnt), ptr(ws.nbr_list), ws.nbr_cap,
+                    grads[k].data_ptr(), ptr(ws.status), 0, None, st), "aev_backward")
+            check(L.ani_b200_reduce_energies(
+                C.byref(model), ptr(ws.e_member), ws.rows_cap, ptr(ws.row_of), ptr(ws.orig_to_sorted),
+                ptr(ws.species_i32), n, 0, n, n_conf, n_per_conf, None, ptr(ws.atomic), ptr(ws.member_atomic),
+                ptr(ws.energies), st), "reduce_energies")
+        e_m = ws.member_atomic.view(M, n_conf, n_per_conf)[active].double().sum(-1)          # (M_active, C)
+        if self.sae is not None:
+            sp = species.clamp(min=0)
+            e_m = e_m + self.sae[sp].masked_fill(species < 0, 0.0).sum(-1).unsqueeze(0)
+        return e_m, grads.view(len(active), n_conf, n_per_conf, 3)
 
     def _use_dataflow_mlp(self, owned: int) -> bool:
         """One data-flow launch (True) or six chained launches (False) for `owned` atoms; see __init__."""

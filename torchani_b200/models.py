@@ -22,8 +22,8 @@ from torch import Tensor
 from . import _lib
 from .aev import AEVComputer
 from .engine import Engine, StepResult
-from .neighbors import (Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff,
-                        effective_periodic_cell, narrow_down)
+from .neighbors import (CellList, Neighbors, NeighborlistArg, _validate_inputs, discard_outside_cutoff,
+                        effective_periodic_cell, narrow_down, supercell_for_thin_cell)
 from .nn import (ANINetworks, ATOMIC_NUMBER, AtomicContainer, AtomicNetwork, Ensemble, SpeciesConverter,
                  SpeciesEnergies)
 
@@ -209,6 +209,20 @@ class ANI(torch.nn.Module):
             parts = [self((species[c:c + 1], coords[c:c + 1]), cell, pbc, charge, atomic, ensemble_values).energies
                      for c in range(elem_idxs.shape[0])]
             return SpeciesEnergies(elem_idxs, torch.cat(parts, dim=1 if ensemble_values else 0))
+        # (with a cell-list neighbour list the reference raises "Cell is too small" instead, neighbors.py:402-403: so
+        # does the engine; all_pairs / adaptive models take the supercell route)
+        sup = None if isinstance(self.neighborlist, CellList) else \
+            supercell_for_thin_cell(species, coords, cell, pbc, self.cutoff)
+        if sup is not None:
+            # periodic cell thinner than the cutoff (neighbors.py:245-275): evaluate a supercell of R translation-
+            # equivalent copies; atomic energies of the original atoms are the first A, the energy is 1/R of the whole
+            sp_rep, co_rep, cell_rep, R = sup
+            a = elem_idxs.shape[1]
+            if atomic:
+                out = self((sp_rep, co_rep), cell_rep, pbc, charge, True, ensemble_values).energies[..., :a]
+            else:
+                out = self((sp_rep, co_rep), cell_rep, pbc, charge, False, ensemble_values).energies / R
+            return SpeciesEnergies(elem_idxs, out)
         cell = effective_periodic_cell(coords, cell, pbc, self.cutoff)   # PBC in some directions only
         e, e_atomic, e_member = self._guarded(lambda: _FusedEnergy.apply(
             coords, elem_idxs, cell, pbc is not None, self.engine(coords.device), bool(coords.requires_grad)))
@@ -280,26 +294,26 @@ class ANI(torch.nn.Module):
     def members_forces(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
                        pbc: tp.Optional[Tensor] = None, charge: int = 0) -> SpeciesForces:
         """Energies (M, C) and forces (M, C, A, 3) of every active ensemble member (arch.py:403-436).
-        The reference differentiates each member's energy by autograd; here the engine is run once per
-        member with only that member active (same kernels, analytic forces)."""
+        The reference differentiates each member's energy by autograd; here ONE pass of the engine
+        (``Engine.step_members``): the layer-1 backward GEMM writes one dE_m/dAEV slab per member instead of their
+        sum, and the force kernel runs once per slab."""
         species, coords = species_coordinates
         self._check_inputs(species, coords, charge)
         elem_idxs = self.species_converter(species, nop=not self.periodic_table_index)
         _validate_inputs(self.cutoff, elem_idxs, coords, cell, pbc)
+        if pbc is not None and elem_idxs.shape[0] > 1:
+            parts = [self.members_forces((species[c:c + 1], coords[c:c + 1]), cell, pbc, charge)
+                     for c in range(elem_idxs.shape[0])]
+            return SpeciesForces(elem_idxs, torch.cat([p.energies for p in parts], 1), torch.cat([p.forces for p in parts], 1))
         cell = effective_periodic_cell(coords, cell, pbc, self.cutoff)
-        eng = self.engine(coords.device)
-        active = list(self.neural_networks.active_members_idxs)
-        energies, forces = [], []
-        try:
-            for m in active:
-                self.neural_networks.set_active_members([m])
-                res = eng.step(elem_idxs, coords.detach(), cell, pbc is not None, want_grad=True)
-                energies.append(res.energies.clone())
-                forces.append(-res.grad.clone())
-        finally:
-            self.neural_networks.set_active_members(active)
-        eng.check_status()
-        return SpeciesForces(elem_idxs, torch.stack(energies).to(coords.dtype), torch.stack(forces))
+
+        def run():
+            eng = self.engine(coords.device)
+            out = eng.step_members(elem_idxs, coords.detach(), cell, pbc is not None)
+            eng.check_status()
+            return out
+        e_m, g_m = self._guarded(run)
+        return SpeciesForces(elem_idxs, e_m.to(coords.dtype), -g_m)
 
     def energies_qbcs(self, species_coordinates: tp.Tuple[Tensor, Tensor], cell: tp.Optional[Tensor] = None,
                       pbc: tp.Optional[Tensor] = None, unbiased: bool = True, charge: int = 0) -> SpeciesEnergiesQBC:

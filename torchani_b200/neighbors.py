@@ -119,6 +119,34 @@ def effective_periodic_cell(coords: Tensor, cell: tp.Optional[Tensor], pbc: tp.O
     return new.to(cell.dtype)
 
 
+def supercell_for_thin_cell(species: Tensor, coords: Tensor, cell: tp.Optional[Tensor], pbc: tp.Optional[Tensor],
+                            cutoff: float):
+    """A periodic cell THINNER than the cutoff (the reference's `all_pairs` pairs every atom with several lattice
+    images, neighbors.py:245-275; the bucket grid needs one bucket per cutoff): replicate the cell n_d = ceil(cutoff /
+    width_d) times along every too-thin direction.  Returns None if the cell is wide enough, else
+    ``(species_rep (1, R*A), coords_rep (1, R*A, 3), cell_rep, R)`` with the original atoms first: every replica is
+    translation-equivalent, so AEVs / atomic energies of the original atoms are those of the first A atoms, the energy
+    is 1/R of the supercell's, and dE/dx of an original atom is the SUM over its R copies of the supercell gradient
+    (which autograd does by itself through the replication below).  One host sync (the cell widths)."""
+    if pbc is None or cell is None or species.shape[0] != 1:
+        return None
+    c = cell.detach().to(torch.float64).cpu()
+    inv = torch.linalg.inv(c)
+    widths = 1.0 / inv.norm(dim=0)          # distance between the lattice planes of direction d
+    flags = [bool(v) for v in pbc.tolist()]
+    reps = [int(-(-(cutoff + 1e-5) // float(widths[d]))) if flags[d] else 1 for d in range(3)]
+    if max(reps) == 1:
+        return None
+    shifts = torch.tensor([[a, b, k] for a in range(reps[0]) for b in range(reps[1]) for k in range(reps[2])],
+                          dtype=coords.dtype, device=coords.device)
+    offs = shifts @ cell.to(coords.dtype)                               # (R, 3); the first one is zero
+    R = offs.shape[0]
+    coords_rep = (coords.unsqueeze(1) + offs.view(1, R, 1, 3)).reshape(1, -1, 3)
+    species_rep = species.repeat(1, R)
+    cell_rep = cell * torch.tensor(reps, dtype=cell.dtype, device=cell.device).view(3, 1)
+    return species_rep, coords_rep, cell_rep, R
+
+
 class BucketGrid:
     """Device buffers of one bucket-grid build (shared by the neighbour list and the AEV API)."""
 
