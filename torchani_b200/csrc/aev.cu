@@ -221,6 +221,37 @@ __device__ __forceinline__ int build_angular_list(const ani_aev_params& P, const
   return total;
 }
 
+// Order-preserving compaction of the neighbours within Rca (backward pass): the pair rotation there looks the
+// species of both partners up per pair and needs neither species segments nor a species-sorted list, so the counting
+// sort of build_angular_list (2 passes x 8 ballots per 32 neighbours; 8.6 % of the kernel's stall samples in round 1)
+// is replaced by one ballot per 32 neighbours.  Fills aidx/afc/afcd, returns the count (clamped to ANI_MAX_ANG).
+__device__ __forceinline__ int compact_angular_list(const ani_aev_params& P, const WarpSmem& s, int cnt, int lane,
+                                                    int32_t* status) {
+  const unsigned lt = (1u << lane) - 1u;
+  int total = 0;
+  for (int base = 0; base < cnt; base += 32) {
+    const int n = base + lane;
+    const float R = n < cnt ? s.nd[n].w : 3.0e38f;
+    const bool keep = R <= P.rca;
+    const unsigned m = __ballot_sync(ANI_FULL_MASK, keep);
+    const int pos = total + __popc(m & lt);
+    if (keep && pos < ANI_MAX_ANG) {
+      float f, df;
+      cutoff_value_grad(R, P.rca, P.cutoff_kind, f, df);
+      s.aidx[pos] = (unsigned char)n;
+      s.afc[pos] = f;
+      s.afcd[pos] = df;
+    }
+    total += __popc(m);
+  }
+  if (total > ANI_MAX_ANG) {
+    if (lane == 0) atomicOr(status, ANI_STATUS_ANG_OVERFLOW);
+    total = ANI_MAX_ANG;
+  }
+  __syncwarp();
+  return total;
+}
+
 // Counting sort (by species) of ALL neighbours: ord[] = neighbour indices grouped by species,
 // seg_all[] = segment starts.  The radial block then accumulates one species segment at a time in
 // registers (no shared-memory read-modify-write chain).
@@ -1075,7 +1106,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
   __syncwarp();
 
   // ---- 4. angular.  Lanes own rows j of the species-sorted angular list.
-  const int n_ang = build_angular_list<true>(P, s, cnt, lane, status);
+  const int n_ang = compact_angular_list(P, s, cnt, lane, status);
   if (n_ang >= 2) {
     float shfA[NA], cz[NZ], sz[NZ];
 #pragma unroll

@@ -267,6 +267,19 @@ static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* r
   return ANI_OK;
 }
 
+// Layer-1 backward dX = sum_m G1_m x W1_m: how many members one work unit contracts in its own accumulator (the
+// rest of the sum goes through vector REDs into dx).  1 = round 1 (one unit per member: most parallelism, 8 partial
+// sums per element); larger groups halve / quarter the RED traffic and the per-unit ramp at the price of fewer units.
+static int l1b_group(int M) {
+  static const int env = []() {
+    const char* e = getenv("ANI_B200_L1B_GROUP");
+    return e ? atoi(e) : 2;
+  }();
+  int g = env < 1 ? 1 : env;
+  while (g > 1 && M % g) --g;
+  return g;
+}
+
 // operand scales (common.cuh): activations / AEVs carry sv, gradients sg, weights their per-tensor
 // w_scale; every GEMM divides the product of its two operand scales out of the accumulator
 static inline float wsc(const ani_mlp_species& p, int layer) { return ANI_OPND_FP16X2 ? p.w_scale[layer] : 1.0f; }
@@ -357,14 +370,15 @@ extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int 
   // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
   // all SMs are busy even when there are fewer row tiles than SMs); the partial tiles are
   // accumulated with vector REDs into the zeroed live column blocks of dx
-  ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M;
+  const int G = l1b_group(M);
+  ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M / G;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr, M * p.h1 / 32, p.h1 / 32,
-                            1.0f / (sg * wsc(p, 0))};
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, G * p.h1, ldx, G * p.h1, 0, 0, nullptr, nullptr,
+                            M * p.h1 / 32, G * p.h1 / 32, 1.0f / (sg * wsc(p, 0))};
   }
   ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
-  ta.c_accumulate = M > 1;
+  ta.c_accumulate = M / G > 1;
   if (ta.c_accumulate && !dx_zeroed) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
   launch_gemm_tc<tc::EPI_PLAIN>(ta, st, true);
   ANI_CUDA_CHECK_LAUNCH();
@@ -410,10 +424,12 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
         ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b2), nullptr, p.h2, p.h1, p.h2, p.h1, 0, nullptr, nullptr, 0, 0,
                                 1.0f / (sg * wsc(p, 1))};
         break;
-      default:
-        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, p.h1, ldx, p.h1, 0, 0, nullptr, nullptr,
-                                M * p.h1 / 32, p.h1 / 32, 1.0f / (sg * wsc(p, 0))};
+      default: {
+        const int G = want_backward == 2 ? 1 : l1b_group(M);
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, G * p.h1, ldx, G * p.h1, 0, 0, nullptr, nullptr,
+                                M * p.h1 / 32, G * p.h1 / 32, 1.0f / (sg * wsc(p, 0))};
         break;
+      }
     }
   }
   switch (phase) {
@@ -427,7 +443,8 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
     case 4: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
             ta.out_scale = sg; break;
     default: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx;
-            ta.members = M; ta.nblocks = aev_blocks; ta.c_accumulate = M > 1; ta.out_scale = sg; break;
+            ta.members = M / (want_backward == 2 ? 1 : l1b_group(M)); ta.nblocks = aev_blocks;
+            ta.c_accumulate = ta.members > 1; ta.out_scale = sg; break;
   }
   if (phase == 5 && want_backward == 2) {
     // per-member dE_m/dAEV: member m writes its own [rows_cap][ldx] slab of dx (plain stores, no accumulation)

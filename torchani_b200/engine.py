@@ -376,8 +376,12 @@ class Workspace:
         self.aev_blocks = torch.zeros(ldx // 32 + 3, **i32)   # [count, ids..., element mask, changed flag]
         self.n_blocks = ldx // 32
         self.bucket_ranges = torch.zeros((self.max_bins - 1) * 27 * 8, **f32) if n_conf == 1 else None
-        # per-bucket species offsets (ani_b200_prepare_step -> ani_b200_aev_forward): i32[max_bins][8]
-        self.bucket_species = torch.zeros(self.max_bins * 8, **i32) if n_conf == 1 else None
+        # per-bucket species offsets (ani_b200_prepare_step -> ani_b200_aev_forward): i32[max_bins][8].  Experiment
+        # (ANI_B200_AEV_BSS=1): lets the AEV forward skip its candidate-counting pass; measured on B200 it is 2 us
+        # SLOWER at 10 k atoms (64.2 vs 62.4 us) -- the table row is one more dependent global load at the head of
+        # every CTA and the per-warp prefixes cost what the two saved barriers bought -- so it is off
+        self.bucket_species = (torch.zeros(self.max_bins * 8, **i32)
+                               if n_conf == 1 and os.environ.get("ANI_B200_AEV_BSS", "0") != "0" else None)
         self.nbr_cap = nbr_cap
         self.nbr_cnt = torch.zeros(n, **i32)
         self.nbr_list = torch.zeros(n * nbr_cap, **i32)
