@@ -270,12 +270,14 @@ static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* r
 // Layer-1 backward dX = sum_m G1_m x W1_m: how many members one work unit contracts in its own accumulator (the
 // rest of the sum goes through vector REDs into dx).  1 = round 1 (one unit per member: most parallelism, 8 partial
 // sums per element); larger groups halve / quarter the RED traffic and the per-unit ramp at the price of fewer units.
-static int l1b_group(int M) {
+// Measured on B200 (profiles/r02_sweep.md, run 16; step ms at G = 1 / 2 / 4): 999 atoms 0.147 / 0.150 / 0.158,
+// 9 999 atoms 0.373 / 0.364 / 0.367, 49 999 atoms 2.062 / 1.960 / 1.929 -> by row capacity unless the env pins it.
+static int l1b_group(int M, int rows_cap) {
   static const int env = []() {
     const char* e = getenv("ANI_B200_L1B_GROUP");
-    return e ? atoi(e) : 2;
+    return e ? atoi(e) : 0;
   }();
-  int g = env < 1 ? 1 : env;
+  int g = env >= 1 ? env : (rows_cap < 4096 ? 1 : rows_cap < 32768 ? 2 : 4);
   while (g > 1 && M % g) --g;
   return g;
 }
@@ -370,7 +372,7 @@ extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int 
   // dX = sum_m G1_m x W1_m: split-K over the members (one work unit per (row tile, member), so
   // all SMs are busy even when there are fewer row tiles than SMs); the partial tiles are
   // accumulated with vector REDs into the zeroed live column blocks of dx
-  const int G = l1b_group(M);
+  const int G = l1b_group(M, rows_cap);
   ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx; ta.members = M / G;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
@@ -425,7 +427,7 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
                                 1.0f / (sg * wsc(p, 1))};
         break;
       default: {
-        const int G = want_backward == 2 ? 1 : l1b_group(M);
+        const int G = want_backward == 2 ? 1 : l1b_group(M, rows_cap);
         ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, G * p.h1, ldx, G * p.h1, 0, 0, nullptr, nullptr,
                                 M * p.h1 / 32, G * p.h1 / 32, 1.0f / (sg * wsc(p, 0))};
         break;
@@ -443,7 +445,7 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
     case 4: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
             ta.out_scale = sg; break;
     default: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx;
-            ta.members = M / (want_backward == 2 ? 1 : l1b_group(M)); ta.nblocks = aev_blocks;
+            ta.members = M / (want_backward == 2 ? 1 : l1b_group(M, rows_cap)); ta.nblocks = aev_blocks;
             ta.c_accumulate = ta.members > 1; ta.out_scale = sg; break;
   }
   if (phase == 5 && want_backward == 2) {
