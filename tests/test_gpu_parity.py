@@ -290,3 +290,52 @@ def test_dataflow_mlp_launch_matches_the_chained_launches(engines, n_mol):
         assert float((out["0"][2] - out["1"][2]).abs().max()) < 1e-6
     finally:
         eng.mlp_mode = saved
+
+
+@pytest.mark.parametrize("n_mol,shard", [(10, (0, 1)), (333, (0, 1)), (3333, (0, 1)), (3333, (1, 4)), (5000, (3, 8))])
+def test_cluster_preparation_matches_the_persistent_grid_kernel(n_mol, shard, monkeypatch):
+    """ani_b200_prepare_step has two single-launch forms: a persistent grid with device-wide barriers
+    (k_prep_fused) and, for periodic single systems of MD size, one thread-block cluster (k_prep_cluster).
+    Everything they hand to the rest of the step must be bit-identical: the bucket grid, the deterministic
+    (bucket, species, input index) order, the neighbour-range table, the row layout and the live AEV blocks --
+    for the whole system and for the owned slice of a rank."""
+    from torchani_b200 import synthetic
+    from torchani_b200.engine import Engine, PackedNetworks, constants_2x
+    dev = torch.device("cuda:0")
+    consts = constants_2x()
+    m = oracle_model("2x")
+    nets = PackedNetworks([[wm[s] for s in m.symbols] for wm in m.weights], consts.out_dim, dev)
+    _, idx, coords, cell, _ = synthetic.water_box(n_mol, seed=3)
+    idx = idx.clone()
+    idx[0, 5] = -1      # one padding atom: the trash bucket is exercised too
+    sp, co, ce = idx.to(dev), coords.to(dev), cell.to(dev)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ANI_B200_PREP_CLUSTER", flag)
+        eng = Engine(consts, nets, [m.sae[s] for s in m.symbols], cuda_graph=False)
+        for _ in range(2):   # the second call starts from the first one's leftovers in the scratch area
+            r = eng.step(sp, co, ce, True, shard=shard)
+        eng.check_status()
+        ws = eng.workspace(*idx.shape)
+        grid = ws.grid.clone()
+        nbins = int(grid.cpu()[25])   # ani_grid: 21 floats, dims[3], pbc, nbins, ...
+        rec = dict(grid=grid, bin_start=ws.bin_start[:nbins + 2].clone(), sorted_orig=ws.sorted_orig.clone(),
+                   orig_to_sorted=ws.orig_to_sorted.clone(), spos=ws.spos.clone(), sbin=ws.sbin.clone(),
+                   ranges=ws.bucket_ranges[:nbins * 27 * 8].clone().view(torch.int32),
+                   row_atom=ws.row_atom.clone(), tile_species=ws.tile_species.clone(),
+                   layout_info=ws.layout_info.clone(), aev_blocks=ws.aev_blocks[:ws.n_blocks + 2].clone(),
+                   energies=r.energies.clone(), grad=r.grad.clone())
+        lo = int(ws.n * shard[0] // shard[1])
+        hi = int(ws.n * (shard[0] + 1) // shard[1])
+        n_real = int(rec["bin_start"][nbins])
+        rec["row_of"] = ws.row_of[lo:min(hi, n_real)].clone()
+        out[flag] = rec
+        assert nbins > 0
+    for k in out["0"]:
+        a, b = out["0"][k], out["1"][k]
+        if k in ("energies", "grad"):
+            assert torch.allclose(a, b, rtol=0, atol=2e-6), k    # (split-K order of the layer-1 backward)
+        elif k == "spos":
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), k
+        else:
+            assert torch.equal(a, b), k

@@ -1064,6 +1064,336 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
 }
 
 // ---------------------------------------------------------------------------------------
+// The preparation as ONE THREAD-BLOCK CLUSTER (k_prep_cluster): at MD sizes (10 k atoms = 40 blocks of
+// work) the step above is nothing but dependency latency -- seven device-wide barriers (atomic + spin on
+// an L2 word, ~2.5 us each) around phases of one or two dependent global round trips.  Eight CTAs of 1024
+// threads on one GPC do the same work with the hardware cluster barrier (barrier.cluster, release /
+// acquire at cluster scope) between the phases, and four barriers instead of seven:
+//   * every CTA scans the bucket counts into ITS OWN shared-memory copy of bin_start (CTA 0 also
+//     writes the global array), so the scan needs no barrier behind it and the scatter / neighbour-range
+//     table / ordering phases read bin_start from shared memory;
+//   * the (species, input index) order inside a bucket is found by ONE WARP PER BUCKET: the lanes load
+//     the bucket's members once (two dependent loads in all) and rank them with shuffles, instead of every
+//     atom walking its bucket through global memory (a chain of 2 x bucket-size dependent loads);
+//   * every CTA scans the chunk histograms itself (shared memory), so the row assignment follows
+//     without another barrier; CTA 0 writes the layout words, the tile table and the live AEV blocks.
+// Outputs are bit-identical to k_prep_fused (tests/test_gpu_api.py::test_prepare_cluster_matches_fused).
+// Used for periodic single systems up to PREP_CLUSTER_MAX_ATOMS atoms and PREP_CLUSTER_MAX_BINS buckets;
+// larger problems have enough work per phase for the whole device and keep the persistent-grid kernel.
+// ---------------------------------------------------------------------------------------
+constexpr int PREP_CLUSTER_CTAS = 8;
+constexpr int PREP_CLUSTER_THREADS = 1024;
+constexpr int PREP_CLUSTER_MAX_ATOMS = 16384;
+constexpr int PREP_CLUSTER_MAX_BINS = 6144;     // shared-memory copy of bin_start (+ 2 words)
+constexpr int PREP_CLUSTER_MAX_CHUNKS = PREP_CLUSTER_MAX_ATOMS / LAYOUT_CHUNK;
+
+__device__ __forceinline__ void prep_cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// live 32-column AEV blocks for the element mask (one warp; the same walk as k_prep_layout)
+__device__ __forceinline__ void live_aev_blocks(const PrepArgs& A, unsigned mask, int lane) {
+  const int S = A.S, RL = S * A.n_shf_r;
+  int count = 0;
+  for (int b0 = 0; b0 < A.ldx / 32; b0 += 32) {
+    const int b = b0 + lane;
+    bool active = false;
+    if (b < A.ldx / 32) {
+      for (int c = b * 32; c < b * 32 + 32 && c < A.out_dim && !active;
+           c = (c < RL) ? c + 1 : RL + ((c - RL) / A.angular_sub + 1) * A.angular_sub) {
+        if (c < RL) {
+          active = (mask >> (c / A.n_shf_r)) & 1u;
+        } else {
+          int s1 = 0, rem = (c - RL) / A.angular_sub;
+          while (rem >= S - s1) {
+            rem -= S - s1;
+            ++s1;
+          }
+          active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
+        }
+      }
+    }
+    const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
+    if (active) A.blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
+    count += __popc(live);
+  }
+  if (lane == 0) {
+    A.blocks[0] = count;
+    A.blocks[A.ldx / 32 + 2] = (A.blocks[A.ldx / 32 + 1] != (int)mask);
+    A.blocks[A.ldx / 32 + 1] = (int)mask;
+  }
+}
+
+__global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP_CLUSTER_THREADS, 1)
+    k_prep_cluster(const __grid_constant__ PrepArgs A) {
+  __shared__ ani_grid sg;
+  __shared__ int s_start[PREP_CLUSTER_MAX_BINS + 2];
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  __shared__ int s_hist[PREP_CLUSTER_MAX_CHUNKS * ANI_MAX_SPECIES];   // exclusive scan over the chunks, per species
+  __shared__ int s_tot[ANI_MAX_SPECIES];
+  __shared__ int s_base[ANI_MAX_SPECIES + 1];
+  __shared__ int s_wcnt[PREP_CLUSTER_THREADS / 32][ANI_MAX_SPECIES];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int gstride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
+  const int n = A.n, S = A.S;
+  // ---- phase 0: the grid (every CTA its own copy) + zero-fill of the counters that are used below
+  if (tid == 0) {
+    const float none[3] = {0.f, 0.f, 0.f};
+    sg = compute_grid(A.n_conf, A.n_per_conf, A.cell, A.pbc, A.mode, A.cutoff, A.max_bins, none, none, A.status);
+    if (blockIdx.x == 0) *A.grid = sg;
+  }
+  __syncthreads();
+  const int nbins = sg.nbins;
+  {
+    // bin_count[0 .. nbins] | counter | present | chunk_hist[(n_chunks + 1) * 8] are contiguous, but bin_count is
+    // max_bins + 1 long: two ranges
+    for (int k = gtid; k <= nbins; k += gstride) A.bin_count[k] = 0;
+    const int tail = 2 + (A.n_chunks + 1) * ANI_MAX_SPECIES;
+    for (int k = gtid; k < tail; k += gstride) A.counter[k] = 0;
+  }
+  prep_cluster_barrier();
+  // ---- phase 1: bucket of every atom, slot inside the bucket by atomics
+  for (int a = gtid; a < n; a += gstride) {
+    int bin;
+    if (A.species[a] < 0) {
+      bin = nbins;  // padding atoms: trash bucket, never a neighbour, never a centre
+    } else {
+      float3 p;
+      wrapped_position(sg, A.coords, a, p, bin);
+    }
+    A.bin_of[a] = bin;
+    A.slot[a] = atomicAdd(&A.bin_count[bin], 1);
+  }
+  prep_cluster_barrier();
+  // ---- phase 1b: EVERY CTA scans the bucket counts (exclusive) into its shared-memory bin_start
+  {
+    const int m = nbins + 1;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < m; base += PREP_CLUSTER_THREADS) {
+      const int i = base + tid;
+      const int v = (i < m) ? __ldcg(&A.bin_count[i]) : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(ANI_FULL_MASK, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_warp[w] = x;
+      __syncthreads();
+      if (w == 0) {
+        int t = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(ANI_FULL_MASK, t, o);
+          if (lane >= o) t += y;
+        }
+        s_warp[lane] = t;  // inclusive over warps
+      }
+      __syncthreads();
+      const int incl = x + ((w == 0) ? 0 : s_warp[w - 1]) + s_carry;
+      if (i < m) {
+        s_start[i] = incl - v;
+        if (blockIdx.x == 0) A.bin_start[i] = incl - v;
+      }
+      __syncthreads();
+      if (tid == PREP_CLUSTER_THREADS - 1) s_carry = incl;
+      __syncthreads();
+    }
+    if (tid == 0) {
+      s_start[m] = s_carry;
+      if (blockIdx.x == 0) {
+        A.bin_start[m] = s_carry;
+        A.grid->n_real = s_start[nbins];  // everything before the trash bucket
+      }
+    }
+    __syncthreads();
+  }
+  const int n_real = s_start[nbins];
+  // ---- phase 2: scatter into buckets + per-bucket table of the 27 neighbouring buckets
+  {
+    const int t2 = A.ranges ? max(n, nbins * 27) : n;
+    for (int idx = gtid; idx < t2; idx += gstride) {
+      if (idx < n) A.tmp_list[s_start[A.bin_of[idx]] + A.slot[idx]] = idx;
+      if (!A.ranges || sg.mode != 0) continue;
+      const int b = idx / 27, o = idx % 27;
+      if (b >= nbins) continue;
+      const int iz = b % sg.dims[2], iy = (b / sg.dims[2]) % sg.dims[1], ix = b / (sg.dims[2] * sg.dims[1]);
+      int j[3] = {ix + o / 9 - 1, iy + (o / 3) % 3 - 1, iz + o % 3 - 1};
+      int wv[3];
+      for (int d = 0; d < 3; ++d) {
+        wv[d] = 0;
+        if (j[d] < 0) {
+          wv[d] = -1;
+          j[d] += sg.dims[d];
+        } else if (j[d] >= sg.dims[d]) {
+          wv[d] = 1;
+          j[d] -= sg.dims[d];
+        }
+      }
+      const bool exists = sg.pbc || !(wv[0] | wv[1] | wv[2]);
+      int lo = 0, hi = 0;
+      const int code = (wv[0] + 1) * 9 + (wv[1] + 1) * 3 + (wv[2] + 1);
+      const int nbk = exists ? (j[0] * sg.dims[1] + j[1]) * sg.dims[2] + j[2] : 0;
+      if (exists) {
+        lo = s_start[nbk];
+        hi = s_start[nbk + 1];
+      }
+      const float wx = (float)wv[0], wy = (float)wv[1], wz = (float)wv[2];
+      A.ranges[2 * (size_t)idx] =
+          make_float4(__int_as_float(lo), __int_as_float(hi), __int_as_float(code), __int_as_float(nbk));
+      A.ranges[2 * (size_t)idx + 1] = make_float4(wx * sg.cell[0] + wy * sg.cell[3] + wz * sg.cell[6],
+                                                  wx * sg.cell[1] + wy * sg.cell[4] + wz * sg.cell[7],
+                                                  wx * sg.cell[2] + wy * sg.cell[5] + wz * sg.cell[8], 0.f);
+    }
+    // (independent of everything above) force accumulator, row table and conformer energies start from zero / -1
+    if (A.zero_f32)
+      for (int k = gtid; k < A.zero_f32_count; k += gstride) A.zero_f32[k] = 0.f;
+    for (int r = gtid; r < A.rows_cap; r += gstride) A.row_atom[r] = -1;
+    if (A.zero_f64)
+      for (int k = gtid; k < A.zero_f64_count; k += gstride) A.zero_f64[k] = 0.0;
+  }
+  prep_cluster_barrier();
+  // ---- phase 3: one warp per bucket: deterministic (species, input index) order, sorted arrays, per-chunk
+  //      species histogram, element presence mask, per-bucket species offsets
+  {
+    const int hi_real = min(A.hi, n_real);
+    const int nwarps = gstride >> 5;
+    unsigned present = 0;
+    for (int b = gtid >> 5; b <= nbins; b += nwarps) {
+      const int lo = s_start[b], hi = s_start[b + 1];
+      int below[ANI_MAX_SPECIES];   // members with species < k (lane-uniform)
+#pragma unroll
+      for (int k = 0; k < ANI_MAX_SPECIES; ++k) below[k] = 0;
+      for (int base = lo; base < hi; base += 32) {
+        const int e = base + lane;
+        const bool valid = e < hi;
+        const int a = valid ? __ldcg(&A.tmp_list[e]) : 0x7fffffff;
+        const int spa = valid ? A.species[a] : 0x7fff;
+        int rank = 0;
+        for (int base2 = lo; base2 < hi; base2 += 32) {
+          int t = a, spt = spa;
+          if (base2 != base) {
+            const int e2 = base2 + lane;
+            t = e2 < hi ? __ldcg(&A.tmp_list[e2]) : 0x7fffffff;
+            spt = e2 < hi ? A.species[t] : 0x7fff;
+          }
+          const int cnt = min(32, hi - base2);
+          for (int k = 0; k < cnt; ++k) {
+            const int tk = __shfl_sync(ANI_FULL_MASK, t, k), sk = __shfl_sync(ANI_FULL_MASK, spt, k);
+            rank += (sk < spa) || (sk == spa && tk < a);
+          }
+        }
+#pragma unroll
+        for (int k = 1; k < ANI_MAX_SPECIES; ++k) below[k] += __popc(__ballot_sync(ANI_FULL_MASK, valid && spa < k));
+#pragma unroll
+        for (int k = 0; k < ANI_MAX_SPECIES; ++k)
+          if (__any_sync(ANI_FULL_MASK, valid && spa == k)) present |= 1u << k;
+        if (valid) {
+          const int i = lo + rank;
+          A.sorted_orig[i] = a;
+          A.orig_to_sorted[a] = i;
+          A.sbin[i] = b;
+          float3 p = make_float3(0.f, 0.f, 0.f);
+          if (spa >= 0) {
+            int bb;
+            wrapped_position(sg, A.coords, a, p, bb);
+          }
+          A.spos[i] = make_float4(p.x, p.y, p.z, __int_as_float(spa));
+          if (spa >= 0 && i >= A.lo && i < hi_real)
+            atomicAdd(&A.chunk_hist[((i - A.lo) / LAYOUT_CHUNK) * ANI_MAX_SPECIES + spa], 1);
+        }
+      }
+      if (A.bss && b < nbins && lane == 0) {
+        int4* dst = reinterpret_cast<int4*>(A.bss + (size_t)b * ANI_MAX_SPECIES);
+        dst[0] = make_int4(below[0], below[1], below[2], below[3]);
+        dst[1] = make_int4(below[4], below[5], below[6], below[7]);
+      }
+    }
+    if (lane == 0 && present) atomicOr(A.present, (int)present);
+  }
+  prep_cluster_barrier();
+  // ---- phase 4: EVERY CTA: exclusive scan of the chunk histograms per species (shared memory), species row
+  //      bases; CTA 0: layout words, tile table, live AEV column blocks
+  {
+    const int nc = A.n_chunks;
+    if (w < ANI_MAX_SPECIES) {   // warp w scans species w over the chunks
+      int run = 0;
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        const int v = c < nc ? __ldcg(&A.chunk_hist[c * ANI_MAX_SPECIES + w]) : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(ANI_FULL_MASK, x, o);
+          if (lane >= o) x += y;
+        }
+        if (c < nc) s_hist[c * ANI_MAX_SPECIES + w] = run + x - v;
+        run += __shfl_sync(ANI_FULL_MASK, x, 31);
+      }
+      if (lane == 0) s_tot[w] = run;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int row = 0, owned = 0;
+      for (int s = 0; s < S; ++s) {
+        s_base[s] = row;
+        owned += s_tot[s];
+        row += (s_tot[s] + ANI_TILE_ROWS - 1) / ANI_TILE_ROWS * ANI_TILE_ROWS;
+      }
+      s_base[S] = row;
+      if (blockIdx.x == 0) {
+        A.layout_info[0] = row / ANI_TILE_ROWS;
+        A.layout_info[1] = row;
+        A.layout_info[2] = owned;
+        A.layout_info[3] = 0;
+        for (int s = 0; s <= S; ++s) A.layout_info[4 + s] = s_base[s] / ANI_TILE_ROWS;
+        for (int s = S + 1; s <= ANI_MAX_SPECIES; ++s) A.layout_info[4 + s] = row / ANI_TILE_ROWS;
+      }
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+      const int n_tiles_cap = A.rows_cap / ANI_TILE_ROWS;
+      for (int t = tid; t < n_tiles_cap; t += PREP_CLUSTER_THREADS) {
+        const int r = t * ANI_TILE_ROWS;
+        int sp = -1;
+        for (int s = 0; s < S; ++s)
+          if (r >= s_base[s] && r < s_base[s + 1] && r < s_base[s] + s_tot[s]) sp = s;
+        A.tile_species[t] = sp;
+      }
+      if (w == 31) live_aev_blocks(A, (unsigned)__ldcg(A.present), lane);
+    }
+  }
+  // ---- phase 5: row assignment, four 256-atom chunks of the owned sorted slice per CTA pass (8 warps each)
+  {
+    const int hi_real = min(A.hi, n_real);
+    constexpr int SUBS = PREP_CLUSTER_THREADS / LAYOUT_CHUNK;   // 4
+    const int sub = tid / LAYOUT_CHUNK, wl = w % (LAYOUT_CHUNK / 32);
+    for (int c0 = blockIdx.x * SUBS; c0 < A.n_chunks; c0 += gridDim.x * SUBS) {
+      const int c = c0 + sub;
+      const int i = A.lo + c * LAYOUT_CHUNK + (tid % LAYOUT_CHUNK);
+      const int sp = (c < A.n_chunks && i < hi_real) ? __float_as_int(__ldcg(&A.spos[i]).w) : -1;
+      int my_rank = 0;
+      for (int s = 0; s < S; ++s) {
+        const unsigned m = __ballot_sync(ANI_FULL_MASK, sp == s);
+        if (sp == s) my_rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_wcnt[w][s] = __popc(m);
+      }
+      __syncthreads();
+      if (sp >= 0) {
+        int off = 0;
+        for (int ww = 0; ww < wl; ++ww) off += s_wcnt[sub * (LAYOUT_CHUNK / 32) + ww][sp];
+        const int row = s_base[sp] + s_hist[c * ANI_MAX_SPECIES + sp] + off + my_rank;
+        A.row_of[i] = row;
+        A.row_atom[row] = i;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Verlet-skin reuse of the bucket grid (neighbors.py:759-884, VerletCellList): a grid built with
 // cutoff + skin stays valid -- every pair within the true cutoff is still found in the 27 buckets
 // around an atom, and the AEV kernels screen with the true cutoff and the CURRENT positions -- as
@@ -1269,7 +1599,13 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
     const char* e = getenv("ANI_B200_PREP_FUSED");  // ANI_B200_PREP_FUSED=0: the five-launch sequence
     return !e || atoi(e) != 0;
   }();
-  if (fused) {
+  // periodic single systems of MD size: one thread-block cluster (ANI_B200_PREP_CLUSTER=0: never)
+  const char* ce = getenv("ANI_B200_PREP_CLUSTER");
+  const bool cluster_ok = (!ce || atoi(ce) != 0) && fused && A.inline_setup && mode == 0 &&
+                          n <= PREP_CLUSTER_MAX_ATOMS && min(max_bins - 1, n + 1) <= PREP_CLUSTER_MAX_BINS;
+  if (cluster_ok) {
+    k_prep_cluster<<<PREP_CLUSTER_CTAS, PREP_CLUSTER_THREADS, 0, st>>>(A);
+  } else if (fused) {
     // one persistent launch, device-wide barriers between the phases; every block must be resident:
     // 2 blocks of 256 threads per SM at most (the kernel allows far more)
     int32_t* bar = grid_bar;

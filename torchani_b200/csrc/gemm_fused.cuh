@@ -26,6 +26,8 @@
 //   * waits are bounded (status ANI_STATUS_INTERNAL instead of a hung GPU).
 // The single-phase kernel of gemm_tc.cuh remains (ANI_B200_MLP_FUSED=0, and the CTA-pair experiment).
 #pragma once
+#include <type_traits>
+
 #include "gemm_tc.cuh"
 
 namespace ani {
@@ -102,12 +104,12 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
   const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
   const int quad = warp & 3, half = warp >> 2;
   const int r_tile = quad * 32 + lane;
-  uint32_t my_off[4], st_off[4];
-#pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    my_off[ch] = swz_off(r_tile, ch);   // inside a 128-row piece (global)
-    st_off[ch] = swz_off(lane, ch);     // inside this warp's 32-row staging image (shared)
-  }
+  // byte offset of 16-byte chunk ch of this thread's row: inside a 128-row piece (global) and inside this warp's
+  // 32-row staging image (shared) -- swz_off() of common.cuh, its row part kept in two registers
+  const uint32_t my_base = swz_off(r_tile, 0) & ~0x30u, st_base = swz_off(lane, 0) & ~0x30u;
+  const uint32_t row_sw = (uint32_t)(lane >> 1) & 3u;   // (row >> 1) & 3 is the same for r_tile and lane
+  auto my_off = [&](int ch) { return my_base + (((uint32_t)ch ^ row_sw) << 4); };
+  auto st_off = [&](int ch) { return st_base + (((uint32_t)ch ^ row_sw) << 4); };
   const float acc_scale = sp.acc_scale;
   const bool tiled_out = EPI != EPI_PLAIN && (EPI != EPI_HEAD || args.want_backward);
   const int my_row = tl.rt * TM + r_tile;
@@ -121,32 +123,36 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
                       ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES;
   float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
   const int ngroups = tl.bn / 32;
-  uint4 yq[2 * PARTS];
-  auto load_y = [&](int g, int hh) {
+  // stored activation of this thread's row: one register set per 16-column half, each refilled for the SAME half of
+  // the warp's next group as soon as it has been consumed -- the loads run two halves (one whole 32-column group of
+  // epilogue math) ahead of their use; one half ahead left ~27 % of the backward epilogues' stall samples on them
+  uint4 yq[2][2 * PARTS];
+  auto load_y = [&](int g, int hh, uint4 (&q)[2 * PARTS]) {
     const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
 #pragma unroll
     for (int p = 0; p < PARTS; ++p) {
       // (plain cached loads: this SM has not read these lines before in this launch, so the L1 cannot hold a stale
       // copy of what another SM's TMA stores wrote in an earlier phase; the four chunks of a row share L1 lines)
-      yq[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]);
-      yq[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]);
+      q[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off(2 * hh));
+      q[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off(2 * hh + 1));
     }
   };
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after();
   // (only now: the accumulator barrier is what orders this warp after the producer's acquire of the row tile's
   // inputs -- the stored activation read here was written by an earlier phase, possibly moments ago)
-  if (EPI == EPI_MUL_DCELU && half < ngroups) load_y(half, 0);
+  if (EPI == EPI_MUL_DCELU && half < ngroups) {
+    load_y(half, 0, yq[0]);
+    load_y(half, 1, yq[1]);
+  }
 
-  auto process = [&](int g, int hh, const uint32_t (&r)[16]) {
+  auto process = [&](int g, auto hh_c, const uint32_t (&r)[16]) {
+    constexpr int hh = decltype(hh_c)::value;
     float y[16];
     if (EPI == EPI_MUL_DCELU) {
-      join_chunk(yq, y);
-      join_chunk(yq + 1, y + 8);
-      if (hh == 0)
-        load_y(g, 1);
-      else if (g + 2 < ngroups)
-        load_y(g + 2, 0);
+      join_chunk(yq[hh], y);
+      join_chunk(yq[hh] + 1, y + 8);
+      if (g + 2 < ngroups) load_y(g + 2, hh, yq[hh]);
     }
     unsigned char* sb = sb0 + buf * EPI_STAGE_BYTES;
     if (tiled_out && hh == 0) {
@@ -195,7 +201,7 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
         uint32_t w[4][PARTS];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_pair(o[8 * c + 2 * i], o[8 * c + 2 * i + 1], w[i]);
-        const uint32_t off = st_off[2 * hh + c];
+        const uint32_t off = st_off(2 * hh + c);
 #pragma unroll
         for (int p = 0; p < PARTS; ++p)
           *reinterpret_cast<uint4*>(sb + p * EPI_PART_BYTES + off) = make_uint4(w[0][p], w[1][p], w[2][p], w[3][p]);
@@ -221,10 +227,10 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
     for (int g = half; g < ngroups; g += 2) {
       tmem_ld_wait(r0);
       tmem_ld16_issue(taddr + g * 32 + 16, r1);
-      process(g, 0, r0);
+      process(g, std::integral_constant<int, 0>{}, r0);
       tmem_ld_wait(r1);
       if (g + 2 < ngroups) tmem_ld16_issue(taddr + (g + 2) * 32, r0);
-      process(g, 1, r1);
+      process(g, std::integral_constant<int, 1>{}, r1);
     }
   }
   if (EPI == EPI_HEAD) {

@@ -38,6 +38,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ani {
@@ -724,33 +726,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       float* cplain = reinterpret_cast<float*>(args.C) + (size_t)my_row * args.ldc + (size_t)tl.mem * sp.c_moff;
       const int ngroups = tl.bn / 32;
       // stored activation (all pieces) of 16 columns = chunks 2*hh, 2*hh+1 of group g, this thread's row
-      uint4 yq[2 * PARTS];
-      auto load_y = [&](int g, int hh) {
+      // one register set per 16-column half, refilled for the same half of the warp's next group as soon as it has
+      // been consumed: the loads run a whole 32-column group of epilogue math ahead of their use
+      uint4 yq[2][2 * PARTS];
+      auto load_y = [&](int g, int hh, uint4 (&q)[2 * PARTS]) {
         const unsigned char* blk = ct + (size_t)g * A_BLOCK_BYTES;
 #pragma unroll
         for (int p = 0; p < PARTS; ++p) {
-          yq[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]);
-          yq[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]);
+          q[2 * p] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh]);
+          q[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off[2 * hh + 1]);
         }
       };
-      if (EPI == EPI_MUL_DCELU && half < ngroups && !(args.debug & 128)) load_y(half, 0);  // overlaps the wait for the accumulator
+      if (EPI == EPI_MUL_DCELU && half < ngroups && !(args.debug & 128)) {  // overlaps the wait for the accumulator
+        load_y(half, 0, yq[0]);
+        load_y(half, 1, yq[1]);
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 0) stamp(tloc, 2, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
 
       // one 16-column half of group g: raw accumulator registers -> epilogue math -> staging / store
-      auto process = [&](int g, int hh, const uint32_t (&r)[16]) {
+      auto process = [&](int g, auto hh_c, const uint32_t (&r)[16]) {
+        constexpr int hh = decltype(hh_c)::value;
         float y[16];
         if (EPI == EPI_MUL_DCELU) {
-          join_chunk(yq, y);
-          join_chunk(yq + 1, y + 8);
-          if (!(args.debug & 128)) {  // prefetch the next half this warp handles
-            if (hh == 0)
-              load_y(g, 1);
-            else if (g + 2 < ngroups)
-              load_y(g + 2, 0);
-          }
+          join_chunk(yq[hh], y);
+          join_chunk(yq[hh] + 1, y + 8);
+          if (!(args.debug & 128) && g + 2 < ngroups) load_y(g + 2, hh, yq[hh]);
         }
         unsigned char* sb = sb0 + buf * EPI_STAGE_BYTES;
         if (tiled_out && hh == 0) {
@@ -828,10 +831,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
         for (int g = half; g < ngroups; g += 2) {
           tmem_ld_wait(r0);
           tmem_ld16_issue(taddr + g * 32 + 16, r1);
-          process(g, 0, r0);
+          process(g, std::integral_constant<int, 0>{}, r0);
           tmem_ld_wait(r1);
           if (g + 2 < ngroups) tmem_ld16_issue(taddr + (g + 2) * 32, r0);
-          process(g, 1, r1);
+          process(g, std::integral_constant<int, 1>{}, r1);
         }
       }
       if (EPI == EPI_HEAD) {
