@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ANI_B200_ABI_VERSION 3
+#define ANI_B200_ABI_VERSION 4
 
 #define ANI_MAX_SPECIES 8
 #define ANI_MAX_SHFR 32
@@ -315,6 +315,11 @@ typedef struct ani_mlp_model {
   float celu_alpha;
   float member_scale[ANI_MAX_MEMBERS]; /* d(output)/d(member energy): 1/M_active or 0       */
   ani_mlp_species sp[ANI_MAX_SPECIES];
+  /* optional device scratch, sum over the species of ldx * (M * h1 / 32) * 2 * P * 32 bytes (the size of the t_b1   */
+  /* operands together), or NULL: every step gathers the LIVE column blocks of the layer-1 backward operands into   */
+  /* it (ani_b200_zero_live_blocks / ani_b200_mlp_step / ani_b200_mlp_backward), so that the GEMM moves one         */
+  /* K-block of them with one bulk copy.  No state is carried between steps; one step at a time per model.          */
+  void* b1_compact;
 } ani_mlp_model;
 
 /* 6a. Model-pack time: plain fp32 weights -> the tiled B operand above (one launch per operand; `batch`   */

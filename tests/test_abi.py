@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in ani_b200.h but not exported"
     from torchani_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "ctypes prototypes out of sync with the header"
-    assert _lib.lib().ani_b200_abi_version() == 3
+    assert _lib.lib().ani_b200_abi_version() == 4
 
 
 def test_struct_layouts_match_header(tmp_path):

@@ -62,6 +62,7 @@ class MLPModel(C.Structure):
         ("h1_max", C.c_int32), ("h2_max", C.c_int32), ("h3_max", C.c_int32), ("pad_", C.c_int32),
         ("celu_alpha", C.c_float), ("member_scale", C.c_float * ANI_MAX_MEMBERS),
         ("sp", MLPSpecies * ANI_MAX_SPECIES),
+        ("b1_compact", C.c_void_p),
     ]
 
 
@@ -136,7 +137,7 @@ def _load(path: str) -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.ani_b200_abi_version() != 3:
+    if lib.ani_b200_abi_version() != 4:
         raise ImportError(f"{path}: ABI version mismatch")
     return lib
 

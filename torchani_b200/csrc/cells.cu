@@ -503,6 +503,7 @@ struct PrepArgs {
   int zero_f64_count;
   int32_t* status;
   int32_t* bss;  // [nbins][8] or nullptr: offset inside bucket b of its first atom of species >= s (buckets are species-sorted)
+  unsigned long long* trace;  // timing experiments (ANI_B200_PREP_TRACE=1): %globaltimer at the phase boundaries of k_prep_cluster
 };
 
 // per-bucket species offsets: bss[b][s] = atoms of bucket b with species < s (s = 0..7; bss[b][0] = 0).  With the
@@ -1137,6 +1138,14 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int gstride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + tid;
   const int n = A.n, S = A.S;
+  auto stamp = [&](int k) {
+    if (A.trace && gtid == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      A.trace[k] = t;
+    }
+  };
+  stamp(0);
   // ---- phase 0: the grid (every CTA its own copy) + zero-fill of the counters that are used below
   if (tid == 0) {
     const float none[3] = {0.f, 0.f, 0.f};
@@ -1144,6 +1153,7 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     if (blockIdx.x == 0) *A.grid = sg;
   }
   __syncthreads();
+  stamp(1);
   const int nbins = sg.nbins;
   {
     // bin_count[0 .. nbins] | counter | present | chunk_hist[(n_chunks + 1) * 8] are contiguous, but bin_count is
@@ -1153,6 +1163,7 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     for (int k = gtid; k < tail; k += gstride) A.counter[k] = 0;
   }
   prep_cluster_barrier();
+  stamp(2);
   // ---- phase 1: bucket of every atom, slot inside the bucket by atomics
   for (int a = gtid; a < n; a += gstride) {
     int bin;
@@ -1165,7 +1176,9 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     A.bin_of[a] = bin;
     A.slot[a] = atomicAdd(&A.bin_count[bin], 1);
   }
+  stamp(3);
   prep_cluster_barrier();
+  stamp(4);
   // ---- phase 1b: EVERY CTA scans the bucket counts (exclusive) into its shared-memory bin_start
   {
     const int m = nbins + 1;
@@ -1211,6 +1224,7 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     __syncthreads();
   }
   const int n_real = s_start[nbins];
+  stamp(5);
   // ---- phase 2: scatter into buckets + per-bucket table of the 27 neighbouring buckets
   {
     const int t2 = A.ranges ? max(n, nbins * 27) : n;
@@ -1254,7 +1268,9 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     if (A.zero_f64)
       for (int k = gtid; k < A.zero_f64_count; k += gstride) A.zero_f64[k] = 0.0;
   }
+  stamp(6);
   prep_cluster_barrier();
+  stamp(7);
   // ---- phase 3: one warp per bucket: deterministic (species, input index) order, sorted arrays, per-chunk
   //      species histogram, element presence mask, per-bucket species offsets
   {
@@ -1313,7 +1329,9 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     }
     if (lane == 0 && present) atomicOr(A.present, (int)present);
   }
+  stamp(8);
   prep_cluster_barrier();
+  stamp(9);
   // ---- phase 4: EVERY CTA: exclusive scan of the chunk histograms per species (shared memory), species row
   //      bases; CTA 0: layout words, tile table, live AEV column blocks
   {
@@ -1365,6 +1383,7 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
       if (w == 31) live_aev_blocks(A, (unsigned)__ldcg(A.present), lane);
     }
   }
+  stamp(10);
   // ---- phase 5: row assignment, four 256-atom chunks of the owned sorted slice per CTA pass (8 warps each)
   {
     const int hi_real = min(A.hi, n_real);
@@ -1391,6 +1410,7 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
       __syncthreads();
     }
   }
+  stamp(11);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1583,6 +1603,12 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   A.zero_f64 = zero_f64_count > 0 ? zero_f64 : nullptr; A.zero_f64_count = zero_f64_count;
   A.status = status;
   A.bss = bucket_species;
+  {  // timing experiments: 16 words behind species_base (the scratch area has 64 spare ints)
+    const char* te = getenv("ANI_B200_PREP_TRACE");
+    A.trace = (te && atoi(te) != 0)
+                  ? reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(A.species_base + ANI_MAX_SPECIES) + 7) & ~(uintptr_t)7)
+                  : nullptr;
+  }
   A.inline_setup = (mode == 1 || pbc) ? 1 : 0;
   const size_t zeroed = (size_t)(max_bins + 1) + 2 + (size_t)(A.n_chunks + 1) * ANI_MAX_SPECIES;
   if (!A.inline_setup)

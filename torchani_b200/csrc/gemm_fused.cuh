@@ -483,8 +483,9 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       const unsigned char* Bm =
           sp.Bt + (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (PARTS * ROW_BYTES));
       const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
-      const bool dense = tm.nb_count < 0;
-      const int n0p = tl.n0 / TN_MAX * TN_MAX, bnp = min(TN_MAX, sp.N - n0p);  // the packed B tile this one lies in
+      const bool dense = tm.nb_count < 0 || args.b_compact;
+      // the packed B tile this one lies in
+      const int n0p = tl.n0 / TN_MAX * TN_MAX, bnp = min(TN_MAX, (args.b_compact ? tm.n_eff[tl.s] : sp.N) - n0p);
       const int gq = lane / PARTS, gpart = lane % PARTS;
       size_t g_src = 0;
       int g_bns = 0;

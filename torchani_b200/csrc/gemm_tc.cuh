@@ -100,6 +100,9 @@ struct Args {
   float y_inv_scale;            // EPI_MUL_DCELU: 1 / scale of the stored activation that C overwrites
   int32_t* status;              // ANI_STATUS_OPERAND_RANGE is raised here (may be NULL)
   int allow_narrow;             // short tile lists may split every accumulator into two column tiles (not EPI_HEAD)
+  int b_compact;                // with `nblocks`: B holds ONLY the live column blocks, packed like a dense operand of
+                                // nb_count * 32 rows (mlp.cu: k_zero_live_blocks builds it every step) -- one bulk copy
+                                // per K-block instead of one 2 KB copy per live block and piece
   int debug;                    // timing experiments only (ANI_B200_GEMM_DEBUG): 2 no copies, 4 no MMA, 8 no epilogue
   float member_scale[ANI_MAX_MEMBERS];
   Species sp[ANI_MAX_SPECIES];
@@ -516,8 +519,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
           sp.Bt + (sp.b_kb_moff ? (size_t)0 : (size_t)tl.mem * sp.N * nkb_all * (PARTS * ROW_BYTES));
       // one piece of this CTA's B rows: all bn rows, or half of them in a CTA pair
       const uint32_t b_bytes = (uint32_t)(PAIR ? tl.bn / 2 : tl.bn) * ROW_BYTES;
-      const bool dense = tm.nb_count < 0;
-      const int n0p = tl.n0 / TN_MAX * TN_MAX, bnp = min(TN_MAX, sp.N - n0p);  // the packed B tile this one lies in
+      const bool dense = tm.nb_count < 0 || args.b_compact;
+      // the packed B tile this one lies in
+      const int n0p = tl.n0 / TN_MAX * TN_MAX, bnp = min(TN_MAX, (args.b_compact ? tm.n_eff[tl.s] : sp.N) - n0p);
       // gathered column blocks (layer-1 backward): lane -> (live block q, piece)
       const int gq = lane / PARTS, gpart = lane % PARTS;
       size_t g_src = 0;

@@ -75,19 +75,54 @@ __global__ void __launch_bounds__(256) k_reduce_energies(const __grid_constant__
   }
 }
 
-// zero the live 32-column blocks of the plain gradient matrix (the split-K layer-1 backward
-// accumulates into it; dead blocks are never read by the AEV backward kernel)
+// Per step, before the backward GEMMs:
+//  (a) zero the live 32-column blocks of the plain gradient matrix (the split-K layer-1 backward accumulates into it;
+//      dead blocks are never read by the AEV backward kernel);
+//  (b) gather the live column blocks of the layer-1 backward operand B = W1^T [ldx][M*h1] of every species that has
+//      rows into ani_mlp_model::b1_compact, packed exactly like a dense operand of (live blocks * 32) rows: the
+//      producer warp of the GEMM then moves one K-block of B with ONE bulk copy instead of one 2 KB copy per live
+//      block and piece (water: 10 per K-block, H C N O S: 40), which had made the layer-1 backward the one phase whose
+//      main loop was bound by the copy-issue rate.  2.6 MB per step for water; no state carried between steps.
+struct CompactArgs {
+  const unsigned char* src[ANI_MAX_SPECIES];
+  unsigned char* dst[ANI_MAX_SPECIES];   // nullptr: nothing to gather for this species
+  int nkb[ANI_MAX_SPECIES];              // K-blocks of the operand (M * h1 / 32)
+};
+
 __global__ void __launch_bounds__(256) k_zero_live_blocks(float* dx, int ldx, const int32_t* layout_info, int num_species,
-                                                          const int32_t* blocks) {
-  const int rows = layout_info[4 + num_species] * ANI_TILE_ROWS;
+                                                          const int32_t* blocks, const __grid_constant__ CompactArgs ca) {
   const int count = blocks ? blocks[0] : ldx / 32;  // no list: every block is live
-  const long long total = (long long)rows * count * 8;  // float4 stores
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i & 7);
-    const long long rb = i >> 3;
-    const int b = (int)(rb % count);
-    const long long row = rb / count;
-    *reinterpret_cast<float4*>(dx + row * ldx + (blocks ? blocks[1 + b] : b) * 32 + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dx) {
+    const int rows = layout_info[4 + num_species] * ANI_TILE_ROWS;
+    const long long total = (long long)rows * count * 8;  // float4 stores
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+      const int q = (int)(i & 7);
+      const long long rb = i >> 3;
+      const int b = (int)(rb % count);
+      const long long row = rb / count;
+      *reinterpret_cast<float4*>(dx + row * ldx + (blocks ? blocks[1 + b] : b) * 32 + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (!blocks) return;
+  // (b) one warp per 2 KB chunk = (live block q, K-block kb, piece): 32 rows x 64 B, contiguous on both sides
+  const int lane = threadIdx.x & 31;
+  const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_c = count * 32;
+  for (int s = 0; s < num_species; ++s) {
+    if (!ca.dst[s] || layout_info[4 + s + 1] <= layout_info[4 + s]) continue;
+    const int nkb = ca.nkb[s], per_q = nkb * OPND_PARTS;
+    for (int c = gwarp; c < count * per_q; c += nwarps) {
+      const int q = c / per_q, rem = c - q * per_q, kb = rem / OPND_PARTS, pc = rem - kb * OPND_PARTS;
+      const int row0 = blocks[1 + q] * 32, n0s = row0 / tc::TN_MAX * tc::TN_MAX, bns = min(tc::TN_MAX, ldx - n0s);
+      const int cr0 = q * 32, n0c = cr0 / tc::TN_MAX * tc::TN_MAX, bnc = min(tc::TN_MAX, n_c - n0c);
+      const unsigned char* src = ca.src[s] + ((size_t)n0s * nkb + (size_t)kb * bns) * (OPND_PARTS * OPND_ROW_BYTES) +
+                                 (size_t)pc * bns * OPND_ROW_BYTES + (size_t)(row0 - n0s) * OPND_ROW_BYTES;
+      unsigned char* dst = ca.dst[s] + ((size_t)n0c * nkb + (size_t)kb * bnc) * (OPND_PARTS * OPND_ROW_BYTES) +
+                           (size_t)pc * bnc * OPND_ROW_BYTES + (size_t)(cr0 - n0c) * OPND_ROW_BYTES;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<uint4*>(dst)[j * 32 + lane] = __ldg(reinterpret_cast<const uint4*>(src) + j * 32 + lane);
+    }
   }
 }
 
@@ -262,6 +297,7 @@ static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* r
     return !e || atoi(e) != 0;
   }();
   ta.allow_narrow = narrow;
+  ta.b_compact = 0;
   ta.out_scale = OPND_SCALE_VALUE;
   ta.y_inv_scale = 1.0f / OPND_SCALE_VALUE;
   return ANI_OK;
@@ -285,6 +321,36 @@ static int l1b_group(int M, int rows_cap) {
 // operand scales (common.cuh): activations / AEVs carry sv, gradients sg, weights their per-tensor
 // w_scale; every GEMM divides the product of its two operand scales out of the accumulator
 static inline float wsc(const ani_mlp_species& p, int layer) { return ANI_OPND_FP16X2 ? p.w_scale[layer] : 1.0f; }
+
+// compacted layer-1 backward operands (k_zero_live_blocks (b)): species s starts where the full operands of the species
+// before it would end -- ani_mlp_model::b1_compact holds sum_s ldx * (M h1_s / 32) * P * 64 bytes
+static bool use_b1_compact(const ani_mlp_model* model, const int32_t* aev_blocks) {
+  static const bool on = []() {
+    const char* e = getenv("ANI_B200_B1_COMPACT");  // 0: gather the live blocks with 2 KB copies inside the GEMM
+    return !e || atoi(e) != 0;
+  }();
+  return on && model->b1_compact && aev_blocks;
+}
+static unsigned char* b1_compact_ptr(const ani_mlp_model* model, int s) {
+  size_t off = 0;
+  for (int t = 0; t < s; ++t)
+    off += (size_t)model->ldx * (size_t)(model->num_members * model->sp[t].h1 / 32) * (OPND_PARTS * OPND_ROW_BYTES);
+  return static_cast<unsigned char*>(model->b1_compact) + off;
+}
+// zero-fill of dE/dAEV (dx may be NULL: nothing to zero) + gather of the compact operands
+static void launch_zero_compact(const ani_mlp_model* model, float* dx, const int32_t* layout_info, const int32_t* aev_blocks,
+                                cudaStream_t st) {
+  CompactArgs ca;
+  const bool compact = use_b1_compact(model, aev_blocks);
+  for (int s = 0; s < ANI_MAX_SPECIES; ++s) {
+    const bool live = compact && s < model->num_species;
+    ca.src[s] = live ? static_cast<const unsigned char*>(model->sp[s].t_b1) : nullptr;
+    ca.dst[s] = live ? b1_compact_ptr(model, s) : nullptr;
+    ca.nkb[s] = live ? model->num_members * model->sp[s].h1 / 32 : 0;
+  }
+  if (!dx && !compact) return;
+  k_zero_live_blocks<<<592, 256, 0, st>>>(dx, model->ldx, layout_info, model->num_species, aev_blocks, ca);
+}
 
 extern "C" int ani_b200_mlp_forward(const ani_mlp_model* model, const void* x, int rows_cap, const int32_t* row_atom,
                                     const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2,
@@ -335,7 +401,7 @@ extern "C" int ani_b200_mlp_forward(const ani_mlp_model* model, const void* x, i
 extern "C" int ani_b200_zero_live_blocks(const ani_mlp_model* model, float* dx, const int32_t* layout_info,
                                          const int32_t* aev_blocks, void* stream) {
   if (!model || !dx || !layout_info) return ANI_ERR_BAD_ARG;
-  k_zero_live_blocks<<<592, 256, 0, (cudaStream_t)stream>>>(dx, model->ldx, layout_info, model->num_species, aev_blocks);
+  launch_zero_compact(model, dx, layout_info, aev_blocks, (cudaStream_t)stream);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }
@@ -381,7 +447,12 @@ extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int 
   }
   ta.nblocks = aev_blocks;  // ... and nobody reads the gradient of a dead column block
   ta.c_accumulate = M / G > 1;
-  if (ta.c_accumulate && !dx_zeroed) k_zero_live_blocks<<<592, 256, 0, st>>>(dx, ldx, layout_info, S, aev_blocks);
+  if (use_b1_compact(model, aev_blocks)) {
+    ta.b_compact = 1;
+    for (int s = 0; s < S; ++s) ta.sp[s].Bt = b1_compact_ptr(model, s);
+  }
+  // (ani_b200_zero_live_blocks, if the caller ran it for this step, has also gathered the compact operands)
+  if (!dx_zeroed) launch_zero_compact(model, ta.c_accumulate ? dx : nullptr, layout_info, aev_blocks, st);
   launch_gemm_tc<tc::EPI_PLAIN>(ta, st, true);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
@@ -448,6 +519,10 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
             ta.members = M / (want_backward == 2 ? 1 : l1b_group(M, rows_cap)); ta.nblocks = aev_blocks;
             ta.c_accumulate = ta.members > 1; ta.out_scale = sg; break;
   }
+  if (phase == 5 && use_b1_compact(model, aev_blocks)) {
+    ta.b_compact = 1;
+    for (int s = 0; s < S; ++s) ta.sp[s].Bt = b1_compact_ptr(model, s);
+  }
   if (phase == 5 && want_backward == 2) {
     // per-member dE_m/dAEV: member m writes its own [rows_cap][ldx] slab of dx (plain stores, no accumulation)
     ta.c_accumulate = 0;
@@ -483,8 +558,7 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
   F.sync = sync_i32;
   F.sync_stride = rows_cap / ANI_TILE_ROWS;
   cudaMemsetAsync(sync_i32, 0, sizeof(int32_t) * (size_t)tc::MAX_PHASES * F.sync_stride, st);
-  if (want_backward == 1 && M > 1)
-    k_zero_live_blocks<<<592, 256, 0, st>>>(dx, model->ldx, layout_info, model->num_species, aev_blocks);
+  if (want_backward) launch_zero_compact(model, (want_backward == 1 && M > 1) ? dx : nullptr, layout_info, aev_blocks, st);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;

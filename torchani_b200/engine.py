@@ -319,7 +319,12 @@ class PackedNetworks:
                 for name, off in (("t_f1", q["d_f1"]), ("t_f2", q["d_f2"]), ("t_f3", q["d_f3"]), ("t_b3", q["d_b3"]),
                                   ("t_b2", q["d_b2"]), ("t_b1", q["d_b1"])):
                     setattr(spm, name, dp0 + off)
-        self._keep = [src, dst]
+        # scratch of the per-step compaction of the layer-1 backward operands (live AEV column blocks only; as large
+        # as those operands together; ani_mlp_model::b1_compact)
+        b1c = torch.empty(sum(self.ldx * (M * q["p"][0] // 32) * 32 * P2 for q in plan), dtype=torch.uint8,
+                          device=self.device)
+        mdl.b1_compact = b1c.data_ptr()
+        self._keep = [src, dst, b1c]
         self._plan = plan
         mdl.h1_max = max(q["p"][0] for q in plan)
         mdl.h2_max = max(q["p"][1] for q in plan)
