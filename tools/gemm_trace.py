@@ -36,8 +36,28 @@ def main():
     eng.step(sp_d, co_d, ce_d, True, True)
     torch.cuda.synchronize()
     _lib.lib().ani_b200_debug_gemm_trace(None, 0)
-    t = buf.view(launches, 4, 8, 3, 4).cpu()
     names = ["fwd1", "fwd2", "fwd3+head", "bwd3", "bwd2", "bwd1"]
+    if eng.mlp_fused:
+        # one data-flow launch (csrc/gemm_fused.cuh): [cta 4][unit 32][role: producer, MMA, epilogue, info][4]
+        t = buf[:4 * 32 * 16].view(4, 32, 4, 4).cpu()
+        for cta in (0, 3):
+            x = t[cta]
+            nz = x[:, :3][x[:, :3] > 0]
+            if nz.numel() == 0:
+                continue
+            t0 = int(nz.min())
+            us = lambda v: (int(v) - t0) / mhz if int(v) > 0 else float("nan")  # noqa: E731
+            print(f"== data-flow launch, cta {cta}: span {(int(nz.max()) - t0) / mhz:.1f} us")
+            for u in range(32):
+                if int(x[u, :3].max()) == 0:
+                    break
+                p, m, e, info = x[u, 0], x[u, 1], x[u, 2], x[u, 3]
+                print(f"  unit {u:2d} {names[int(info[0])]:9s} rt {int(info[1]):3d} m {int(info[2])} bn {int(info[3]):3d}: "
+                      f"prod start {us(p[0]):6.1f} dep-ok {us(p[1]):6.1f} first {us(p[2]):6.1f} done {us(p[3]):6.1f} | "
+                      f"mma begin {us(m[0]):6.1f} acc-free {us(m[1]):6.1f} data {us(m[2]):6.1f} issued {us(m[3]):6.1f} | "
+                      f"epi begin {us(e[0]):6.1f} start {us(e[1]):6.1f} done {us(e[2]):6.1f} flushed {us(e[3]):6.1f}")
+        return
+    t = buf.view(launches, 4, 8, 3, 4).cpu()
     for la in range(launches):
         for cta in (0, 3):
             x = t[la, cta]

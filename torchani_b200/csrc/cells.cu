@@ -248,10 +248,16 @@ __global__ void k_bin_finalize(const float* __restrict__ coords, const int32_t* 
   // every bucket being species-sorted)
   const int spa = species[a];
   int rank = 0;
-  for (int e = lo; e < hi; ++e) {
-    const int t = tmp_list[e];
-    const int spt = species[t];
-    rank += (spt < spa) || (spt == spa && t < a);
+  if (spa < 0) {
+    // trash bucket (padding atoms of a conformer batch, possibly thousands): all of one "species", so the rank is
+    // the number of smaller indices -- independent loads, no dependent species gather per entry
+    for (int e = lo; e < hi; ++e) rank += tmp_list[e] < a;
+  } else {
+    for (int e = lo; e < hi; ++e) {
+      const int t = tmp_list[e];
+      const int spt = species[t];
+      rank += (spt < spa) || (spt == spa && t < a);
+    }
   }
   int i = lo + rank;
   sorted_orig[i] = a;
@@ -649,10 +655,16 @@ __global__ void __launch_bounds__(256) k_prep_finalize(const __grid_constant__ P
     // rank by (species, input index): deterministic order, every bucket species-sorted
     const int spa = A.species[a];
     int rank = 0;
-    for (int e = lo; e < hi; ++e) {
-      const int t = A.tmp_list[e];
-      const int spt = A.species[t];
-      rank += (spt < spa) || (spt == spa && t < a);
+    if (spa < 0) {
+      // padding atoms (trash bucket) are never neighbours nor centres: any order will do -- their arrival slot,
+      // instead of ranking thousands of padded entries of a conformer batch against each other
+      rank = A.slot[a];
+    } else {
+      for (int e = lo; e < hi; ++e) {
+        const int t = A.tmp_list[e];
+        const int spt = A.species[t];
+        rank += (spt < spa) || (spt == spa && t < a);
+      }
     }
     i = lo + rank;
     A.sorted_orig[i] = a;
@@ -927,10 +939,14 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
         const int lo = __ldcg(&A.bin_start[b]), hi = __ldcg(&A.bin_start[b + 1]);
         const int spa = A.species[a];
         int rank = 0;
-        for (int e = lo; e < hi; ++e) {
-          const int t = __ldcg(&A.tmp_list[e]);
-          const int spt = A.species[t];
-          rank += (spt < spa) || (spt == spa && t < a);
+        if (spa < 0) {
+          rank = A.slot[a];   // padding atoms: arrival order (see k_prep_finalize)
+        } else {
+          for (int e = lo; e < hi; ++e) {
+            const int t = __ldcg(&A.tmp_list[e]);
+            const int spt = A.species[t];
+            rank += (spt < spa) || (spt == spa && t < a);
+          }
         }
         const int i = lo + rank;
         A.sorted_orig[i] = a;
@@ -1085,8 +1101,10 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
 constexpr int PREP_CLUSTER_CTAS = 8;
 constexpr int PREP_CLUSTER_THREADS = 1024;
 constexpr int PREP_CLUSTER_MAX_ATOMS = 16384;
-constexpr int PREP_CLUSTER_MAX_BINS = 6144;     // shared-memory copy of bin_start (+ 2 words)
+constexpr int PREP_CLUSTER_MAX_BINS = PREP_CLUSTER_MAX_ATOMS + 1;   // max_bins - 1 = n + 1 buckets at most: the
+                                                                    // shared-memory copy of bin_start is dynamic
 constexpr int PREP_CLUSTER_MAX_CHUNKS = PREP_CLUSTER_MAX_ATOMS / LAYOUT_CHUNK;
+constexpr int MAX_AEV_BLOCKS = 64;   // ldx / 32 (gemm_tc.cuh: MAX_BLOCKS)
 
 __device__ __forceinline__ void prep_cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -1127,8 +1145,9 @@ __device__ __forceinline__ void live_aev_blocks(const PrepArgs& A, unsigned mask
 
 __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP_CLUSTER_THREADS, 1)
     k_prep_cluster(const __grid_constant__ PrepArgs A) {
+  extern __shared__ int s_start[];   // [nbins + 2]: this CTA's copy of bin_start
   __shared__ ani_grid sg;
-  __shared__ int s_start[PREP_CLUSTER_MAX_BINS + 2];
+  __shared__ int s_live[MAX_AEV_BLOCKS];
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   __shared__ int s_hist[PREP_CLUSTER_MAX_CHUNKS * ANI_MAX_SPECIES];   // exclusive scan over the chunks, per species
@@ -1288,7 +1307,8 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
         const int a = valid ? __ldcg(&A.tmp_list[e]) : 0x7fffffff;
         const int spa = valid ? A.species[a] : 0x7fff;
         int rank = 0;
-        for (int base2 = lo; base2 < hi; base2 += 32) {
+        if (b == nbins) rank = valid ? A.slot[a] : 0;   // padding atoms: arrival order (see k_prep_finalize)
+        for (int base2 = lo; base2 < hi && b < nbins; base2 += 32) {
           int t = a, spt = spa;
           if (base2 != base) {
             const int e2 = base2 + lane;
@@ -1380,7 +1400,44 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
           if (r >= s_base[s] && r < s_base[s + 1] && r < s_base[s] + s_tot[s]) sp = s;
         A.tile_species[t] = sp;
       }
-      if (w == 31) live_aev_blocks(A, (unsigned)__ldcg(A.present), lane);
+      // live 32-column AEV blocks: warp w tests the 32 columns of block w (+32, ...) -- one column per lane -- instead
+      // of one lane walking a whole block (the serial walk was 5 us of this kernel's critical path)
+      const unsigned mask = (unsigned)__ldcg(A.present);
+      const int RL = S * A.n_shf_r, nblk = A.ldx / 32;
+      for (int b = w; b < nblk; b += PREP_CLUSTER_THREADS / 32) {
+        const int c = b * 32 + lane;
+        bool active = false;
+        if (c < A.out_dim) {
+          if (c < RL) {
+            active = (mask >> (c / A.n_shf_r)) & 1u;
+          } else {
+            int s1 = 0, rem = (c - RL) / A.angular_sub;
+            while (rem >= S - s1) {
+              rem -= S - s1;
+              ++s1;
+            }
+            active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
+          }
+        }
+        const bool live = __any_sync(ANI_FULL_MASK, active);
+        if (lane == 0) s_live[b] = live;
+      }
+      __syncthreads();
+      if (w == 0) {
+        int count = 0;
+        for (int b0 = 0; b0 < nblk; b0 += 32) {
+          const int b = b0 + lane;
+          const bool live = b < nblk && s_live[b];
+          const unsigned m = __ballot_sync(ANI_FULL_MASK, live);
+          if (live) A.blocks[1 + count + __popc(m & ((1u << lane) - 1u))] = b;
+          count += __popc(m);
+        }
+        if (lane == 0) {
+          A.blocks[0] = count;
+          A.blocks[nblk + 2] = (A.blocks[nblk + 1] != (int)mask);
+          A.blocks[nblk + 1] = (int)mask;
+        }
+      }
     }
   }
   stamp(10);
@@ -1628,9 +1685,16 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   // periodic single systems of MD size: one thread-block cluster (ANI_B200_PREP_CLUSTER=0: never)
   const char* ce = getenv("ANI_B200_PREP_CLUSTER");
   const bool cluster_ok = (!ce || atoi(ce) != 0) && fused && A.inline_setup && mode == 0 &&
-                          n <= PREP_CLUSTER_MAX_ATOMS && min(max_bins - 1, n + 1) <= PREP_CLUSTER_MAX_BINS;
+                          n <= PREP_CLUSTER_MAX_ATOMS && A.ldx / 32 <= MAX_AEV_BLOCKS;
   if (cluster_ok) {
-    k_prep_cluster<<<PREP_CLUSTER_CTAS, PREP_CLUSTER_THREADS, 0, st>>>(A);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_prep_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)sizeof(int32_t) * (PREP_CLUSTER_MAX_BINS + 2));
+      attr_set = true;
+    }
+    const size_t dyn = sizeof(int32_t) * (size_t)(min(max_bins - 1, n + 1) + 2);
+    k_prep_cluster<<<PREP_CLUSTER_CTAS, PREP_CLUSTER_THREADS, dyn, st>>>(A);
   } else if (fused) {
     // one persistent launch, device-wide barriers between the phases; every block must be resident:
     // 2 blocks of 256 threads per SM at most (the kernel allows far more)

@@ -36,6 +36,7 @@ namespace tc {
 constexpr int MAX_PHASES = 6;
 constexpr int FUSED_SMEM_BYTES = 227 * 1024 - 12 * 1024;  // 12 KB left for the static part (six tile maps, staging)
 constexpr long long FUSED_SPIN_LIMIT = 6000000000LL;      // ~3 s of clock64 ticks
+constexpr int FTRACE_UNITS = 32;                          // units per CTA the role timeline records
 
 struct FusedArgs {
   int n_phases;
@@ -44,6 +45,7 @@ struct FusedArgs {
   int32_t* sync;          // [MAX_PHASES][sync_stride] arrivals per (phase, row tile); zeroed by the launcher
   int sync_stride;
   int prefetch_b;         // issue the weight copies of a unit's first K-blocks before waiting for its inputs
+  long long* trace;       // optional clock64 stamps [cta < 4][unit < FTRACE_UNITS][role 4][4] (ani_b200_debug_gemm_trace)
   Args ph[MAX_PHASES];
 };
 
@@ -447,6 +449,11 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
   const int EPI_BUFS = s_epi_bufs;
   unsigned char* epi_stage = smem + AVAIL - EPI_BUFS * EPI_SETS * EPI_STAGE_BYTES;
   const int total_units = phase_base[NP];
+  // timing experiments: role 0 producer, 1 MMA, 2 epilogue (clock64 stamps), 3 = what the unit is
+  auto stamp = [&](int kloc, int role, int slot, long long v = -1) {
+    if (F.trace && blockIdx.x < 4 && kloc < FTRACE_UNITS)
+      F.trace[(((size_t)blockIdx.x * FTRACE_UNITS + kloc) * 4 + role) * 4 + slot] = v >= 0 ? v : clock64();
+  };
   auto find_phase = [&](int g) {
     int p = 0;
     while (g >= phase_base[p + 1]) ++p;
@@ -461,7 +468,10 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
     int cur_phase = -1, STAGES = 1, STAGE_BYTES = 0;
     int ahead = 0;   // counter of the NEXT unit's inputs, read (relaxed) while this unit's copies are issued
     bool ahead_valid = false;
+    int kloc = -1;
     for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+      ++kloc;
+      if (lane == 0) stamp(kloc, 0, 0);
       const int p = find_phase(g);
       const Args& args = F.ph[p];
       const TileMap& tm = tms[p];
@@ -563,6 +573,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
         stage = (stage + pre) % (uint32_t)STAGES;
         kb_first = pre;
       }
+      if (lane == 0) stamp(kloc, 0, 1);
       // look ahead: the counter the next unit of this CTA will wait on
       ahead_valid = false;
       {
@@ -581,14 +592,19 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
         load_a(stage, kb);
         load_b(stage, kb);
         __syncwarp();
+        if (lane == 0 && kb == kb_first) stamp(kloc, 0, 2);
         if (++stage == (uint32_t)STAGES) stage = 0;
       }
+      if (lane == 0) stamp(kloc, 0, 3);
     }
   } else if (warp == F_MMA_WARP) {
     // ================================ MMA issuer ================================
     uint32_t stage = 0, full_par = 0u, acc = 0, acc_phase = 0;
     int cur_phase = -1, STAGES = 1, STAGE_BYTES = 0;
+    int kloc = -1;
     for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+      ++kloc;
+      if (lane == 0) stamp(kloc, 1, 0);
       const int p = find_phase(g);
       const Args& args = F.ph[p];
       const TileMap& tm = tms[p];
@@ -604,11 +620,13 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       const uint32_t b_bytes = (uint32_t)tl.bn * ROW_BYTES;
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
+      if (lane == 0) stamp(kloc, 1, 1);
       const uint32_t d_tmem = tmem_base + acc * TN_MAX;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[stage], (full_par >> stage) & 1u);
         full_par ^= 1u << stage;
         tc_fence_after();
+        if (lane == 0 && kb == 0) stamp(kloc, 1, 2);
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BLOCK_BYTES;
@@ -634,7 +652,10 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
 #endif
           }
           umma_commit(&empty[stage]);
-          if (kb == nkb - 1) umma_commit(&tfull[acc]);
+          if (kb == nkb - 1) {
+            umma_commit(&tfull[acc]);
+            stamp(kloc, 1, 3);
+          }
         }
         __syncwarp();
         if (++stage == (uint32_t)STAGES) stage = 0;
@@ -699,13 +720,22 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       __syncwarp();
       pending = false;
     };
+    int kloc = -1;
     for (int g = blockIdx.x; g < total_units; g += gridDim.x) {
+      ++kloc;
       const int p = find_phase(g);
       const Args& args = F.ph[p];
       const TileMap& tm = tms[p];
       const int epi = F.epi[p];
       const Tile tl = decode_tile(args, tm, g - phase_base[p]);
       const Species& sp = args.sp[tl.s];
+      if (threadIdx.x == 0) {
+        stamp(kloc, 2, 0);
+        stamp(kloc, 3, 0, p);
+        stamp(kloc, 3, 1, tl.rt);
+        stamp(kloc, 3, 2, tl.mem);
+        stamp(kloc, 3, 3, tl.bn);
+      }
       if (epi == EPI_BIAS_CELU || epi == EPI_HEAD) {
         const int c = threadIdx.x;
         if (c < tl.bn) {
@@ -740,6 +770,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       // synchronisation is a causality chain; the lines have not been in this SM's L1 before.)
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
       int groups = 0;
+      if (threadIdx.x == 0) stamp(kloc, 2, 1);
       switch (epi) {
         case EPI_BIAS_CELU:
           if (NW == 16)
@@ -778,12 +809,14 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (threadIdx.x == 0) stamp(kloc, 2, 2);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
       // the previous unit's stores were committed a whole tile ago: complete it, then this unit becomes pending
       flush_pending(groups);   // (a tile has at most 8 column groups: 4 per warp)
+      if (threadIdx.x == 0) stamp(kloc, 2, 3);
       pending = true;
       pend_groups = groups;
       pend_phase = p;

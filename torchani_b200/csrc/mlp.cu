@@ -555,6 +555,12 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     return e && atoi(e) != 0;                       // (measured on B200: no gain at 1k atoms, -4 % at 10k: off)
   }();
   F.prefetch_b = prefetch_b;
+  // role timeline of the first CTAs (tools/gemm_trace.py): needs the whole six-launch buffer
+  F.trace = nullptr;
+  if (g_trace && g_trace_next == 0 && (size_t)g_trace_launches * TRACE_WORDS_PER_LAUNCH >= (size_t)4 * tc::FTRACE_UNITS * 16) {
+    F.trace = g_trace;
+    g_trace_next = g_trace_launches;
+  }
   F.sync = sync_i32;
   F.sync_stride = rows_cap / ANI_TILE_ROWS;
   cudaMemsetAsync(sync_i32, 0, sizeof(int32_t) * (size_t)tc::MAX_PHASES * F.sync_stride, st);
