@@ -1098,7 +1098,7 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
 // Used for periodic single systems up to PREP_CLUSTER_MAX_ATOMS atoms and PREP_CLUSTER_MAX_BINS buckets;
 // larger problems have enough work per phase for the whole device and keep the persistent-grid kernel.
 // ---------------------------------------------------------------------------------------
-constexpr int PREP_CLUSTER_CTAS = 8;
+constexpr int PREP_CLUSTER_CTAS = 8;          // portable cluster size; 16 (opt-in) where the device can place it
 constexpr int PREP_CLUSTER_THREADS = 1024;
 constexpr int PREP_CLUSTER_MAX_ATOMS = 16384;
 constexpr int PREP_CLUSTER_MAX_BINS = PREP_CLUSTER_MAX_ATOMS + 1;   // max_bins - 1 = n + 1 buckets at most: the
@@ -1143,7 +1143,7 @@ __device__ __forceinline__ void live_aev_blocks(const PrepArgs& A, unsigned mask
   }
 }
 
-__global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP_CLUSTER_THREADS, 1)
+__global__ void __launch_bounds__(PREP_CLUSTER_THREADS, 1)
     k_prep_cluster(const __grid_constant__ PrepArgs A) {
   extern __shared__ int s_start[];   // [nbins + 2]: this CTA's copy of bin_start
   __shared__ ani_grid sg;
@@ -1195,6 +1195,13 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     A.bin_of[a] = bin;
     A.slot[a] = atomicAdd(&A.bin_count[bin], 1);
   }
+  // (independent of everything else, in the shadow of the atomics' round trip) the force accumulator, the row table and
+  // the conformer energies start from zero / -1; the row table is written again two cluster barriers further down
+  if (A.zero_f32)
+    for (int k = gtid; k < A.zero_f32_count; k += gstride) A.zero_f32[k] = 0.f;
+  for (int r = gtid; r < A.rows_cap; r += gstride) A.row_atom[r] = -1;
+  if (A.zero_f64)
+    for (int k = gtid; k < A.zero_f64_count; k += gstride) A.zero_f64[k] = 0.0;
   stamp(3);
   prep_cluster_barrier();
   stamp(4);
@@ -1280,12 +1287,6 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
                                                   wx * sg.cell[1] + wy * sg.cell[4] + wz * sg.cell[7],
                                                   wx * sg.cell[2] + wy * sg.cell[5] + wz * sg.cell[8], 0.f);
     }
-    // (independent of everything above) force accumulator, row table and conformer energies start from zero / -1
-    if (A.zero_f32)
-      for (int k = gtid; k < A.zero_f32_count; k += gstride) A.zero_f32[k] = 0.f;
-    for (int r = gtid; r < A.rows_cap; r += gstride) A.row_atom[r] = -1;
-    if (A.zero_f64)
-      for (int k = gtid; k < A.zero_f64_count; k += gstride) A.zero_f64[k] = 0.0;
   }
   stamp(6);
   prep_cluster_barrier();
@@ -1296,16 +1297,27 @@ __global__ void __cluster_dims__(PREP_CLUSTER_CTAS, 1, 1) __launch_bounds__(PREP
     const int hi_real = min(A.hi, n_real);
     const int nwarps = gstride >> 5;
     unsigned present = 0;
-    for (int b = gtid >> 5; b <= nbins; b += nwarps) {
+    // (the first 32 members of the warp's NEXT bucket are loaded before the current one is ranked: the two dependent
+    // loads per bucket overlap the shuffles of the previous one)
+    auto load_members = [&](int base, int hi, int& a, int& spa) {
+      const int e = base + lane;
+      a = e < hi ? __ldcg(&A.tmp_list[e]) : 0x7fffffff;
+      spa = e < hi ? A.species[a] : 0x7fff;
+    };
+    int b = gtid >> 5, pre_a = 0x7fffffff, pre_sp = 0x7fff;
+    if (b <= nbins) load_members(s_start[b], s_start[b + 1], pre_a, pre_sp);
+    for (; b <= nbins; b += nwarps) {
       const int lo = s_start[b], hi = s_start[b + 1];
+      const int first_a = pre_a, first_sp = pre_sp;
+      if (b + nwarps <= nbins) load_members(s_start[b + nwarps], s_start[b + nwarps + 1], pre_a, pre_sp);
       int below[ANI_MAX_SPECIES];   // members with species < k (lane-uniform)
 #pragma unroll
       for (int k = 0; k < ANI_MAX_SPECIES; ++k) below[k] = 0;
       for (int base = lo; base < hi; base += 32) {
         const int e = base + lane;
         const bool valid = e < hi;
-        const int a = valid ? __ldcg(&A.tmp_list[e]) : 0x7fffffff;
-        const int spa = valid ? A.species[a] : 0x7fff;
+        int a = first_a, spa = first_sp;
+        if (base != lo) load_members(base, hi, a, spa);
         int rank = 0;
         if (b == nbins) rank = valid ? A.slot[a] : 0;   // padding atoms: arrival order (see k_prep_finalize)
         for (int base2 = lo; base2 < hi && b < nbins; base2 += 32) {
@@ -1687,14 +1699,40 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   const bool cluster_ok = (!ce || atoi(ce) != 0) && fused && A.inline_setup && mode == 0 &&
                           n <= PREP_CLUSTER_MAX_ATOMS && A.ldx / 32 <= MAX_AEV_BLOCKS;
   if (cluster_ok) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    const size_t dyn = sizeof(int32_t) * (size_t)(min(max_bins - 1, n + 1) + 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(PREP_CLUSTER_THREADS);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // cluster size: 16 CTAs (non-portable, opt-in) if the device can co-schedule them with the largest shared-memory
+    // request, else the portable 8; ANI_B200_PREP_CLUSTER_CTAS pins it
+    static int cluster_ctas = 0;
+    if (cluster_ctas == 0) {
       cudaFuncSetAttribute(k_prep_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)sizeof(int32_t) * (PREP_CLUSTER_MAX_BINS + 2));
-      attr_set = true;
+      cluster_ctas = PREP_CLUSTER_CTAS;
+      const char* pe = getenv("ANI_B200_PREP_CLUSTER_CTAS");
+      const int want = pe ? atoi(pe) : 16;
+      if (want == 16 &&
+          cudaFuncSetAttribute(k_prep_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t probe = cfg;
+        probe.gridDim = dim3(16);
+        probe.dynamicSmemBytes = sizeof(int32_t) * (PREP_CLUSTER_MAX_BINS + 2);
+        attr[0].val.clusterDim.x = 16;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, k_prep_cluster, &probe) == cudaSuccess && nclusters >= 1)
+          cluster_ctas = 16;
+      }
+      cudaGetLastError();   // a refused probe is not an error of this call
     }
-    const size_t dyn = sizeof(int32_t) * (size_t)(min(max_bins - 1, n + 1) + 2);
-    k_prep_cluster<<<PREP_CLUSTER_CTAS, PREP_CLUSTER_THREADS, dyn, st>>>(A);
+    cfg.gridDim = dim3(cluster_ctas);
+    attr[0].val.clusterDim.x = cluster_ctas;
+    cudaLaunchKernelEx(&cfg, k_prep_cluster, A);
   } else if (fused) {
     // one persistent launch, device-wide barriers between the phases; every block must be resident:
     // 2 blocks of 256 threads per SM at most (the kernel allows far more)

@@ -100,6 +100,7 @@ struct Args {
   float y_inv_scale;            // EPI_MUL_DCELU: 1 / scale of the stored activation that C overwrites
   int32_t* status;              // ANI_STATUS_OPERAND_RANGE is raised here (may be NULL)
   int allow_narrow;             // short tile lists may split every accumulator into two column tiles (not EPI_HEAD)
+  int epi_direct;               // tiled outputs straight from registers (gemm_epilogue.cuh); 0: shared-memory staging + TMA stores
   int b_compact;                // with `nblocks`: B holds ONLY the live column blocks, packed like a dense operand of
                                 // nb_count * 32 rows (mlp.cu: k_zero_live_blocks builds it every step) -- one bulk copy
                                 // per K-block instead of one 2 KB copy per live block and piece
@@ -364,7 +365,7 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool 
   tm.stage_bytes = A_BLOCK_BYTES + PARTS * (pair ? bn_max / 2 : bn_max) * ROW_BYTES;  // a pair member holds half of B
   // two store-staging buffers per epilogue warp if that still leaves a double-buffered main loop
   const int avail = SMEM_BYTES - 1024;
-  tm.epi_bufs = (avail - 2 * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes >= 2 ? 2 : 1;
+  tm.epi_bufs = a.epi_direct ? 0 : (avail - 2 * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes >= 2 ? 2 : 1;
   // (a single store buffer per warp would buy one more main-loop stage: measured on B200, no gain --
   // 0.2374 vs 0.2358 ms for the six launches)
   tm.stages = min(MAX_STAGES, (avail - tm.epi_bufs * NUM_EPI_WARPS * EPI_STAGE_BYTES) / tm.stage_bytes);
@@ -428,6 +429,12 @@ __device__ __forceinline__ void join_chunk(const uint4* q, float* y) {
     y[2 * i + 1] = hi;
   }
 }
+
+template <int EPI>
+__device__ __forceinline__ void tile_epilogue_direct(const Args& args, const Tile& tl, int rt_mine, const Species& sp,
+                                                     uint32_t taddr, const float* __restrict__ bias,
+                                                     const float* __restrict__ w4, float* e_part, int warp, int lane,
+                                                     uint64_t* tfull_bar, uint32_t tfull_parity, float& omax, bool y_early);
 
 // ---- the kernel -----------------------------------------------------------------------------
 template <int EPI, bool PAIR = false>
@@ -711,12 +718,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(const __grid_constant__ 
       if (EPI == EPI_BIAS_CELU || EPI == EPI_HEAD) {
         const int c = threadIdx.x;  // 256 epilogue threads == TN_MAX columns
         if (c < tl.bn) {
-          s_bias[acc][c] = sp.bias[(size_t)tl.mem * sp.bias_mstride + tl.n0 + c];
+          // (the register-direct epilogue folds the output scale into the staged bias)
+          s_bias[acc][c] = sp.bias[(size_t)tl.mem * sp.bias_mstride + tl.n0 + c] *
+                           (args.epi_direct && EPI == EPI_BIAS_CELU ? args.out_scale : 1.0f);
           if (EPI == EPI_HEAD) s_w4[acc][c] = sp.w4[(size_t)tl.mem * sp.N + c];
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");  // epilogue warps only
       }
-      if (valid) {
+      if (EPI != EPI_PLAIN && args.epi_direct && valid && !(args.debug & 8)) {
+        if (threadIdx.x == 0) stamp(tloc, 2, 1);
+        tile_epilogue_direct<EPI == EPI_PLAIN ? EPI_BIAS_CELU : EPI>(
+            args, tl, rt_mine, sp, tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX, bias, w4, e_part, warp, lane,
+            &tfull[acc], acc_phase, omax, true);
+      } else if (valid) {
       const int my_row = rt_mine * TM + r_tile;
       float e_acc = 0.f, seed = 0.f;
       bool row_valid = false;

@@ -298,6 +298,11 @@ static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* r
   }();
   ta.allow_narrow = narrow;
   ta.b_compact = 0;
+  static const int epi_direct = []() {
+    const char* e = getenv("ANI_B200_EPI_DIRECT");  // 0: shared-memory staging + TMA bulk stores (round 1 / early round 2)
+    return !e || atoi(e) != 0;
+  }();
+  ta.epi_direct = epi_direct;
   ta.out_scale = OPND_SCALE_VALUE;
   ta.y_inv_scale = 1.0f / OPND_SCALE_VALUE;
   return ANI_OK;
@@ -530,6 +535,14 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
   }
 }
 
+static int epi_warps_env() {
+  static const int v = []() {
+    const char* e = getenv("ANI_B200_EPI_WARPS");  // 8 (default) or 16: epilogue warps of the fused kernel
+    return e && atoi(e) == 16 ? 16 : 8;
+  }();
+  return v;
+}
+
 extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, float* dx, int rows_cap,
                                  const int32_t* row_atom, const int32_t* layout_info, const int32_t* aev_blocks,
                                  void* act1, void* act2, void* act3, float* e_member, int want_backward,
@@ -549,12 +562,14 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     F.dep[p] = p - 1;
     F.ph[p] = base;
     fill_phase(F.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward, rows_cap);
+    F.ph[p].epi_direct = base.epi_direct && epi_warps_env() == 8;   // (the 16-warp experiment keeps the staged stores)
   }
   static const int prefetch_b = []() {
     const char* e = getenv("ANI_B200_PREFETCH_B");  // 1: issue a unit's weight copies before waiting for its inputs
     return e && atoi(e) != 0;                       // (measured on B200: no gain at 1k atoms, -4 % at 10k: off)
   }();
   F.prefetch_b = prefetch_b;
+  F.epi_direct = base.epi_direct && epi_warps_env() == 8;
   // role timeline of the first CTAs (tools/gemm_trace.py): needs the whole six-launch buffer
   F.trace = nullptr;
   if (g_trace && g_trace_next == 0 && (size_t)g_trace_launches * TRACE_WORDS_PER_LAUNCH >= (size_t)4 * tc::FTRACE_UNITS * 16) {
@@ -573,10 +588,7 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     cudaFuncSetAttribute(tc::k_mlp_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
     cudaFuncSetAttribute(tc::k_mlp_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
   }
-  static const int epi_warps = []() {
-    const char* e = getenv("ANI_B200_EPI_WARPS");  // 8 (default) or 16: epilogue warps of the fused kernel
-    return e && atoi(e) == 16 ? 16 : 8;
-  }();
+  const int epi_warps = epi_warps_env();
   if (epi_warps == 16)
     tc::k_mlp_fused<16><<<num_sms, tc::fused_threads(16), tc::FUSED_SMEM_BYTES, st>>>(F);
   else
