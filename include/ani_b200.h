@@ -73,6 +73,12 @@ typedef struct ani_aev_params {
   float shf_a[ANI_MAX_SHFA];
   float cos_z[ANI_MAX_SHFZ]; /* cos / sin of the angular sections ShfZ                     */
   float sin_z[ANI_MAX_SHFZ];
+  /* internal column layout of the TILED AEV operand (ani_b200_aev_forward layout 1) and of the dE/dAEV rows the      */
+  /* backward kernels read: the angular block starts ang_pad columns after the radial block, so that every element   */
+  /* pair's 32 features fill exactly one 32-column GEMM block (ANI-2x: 7 x 16 radial columns + 16 = 128; water then   */
+  /* has 5 live blocks instead of 8).  The padding columns are never written (zero) and the packed layer-1 weights    */
+  /* hold zeros there.  0 = the reference's column order (always so for plain rows, layout 0).                        */
+  int32_t ang_pad;
 } ani_aev_params;
 
 /* Device-resident description of the bucket grid, written by ani_b200_build_cells.     */
@@ -143,7 +149,7 @@ int ani_b200_species_layout(const float* spos, const ani_grid* grid, int n, int 
 /*    hold the element-presence bit mask and a "mask changed since the previous call" flag      */
 /*    (together: ani_b200_aev_forward's species_mask); scratch i32[1].                           */
 int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, int num_species,
-                               int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* blocks,
+                               int n_shf_r, int angular_sub, int out_dim, int ldx, int ang_pad, int32_t* blocks,
                                int32_t* scratch_i32, void* stream);
 
 /* 3. Fused neighbour search + AEV forward for sorted atoms lo..hi-1.                      */
@@ -253,7 +259,7 @@ int ani_b200_prepare_step(const float* coords, const int32_t* species, int n_con
                           int32_t* bin_start, int32_t* sorted_orig, int32_t* orig_to_sorted, float* spos,
                           int32_t* sbin, float* bucket_ranges, int lo, int hi, int num_species, int rows_cap,
                           int32_t* row_of, int32_t* row_atom, int32_t* tile_species, int32_t* layout_info,
-                          int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* aev_blocks,
+                          int n_shf_r, int angular_sub, int out_dim, int ldx, int ang_pad, int32_t* aev_blocks,
                           float* zero_f32, int zero_f32_count, double* zero_f64, int zero_f64_count,
                           int32_t* bucket_species, int32_t* scratch_i32, int32_t* status, void* stream);
 
@@ -370,6 +376,10 @@ int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int rows_cap, c
 /*    the call).  Same arguments and results as ani_b200_mlp_forward_backward otherwise.  want_backward == 2:          */
 /*    PER-MEMBER gradients (arch.py:403-436, members_forces): dx is f32[M][rows_cap][ldx] and member m's slab receives   */
 /*    d(member_scale[m] * e_m)/dAEV by plain stores (no sum over the members, no zero-fill needed).                      */
+/*    ani_b200_mlp_step runs a step as ani_b200_mlp_step_windows(model, rows_cap) launches of the data-flow kernel, */
+/*    one per window of the row tiles (all six phases of a window, then the next), sized so that a window's         */
+/*    activations stay in the L2 between the phase that writes them and the phases that read them.                  */
+int ani_b200_mlp_step_windows(const ani_mlp_model* model, int rows_cap);
 int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, float* dx, int rows_cap, const int32_t* row_atom,
                       const int32_t* layout_info, const int32_t* aev_blocks, void* act1, void* act2, void* act3,
                       float* e_member, int want_backward, int32_t* sync_i32, int32_t* status, void* stream);

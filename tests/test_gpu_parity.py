@@ -339,3 +339,36 @@ def test_cluster_preparation_matches_the_persistent_grid_kernel(n_mol, shard, mo
             assert torch.equal(a.view(torch.int32), b.view(torch.int32)), k
         else:
             assert torch.equal(a, b), k
+
+
+def test_aligned_angular_block_and_row_tile_windows(monkeypatch):
+    """Two internal re-arrangements that must not change any result: (i) the angular block of the tiled AEV operand
+    starts on a 32-column boundary (ani_aev_params::ang_pad; water then has 5 live GEMM blocks instead of 8) --
+    compared with networks packed in the reference's column order; (ii) the data-flow MLP launch cut into windows of
+    the row tiles (ANI_B200_MLP_CHUNKS) -- compared with one launch over all row tiles."""
+    from torchani_b200 import synthetic
+    from torchani_b200.engine import Engine, PackedNetworks, constants_2x
+    dev = torch.device("cuda:0")
+    consts = constants_2x()
+    m = oracle_model("2x")
+    w = [[wm[s] for s in m.symbols] for wm in m.weights]
+    sae = [m.sae[s] for s in m.symbols]
+    _, idx, coords, cell, _ = synthetic.water_box(1000, seed=5)
+    sp, co, ce = idx.to(dev), coords.to(dev), cell.to(dev)
+    out = {}
+    for name, rl, chunks in (("ref_order", 0, "1"), ("aligned", consts.num_species * len(consts.shf_r), "1"),
+                             ("aligned_windows", consts.num_species * len(consts.shf_r), "3")):
+        monkeypatch.setenv("ANI_B200_MLP_CHUNKS", chunks)
+        nets = PackedNetworks(w, consts.out_dim, dev, radial_len=rl)
+        eng = Engine(consts, nets, sae, cuda_graph=False)
+        eng.mlp_mode = "1"
+        r = eng.step(sp, co, ce, True)
+        eng.check_status()
+        ws = eng.workspace(*idx.shape)
+        out[name] = (r.energies.clone(), r.grad.clone(), r.member_atomic.clone(), int(ws.aev_blocks[0]), nets.col_pad)
+    assert out["ref_order"][4] == 0 and out["aligned"][4] == 16
+    assert out["ref_order"][3] == 8 and out["aligned"][3] == 5      # live 32-column blocks of a water box
+    for name in ("aligned", "aligned_windows"):
+        assert abs(float(out[name][0][0] - out["ref_order"][0][0])) < 3e-3, name
+        assert float((out[name][1] - out["ref_order"][1]).abs().max()) < 2e-6, name
+        assert float((out[name][2] - out["ref_order"][2]).abs().max()) < 1e-6, name

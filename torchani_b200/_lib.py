@@ -38,6 +38,7 @@ class AEVParams(C.Structure):
         ("num_species", C.c_int32), ("cutoff_kind", C.c_int32),
         ("shf_r", C.c_float * ANI_MAX_SHFR), ("shf_a", C.c_float * ANI_MAX_SHFA),
         ("cos_z", C.c_float * ANI_MAX_SHFZ), ("sin_z", C.c_float * ANI_MAX_SHFZ),
+        ("ang_pad", C.c_int32),
     ]
 
 
@@ -84,12 +85,13 @@ _PROTOTYPES = {
     "ani_b200_aev_forward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "ani_b200_aev_backward_rows": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     "ani_b200_prepare_step": (C.c_int, [_P, _P, _I, _I, _P, _I, _I, C.c_float, _I, _P, _P, _P, _P, _P, _P, _P,
-                                        _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
+                                        _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _P]),
     "ani_b200_verlet_positions": (C.c_int, [_I, _P, _P, _P, _I, _F, _P, _P, _P, _P, _P, _I, _P, _I, _P]),
     "ani_b200_debug_gemm_trace": (C.c_int, [_P, _I]),
     "ani_b200_half_neighbor_count": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, _P]),
     "ani_b200_half_neighbor_fill": (C.c_int, [_P, _P, _P, _P, _P, _I, _F, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "ani_b200_mlp_forward_backward": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "ani_b200_mlp_step_windows": (C.c_int, [_P, _I]),
     "ani_b200_mlp_step": (C.c_int, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "ani_b200_mlp_forward": (C.c_int, [_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "ani_b200_zero_live_blocks": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -101,7 +103,7 @@ _PROTOTYPES = {
     "ani_b200_comm_buffers": (C.c_int, [_P, _P, _P, _P]),
     "ani_b200_comm_allreduce": (C.c_int, [_P, _P, _P, _P]),
     "ani_b200_comm_destroy": (C.c_int, [_P]),
-    "ani_b200_active_aev_blocks": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "ani_b200_active_aev_blocks": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "ani_b200_reduce_energies": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
 }
 

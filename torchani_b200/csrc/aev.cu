@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32)
         }
         out = transpose_reduce32(acc, lane);
       }
-      store_feature(RL + p * 32 + lane, out);
+      store_feature(RL + (layout ? P.ang_pad : 0) + p * 32 + lane, out);
     }
   }
   if (ANI_OPND_FP16X2 && !(vmax <= OPND_HALF_MAX)) atomicOr(status, ANI_STATUS_OPERAND_RANGE);
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(AEV_FWD_WARPS * 32, ANI_AEV_FWD_MIN_CTAS)
         }
         out = transpose_reduce32(acc, lane);
       }
-      store_feature(RL + p * 32 + lane, out);
+      store_feature(RL + (layout ? P.ang_pad : 0) + p * 32 + lane, out);
     }
   }
   if (ANI_OPND_FP16X2 && !(vmax <= OPND_HALF_MAX)) atomicOr(status, ANI_STATUS_OPERAND_RANGE);
@@ -1046,7 +1046,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
       for (unsigned m2 = m1; m2; m2 &= m2 - 1, ++c2) {
         const int pp = base + __ffs(m2) - 1;
         const int cp = c1 * (2 * n_present - c1 + 1) / 2 + (c2 - c1);
-        if (cp < pair_cap) copy_async4(g_ang + cp * GSTRIDE + lane, gaev + row + RL + pp * 32 + lane);
+        if (cp < pair_cap) copy_async4(g_ang + cp * GSTRIDE + lane, gaev + row + RL + P.ang_pad + pp * 32 + lane);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1136,7 +1136,7 @@ __global__ void __launch_bounds__(AEV_WARPS * 32, ANI_AEV_BWD_MIN_CTAS)
       const int cp = clo * (2 * n_present - clo + 1) / 2 + (chi - clo);
       const float4* __restrict__ gp =
           cp < pair_cap ? reinterpret_cast<const float4*>(g_ang + cp * GSTRIDE)
-                        : reinterpret_cast<const float4*>(gaev + row + RL + pair_index(sj, sk, S) * 32);
+                        : reinterpret_cast<const float4*>(gaev + row + RL + P.ang_pad + pair_index(sj, sk, S) * 32);
       float tz[NZ], uz[NZ];
 #pragma unroll
       for (int z = 0; z < NZ; ++z) tz[z] = uz[z] = 0.f;

@@ -422,6 +422,23 @@ __global__ void k_layout_assign(const float4* __restrict__ spos, const ani_grid*
 // species pair (angular); if that species / pair does not occur among the real atoms, the column
 // is identically zero for every atom and its gradient is never consumed.
 // ---------------------------------------------------------------------------------------
+// Is internal column c of the AEV operand live for the element mask?  Internal order (ani_aev_params::ang_pad): radial
+// block [0, RL), `pad` never-written columns, angular block of angular_sub columns per element pair.
+__device__ __forceinline__ bool aev_column_live(int c, unsigned mask, int S, int n_shf_r, int angular_sub, int out_dim,
+                                                int pad) {
+  const int RL = S * n_shf_r;
+  if (c < RL) return (mask >> (c / n_shf_r)) & 1u;
+  c -= pad;
+  if (c < RL || c >= out_dim) return false;
+  // invert the row-major upper-triangle pair index
+  int s1 = 0, rem = (c - RL) / angular_sub;
+  while (rem >= S - s1) {
+    rem -= S - s1;
+    ++s1;
+  }
+  return ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
+}
+
 __global__ void k_species_present(const float4* __restrict__ spos, const ani_grid* __restrict__ grid, int n,
                                   int32_t* __restrict__ present) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -433,7 +450,7 @@ __global__ void k_species_present(const float4* __restrict__ spos, const ani_gri
 }
 
 __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int n_shf_r, int angular_sub,
-                                int out_dim, int ldx, int32_t* __restrict__ blocks) {
+                                int out_dim, int ldx, int ang_pad, int32_t* __restrict__ blocks) {
   // one warp; lane b tests the 32 columns of block b (32 blocks per round), a ballot compacts
   const unsigned mask = (unsigned)*present;
   const int RL = S * n_shf_r;
@@ -444,20 +461,8 @@ __global__ void k_active_blocks(const int32_t* __restrict__ present, int S, int 
     bool active = false;
     if (b < ldx / 32) {
       // radial columns one by one, angular columns pair block by pair block
-      for (int c = b * 32; c < b * 32 + 32 && c < out_dim && !active;
-           c = (c < RL) ? c + 1 : RL + ((c - RL) / angular_sub + 1) * angular_sub) {
-        if (c < RL) {
-          active = (mask >> (c / n_shf_r)) & 1u;
-        } else {
-          // invert the row-major upper-triangle pair index (one test per pair block is enough)
-          int s1 = 0, rem = (c - RL) / angular_sub;
-          while (rem >= S - s1) {
-            rem -= S - s1;
-            ++s1;
-          }
-          active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
-        }
-      }
+      for (int c = b * 32; c < b * 32 + 32 && !active; ++c)
+        active = aev_column_live(c, mask, S, n_shf_r, angular_sub, out_dim, ang_pad);
     }
     const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
     if (active) blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
@@ -499,7 +504,7 @@ struct PrepArgs {
   float4* ranges;
   int lo, hi, S, rows_cap;
   int32_t *row_of, *row_atom, *tile_species, *layout_info;
-  int n_shf_r, angular_sub, out_dim, ldx;
+  int n_shf_r, angular_sub, out_dim, ldx, ang_pad;
   int32_t* blocks;
   int32_t *bin_of, *slot, *tmp_list, *bin_count, *counter, *present, *chunk_hist, *species_base;
   int n_chunks, inline_setup;
@@ -707,19 +712,8 @@ __global__ void __launch_bounds__(1024) k_prep_layout(const __grid_constant__ Pr
       const int b = b0 + lane;
       bool active = false;
       if (b < A.ldx / 32) {
-        for (int c = b * 32; c < b * 32 + 32 && c < A.out_dim && !active;
-             c = (c < RL) ? c + 1 : RL + ((c - RL) / A.angular_sub + 1) * A.angular_sub) {
-          if (c < RL) {
-            active = (mask >> (c / A.n_shf_r)) & 1u;
-          } else {
-            int s1 = 0, rem = (c - RL) / A.angular_sub;
-            while (rem >= S - s1) {
-              rem -= S - s1;
-              ++s1;
-            }
-            active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
-          }
-        }
+        for (int c = b * 32; c < b * 32 + 32 && !active; ++c)
+          active = aev_column_live(c, mask, S, A.n_shf_r, A.angular_sub, A.out_dim, A.ang_pad);
       }
       const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
       if (active) A.blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
@@ -984,19 +978,8 @@ __global__ void __launch_bounds__(256) k_prep_fused(const __grid_constant__ Prep
         const int b = b0 + lane;
         bool active = false;
         if (b < A.ldx / 32) {
-          for (int c = b * 32; c < b * 32 + 32 && c < A.out_dim && !active;
-               c = (c < RL) ? c + 1 : RL + ((c - RL) / A.angular_sub + 1) * A.angular_sub) {
-            if (c < RL) {
-              active = (mask >> (c / A.n_shf_r)) & 1u;
-            } else {
-              int s1 = 0, rem = (c - RL) / A.angular_sub;
-              while (rem >= S - s1) {
-                rem -= S - s1;
-                ++s1;
-              }
-              active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
-            }
-          }
+          for (int c = b * 32; c < b * 32 + 32 && !active; ++c)
+            active = aev_column_live(c, mask, S, A.n_shf_r, A.angular_sub, A.out_dim, A.ang_pad);
         }
         const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
         if (active) A.blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
@@ -1108,39 +1091,6 @@ constexpr int MAX_AEV_BLOCKS = 64;   // ldx / 32 (gemm_tc.cuh: MAX_BLOCKS)
 
 __device__ __forceinline__ void prep_cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-// live 32-column AEV blocks for the element mask (one warp; the same walk as k_prep_layout)
-__device__ __forceinline__ void live_aev_blocks(const PrepArgs& A, unsigned mask, int lane) {
-  const int S = A.S, RL = S * A.n_shf_r;
-  int count = 0;
-  for (int b0 = 0; b0 < A.ldx / 32; b0 += 32) {
-    const int b = b0 + lane;
-    bool active = false;
-    if (b < A.ldx / 32) {
-      for (int c = b * 32; c < b * 32 + 32 && c < A.out_dim && !active;
-           c = (c < RL) ? c + 1 : RL + ((c - RL) / A.angular_sub + 1) * A.angular_sub) {
-        if (c < RL) {
-          active = (mask >> (c / A.n_shf_r)) & 1u;
-        } else {
-          int s1 = 0, rem = (c - RL) / A.angular_sub;
-          while (rem >= S - s1) {
-            rem -= S - s1;
-            ++s1;
-          }
-          active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
-        }
-      }
-    }
-    const unsigned live = __ballot_sync(ANI_FULL_MASK, active);
-    if (active) A.blocks[1 + count + __popc(live & ((1u << lane) - 1u))] = b;
-    count += __popc(live);
-  }
-  if (lane == 0) {
-    A.blocks[0] = count;
-    A.blocks[A.ldx / 32 + 2] = (A.blocks[A.ldx / 32 + 1] != (int)mask);
-    A.blocks[A.ldx / 32 + 1] = (int)mask;
-  }
 }
 
 __global__ void __launch_bounds__(PREP_CLUSTER_THREADS, 1)
@@ -1415,22 +1365,9 @@ __global__ void __launch_bounds__(PREP_CLUSTER_THREADS, 1)
       // live 32-column AEV blocks: warp w tests the 32 columns of block w (+32, ...) -- one column per lane -- instead
       // of one lane walking a whole block (the serial walk was 5 us of this kernel's critical path)
       const unsigned mask = (unsigned)__ldcg(A.present);
-      const int RL = S * A.n_shf_r, nblk = A.ldx / 32;
+      const int nblk = A.ldx / 32;
       for (int b = w; b < nblk; b += PREP_CLUSTER_THREADS / 32) {
-        const int c = b * 32 + lane;
-        bool active = false;
-        if (c < A.out_dim) {
-          if (c < RL) {
-            active = (mask >> (c / A.n_shf_r)) & 1u;
-          } else {
-            int s1 = 0, rem = (c - RL) / A.angular_sub;
-            while (rem >= S - s1) {
-              rem -= S - s1;
-              ++s1;
-            }
-            active = ((mask >> s1) & 1u) && ((mask >> (s1 + rem)) & 1u);
-          }
-        }
+        const bool active = aev_column_live(b * 32 + lane, mask, S, A.n_shf_r, A.angular_sub, A.out_dim, A.ang_pad);
         const bool live = __any_sync(ANI_FULL_MASK, active);
         if (lane == 0) s_live[b] = live;
       }
@@ -1528,15 +1465,16 @@ __global__ void __launch_bounds__(256)
 using namespace ani;
 
 extern "C" int ani_b200_active_aev_blocks(const float* spos, const ani_grid* grid, int n, int num_species,
-                                          int n_shf_r, int angular_sub, int out_dim, int ldx, int32_t* blocks,
-                                          int32_t* scratch_i32, void* stream) {
+                                          int n_shf_r, int angular_sub, int out_dim, int ldx, int ang_pad,
+                                          int32_t* blocks, int32_t* scratch_i32, void* stream) {
   if (!spos || !grid || !blocks || !scratch_i32) return ANI_ERR_BAD_ARG;
-  if (num_species < 1 || num_species > ANI_MAX_SPECIES || n_shf_r < 1 || angular_sub < 1 || ldx % 32 || out_dim > ldx)
+  if (num_species < 1 || num_species > ANI_MAX_SPECIES || n_shf_r < 1 || angular_sub < 1 || ldx % 32 || ang_pad < 0 ||
+      out_dim + ang_pad > ldx)
     return ANI_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(scratch_i32, 0, sizeof(int32_t), st);
   k_species_present<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(spos), grid, n, scratch_i32);
-  k_active_blocks<<<1, 32, 0, st>>>(scratch_i32, num_species, n_shf_r, angular_sub, out_dim, ldx, blocks);
+  k_active_blocks<<<1, 32, 0, st>>>(scratch_i32, num_species, n_shf_r, angular_sub, out_dim, ldx, ang_pad, blocks);
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }
@@ -1627,7 +1565,8 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
                                      int32_t* orig_to_sorted, float* spos, int32_t* sbin, float* bucket_ranges,
                                      int lo, int hi, int num_species, int rows_cap, int32_t* row_of,
                                      int32_t* row_atom, int32_t* tile_species, int32_t* layout_info, int n_shf_r,
-                                     int angular_sub, int out_dim, int ldx, int32_t* aev_blocks, float* zero_f32,
+                                     int angular_sub, int out_dim, int ldx, int ang_pad, int32_t* aev_blocks,
+                                     float* zero_f32,
                                      int zero_f32_count, double* zero_f64, int zero_f64_count,
                                      int32_t* bucket_species, int32_t* scratch_i32, int32_t* status, void* stream) {
   if (!coords || !species || !grid || !bin_start || !sorted_orig || !orig_to_sorted || !spos || !sbin ||
@@ -1644,7 +1583,7 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   if (num_species < 1 || num_species > ANI_MAX_SPECIES || lo < 0 || hi > n || lo > hi) return ANI_ERR_BAD_ARG;
   if (rows_cap % ANI_TILE_ROWS != 0) return ANI_ERR_BAD_ARG;
   if ((long long)rows_cap < (long long)(hi - lo) + (long long)num_species * (ANI_TILE_ROWS - 1)) return ANI_ERR_BAD_ARG;
-  if (n_shf_r < 1 || angular_sub < 1 || ldx % 32 || out_dim > ldx) return ANI_ERR_BAD_ARG;
+  if (n_shf_r < 1 || angular_sub < 1 || ldx % 32 || ang_pad < 0 || out_dim + ang_pad > ldx) return ANI_ERR_BAD_ARG;
   if ((zero_f32_count > 0 && !zero_f32) || (zero_f64_count > 0 && !zero_f64)) return ANI_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   PrepArgs A;
@@ -1655,7 +1594,7 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   A.ranges = (bucket_ranges && mode == 0) ? reinterpret_cast<float4*>(bucket_ranges) : nullptr;
   A.lo = lo; A.hi = hi; A.S = num_species; A.rows_cap = rows_cap;
   A.row_of = row_of; A.row_atom = row_atom; A.tile_species = tile_species; A.layout_info = layout_info;
-  A.n_shf_r = n_shf_r; A.angular_sub = angular_sub; A.out_dim = out_dim; A.ldx = ldx; A.blocks = aev_blocks;
+  A.n_shf_r = n_shf_r; A.angular_sub = angular_sub; A.out_dim = out_dim; A.ldx = ldx; A.ang_pad = ang_pad; A.blocks = aev_blocks;
   A.n_chunks = max(1, (hi - lo + LAYOUT_CHUNK - 1) / LAYOUT_CHUNK);
   // scratch: bin_of[n] slot[n] tmp_list[n] | zeroed: bin_count[max_bins+1] counter present chunk_hist | species_base
   A.bin_of = scratch_i32;

@@ -46,7 +46,6 @@ struct FusedArgs {
   int32_t* sync;          // [MAX_PHASES][sync_stride] arrivals per (phase, row tile); zeroed by the launcher
   int sync_stride;
   int prefetch_b;         // issue the weight copies of a unit's first K-blocks before waiting for its inputs
-  int epi_direct;         // tiled outputs straight from registers (gemm_epilogue.cuh)
   long long* trace;       // optional clock64 stamps [cta < 4][unit < FTRACE_UNITS][role 4][4] (ani_b200_debug_gemm_trace)
   Args ph[MAX_PHASES];
 };
@@ -393,18 +392,10 @@ __device__ __forceinline__ void tile_epilogue16(const Args& args, const TileMap&
   }
 }
 
-// The register-direct epilogue as a real function call in the data-flow kernel: the kernel around it keeps ~25
-// registers of unit bookkeeping alive, which pushed the inlined epilogue over the 168-register ceiling (512 B of spills
-// in its inner loops); a call per tile costs nothing next to 4 us of tile
-template <int EPI>
-__device__ __noinline__ void tile_epilogue_direct_call(const Args& args, const Tile& tl, const Species& sp, uint32_t taddr,
-                                                       const float* bias, const float* w4, float* e_part, int warp,
-                                                       int lane, uint64_t* tfull_bar, uint32_t tfull_parity, float* omax) {
-  float om = *omax;
-  tile_epilogue_direct<EPI>(args, tl, tl.rt, sp, taddr, bias, w4, e_part, warp, lane, tfull_bar, tfull_parity, om, false);
-  *omax = om;
-}
-
+// (The register-direct epilogue of gemm_epilogue.cuh is used by the chained launches only.  Measured in this kernel
+// on B200, 9 999 atoms: 277 us against 237 us with the staged stores -- here the stored activation may only be read
+// after the accumulator barrier, which exposes its L2 latency on every tile (backward tiles 12 us instead of 5-6), and
+// the extra live state of the data-flow bookkeeping pushed the inlined epilogue into spills.)
 // ---- the kernel -----------------------------------------------------------------------------
 // NW = 8: thread = row, two warps per quadrant (tile_epilogue8).  NW = 16: warp pairs per 16-column half
 // (tile_epilogue16).  Measured on B200 (profiles/): see DESIGN.md 4.1 for which one runs by default.
@@ -437,10 +428,8 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       build_tile_map(F.ph[p], tms[p]);
       phase_base[p] = run;
       run += tms[p].prefix[F.ph[p].num_species];
-      // (phases without staged stores -- register-direct epilogues, the plain layer-1 backward -- do not count)
-      if (!(F.ph[p].epi_direct || F.epi[p] == EPI_PLAIN)) bufs = min(bufs, tms[p].epi_bufs);
+      bufs = min(bufs, tms[p].epi_bufs);
     }
-    if (NW == 8 && F.epi_direct) bufs = 0;
     for (int p = NP; p <= MAX_PHASES; ++p) phase_base[p] = run;
     // one store-staging depth for all phases (the region is anchored at the end of the dynamic shared memory)
     s_epi_bufs = bufs;
@@ -746,7 +735,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       const int epi = F.epi[p];
       const Tile tl = decode_tile(args, tm, g - phase_base[p]);
       const Species& sp = args.sp[tl.s];
-      const bool direct = NW == 8 && F.epi_direct && epi != EPI_PLAIN;
+      const bool direct = false;   // (see the note above k_mlp_fused)
       if (threadIdx.x == 0) {
         stamp(kloc, 2, 0);
         stamp(kloc, 3, 0, p);
@@ -790,22 +779,6 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
       int groups = 0;
       if (threadIdx.x == 0) stamp(kloc, 2, 1);
-      if (direct) {
-        switch (epi) {
-          case EPI_BIAS_CELU:
-            tile_epilogue_direct_call<EPI_BIAS_CELU>(args, tl, sp, taddr, s_bias[acc], s_w4[acc], e_part, warp, lane, &tfull[acc],
-                                                     acc_phase, &omax);
-            break;
-          case EPI_MUL_DCELU:
-            tile_epilogue_direct_call<EPI_MUL_DCELU>(args, tl, sp, taddr, s_bias[acc], s_w4[acc], e_part, warp, lane, &tfull[acc],
-                                                     acc_phase, &omax);
-            break;
-          default:
-            tile_epilogue_direct_call<EPI_HEAD>(args, tl, sp, taddr, s_bias[acc], s_w4[acc], e_part, warp, lane, &tfull[acc],
-                                                acc_phase, &omax);
-            break;
-        }
-      } else
       switch (epi) {
         case EPI_BIAS_CELU:
           if (NW == 16)
@@ -855,9 +828,6 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       pend_groups = groups;
       pend_phase = p;
       pend_rt = tl.rt;
-      // register-direct stores: nothing to wait for here -- the warp arrives at once and the signal warp's gpu-scope
-      // fence publishes the stores of all eight warps
-      if (direct) flush_pending(0);
       if (threadIdx.x == 0) stamp(kloc, 2, 3);
     }
     flush_pending(0);

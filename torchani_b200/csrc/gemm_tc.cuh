@@ -100,6 +100,8 @@ struct Args {
   float y_inv_scale;            // EPI_MUL_DCELU: 1 / scale of the stored activation that C overwrites
   int32_t* status;              // ANI_STATUS_OPERAND_RANGE is raised here (may be NULL)
   int allow_narrow;             // short tile lists may split every accumulator into two column tiles (not EPI_HEAD)
+  int win_idx, win_cnt;         // this launch covers window win_idx of win_cnt equal parts of every species' row tiles
+                                // (mlp.cu: a step may run as several launches whose working sets stay in the L2)
   int epi_direct;               // tiled outputs straight from registers (gemm_epilogue.cuh); 0: shared-memory staging + TMA stores
   int b_compact;                // with `nblocks`: B holds ONLY the live column blocks, packed like a dense operand of
                                 // nb_count * 32 rows (mlp.cu: k_zero_live_blocks builds it every step) -- one bulk copy
@@ -303,7 +305,8 @@ __device__ __forceinline__ float dcelu_from_out(float y, const CeluConst& c) {
 // Row tiles of one species are contiguous; tile t -> (species, row tile, member, n0, bn).
 constexpr int MAX_BLOCKS = 64;         // ldx / 32 <= 64
 struct TileMap {
-  int first_rt[ANI_MAX_SPECIES + 1];   // first row tile of each species (+ total)
+  int first_rt[ANI_MAX_SPECIES + 1];   // first row tile of each species inside this launch's window
+  int cnt_rt[ANI_MAX_SPECIES];         // row tiles of each species inside the window
   int ntn[ANI_MAX_SPECIES];            // N tiles per (row tile, member)
   int prefix[ANI_MAX_SPECIES + 1];     // exclusive prefix of tile counts
   int n_eff[ANI_MAX_SPECIES];          // columns actually computed (compacted when nblocks is given)
@@ -331,8 +334,12 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool 
     tm.nb_count = min(a.nblocks[0], MAX_BLOCKS);
     for (int i = 0; i < tm.nb_count; ++i) tm.nb[i] = a.nblocks[1 + i];
   }
+  const int wc = a.win_cnt > 1 ? a.win_cnt : 1, wi = a.win_cnt > 1 ? a.win_idx : 0;
   for (int s = 0; s < S; ++s) {
-    tm.first_rt[s] = a.layout_info[4 + s];
+    const int f = a.layout_info[4 + s], nrt_all = a.layout_info[4 + s + 1] - f;
+    const int lo = f + (int)((long long)nrt_all * wi / wc), hi = f + (int)((long long)nrt_all * (wi + 1) / wc);
+    tm.first_rt[s] = lo;
+    tm.cnt_rt[s] = hi - lo;
     tm.n_eff[s] = tm.nb_count >= 0 ? tm.nb_count * 32 : a.sp[s].N;
     tm.tn[s] = TN_MAX;
     tm.ntn[s] = (tm.n_eff[s] + TN_MAX - 1) / TN_MAX;
@@ -342,7 +349,7 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool 
     int run = 0;
     for (int s = 0; s < S; ++s) {
       tm.prefix[s] = run;
-      const int nrt = tm.first_rt[s + 1] - tm.first_rt[s];
+      const int nrt = tm.cnt_rt[s];
       run += (pair ? (nrt + 1) / 2 : nrt) * a.members * tm.ntn[s];
     }
     tm.prefix[S] = run;
@@ -361,7 +368,7 @@ __device__ __forceinline__ void build_tile_map(const Args& a, TileMap& tm, bool 
   }
   int bn_max = 32;
   for (int s = 0; s < S; ++s)
-    if (tm.first_rt[s + 1] > tm.first_rt[s]) bn_max = max(bn_max, min(tm.tn[s], tm.n_eff[s]));
+    if (tm.cnt_rt[s] > 0) bn_max = max(bn_max, min(tm.tn[s], tm.n_eff[s]));
   tm.stage_bytes = A_BLOCK_BYTES + PARTS * (pair ? bn_max / 2 : bn_max) * ROW_BYTES;  // a pair member holds half of B
   // two store-staging buffers per epilogue warp if that still leaves a double-buffered main loop
   const int avail = SMEM_BYTES - 1024;
@@ -382,7 +389,7 @@ __device__ __forceinline__ Tile decode_tile(const Args& a, const TileMap& tm, in
   x.s = s;
   x.mem = rm % a.members;
   x.rt = tm.first_rt[s] + (pair ? 2 : 1) * (rm / a.members);
-  x.rt_last = tm.first_rt[s + 1] - 1;
+  x.rt_last = tm.first_rt[s] + tm.cnt_rt[s] - 1;
   x.n0 = nt * tm.tn[s];
   x.bn = min(tm.tn[s], tm.n_eff[s] - x.n0);
   return x;

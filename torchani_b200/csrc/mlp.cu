@@ -298,6 +298,8 @@ static int mlp_common(const ani_mlp_model* model, int rows_cap, const int32_t* r
   }();
   ta.allow_narrow = narrow;
   ta.b_compact = 0;
+  ta.win_idx = 0;
+  ta.win_cnt = 1;
   static const int epi_direct = []() {
     const char* e = getenv("ANI_B200_EPI_DIRECT");  // 0: shared-memory staging + TMA bulk stores (round 1 / early round 2)
     return !e || atoi(e) != 0;
@@ -535,6 +537,21 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
   }
 }
 
+// number of row-tile windows (= launches of the data-flow kernel) ani_b200_mlp_step cuts a step into
+extern "C" int ani_b200_mlp_step_windows(const ani_mlp_model* model, int rows_cap) {
+  if (!model || rows_cap < ANI_TILE_ROWS) return 1;
+  const char* e = getenv("ANI_B200_MLP_CHUNKS");   // number of windows; 0 / unset: by working-set size
+  int chunks = e ? atoi(e) : 0;
+  if (chunks < 1) {
+    const double act_bytes = (double)rows_cap * model->num_members * (model->h1_max + model->h2_max + model->h3_max) *
+                             (2.0 * OPND_PARTS);
+    chunks = (int)(act_bytes / (72.0 * 1024 * 1024)) + 1;
+  }
+  const int n_tiles_cap = rows_cap / ANI_TILE_ROWS;
+  if (chunks > n_tiles_cap / 8) chunks = n_tiles_cap / 8 > 1 ? n_tiles_cap / 8 : 1;   // a window keeps >= 8 row tiles
+  return chunks;
+}
+
 static int epi_warps_env() {
   static const int v = []() {
     const char* e = getenv("ANI_B200_EPI_WARPS");  // 8 (default) or 16: epilogue warps of the fused kernel
@@ -562,14 +579,13 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     F.dep[p] = p - 1;
     F.ph[p] = base;
     fill_phase(F.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward, rows_cap);
-    F.ph[p].epi_direct = base.epi_direct && epi_warps_env() == 8;   // (the 16-warp experiment keeps the staged stores)
+    F.ph[p].epi_direct = 0;   // the data-flow launch keeps the staged stores (gemm_fused.cuh)
   }
   static const int prefetch_b = []() {
     const char* e = getenv("ANI_B200_PREFETCH_B");  // 1: issue a unit's weight copies before waiting for its inputs
     return e && atoi(e) != 0;                       // (measured on B200: no gain at 1k atoms, -4 % at 10k: off)
   }();
   F.prefetch_b = prefetch_b;
-  F.epi_direct = base.epi_direct && epi_warps_env() == 8;
   // role timeline of the first CTAs (tools/gemm_trace.py): needs the whole six-launch buffer
   F.trace = nullptr;
   if (g_trace && g_trace_next == 0 && (size_t)g_trace_launches * TRACE_WORDS_PER_LAUNCH >= (size_t)4 * tc::FTRACE_UNITS * 16) {
@@ -589,10 +605,22 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     cudaFuncSetAttribute(tc::k_mlp_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
   }
   const int epi_warps = epi_warps_env();
-  if (epi_warps == 16)
-    tc::k_mlp_fused<16><<<num_sms, tc::fused_threads(16), tc::FUSED_SMEM_BYTES, st>>>(F);
-  else
-    tc::k_mlp_fused<8><<<num_sms, tc::fused_threads(8), tc::FUSED_SMEM_BYTES, st>>>(F);
+  // The activations of a step (act1..3: 19.5 KB per row for ANI-2x x 8) outgrow the 126 MB L2 beyond ~6 k atoms: the
+  // layers then stream through HBM (ncu at 10 k atoms: 554 MB of DRAM traffic per launch, L2 hit rate 60 %).  The
+  // launch is therefore cut into windows of the row tiles -- all six phases of one window, then the next -- sized so
+  // that a window's activations stay in the L2 between the phase that writes them and the phases that read them.
+  const int chunks = ani_b200_mlp_step_windows(model, rows_cap);
+  for (int c = 0; c < chunks; ++c) {
+    for (int p = 0; p < tc::MAX_PHASES; ++p) {
+      F.ph[p].win_idx = c;
+      F.ph[p].win_cnt = chunks;
+    }
+    if (epi_warps == 16)
+      tc::k_mlp_fused<16><<<num_sms, tc::fused_threads(16), tc::FUSED_SMEM_BYTES, st>>>(F);
+    else
+      tc::k_mlp_fused<8><<<num_sms, tc::fused_threads(8), tc::FUSED_SMEM_BYTES, st>>>(F);
+    if (F.trace) F.trace = nullptr;   // (the role timeline records the first window)
+  }
   ANI_CUDA_CHECK_LAUNCH();
   return ANI_OK;
 }

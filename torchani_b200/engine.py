@@ -204,7 +204,13 @@ class PackedNetworks:
     """
 
     def __init__(self, weights: tp.Sequence[tp.Sequence[tp.Sequence[tp.Tuple[Tensor, Tensor]]]],
-                 in_dim: int, device: torch.device, celu_alpha: float = 0.1, variant: tp.Optional[str] = None):
+                 in_dim: int, device: torch.device, celu_alpha: float = 0.1, variant: tp.Optional[str] = None,
+                 radial_len: int = 0):
+        """``radial_len`` (number of radial AEV columns, S * len(ShfR)) > 0 and not a multiple of 32: the angular block
+        of the layer-1 operands starts at the next 32-column boundary (``col_pad`` zero columns in between) if that
+        still fits the padded width -- every element pair then fills exactly one 32-column GEMM block, and the
+        block-sparse layer 1 skips more (water: 5 live blocks instead of 8).  The AEV kernels write / read the same
+        internal order (``ani_aev_params::ang_pad``); plain AEV rows keep the reference's order."""
         self.device = torch.device(device)
         self.variant = variant or ""   # build of the library (operand format) these operands are packed for
         M = len(weights)
@@ -213,6 +219,10 @@ class PackedNetworks:
             raise ValueError("unsupported number of ensemble members / species")
         self.num_members, self.num_species, self.in_dim = M, S, in_dim
         self.ldx = (in_dim + 31) // 32 * 32
+        self.radial_len = int(radial_len)
+        self.col_pad = (-self.radial_len) % 32 if 0 < self.radial_len < in_dim else 0
+        if in_dim + self.col_pad > self.ldx or os.environ.get("ANI_B200_ALIGN_ANGULAR", "1") == "0":
+            self.col_pad = 0
         self.celu_alpha = celu_alpha
         self.dims: tp.List[tp.Tuple[int, int, int]] = []
         self._keep: tp.List[Tensor] = []
@@ -281,7 +291,12 @@ class PackedNetworks:
             w4 = host[q["s_w4"]:q["s_w4"] + M * p3].view(M, p3)
             b4 = host[q["s_b4"]:q["s_b4"] + M]
             for m in range(M):
-                w1[m, :h1, :in_dim] = W[0][m]
+                if self.col_pad:   # internal column order: radial | col_pad zeros | angular
+                    RLc = self.radial_len
+                    w1[m, :h1, :RLc] = W[0][m][:, :RLc]
+                    w1[m, :h1, RLc + self.col_pad:in_dim + self.col_pad] = W[0][m][:, RLc:]
+                else:
+                    w1[m, :h1, :in_dim] = W[0][m]
                 w2[m, :h2, :h1] = W[1][m]
                 w3[m, :h3, :h2] = W[2][m]
                 b1[m, :h1], b2[m, :h2], b3[m, :h3] = Bv[0][m], Bv[1][m], Bv[2][m]
@@ -444,6 +459,10 @@ class Engine:
         self.consts, self.nets = consts, nets
         self.device = nets.device
         self.params = consts.to_struct()
+        # internal column order of the tiled AEV operand / dE/dAEV rows: must be the one the layer-1 weights were packed in
+        if nets.col_pad and nets.radial_len != consts.num_species * len(consts.shf_r):
+            raise ValueError("the networks were packed for another radial AEV length")
+        self.params.ang_pad = nets.col_pad
         self.nbr_cap = nbr_cap
         # > 0: buckets are built for cutoff + skin, so that a grid can be reused while no atom has moved
         # more than skin/2 (run(..., reuse=True); calculator.HostCalculator drives it)
@@ -579,7 +598,8 @@ class Engine:
         # kernels launched by this library in one step (memsets excluded):
         # prepare 1 (+1 grid kernel for open single systems), AEV fwd 1, GEMM fwd 3,
         # (zero + GEMM bwd 3 + AEV bwd 1), reduce 1
-        mlp = (1 + (1 if want_grad else 0)) if self._use_dataflow_mlp(hi - lo) else (3 + (4 if want_grad else 0))
+        mlp = ((self.lib.ani_b200_mlp_step_windows(C.byref(self.nets.model), ws.rows_cap) + (1 if want_grad else 0))
+               if self._use_dataflow_mlp(hi - lo) else (3 + (4 if want_grad else 0)))
         self.launches_per_step = 1 + (0 if (pbc or n_conf > 1) else 1) + 1 + mlp + (1 if want_grad else 0) + 1
         grad = ws.grad.view(n_conf, n_per_conf, 3) if want_grad else None
         virial = ws.virial.sum(0).view(3, 3) if want_virial else None
@@ -611,7 +631,7 @@ class Engine:
                 ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges),
                 lo, hi, c.num_species, ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species),
                 ptr(ws.layout_info), len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, self.nets.ldx,
-                ptr(ws.aev_blocks), ws.grad_ptr if want_grad else None, 3 * n if want_grad else 0,
+                self.nets.col_pad, ptr(ws.aev_blocks), ws.grad_ptr if want_grad else None, 3 * n if want_grad else 0,
                 ptr(ws.virial) if want_virial else None, ws.virial.numel() if want_virial else 0,
                 ptr(ws.bucket_species), ptr(ws.scratch), ptr(ws.status), st))
             if self.skin > 0:
@@ -733,7 +753,8 @@ class Engine:
                 0 if n_conf == 1 else 1, c.rcr, ws.max_bins, ptr(ws.grid), ptr(ws.bin_start), ptr(ws.sorted_orig),
                 ptr(ws.orig_to_sorted), ptr(ws.spos), ptr(ws.sbin), ptr(ws.bucket_ranges), 0, n, c.num_species,
                 ws.rows_cap, ptr(ws.row_of), ptr(ws.row_atom), ptr(ws.tile_species), ptr(ws.layout_info),
-                len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, ldx, ptr(ws.aev_blocks), None, 0, None, 0,
+                len(c.shf_r), len(c.shf_a) * len(c.shf_z), c.out_dim, ldx, self.nets.col_pad, ptr(ws.aev_blocks), None, 0,
+                None, 0,
                 ptr(ws.bucket_species), ptr(ws.scratch), ptr(ws.status), st), "prepare_step")
             mask_ptr = ws.aev_blocks.data_ptr() + 4 * (ws.n_blocks + 1)
             check(L.ani_b200_aev_forward(

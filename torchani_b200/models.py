@@ -164,6 +164,9 @@ class ANI(torch.nn.Module):
 
     # -- fused engine ----------------------------------------------------------------------
     def engine(self, device: torch.device) -> Engine:
+        # (the layer-1 operands are packed in the AEV kernels' internal column order: 32-aligned angular block)
+        c = self.aev_computer.constants
+        self.neural_networks._radial_len = c.num_species * len(c.shf_r)
         nets = self.neural_networks.packed(device)
         shifter = self.energy_shifter
         # the engine bakes the self energies in: key it on their values (edits, `_enabled` toggles)

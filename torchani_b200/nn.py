@@ -101,7 +101,12 @@ class _MLPFunction(torch.autograd.Function):
         src = aevs.detach().reshape(n, D).to(torch.float32).index_select(0, order)
         src = src * real.view(-1, 1)
         # padding atoms all map to row 0 with zero contribution -> index_add keeps row 0 intact
-        xp[:, :D].index_add_(0, rows, src)
+        RLc, cp = nets.radial_len, nets.col_pad       # internal column order of the layer-1 operands (engine.PackedNetworks)
+        if cp:
+            xp[:, :RLc].index_add_(0, rows, src[:, :RLc])
+            xp[:, RLc + cp:D + cp].index_add_(0, rows, src[:, RLc:])
+        else:
+            xp[:, :D].index_add_(0, rows, src)
         x_tiled = tile_a_operand(xp, variant=nets.variant)                    # the GEMM consumes the tiled form
         x = torch.zeros(rows_cap, ldx, dtype=torch.float32, device=dev)   # dE/dAEV comes back as plain rows
         ld = nets.ld
@@ -119,7 +124,10 @@ class _MLPFunction(torch.autograd.Function):
         out = torch.zeros(M, n, dtype=torch.float32, device=dev)
         out[:, order] = em_sorted
         if want_grad:
-            g_sorted = x[rows, :D] * real.view(-1, 1)              # d(mean energy)/d(aev), sorted order
+            gx = x[rows]
+            if cp:
+                gx = torch.cat([gx[:, :RLc], gx[:, RLc + cp:D + cp]], 1)
+            g_sorted = gx[:, :D] * real.view(-1, 1)                # d(mean energy)/d(aev), sorted order
             g = torch.zeros(n, D, dtype=torch.float32, device=dev)
             g[order] = g_sorted
             ctx.save_for_backward(g)
@@ -218,15 +226,17 @@ class AtomicContainer(torch.nn.Module):
         if self._packed_params is None:
             self._packed_params = [p for m in self.member_networks() for p in m.parameters()]
         params = self._packed_params
-        key = (str(device), self._variant, tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
+        rl = getattr(self, "_radial_len", 0)   # set by the model that owns the AEV computer (models.ANI.engine)
+        key = (str(device), self._variant, rl, tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:2]))
         if self._packed is None or self._packed_key != key:
             members = self.member_networks()
             params = self._packed_params = [p for m in members for p in m.parameters()]
-            key = (str(device), self._variant, tuple(p._version for p in params),
+            key = (str(device), self._variant, rl, tuple(p._version for p in params),
                    tuple(p.data_ptr() for p in params[:2]))
             weights = [[m.atomics[s].linear_pairs() for s in m.atomics] for m in members]
             in_dim = members[0].in_dim
-            self._packed = PackedNetworks(weights, in_dim, device, variant=self._variant)
+            self._packed = PackedNetworks(weights, in_dim, device, variant=self._variant,
+                                          radial_len=getattr(self, "_radial_len", 0))
             self._packed.set_active_members(self.active_members_idxs)
             self._packed_key = key
         return self._packed
