@@ -307,7 +307,7 @@ typedef struct ani_mlp_species {
   const float* b3;   /* [M*h3]                                                                  */
   const float* w4;   /* [M][h3]                                                                 */
   const float* b4;   /* [M]                                                                     */
-  const void* t_f1;  /* forward  layer 1: B = W1 stacked over members [M*h1][in_dim -> ldx]    */
+  const void* t_f1;  /* forward  layer 1: per member B = W1_m [h1][in_dim -> ldx]               */
   const void* t_f2;  /* forward  layer 2: per member B = W2_m [h2][h1]                          */
   const void* t_f3;  /* forward  layer 3: per member B = W3_m [h3][h2]                          */
   const void* t_b3;  /* backward layer 3: per member B = W3_m^T [h2][h3]                        */

@@ -376,7 +376,7 @@ def test_weight_packing_kernel_matches_the_python_tiler():
             sc = list(sp.w_scale)
             w1n = torch.cat(Wp[0], 0)
             expect = {
-                "d_f1": tile_b_operand(w1n, sc[0]),
+                "d_f1": torch.cat([tile_b_operand(x, sc[0]) for x in Wp[0]]),
                 "d_f2": torch.cat([tile_b_operand(x, sc[1]) for x in Wp[1]]),
                 "d_f3": torch.cat([tile_b_operand(x, sc[2]) for x in Wp[2]]),
                 "d_b3": torch.cat([tile_b_operand(x.t().contiguous(), sc[2]) for x in Wp[2]]),

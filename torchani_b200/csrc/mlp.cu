@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_fused.cuh"
+#include "gemm_chain.cuh"
 
 namespace ani {
 
@@ -373,11 +374,11 @@ extern "C" int ani_b200_mlp_forward(const ani_mlp_model* model, const void* x, i
   const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32, kbx = ldx / 32;
   ta.e_member = e_member;
   ta.want_backward = want_backward;
-  // Layer 1: the members share the input -> one GEMM with N = M*h1.
-  ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
+  // Layer 1: the members share the input (A offset 0 for every member), one GEMM per member like the other layers
+  ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
   for (int s = 0; s < S; ++s) {
     const ani_mlp_species& p = model->sp[s];
-    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr, 0, 0,
+    ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, p.h1, 0, p.h1, p.h1, nullptr, nullptr, 0, 0,
                             1.0f / (sv * wsc(p, 0))};
   }
   ta.kblocks = aev_blocks;  // dead AEV column blocks contribute exact zeros: skip them
@@ -469,7 +470,7 @@ extern "C" int ani_b200_mlp_backward(const ani_mlp_model* model, float* dx, int 
 // phase p of the list: 0-2 forward layers (2 = head), 3-5 backward-to-input.  `sync`: 6 * (rows_cap / 128) ints.
 static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, const void* x, float* dx, void* act1,
                        void* act2, void* act3, float* e_member, const int32_t* aev_blocks, int want_backward,
-                       int rows_cap = 0) {
+                       int rows_cap = 0, int group_override = 0) {
   const int S = model->num_species, M = model->num_members, ldx = model->ldx;
   const float sv = OPND_SCALE_VALUE, sg = OPND_SCALE_GRAD;
   const int kb1 = M * model->h1_max / 32, kb2 = M * model->h2_max / 32, kb3 = M * model->h3_max / 32, kbx = ldx / 32;
@@ -485,7 +486,7 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
     const ani_mlp_species& p = model->sp[s];
     switch (phase) {
       case 0:
-        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, M * p.h1, 0, 0, 0, nullptr, nullptr, 0, 0,
+        ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_f1), p.b1, ldx, p.h1, 0, p.h1, p.h1, nullptr, nullptr, 0, 0,
                                 1.0f / (sv * wsc(p, 0))};
         break;
       case 1:
@@ -505,7 +506,7 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
                                 1.0f / (sg * wsc(p, 1))};
         break;
       default: {
-        const int G = want_backward == 2 ? 1 : l1b_group(M, rows_cap);
+        const int G = (want_backward == 2 || group_override) ? max(1, group_override) : l1b_group(M, rows_cap);
         ta.sp[s] = tc::Species{static_cast<const unsigned char*>(p.t_b1), nullptr, G * p.h1, ldx, G * p.h1, 0, 0, nullptr, nullptr,
                                 M * p.h1 / 32, G * p.h1 / 32, 1.0f / (sg * wsc(p, 0))};
         break;
@@ -513,7 +514,7 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
     }
   }
   switch (phase) {
-    case 0: ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = 1;
+    case 0: ta.A = static_cast<const unsigned char*>(x); ta.a_kblocks = kbx; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
             ta.kblocks = aev_blocks; break;
     case 1: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = act2; ta.c_kblocks = kb2; ta.members = M; break;
     case 2: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act3; ta.c_kblocks = kb3; ta.members = M;
@@ -523,7 +524,8 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
     case 4: ta.A = static_cast<const unsigned char*>(act2); ta.a_kblocks = kb2; ta.C = act1; ta.c_kblocks = kb1; ta.members = M;
             ta.out_scale = sg; break;
     default: ta.A = static_cast<const unsigned char*>(act1); ta.a_kblocks = kb1; ta.C = dx; ta.c_kblocks = 0; ta.ldc = ldx;
-            ta.members = M / (want_backward == 2 ? 1 : l1b_group(M, rows_cap)); ta.nblocks = aev_blocks;
+            ta.members = M / ((want_backward == 2 || group_override) ? max(1, group_override) : l1b_group(M, rows_cap));
+            ta.nblocks = aev_blocks;
             ta.c_accumulate = ta.members > 1; ta.out_scale = sg; break;
   }
   if (phase == 5 && use_b1_compact(model, aev_blocks)) {
@@ -538,15 +540,23 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
 }
 
 // number of row-tile windows (= launches of the data-flow kernel) ani_b200_mlp_step cuts a step into
+static bool use_chain_launch(const ani_mlp_model* model) {
+  const char* ce = getenv("ANI_B200_MLP_CHAIN");
+  bool ok = !ce || atoi(ce) != 0;
+  for (int s = 0; s < model->num_species; ++s)
+    ok = ok && model->sp[s].h1 <= tc::TN_MAX && model->sp[s].h2 <= tc::TN_MAX && model->sp[s].h3 <= tc::TN_MAX;
+  return ok;
+}
+
 extern "C" int ani_b200_mlp_step_windows(const ani_mlp_model* model, int rows_cap) {
   if (!model || rows_cap < ANI_TILE_ROWS) return 1;
-  const char* e = getenv("ANI_B200_MLP_CHUNKS");   // number of windows; 0 / unset: by working-set size
-  int chunks = e ? atoi(e) : 0;
-  if (chunks < 1) {
-    const double act_bytes = (double)rows_cap * model->num_members * (model->h1_max + model->h2_max + model->h3_max) *
-                             (2.0 * OPND_PARTS);
-    chunks = (int)(act_bytes / (72.0 * 1024 * 1024)) + 1;
-  }
+  if (use_chain_launch(model)) return 1;   // independent chains: one launch whatever the size
+  // Experiment (measured on B200, 9 999 atoms: 214 / 305 / 387 / 479 us for 1 / 2 / 3 / 4 windows): every launch of the
+  // phase-major kernel costs ~90 us of dependency ramp before its ~4.9 us per unit and CTA, far more than the L2
+  // residency of a window buys -- one window unless the environment asks for more
+  const char* e = getenv("ANI_B200_MLP_CHUNKS");
+  int chunks = e ? atoi(e) : 1;
+  if (chunks < 1) chunks = 1;
   const int n_tiles_cap = rows_cap / ANI_TILE_ROWS;
   if (chunks > n_tiles_cap / 8) chunks = n_tiles_cap / 8 > 1 ? n_tiles_cap / 8 : 1;   // a window keeps >= 8 row tiles
   return chunks;
@@ -571,6 +581,41 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
   if (rc != ANI_OK) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int M = model->num_members;
+  static int num_sms_c = 0;
+  if (num_sms_c == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms_c, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(tc::k_mlp_chain<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FUSED_SMEM_BYTES);
+  }
+  // independent chains (gemm_chain.cuh): one launch, no synchronisation between CTAs.  ANI_B200_MLP_CHAIN=0: the
+  // phase-major data-flow launch below; ANI_B200_CHAIN_DEPTH: chains a CTA interleaves
+  if (use_chain_launch(model)) {
+    static tc::ChainArgs CA;
+    CA.n_phases = want_backward ? 6 : 3;
+    const char* de = getenv("ANI_B200_CHAIN_DEPTH");
+    CA.depth = de ? atoi(de) : 3;
+    if (CA.depth < 1) CA.depth = 1;
+    if (CA.depth > tc::CHAIN_MAX_D) CA.depth = tc::CHAIN_MAX_D;
+    static const int epis_c[6] = {tc::EPI_BIAS_CELU, tc::EPI_BIAS_CELU, tc::EPI_HEAD, tc::EPI_MUL_DCELU, tc::EPI_MUL_DCELU,
+                                  tc::EPI_PLAIN};
+    for (int p = 0; p < tc::MAX_PHASES; ++p) {
+      CA.epi[p] = epis_c[p];
+      CA.ph[p] = base;
+      fill_phase(CA.ph[p], p, model, x, dx, act1, act2, act3, e_member, aev_blocks, want_backward, rows_cap, 1);
+      CA.ph[p].allow_narrow = 0;   // a chain has one column tile per member and phase (the layer-1 backward: any number)
+      CA.ph[p].epi_direct = 0;
+    }
+    CA.trace = nullptr;
+    if (g_trace && g_trace_next == 0 && (size_t)g_trace_launches * TRACE_WORDS_PER_LAUNCH >= (size_t)4 * tc::FTRACE_UNITS * 16) {
+      CA.trace = g_trace;
+      g_trace_next = g_trace_launches;
+    }
+    if (want_backward) launch_zero_compact(model, (want_backward == 1 && M > 1) ? dx : nullptr, layout_info, aev_blocks, st);
+    tc::k_mlp_chain<8><<<num_sms_c, tc::CHAIN_THREADS, tc::FUSED_SMEM_BYTES, st>>>(CA);
+    ANI_CUDA_CHECK_LAUNCH();
+    return ANI_OK;
+  }
   F.n_phases = want_backward ? 6 : 3;
   static const int epis[6] = {tc::EPI_BIAS_CELU, tc::EPI_BIAS_CELU, tc::EPI_HEAD, tc::EPI_MUL_DCELU, tc::EPI_MUL_DCELU,
                               tc::EPI_PLAIN};

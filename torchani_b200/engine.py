@@ -313,7 +313,7 @@ class PackedNetworks:
                 (p1, p2, p3), sc = q["p"], q["sc"]
                 ldx_ = self.ldx
                 jobs = [   # (src, n, k, ld_src, transpose, scale, batch, src stride, dst, dst stride in bytes)
-                    (q["s_w1"], M * p1, ldx_, ldx_, 0, sc[0], 1, 0, q["d_f1"], 0),                      # [M*h1][ldx]
+                    (q["s_w1"], p1, ldx_, ldx_, 0, sc[0], M, p1 * ldx_, q["d_f1"], p1 * ldx_ * P2),      # per member [h1][ldx]
                     (q["s_w2"], p2, p1, p1, 0, sc[1], M, p2 * p1, q["d_f2"], p2 * p1 * P2),              # per member [h2][h1]
                     (q["s_w3"], p3, p2, p2, 0, sc[2], M, p3 * p2, q["d_f3"], p3 * p2 * P2),              # per member [h3][h2]
                     (q["s_w3"], p2, p3, p2, 1, sc[2], M, p3 * p2, q["d_b3"], p2 * p3 * P2),              # W3^T [h2][h3]
