@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
     const int quad = warp & 3;
     unsigned char* sb0 = epi_stage + warp * (EPI_BUFS * EPI_STAGE_BYTES);
     // the unit whose bulk stores may still be in flight: it is published (one arrival of this warp on its slot's
-    // barrier) once they have fully completed -- normally a unit late, at once whenever this warp would idle anyway
+    // barrier) once they have fully completed
     bool pending = false;
     int pend_groups = 0, pend_slot = 0;
     auto flush_pending = [&](int newer) {
@@ -360,20 +360,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
       }
-      // the pending unit is normally published at the end of this one.  It is published NOW if the accumulator has not
-      // shown up after a short grace period: a warp that blocks for real has published everything it owes, so the
-      // producer (which may be waiting for exactly that unit before it can feed the MMAs this warp waits for) goes on
+      // The previous unit of this warp (stores possibly still in flight) is published as early as it can be without
+      // idling: inside this tile's epilogue, right after its first store group has been committed (by then the older
+      // stores have had the accumulator wait + one column group of math to land).  At once instead when this very unit
+      // follows it in the same chain (the producer is waiting for it before it can feed the MMAs this warp waits for),
+      // or when this warp commits no store group in this tile.
+      uint64_t* publish = nullptr;
       if (pending) {
-        // (a unit that follows its own chain's previous unit directly -- a round with a single chain -- needs it now)
-        bool now = true;
-        for (int spin = 0; spin < 24 && pend_slot != cu.slot; ++spin) {
-          if (mbar_try(&tfull[acc], acc_phase)) {
-            now = false;
-            break;
-          }
-          __nanosleep(64);
-        }
-        if (now) flush_pending(0);
+        const bool stores_here = epi != EPI_PLAIN && (epi != EPI_HEAD || args.want_backward) && (warp >> 2) < tl.bn / 32;
+        if (pend_slot == cu.slot || !stores_here || pend_groups == 0)
+          flush_pending(0);
+        else
+          publish = &cdone[pend_slot];
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
       int groups = 0;
@@ -381,19 +379,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
       switch (epi) {
         case EPI_BIAS_CELU:
           tile_epilogue8<EPI_BIAS_CELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                        &tfull[acc], acc_phase, omax, groups);
+                                        &tfull[acc], acc_phase, omax, groups, publish);
           break;
         case EPI_MUL_DCELU:
           tile_epilogue8<EPI_MUL_DCELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                        &tfull[acc], acc_phase, omax, groups);
+                                        &tfull[acc], acc_phase, omax, groups, publish);
           break;
         case EPI_HEAD:
           tile_epilogue8<EPI_HEAD>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                   &tfull[acc], acc_phase, omax, groups);
+                                   &tfull[acc], acc_phase, omax, groups, publish);
           break;
         default:
           tile_epilogue8<EPI_PLAIN>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                    &tfull[acc], acc_phase, omax, groups);
+                                    &tfull[acc], acc_phase, omax, groups, publish);
           break;
       }
       tc_fence_before();
@@ -404,6 +402,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
         acc = 0;
         acc_phase ^= 1;
       }
+      if (publish) pending = false;   // published inside the tile's epilogue
       flush_pending(groups);
       pending = true;
       pend_groups = groups;

@@ -103,7 +103,10 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
                                               uint32_t taddr, unsigned char* sb0, int epi_bufs, uint32_t& buf,
                                               const float* __restrict__ bias, const float* __restrict__ w4,
                                               float* e_part, int warp, int lane, uint64_t* tfull_bar,
-                                              uint32_t tfull_parity, float& omax, int& groups_committed) {
+                                              uint32_t tfull_parity, float& omax, int& groups_committed,
+                                              uint64_t* publish_bar = nullptr) {
+  // publish_bar (gemm_chain.cuh): this warp's stores of the PREVIOUS unit are still in flight; once the first store group
+  // of this tile has been committed, wait for everything older (cp.async.bulk.wait_group 1) and arrive there
   const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
   const int quad = warp & 3, half = warp >> 2;
   const int r_tile = quad * 32 + lane;
@@ -217,6 +220,10 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
 #pragma unroll
           for (int p = 0; p < PARTS; ++p) bulk_s2g(blk + p * A_PART_BYTES, sb + p * EPI_PART_BYTES, EPI_PART_BYTES);
           bulk_commit();
+          if (publish_bar && groups_committed == 0) {
+            bulk_wait_done<1>();
+            mbar_arrive(publish_bar);
+          }
         }
         ++groups_committed;
         if (epi_bufs == 2) buf ^= 1;
