@@ -21,14 +21,14 @@
 namespace ani {
 namespace tc {
 
-constexpr int CHAIN_MAX_D = 4;
+constexpr int CHAIN_MAX_D = 8;
 constexpr int CHAIN_STAGE_BYTES = A_BLOCK_BYTES + PARTS * TN_MAX * ROW_BYTES;   // one ring geometry for all phases
 constexpr int CHAIN_WARPS = NUM_EPI_WARPS + 2;                                   // epilogue x 8, MMA, producer
 constexpr int CHAIN_THREADS = CHAIN_WARPS * 32;
 
 struct ChainArgs {
   int n_phases;            // 3 (forward only) or 6
-  int depth;               // chains a CTA interleaves (1 .. CHAIN_MAX_D)
+  int depth;               // chains a CTA interleaves (1 .. CHAIN_MAX_D); 0: all of its chains, in equal rounds of <= CHAIN_MAX_D
   int epi[MAX_PHASES];
   long long* trace;        // optional clock64 stamps [cta < 4][unit < FTRACE_UNITS][role 4][4]
   Args ph[MAX_PHASES];
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
   uint64_t* cdone = bars + 2 * MAX_STAGES + 5;    // [depth]: "the previous unit of this slot's chain is in global memory"
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NP = F.n_phases, D = F.depth;
+  const int NP = F.n_phases;
   constexpr int AVAIL = FUSED_SMEM_BYTES - 1024;
 
   if (threadIdx.x == 0) {
@@ -130,6 +130,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
   unsigned char* epi_stage = smem + AVAIL - EPI_BUFS * NW * EPI_STAGE_BYTES;
   const int M = F.ph[0].members;
   const int num_chains = s_total_rt * M, U = s_units_per_chain;
+  // interleave depth: the chains of a CTA (at most ceil(chains / CTAs)) in as few, equally deep rounds as possible -- a
+  // round with a single chain left runs its units back to back with every latency exposed
+  int D = F.depth;
+  if (D < 1) {
+    const int per_cta = (num_chains + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int rounds = (per_cta + CHAIN_MAX_D - 1) / CHAIN_MAX_D;
+    D = rounds > 0 ? (per_cta + rounds - 1) / rounds : 1;
+  }
+  D = max(1, min(D, CHAIN_MAX_D));
   auto stamp = [&](int kloc, int role, int slot, long long v = -1) {
     if (F.trace && blockIdx.x < 4 && kloc < FTRACE_UNITS)
       F.trace[(((size_t)blockIdx.x * FTRACE_UNITS + kloc) * 4 + role) * 4 + slot] = v >= 0 ? v : clock64();

@@ -594,8 +594,7 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     static tc::ChainArgs CA;
     CA.n_phases = want_backward ? 6 : 3;
     const char* de = getenv("ANI_B200_CHAIN_DEPTH");
-    CA.depth = de ? atoi(de) : 3;
-    if (CA.depth < 1) CA.depth = 1;
+    CA.depth = de ? atoi(de) : 0;   // 0: chosen on the device from the number of chains
     if (CA.depth > tc::CHAIN_MAX_D) CA.depth = tc::CHAIN_MAX_D;
     static const int epis_c[6] = {tc::EPI_BIAS_CELU, tc::EPI_BIAS_CELU, tc::EPI_HEAD, tc::EPI_MUL_DCELU, tc::EPI_MUL_DCELU,
                                   tc::EPI_PLAIN};
