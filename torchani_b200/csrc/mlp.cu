@@ -541,8 +541,12 @@ static void fill_phase(tc::Args& ta, int phase, const ani_mlp_model* model, cons
 
 // number of row-tile windows (= launches of the data-flow kernel) ani_b200_mlp_step cuts a step into
 static bool use_chain_launch(const ani_mlp_model* model) {
+  // Opt-in (ANI_B200_MLP_CHAIN=1).  Measured on B200 (profiles/r02_sweep.md): 224 us at 9 999 atoms whatever the
+  // interleave depth against 215 us for the phase-major launch, 94 vs 76 us (chained launches) at 999 atoms, 1.41 vs
+  // 1.10 ms at 50 k atoms -- all three schedules are bound by the same eight epilogue warps, and the chains give up
+  // the per-phase ring geometry and the member grouping of the layer-1 backward.
   const char* ce = getenv("ANI_B200_MLP_CHAIN");
-  bool ok = !ce || atoi(ce) != 0;
+  bool ok = ce && atoi(ce) != 0;
   for (int s = 0; s < model->num_species; ++s)
     ok = ok && model->sp[s].h1 <= tc::TN_MAX && model->sp[s].h2 <= tc::TN_MAX && model->sp[s].h3 <= tc::TN_MAX;
   return ok;
