@@ -372,3 +372,32 @@ def test_aligned_angular_block_and_row_tile_windows(monkeypatch):
         assert abs(float(out[name][0][0] - out["ref_order"][0][0])) < 3e-3, name
         assert float((out[name][1] - out["ref_order"][1]).abs().max()) < 2e-6, name
         assert float((out[name][2] - out["ref_order"][2]).abs().max()) < 1e-6, name
+
+
+@pytest.mark.parametrize("n_mol,depth", [(20, "0"), (333, "2"), (3333, "0"), (3333, "3")])
+def test_independent_chain_mlp_launch_matches_the_chained_launches(engines, n_mol, depth, monkeypatch):
+    """The opt-in third schedule of the MLP (csrc/gemm_chain.cuh, ANI_B200_MLP_CHAIN=1): a CTA owns whole (row tile,
+    member) chains and interleaves them, no synchronisation between CTAs.  Same tile code, so it must agree with the six
+    chained launches to rounding -- with fewer chains than SMs, a handful per CTA, and a fixed interleave depth."""
+    from torchani_b200 import synthetic
+    eng = engines["2x"]
+    d = eng.device
+    _, idx, coords, cell, _ = synthetic.water_box(n_mol, seed=13)
+    sp, co, ce = idx.to(d), coords.to(d), cell.to(d)
+    saved, saved_graph = eng.mlp_mode, eng.cuda_graph
+    try:
+        eng.cuda_graph = False
+        out = {}
+        for mode, chain in (("0", "0"), ("1", "1")):
+            monkeypatch.setenv("ANI_B200_MLP_CHAIN", chain)
+            monkeypatch.setenv("ANI_B200_CHAIN_DEPTH", depth)
+            eng.mlp_mode = mode
+            for _ in range(2):
+                r = eng.step(sp, co, ce, True)
+            out[mode] = (r.energies.clone(), r.grad.clone(), r.member_atomic.clone())
+            eng.check_status()
+        assert abs(float(out["0"][0][0] - out["1"][0][0])) < 1e-6 * max(1, 3 * n_mol)
+        assert float((out["0"][1] - out["1"][1]).abs().max()) < 2e-6
+        assert float((out["0"][2] - out["1"][2]).abs().max()) < 1e-6
+    finally:
+        eng.mlp_mode, eng.cuda_graph = saved, saved_graph
