@@ -94,12 +94,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) k_mlp_chain(const __grid_con
   const int NP = F.n_phases;
   constexpr int AVAIL = FUSED_SMEM_BYTES - 1024;
 
+  if (lane == 0 && warp < NP) build_tile_map(F.ph[warp], tms[warp]);   // (side by side, see k_mlp_fused)
+  __syncthreads();
   if (threadIdx.x == 0) {
     int bufs = 2;
-    for (int p = 0; p < NP; ++p) {
-      build_tile_map(F.ph[p], tms[p]);
+    for (int p = 0; p < NP; ++p)
       if (F.epi[p] != EPI_PLAIN) bufs = min(bufs, tms[p].epi_bufs);
-    }
     // one ring geometry for all phases (a CTA changes phase with every unit): stages of 16 KB + 256 rows of B
     bufs = min(bufs, (AVAIL - 2 * CHAIN_STAGE_BYTES) / (NW * EPI_STAGE_BYTES) >= 2 ? 2 : 1);
     s_epi_bufs = bufs;

@@ -104,7 +104,10 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
                                               const float* __restrict__ bias, const float* __restrict__ w4,
                                               float* e_part, int warp, int lane, uint64_t* tfull_bar,
                                               uint32_t tfull_parity, float& omax, int& groups_committed,
-                                              uint64_t* publish_bar = nullptr) {
+                                              uint64_t* publish_bar = nullptr, uint64_t* ydep_bar = nullptr,
+                                              uint32_t ydep_parity = 0) {
+  // ydep_bar (data-flow launch): "the producer has acquired this unit's inputs" -- the stored activation may be read from
+  // there on, i.e. during the main loop, instead of only after the accumulator barrier
   // publish_bar (gemm_chain.cuh): this warp's stores of the PREVIOUS unit are still in flight; once the first store group
   // of this tile has been committed, wait for everything older (cp.async.bulk.wait_group 1) and arrive there
   const CeluConst cc{args.alpha, 1.0f / args.alpha, 1.4426950408889634f / args.alpha};
@@ -143,11 +146,20 @@ __device__ __forceinline__ void tile_epilogue8(const Args& args, const TileMap& 
       q[2 * p + 1] = *reinterpret_cast<const uint4*>(blk + p * A_PART_BYTES + my_off(2 * hh + 1));
     }
   };
+  // The stored activation read here was written by an earlier phase, possibly moments ago: it may be read once this
+  // warp is ordered after the producer's acquire of the row tile's inputs -- through the producer's `ydep` barrier
+  // (then the loads fly during the main loop) or, without one, through the accumulator barrier.
+  const bool y_early = EPI == EPI_MUL_DCELU && ydep_bar != nullptr;
+  if (y_early) {
+    mbar_wait(ydep_bar, ydep_parity);
+    if (half < ngroups) {
+      load_y(half, 0, yq[0]);
+      load_y(half, 1, yq[1]);
+    }
+  }
   mbar_wait(tfull_bar, tfull_parity);
   tc_fence_after();
-  // (only now: the accumulator barrier is what orders this warp after the producer's acquire of the row tile's
-  // inputs -- the stored activation read here was written by an earlier phase, possibly moments ago)
-  if (EPI == EPI_MUL_DCELU && half < ngroups) {
+  if (EPI == EPI_MUL_DCELU && !y_early && half < ngroups) {
     load_y(half, 0, yq[0]);
     load_y(half, 1, yq[1]);
   }
@@ -420,6 +432,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
   __shared__ __align__(16) float s_bias[2][TN_MAX];
   __shared__ __align__(16) float s_w4[2][TN_MAX];
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 5];
+  __shared__ __align__(8) uint64_t ydep[4];   // unit k of this CTA: the producer has acquired its inputs (barrier k & 3)
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tfull = bars + 2 * MAX_STAGES;
@@ -429,10 +442,13 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
   const int NP = F.n_phases;
   constexpr int AVAIL = FUSED_SMEM_BYTES - 1024;
 
+  // the tile maps of the phases are built side by side (one lane of warp p builds phase p): a single thread building
+  // all six was 9 % of this kernel's stall samples (every other warp at the barrier below; ncu, profiles/r02_*)
+  if (lane == 0 && warp < NP) build_tile_map(F.ph[warp], tms[warp]);
+  __syncthreads();
   if (threadIdx.x == 0) {
     int run = 0, bufs = 2;
     for (int p = 0; p < NP; ++p) {
-      build_tile_map(F.ph[p], tms[p]);
       phase_base[p] = run;
       run += tms[p].prefix[F.ph[p].num_species];
       bufs = min(bufs, tms[p].epi_bufs);
@@ -451,6 +467,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], FEPI_WARPS);
     }
+    for (int i = 0; i < 4; ++i) mbar_init(&ydep[i], 1);
     fence_barrier_init();
   }
   if (warp == F_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -585,7 +602,12 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
         stage = (stage + pre) % (uint32_t)STAGES;
         kb_first = pre;
       }
-      if (lane == 0) stamp(kloc, 0, 1);
+      if (lane == 0) {
+        stamp(kloc, 0, 1);
+        // (the producer is never more than two units ahead of the epilogue -- two accumulators -- so four barriers
+        // cannot be re-armed before they have been waited on)
+        mbar_arrive(&ydep[kloc & 3]);
+      }
       // look ahead: the counter the next unit of this CTA will wait on
       ahead_valid = false;
       {
@@ -801,7 +823,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
                                  &tfull[acc], acc_phase, omax, groups);
           else
             tile_epilogue8<EPI_MUL_DCELU>(args, tm, tl, sp, taddr, sb0, EPI_BUFS, buf, s_bias[acc], s_w4[acc], e_part, warp, lane,
-                                &tfull[acc], acc_phase, omax, groups);
+                                &tfull[acc], acc_phase, omax, groups, nullptr, &ydep[kloc & 3], (uint32_t)(kloc >> 2) & 1u);
           break;
         case EPI_HEAD:
           if (NW == 16)
