@@ -390,11 +390,22 @@ def main():
     split = ("2 x fp16 split of every (power-of-two scaled) fp32 operand, 3 products" if fmt.parts == 2
              else "3 x bf16 split of every fp32 operand, 6 products")
     traffic = measured_traffic(args.config) if world == 1 else {}
-    roofline = {"kernel": "tc::k_gemm_tc (ani_b200_mlp_forward_backward): ensemble MLP fwd + bwd-to-input, "
+    # what the tensor cores actually execute: layer 1 over the live 32-column AEV blocks only, every product of the
+    # operand split counted (3 for 2 x fp16, 6 for 3 x bf16)
+    ws_b = eng.workspace(*idx.shape)
+    live_cols = 32 * int(ws_b.aev_blocks[0].item())
+    products = 3 if fmt.parts == 2 else 6
+    executed = sum(2.0 * (live_cols * h1 + h1 * h2 + h2 * h3 + h3) * eng.nets.num_members * 2 * c
+                   for (h1, h2, h3), c in zip(eng.nets.dims, counts)) * products / world
+    mlp_kernel = ("tc::k_mlp_fused (ani_b200_mlp_step, one data-flow launch)" if getattr(eng, "mlp_fused", False)
+                  else "tc::k_gemm_tc x 6 (ani_b200_mlp_forward_backward, chained launches)")
+    roofline = {"kernel": f"{mlp_kernel}: ensemble MLP fwd + bwd-to-input, "
                           f"tcgen05 kind::f16 on a {split} (fp32-accurate)",
                 "bound": "tensor", "achieved": flops / mlp_s / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                 "frac": flops / mlp_s / 1e12 / pk["bf16_tflops"], "traffic": traffic.get("mlp"),
                 "algorithmic_flops_per_launch_sequence": flops, "peak_source": pk["source"],
+                "live_aev_columns": live_cols, "executed_tensor_flops_per_launch_sequence": executed,
+                "executed_tensor_frac": executed / mlp_s / 1e12 / pk["bf16_tflops"],
                 "note": "achieved = dense algorithmic FLOPs of SURVEY 8(d) (2 x MACs x 8 members, forward + "
                         "backward-to-input, per atom by element) / device time of the GEMM launches of one step (CUDA "
                         "events on the launch stream); peak = measured dense bf16 rate (= the fp16 rate).  traffic = "
