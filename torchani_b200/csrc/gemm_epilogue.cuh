@@ -256,5 +256,155 @@ __device__ __forceinline__ void tile_epilogue_direct(const Args& args, const Til
   }
 }
 
+
+// The same epilogue with SIXTEEN warps: the four warps of a TMEM lane quadrant split a tile by (group parity, 16-column
+// half) -- warp w: quadrant w & 3, groups g = (w >> 3), (w >> 3) + 2, ..., half (w >> 2) & 1 -- so every warp does half
+// of what one of the eight does above, whatever the tile width, with no barrier between warps (the round-1/2 sixteen-warp
+// variant paired warps on one staging buffer): a half of a row is one 32-byte sector per piece, written / read by its
+// own thread.  The point is not arithmetic throughput: a tile's epilogue is three transfers on three different paths
+// -- tensor memory -> registers (64 B/clk), registers -> L2 (64 B/clk), and for the backward the stored activation
+// L2 -> registers -- and eight warps with one load in flight each leave them idle most of the time.
+template <int EPI>
+__device__ __forceinline__ void tile_epilogue_direct16(const Args& args, const Tile& tl, const Species& sp, uint32_t taddr,
+                                                       const float* __restrict__ bias, const float* __restrict__ w4,
+                                                       float* e_part, int warp, int lane, uint64_t* tfull_bar,
+                                                       uint32_t tfull_parity, float& omax, uint64_t* ydep_bar,
+                                                       uint32_t ydep_parity) {
+  static_assert(EPI == EPI_BIAS_CELU || EPI == EPI_MUL_DCELU || EPI == EPI_HEAD, "tiled-output epilogues only");
+  const int quad = warp & 3, hh = (warp >> 2) & 1, gp = warp >> 3;
+  const int r_tile = quad * 32 + lane;
+  const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+  const bool swapped = sw & 1u;
+  const uint32_t row_base = (uint32_t)(r_tile >> 3) * 512u + (uint32_t)(r_tile & 7) * 64u + ((uint32_t)(hh ^ (int)(sw >> 1)) << 5);
+  const bool tiled_out = EPI != EPI_HEAD || args.want_backward;
+  const int my_row = tl.rt * TM + r_tile;
+  unsigned char* ct = reinterpret_cast<unsigned char*>(args.C) +
+                      ((size_t)tl.rt * args.c_kblocks + (size_t)(tl.mem * sp.c_moff + tl.n0) / TK) * A_BLOCK_BYTES + row_base;
+  const int ngroups = tl.bn / 32;
+  const float os = args.out_scale;
+  const float a_s = sp.acc_scale * (EPI == EPI_HEAD ? 1.0f : os);
+  const f32x2 a2 = pack2(a_s, a_s);
+  const float inv_alpha = 1.0f / args.alpha;
+  const float kx = (EPI == EPI_HEAD ? 1.0f : 1.0f / os) * 1.4426950408889634f * inv_alpha;
+  const float al = args.alpha * (EPI == EPI_HEAD ? 1.0f : os);
+  const f32x2 kx2 = pack2(kx, kx), al2 = pack2(al, al), nal2 = pack2(-al, -al);
+  const float cy = inv_alpha * args.y_inv_scale * a_s;
+  const f32x2 cy2 = pack2(cy, cy);
+  const f32x2 ia2 = pack2(inv_alpha, inv_alpha), one2 = pack2(1.0f, 1.0f);
+  float seed = 0.f;
+  bool row_valid = false;
+  if (EPI == EPI_HEAD) {
+    row_valid = args.row_atom[my_row] >= 0;
+    seed = row_valid ? args.member_scale[tl.mem] * os : 0.f;
+  }
+  const f32x2 seed2 = pack2(seed, seed);
+  f32x2 e_acc2 = pack2(0.f, 0.f);
+
+  uint4 yq[PARTS][2];   // stored activation of this row, this warp's half of the group in flight: [piece][chunk]
+  auto load_y = [&](int g) {
+    const unsigned char* src = ct + (size_t)g * A_BLOCK_BYTES;
+#pragma unroll
+    for (int p = 0; p < PARTS; ++p) {
+      if (swapped)
+        ldg256_cg(src + p * A_PART_BYTES, yq[p][1], yq[p][0]);
+      else
+        ldg256_cg(src + p * A_PART_BYTES, yq[p][0], yq[p][1]);
+    }
+  };
+  if (EPI == EPI_MUL_DCELU) {
+    // the producer has acquired this unit's inputs: the stored activation may be read while the main loop runs
+    mbar_wait(ydep_bar, ydep_parity);
+    if (gp < ngroups) load_y(gp);
+  }
+  mbar_wait(tfull_bar, tfull_parity);
+  tc_fence_after();
+
+  uint32_t wp[PARTS][8];
+  auto chunk = [&](int g, auto c8_c, const uint32_t (&r)[8]) {
+    constexpr int c8 = decltype(c8_c)::value;
+    const int c0 = g * 32 + hh * 16;
+#pragma unroll
+    for (int i = 4 * c8; i < 4 * c8 + 4; ++i) {
+      const f32x2 acc = pack2(__uint_as_float(r[2 * (i - 4 * c8)]), __uint_as_float(r[2 * (i - 4 * c8) + 1]));
+      float o0, o1;
+      if (EPI == EPI_MUL_DCELU) {
+        uint32_t yw[PARTS];
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) yw[p] = u4_word(yq[p][i >> 2], i & 3);
+        const f32x2 y = join_pair(yw);
+        float y0, y1, d0, d1;
+        unpack2(y, y0, y1);
+        unpack2(fma2(y, cy2, a2), d0, d1);
+        d0 = y0 > 0.f ? a_s : d0;
+        d1 = y1 > 0.f ? a_s : d1;
+        unpack2(mul2(acc, pack2(d0, d1)), o0, o1);
+      } else {
+        const f32x2 x = fma2(acc, a2, *reinterpret_cast<const f32x2*>(bias + c0 + 2 * i));
+        float x0, x1, t0, t1, n0, n1;
+        unpack2(x, x0, x1);
+        unpack2(mul2(x, kx2), t0, t1);
+        const f32x2 n = fma2(al2, pack2(ex2_approx(t0), ex2_approx(t1)), nal2);
+        unpack2(n, n0, n1);
+        if (EPI == EPI_BIAS_CELU) {
+          o0 = x0 > 0.f ? x0 : n0;
+          o1 = x1 > 0.f ? x1 : n1;
+        } else {
+          const f32x2 w = *reinterpret_cast<const f32x2*>(w4 + c0 + 2 * i);
+          e_acc2 = fma2(pack2(x0 > 0.f ? x0 : n0, x1 > 0.f ? x1 : n1), w, e_acc2);
+          float d0, d1;
+          unpack2(fma2(n, ia2, one2), d0, d1);
+          d0 = x0 > 0.f ? 1.0f : d0;
+          d1 = x1 > 0.f ? 1.0f : d1;
+          unpack2(mul2(mul2(w, seed2), pack2(d0, d1)), o0, o1);
+        }
+      }
+      omax = fmaxf(omax, fmaxf(fabsf(o0), fabsf(o1)));
+      uint32_t w[PARTS];
+      split_pair(o0, o1, w);
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) wp[p][i] = w[p];
+    }
+  };
+  {
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    uint32_t r0[8], r1[8];
+    if (gp < ngroups) tmem_ld8_issue(taddr + gp * 32 + hh * 16, r0);
+    for (int g = gp; g < ngroups; g += 2) {
+      tmem_ld_wait8(r0);
+      tmem_ld8_issue(taddr + g * 32 + hh * 16 + 8, r1);
+      chunk(g, I0{}, r0);
+      tmem_ld_wait8(r1);
+      if (g + 2 < ngroups) tmem_ld8_issue(taddr + (g + 2) * 32 + hh * 16, r0);
+      chunk(g, I1{}, r1);
+      if (EPI == EPI_MUL_DCELU && g + 2 < ngroups) load_y(g + 2);
+      if (tiled_out) {
+        unsigned char* dst = ct + (size_t)g * A_BLOCK_BYTES;
+#pragma unroll
+        for (int p = 0; p < PARTS; ++p) {
+          const uint4 lo = make_uint4(wp[p][0], wp[p][1], wp[p][2], wp[p][3]);
+          const uint4 hi = make_uint4(wp[p][4], wp[p][5], wp[p][6], wp[p][7]);
+          if (swapped)
+            stg256(dst + p * A_PART_BYTES, hi, lo);
+          else
+            stg256(dst + p * A_PART_BYTES, lo, hi);
+        }
+      }
+    }
+  }
+  if (EPI == EPI_HEAD) {
+    float e0, e1;
+    unpack2(e_acc2, e0, e1);
+    e_part[warp * 32 + lane] = e0 + e1;
+    asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
+    if (warp < 4)
+      args.e_member[(size_t)tl.mem * args.rows_cap + my_row] =
+          row_valid ? e_part[warp * 32 + lane] + e_part[(warp + 4) * 32 + lane] + e_part[(warp + 8) * 32 + lane] +
+                          e_part[(warp + 12) * 32 + lane] + sp.b4[tl.mem]
+                    : 0.f;
+    asm volatile("bar.sync 1, %0;" ::"n"(16 * 32) : "memory");
+  }
+}
+
 }  // namespace tc
 }  // namespace ani

@@ -46,6 +46,7 @@ struct FusedArgs {
   int32_t* sync;          // [MAX_PHASES][sync_stride] arrivals per (phase, row tile); zeroed by the launcher
   int sync_stride;
   int prefetch_b;         // issue the weight copies of a unit's first K-blocks before waiting for its inputs
+  int epi_direct16;       // k_mlp_fused<16>: register-direct epilogue, a warp per (group parity, 16-column half)
   long long* trace;       // optional clock64 stamps [cta < 4][unit < FTRACE_UNITS][role 4][4] (ani_b200_debug_gemm_trace)
   Args ph[MAX_PHASES];
 };
@@ -415,6 +416,18 @@ __device__ __forceinline__ void tile_epilogue16(const Args& args, const TileMap&
 // on B200, 9 999 atoms: 277 us against 237 us with the staged stores -- here the stored activation may only be read
 // after the accumulator barrier, which exposes its L2 latency on every tile (backward tiles 12 us instead of 5-6), and
 // the extra live state of the data-flow bookkeeping pushed the inlined epilogue into spills.)
+// The sixteen-warp register-direct epilogue as a real call: at 96 registers per thread the unit bookkeeping of the kernel
+// around it must not stay live inside its loops
+template <int EPI>
+__device__ __noinline__ void tile_epilogue_direct16_call(const Args& args, const Tile& tl, const Species& sp, uint32_t taddr,
+                                                         const float* bias, const float* w4, float* e_part, int warp,
+                                                         int lane, uint64_t* tfull_bar, uint32_t tfull_parity, float* omax,
+                                                         uint64_t* ydep_bar, uint32_t ydep_parity) {
+  float om = *omax;
+  tile_epilogue_direct16<EPI>(args, tl, sp, taddr, bias, w4, e_part, warp, lane, tfull_bar, tfull_parity, om, ydep_bar, ydep_parity);
+  *omax = om;
+}
+
 // ---- the kernel -----------------------------------------------------------------------------
 // NW = 8: thread = row, two warps per quadrant (tile_epilogue8).  NW = 16: warp pairs per 16-column half
 // (tile_epilogue16).  Measured on B200 (profiles/): see DESIGN.md 4.1 for which one runs by default.
@@ -453,6 +466,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       run += tms[p].prefix[F.ph[p].num_species];
       bufs = min(bufs, tms[p].epi_bufs);
     }
+    if (NW == 16 && F.epi_direct16) bufs = 0;   // no store staging at all (the plain layer-1 backward has none either)
     for (int p = NP; p <= MAX_PHASES; ++p) phase_base[p] = run;
     // one store-staging depth for all phases (the region is anchored at the end of the dynamic shared memory)
     s_epi_bufs = bufs;
@@ -764,7 +778,7 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       const int epi = F.epi[p];
       const Tile tl = decode_tile(args, tm, g - phase_base[p]);
       const Species& sp = args.sp[tl.s];
-      const bool direct = false;   // (see the note above k_mlp_fused)
+      const bool direct = NW == 16 && F.epi_direct16 && epi != EPI_PLAIN;   // (tile_epilogue_direct16, gemm_epilogue.cuh)
       if (threadIdx.x == 0) {
         stamp(kloc, 2, 0);
         stamp(kloc, 3, 0, p);
@@ -808,6 +822,19 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TN_MAX;
       int groups = 0;
       if (threadIdx.x == 0) stamp(kloc, 2, 1);
+      if (NW == 16 && direct) {
+        uint64_t* yb = &ydep[kloc & 3];
+        const uint32_t yp = (uint32_t)(kloc >> 2) & 1u;
+        if (epi == EPI_BIAS_CELU)
+          tile_epilogue_direct16_call<EPI_BIAS_CELU>(args, tl, sp, taddr, s_bias[acc], s_w4[acc], e_part, warp, lane, &tfull[acc],
+                                                     acc_phase, &omax, yb, yp);
+        else if (epi == EPI_MUL_DCELU)
+          tile_epilogue_direct16_call<EPI_MUL_DCELU>(args, tl, sp, taddr, s_bias[acc], s_w4[acc], e_part, warp, lane, &tfull[acc],
+                                                     acc_phase, &omax, yb, yp);
+        else
+          tile_epilogue_direct16_call<EPI_HEAD>(args, tl, sp, taddr, s_bias[acc], s_w4[acc], e_part, warp, lane, &tfull[acc],
+                                                acc_phase, &omax, yb, yp);
+      } else
       switch (epi) {
         case EPI_BIAS_CELU:
           if (NW == 16)
@@ -857,6 +884,9 @@ __global__ void __launch_bounds__(fused_threads(NW), 1) k_mlp_fused(const __grid
       pend_groups = groups;
       pend_phase = p;
       pend_rt = tl.rt;
+      // register-direct stores: nothing to wait for here -- the warp arrives at once and the signal warp's gpu-scope
+      // fence publishes the stores of all sixteen warps (cumulativity through the CTA-scope synchronisation)
+      if (direct) flush_pending(0);
       if (threadIdx.x == 0) stamp(kloc, 2, 3);
     }
     flush_pending(0);

@@ -634,6 +634,10 @@ extern "C" int ani_b200_mlp_step(const ani_mlp_model* model, const void* x, floa
     return e && atoi(e) != 0;                       // (measured on B200: no gain at 1k atoms, -4 % at 10k: off)
   }();
   F.prefetch_b = prefetch_b;
+  {
+    const char* pe = getenv("ANI_B200_EPI16_PAIRS");   // 1: the paired sixteen-warp epilogue with staged stores
+    F.epi_direct16 = epi_warps_env() == 16 && !(pe && atoi(pe) != 0);
+  }
   // role timeline of the first CTAs (tools/gemm_trace.py): needs the whole six-launch buffer
   F.trace = nullptr;
   if (g_trace && g_trace_next == 0 && (size_t)g_trace_launches * TRACE_WORDS_PER_LAUNCH >= (size_t)4 * tc::FTRACE_UNITS * 16) {
