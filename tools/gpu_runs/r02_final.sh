@@ -20,6 +20,6 @@ timeout 400 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/r
 timeout 600 python tools/reference_gpu_path.py --out gpurun_out/r02_final_reference_gpu_path.json > gpurun_out/r02_final_refpath.log 2>&1; echo "refpath rc=$?"; grep ratio gpurun_out/r02_final_refpath.log
 # launch list of two steps (eager warm-up launches + graph replays are all visible to ncu)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_final_launches.csv python bench.py --steps 2 --warmup 3 --cpu-steps 0 > gpurun_out/r02_final_launches.log 2>&1; echo "launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_aev_forward_cta|k_aev_backward|k_mlp_fused|k_gemm_tc|k_prep_fused' -c 12 -o gpurun_out/r02_final_ncu_full -f python bench.py --steps 1 --warmup 3 --cpu-steps 0 > gpurun_out/r02_final_ncu.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_aev_forward_cta|k_aev_backward|k_mlp_fused|k_gemm_tc|k_prep_fused|k_prep_cluster' -c 12 -o gpurun_out/r02_final_ncu_full -f python bench.py --steps 1 --warmup 3 --cpu-steps 0 > gpurun_out/r02_final_ncu.log 2>&1; echo "ncu full rc=$?"
 ncu -i gpurun_out/r02_final_ncu_full.ncu-rep --page raw --csv > gpurun_out/r02_final_ncu_full_raw.csv 2>/dev/null
 python tools/make_traffic.py gpurun_out/r02_final_ncu_full_raw.csv water10k; cp profiles/traffic.json gpurun_out/traffic.json
