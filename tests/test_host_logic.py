@@ -303,3 +303,89 @@ def test_species_major_staging_arithmetic():
                     seg_end[s + 1] = count
         assert (seen == 1).all()
         assert seg_end[1:].tolist() == [int(off[(s + 1) * R]) for s in range(S)]
+
+
+def _column_live(c, mask, S, n_shf_r, angular_sub, out_dim, pad):
+    """Python statement of aev_column_live (csrc/cells.cu): internal column c of the tiled AEV operand -- radial block,
+    `pad` never-written columns, angular block of `angular_sub` columns per element pair (row-major upper triangle)."""
+    RL = S * n_shf_r
+    if c < RL:
+        return bool((mask >> (c // n_shf_r)) & 1)
+    c -= pad
+    if c < RL or c >= out_dim:
+        return False
+    s1, rem = 0, (c - RL) // angular_sub
+    while rem >= S - s1:
+        rem -= S - s1
+        s1 += 1
+    return bool((mask >> s1) & 1) and bool((mask >> (s1 + rem)) & 1)
+
+
+def test_aligned_angular_block_live_blocks():
+    """ani_aev_params::ang_pad: with the angular block of ANI-2x on a 32-column boundary every element pair fills exactly
+    one 32-column GEMM block.  Live blocks for water / H C N O S, reference order vs internal order; the padded layout
+    still fits ldx = 1024 and maps every reference column to a distinct internal column."""
+    S, nR, sub, out_dim, ldx = 7, 16, 32, 1008, 1024
+    pad = (-S * nR) % 32
+    assert pad == 16 and out_dim + pad == ldx
+
+    def live_blocks(mask, pad):
+        return [b for b in range(ldx // 32) if any(_column_live(c, mask, S, nR, sub, out_dim, pad) for c in range(32 * b, 32 * b + 32))]
+
+    water = (1 << 0) | (1 << 3)                         # H, O of (H, C, N, O, S, F, Cl)
+    hcnos = (1 << 0) | (1 << 1) | (1 << 2) | (1 << 3) | (1 << 4)
+    assert len(live_blocks(water, 0)) == 8 and len(live_blocks(water, pad)) == 5
+    assert len(live_blocks(hcnos, pad)) == 3 + 15       # radial blocks {0, 1, 2} + one block per element pair
+    assert len(live_blocks(hcnos, pad)) < len(live_blocks(hcnos, 0))
+    internal = [c if c < S * nR else c + pad for c in range(out_dim)]   # what PackedNetworks / the AEV kernels apply
+    assert len(set(internal)) == out_dim and max(internal) < ldx
+    assert all(_column_live(ci, 0x7f, S, nR, sub, out_dim, pad) for ci in internal)
+    assert not any(_column_live(c, 0x7f, S, nR, sub, out_dim, pad) for c in range(S * nR, S * nR + pad))
+
+
+def test_chain_walk_covers_every_unit_once_in_dependency_order():
+    """Python statement of ChainWalk (csrc/gemm_chain.cuh): CTA c runs rounds of D chains, inside a round unit-major and
+    chain-minor.  Every (chain, unit) is visited exactly once by exactly one CTA, a chain's units appear in order in its
+    CTA's sequence, and with D >= 2 full slots a unit's predecessor is at least D - 1 units back (what the shared-memory
+    barriers and the lagged publication of finished units rely on)."""
+    def walk(G, c, D, U, num_chains):
+        out, rnd = [], 0
+        while c + G * D * rnd < num_chains:
+            for u in range(U):
+                for j in range(D):
+                    chain = c + G * D * rnd + G * j
+                    if chain < num_chains:
+                        out.append((j, chain, u))
+            rnd += 1
+        return out
+
+    for G, D, U, num_chains in ((148, 3, 6, 632), (148, 1, 6, 72), (4, 2, 8, 11), (148, 8, 6, 3200), (5, 4, 3, 5)):
+        seen = {}
+        for c in range(G):
+            seq = walk(G, c, D, U, num_chains)
+            pos = {}
+            for k, (slot, chain, u) in enumerate(seq):
+                assert (chain, u) not in seen
+                seen[(chain, u)] = c
+                pos[(chain, u)] = k
+                if u > 0:
+                    assert pos[(chain, u - 1)] < k                       # producer first, same CTA
+            # the device picks the interleave depth so that rounds are equally deep (k_mlp_chain)
+        assert len(seen) == num_chains * U
+        per_cta = -(-num_chains // G)
+        rounds = -(-per_cta // 8)
+        assert 1 <= -(-per_cta // rounds) <= 8
+
+
+def test_row_tile_windows_partition_the_tiles():
+    """build_tile_map (csrc/gemm_tc.cuh): window w of W takes tiles [first + n w / W, first + n (w + 1) / W) of every
+    species -- a partition, whatever the counts."""
+    for counts in ((53, 27), (1, 0, 3), (7,), (400, 0, 0, 13, 2)):
+        for W in (1, 2, 3, 4, 16):
+            first = np.concatenate([[0], np.cumsum(counts)])
+            taken = []
+            for w in range(W):
+                for s, n in enumerate(counts):
+                    lo, hi = first[s] + n * w // W, first[s] + n * (w + 1) // W
+                    taken += list(range(lo, hi))
+            assert sorted(taken) == list(range(sum(counts)))
