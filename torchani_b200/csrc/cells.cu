@@ -1671,7 +1671,14 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
     }
     cfg.gridDim = dim3(cluster_ctas);
     attr[0].val.clusterDim.x = cluster_ctas;
-    cudaLaunchKernelEx(&cfg, k_prep_cluster, A);
+    if (cudaLaunchKernelEx(&cfg, k_prep_cluster, A) != cudaSuccess && cluster_ctas == 16) {
+      // the probe said yes but the launch was refused (partitioned device, ...): the portable size from now on
+      cudaGetLastError();
+      cluster_ctas = PREP_CLUSTER_CTAS;
+      cfg.gridDim = dim3(cluster_ctas);
+      attr[0].val.clusterDim.x = cluster_ctas;
+      cudaLaunchKernelEx(&cfg, k_prep_cluster, A);
+    }
   } else if (fused) {
     // one persistent launch, device-wide barriers between the phases; every block must be resident:
     // 2 blocks of 256 threads per SM at most (the kernel allows far more)
