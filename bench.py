@@ -98,14 +98,24 @@ def library_hash() -> str:
     return h.hexdigest()[:16]
 
 
+def library_build_id() -> str:
+    """Fingerprint of the sources + flags the library on disk was built from (torchani_b200.build.build_id)."""
+    from torchani_b200 import build as _build
+    return _build.build_id()
+
+
 def measured_traffic(config: str):
-    """dram bytes per launch from an `ncu --set full` capture OF THE LIBRARY BEING RUN: profiles/traffic.json maps
-    library hash -> config -> {mlp, aev_forward, aev_backward}; anything else is null (never a stale literal)."""
+    """dram bytes per launch from an `ncu --set full` capture OF THE LIBRARY BUILD BEING RUN: profiles/traffic.json maps
+    build id (fingerprint of sources + flags; nvcc output is not byte-reproducible) or library hash -> config ->
+    {mlp, aev_forward, aev_backward}; anything else is null (never a stale literal)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return {}
     try:
-        return json.load(open(path)).get(library_hash(), {}).get(config, {})
+        data = json.load(open(path))
+        bid = library_build_id()
+        entry = data.get(bid) if bid else None
+        return (entry or data.get(library_hash(), {})).get(config, {})
     except (OSError, ValueError):
         return {}
 
@@ -448,7 +458,7 @@ def main():
                             "calls": calc._calls} if args.skin > 0 else {})},
                 "gpu_launches": launches_per_step * args.steps,
                 "operand_format": {"parts": fmt.parts, "bytes_per_element": 2 * fmt.parts},
-                "library_sha256_16": library_hash(),
+                "library_sha256_16": library_hash(), "library_build_id": library_build_id(),
                 "stage_ms": stage, "roofline": roofline, "roofline_aev": roofline_aev, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:

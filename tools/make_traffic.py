@@ -6,7 +6,7 @@
     ncu -i gpurun_out/traffic_cap.ncu-rep --page raw --csv > gpurun_out/traffic_cap.csv
     python tools/make_traffic.py gpurun_out/traffic_cap.csv water10k
 
-Adds {library sha256[:16]: {config: {"mlp": bytes, "aev_forward": bytes, "aev_backward": bytes, "launches": {...}}}} --
+Adds {library sha256[:16] and build id (torchani_b200.build.build_id): {config: {"mlp": bytes, "aev_forward": bytes, "aev_backward": bytes, "launches": {...}}}} --
 dram__bytes_read.sum + dram__bytes_write.sum PER STEP'S LAUNCHES of each kernel family (one step = the last complete
 set in the capture; ncu flushes caches between kernels, so these are cold-cache figures).  bench.py reports them as
 roofline.traffic only when the hash of the library it runs matches."""
@@ -52,8 +52,12 @@ def main():
     dst = os.path.join(ROOT, "profiles", "traffic.json")
     data = json.load(open(dst)) if os.path.exists(dst) else {}
     data.setdefault(h, {})[config] = out
+    from torchani_b200 import build as _build
+    bid = _build.build_id()          # the same capture under the reproducible identity of the build
+    if bid:
+        data.setdefault(bid, {})[config] = out
     json.dump(data, open(dst, "w"), indent=1)
-    print(h, config, out)
+    print(h, bid, config, out)
 
 
 if __name__ == "__main__":

@@ -67,6 +67,17 @@ def _fingerprint(extra=()) -> str:
     return h.hexdigest()
 
 
+def build_id(variant: str = "") -> str:
+    """Identity of the library build on disk: the fingerprint of the sources + flags it was compiled from (nvcc output
+    is not byte-reproducible, the sources are), or "" when the library is missing or older than the sources."""
+    bdir = BUILD if not variant else BUILD + "_" + variant
+    stamp = os.path.join(bdir, "fingerprint.txt")
+    if not (os.path.exists(lib_path(variant)) and os.path.exists(stamp)):
+        return ""
+    fp = _fingerprint(VARIANTS[variant])
+    return fp[:16] if open(stamp).read() == fp else ""
+
+
 def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:
     extra = VARIANTS[variant]
     bdir = BUILD if not variant else BUILD + "_" + variant
