@@ -70,12 +70,17 @@ class HostCalculator:
         else:
             self.ws = self.engine.workspace(1, self.n)
         self.ws.species_i32.copy_(self.elem_idxs.reshape(-1))
-        self.h_coords = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
-        self.h_cell = torch.zeros(9, dtype=torch.float32).pin_memory()
-        self.h_grad = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
-        self.h_energy = torch.empty(1, dtype=torch.float64).pin_memory()
+        # pinned mirrors of the workspace's two transfer blocks (engine.Workspace.in_block / out_block): ONE H2D copy of
+        # [cell | coords] and ONE D2H copy of [energy | status | gradient] per step
+        self.h_in = torch.zeros(self.ws.in_block.numel(), dtype=torch.float32).pin_memory()
+        self.h_out = torch.zeros(self.ws.out_block.numel(), dtype=torch.uint8).pin_memory()
+        self.h_coords = self.h_in[16:].view(self.n, 3)
+        self.h_cell = self.h_in[:9]
+        off = self.ws._out_grad_off
+        self.h_grad = self.h_out[off:].view(torch.float32).view(self.n, 3)
+        self.h_energy = self.h_out[:8].view(torch.float64)
+        self.h_status = self.h_out[8:12].view(torch.int32)
         self.h_moved = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self.h_status = torch.zeros(1, dtype=torch.int32).pin_memory()
         self._have_grid = False       # a grid built with the skin exists and may be reused
         self.rebuilds = 0             # steps that built the grid
         self.redone = 0               # reuse steps that had to be recomputed (an atom left its skin/2 sphere)
@@ -83,8 +88,8 @@ class HostCalculator:
             raise ValueError("If pbc is not None, cell should be present")
         if cell is not None:
             self.set_cell(cell)
-        self.h2d_bytes = self.h_coords.numel() * 4 + (36 if pbc else 0)
-        self.d2h_bytes = self.h_grad.numel() * 4 + 8 + 4
+        self.h2d_bytes = self.h_in.numel() * 4
+        self.d2h_bytes = self.h_out.numel()
         self.graph_after = 3          # eager host-driven steps before copies + kernels are captured as one graph
         self._calls = 0
         self._graphs: tp.Dict[bool, torch.cuda.CUDAGraph] = {}   # reuse flag -> captured step
@@ -207,14 +212,10 @@ class HostCalculator:
     def _copies_in(self, reuse: bool = False) -> None:
         if reuse:
             self.ws.moved.zero_()
-        self.ws.coords.copy_(self.h_coords, non_blocking=True)
-        if self.pbc:
-            self.ws.cell.copy_(self.h_cell, non_blocking=True)
+        self.ws.in_block.copy_(self.h_in, non_blocking=True)
 
     def _copies_out(self, reuse: bool = False) -> None:
-        self.h_grad.copy_(self.ws.grad.view(self.n, 3), non_blocking=True)
-        self.h_energy.copy_(self.ws.energies, non_blocking=True)
-        self.h_status.copy_(self.ws.status, non_blocking=True)
+        self.h_out.copy_(self.ws.out_block, non_blocking=True)
         if reuse:
             self.h_moved.copy_(self.ws.moved, non_blocking=True)
 

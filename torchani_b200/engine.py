@@ -382,7 +382,14 @@ class Workspace:
         i32 = dict(dtype=torch.int32, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         self.grid = torch.zeros(C.sizeof(Grid) // 4, **i32)
-        self.status = torch.zeros(1, **i32)
+        # What a host-driven loop moves per step lives in TWO contiguous blocks, so that calculator.HostCalculator needs one
+        # H2D and one D2H copy (each copy is a node of the captured graph with its own DMA set-up latency):
+        #   in_block  f32: [cell 9 | pad to 16 | coords 3 n]
+        #   out_block u8 : [energies f64 x n_conf | status i32 | pad to 16 B | grad f32 x 3 n]
+        self.in_block = torch.zeros(16 + 3 * n, **f32)
+        self._out_grad_off = (8 * n_conf + 4 + 15) // 16 * 16
+        self.out_block = torch.zeros(self._out_grad_off + 12 * n, dtype=torch.uint8, device=device)
+        self.status = self.out_block[8 * n_conf: 8 * n_conf + 4].view(torch.int32)
         self.bin_start = torch.zeros(self.max_bins + 2, **i32)
         self.sorted_orig = torch.zeros(n, **i32)
         self.orig_to_sorted = torch.zeros(n, **i32)
@@ -414,12 +421,12 @@ class Workspace:
         self.e_member = torch.zeros(num_members, self.rows_cap, **f32)
         self.mlp_sync = torch.zeros(6 * (self.rows_cap // TILE) + 8, **i32)   # data-flow counters of ani_b200_mlp_step
         self.species_i32 = torch.zeros(n, **i32)
-        self.coords = torch.zeros(n, 3, **f32)
-        self.cell = torch.zeros(9, **f32)
-        self.grad = torch.zeros(n, 3, **f32)
+        self.coords = self.in_block[16:].view(n, 3)
+        self.cell = self.in_block[:9]
+        self.grad = self.out_block[self._out_grad_off:].view(torch.float32).view(n, 3)
         self.atomic = torch.zeros(n, **f32)
         self.member_atomic = torch.zeros(num_members, n, **f32)
-        self.energies = torch.zeros(n_conf, dtype=torch.float64, device=device)
+        self.energies = self.out_block[:8 * n_conf].view(torch.float64)
         # where the step's kernels ACCUMULATE forces / conformer energies: these buffers, or -- multi-GPU,
         # parallel.ShardedEngine.attach -- partial-sum buffers in peer-mapped memory whose reduction over the
         # ranks (reducer.launch, the last launch of the step) lands in `grad` / `energies`
