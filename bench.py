@@ -106,16 +106,19 @@ def library_build_id() -> str:
 
 def measured_traffic(config: str):
     """dram bytes per launch from an `ncu --set full` capture OF THE LIBRARY BUILD BEING RUN: profiles/traffic.json maps
-    build id (fingerprint of sources + flags; nvcc output is not byte-reproducible) or library hash -> config ->
-    {mlp, aev_forward, aev_backward}; anything else is null (never a stale literal)."""
+    kernel build id (fingerprint of the sources + flags the AEV / GEMM kernels are compiled from; nvcc output is not
+    byte-reproducible), build id or library hash -> config -> {mlp, aev_forward, aev_backward}; anything else is null
+    (never a stale literal)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return {}
     try:
         data = json.load(open(path))
-        bid = library_build_id()
-        entry = data.get(bid) if bid else None
-        return (entry or data.get(library_hash(), {})).get(config, {})
+        from torchani_b200 import build as _build
+        for key in (_build.build_id(kernels_only=True), library_build_id(), library_hash()):
+            if key and key in data:
+                return data[key].get(config, {})
+        return {}
     except (OSError, ValueError):
         return {}
 

@@ -53,9 +53,10 @@ def main():
     data = json.load(open(dst)) if os.path.exists(dst) else {}
     data.setdefault(h, {})[config] = out
     from torchani_b200 import build as _build
-    bid = _build.build_id()          # the same capture under the reproducible identity of the build
-    if bid:
-        data.setdefault(bid, {})[config] = out
+    bid = _build.build_id()          # the same capture under the reproducible identities of the build
+    for key in (bid, _build.build_id(kernels_only=True)):
+        if key:
+            data.setdefault(key, {})[config] = out
     json.dump(data, open(dst, "w"), indent=1)
     print(h, bid, config, out)
 

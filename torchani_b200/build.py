@@ -67,15 +67,34 @@ def _fingerprint(extra=()) -> str:
     return h.hexdigest()
 
 
-def build_id(variant: str = "") -> str:
+# translation units without any of the profiled kernels (preparation, communicator, ABI glue): a change there does not
+# touch the AEV / GEMM kernels whose measured DRAM traffic bench.py reports
+_NOT_PROFILED = ("cells.cu", "comm.cu", "api.cu")
+
+
+def build_id(variant: str = "", kernels_only: bool = False) -> str:
     """Identity of the library build on disk: the fingerprint of the sources + flags it was compiled from (nvcc output
-    is not byte-reproducible, the sources are), or "" when the library is missing or older than the sources."""
+    is not byte-reproducible, the sources are), or "" when the library is missing or older than the sources.
+    ``kernels_only``: the fingerprint of what the AEV and GEMM kernels are compiled from (``aev.cu``, ``mlp.cu``, the
+    headers, the flags) -- the key of profiles/traffic.json."""
     bdir = BUILD if not variant else BUILD + "_" + variant
     stamp = os.path.join(bdir, "fingerprint.txt")
     if not (os.path.exists(lib_path(variant)) and os.path.exists(stamp)):
         return ""
     fp = _fingerprint(VARIANTS[variant])
-    return fp[:16] if open(stamp).read() == fp else ""
+    if open(stamp).read() != fp:
+        return ""
+    if not kernels_only:
+        return fp[:16]
+    h = hashlib.sha256()
+    files = [f for f in _sources() if os.path.basename(f) not in _NOT_PROFILED]
+    files += [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    files.append(os.path.join(os.path.dirname(HERE), "include", "ani_b200.h"))
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(list(NVCC_FLAGS) + list(VARIANTS[variant])).encode())
+    return "k" + h.hexdigest()[:15]
 
 
 def build(force: bool = False, verbose: bool = False, variant: str = "") -> str:

@@ -1636,9 +1636,11 @@ extern "C" int ani_b200_prepare_step(const float* coords, const int32_t* species
   // periodic single systems of MD size: one thread-block cluster (ANI_B200_PREP_CLUSTER=0: never)
   const char* ce = getenv("ANI_B200_PREP_CLUSTER");
   const bool cluster_ok = (!ce || atoi(ce) != 0) && fused && A.inline_setup && mode == 0 &&
-                          n <= PREP_CLUSTER_MAX_ATOMS && A.ldx / 32 <= MAX_AEV_BLOCKS;
+                          n <= PREP_CLUSTER_MAX_ATOMS && max_bins - 1 <= PREP_CLUSTER_MAX_BINS && A.ldx / 32 <= MAX_AEV_BLOCKS;
   if (cluster_ok) {
-    const size_t dyn = sizeof(int32_t) * (size_t)(min(max_bins - 1, n + 1) + 2);
+    // (bin_start copy: nbins + 2 words, nbins <= max_bins - 1 -- NOT bounded by the number of atoms: a dilute system has
+    // more buckets than atoms)
+    const size_t dyn = sizeof(int32_t) * (size_t)(max_bins + 1);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(PREP_CLUSTER_THREADS);
     cfg.dynamicSmemBytes = dyn;
