@@ -292,8 +292,9 @@ def test_dataflow_mlp_launch_matches_the_chained_launches(engines, n_mol):
         eng.mlp_mode = saved
 
 
-@pytest.mark.parametrize("n_mol,shard", [(10, (0, 1)), (333, (0, 1)), (3333, (0, 1)), (3333, (1, 4)), (5000, (3, 8))])
-def test_cluster_preparation_matches_the_persistent_grid_kernel(n_mol, shard, monkeypatch):
+@pytest.mark.parametrize("n_mol,shard,dilate", [(10, (0, 1), 1.0), (333, (0, 1), 1.0), (3333, (0, 1), 1.0),
+                                                (3333, (1, 4), 1.0), (5000, (3, 8), 1.0), (20, (0, 1), 4.0)])
+def test_cluster_preparation_matches_the_persistent_grid_kernel(n_mol, shard, dilate, monkeypatch):
     """ani_b200_prepare_step has two single-launch forms: a persistent grid with device-wide barriers
     (k_prep_fused) and, for periodic single systems of MD size, one thread-block cluster (k_prep_cluster).
     Everything they hand to the rest of the step must be bit-identical: the bucket grid, the deterministic
@@ -306,6 +307,7 @@ def test_cluster_preparation_matches_the_persistent_grid_kernel(n_mol, shard, mo
     m = oracle_model("2x")
     nets = PackedNetworks([[wm[s] for s in m.symbols] for wm in m.weights], consts.out_dim, dev)
     _, idx, coords, cell, _ = synthetic.water_box(n_mol, seed=3)
+    coords, cell = coords * dilate, cell * dilate   # dilate > 1: a dilute system with more buckets than atoms
     idx = idx.clone()
     idx[0, 5] = -1      # one padding atom: the trash bucket is exercised too
     sp, co, ce = idx.to(dev), coords.to(dev), cell.to(dev)
